@@ -1,0 +1,133 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into or called from the product path.
+//
+// Harness `main` for the UNMODIFIED reference sources (/root/reference/src/cpp/*.cpp, compiled where
+// they lie by oracle/Makefile into oracle/_ref/).  It drives the same sequence as
+// IS3D::run_particlization(1) (reference src/cpp/iS3D.cpp:81-286) from the current working directory
+// (which must hold iS3D_parameters.dat, input/surface.dat, PDG/, tables/, deltaf_coefficients/ and the
+// results/ tree of clear_results.sh) and additionally dumps, in binary, the in-memory results that the
+// reference's text writers truncate to 9 digits:
+//   ref_dump/spectra.bin      EmissionFunctionArray::dN_pTdpTdphidy (EmissionFunction.h:114)
+//   ref_dump/particles.bin    particle_event_list (EmissionFunction.h:121)
+//   ref_dump/species.bin      per-PDG-entry (mcid, mass, gspin, baryon, sign, neq, dn_bulk, dn_diff)
+//   ref_dump/jonah.bin        PTB tables bulkPi/P, lambda^2, z (DeltafData.h:72-79), include_baryon = 0 only
+//   ref_dump/timing.txt       seconds spent inside calculate_spectra (same region as the reference's
+//                             own "Spectra calculation took" print, EmissionFunction.cpp:1375-1385)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <chrono>
+#include <sys/stat.h>
+
+#define private public
+#include "iS3D.h"
+#include "readindata.h"
+#include "EmissionFunction.h"
+#include "ParameterReader.h"
+#include "DeltafData.h"
+#include "Table.h"
+#undef private
+
+static void wr(FILE *f, const void *p, size_t n) { if (fwrite(p, 1, n, f) != n) { perror("fwrite"); exit(1); } }
+
+int main(int argc, char **argv)
+{
+  bool quiet_exit = true;   // skip destructors that segfault for include_baryon = 1 (DeltafData.cpp:49-63)
+  (void)argc; (void)argv;
+  mkdir("ref_dump", 0755);
+
+  ParameterReader *paraRdr = new ParameterReader;
+  paraRdr->readFromFile("iS3D_parameters.dat");
+  int include_baryon = paraRdr->getVal("include_baryon");
+  int operation = paraRdr->getVal("operation");
+
+  FO_data_reader freeze_out_data(paraRdr, "input");
+  long FO_length = freeze_out_data.get_number_cells();
+  FO_surf *surf_ptr = new FO_surf[FO_length];
+  freeze_out_data.read_freezeout_surface(surf_ptr);
+  printf("Number of freezeout cells = %ld\n", FO_length);
+
+  particle_info *particle_data = new particle_info[Maxparticle];
+  PDG_Data pdg(paraRdr);
+  int Nparticle = pdg.read_resonances(particle_data);
+
+  Table chosen_particles("PDG/chosen_particles.dat");
+
+  Deltaf_Data *df_data = new Deltaf_Data(paraRdr);
+  df_data->load_df_coefficient_data();
+  if(!include_baryon)
+  {
+    df_data->construct_cubic_splines();
+    df_data->compute_jonah_coefficients(particle_data, Nparticle);
+  }
+  df_data->compute_particle_densities(particle_data, Nparticle);
+  df_data->test_df_coefficients(-0.1);
+
+  {
+    FILE *f = fopen("ref_dump/species.bin", "wb");
+    long n = Nparticle; wr(f, &n, sizeof(long));
+    for(int i = 0; i < Nparticle; i++)
+    {
+      double rec[8] = {(double)particle_data[i].mc_id, particle_data[i].mass, (double)particle_data[i].gspin,
+                       (double)particle_data[i].baryon, (double)particle_data[i].sign,
+                       particle_data[i].equilibrium_density, particle_data[i].bulk_density, particle_data[i].diff_density};
+      wr(f, rec, sizeof(rec));
+    }
+    fclose(f);
+    if(!include_baryon)
+    {
+      f = fopen("ref_dump/jonah.bin", "wb");
+      long m = df_data->jonah_points; wr(f, &m, sizeof(long));
+      wr(f, df_data->bulkPi_over_Peq_array, m * sizeof(double));
+      wr(f, df_data->lambda_squared_array, m * sizeof(double));
+      wr(f, df_data->z_array, m * sizeof(double));
+      wr(f, &df_data->bulkPi_over_Peq_max, sizeof(double));
+      fclose(f);
+    }
+  }
+
+  Table pT_tab("tables/momentum/pT_table.dat");
+  Table phi_tab("tables/momentum/phi_table.dat");
+  Table y_tab("tables/momentum/y_table.dat");
+  Table eta_tab("tables/spacetime_rapidity/eta_table.dat");
+
+  EmissionFunctionArray efa(paraRdr, &chosen_particles, &pT_tab, &phi_tab, &y_tab, &eta_tab, particle_data, Nparticle, surf_ptr, FO_length, df_data);
+
+  std::vector<std::vector<Sampled_Particle>> events;
+  auto t0 = std::chrono::steady_clock::now();
+  efa.calculate_spectra(events);
+  auto t1 = std::chrono::steady_clock::now();
+  double secs = std::chrono::duration<double>(t1 - t0).count();
+  {
+    FILE *f = fopen("ref_dump/timing.txt", "w");
+    fprintf(f, "%.9e\n", secs);
+    fclose(f);
+  }
+
+  if(operation == 1)
+  {
+    FILE *f = fopen("ref_dump/spectra.bin", "wb");
+    long dims[4] = {(long)efa.number_of_chosen_particles, efa.pT_tab_length, efa.phi_tab_length, efa.y_tab_length};
+    wr(f, dims, sizeof(dims));
+    wr(f, efa.dN_pTdpTdphidy, sizeof(double) * dims[0] * dims[1] * dims[2] * dims[3]);
+    fclose(f);
+  }
+  if(operation == 2)
+  {
+    FILE *f = fopen("ref_dump/particles.bin", "wb");
+    long nev = (long)events.size(); wr(f, &nev, sizeof(long));
+    for(long e = 0; e < nev; e++)
+    {
+      long np = (long)events[e].size(); wr(f, &np, sizeof(long));
+      for(long i = 0; i < np; i++)
+      {
+        const Sampled_Particle &p = events[e][i];
+        double rec[13] = {(double)p.chosen_index, (double)p.mcID, p.mass, p.tau, p.x, p.y, p.eta, p.t, p.z, p.E, p.px, p.py, p.pz};
+        wr(f, rec, sizeof(rec));
+      }
+    }
+    fclose(f);
+  }
+  fflush(stdout);
+  if(quiet_exit) _Exit(0);
+  return 0;
+}

@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE: run the compiled reference (oracle/_ref/is3d_ref, built by oracle/Makefile from the
+unmodified sources) in a scratch working directory and read back its binary dumps."""
+from __future__ import annotations
+
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+from is3d_b200 import synthetic, workdir
+
+REPO = workdir.REPO
+REF_BIN = os.path.join(REPO, "oracle", "_ref", "is3d_ref")
+REF_BIN_OMP = os.path.join(REPO, "oracle", "_ref", "is3d_ref_omp")
+
+
+def have_ref() -> bool:
+    return os.access(REF_BIN, os.X_OK)
+
+
+def run_ref(root: str, surface: dict, params: dict, chosen: str = "pikp", baryon: bool | None = None,
+            omp_threads: int = 0, timeout: float = 3600.0, **tables) -> dict:
+    if baryon is None:
+        baryon = bool(int(params.get("include_baryon", 0)))
+    workdir.make_workdir(root, params, chosen=chosen, **tables)
+    synthetic.write_mode1(os.path.join(root, "input", "surface.dat"), surface, baryon=baryon)
+    env = dict(os.environ)
+    exe = REF_BIN
+    if omp_threads:
+        exe = REF_BIN_OMP
+        env["OMP_NUM_THREADS"] = str(omp_threads)
+    with open(os.path.join(root, "ref_stdout.log"), "w") as log:
+        r = subprocess.run([exe], cwd=root, stdout=log, stderr=subprocess.STDOUT, env=env, timeout=timeout)
+    if r.returncode != 0:
+        tail = open(os.path.join(root, "ref_stdout.log")).read()[-2000:]
+        raise RuntimeError(f"reference exited {r.returncode}:\n{tail}")
+    return read_dumps(root)
+
+
+def read_dumps(root: str) -> dict:
+    out = {}
+    d = os.path.join(root, "ref_dump")
+    p = os.path.join(d, "spectra.bin")
+    if os.path.exists(p):
+        raw = open(p, "rb").read()
+        dims = struct.unpack("4l", raw[:32])
+        out["spectra"] = np.frombuffer(raw[32:], dtype=np.float64).reshape(dims).copy()
+    p = os.path.join(d, "species.bin")
+    if os.path.exists(p):
+        raw = open(p, "rb").read()
+        n = struct.unpack("l", raw[:8])[0]
+        out["species"] = np.frombuffer(raw[8:], dtype=np.float64).reshape(n, 8).copy()
+    p = os.path.join(d, "jonah.bin")
+    if os.path.exists(p):
+        raw = open(p, "rb").read()
+        m = struct.unpack("l", raw[:8])[0]
+        a = np.frombuffer(raw[8:], dtype=np.float64)
+        out["jonah"] = {"bulkPi_over_P": a[:m].copy(), "lambda2": a[m:2 * m].copy(), "z": a[2 * m:3 * m].copy(),
+                        "max": float(a[3 * m])}
+    p = os.path.join(d, "particles.bin")
+    if os.path.exists(p):
+        raw = open(p, "rb").read()
+        nev = struct.unpack("l", raw[:8])[0]
+        off = 8
+        events = []
+        for _ in range(nev):
+            npart = struct.unpack("l", raw[off:off + 8])[0]
+            off += 8
+            events.append(np.frombuffer(raw[off:off + npart * 104], dtype=np.float64).reshape(npart, 13).copy())
+            off += npart * 104
+        out["events"] = events
+    p = os.path.join(d, "timing.txt")
+    if os.path.exists(p):
+        out["seconds"] = float(open(p).read().split()[0])
+    return out
