@@ -1,0 +1,210 @@
+/*
+ * is3d_b200.h -- C ABI of the B200-native Cooper-Frye particlization hot path.
+ *
+ * Drop-in boundary: the reference has no FFI; the seam is the C++ member-function boundary
+ * between EmissionFunctionArray::calculate_spectra and its eight compute members, taken AFTER the AoS->SoA
+ * unpack of the freezeout surface (reference src/cpp/EmissionFunction.cpp:1050-1161, dispatch :1164-1277).
+ * Every entry point below names the reference interface it replaces.  Plain C: pointers and sizes only, no
+ * C++/torch types, no exceptions.  All floating point is FP64; all arrays are caller-owned unless stated.
+ *
+ * Conventions
+ *   - every function returns an is3d_status (0 = ok); is3d_last_error() gives the message.  The reference's
+ *     convention is printf + exit(-1) (e.g. EmissionFunction.cpp:156-157, DeltafData.cpp:430-434) or a GSL
+ *     abort; the host layer (is3d_host.h) turns a non-zero status back into that behaviour.
+ *   - one context per host thread and per GPU; calls are synchronous unless suffixed _async.
+ *   - there is NO CPU fallback: if no sm_100-class device is usable, is3d_create fails.
+ */
+#ifndef IS3D_B200_H
+#define IS3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct is3d_ctx is3d_ctx;
+
+typedef enum {
+  IS3D_OK = 0,
+  IS3D_ERR_INVALID = 1,      /* bad argument / call order */
+  IS3D_ERR_CUDA = 2,         /* CUDA runtime failure (message holds cudaGetErrorString) */
+  IS3D_ERR_TABLE_RANGE = 3,  /* a cell's (T, muB, Pi/P) is outside the df coefficient tables: the reference aborts
+                                (GSL domain error, DeltafData.cpp:338-377) or exit(-1)s (DeltafData.cpp:430-434) */
+  IS3D_ERR_UNSUPPORTED = 4,  /* combination the reference itself rejects (e.g. dN/dX with df_mode 5,
+                                EmissionFunction.cpp:1184-1189; PTB with include_baryon, DeltafData.cpp:480-484) */
+  IS3D_ERR_NO_DEVICE = 5
+} is3d_status;
+
+/* Number of structure-of-arrays surface columns and their order (is3d_set_surface).  This is the column set the
+ * reference unpacks in EmissionFunction.cpp:1050-1092 (tau x y eta | dat dax day dan | ux uy un | E T P |
+ * pixx pixy pixn piyy piyn | bulkPi | muB nB Vx Vy Vn), in physical units (GeV, fm) as left by the readers. */
+#define IS3D_SURFACE_COLUMNS 25
+enum {
+  IS3D_COL_TAU = 0, IS3D_COL_X, IS3D_COL_Y, IS3D_COL_ETA,
+  IS3D_COL_DAT, IS3D_COL_DAX, IS3D_COL_DAY, IS3D_COL_DAN,
+  IS3D_COL_UX, IS3D_COL_UY, IS3D_COL_UN,
+  IS3D_COL_E, IS3D_COL_T, IS3D_COL_P,
+  IS3D_COL_PIXX, IS3D_COL_PIXY, IS3D_COL_PIXN, IS3D_COL_PIYY, IS3D_COL_PIYN,
+  IS3D_COL_BULKPI,
+  IS3D_COL_MUB, IS3D_COL_NB, IS3D_COL_VX, IS3D_COL_VY, IS3D_COL_VN
+};
+
+/* Run-time switches: the members of EmissionFunctionArray that the compute paths read
+ * (EmissionFunction.h:34-93, filled from iS3D_parameters.dat in EmissionFunction.cpp:139-247). */
+typedef struct {
+  int operation;                 /* 0 dN/dX, 1 continuous spectra, 2 sampler */
+  int dimension;                 /* 2 = boost-invariant 2+1d, 3 = 3+1d */
+  int df_mode;                   /* 1 Grad 14-moment, 2 RTA Chapman-Enskog, 3 PTM, 4 PTB, 5 PTMA */
+  int include_baryon;
+  int include_bulk_deltaf;
+  int include_shear_deltaf;
+  int include_baryondiff_deltaf;
+  int regulate_deltaf;
+  int outflow;
+  double deta_min;
+  double mass_pion0;
+  int fast;                      /* sampler: species densities at (T_avg, muB_avg) */
+  double y_cut;
+  int64_t sampler_seed;          /* must be >= 0 here; the host layer resolves "< 0 = clock" */
+  int test_sampler;
+  /* histogram grids for the sampler self-test and dN/dX (EmissionFunction.h:69-93) */
+  double pT_min, pT_max;  int pT_bins;
+  int y_bins;
+  int phip_bins;
+  double eta_cut;         int eta_bins;
+  double tau_min, tau_max; int tau_bins;
+  double r_min, r_max;     int r_bins;
+  /* device selection and library-only knobs (no reference counterpart) */
+  int device;                    /* CUDA ordinal */
+  int famod_chain;               /* df_mode 5 initial guess policy: 1 = reference-faithful serial chain (previous
+                                    cell's solution, MomentumSpectra.cpp:1308-1364), 0 = chain-free (T,1,1) */
+  int dndx_bug_compat;           /* 1 = reproduce the reference's partial memset (SpacetimeDistribution.cpp:166-168):
+                                    histograms accumulate over species above bin CORES*bins/8 */
+} is3d_params;
+
+/* Counters the reference prints (MomentumSpectra.cpp:1039-1040, :1674-1679; ParticleSampler.cpp:1133). */
+typedef struct {
+  int64_t cells_total;
+  int64_t cells_skipped;         /* u.dsigma <= 0 */
+  int64_t cells_breakdown;       /* feqmod / famod breakdown */
+  int64_t cells_pl_negative;
+  int64_t reconstruction_failures;
+  int64_t newton_iterations;
+  int64_t cells_out_of_table;
+  int64_t sampler_proposals;
+  int64_t sampler_accepted;
+  double  tau_breakdown;
+  double  tau_pl_negative;
+  double  kernel_ms;             /* device time of the dominant kernel(s) of the last call (CUDA events) */
+  int64_t kernel_launches;       /* kernels launched by the last call */
+} is3d_stats;
+
+/* One sampled hadron: the reference's Sampled_Particle (SampledParticle.h:32-54), same fields. */
+typedef struct {
+  int32_t chosen_index;
+  int32_t mcid;
+  int32_t event;
+  int32_t pad_;
+  double mass;
+  double tau, x, y, eta;
+  double t, z;
+  double E, px, py, pz;
+} is3d_particle;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+void        is3d_default_params(is3d_params *p);
+is3d_status is3d_create(const is3d_params *p, is3d_ctx **out);
+void        is3d_destroy(is3d_ctx *ctx);
+const char *is3d_last_error(const is3d_ctx *ctx);          /* ctx may be NULL: last create error */
+const char *is3d_version(void);
+
+/* ---- static inputs (reference: arrays built in EmissionFunction.cpp:998-1046) --------------------------------- */
+/* chosen species: Mass/Sign/Degeneracy/Baryon/MCID and the fast-mode densities (EmissionFunction.cpp:998-1021) */
+is3d_status is3d_set_species(is3d_ctx *ctx, int n, const double *mass, const double *sign, const double *degeneracy,
+                             const double *baryon, const int *mcid, const double *equilibrium_density,
+                             const double *bulk_density, const double *diffusion_density);
+/* whole PDG table for the PTMA reconstruction (EmissionFunction.cpp:1025-1036; first min(320,n) used) */
+is3d_status is3d_set_pdg(is3d_ctx *ctx, int n, const double *mass, const double *sign, const double *degeneracy,
+                         const double *baryon);
+/* momentum / rapidity tables: column 1 = node, column 2 = weight of tables/momentum/{pT,phi,y}_table.dat and
+ * tables/spacetime_rapidity/eta_table.dat (iS3D.cpp:254-257).  Lengths are the FILE lengths; the library applies
+ * the reference's dimension rule itself (2+1d: y = {0}; 3+1d: eta = cell eta, EmissionFunction.cpp:146-153). */
+is3d_status is3d_set_momentum_tables(is3d_ctx *ctx, int npT, const double *pT, const double *pT_weight,
+                                     int nphi, const double *phi, const double *phi_weight,
+                                     int ny, const double *y, const double *y_weight,
+                                     int neta, const double *eta, const double *eta_weight);
+/* Gauss-Laguerre (n_alpha x n_points, row-major; tables/gauss/gla_roots_weights.txt) and Gauss-Legendre tables
+ * (readindata.cpp:26-92) */
+is3d_status is3d_set_gauss_tables(is3d_ctx *ctx, int n_alpha, int n_points, const double *gla_root,
+                                  const double *gla_weight, int n_legendre, const double *legendre_root,
+                                  const double *legendre_weight);
+/* surface-averaged thermodynamics (Plasma, readindata.cpp:104-119) */
+is3d_status is3d_set_thermo_averages(is3d_ctx *ctx, double T, double E, double P, double muB, double nB);
+/* df coefficient tables, each n_muB x n_T row-major (DeltafData.cpp:65-217).  For include_baryon = 0 pass
+ * n_muB = 1 (the reader's rule, DeltafData.cpp:134); the library builds the natural cubic splines in T
+ * (DeltafData.cpp:298-321) itself. */
+is3d_status is3d_set_df_tables(is3d_ctx *ctx, int n_T, int n_muB, const double *T, const double *muB,
+                               const double *c0, const double *c1, const double *c2, const double *c3,
+                               const double *c4, const double *F, const double *G, const double *betabulk,
+                               const double *betaV, const double *betapi);
+/* PTB tables lambda^2(Pi/P), z(Pi/P) (DeltafData.cpp:220-295); n = 301 in the reference */
+is3d_status is3d_set_ptb_tables(is3d_ctx *ctx, int n, const double *bulkPi_over_P, const double *lambda_squared,
+                                const double *z, double bulkPi_over_P_max);
+
+/* ---- surface -------------------------------------------------------------------------------------------- */
+/* cols[k] = host pointer to n doubles (k as IS3D_COL_*); copied to HBM as structure-of-arrays.  Baryon columns
+ * may be NULL when include_baryon = 0.  global_offset = index of cols[.][0] in the whole surface when the caller
+ * shards cells across GPUs (keys the sampler's counter-based RNG so results do not depend on the sharding). */
+is3d_status is3d_set_surface(is3d_ctx *ctx, int64_t n, const double *const cols[IS3D_SURFACE_COLUMNS],
+                             int64_t global_offset);
+/* same, but cols[k] are DEVICE pointers that stay owned by the caller and must outlive the compute calls */
+is3d_status is3d_set_surface_device(is3d_ctx *ctx, int64_t n, const double *const cols[IS3D_SURFACE_COLUMNS],
+                                    int64_t global_offset);
+
+/* ---- compute (reference: the eight compute members, EmissionFunction.h:147-179) ----------------------------- */
+/* number of doubles is3d_spectra writes: Ns * NpT * Nphi * Ny, index iy + Ny*(iphi + Nphi*(ipT + NpT*is))
+ * (MomentumSpectra.cpp:252-295) */
+int64_t     is3d_spectra_size(const is3d_ctx *ctx);
+/* calculate_dN_pTdpTdphidy / _feqmod / _famod (EmissionFunction.h:147-152): out is a HOST buffer */
+is3d_status is3d_spectra(is3d_ctx *ctx, double *out, is3d_stats *stats);
+/* same, result left in a caller-owned DEVICE buffer (for a cross-GPU reduction by the caller) */
+is3d_status is3d_spectra_device(is3d_ctx *ctx, double *out_device, is3d_stats *stats);
+
+/* calculate_dN_dX / calculate_dN_dX_feqmod (EmissionFunction.h:155-161): three histograms per species, each
+ * Ns x bins row-major, UNnormalised sums of dN_dy_cell exactly as accumulated in SpacetimeDistribution.cpp:413-440
+ * (the writers' normalisation lives in the host layer). */
+is3d_status is3d_dndx(is3d_ctx *ctx, double *tau_hist, double *r_hist, double *phi_hist, is3d_stats *stats);
+is3d_status is3d_dndx_device(is3d_ctx *ctx, double *tau_hist_dev, double *r_hist_dev, double *phi_hist_dev,
+                             is3d_stats *stats);
+
+/* calculate_total_yield (EmissionFunction.h:172) */
+is3d_status is3d_total_yield(is3d_ctx *ctx, double *ntotal, is3d_stats *stats);
+/* per-cell mean yields of the sampler: dn_tot[cell] (after the 2*y_max*ds_max factor, ParticleSampler.cpp:915)
+ * and, if dn_list != NULL, dn_list[cell*Ns + s] (ParticleSampler.cpp:876-911).  Host buffers. */
+is3d_status is3d_cell_yields(is3d_ctx *ctx, double *dn_tot, double *dn_list, is3d_stats *stats);
+
+/* sample_dN_pTdpTdphidy / _famod (EmissionFunction.h:175-179).  Particles of all events are returned in one
+ * library-owned host array (event index in each record, grouped by event); counts[e] = hadrons in event e
+ * (caller-owned, nevents entries).  Release with is3d_free_particles. */
+is3d_status is3d_sample(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total,
+                        int64_t *counts, is3d_stats *stats);
+void        is3d_free_particles(is3d_particle *particles);
+/* sampler self-test histograms (BinSampledParticle.cpp): filled on the device during is3d_sample when
+ * test_sampler = 1.  Each output is Ns x bins row-major (vn: 7 x Ns x pT_bins); pass NULL to skip one. */
+is3d_status is3d_sample_histograms(is3d_ctx *ctx, double *dN_dy, double *dN_deta, double *dN_dphipdy,
+                                   double *dN_2pipTdpTdy, double *pT_count, double *vn_real, double *vn_imag,
+                                   double *dN_taudtaudy, double *dN_twopirdrdy, double *dN_dphisdy);
+
+/* ---- measurement helpers (no reference counterpart) ---------------------------------------------------------- */
+/* sustained DFMA throughput of this GPU in TFLOP/s (2 flops per DFMA), measured with a register-resident
+ * micro-kernel and CUDA events: the roofline denominator of the FP64-bound kernels. */
+is3d_status is3d_measure_fp64_peak(is3d_ctx *ctx, double *tflops);
+/* the CUDA stream all kernels of this context are launched on (as a void* cudaStream_t) */
+void       *is3d_stream(is3d_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IS3D_B200_H */

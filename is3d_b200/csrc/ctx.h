@@ -1,0 +1,139 @@
+// Internal context of the C ABI (include/is3d_b200.h).  Not part of the public interface.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/is3d_b200.h"
+#include "cellmath.cuh"
+#include "dftables.cuh"
+
+#define IS3D_CUDA_TRY(ctx, expr)                                                                          \
+  do {                                                                                                    \
+    cudaError_t err__ = (expr);                                                                           \
+    if (err__ != cudaSuccess) {                                                                           \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(err__) + " (" + __FILE__ + ":" +    \
+                       std::to_string(__LINE__) + ")");                                                   \
+      return IS3D_ERR_CUDA;                                                                               \
+    }                                                                                                     \
+  } while (0)
+
+#define IS3D_TRY(expr)                      \
+  do {                                      \
+    is3d_status st__ = (expr);              \
+    if (st__ != IS3D_OK) return st__;       \
+  } while (0)
+
+struct is3d_ctx {
+  is3d_params prm;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+
+  // chosen species (host copies + device arrays)
+  int ns = 0;
+  std::vector<double> h_mass, h_sign, h_deg, h_baryon, h_neq, h_dnbulk, h_dndiff;
+  std::vector<int> h_mcid;
+  double *d_mass = nullptr, *d_sign = nullptr, *d_deg = nullptr, *d_baryon = nullptr;
+  double *d_neq = nullptr, *d_dnbulk = nullptr, *d_dndiff = nullptr;
+  int *d_mcid = nullptr;
+
+  // PDG table (PTMA reconstruction)
+  int npdg = 0;
+  std::vector<double> h_pdg_mass, h_pdg_sign, h_pdg_deg, h_pdg_baryon;
+  double *d_pdg_mass = nullptr, *d_pdg_sign = nullptr, *d_pdg_deg = nullptr, *d_pdg_baryon = nullptr;
+
+  // momentum tables as read from file (nodes, weights)
+  std::vector<double> pT, pTw, phi, phiw, y, yw, eta, etaw;
+  bool have_momentum = false;
+  // effective grid after the dimension rule (EmissionFunction.cpp:146-153)
+  int NpT = 0, Nphi = 0, Ny = 0, Neta = 0;
+  std::vector<double> yv, etav, etawv;     // effective y nodes / eta nodes+weights
+  double *d_pT = nullptr, *d_pTw = nullptr, *d_cosphi = nullptr, *d_sinphi = nullptr, *d_phiw = nullptr;
+  double *d_y = nullptr, *d_yw = nullptr, *d_eta = nullptr, *d_etaw = nullptr;
+
+  // Gauss-Laguerre / Legendre
+  int gla_alpha = 0, gla_pts = 0, leg_pts = 0;
+  std::vector<double> h_gla_root, h_gla_weight, h_leg_root, h_leg_weight;
+  double *d_gla_root = nullptr, *d_gla_weight = nullptr, *d_leg_root = nullptr, *d_leg_weight = nullptr;
+
+  // thermodynamic averages
+  bool have_avg = false;
+  double T_avg = 0, E_avg = 0, P_avg = 0, muB_avg = 0, nB_avg = 0;
+
+  // df tables (device pointers inside) + host copies for fast-mode coefficients
+  is3d::DfTables tb;
+  bool have_df = false, have_ptb = false;
+  std::vector<double> h_T, h_muB, h_tab[10], h_spc[5];
+  std::vector<double> h_ptb_x, h_ptb_l2, h_ptb_z, h_ptb_l2c, h_ptb_zc;
+
+  // surface
+  is3d::SurfaceView surf{};
+  bool have_surface = false;
+  bool surface_owned = false;
+  int64_t global_offset = 0;
+  double *d_surface_block = nullptr;       // one allocation holding all owned columns
+
+  // sampler histograms (device)
+  std::map<std::string, double *> hist;
+
+  // every device allocation made by this context
+  std::vector<void *> owned;
+  // grow-only named scratch buffers
+  std::map<std::string, std::pair<void *, size_t>> scratch;
+
+  void set_error(const std::string &m) { err = m; }
+
+  is3d_status dev_alloc(void **p, size_t bytes)
+  {
+    *p = nullptr;
+    if (bytes == 0) bytes = 8;
+    IS3D_CUDA_TRY(this, cudaMalloc(p, bytes));
+    owned.push_back(*p);
+    return IS3D_OK;
+  }
+  void dev_free(void *p)
+  {
+    if (!p) return;
+    for (size_t i = 0; i < owned.size(); i++)
+      if (owned[i] == p) { owned.erase(owned.begin() + i); break; }
+    cudaFree(p);
+  }
+  template <class T>
+  is3d_status upload(T **dst, const T *src, size_t n)
+  {
+    if (*dst) { dev_free(*dst); *dst = nullptr; }
+    IS3D_TRY(dev_alloc((void **)dst, n * sizeof(T)));
+    if (n) IS3D_CUDA_TRY(this, cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+    IS3D_CUDA_TRY(this, cudaStreamSynchronize(stream));
+    return IS3D_OK;
+  }
+  is3d_status get_scratch(const char *name, size_t bytes, void **p)
+  {
+    auto it = scratch.find(name);
+    if (it != scratch.end() && it->second.second >= bytes) { *p = it->second.first; return IS3D_OK; }
+    if (it != scratch.end()) { dev_free(it->second.first); scratch.erase(it); }
+    IS3D_TRY(dev_alloc(p, bytes));
+    scratch[name] = {*p, bytes};
+    return IS3D_OK;
+  }
+};
+
+namespace is3d {
+
+// compute paths (one translation unit each)
+is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);        // df_mode 1,2
+is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);    // df_mode 3,4
+is3d_status run_spectra_famod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);     // df_mode 5
+is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_dev, is3d_stats *stats);
+is3d_status run_total_yield(is3d_ctx *ctx, double *ntotal, is3d_stats *stats);
+is3d_status run_cell_yields(is3d_ctx *ctx, double *dn_tot_host, double *dn_list_host, is3d_stats *stats);
+is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts,
+                        is3d_stats *stats);
+is3d_status measure_fp64_peak(is3d_ctx *ctx, double *tflops);
+
+}  // namespace is3d

@@ -1,0 +1,287 @@
+// K1: continuous Cooper-Frye spectra for df_mode 1 (Grad 14-moment) and 2 (RTA Chapman-Enskog) on sm_100a.
+// Replaces EmissionFunctionArray::calculate_dN_pTdpTdphidy (reference src/cpp/MomentumSpectra.cpp:32-415).
+//
+// Layout / schedule
+//   1. df_setup_kernel: one thread per cell; reads the 20-25 SoA surface columns (coalesced), evaluates the df
+//      coefficients and writes a 30-double "cell pack" as SoA into HBM (240 B / cell).
+//   2. df_spectra_kernel: output-stationary.  blockIdx.x = slice of (species, pT) bins, blockIdx.y = (iy, iphi),
+//      blockIdx.z = contiguous chunk of cells.  A block streams its chunk in tiles of 256 cells: each thread turns
+//      one cell pack into the 16-double item constants for the block's (y, phi) -- one sinh per cell per tile --
+//      with invalid (u.dsigma <= 0) cells compacted away by ballot/prefix; then every thread marches over the
+//      tile, reading the warp-uniform item with broadcast LDS.128 and updating its R register accumulators.
+//      FP64-pipe bound: HBM traffic is 240 B per cell per block against >= 768 * ~40 DFMA per cell per block.
+//   3. reduce_partials_kernel: deterministic sum over the cell chunks.
+#include "ctx.h"
+#include "spectra_df.cuh"
+
+namespace is3d {
+
+namespace {
+
+constexpr int kTile = 256;      // cells per shared-memory tile = threads per block
+constexpr int kThreads = 256;
+
+__global__ void df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, DfTables tb, DfFlags fl,
+                                double *__restrict__ pack, int64_t stride, unsigned long long *counters)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Cell c = load_cell(surf, begin + i, fl.include_baryon != 0);
+  double p[DP_SIZE];
+  int st = df_setup_cell(c, tb, fl, p);
+#pragma unroll
+  for (int k = 0; k < DP_SIZE; k++) pack[k * stride + i] = p[k];
+  if (st == CELL_SKIPPED) atomicAdd(&counters[0], 1ull);
+  if (st == CELL_OUT_OF_TABLE) atomicAdd(&counters[1], 1ull);
+}
+
+struct DfGrid {
+  const double *mT, *pT, *m2, *baryon, *sign, *deg;   // per (species, pT) bin, [nbins]
+  int nbins;
+  int Ny, Nphi, Neta, dimension;
+  const double *yv, *cosphi, *sinphi, *etav, *etaw;
+};
+
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, int R>
+__global__ void __launch_bounds__(kThreads, 2)
+df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk, DfGrid g,
+                  double *__restrict__ partial, int64_t total)
+{
+  __shared__ DfItem items[kTile];
+  __shared__ int warp_count[kThreads / 32];
+
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;
+  const double yval = g.yv[iy], cphi = g.cosphi[iphi], sphi = g.sinphi[iphi];
+
+  DfBin bin[R];
+  double acc[R];
+  int jbin[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    int j = blockIdx.x * (kThreads * R) + r * kThreads + t;
+    jbin[r] = j;
+    int jj = j < g.nbins ? j : g.nbins - 1;
+    double mT = g.mT[jj], pT = g.pT[jj];
+    bin[r].mT = mT; bin[r].pT = pT; bin[r].mT2 = mT * mT; bin[r].mTpT = mT * pT; bin[r].pT2 = pT * pT;
+    bin[r].m2 = g.m2[jj]; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
+    acc[r] = 0.0;
+  }
+
+  const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
+  int64_t chunk_end = chunk_begin + cells_per_chunk;
+  if (chunk_end > ncells) chunk_end = ncells;
+
+  for (int64_t tile = chunk_begin; tile < chunk_end; tile += kTile) {
+    const int64_t cell = tile + t;
+    const bool valid = (cell < chunk_end) && (pack[DP_VALID * stride + cell] != 0.0);
+    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
+    for (int ie = 0; ie < g.Neta; ie++) {
+      __syncthreads();                       // previous tile fully consumed
+      if (lane == 0) warp_count[warp] = __popc(ballot);
+      __syncthreads();
+      int base = 0, n_items = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; w++) {
+        int c = warp_count[w];
+        if (w < warp) base += c;
+        n_items += c;
+      }
+      if (valid) {
+        double eta, w;
+        if (g.dimension == 3) { eta = pack[DP_ETA * stride + cell]; w = 1.0; }
+        else { eta = g.etav[ie]; w = g.etaw[ie]; }
+        double sh = sinh(yval - eta);
+        double ch = sqrt(1.0 + sh * sh);     // the reference's cosh (MomentumSpectra.cpp:307-308)
+        auto pk = [&](int k) { return pack[k * stride + cell]; };
+        items[base + __popc(ballot & ((1u << lane) - 1u))] = df_make_item(pk, sh, ch, cphi, sphi, w);
+      }
+      __syncthreads();
+#pragma unroll 1
+      for (int k = 0; k < n_items; k++) {
+        const DfItem it = items[k];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] += df_eval<MODE, BARYON, REGULATE, OUTFLOW>(it, bin[r]);
+      }
+    }
+  }
+
+  const int64_t pbase = (int64_t)blockIdx.z * total;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    if (jbin[r] < g.nbins) {
+      int64_t idx = iy + (int64_t)g.Ny * (iphi + (int64_t)g.Nphi * jbin[r]);
+      partial[pbase + idx] += kCooperFryePrefactor * g.deg[jbin[r]] * acc[r];
+    }
+  }
+}
+
+}  // namespace
+
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int64_t total,
+                                       double *__restrict__ out)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; c++) s += partial[(int64_t)c * total + i];
+  out[i] = s;
+}
+
+namespace {
+
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+void launch_df(dim3 grid, cudaStream_t st, const double *pack, int64_t stride, int64_t n, int64_t cpc, const DfGrid &g,
+               double *partial, int64_t total)
+{
+  df_spectra_kernel<MODE, BARYON, REGULATE, OUTFLOW, 3><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, g, partial, total);
+}
+
+template <int MODE, bool BARYON>
+void dispatch_df2(bool reg, bool outflow, dim3 grid, cudaStream_t st, const double *pack, int64_t stride, int64_t n,
+                  int64_t cpc, const DfGrid &g, double *partial, int64_t total)
+{
+  if (reg && outflow) launch_df<MODE, BARYON, true, true>(grid, st, pack, stride, n, cpc, g, partial, total);
+  else if (reg) launch_df<MODE, BARYON, true, false>(grid, st, pack, stride, n, cpc, g, partial, total);
+  else if (outflow) launch_df<MODE, BARYON, false, true>(grid, st, pack, stride, n, cpc, g, partial, total);
+  else launch_df<MODE, BARYON, false, false>(grid, st, pack, stride, n, cpc, g, partial, total);
+}
+
+}  // namespace
+
+constexpr int kDfBinsPerThread = 3;
+
+// Builds the per-(species, pT) bin arrays shared by all spectra kernels; returns device pointers in `out`.
+is3d_status build_bin_arrays(is3d_ctx *ctx, const double **mT, const double **pT, const double **m2, const double **baryon,
+                             const double **sign, const double **deg)
+{
+  const int nb = ctx->ns * ctx->NpT;
+  std::vector<double> h(6 * (size_t)nb);
+  for (int s = 0; s < ctx->ns; s++)
+    for (int ip = 0; ip < ctx->NpT; ip++) {
+      int j = s * ctx->NpT + ip;
+      double m = ctx->h_mass[s], p = ctx->pT[ip];
+      double mass2 = m * m;
+      h[0 * nb + j] = sqrt(mass2 + p * p);      // mT, MomentumSpectra.cpp:266
+      h[1 * nb + j] = p;
+      h[2 * nb + j] = mass2;
+      h[3 * nb + j] = ctx->h_baryon[s];
+      h[4 * nb + j] = ctx->h_sign[s];
+      h[5 * nb + j] = ctx->h_deg[s];
+    }
+  void *d = nullptr;
+  IS3D_TRY(ctx->get_scratch("bin_arrays", h.size() * sizeof(double), &d));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const double *b = (const double *)d;
+  *mT = b; *pT = b + nb; *m2 = b + 2 * nb; *baryon = b + 3 * nb; *sign = b + 4 * nb; *deg = b + 5 * nb;
+  return IS3D_OK;
+}
+
+// chunking policy shared by the spectra kernels: enough blocks for ~16 waves, partial sums <= 1 GiB
+void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
+                   int64_t *cells_per_chunk)
+{
+  int64_t resident = 2 * (int64_t)ctx->sm_count;
+  int64_t want = (16 * resident + blocks_per_chunk - 1) / blocks_per_chunk;
+  int64_t max_by_cells = (ncells + tile - 1) / tile;
+  int64_t max_by_mem = ((int64_t)1 << 30) / (total * 8);
+  if (max_by_mem < 1) max_by_mem = 1;
+  int64_t nc = want;
+  if (nc > max_by_cells) nc = max_by_cells;
+  if (nc > max_by_mem) nc = max_by_mem;
+  if (nc > 65535) nc = 65535;
+  if (nc < 1) nc = 1;
+  int64_t cpc = (ncells + nc - 1) / nc;
+  cpc = (cpc + tile - 1) / tile * tile;
+  nc = (ncells + cpc - 1) / cpc;
+  *nchunks = (int)nc;
+  *cells_per_chunk = cpc;
+}
+
+is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
+{
+  const is3d_params &p = ctx->prm;
+  const int64_t n = ctx->surf.n;
+  const int64_t total = (int64_t)ctx->ns * ctx->NpT * ctx->Nphi * ctx->Ny;
+  const int nbins = ctx->ns * ctx->NpT;
+
+  DfFlags fl;
+  fl.df_mode = p.df_mode; fl.dimension = p.dimension; fl.include_baryon = p.include_baryon;
+  fl.include_bulk = p.include_bulk_deltaf; fl.include_shear = p.include_shear_deltaf;
+  fl.include_baryondiff = p.include_baryondiff_deltaf;
+
+  DfGrid g;
+  IS3D_TRY(build_bin_arrays(ctx, &g.mT, &g.pT, &g.m2, &g.baryon, &g.sign, &g.deg));
+  g.nbins = nbins; g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
+  g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw;
+
+  const int nslices = (nbins + kThreads * kDfBinsPerThread - 1) / (kThreads * kDfBinsPerThread);
+  const int64_t blocks_per_chunk = (int64_t)nslices * ctx->Ny * ctx->Nphi;
+  if ((int64_t)ctx->Ny * ctx->Nphi > 65535) { ctx->set_error("Ny*Nphi exceeds 65535"); return IS3D_ERR_INVALID; }
+
+  const int64_t macro = 4 << 20;                      // cells per pass: bounds the pack scratch to ~1 GB
+  const int64_t stride = n < macro ? n : macro;
+  int nchunks; int64_t cpc;
+  choose_chunks(ctx, stride, blocks_per_chunk, total, kTile, &nchunks, &cpc);
+
+  void *pack = nullptr, *partial = nullptr, *counters = nullptr;
+  IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)DP_SIZE * stride * sizeof(double), &pack));
+  IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total * sizeof(double), &partial));
+  IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total * sizeof(double), ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+
+  cudaEvent_t e0, e1;
+  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
+  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));
+  float ms_total = 0.f;
+  int64_t launches = 0;
+
+  for (int64_t begin = 0; begin < n; begin += macro) {
+    int64_t count = n - begin < macro ? n - begin : macro;
+    df_setup_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->surf, begin, count, ctx->tb, fl, (double *)pack, stride, (unsigned long long *)counters);
+    IS3D_CUDA_TRY(ctx, cudaGetLastError());
+    int nch = (int)((count + cpc - 1) / cpc);
+    dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch);
+    IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0;
+    if (p.df_mode == 1) {
+      if (p.include_baryon) dispatch_df2<1, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total);
+      else dispatch_df2<1, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total);
+    } else {
+      if (p.include_baryon) dispatch_df2<2, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total);
+      else dispatch_df2<2, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total);
+    }
+    IS3D_CUDA_TRY(ctx, cudaGetLastError());
+    IS3D_CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    IS3D_CUDA_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    IS3D_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    ms_total += ms;
+    launches += 2;
+  }
+  reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total, out_dev);
+  IS3D_CUDA_TRY(ctx, cudaGetLastError());
+  launches += 1;
+  unsigned long long h_counters[16];
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (stats) {
+    stats->cells_total = n;
+    stats->cells_skipped = (int64_t)h_counters[0];
+    stats->cells_out_of_table = (int64_t)h_counters[1];
+    stats->kernel_ms = ms_total;
+    stats->kernel_launches = launches;
+  }
+  if (h_counters[1] != 0) {
+    ctx->set_error(std::to_string(h_counters[1]) + " cell(s) outside the df coefficient tables (the reference aborts here)");
+    return IS3D_ERR_TABLE_RANGE;
+  }
+  return IS3D_OK;
+}
+
+}  // namespace is3d

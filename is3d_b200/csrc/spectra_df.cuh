@@ -1,0 +1,167 @@
+// K1 math: continuous Cooper-Frye spectra with linear df corrections (df_mode 1 Grad 14-moment, df_mode 2 RTA
+// Chapman-Enskog).  Reference: EmissionFunctionArray::calculate_dN_pTdpTdphidy, src/cpp/MomentumSpectra.cpp:32-415.
+//
+// The reference evaluates, per (cell, species, pT, phi, y[, eta]),
+//     p^tau = mT cosh(y-eta), p^eta = mT sinh(y-eta)/tau, p^x = pT cos(phi), p^y = pT sin(phi)
+//     f = feq (1 + df),  feq = 1/(exp(u.p/T - b muB/T) + sign)
+// Every scalar product of p with a cell tensor is a polynomial in (mT, pT) whose coefficients depend only on
+// (cell, y, phi).  Those coefficients are formed once per (cell, iy, iphi) ("item constants", 16 doubles in shared
+// memory, warp-uniform) and the inner loop per momentum bin is ~15 FMAs + one exp + one (mode 2: two) reciprocals:
+//     x_E  = mT aT - pT bT                (= u.p / T)
+//     p.ds = mT c1 + pT d1
+//     pi^{mu nu} p_mu p_nu (scaled) = mT^2 q1 + mT pT q2 + pT^2 q3
+//     V^mu p_mu = mT v1 - pT v2
+#pragma once
+
+#include "cellmath.cuh"
+#include "dftables.cuh"
+
+namespace is3d {
+
+// per-cell pack written by the setup kernel, SoA in HBM: pack[k * stride + cell]
+enum DfPackIdx {
+  DP_VALID = 0, DP_ETA, DP_UTT, DP_TUNT, DP_UXT, DP_UYT, DP_ALPHAB,
+  DP_DAT, DP_DAX, DP_DAY, DP_DANT,
+  DP_PITT, DP_T2PINN, DP_TPITN, DP_PITX, DP_PITY, DP_TPIXN, DP_TPIYN, DP_PIXX, DP_PIYY, DP_PIXY,
+  DP_K0, DP_K1, DP_K2, DP_G0, DP_G1, DP_VT, DP_TVN, DP_VX, DP_VY,
+  DP_SIZE
+};
+
+struct DfFlags {
+  int df_mode;                 // 1 or 2
+  int dimension;
+  int include_baryon;
+  int include_bulk, include_shear, include_baryondiff;
+};
+
+// status bits returned by the per-cell setup
+enum { CELL_OK = 0, CELL_SKIPPED = 1, CELL_OUT_OF_TABLE = 2 };
+
+// Per-cell prologue of the reference loop (MomentumSpectra.cpp:109-246) folded into the pack.
+IS3D_HD int df_setup_cell(const Cell &c, const DfTables &tb, const DfFlags &fl, double pack[DP_SIZE])
+{
+  for (int k = 0; k < DP_SIZE; k++) pack[k] = 0.0;
+  double tau = c.tau, tau2 = tau * tau;
+  double ux = c.ux, uy = c.uy, un = c.un;
+  double utperp = sqrt(1.0 + ux * ux + uy * uy);
+  double tau2_un = tau2 * un;
+  double ut = sqrt(utperp * utperp + tau2_un * un);
+  // skip cells with u.dsigma <= 0 (:132)
+  if (ut * c.dat + ux * c.dax + uy * c.day + un * c.dan <= 0.0) return CELL_SKIPPED;
+
+  double T = c.T, P = c.P, E = c.E;
+  Shear pi;
+  if (fl.include_shear) pi = complete_shear(c.pixx, c.pixy, c.pixn, c.piyy, c.piyn, ut, ux, uy, un, tau2);
+  double bulkPi = fl.include_bulk ? c.bulkPi : 0.0;
+  double muB = 0.0, alphaB = 0.0, nB = 0.0, Vt = 0.0, Vx = 0.0, Vy = 0.0, Vn = 0.0, baryon_enthalpy_ratio = 0.0;
+  if (fl.include_baryon && fl.include_baryondiff) {      // :176-187
+    muB = c.muB; nB = c.nB; Vx = c.Vx; Vy = c.Vy; Vn = c.Vn;
+    Vt = (Vx * ux + Vy * uy + Vn * tau2_un) / ut;
+    alphaB = muB / T;
+    baryon_enthalpy_ratio = nB / (E + P);
+  }
+  DfCoeff df;
+  if (!evaluate_df_coefficients(tb, fl.df_mode, fl.include_baryon, T, muB, E, P, bulkPi, &df)) return CELL_OUT_OF_TABLE;
+
+  double invT = 1.0 / T;
+  double sc, K0, K1, K2, G0, G1;
+  if (fl.df_mode == 1) {                                 // :222-231
+    double shear_coeff = 1.0 / df.shear14_coeff;
+    double bulk0 = (df.c0 - df.c2) * bulkPi, bulk1 = df.c1 * bulkPi, bulk2 = (4. * df.c2 - df.c0) * bulkPi;
+    sc = shear_coeff;
+    K0 = bulk0; K1 = bulk1 * T; K2 = bulk2 * T * T;      // df_bulk = K0 m^2 + (K1 b + K2 xE) xE
+    G0 = df.c3; G1 = df.c4 * T;                          // df_diff = (G0 b + G1 xE) V.p
+  } else {                                               // :232-241
+    double shear_coeff = 0.5 / (df.betapi * T);
+    double bulk0 = df.F / (T * T * df.betabulk) * bulkPi, bulk1 = df.G / df.betabulk * bulkPi;
+    double bulk2 = bulkPi / (3.0 * T * df.betabulk);
+    sc = shear_coeff * invT;                             // df_shear = sc' pipp / xE
+    K0 = (bulk0 + bulk2) * T; K1 = bulk1; K2 = bulk2 * invT;   // df_bulk = K0 xE + K1 b - K2 m^2 / xE
+    G0 = baryon_enthalpy_ratio / df.betaV; G1 = invT / df.betaV;   // df_diff = (G0 - G1 b / xE) V.p
+  }
+  pack[DP_VALID] = 1.0;
+  pack[DP_ETA] = c.eta;
+  pack[DP_UTT] = ut * invT;  pack[DP_TUNT] = tau * un * invT;  pack[DP_UXT] = ux * invT;  pack[DP_UYT] = uy * invT;
+  pack[DP_ALPHAB] = alphaB;
+  pack[DP_DAT] = c.dat; pack[DP_DAX] = c.dax; pack[DP_DAY] = c.day; pack[DP_DANT] = c.dan / tau;
+  pack[DP_PITT] = sc * pi.tt; pack[DP_T2PINN] = sc * tau2 * pi.nn; pack[DP_TPITN] = sc * tau * pi.tn;
+  pack[DP_PITX] = sc * pi.tx; pack[DP_PITY] = sc * pi.ty; pack[DP_TPIXN] = sc * tau * pi.xn; pack[DP_TPIYN] = sc * tau * pi.yn;
+  pack[DP_PIXX] = sc * pi.xx; pack[DP_PIYY] = sc * pi.yy; pack[DP_PIXY] = sc * pi.xy;
+  pack[DP_K0] = K0; pack[DP_K1] = K1; pack[DP_K2] = K2; pack[DP_G0] = G0; pack[DP_G1] = G1;
+  pack[DP_VT] = Vt; pack[DP_TVN] = tau * Vn; pack[DP_VX] = Vx; pack[DP_VY] = Vy;
+  return CELL_OK;
+}
+
+// item constants: one (cell, eta-node) seen from a fixed (y, phi)
+struct alignas(16) DfItem {
+  double aT, bT, c1, d1;
+  double q1, q2, q3, K0;
+  double K1, K2, alphaB, v1;
+  double v2, G0, G1, pad;
+};
+
+// pk(k) returns pack entry k of this cell.  sh/ch = sinh, cosh of (y - eta); w = eta quadrature weight (1 in 3+1d).
+template <class PackFn>
+IS3D_HD DfItem df_make_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w)
+{
+  DfItem it;
+  it.aT = ch * pk(DP_UTT) - sh * pk(DP_TUNT);
+  it.bT = cphi * pk(DP_UXT) + sphi * pk(DP_UYT);
+  it.c1 = w * (ch * pk(DP_DAT) + sh * pk(DP_DANT));
+  it.d1 = w * (cphi * pk(DP_DAX) + sphi * pk(DP_DAY));
+  it.q1 = ch * ch * pk(DP_PITT) + sh * sh * pk(DP_T2PINN) - 2.0 * ch * sh * pk(DP_TPITN);
+  it.q2 = 2.0 * (sh * (pk(DP_TPIXN) * cphi + pk(DP_TPIYN) * sphi) - ch * (pk(DP_PITX) * cphi + pk(DP_PITY) * sphi));
+  it.q3 = pk(DP_PIXX) * cphi * cphi + pk(DP_PIYY) * sphi * sphi + 2.0 * pk(DP_PIXY) * cphi * sphi;
+  it.K0 = pk(DP_K0); it.K1 = pk(DP_K1); it.K2 = pk(DP_K2);
+  it.alphaB = pk(DP_ALPHAB);
+  it.v1 = pk(DP_VT) * ch - pk(DP_TVN) * sh;
+  it.v2 = pk(DP_VX) * cphi + pk(DP_VY) * sphi;
+  it.G0 = pk(DP_G0); it.G1 = pk(DP_G1);
+  it.pad = 0.0;
+  return it;
+}
+
+// per-bin registers
+struct DfBin {
+  double mT, pT, mT2, mTpT, pT2, m2, baryon, sign;
+};
+
+// One integrand evaluation: returns w * p.dsigma * feq (1 + df)   (MomentumSpectra.cpp:304-361)
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+IS3D_HD double df_eval(const DfItem &it, const DfBin &b)
+{
+  double xE = fma(b.mT, it.aT, -b.pT * it.bT);
+  double pds = fma(b.mT, it.c1, b.pT * it.d1);
+  double x = xE;
+  if (BARYON) x = fma(-b.baryon, it.alphaB, xE);
+  double feq = fast_rcp(fast_exp(x) + b.sign);
+  double feqbar = fma(-b.sign, feq, 1.0);
+  double pipp = fma(b.mT2, it.q1, fma(b.mTpT, it.q2, b.pT2 * it.q3));
+  double dfv;
+  if (MODE == 1) {
+    double lin = it.K2 * xE;                         // (K1 b + K2 xE)
+    if (BARYON) lin = fma(it.K1, b.baryon, lin);
+    dfv = fma(lin, xE, fma(it.K0, b.m2, pipp));
+    if (BARYON) {
+      double Vp = fma(b.mT, it.v1, -b.pT * it.v2);
+      dfv = fma(fma(it.G1, xE, it.G0 * b.baryon), Vp, dfv);
+    }
+  } else {
+    double r = fast_rcp(xE);
+    double t = fma(-it.K2, b.m2, pipp);              // (pipp' - K2 m^2)
+    dfv = fma(t, r, it.K0 * xE);
+    if (BARYON) {
+      dfv = fma(it.K1, b.baryon, dfv);
+      double Vp = fma(b.mT, it.v1, -b.pT * it.v2);
+      dfv = fma(fma(-it.G1 * b.baryon, r, it.G0), Vp, dfv);
+    }
+  }
+  double df = feqbar * dfv;
+  if (REGULATE) df = fmax(-1.0, fmin(df, 1.0));
+  double f = fma(feq, df, feq);
+  double contrib = pds * f;
+  if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
+  return contrib;
+}
+
+}  // namespace is3d

@@ -1,0 +1,117 @@
+// TEST INFRASTRUCTURE ONLY (development aid) -- never built into, loaded by or called from the product.
+//
+// Compiles the IS3D_HD per-cell / per-momentum formulas of is3d_b200/csrc/*.cuh with g++ and runs them in plain
+// loops over a working directory, so that a formula slip is caught here (no GPU in the build container) before a
+// GPU run.  The CUDA kernels call the very same inline functions; what this cannot check is the kernels' launch
+// geometry, shared-memory staging and reductions -- the `-m gpu` parity tests do that through the C ABI.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../is3d_b200/csrc/spectra_df.cuh"
+#include "../../is3d_b200/host/host_dfview.hpp"
+#include "../../is3d_b200/host/is3d_host.hpp"
+
+using namespace is3dhost;
+
+namespace {
+struct Loaded {
+  ParameterReader par;
+  FO_surface surf;
+  std::vector<particle_info> pdg;
+  std::vector<int> chosen;
+  Table pT, phi, y, eta;
+  Deltaf_Data *df = nullptr;
+  void load(const char *root)
+  {
+    set_root(root);
+    par.readFromFile("iS3D_parameters.dat");
+    FO_data_reader rd(&par, "input");
+    rd.get_number_cells();
+    rd.read_freezeout_surface(surf);
+    PDG_Data p(&par);
+    p.read_resonances(pdg);
+    Table ch("PDG/chosen_particles.dat");
+    for (long m = 0; m < ch.getNumberOfRows(); m++)
+      for (size_t n = 0; n < pdg.size(); n++)
+        if (pdg[n].mc_id == (long)ch.get(1, m + 1)) { chosen.push_back((int)n); break; }
+    df = new Deltaf_Data(&par);
+    df->load_df_coefficient_data();
+    if (!(int)par.getVal("include_baryon")) df->compute_jonah_coefficients(pdg);
+    df->compute_particle_densities(pdg);
+    pT.loadTableFromFile("tables/momentum/pT_table.dat");
+    phi.loadTableFromFile("tables/momentum/phi_table.dat");
+    y.loadTableFromFile("tables/momentum/y_table.dat");
+    eta.loadTableFromFile("tables/spacetime_rapidity/eta_table.dat");
+  }
+};
+
+template <int MODE, bool BARYON>
+double eval_dispatch(bool reg, bool outflow, const is3d::DfItem &it, const is3d::DfBin &b)
+{
+  if (reg && outflow) return is3d::df_eval<MODE, BARYON, true, true>(it, b);
+  if (reg) return is3d::df_eval<MODE, BARYON, true, false>(it, b);
+  if (outflow) return is3d::df_eval<MODE, BARYON, false, true>(it, b);
+  return is3d::df_eval<MODE, BARYON, false, false>(it, b);
+}
+}  // namespace
+
+// out: Ns*NpT*Nphi*Ny doubles, reference indexing.  Returns the number of doubles written (0 on unsupported mode).
+extern "C" long hostcheck_spectra_df(const char *root, double *out, long capacity)
+{
+  Loaded L;
+  L.load(root);
+  is3d::DfFlags fl;
+  fl.df_mode = L.par.getVal("df_mode"); fl.dimension = L.par.getVal("dimension");
+  fl.include_baryon = L.par.getVal("include_baryon"); fl.include_bulk = L.par.getVal("include_bulk_deltaf");
+  fl.include_shear = L.par.getVal("include_shear_deltaf"); fl.include_baryondiff = L.par.getVal("include_baryondiff_deltaf");
+  const bool reg = (int)L.par.getVal("regulate_deltaf"), outflow = (int)L.par.getVal("outflow");
+  if (fl.df_mode != 1 && fl.df_mode != 2) return 0;
+  HostDfView view(*L.df);
+  const int ns = (int)L.chosen.size(), npT = (int)L.pT.getNumberOfRows(), nphi = (int)L.phi.getNumberOfRows();
+  const int ny = fl.dimension == 3 ? (int)L.y.getNumberOfRows() : 1;
+  const int neta = fl.dimension == 3 ? 1 : (int)L.eta.getNumberOfRows();
+  const long total = (long)ns * npT * nphi * ny;
+  if (total > capacity) return -total;
+  std::vector<double> acc(total, 0.0);
+  is3d::SurfaceView sv;
+  for (int k = 0; k < 25; k++) sv.col[k] = L.surf.col[k].data();
+  sv.n = L.surf.size();
+  for (int64_t ic = 0; ic < sv.n; ic++) {
+    is3d::Cell c = is3d::load_cell(sv, ic, fl.include_baryon != 0);
+    double pack[is3d::DP_SIZE];
+    int st = is3d::df_setup_cell(c, view.tb, fl, pack);
+    if (st == is3d::CELL_OUT_OF_TABLE) { printf("hostcheck: cell %ld out of table\n", (long)ic); return 0; }
+    if (st != is3d::CELL_OK) continue;
+    auto pk = [&](int k) { return pack[k]; };
+    for (int iy = 0; iy < ny; iy++) {
+      double yv = fl.dimension == 3 ? L.y.get(1, iy + 1) : 0.0;
+      for (int ie = 0; ie < neta; ie++) {
+        double etav = fl.dimension == 3 ? pack[is3d::DP_ETA] : L.eta.get(1, ie + 1);
+        double w = fl.dimension == 3 ? 1.0 : L.eta.get(2, ie + 1);
+        double sh = sinh(yv - etav), ch = sqrt(1.0 + sh * sh);
+        for (int ip = 0; ip < nphi; ip++) {
+          double ph = L.phi.get(1, ip + 1);
+          is3d::DfItem it = is3d::df_make_item(pk, sh, ch, cos(ph), sin(ph), w);
+          for (int s = 0; s < ns; s++) {
+            const particle_info &p = L.pdg[L.chosen[s]];
+            for (int ipT = 0; ipT < npT; ipT++) {
+              double pTv = L.pT.get(1, ipT + 1), m2 = p.mass * p.mass, mT = sqrt(m2 + pTv * pTv);
+              is3d::DfBin b{mT, pTv, mT * mT, mT * pTv, pTv * pTv, m2, (double)p.baryon, (double)p.sign};
+              double v;
+              if (fl.df_mode == 1) v = fl.include_baryon ? eval_dispatch<1, true>(reg, outflow, it, b) : eval_dispatch<1, false>(reg, outflow, it, b);
+              else v = fl.include_baryon ? eval_dispatch<2, true>(reg, outflow, it, b) : eval_dispatch<2, false>(reg, outflow, it, b);
+              acc[iy + (long)ny * (ip + (long)nphi * (ipT + (long)npT * s))] += v;
+            }
+          }
+        }
+      }
+    }
+  }
+  for (int s = 0; s < ns; s++) {
+    double g = (double)L.pdg[L.chosen[s]].gspin;
+    for (long k = 0; k < (long)npT * nphi * ny; k++) out[(long)s * npT * nphi * ny + k] = is3d::kCooperFryePrefactor * g * acc[(long)s * npT * nphi * ny + k];
+  }
+  return total;
+}
