@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Headline benchmark: Cooper-Frye cell x species x momentum evaluations per second (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path (default)
+    python bench.py --impl reference ...                     # the reference's own CPU (OpenMP) path, bounded sample
+    torchrun --nproc-per-node N ... bench.py --gpus N ...    # cells sharded over N GPUs + one NCCL all-reduce
+
+Workload (config.workload): continuous spectra, all 444 SMASH species, shipped 51 pT x 1 phi x 21 y grid,
+df_mode 2 (RTA Chapman-Enskog) with bulk + shear + baryon diffusion on the seeded synthetic 3+1D surface S-3D
+(SURVEY.md 8d), `--cells-per-gpu` cells per GPU (weak scaling; 1.25 M x 8 GPUs = the 10 M-cell surface of
+BASELINE.json config 5).  One "step" = one full Cooper-Frye pass over the rank's cells (per-cell set-up kernel +
+spectra kernel + partial reduction) followed, for N > 1, by the all-reduce of the spectra array.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+from is3d_b200 import synthetic, workdir  # noqa: E402
+
+# algorithmic FLOPs per integrand evaluation (SURVEY.md 8d / BASELINE.md 4; DESIGN.md restates the derivation)
+F_ALG = {1: 165.0, 2: 194.0, 3: 265.0, 4: 265.0, 5: 265.0}
+NS_SMASH, NPT, NPHI, NY = 444, 51, 1, 21
+
+
+def bench_params(df_mode: int) -> dict:
+    return dict(operation=1, mode=1, hrg_eos=2, dimension=3, df_mode=df_mode, include_baryon=1,
+                include_bulk_deltaf=1, include_shear_deltaf=1, include_baryondiff_deltaf=1, regulate_deltaf=0, outflow=0)
+
+
+def workload_name(df_mode: int, cells: int, n_gpus: int) -> str:
+    return (f"continuous spectra, all SMASH species (444), df_mode={df_mode} with bulk+shear+baryon diffusion, "
+            f"51pT x 1phi x 21y, synthetic 3+1D surface S-3D, {cells} cells per GPU x {n_gpus} GPU")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args) -> None:
+    """The reference's own CPU implementation (oracle/_ref, unmodified sources, OpenMP build) on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    exe = os.path.join(REPO, "oracle", "_ref", "is3d_ref_omp")
+    cores = os.cpu_count() or 1
+    cells = args.ref_cells
+    if not os.access(exe, os.X_OK):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/is3d_ref_omp not built (run oracle/Makefile where /root/reference exists)"}))
+        return
+    surf = synthetic.s3d(cells, seed=2024, baryon=True)
+    params = bench_params(args.df_mode)
+    root = tempfile.mkdtemp(prefix="is3d_ref_")
+    try:
+        workdir.make_workdir(root, params, chosen="smash")
+        synthetic.write_mode1(os.path.join(root, "input", "surface.dat"), surf, baryon=True)
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+        times = []
+        for i in range(args.warmup + args.steps):
+            with open(os.path.join(root, "ref_stdout.log"), "w") as log:
+                subprocess.run([exe], cwd=root, stdout=log, stderr=subprocess.STDOUT, env=env, check=True)
+            t = float(open(os.path.join(root, "ref_dump", "timing.txt")).read().split()[0])
+            if i >= args.warmup:
+                times.append(t)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    evals = float(cells) * NS_SMASH * NPT * NPHI * NY
+    sec = float(np.mean(times))
+    value = evals / sec
+    sample = f"{cells}-cell prefix-sized S-3D sample (seed 2024) of the same workload, timed inside calculate_spectra"
+    line = {"impl": "reference", "metric": "Cooper-Frye cell*species*momentum evals/s", "value": value, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.df_mode, args.cells_per_gpu, args.gpus), "sample": sample,
+                       "note": "3+1D OpenMP loop of the reference is racy (shared etaValues[0]); timing only"},
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline(args) -> dict:
+    """Bounded reference run beside the GPU number (rank 0, N = 1 only)."""
+    exe = os.path.join(REPO, "oracle", "_ref", "is3d_ref_omp")
+    cores = os.cpu_count() or 1
+    if not os.access(exe, os.X_OK):
+        return {"value": None, "unit": "evals/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref not built"}
+    cells = args.ref_cells
+    surf = synthetic.s3d(cells, seed=2024, baryon=True)
+    root = tempfile.mkdtemp(prefix="is3d_cpu_")
+    try:
+        workdir.make_workdir(root, bench_params(args.df_mode), chosen="smash")
+        synthetic.write_mode1(os.path.join(root, "input", "surface.dat"), surf, baryon=True)
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+        with open(os.path.join(root, "ref_stdout.log"), "w") as log:
+            subprocess.run([exe], cwd=root, stdout=log, stderr=subprocess.STDOUT, env=env, check=True)
+        sec = float(open(os.path.join(root, "ref_dump", "timing.txt")).read().split()[0])
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    evals = float(cells) * NS_SMASH * NPT * NPHI * NY
+    return {"value": evals / sec, "unit": "evals/s", "cores": cores, "kind": "reference",
+            "sample": f"{cells} cells of the same S-3D workload, reference OpenMP build with {cores} threads, {sec:.2f} s inside calculate_spectra"}
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from is3d_b200 import HostSession
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this repository has no CPU compute path")
+    torch.cuda.set_device(local)
+    os.environ["IS3D_DEVICE"] = str(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cells = args.cells_per_gpu
+    surf = synthetic.s3d(cells, seed=2024 + rank, baryon=True)         # rank's shard of the surface
+    params = bench_params(args.df_mode)
+    root = tempfile.mkdtemp(prefix=f"is3d_bench_r{rank}_")
+    workdir.make_workdir(root, params, chosen="smash")
+    h = HostSession(root)
+    # thermodynamic averages (only the sampler uses them) from a small prefix: the host loop is O(cells) python-free C++
+    h.set_surface({k: v[:1000] for k, v in surf.items()})
+    h.prepare()
+    shape = h.spectra_shape()
+    total = int(np.prod(shape))
+    evals_rank = float(cells) * total
+
+    ext = torch.cuda.ExternalStream(h.lib.is3d_stream(h.ctx), device=torch.device("cuda", local))
+    # pinned host copies (e2e path) and resident device copies (value path)
+    host_cols = {k: torch.from_numpy(v).pin_memory() for k, v in surf.items()}
+    dev_cols = {k: t.cuda(non_blocking=True) for k, t in host_cols.items()}
+    torch.cuda.synchronize()
+    out_dev = torch.zeros(total, dtype=torch.float64, device="cuda")
+    h.abi_set_surface_device({k: t.data_ptr() for k, t in dev_cols.items()}, cells, global_offset=rank * cells)
+
+    def step():
+        st = h.abi_spectra_device(out_dev.data_ptr())
+        if world > 1:
+            dist.all_reduce(out_dev)                                      # the one collective of the path (NCCL / NVLink)
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(ext):
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kernel_ms, launches = 0.0, 0
+        ev0.record(ext)
+        for _ in range(args.steps):
+            st = step()
+            kernel_ms += st.kernel_ms
+            launches += st.kernel_launches
+        ev1.record(ext)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+
+        # ---- end to end through the C ABI with HOST buffers: H2D of the 25 columns + compute + D2H of the spectra ----
+        host_np = {k: t_.numpy() for k, t_ in host_cols.items()}
+        e2e_steps = max(1, min(args.steps, 2))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h.abi_set_surface(host_np, global_offset=rank * cells)
+            spec, _ = h.abi_spectra()
+            if world > 1:
+                tmp = torch.from_numpy(spec.reshape(-1)).cuda()
+                dist.all_reduce(tmp)
+                spec = tmp.cpu().numpy()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+
+    fp64_peak = h.abi_fp64_peak()
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = evals_rank * world / (ms_step * 1e-3)
+        kern_s = kernel_ms / args.steps * 1e-3
+        achieved = evals_rank * F_ALG[args.df_mode] / kern_s / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        bytes_alg = cells * 25 * 8.0 + total * 8.0
+        line = {
+            "metric": "Cooper-Frye cell*species*momentum evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.df_mode, cells, world), "global_cells": cells * world,
+                       "evals_per_step": evals_rank * world, "l2_policy": "inputs larger than L2 (cell packs: 240 B x cells per pass)",
+                       "parallelism": f"cells sharded x{world}, one NCCL all-reduce of {total} doubles" if world > 1 else "single GPU"},
+            "e2e": {"value": evals_rank * world / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(cells * 25 * 8),
+                    "d2h_bytes_per_step": int(total * 8)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                         "traffic": None, "kernel": "df_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
+                         "flops_per_eval_algorithmic": F_ALG[args.df_mode],
+                         "peak_source": "DFMA micro-benchmark run live by is3d_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
+                         "hbm_gbs_algorithmic": bytes_alg / kern_s / 1e9, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    h.close()
+    shutil.rmtree(root, ignore_errors=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells-per-gpu", type=int, default=1_250_000)
+    ap.add_argument("--df-mode", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--ref-cells", type=int, default=2000, help="cells of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

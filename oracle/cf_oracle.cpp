@@ -1,0 +1,528 @@
+// TEST INFRASTRUCTURE ONLY -- see cf_oracle.h.  CPU restatement of the reference's Cooper-Frye hot path.
+// Scalar, single-threaded, one loop nest per reference function, same loop order (cell -> species -> pT -> phi ->
+// y -> eta) and the same association of the floating-point expressions wherever that matters at 1e-10.
+#include "cf_oracle.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+const double hbarC = 0.197327053;                               // reference iS3D.h:14
+const double two_pi2_hbarC3 = 2.0 * pow(M_PI, 2) * pow(hbarC, 3);   // iS3D.h:16
+
+// ---------------------------------------------------------------------------------------------------------------
+// GSL pieces (third party, GSL 2.x): natural cubic spline (interpolation/cspline.c) and 3x3 LU (linalg/lu.c)
+// ---------------------------------------------------------------------------------------------------------------
+struct Spline {
+  std::vector<double> x, y, c;
+  void init(const double *xa, const double *ya, int n)
+  {
+    x.assign(xa, xa + n); y.assign(ya, ya + n); c.assign(n, 0.0);
+    int sys = n - 2;
+    if (sys <= 0) return;
+    std::vector<double> g(sys), diag(sys), off(sys);
+    for (int i = 0; i < sys; i++) {
+      double h_i = xa[i + 1] - xa[i], h_ip1 = xa[i + 2] - xa[i + 1];
+      double yd_i = ya[i + 1] - ya[i], yd_ip1 = ya[i + 2] - ya[i + 1];
+      off[i] = h_ip1;
+      diag[i] = 2.0 * (h_ip1 + h_i);
+      g[i] = 3.0 * (yd_ip1 * (1.0 / h_ip1) - yd_i * (1.0 / h_i));
+    }
+    if (sys == 1) { c[1] = g[0] / diag[0]; return; }
+    std::vector<double> gamma(sys), alpha(sys), z(sys), cc(sys);
+    alpha[0] = diag[0]; gamma[0] = off[0] / alpha[0];
+    for (int i = 1; i < sys - 1; i++) { alpha[i] = diag[i] - off[i - 1] * gamma[i - 1]; gamma[i] = off[i] / alpha[i]; }
+    alpha[sys - 1] = diag[sys - 1] - off[sys - 2] * gamma[sys - 2];
+    z[0] = g[0];
+    for (int i = 1; i < sys; i++) z[i] = g[i] - gamma[i - 1] * z[i - 1];
+    for (int i = 0; i < sys; i++) cc[i] = z[i] / alpha[i];
+    c[sys] = cc[sys - 1];
+    for (int i = sys - 2; i >= 0; i--) c[i + 1] = cc[i] - gamma[i] * c[i + 2];
+  }
+  // false = domain error (the reference aborts in gsl_spline_eval)
+  bool eval(double v, double *out) const
+  {
+    int n = (int)x.size();
+    if (!(v >= x[0] && v <= x[n - 1])) return false;
+    int lo = 0, hi = n - 1;
+    while (hi > lo + 1) { int i = (hi + lo) / 2; if (x[i] > v) hi = i; else lo = i; }
+    double dx = x[lo + 1] - x[lo], dy = y[lo + 1] - y[lo];
+    double b = (dy / dx) - dx * (c[lo + 1] + 2.0 * c[lo]) / 3.0;
+    double d = (c[lo + 1] - c[lo]) / (3.0 * dx);
+    double delta = v - x[lo];
+    *out = y[lo] + delta * (b + delta * (c[lo] + delta * d));
+    return true;
+  }
+};
+
+// LU decomposition with partial pivoting + inverse, as gsl_linalg_LU_decomp / LU_invert do it
+void lu_invert3(const double Ain[9], double inv[9])
+{
+  double A[3][3];
+  int perm[3] = {0, 1, 2};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) A[i][j] = Ain[3 * i + j];
+  for (int j = 0; j < 2; j++) {
+    double max = fabs(A[j][j]); int ip = j;
+    for (int i = j + 1; i < 3; i++) if (fabs(A[i][j]) > max) { max = fabs(A[i][j]); ip = i; }
+    if (ip != j) { for (int k = 0; k < 3; k++) { double t = A[j][k]; A[j][k] = A[ip][k]; A[ip][k] = t; } int t = perm[j]; perm[j] = perm[ip]; perm[ip] = t; }
+    if (A[j][j] != 0.0)
+      for (int i = j + 1; i < 3; i++) {
+        double aij = A[i][j] / A[j][j];
+        A[i][j] = aij;
+        for (int k = j + 1; k < 3; k++) A[i][k] -= aij * A[j][k];
+      }
+  }
+  for (int col = 0; col < 3; col++) {
+    double b[3];
+    for (int i = 0; i < 3; i++) b[i] = (perm[i] == col) ? 1.0 : 0.0;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < i; j++) b[i] -= A[i][j] * b[j];
+    for (int i = 2; i >= 0; i--) { for (int j = i + 1; j < 3; j++) b[i] -= A[i][j] * b[j]; b[i] /= A[i][i]; }
+    for (int i = 0; i < 3; i++) inv[3 * i + col] = b[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// df coefficients: Deltaf_Data::evaluate_df_coefficients (DeltafData.cpp:324-519)
+// ---------------------------------------------------------------------------------------------------------------
+struct DfCoeff {
+  double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, shear14_coeff = 0;
+  double F = 0, G = 0, betabulk = 0, betaV = 0, betapi = 0;
+  double lambda = 0, z = 0, delta_lambda = 0, delta_z = 0;
+};
+
+struct DfData {
+  const cf_inputs *in;
+  int df_mode, include_baryon;
+  Spline c0, c2, F, betabulk, betapi, lambda2, z;
+  double T_min, muB_min, dT, dmuB;
+  DfData(const cf_params *p, const cf_inputs *in_) : in(in_), df_mode(p->df_mode), include_baryon(p->include_baryon)
+  {
+    T_min = in->T_arr[0]; muB_min = in->muB_arr ? in->muB_arr[0] : 0.0;
+    dT = fabs(in->T_arr[1] - in->T_arr[0]);
+    dmuB = (in->n_muB > 1) ? fabs(in->muB_arr[1] - in->muB_arr[0]) : 0.0;
+    if (!include_baryon) {     // construct_cubic_splines, DeltafData.cpp:298-321 (muB = 0 row)
+      c0.init(in->T_arr, in->c0, in->n_T); c2.init(in->T_arr, in->c2, in->n_T);
+      F.init(in->T_arr, in->F, in->n_T); betabulk.init(in->T_arr, in->betabulk, in->n_T); betapi.init(in->T_arr, in->betapi, in->n_T);
+      if (in->n_ptb > 0) { lambda2.init(in->ptb_x, in->ptb_lambda2, in->n_ptb); z.init(in->ptb_x, in->ptb_z, in->n_ptb); }
+    }
+  }
+  double bil(const double *f, double T, double muB, int iTL, int iBL) const   // calculate_bilinear, :404-417
+  {
+    int iTR = iTL + 1, iBR = iBL + 1, nT = in->n_T;
+    double TL = in->T_arr[iTL], TR = in->T_arr[iTR], muBL = in->muB_arr[iBL], muBR = in->muB_arr[iBR];
+    double f_LL = f[iBL * nT + iTL], f_LR = f[iBR * nT + iTL], f_RL = f[iBL * nT + iTR], f_RR = f[iBR * nT + iTR];
+    return ((f_LL * (TR - T) + f_RL * (T - TL)) * (muBR - muB) + (f_LR * (TR - T) + f_RR * (T - TL)) * (muB - muBL)) / (dT * dmuB);
+  }
+  bool evaluate(double T, double muB, double E, double P, double bulkPi, DfCoeff *out) const
+  {
+    DfCoeff df;
+    bool ok = true;
+    if (!include_baryon) {                      // cubic_spline, :324-402
+      double T4 = T * T * T * T, v;
+      switch (df_mode) {
+        case 1:
+          ok &= c0.eval(T, &v); df.c0 = v / T4;
+          ok &= c2.eval(T, &v); df.c2 = v / T4;
+          df.shear14_coeff = 2.0 * T * T * (E + P);
+          break;
+        case 2: case 3: case 5:
+          ok &= F.eval(T, &v); df.F = v * T;
+          ok &= betabulk.eval(T, &v); df.betabulk = v * T4;
+          df.betaV = 1.0;
+          ok &= betapi.eval(T, &v); df.betapi = v * T4;
+          break;
+        case 4: {
+          double l2 = 0;
+          ok &= lambda2.eval(bulkPi / P, &l2);
+          if (bulkPi < 0.0) df.lambda = -sqrt(l2); else if (bulkPi > 0.0) df.lambda = sqrt(l2);   // 0 left as 0
+          ok &= z.eval(bulkPi / P, &df.z);
+          ok &= betapi.eval(T, &v); df.betapi = v * T4;
+          df.delta_lambda = bulkPi / (5.0 * df.betapi - 3.0 * P * (E + P) / E);
+          df.delta_z = -3.0 * df.delta_lambda * P / E;
+          break;
+        }
+      }
+    } else {                                    // bilinear_interpolation, :419-499
+      int iTL = (int)floor((T - T_min) / dT), iBL = (int)floor((muB - muB_min) / dmuB);
+      if (!(iTL >= 0 && iTL + 1 < in->n_T) || !(iBL >= 0 && iBL + 1 < in->n_muB)) { *out = df; return false; }
+      double T3 = T * T * T, T4 = T3 * T, T5 = T4 * T;
+      if (df_mode == 1) {
+        df.c0 = bil(in->c0, T, muB, iTL, iBL) / T4; df.c1 = bil(in->c1, T, muB, iTL, iBL) / T3;
+        df.c2 = bil(in->c2, T, muB, iTL, iBL) / T4; df.c3 = bil(in->c3, T, muB, iTL, iBL) / T4;
+        df.c4 = bil(in->c4, T, muB, iTL, iBL) / T5;
+        df.shear14_coeff = 2.0 * T * T * (E + P);
+      } else if (df_mode == 2 || df_mode == 3 || df_mode == 5) {
+        df.F = bil(in->F, T, muB, iTL, iBL) * T; df.G = bil(in->G, T, muB, iTL, iBL);
+        df.betabulk = bil(in->betabulk, T, muB, iTL, iBL) * T4; df.betaV = bil(in->betaV, T, muB, iTL, iBL) * T3;
+        df.betapi = bil(in->betapi, T, muB, iTL, iBL) * T4;
+      } else ok = false;
+    }
+    *out = df;
+    return ok;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// GaussThermal.cpp:7-85
+// ---------------------------------------------------------------------------------------------------------------
+typedef double (*thermal_fn)(double, double, double, double, double);
+double neq_int(double pbar, double mbar, double alphaB, double baryon, double sign)
+{ double Ebar = sqrt(pbar * pbar + mbar * mbar); return pbar * exp(pbar) / (exp(Ebar - baryon * alphaB) + sign); }
+double J10_int(double pbar, double mbar, double alphaB, double baryon, double sign)
+{ double Ebar = sqrt(pbar * pbar + mbar * mbar), q = exp(Ebar - baryon * alphaB) + sign; return pbar * exp(pbar + Ebar - baryon * alphaB) / (q * q); }
+double J20_int(double pbar, double mbar, double alphaB, double baryon, double sign)
+{ double Ebar = sqrt(pbar * pbar + mbar * mbar), q = exp(Ebar - baryon * alphaB) + sign; return Ebar * exp(pbar + Ebar - baryon * alphaB) / (q * q); }
+double GaussThermal(thermal_fn f, const double *root, const double *weight, int pts, double mbar, double alphaB, double baryon, double sign)
+{ double s = 0.0; for (int k = 0; k < pts; k++) s += weight[k] * f(root[k], mbar, alphaB, baryon, sign); return s; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-cell pieces shared by all paths
+// ---------------------------------------------------------------------------------------------------------------
+struct CellState {
+  double tau, tau2, eta, x, y, dat, dax, day, dan, ux, uy, un, ut, ut2, ux2, uy2, uperp, utperp, T, P, E;
+  double pitt, pitx, pity, pitn, pixx, pixy, pixn, piyy, piyn, pinn, bulkPi;
+  double muB, alphaB, nB, Vt, Vx, Vy, Vn, baryon_enthalpy_ratio;
+};
+
+// MomentumSpectra.cpp:109-187 (and the identical prologues at :516-599, :1159-1225)
+// df_variant: the df_mode 1,2 prologue forms u^tau and pi^{eta eta} through utperp and tau2_un (:124-160); the
+// feqmod / famod prologues write the same quantities slightly differently (:531, :564-568)
+bool load_cell(const cf_params *p, const cf_inputs *in, long i, bool always_shear_bulk, bool baryon_needs_diff, CellState *c,
+               bool df_variant = false)
+{
+  c->tau = in->col[0][i]; c->tau2 = c->tau * c->tau;
+  c->x = in->col[1][i]; c->y = in->col[2][i]; c->eta = in->col[3][i];
+  c->dat = in->col[4][i]; c->dax = in->col[5][i]; c->day = in->col[6][i]; c->dan = in->col[7][i];
+  c->ux = in->col[8][i]; c->uy = in->col[9][i]; c->un = in->col[10][i];
+  c->ux2 = c->ux * c->ux; c->uy2 = c->uy * c->uy;
+  c->uperp = sqrt(c->ux * c->ux + c->uy * c->uy);
+  c->utperp = sqrt(1.0 + c->ux * c->ux + c->uy * c->uy);
+  c->ut = sqrt(1.0 + c->ux * c->ux + c->uy * c->uy + c->tau2 * c->un * c->un);
+  if (df_variant) { double tau2_un = c->tau2 * c->un; c->ut = sqrt(c->utperp * c->utperp + tau2_un * c->un); }
+  c->ut2 = c->ut * c->ut;
+  if (c->ut * c->dat + c->ux * c->dax + c->uy * c->day + c->un * c->dan <= 0.0) return false;
+  c->E = in->col[11][i]; c->T = in->col[12][i]; c->P = in->col[13][i];
+  c->pitt = c->pitx = c->pity = c->pitn = c->pixx = c->pixy = c->pixn = c->piyy = c->piyn = c->pinn = 0.0;
+  if (p->include_shear_deltaf || always_shear_bulk) {
+    c->pixx = in->col[14][i]; c->pixy = in->col[15][i]; c->pixn = in->col[16][i]; c->piyy = in->col[17][i]; c->piyn = in->col[18][i];
+    double tau2 = c->tau2, un = c->un, ux = c->ux, uy = c->uy, ut = c->ut;
+    if (df_variant) {
+      double tau2_un = tau2 * un;
+      c->pinn = (c->pixx * (c->ux2 - c->ut2) + c->piyy * (c->uy2 - c->ut2) + 2.0 * (c->pixy * ux * uy + tau2_un * (c->pixn * ux + c->piyn * uy))) / (tau2 * c->utperp * c->utperp);
+      c->pitn = (c->pixn * ux + c->piyn * uy + tau2_un * c->pinn) / ut;
+      c->pity = (c->pixy * ux + c->piyy * uy + tau2_un * c->piyn) / ut;
+      c->pitx = (c->pixx * ux + c->pixy * uy + tau2_un * c->pixn) / ut;
+      c->pitt = (c->pitx * ux + c->pity * uy + tau2_un * c->pitn) / ut;
+    } else {
+      c->pinn = (c->pixx * (c->ux2 - c->ut2) + c->piyy * (c->uy2 - c->ut2) + 2.0 * (c->pixy * ux * uy + tau2 * un * (c->pixn * ux + c->piyn * uy))) / (tau2 * c->utperp * c->utperp);
+      c->pitn = (c->pixn * ux + c->piyn * uy + tau2 * c->pinn * un) / ut;
+      c->pity = (c->pixy * ux + c->piyy * uy + tau2 * c->piyn * un) / ut;
+      c->pitx = (c->pixx * ux + c->pixy * uy + tau2 * c->pixn * un) / ut;
+      c->pitt = (c->pitx * ux + c->pity * uy + tau2 * c->pitn * un) / ut;
+    }
+  }
+  c->bulkPi = (p->include_bulk_deltaf || always_shear_bulk) ? in->col[19][i] : 0.0;
+  c->muB = c->alphaB = c->nB = c->Vt = c->Vx = c->Vy = c->Vn = c->baryon_enthalpy_ratio = 0.0;
+  if (baryon_needs_diff) {
+    if (p->include_baryon && p->include_baryondiff_deltaf) {
+      c->muB = in->col[20][i]; c->nB = in->col[21][i]; c->Vx = in->col[22][i]; c->Vy = in->col[23][i]; c->Vn = in->col[24][i];
+      c->Vt = df_variant ? (c->Vx * c->ux + c->Vy * c->uy + c->Vn * (c->tau2 * c->un)) / c->ut
+                         : (c->Vx * c->ux + c->Vy * c->uy + c->tau2 * c->Vn * c->un) / c->ut;
+      c->alphaB = c->muB / c->T;
+      c->baryon_enthalpy_ratio = c->nB / (c->E + c->P);
+    }
+  } else if (p->include_baryon) {              // famod: muB alone (MomentumSpectra.cpp:1212-1225)
+    c->muB = in->col[20][i];
+    if (p->include_baryondiff_deltaf) {
+      c->Vx = in->col[22][i]; c->Vy = in->col[23][i]; c->Vn = in->col[24][i];
+      c->Vt = (c->Vx * c->ux + c->Vy * c->uy + c->tau2 * c->Vn * c->un) / c->ut;
+    }
+    c->alphaB = c->muB / c->T;
+  }
+  return true;
+}
+
+// Milne_Basis (LocalRestFrame.cpp:12-41) and boosts (:133-154, :173-185)
+struct Basis { double Xt, Xx, Xy, Xn, Yx, Yy, Zt, Zn; };
+Basis milne_basis(const CellState &c)
+{
+  Basis b;
+  double sinhL = c.tau * c.un / c.utperp, coshL = c.ut / c.utperp;
+  b.Xt = c.uperp * coshL; b.Xx = 1; b.Xy = 0; b.Xn = c.uperp * sinhL / c.tau;
+  b.Yx = 0; b.Yy = 1; b.Zt = sinhL; b.Zn = coshL / c.tau;
+  if (c.uperp > 1.e-5) { b.Xx = c.utperp * c.ux / c.uperp; b.Xy = c.utperp * c.uy / c.uperp; b.Yx = -c.uy / c.uperp; b.Yy = c.ux / c.uperp; }
+  return b;
+}
+struct PiLRF { double xx, xy, xz, yy, yz, zz; };
+PiLRF boost_pi(const CellState &c, const Basis &b)
+{
+  PiLRF l;
+  double tau2 = c.tau2, Xt = b.Xt, Xx = b.Xx, Xy = b.Xy, Xn = b.Xn, Yx = b.Yx, Yy = b.Yy, Zt = b.Zt, Zn = b.Zn;
+  l.xx = c.pitt * Xt * Xt + c.pixx * Xx * Xx + c.piyy * Xy * Xy + tau2 * tau2 * c.pinn * Xn * Xn
+       + 2.0 * (-Xt * (c.pitx * Xx + c.pity * Xy) + c.pixy * Xx * Xy + tau2 * Xn * (c.pixn * Xx + c.piyn * Xy - c.pitn * Xt));
+  l.xy = Yx * (-c.pitx * Xt + c.pixx * Xx + c.pixy * Xy + tau2 * c.pixn * Xn) + Yy * (-c.pity * Xt + c.pixy * Xx + c.piyy * Xy + tau2 * c.piyn * Xn);
+  l.xz = Zt * (c.pitt * Xt - c.pitx * Xx - c.pity * Xy - tau2 * c.pitn * Xn) - tau2 * Zn * (c.pitn * Xt - c.pixn * Xx - c.piyn * Xy - tau2 * c.pinn * Xn);
+  l.yy = c.pixx * Yx * Yx + 2.0 * c.pixy * Yx * Yy + c.piyy * Yy * Yy;
+  l.yz = -Zt * (c.pitx * Yx + c.pity * Yy) + tau2 * Zn * (c.pixn * Yx + c.piyn * Yy);
+  l.zz = -(l.xx + l.yy);
+  return l;
+}
+
+struct Grids {
+  std::vector<double> cosphi, sinphi, phiw, pT, pTw, y, eta, etaw;
+  int ny, neta;
+  Grids(const cf_params *p, const cf_inputs *in)
+  {
+    for (int i = 0; i < in->n_phi; i++) { cosphi.push_back(cos(in->phi[i])); sinphi.push_back(sin(in->phi[i])); phiw.push_back(in->phi_w ? in->phi_w[i] : 1.0); }
+    for (int i = 0; i < in->n_pT; i++) { pT.push_back(in->pT[i]); pTw.push_back(in->pT_w ? in->pT_w[i] : 1.0); }
+    if (p->dimension == 2) {                   // MomentumSpectra.cpp:73-82
+      y.assign(1, 0.0); ny = 1; neta = in->n_eta;
+      eta.assign(in->eta, in->eta + in->n_eta); etaw.assign(in->eta_w, in->eta_w + in->n_eta);
+    } else {                                   // :83-91 (eta value taken from the cell)
+      y.assign(in->y, in->y + in->n_y); ny = in->n_y; neta = 1;
+      eta.assign(1, 0.0); etaw.assign(1, 1.0);
+    }
+  }
+};
+
+// does_feqmod_breakdown with fast = 0 (EmissionFunction.cpp:65-109)
+bool does_feqmod_breakdown(const cf_inputs *in, double mass_pion0, double T, double F, double bulkPi, double betabulk, double detA,
+                           double detA_min, double z, int df_mode)
+{
+  if (df_mode == 3) {
+    const double *r1 = in->gla_root + 1 * in->n_gla, *w1 = in->gla_weight + 1 * in->n_gla;
+    const double *r2 = in->gla_root + 2 * in->n_gla, *w2 = in->gla_weight + 2 * in->n_gla;
+    double mbar_pion0 = mass_pion0 / T;
+    double neq_fact = T * T * T / two_pi2_hbarC3, J20_fact = T * neq_fact;
+    double neq_pion0 = neq_fact * GaussThermal(neq_int, r1, w1, in->n_gla, mbar_pion0, 0., 0., -1.);
+    double J20_pion0 = J20_fact * GaussThermal(J20_int, r2, w2, in->n_gla, mbar_pion0, 0., 0., -1.);
+    double dn_pion0 = bulkPi * (neq_pion0 + J20_pion0 * F / T / T) / betabulk;     // is_linear_pion0_density_negative, :52-63
+    bool negative = (neq_pion0 + dn_pion0 < 0.0);
+    if (detA <= detA_min || negative) return true;
+  } else if (df_mode == 4) {
+    if (detA <= detA_min || z < 0.0) return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// calculate_dN_pTdpTdphidy, df_mode 1,2 (MomentumSpectra.cpp:32-415)
+// ---------------------------------------------------------------------------------------------------------------
+int spectra_df(const cf_params *p, const cf_inputs *in, double *out, cf_stats *st)
+{
+  const double prefactor = pow(2.0 * M_PI * hbarC, -3);
+  Grids g(p, in);
+  DfData dfd(p, in);
+  const int npart = in->n_species, npT = in->n_pT, nphi = in->n_phi, ny = g.ny;
+  for (long icell = 0; icell < in->n_cells; icell++) {
+    CellState c;
+    if (!load_cell(p, in, icell, false, true, &c, true)) { st->cells_skipped++; continue; }
+    if (p->dimension == 3) g.eta[0] = c.eta;
+    double tau2_un = c.tau2 * c.un;
+    double tau2_pitn = c.tau2 * c.pitn, tau2_pixn = c.tau2 * c.pixn, tau2_piyn = c.tau2 * c.piyn;
+    double tau4_pinn = c.tau2 * c.tau2 * c.pinn, tau2_Vn = c.tau2 * c.Vn;
+    DfCoeff df;
+    if (!dfd.evaluate(c.T, c.muB, c.E, c.P, c.bulkPi, &df)) { st->cells_out_of_table++; return 3; }
+    double shear_coeff = 0, bulk0 = 0, bulk1 = 0, bulk2 = 0, diff0 = 0, diff1 = 0;
+    if (p->df_mode == 1) {
+      shear_coeff = 1.0 / df.shear14_coeff;
+      bulk0 = (df.c0 - df.c2) * c.bulkPi; bulk1 = df.c1 * c.bulkPi; bulk2 = (4. * df.c2 - df.c0) * c.bulkPi;
+      diff0 = df.c3; diff1 = df.c4;
+    } else {
+      shear_coeff = 0.5 / (df.betapi * c.T);
+      bulk0 = df.F / (c.T * c.T * df.betabulk) * c.bulkPi; bulk1 = df.G / df.betabulk * c.bulkPi;
+      bulk2 = c.bulkPi / (3.0 * c.T * df.betabulk);
+      diff0 = c.baryon_enthalpy_ratio / df.betaV; diff1 = 1.0 / df.betaV;
+    }
+    for (int ipart = 0; ipart < npart; ipart++) {
+      double mass = in->mass[ipart], mass_squared = mass * mass, sign = in->sign[ipart], degeneracy = in->degeneracy[ipart];
+      double baryon = in->baryon[ipart], chem = baryon * c.alphaB;
+      for (int ipT = 0; ipT < npT; ipT++) {
+        double pT = g.pT[ipT], mT = sqrt(mass_squared + pT * pT), mT_over_tau = mT / c.tau;
+        for (int iphip = 0; iphip < nphi; iphip++) {
+          double px = pT * g.cosphi[iphip], py = pT * g.sinphi[iphip];
+          for (int iy = 0; iy < ny; iy++) {
+            double y = g.y[iy], eta_integral = 0.0;
+            for (int ieta = 0; ieta < g.neta; ieta++) {
+              double eta = g.eta[ieta], eta_weight = g.etaw[ieta];
+              double sinhyeta = sinh(y - eta), coshyeta = sqrt(1.0 + sinhyeta * sinhyeta);
+              double pt = mT * coshyeta, pn = mT_over_tau * sinhyeta;
+              double pdotdsigma = pt * c.dat + px * c.dax + py * c.day + pn * c.dan;
+              if (p->outflow && pdotdsigma <= 0.0) continue;
+              double E = pt * c.ut - px * c.ux - py * c.uy - pn * tau2_un;
+              double feq = 1.0 / (exp(E / c.T - chem) + sign);
+              double feqbar = 1.0 - sign * feq;
+              double pimunu_pmu_pnu = c.pitt * pt * pt + c.pixx * px * px + c.piyy * py * py + tau4_pinn * pn * pn
+                  + 2.0 * (-(c.pitx * px + c.pity * py) * pt + c.pixy * px * py + pn * (tau2_pixn * px + tau2_piyn * py - tau2_pitn * pt));
+              double Vmu_pmu = c.Vt * pt - c.Vx * px - c.Vy * py - tau2_Vn * pn;
+              double dfv;
+              if (p->df_mode == 1) {
+                double df_shear = shear_coeff * pimunu_pmu_pnu;
+                double df_bulk = bulk0 * mass_squared + (bulk1 * baryon + bulk2 * E) * E;
+                double df_diff = (diff0 * baryon + diff1 * E) * Vmu_pmu;
+                dfv = feqbar * (df_shear + df_bulk + df_diff);
+              } else {
+                double df_shear = shear_coeff * pimunu_pmu_pnu / E;
+                double df_bulk = bulk0 * E + bulk1 * baryon + bulk2 * (E - mass_squared / E);
+                double df_diff = (diff0 - diff1 * baryon / E) * Vmu_pmu;
+                dfv = feqbar * (df_shear + df_bulk + df_diff);
+              }
+              if (p->regulate_deltaf) dfv = fmax(-1.0, fmin(dfv, 1.0));
+              eta_integral += eta_weight * pdotdsigma * feq * (1.0 + dfv);
+            }
+            out[iy + (long)ny * (iphip + (long)nphi * (ipT + (long)npT * ipart))] += prefactor * degeneracy * eta_integral;
+          }
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// calculate_dN_pTdpTdphidy_feqmod, df_mode 3,4 (MomentumSpectra.cpp:419-1044)
+// ---------------------------------------------------------------------------------------------------------------
+int spectra_feqmod(const cf_params *p, const cf_inputs *in, double *out, cf_stats *st)
+{
+  const double prefactor = pow(2.0 * M_PI * hbarC, -3);
+  Grids g(p, in);
+  DfData dfd(p, in);
+  const int npart = in->n_species, npT = in->n_pT, nphi = in->n_phi, ny = g.ny, pts = in->n_gla;
+  const double *r1 = in->gla_root + 1 * pts, *w1 = in->gla_weight + 1 * pts, *r2 = in->gla_root + 2 * pts, *w2 = in->gla_weight + 2 * pts;
+  const double detA_min = p->deta_min;
+  for (long icell = 0; icell < in->n_cells; icell++) {
+    CellState c;
+    if (!load_cell(p, in, icell, false, true, &c)) { st->cells_skipped++; continue; }
+    if (p->dimension == 3) g.eta[0] = c.eta;
+    double T = c.T, P = c.P, E = c.E, bulkPi = c.bulkPi, tau2 = c.tau2;
+    if (p->df_mode == 4) {                       // :603-615
+      if (bulkPi < -P) bulkPi = -(1.0 - 1.e-5) * P;
+      else if (bulkPi / P > in->ptb_x_max) bulkPi = P * (in->ptb_x_max - 1.e-5);
+    }
+    double zt = c.tau * c.un / c.utperp, zn = c.ut / (c.tau * c.utperp);
+    double pl = P + bulkPi + zt * zt * c.pitt + tau2 * tau2 * zn * zn * c.pinn + 2. * tau2 * zt * zn * c.pitn;
+    if (pl < 0) st->cells_pl_negative++;
+    DfCoeff df;
+    if (!dfd.evaluate(T, c.muB, E, P, bulkPi, &df)) { st->cells_out_of_table++; return 3; }
+    Basis b = milne_basis(c);
+    PiLRF pl_ = boost_pi(c, b);
+    double T_mod = T, alphaB_mod = c.alphaB;
+    if (p->df_mode == 3) { T_mod = T + bulkPi * df.F / df.betabulk; alphaB_mod = c.alphaB + bulkPi * df.G / df.betabulk; }
+    double shear_coeff = 0.5 / (df.betapi * T), bulk0 = df.F / (T * T * df.betabulk), bulk1 = df.G / df.betabulk, bulk2 = 1.0 / (3.0 * T * df.betabulk);
+    double shear_mod = 0.5 / df.betapi, bulk_mod = bulkPi / (3.0 * df.betabulk);
+    if (p->df_mode == 4) bulk_mod = df.lambda;
+    double Axx = 1.0 + pl_.xx * shear_mod + bulk_mod, Axy = pl_.xy * shear_mod, Axz = pl_.xz * shear_mod;
+    double Ayy = 1.0 + pl_.yy * shear_mod + bulk_mod, Ayz = pl_.yz * shear_mod, Azz = 1.0 + pl_.zz * shear_mod + bulk_mod;
+    double detA = Axx * (Ayy * Azz - Ayz * Ayz) - Axy * (Axy * Azz - Ayz * Axz) + Axz * (Axy * Ayz - Ayy * Axz);
+    double detA_bulk_two_thirds = pow(1.0 + bulk_mod, 2);
+    double A[9] = {Axx, Axy, Axz, Axy, Ayy, Ayz, Axz, Ayz, Azz}, A_inv[9];
+    lu_invert3(A, A_inv);
+    double neq_fact = T * T * T / two_pi2_hbarC3, dn_fact = bulkPi / df.betabulk, J20_fact = T * neq_fact, N10_fact = neq_fact;
+    double nmod_fact = T_mod * T_mod * T_mod / two_pi2_hbarC3;
+    bool breaks = does_feqmod_breakdown(in, p->mass_pion0, T, df.F, bulkPi, df.betabulk, detA, detA_min, df.z, p->df_mode);
+    if (breaks) st->cells_breakdown++;
+    double eta_scale = 1.0;
+    if (detA > detA_min && p->dimension == 2) eta_scale = detA / detA_bulk_two_thirds;
+    for (int ipart = 0; ipart < npart; ipart++) {
+      double mass = in->mass[ipart], mass2 = mass * mass, sign = in->sign[ipart], degeneracy = in->degeneracy[ipart], baryon = in->baryon[ipart];
+      double chem = baryon * c.alphaB, chem_mod = baryon * alphaB_mod;
+      double renorm = 1.0;
+      if (p->include_bulk_deltaf) {
+        if (p->df_mode == 3) {                   // :795-811
+          double mbar = mass / T, mbar_mod = mass / T_mod;
+          double neq = neq_fact * degeneracy * GaussThermal(neq_int, r1, w1, pts, mbar, c.alphaB, baryon, sign);
+          double N10 = baryon * N10_fact * degeneracy * GaussThermal(J10_int, r1, w1, pts, mbar, c.alphaB, baryon, sign);
+          double J20 = J20_fact * degeneracy * GaussThermal(J20_int, r2, w2, pts, mbar, c.alphaB, baryon, sign);
+          double n_linear = neq + dn_fact * (neq + N10 * df.G + J20 * df.F / T / T);
+          double n_mod = nmod_fact * degeneracy * GaussThermal(neq_int, r1, w1, pts, mbar_mod, alphaB_mod, baryon, sign);
+          renorm = n_linear / n_mod;
+        } else renorm = df.z;
+      }
+      if (p->dimension == 2) renorm /= detA_bulk_two_thirds; else renorm /= detA;
+      if (std::isnan(renorm) || std::isinf(renorm)) continue;
+      for (int ipT = 0; ipT < npT; ipT++) {
+        double pT = g.pT[ipT], mT = sqrt(mass2 + pT * pT), mT_over_tau = mT / c.tau;
+        for (int iphip = 0; iphip < nphi; iphip++) {
+          double px = pT * g.cosphi[iphip], py = pT * g.sinphi[iphip];
+          for (int iy = 0; iy < ny; iy++) {
+            double y = g.y[iy], eta_integral = 0.0;
+            for (int ieta = 0; ieta < g.neta; ieta++) {
+              double eta = g.eta[ieta], eta_weight = g.etaw[ieta];
+              bool narrow = false;
+              if (p->dimension == 3 && !breaks) if (detA < 0.01 && fabs(y - eta) < detA) narrow = true;
+              double pdotdsigma, f;
+              if (breaks || narrow) {
+                double pt = mT * cosh(y - eta), pn = mT_over_tau * sinh(y - eta), tau2_pn = tau2 * pn;
+                pdotdsigma = eta_weight * (pt * c.dat + px * c.dax + py * c.day) + pn * c.dan;
+                if (p->outflow && pdotdsigma <= 0.0) continue;
+                double pdotu = pt * c.ut - px * c.ux - py * c.uy - tau2_pn * c.un;
+                double pimunu_pmu_pnu = c.pitt * pt * pt + c.pixx * px * px + c.piyy * py * py + c.pinn * tau2_pn * tau2_pn
+                    + 2.0 * (-(c.pitx * px + c.pity * py) * pt + c.pixy * px * py + tau2_pn * (c.pixn * px + c.piyn * py - c.pitn * pt));
+                double dfv;
+                if (p->df_mode == 3) {
+                  double feq = 1.0 / (exp(pdotu / T - chem) + sign), feqbar = 1.0 - sign * feq;
+                  double Vmu_pmu = c.Vt * pt - c.Vx * px - c.Vy * py - c.Vn * tau2_pn;
+                  double df_shear = shear_coeff * pimunu_pmu_pnu / pdotu;
+                  double df_bulk = (bulk0 * pdotu + bulk1 * baryon + bulk2 * (pdotu - mass2 / pdotu)) * bulkPi;
+                  double df_diff = (c.baryon_enthalpy_ratio - baryon / pdotu) * Vmu_pmu / df.betaV;
+                  dfv = feqbar * (df_shear + df_bulk + df_diff);
+                  if (p->regulate_deltaf) dfv = fmax(-1.0, fmin(dfv, 1.0));
+                  f = feq * (1.0 + dfv);
+                } else {
+                  double feq = 1.0 / (exp(pdotu / T) + sign), feqbar = 1.0 - sign * feq;
+                  double df_shear = feqbar * shear_coeff * pimunu_pmu_pnu / pdotu;
+                  double df_bulk = df.delta_z - 3.0 * df.delta_lambda + feqbar * df.delta_lambda * (pdotu - mass2 / pdotu) / T;
+                  dfv = df_shear + df_bulk;
+                  if (p->regulate_deltaf) dfv = fmax(-1.0, fmin(dfv, 1.0));
+                  f = feq * (1.0 + dfv);
+                }
+              } else {
+                double pt = mT * cosh(y - eta_scale * eta), pn = mT_over_tau * sinh(y - eta_scale * eta), tau2_pn = tau2 * pn;
+                pdotdsigma = eta_weight * (pt * c.dat + px * c.dax + py * c.day) + pn * c.dan;
+                if (p->outflow && pdotdsigma <= 0.0) continue;
+                double pLRF[3] = {-b.Xt * pt + b.Xx * px + b.Xy * py + b.Xn * tau2_pn, b.Yx * px + b.Yy * py, -b.Zt * pt + b.Zn * tau2_pn};
+                double pmod[3];
+                for (int i = 0; i < 3; i++) pmod[i] = A_inv[3 * i] * pLRF[0] + A_inv[3 * i + 1] * pLRF[1] + A_inv[3 * i + 2] * pLRF[2];
+                for (int it = 0; it < 5; it++) {   // iterative refinement, :959-971
+                  double prev[3] = {pmod[0], pmod[1], pmod[2]}, back[3], dp[3];
+                  for (int i = 0; i < 3; i++) back[i] = A[3 * i] * prev[0] + A[3 * i + 1] * prev[1] + A[3 * i + 2] * prev[2];
+                  for (int i = 0; i < 3; i++) dp[i] = pLRF[i] - back[i];
+                  if (sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) <= 1.e-16) break;
+                  for (int i = 0; i < 3; i++) pmod[i] = prev[i] + (A_inv[3 * i] * dp[0] + A_inv[3 * i + 1] * dp[1] + A_inv[3 * i + 2] * dp[2]);
+                }
+                double E_mod = sqrt(mass2 + pmod[0] * pmod[0] + pmod[1] * pmod[1] + pmod[2] * pmod[2]);
+                f = fabs(renorm) / (exp(E_mod / T_mod - chem_mod) + sign);
+              }
+              eta_integral += pdotdsigma * f;
+            }
+            out[iy + (long)ny * (iphip + (long)nphi * (ipT + (long)npT * ipart))] += prefactor * degeneracy * eta_integral;
+          }
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int cf_oracle_spectra(const cf_params *p, const cf_inputs *in, double *out, cf_stats *st)
+{
+  cf_stats local;
+  if (!st) st = &local;
+  memset(st, 0, sizeof(*st));
+  const int ny = (p->dimension == 3) ? in->n_y : 1;
+  memset(out, 0, sizeof(double) * (size_t)in->n_species * in->n_pT * in->n_phi * ny);
+  switch (p->df_mode) {
+    case 1: case 2: return spectra_df(p, in, out, st);
+    case 3: case 4: return spectra_feqmod(p, in, out, st);
+    default: return 4;
+  }
+}
+
+extern "C" int cf_oracle_dndx(const cf_params *, const cf_inputs *, double *, double *, double *, cf_stats *) { return 4; }
+extern "C" int cf_oracle_total_yield(const cf_params *, const cf_inputs *, double *) { return 4; }
+extern "C" int cf_oracle_cell_yields(const cf_params *, const cf_inputs *, double *, double *) { return 4; }

@@ -1,0 +1,46 @@
+"""Parity cases shared by the golden-vector generator and the tests: (name, surface spec, parameters, species,
+tables).  Sizes are chosen so the reference finishes each in about a second."""
+from __future__ import annotations
+
+from is3d_b200 import synthetic
+
+BASE = dict(operation=1, mode=1, hrg_eos=2, dimension=3, include_baryon=0, include_bulk_deltaf=1,
+            include_shear_deltaf=1, include_baryondiff_deltaf=0, regulate_deltaf=0, outflow=0)
+
+
+def _p(**kw):
+    d = dict(BASE)
+    d.update(kw)
+    return d
+
+
+# name -> dict(surface=(kind, kwargs), params, chosen, tables)
+SPECTRA_CASES = {
+    # BASELINE.json config 1: the bundled static cell, pikp, Grad, UrQMD, 2+1d
+    "bundled_m1_2d": dict(surface=("bundled", {}), params=_p(df_mode=1, hrg_eos=1, dimension=2), chosen="pikp"),
+    "s3d_m1": dict(surface=("s3d", dict(n=300, seed=12345)), params=_p(df_mode=1), chosen="pikp"),
+    "s3d_m2": dict(surface=("s3d", dict(n=300, seed=12345)), params=_p(df_mode=2), chosen="pikp"),
+    "s3d_m2_phi48_reg_outflow": dict(surface=("s3d", dict(n=120, seed=5)), params=_p(df_mode=2, hrg_eos=1, regulate_deltaf=1, outflow=1),
+                                     chosen="pikp", tables=dict(phi_table="phi_table_48pt.dat")),
+    # BASELINE.json config 2 in miniature: RTA Chapman-Enskog with bulk + shear + baryon diffusion
+    "s3d_m2_baryon": dict(surface=("s3d", dict(n=300, seed=7, baryon=True)),
+                          params=_p(df_mode=2, include_baryon=1, include_baryondiff_deltaf=1), chosen="pikp"),
+    "s3d_m1_baryon": dict(surface=("s3d", dict(n=300, seed=7, baryon=True)),
+                          params=_p(df_mode=1, include_baryon=1, include_baryondiff_deltaf=1), chosen="pikp"),
+    "s3d_m2_baryon_nodiff": dict(surface=("s3d", dict(n=200, seed=8, baryon=True)),
+                                 params=_p(df_mode=2, include_baryon=1, include_baryondiff_deltaf=0), chosen="pikp"),
+    "s2d_m1_phi48": dict(surface=("s3d", dict(n=100, seed=3, dimension=2)), params=_p(df_mode=1, hrg_eos=1, dimension=2),
+                         chosen="pikp", tables=dict(phi_table="phi_table_48pt.dat")),
+    "s2d_m2": dict(surface=("s3d", dict(n=150, seed=4, dimension=2)), params=_p(df_mode=2, dimension=2), chosen="pikp"),
+    "s3d_m1_noshear_nobulk": dict(surface=("s3d", dict(n=100, seed=9)), params=_p(df_mode=1, include_bulk_deltaf=0, include_shear_deltaf=0), chosen="pikp"),
+    # ragged sizes around the 256-cell tile / chunk boundaries, all SMASH species on a few cells
+    "s3d_m2_smash_17cells": dict(surface=("s3d", dict(n=17, seed=11)), params=_p(df_mode=2), chosen="smash"),
+    "s3d_m1_257cells": dict(surface=("s3d", dict(n=257, seed=12)), params=_p(df_mode=1), chosen="pikp"),
+}
+
+
+def make_surface(spec):
+    kind, kw = spec
+    if kind == "bundled":
+        return synthetic.bundled_cell()
+    return synthetic.s3d(**kw)

@@ -1,0 +1,89 @@
+"""GPU parity of the continuous Cooper-Frye spectra (K1: df_mode 1, 2) through the C ABI against the golden
+vectors produced by the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+import cases
+import harness
+
+pytestmark = pytest.mark.gpu
+
+DF_CASES = [n for n, c in cases.SPECTRA_CASES.items() if c["params"]["df_mode"] in (1, 2)]
+
+
+@pytest.mark.parametrize("name", DF_CASES)
+def test_spectra_df_matches_reference(libs, tmp_path, name):
+    case = cases.SPECTRA_CASES[name]
+    surf, ref = harness.load_golden(name)
+    with harness.open_session(str(tmp_path), case, surf) as h:
+        got, st = h.abi_spectra()
+        worst = harness.assert_spectra_close(got, ref, what=name)
+        assert st.cells_total == len(surf["tau"])
+        assert st.kernel_launches >= 3
+        # same call again: deterministic reduction => bit-identical
+        again, _ = h.abi_spectra()
+        np.testing.assert_array_equal(got, again)
+    print(f"{name}: max rel err {worst:.3e}")
+
+
+def test_known_answer_static_cell(libs, tmp_path):
+    """Ideal static cell: dN = g/(2 pi hbarc)^3 mT cosh(eta) dsigma_tau feq, and the reference's own
+    printed value for pi+ at pT = 0 (1.37049908e+01)."""
+    case = cases.SPECTRA_CASES["bundled_m1_2d"]
+    surf, ref = harness.load_golden("bundled_m1_2d")
+    with harness.open_session(str(tmp_path), case, surf) as h:
+        got, _ = h.abi_spectra()
+    assert abs(got[0, 0, 0, 0] / 1.37049908e+01 - 1) < 1e-8
+    harness.assert_spectra_close(got, ref, what="bundled")
+
+
+def test_linearity_in_cells(libs, tmp_path):
+    """Size-independent property: spectra are additive over cells -- two halves sum to the whole, and a
+    surface with every cell duplicated gives exactly twice the spectra (same summation tree per bin is not
+    guaranteed, so compare at 1e-12)."""
+    case = cases.SPECTRA_CASES["s3d_m2"]
+    surf, ref = harness.load_golden("s3d_m2")
+    n = len(surf["tau"])
+    with harness.open_session(str(tmp_path), case, surf) as h:
+        whole, _ = h.abi_spectra()
+        a = {k: v[: n // 3] for k, v in surf.items()}
+        b = {k: v[n // 3:] for k, v in surf.items()}
+        h.abi_set_surface(a)
+        sa, _ = h.abi_spectra()
+        h.abi_set_surface(b)
+        sb, _ = h.abi_spectra()
+        h.abi_set_surface({k: np.concatenate([v, v]) for k, v in surf.items()})
+        twice, _ = h.abi_spectra()
+    harness.assert_spectra_close(sa + sb, whole, rtol=1e-11, what="halves")
+    harness.assert_spectra_close(twice, 2.0 * whole, rtol=1e-11, what="duplicated")
+
+
+def test_skipped_cells_and_empty_surface(libs, tmp_path):
+    """Cells with u.dsigma <= 0 contribute nothing (reference MomentumSpectra.cpp:132); an empty surface gives zeros."""
+    case = cases.SPECTRA_CASES["s3d_m1"]
+    surf, ref = harness.load_golden("s3d_m1")
+    flipped = {k: v.copy() for k, v in surf.items()}
+    for k in ("dat", "dax", "day", "dan"):
+        flipped[k] = -flipped[k]
+    both = {k: np.concatenate([surf[k], flipped[k]]) for k in surf}
+    with harness.open_session(str(tmp_path), case, surf) as h:
+        h.abi_set_surface(both)
+        got, st = h.abi_spectra()
+        assert st.cells_skipped == len(surf["tau"])
+        harness.assert_spectra_close(got, ref, what="skipped")
+        h.abi_set_surface({k: v[:0] for k, v in surf.items()})
+        zero, _ = h.abi_spectra()
+        assert np.all(zero == 0.0)
+
+
+def test_out_of_table_cell_is_an_error(libs, tmp_path):
+    """T outside [0.1, 0.2] GeV aborts the reference (GSL domain error); the ABI returns IS3D_ERR_TABLE_RANGE."""
+    from is3d_b200 import Is3dError
+    case = cases.SPECTRA_CASES["s3d_m1"]
+    surf, _ = harness.load_golden("s3d_m1")
+    bad = {k: v.copy() for k, v in surf.items()}
+    bad["T"][5] = 0.25
+    with harness.open_session(str(tmp_path), case, surf) as h:
+        h.abi_set_surface(bad)
+        with pytest.raises(Is3dError, match="status 3"):
+            h.abi_spectra()
