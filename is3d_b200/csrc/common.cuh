@@ -45,6 +45,9 @@ IS3D_HD int64_t as_int64(double d)
 #endif
 }
 
+// NaN or +-inf (portable between nvcc and g++)
+IS3D_HD bool not_finite(double x) { return !(fabs(x) <= 1.7976931348623157e308); }
+
 // exp(x) for the Bose/Fermi factor, kept entirely in the FP64 FMA pipe: Cody-Waite reduction x = n ln2 + r,
 // |r| <= ln2/2, degree-11 polynomial (Chebyshev-node fit, max relative error 1.7e-17 before rounding), exponent
 // patched by integer add.  x is clamped to [-700, 700] so the result stays normal: 1/(e^700 + s) ~ 1e-304 stands

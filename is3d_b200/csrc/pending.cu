@@ -7,7 +7,6 @@ static is3d_status pending(is3d_ctx *ctx, const char *what)
   ctx->set_error(std::string(what) + ": CUDA kernel not implemented in this build");
   return IS3D_ERR_UNSUPPORTED;
 }
-is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *, is3d_stats *) { return pending(ctx, "spectra df_mode 3/4"); }
 is3d_status run_spectra_famod(is3d_ctx *ctx, double *, is3d_stats *) { return pending(ctx, "spectra df_mode 5"); }
 is3d_status run_dndx(is3d_ctx *ctx, double *, double *, double *, is3d_stats *) { return pending(ctx, "dN/dX"); }
 is3d_status run_total_yield(is3d_ctx *ctx, double *, is3d_stats *) { return pending(ctx, "total yield"); }

@@ -156,7 +156,7 @@ IS3D_HD double df_eval(const DfItem &it, const DfBin &b)
       dfv = fma(fma(-it.G1 * b.baryon, r, it.G0), Vp, dfv);
     }
   }
-  double df = feqbar * dfv;
+  double df = fma(feqbar, dfv, it.pad);   // pad = 0 except for the PTB fallback's additive delta_z - 3 delta_lambda
   if (REGULATE) df = fmax(-1.0, fmin(df, 1.0));
   double f = fma(feq, df, feq);
   double contrib = pds * f;

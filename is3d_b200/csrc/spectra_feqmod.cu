@@ -1,0 +1,308 @@
+// K2: continuous Cooper-Frye spectra for df_mode 3 (PTM) and 4 (PTB) modified equilibrium distributions on sm_100a.
+// Replaces EmissionFunctionArray::calculate_dN_pTdpTdphidy_feqmod (reference src/cpp/MomentumSpectra.cpp:419-1044).
+//
+// Schedule (same output-stationary design as K1, see spectra_df.cu):
+//   1. feqmod_setup_kernel   one thread per cell: LRF boost, A_ij, refined inverse, breakdown test (two 32-point
+//                            Gauss-Laguerre sums for PTM), linear-df fallback coefficients -> 55-double cell pack
+//   2. feqmod_renorm_kernel  PTM with bulk only: one thread per (cell, species): n_linear / n_mod from four
+//                            32-point Gauss-Laguerre sums -> renorm[cell][species]
+//   3. feqmod_spectra_kernel blocks = (species x pT slice, (y, phi), cell chunk); per 256-cell tile every thread
+//                            builds one cell's item for the block's (y, phi); the inner loop takes a warp-uniform
+//                            branch per item: modified distribution (4 FMA + sqrt + exp + rcp) or linear-df fallback
+//   4. reduce_partials_kernel (shared with K1)
+#include "ctx.h"
+#include "spectra_feqmod.cuh"
+
+namespace is3d {
+
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int64_t total, double *__restrict__ out);
+is3d_status build_bin_arrays(is3d_ctx *ctx, const double **mT, const double **pT, const double **m2, const double **baryon,
+                             const double **sign, const double **deg);
+void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
+                   int64_t *cells_per_chunk);
+
+namespace {
+
+constexpr int kTile = 256;
+constexpr int kThreads = 256;
+constexpr int kBins = 3;
+
+__global__ void feqmod_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, DfTables tb, FeqmodFlags fl,
+                                    const double *__restrict__ gla_root, const double *__restrict__ gla_weight, int gla_pts,
+                                    double *__restrict__ pack, int64_t stride, unsigned long long *counters)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Cell c = load_cell(surf, begin + i, fl.include_baryon != 0);
+  double p[FP_SIZE];
+  int st = feqmod_setup_cell(c, tb, fl, gla_root, gla_weight, gla_pts, p);
+#pragma unroll
+  for (int k = 0; k < FP_SIZE; k++) pack[k * stride + i] = p[k];
+  if (st == CELL_SKIPPED) { atomicAdd(&counters[0], 1ull); return; }
+  if (st == CELL_OUT_OF_TABLE) { atomicAdd(&counters[1], 1ull); return; }
+  if (st & CELL_BREAKDOWN) { atomicAdd(&counters[2], 1ull); atomicMax(&counters[4], (unsigned long long)(begin + i + 1)); }
+  if (st & CELL_PL_NEGATIVE) { atomicAdd(&counters[3], 1ull); atomicMax(&counters[5], (unsigned long long)(begin + i + 1)); }
+}
+
+__global__ void feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int ns,
+                                     const double *__restrict__ mass, const double *__restrict__ deg,
+                                     const double *__restrict__ baryon, const double *__restrict__ sign,
+                                     const double *__restrict__ gla_root, const double *__restrict__ gla_weight, int gla_pts,
+                                     double *__restrict__ renorm)
+{
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count * ns) return;
+  int64_t cell = idx / ns;
+  int s = (int)(idx - cell * ns);
+  double r = 0.0;
+  if (pack[DP_VALID * stride + cell] != 0.0) {
+    auto pk = [&](int k) { return pack[k * stride + cell]; };
+    r = feqmod_renorm_ptm(pk, mass[s], deg[s], baryon[s], sign[s], gla_root, gla_weight, gla_pts);
+  }
+  renorm[idx] = r;
+}
+
+struct FeqGrid {
+  const double *mT, *pT, *m2, *baryon, *sign, *deg;
+  int nbins, NpT, ns;
+  int Ny, Nphi, Neta, dimension;
+  const double *yv, *cosphi, *sinphi, *etav, *etaw;
+};
+
+union ItemSlot {
+  DfItem lin;
+  FeqmodItem mod;
+  __device__ ItemSlot() {}
+};
+
+template <bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM, int R>
+__global__ void __launch_bounds__(kThreads, 2)
+feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk,
+                      const double *__restrict__ renorm, FeqGrid g, double *__restrict__ partial, int64_t total)
+{
+  __shared__ ItemSlot items[kTile];
+  __shared__ int item_cell[kTile];
+  __shared__ unsigned char item_linear[kTile];
+  __shared__ int warp_count[kThreads / 32];
+
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;
+  const double yval = g.yv[iy], cphi = g.cosphi[iphi], sphi = g.sinphi[iphi];
+
+  DfBin bin[R];
+  double acc[R];
+  int jbin[R], sp[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    int j = blockIdx.x * (kThreads * R) + r * kThreads + t;
+    jbin[r] = j;
+    int jj = j < g.nbins ? j : g.nbins - 1;
+    sp[r] = jj / g.NpT;
+    double mT = g.mT[jj], pT = g.pT[jj];
+    bin[r].mT = mT; bin[r].pT = pT; bin[r].mT2 = mT * mT; bin[r].mTpT = mT * pT; bin[r].pT2 = pT * pT;
+    bin[r].m2 = g.m2[jj]; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
+    acc[r] = 0.0;
+  }
+
+  const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
+  int64_t chunk_end = chunk_begin + cells_per_chunk;
+  if (chunk_end > ncells) chunk_end = ncells;
+
+  for (int64_t tile = chunk_begin; tile < chunk_end; tile += kTile) {
+    const int64_t cell = tile + t;
+    const bool valid = (cell < chunk_end) && (pack[DP_VALID * stride + cell] != 0.0);
+    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
+    for (int ie = 0; ie < g.Neta; ie++) {
+      __syncthreads();
+      if (lane == 0) warp_count[warp] = __popc(ballot);
+      __syncthreads();
+      int base = 0, n_items = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; w++) {
+        int c = warp_count[w];
+        if (w < warp) base += c;
+        n_items += c;
+      }
+      if (valid) {
+        auto pk = [&](int k) { return pack[k * stride + cell]; };
+        double eta, w;
+        if (g.dimension == 3) { eta = pk(DP_ETA); w = 1.0; }
+        else { eta = g.etav[ie]; w = g.etaw[ie]; }
+        bool linear = pk(FP_BREAKDOWN) != 0.0;
+        if (g.dimension == 3 && !linear) {                       // narrow (y - eta) window, MomentumSpectra.cpp:865-871
+          double detA = pk(FP_DETA);
+          if (detA < 0.01 && fabs(yval - eta) < detA) linear = true;
+        }
+        const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+        if (linear) {
+          double d = yval - eta;
+          items[slot].lin = feqmod_make_linear_item(pk, sinh(d), cosh(d), cphi, sphi, w);
+        } else {
+          double d = yval - pk(FP_ETA_SCALE) * eta;
+          items[slot].mod = feqmod_make_item(pk, sinh(d), cosh(d), cphi, sphi, w);
+        }
+        item_linear[slot] = linear ? 1 : 0;
+        item_cell[slot] = (int)(cell - 0);   // index inside this pass's pack / renorm arrays
+      }
+      __syncthreads();
+#pragma unroll 1
+      for (int k = 0; k < n_items; k++) {
+        double rn[R];
+        if (SPECIES_RENORM) {
+          const double *row = renorm + (int64_t)item_cell[k] * g.ns;
+#pragma unroll
+          for (int r = 0; r < R; r++) rn[r] = row[sp[r]];
+        }
+        if (!item_linear[k]) {
+          const FeqmodItem it = items[k].mod;
+#pragma unroll
+          for (int r = 0; r < R; r++) acc[r] += feqmod_eval<BARYON, OUTFLOW>(it, bin[r], SPECIES_RENORM ? rn[r] : it.renorm);
+        } else {
+          const DfItem it = items[k].lin;
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            double v = df_eval<2, BARYON, REGULATE, OUTFLOW>(it, bin[r]);
+            if (SPECIES_RENORM) v = (rn[r] != 0.0) ? v : 0.0;   // NaN renorm: the reference skips the species (:828-832)
+            acc[r] += v;
+          }
+        }
+      }
+    }
+  }
+
+  const int64_t pbase = (int64_t)blockIdx.z * total;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    if (jbin[r] < g.nbins) {
+      int64_t idx = iy + (int64_t)g.Ny * (iphi + (int64_t)g.Nphi * jbin[r]);
+      partial[pbase + idx] += kCooperFryePrefactor * g.deg[jbin[r]] * acc[r];
+    }
+  }
+}
+
+template <bool BARYON, bool SPECIES_RENORM>
+void launch_feqmod(bool reg, bool outflow, dim3 grid, cudaStream_t st, const double *pack, int64_t stride, int64_t n, int64_t cpc,
+                   const double *renorm, const FeqGrid &g, double *partial, int64_t total)
+{
+#define IS3D_LAUNCH(REG, OUT) feqmod_spectra_kernel<BARYON, REG, OUT, SPECIES_RENORM, kBins><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, renorm, g, partial, total)
+  if (reg && outflow) IS3D_LAUNCH(true, true);
+  else if (reg) IS3D_LAUNCH(true, false);
+  else if (outflow) IS3D_LAUNCH(false, true);
+  else IS3D_LAUNCH(false, false);
+#undef IS3D_LAUNCH
+}
+
+}  // namespace
+
+is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
+{
+  const is3d_params &p = ctx->prm;
+  if (ctx->gla_pts <= 0) { ctx->set_error("Gauss-Laguerre tables not set"); return IS3D_ERR_INVALID; }
+  const int64_t n = ctx->surf.n;
+  const int64_t total = (int64_t)ctx->ns * ctx->NpT * ctx->Nphi * ctx->Ny;
+  const int nbins = ctx->ns * ctx->NpT;
+
+  FeqmodFlags fl;
+  fl.df_mode = p.df_mode; fl.dimension = p.dimension; fl.include_baryon = p.include_baryon;
+  fl.include_bulk = p.include_bulk_deltaf; fl.include_shear = p.include_shear_deltaf;
+  fl.include_baryondiff = p.include_baryondiff_deltaf;
+  fl.deta_min = p.deta_min; fl.mass_pion0 = p.mass_pion0; fl.bulkPi_over_P_max = ctx->tb.bulkPi_over_P_max;
+  const bool species_renorm = (p.df_mode == 3 && p.include_bulk_deltaf);
+
+  FeqGrid g;
+  IS3D_TRY(build_bin_arrays(ctx, &g.mT, &g.pT, &g.m2, &g.baryon, &g.sign, &g.deg));
+  g.nbins = nbins; g.NpT = ctx->NpT; g.ns = ctx->ns;
+  g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
+  g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw;
+
+  const int nslices = (nbins + kThreads * kBins - 1) / (kThreads * kBins);
+  const int64_t blocks_per_chunk = (int64_t)nslices * ctx->Ny * ctx->Nphi;
+  if ((int64_t)ctx->Ny * ctx->Nphi > 65535) { ctx->set_error("Ny*Nphi exceeds 65535"); return IS3D_ERR_INVALID; }
+
+  // cells per pass: bounds the pack (440 B/cell) and the PTM renorm table (8 Ns B/cell) to ~2 GB
+  int64_t macro = 2 << 20;
+  if (species_renorm) { int64_t m2 = ((int64_t)1 << 31) / (8 * (int64_t)ctx->ns); if (m2 < macro) macro = m2; }
+  macro = macro / kTile * kTile;
+  if (macro < kTile) macro = kTile;
+  const int64_t stride = n < macro ? n : macro;
+  int nchunks; int64_t cpc;
+  choose_chunks(ctx, stride, blocks_per_chunk, total, kTile, &nchunks, &cpc);
+
+  void *pack = nullptr, *partial = nullptr, *counters = nullptr, *renorm = nullptr;
+  IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)FP_SIZE * stride * sizeof(double), &pack));
+  IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total * sizeof(double), &partial));
+  IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
+  if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm", (size_t)stride * ctx->ns * sizeof(double), &renorm));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total * sizeof(double), ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+
+  cudaEvent_t e0, e1;
+  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
+  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));
+  float ms_total = 0.f;
+  int64_t launches = 0;
+  for (int64_t begin = 0; begin < n; begin += macro) {
+    int64_t count = n - begin < macro ? n - begin : macro;
+    IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    feqmod_setup_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
+        ctx->surf, begin, count, ctx->tb, fl, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts, (double *)pack, stride,
+        (unsigned long long *)counters);
+    IS3D_CUDA_TRY(ctx, cudaGetLastError());
+    launches++;
+    if (species_renorm) {
+      int64_t work = count * ctx->ns;
+      feqmod_renorm_kernel<<<(unsigned)((work + 127) / 128), 128, 0, ctx->stream>>>(
+          (double *)pack, stride, count, ctx->ns, ctx->d_mass, ctx->d_deg, ctx->d_baryon, ctx->d_sign, ctx->d_gla_root,
+          ctx->d_gla_weight, ctx->gla_pts, (double *)renorm);
+      IS3D_CUDA_TRY(ctx, cudaGetLastError());
+      launches++;
+    }
+    int nch = (int)((count + cpc - 1) / cpc);
+    dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch);
+    const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0;
+    if (p.include_baryon) {
+      if (species_renorm) launch_feqmod<true, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total);
+      else launch_feqmod<true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total);
+    } else {
+      if (species_renorm) launch_feqmod<false, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total);
+      else launch_feqmod<false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total);
+    }
+    IS3D_CUDA_TRY(ctx, cudaGetLastError());
+    launches++;
+    IS3D_CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    IS3D_CUDA_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    IS3D_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    ms_total += ms;
+  }
+  reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total, out_dev);
+  IS3D_CUDA_TRY(ctx, cudaGetLastError());
+  launches++;
+  unsigned long long h_counters[16];
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (stats) {
+    stats->cells_total = n;
+    stats->cells_skipped = (int64_t)h_counters[0];
+    stats->cells_out_of_table = (int64_t)h_counters[1];
+    stats->cells_breakdown = (int64_t)h_counters[2];
+    stats->cells_pl_negative = (int64_t)h_counters[3];
+    // "until t = ..." of the reference's printout: tau of the last (highest-index) such cell
+    double tau_b = 0.0, tau_p = 0.0;
+    if (h_counters[4]) IS3D_CUDA_TRY(ctx, cudaMemcpy(&tau_b, ctx->surf.col[0] + (h_counters[4] - 1), sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_counters[5]) IS3D_CUDA_TRY(ctx, cudaMemcpy(&tau_p, ctx->surf.col[0] + (h_counters[5] - 1), sizeof(double), cudaMemcpyDeviceToHost));
+    stats->tau_breakdown = tau_b;
+    stats->tau_pl_negative = tau_p;
+    stats->kernel_ms = ms_total;
+    stats->kernel_launches = launches;
+  }
+  if (h_counters[1] != 0) {
+    ctx->set_error(std::to_string(h_counters[1]) + " cell(s) outside the df coefficient tables (the reference aborts here)");
+    return IS3D_ERR_TABLE_RANGE;
+  }
+  return IS3D_OK;
+}
+
+}  // namespace is3d

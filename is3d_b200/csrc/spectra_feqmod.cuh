@@ -1,0 +1,251 @@
+// K2 math: continuous spectra with the PTM / PTB modified equilibrium distributions (df_mode 3, 4).
+// Reference: EmissionFunctionArray::calculate_dN_pTdpTdphidy_feqmod, src/cpp/MomentumSpectra.cpp:419-1044.
+//
+// Non-breakdown cells evaluate f = |renorm| / (exp(E'/T' - b alphaB') + sign) with p' = A^-1 p_LRF.  p_LRF is linear
+// in (mT, pT):  p_LRF = mT (ch a + sh b) + pT (cphi c + sphi d)  with a,b,c,d built from the Milne basis, so
+//     E'^2 / T'^2 = m^2/T'^2 + mT^2 h1 + mT pT h2 + pT^2 h3,   h = quadratic forms of A^-1{a,b,c,d}/T'
+// per (cell, y, phi): 4 FMAs + one square root per momentum bin instead of a 3x3 solve.  The reference's LU inverse
+// plus per-momentum iterative refinement (:954-971) is replaced by a refined cofactor inverse per cell.
+// Breakdown cells (and the "narrow" |y - eta| < detA case, :865-871) fall back to the linear df of K1 with the
+// PTM / PTB coefficient sets, evaluated by the same df_eval as df_mode 2.
+#pragma once
+
+#include "gauss_thermal.cuh"
+#include "spectra_df.cuh"
+
+namespace is3d {
+
+enum FeqmodPackIdx {
+  // 0 .. DP_SIZE-1: the linear-df pack of spectra_df.cuh (used on breakdown)
+  FP_BREAKDOWN = DP_SIZE, FP_DETA, FP_ETA_SCALE, FP_RENORM, FP_IT2, FP_ALPHAB_MOD,
+  FP_A1X, FP_A1Y, FP_A1Z, FP_A2X, FP_A2Y, FP_A2Z, FP_A3X, FP_A3Y, FP_A3Z, FP_A4X, FP_A4Y, FP_A4Z,
+  FP_ADD,                       // PTB linear df: additive delta_z - 3 delta_lambda (outside feqbar)
+  // inputs of the per-(cell, species) PTM renormalisation
+  FP_T, FP_TMOD, FP_DNFACT, FP_G, FP_F_T2, FP_RENORM_DIV,
+  FP_SIZE
+};
+
+struct FeqmodFlags {
+  int df_mode;                 // 3 or 4
+  int dimension;
+  int include_baryon, include_bulk, include_shear, include_baryondiff;
+  double deta_min, mass_pion0, bulkPi_over_P_max;
+};
+
+enum { CELL_BREAKDOWN = 4, CELL_PL_NEGATIVE = 8 };
+
+// does_feqmod_breakdown with fast = 0 (EmissionFunction.cpp:65-109)
+IS3D_HD bool feqmod_breaks_down(const FeqmodFlags &fl, double T, double F, double bulkPi, double betabulk, double detA,
+                                double z, const double *gla_root, const double *gla_weight, int gla_pts)
+{
+  if (fl.df_mode == 3) {
+    const double *r1 = gla_root + 1 * gla_pts, *w1 = gla_weight + 1 * gla_pts;
+    const double *r2 = gla_root + 2 * gla_pts, *w2 = gla_weight + 2 * gla_pts;
+    double mbar = fl.mass_pion0 / T;
+    double neq_fact = T * T * T / kTwoPi2HbarC3, J20_fact = T * neq_fact;
+    double neq = neq_fact * gauss_thermal<TI_NEQ>(r1, w1, gla_pts, mbar, 0., 0., -1.);
+    double J20 = J20_fact * gauss_thermal<TI_J20>(r2, w2, gla_pts, mbar, 0., 0., -1.);
+    double dn = bulkPi * (neq + J20 * F / T / T) / betabulk;
+    return detA <= fl.deta_min || (neq + dn < 0.0);
+  }
+  return detA <= fl.deta_min || z < 0.0;
+}
+
+// Per-cell prologue (MomentumSpectra.cpp:516-773).  Returns CELL_* bits.
+IS3D_HD int feqmod_setup_cell(const Cell &c, const DfTables &tb, const FeqmodFlags &fl, const double *gla_root,
+                              const double *gla_weight, int gla_pts, double pack[FP_SIZE])
+{
+  for (int k = 0; k < FP_SIZE; k++) pack[k] = 0.0;
+  double tau = c.tau, tau2 = tau * tau;
+  double ux = c.ux, uy = c.uy, un = c.un;
+  double ut = sqrt(1.0 + ux * ux + uy * uy + tau2 * un * un);
+  if (ut * c.dat + ux * c.dax + uy * c.day + un * c.dan <= 0.0) return CELL_SKIPPED;
+  int status = CELL_OK;
+  double utperp = sqrt(1.0 + ux * ux + uy * uy);
+  double T = c.T, P = c.P, E = c.E;
+  Shear pi;
+  if (fl.include_shear) pi = complete_shear(c.pixx, c.pixy, c.pixn, c.piyy, c.piyn, ut, ux, uy, un, tau2);
+  double bulkPi = fl.include_bulk ? c.bulkPi : 0.0;
+  double muB = 0.0, alphaB = 0.0, nB = 0.0, Vt = 0.0, Vx = 0.0, Vy = 0.0, Vn = 0.0, ber = 0.0;
+  if (fl.include_baryon && fl.include_baryondiff) {
+    muB = c.muB; nB = c.nB; Vx = c.Vx; Vy = c.Vy; Vn = c.Vn;
+    Vt = (Vx * ux + Vy * uy + tau2 * Vn * un) / ut;
+    alphaB = muB / T;
+    ber = nB / (E + P);
+  }
+  if (fl.df_mode == 4) {        // keep Pi/P inside the PTB table (:603-615)
+    if (bulkPi < -P) bulkPi = -(1.0 - 1.e-5) * P;
+    else if (bulkPi / P > fl.bulkPi_over_P_max) bulkPi = P * (fl.bulkPi_over_P_max - 1.e-5);
+  }
+  double zt = tau * un / utperp, zn = ut / (tau * utperp);
+  double pl = P + bulkPi + zt * zt * pi.tt + tau2 * tau2 * zn * zn * pi.nn + 2. * tau2 * zt * zn * pi.tn;
+  if (pl < 0) status |= CELL_PL_NEGATIVE;
+
+  DfCoeff df;
+  if (!evaluate_df_coefficients(tb, fl.df_mode, fl.include_baryon, T, muB, E, P, bulkPi, &df)) return CELL_OUT_OF_TABLE;
+  Basis b = milne_basis(ut, ux, uy, un, tau);
+  ShearLRF l = boost_shear_to_lrf(pi, b, tau2);
+
+  double T_mod = T, alphaB_mod = alphaB;
+  if (fl.df_mode == 3) { T_mod = T + bulkPi * df.F / df.betabulk; alphaB_mod = alphaB + bulkPi * df.G / df.betabulk; }
+  double shear_mod = 0.5 / df.betapi;
+  double bulk_mod = (fl.df_mode == 4) ? df.lambda : bulkPi / (3.0 * df.betabulk);
+  double A[9];
+  A[0] = 1.0 + l.xx * shear_mod + bulk_mod; A[1] = l.xy * shear_mod; A[2] = l.xz * shear_mod;
+  A[3] = A[1]; A[4] = 1.0 + l.yy * shear_mod + bulk_mod; A[5] = l.yz * shear_mod;
+  A[6] = A[2]; A[7] = A[5]; A[8] = 1.0 + l.zz * shear_mod + bulk_mod;
+  double detA = A[0] * (A[4] * A[8] - A[5] * A[5]) - A[1] * (A[1] * A[8] - A[5] * A[2]) + A[2] * (A[1] * A[5] - A[4] * A[2]);
+  double detA_bulk_two_thirds = (1.0 + bulk_mod) * (1.0 + bulk_mod);
+  double Ainv[9], det_unused;
+  invert3x3(A, Ainv, &det_unused);
+
+  bool breaks = feqmod_breaks_down(fl, T, df.F, bulkPi, df.betabulk, detA, df.z, gla_root, gla_weight, gla_pts);
+  if (breaks) status |= CELL_BREAKDOWN;
+  double eta_scale = 1.0;
+  if (detA > fl.deta_min && fl.dimension == 2) eta_scale = detA / detA_bulk_two_thirds;
+
+  // ---- linear-df pack (breakdown branch, :887-928) ----
+  double invT = 1.0 / T;
+  double shear_coeff = 0.5 / (df.betapi * T);
+  double sc = shear_coeff * invT, K0, K1, K2, G0, G1, add = 0.0;
+  if (fl.df_mode == 3) {
+    double bulk0 = df.F / (T * T * df.betabulk) * bulkPi, bulk1 = df.G / df.betabulk * bulkPi, bulk2 = bulkPi / (3.0 * T * df.betabulk);
+    K0 = (bulk0 + bulk2) * T; K1 = bulk1; K2 = bulk2 * invT;
+    G0 = ber / df.betaV; G1 = invT / df.betaV;
+  } else {                     // PTB: df = feqbar (shear + dl (xE - m^2/T^2 / xE)) + dz - 3 dl
+    K0 = df.delta_lambda; K1 = 0.0; K2 = df.delta_lambda * invT * invT; G0 = 0.0; G1 = 0.0;
+    add = df.delta_z - 3.0 * df.delta_lambda;
+    alphaB = 0.0;              // the PTB fallback has no chemical-potential term (:913)
+  }
+  pack[DP_VALID] = 1.0;
+  pack[DP_ETA] = c.eta;
+  pack[DP_UTT] = ut * invT; pack[DP_TUNT] = tau * un * invT; pack[DP_UXT] = ux * invT; pack[DP_UYT] = uy * invT;
+  pack[DP_ALPHAB] = alphaB;
+  pack[DP_DAT] = c.dat; pack[DP_DAX] = c.dax; pack[DP_DAY] = c.day; pack[DP_DANT] = c.dan / tau;
+  pack[DP_PITT] = sc * pi.tt; pack[DP_T2PINN] = sc * tau2 * pi.nn; pack[DP_TPITN] = sc * tau * pi.tn;
+  pack[DP_PITX] = sc * pi.tx; pack[DP_PITY] = sc * pi.ty; pack[DP_TPIXN] = sc * tau * pi.xn; pack[DP_TPIYN] = sc * tau * pi.yn;
+  pack[DP_PIXX] = sc * pi.xx; pack[DP_PIYY] = sc * pi.yy; pack[DP_PIXY] = sc * pi.xy;
+  pack[DP_K0] = K0; pack[DP_K1] = K1; pack[DP_K2] = K2; pack[DP_G0] = G0; pack[DP_G1] = G1;
+  pack[DP_VT] = Vt; pack[DP_TVN] = tau * Vn; pack[DP_VX] = Vx; pack[DP_VY] = Vy;
+  pack[FP_ADD] = add;
+
+  // ---- modified-distribution pack ----
+  pack[FP_BREAKDOWN] = breaks ? 1.0 : 0.0;
+  pack[FP_DETA] = detA;
+  pack[FP_ETA_SCALE] = eta_scale;
+  double renorm_div = (fl.dimension == 2) ? detA_bulk_two_thirds : detA;
+  double renorm = 1.0;
+  if (fl.include_bulk && fl.df_mode == 4) renorm = df.z;
+  renorm /= renorm_div;
+  if (not_finite(renorm)) renorm = 0.0;          // the reference skips the species (:828-832)
+  pack[FP_RENORM] = fabs(renorm);
+  double iTm = 1.0 / T_mod;
+  pack[FP_IT2] = iTm * iTm;
+  pack[FP_ALPHAB_MOD] = alphaB_mod;
+  // p_LRF = mT (ch a + sh b) + pT (cphi c + sphi d),  a = (-Xt, 0, -Zt), b = tau (Xn, 0, Zn), c = (Xx, Yx, 0), d = (Xy, Yy, 0)
+  const double va[3] = {-b.Xt, 0.0, -b.Zt}, vb[3] = {tau * b.Xn, 0.0, tau * b.Zn};
+  const double vc[3] = {b.Xx, b.Yx, 0.0}, vd[3] = {b.Xy, b.Yy, 0.0};
+  for (int i = 0; i < 3; i++) {
+    pack[FP_A1X + i] = iTm * (Ainv[3 * i] * va[0] + Ainv[3 * i + 1] * va[1] + Ainv[3 * i + 2] * va[2]);
+    pack[FP_A2X + i] = iTm * (Ainv[3 * i] * vb[0] + Ainv[3 * i + 1] * vb[1] + Ainv[3 * i + 2] * vb[2]);
+    pack[FP_A3X + i] = iTm * (Ainv[3 * i] * vc[0] + Ainv[3 * i + 1] * vc[1] + Ainv[3 * i + 2] * vc[2]);
+    pack[FP_A4X + i] = iTm * (Ainv[3 * i] * vd[0] + Ainv[3 * i + 1] * vd[1] + Ainv[3 * i + 2] * vd[2]);
+  }
+  pack[FP_T] = T; pack[FP_TMOD] = T_mod; pack[FP_DNFACT] = bulkPi / df.betabulk; pack[FP_G] = df.G;
+  pack[FP_F_T2] = df.F / T / T; pack[FP_RENORM_DIV] = renorm_div;
+  return status;
+}
+
+// PTM renormalisation n_linear / n_mod of one species in one cell (MomentumSpectra.cpp:795-826); 0 encodes the
+// reference's "skip this species" for a NaN / inf factor.
+template <class PackFn>
+IS3D_HD double feqmod_renorm_ptm(PackFn pk, double mass, double degeneracy, double baryon, double sign,
+                                 const double *gla_root, const double *gla_weight, int pts)
+{
+  const double *r1 = gla_root + 1 * pts, *w1 = gla_weight + 1 * pts, *r2 = gla_root + 2 * pts, *w2 = gla_weight + 2 * pts;
+  double T = pk(FP_T), T_mod = pk(FP_TMOD), alphaB = pk(DP_ALPHAB), alphaB_mod = pk(FP_ALPHAB_MOD);
+  double neq_fact = T * T * T / kTwoPi2HbarC3, J20_fact = T * neq_fact, N10_fact = neq_fact;
+  double nmod_fact = T_mod * T_mod * T_mod / kTwoPi2HbarC3;
+  double mbar = mass / T, mbar_mod = mass / T_mod;
+  double neq = neq_fact * degeneracy * gauss_thermal<TI_NEQ>(r1, w1, pts, mbar, alphaB, baryon, sign);
+  double N10 = baryon * N10_fact * degeneracy * gauss_thermal<TI_J10>(r1, w1, pts, mbar, alphaB, baryon, sign);
+  double J20 = J20_fact * degeneracy * gauss_thermal<TI_J20>(r2, w2, pts, mbar, alphaB, baryon, sign);
+  double n_linear = neq + pk(FP_DNFACT) * (neq + N10 * pk(FP_G) + J20 * pk(FP_F_T2));
+  double n_mod = nmod_fact * degeneracy * gauss_thermal<TI_NEQ>(r1, w1, pts, mbar_mod, alphaB_mod, baryon, sign);
+  double renorm = (n_linear / n_mod) / pk(FP_RENORM_DIV);
+  if (not_finite(renorm)) return 0.0;
+  return fabs(renorm);
+}
+
+// item constants of the modified branch
+struct alignas(16) FeqmodItem {
+  double c1, d1, h1, h2;
+  double h3, iT2, alphaB_mod, renorm;
+};
+
+// sh/ch = sinh, cosh of (y - eta_scale eta); eta weight placement of the feqmod path:
+// w (p^tau ds_tau + p^x ds_x + p^y ds_y) + p^eta ds_eta  (MomentumSpectra.cpp:883, :936)
+template <class PackFn>
+IS3D_HD FeqmodItem feqmod_make_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w)
+{
+  FeqmodItem it;
+  it.c1 = w * ch * pk(DP_DAT) + sh * pk(DP_DANT);
+  it.d1 = w * (cphi * pk(DP_DAX) + sphi * pk(DP_DAY));
+  double g1[3], g2[3];
+  for (int i = 0; i < 3; i++) {
+    g1[i] = ch * pk(FP_A1X + i) + sh * pk(FP_A2X + i);
+    g2[i] = cphi * pk(FP_A3X + i) + sphi * pk(FP_A4X + i);
+  }
+  it.h1 = g1[0] * g1[0] + g1[1] * g1[1] + g1[2] * g1[2];
+  it.h2 = 2.0 * (g1[0] * g2[0] + g1[1] * g2[1] + g1[2] * g2[2]);
+  it.h3 = g2[0] * g2[0] + g2[1] * g2[1] + g2[2] * g2[2];
+  it.iT2 = pk(FP_IT2);
+  it.alphaB_mod = pk(FP_ALPHAB_MOD);
+  it.renorm = pk(FP_RENORM);
+  return it;
+}
+
+// linear-df item of the breakdown branch: as df_make_item but with the feqmod weight placement
+template <class PackFn>
+IS3D_HD DfItem feqmod_make_linear_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w)
+{
+  DfItem it = df_make_item(pk, sh, ch, cphi, sphi, 1.0);
+  it.c1 = w * ch * pk(DP_DAT) + sh * pk(DP_DANT);
+  it.d1 = w * (cphi * pk(DP_DAX) + sphi * pk(DP_DAY));
+  it.pad = pk(FP_ADD);
+  return it;
+}
+
+// sqrt(a) for a > 0 in the FMA pipe: hardware rsqrt seed + two coupled Newton (Goldschmidt) steps + residual fix
+IS3D_HD double fast_sqrt(double a)
+{
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  double d = fma(-g, g, a);
+  return fma(d, h, g);
+#else
+  return sqrt(a);
+#endif
+}
+
+// f p.dsigma of the modified distribution (MomentumSpectra.cpp:932-982); renorm_sp = |renorm| of this (cell, species)
+template <bool BARYON, bool OUTFLOW>
+IS3D_HD double feqmod_eval(const FeqmodItem &it, const DfBin &b, double renorm_sp)
+{
+  double pds = fma(b.mT, it.c1, b.pT * it.d1);
+  double e2 = fma(b.m2, it.iT2, fma(b.mT2, it.h1, fma(b.mTpT, it.h2, b.pT2 * it.h3)));
+  double x = fast_sqrt(e2);
+  if (BARYON) x = fma(-b.baryon, it.alphaB_mod, x);
+  double f = renorm_sp * fast_rcp(fast_exp(x) + b.sign);
+  double contrib = pds * f;
+  if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
+  return contrib;
+}
+
+}  // namespace is3d

@@ -29,7 +29,8 @@ def bundled_cell() -> dict:
     return s
 
 
-def s3d(n: int, seed: int = 12345, baryon: bool = False, dimension: int = 3, vah: bool = False) -> dict:
+def s3d(n: int, seed: int = 12345, baryon: bool = False, dimension: int = 3, vah: bool = False,
+        stress: float = 0.0) -> dict:
     """S-3D(N, seed): random 3+1D viscous-hydro cells in physical (GeV, fm) units as the kernels consume them.
 
     vah=True gives the S-VAH variant: a large pi^{eta eta}-dominated pressure anisotropy, P_L/P_T in [0.3, 1].
@@ -71,6 +72,15 @@ def s3d(n: int, seed: int = 12345, baryon: bool = False, dimension: int = 3, vah
         s["piyn"] = u(-0.03, 0.03, n) * P / tau
         s["ux"] = u(-0.4, 0.4, n)
         s["uy"] = u(-0.4, 0.4, n)
+    if stress > 0.0:
+        # a fraction `stress` of the cells gets large viscous corrections (|pi| ~ P, Pi ~ -0.6 P): these are the cells
+        # where the modified distributions break down (detA <= deta_min, negative pion density, pl < 0)
+        hot = u(0.0, 1.0, n) < stress
+        for k in ("pixx", "pixy", "piyy"):
+            s[k] = np.where(hot, 12.0 * s[k], s[k])
+        for k in ("pixn", "piyn"):
+            s[k] = np.where(hot, 12.0 * s[k], s[k])
+        s["bulkPi"] = np.where(hot, -u(0.3, 0.9, n) * P, s["bulkPi"])
     if baryon:
         s["muB"] = u(0.05, 0.4, n)
         s["nB"] = u(0.01, 0.1, n)

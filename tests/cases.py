@@ -2,7 +2,11 @@
 tables).  Sizes are chosen so the reference finishes each in about a second."""
 from __future__ import annotations
 
+import os
+
 from is3d_b200 import synthetic
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 BASE = dict(operation=1, mode=1, hrg_eos=2, dimension=3, include_baryon=0, include_bulk_deltaf=1,
             include_shear_deltaf=1, include_baryondiff_deltaf=0, regulate_deltaf=0, outflow=0)
@@ -36,6 +40,24 @@ SPECTRA_CASES = {
     # ragged sizes around the 256-cell tile / chunk boundaries, all SMASH species on a few cells
     "s3d_m2_smash_17cells": dict(surface=("s3d", dict(n=17, seed=11)), params=_p(df_mode=2), chosen="smash"),
     "s3d_m1_257cells": dict(surface=("s3d", dict(n=257, seed=12)), params=_p(df_mode=1), chosen="pikp"),
+    # ---- K2: PTM / PTB modified equilibrium (df_mode 3, 4); "stress" surfaces contain breakdown and pl < 0 cells ----
+    "s3d_m3": dict(surface=("s3d", dict(n=300, seed=12345, stress=0.3)), params=_p(df_mode=3), chosen="pikp"),
+    "s3d_m4": dict(surface=("s3d", dict(n=300, seed=12345, stress=0.3)), params=_p(df_mode=4), chosen="pikp"),
+    "s3d_m3_calm": dict(surface=("s3d", dict(n=300, seed=21)), params=_p(df_mode=3), chosen="pikp"),
+    "s3d_m4_calm": dict(surface=("s3d", dict(n=300, seed=21)), params=_p(df_mode=4), chosen="pikp"),
+    "s3d_m3_phi48_reg_outflow": dict(surface=("s3d", dict(n=100, seed=5, stress=0.3)),
+                                     params=_p(df_mode=3, hrg_eos=1, regulate_deltaf=1, outflow=1, deta_min=0.01),
+                                     chosen="pikp", tables=dict(phi_table="phi_table_48pt.dat")),
+    "s3d_m4_nobulk": dict(surface=("s3d", dict(n=200, seed=6, stress=0.3)), params=_p(df_mode=4, include_bulk_deltaf=0), chosen="pikp"),
+    "s3d_m3_noshear": dict(surface=("s3d", dict(n=200, seed=6, stress=0.3)), params=_p(df_mode=3, include_shear_deltaf=0), chosen="pikp"),
+    "s3d_m3_baryon": dict(surface=("s3d", dict(n=300, seed=7, baryon=True, stress=0.3)),
+                          params=_p(df_mode=3, include_baryon=1, include_baryondiff_deltaf=1), chosen="pikp"),
+    "s3d_m3_baryon_nodiff": dict(surface=("s3d", dict(n=200, seed=8, baryon=True, stress=0.3)),
+                                 params=_p(df_mode=3, include_baryon=1, include_baryondiff_deltaf=0), chosen="pikp"),
+    "s2d_m3": dict(surface=("s3d", dict(n=150, seed=3, dimension=2, stress=0.3)), params=_p(df_mode=3, dimension=2, hrg_eos=1), chosen="pikp"),
+    "s2d_m4_box_phi48": dict(surface=("s3d", dict(n=40, seed=3, dimension=2, stress=0.3)), params=_p(df_mode=4, dimension=2, hrg_eos=3),
+                             chosen=os.path.join(_GOLDEN, "chosen_box_small.dat"), tables=dict(phi_table="phi_table_48pt.dat")),
+    "s3d_m3_smash_9cells": dict(surface=("s3d", dict(n=9, seed=13, stress=0.3)), params=_p(df_mode=3), chosen="smash"),
 }
 
 

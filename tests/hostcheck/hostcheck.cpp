@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../is3d_b200/csrc/spectra_df.cuh"
+#include "../../is3d_b200/csrc/spectra_feqmod.cuh"
 #include "../../is3d_b200/host/host_dfview.hpp"
 #include "../../is3d_b200/host/is3d_host.hpp"
 
@@ -113,5 +114,90 @@ extern "C" long hostcheck_spectra_df(const char *root, double *out, long capacit
     double g = (double)L.pdg[L.chosen[s]].gspin;
     for (long k = 0; k < (long)npT * nphi * ny; k++) out[(long)s * npT * nphi * ny + k] = is3d::kCooperFryePrefactor * g * acc[(long)s * npT * nphi * ny + k];
   }
+  return total;
+}
+
+// df_mode 3, 4 (K2).  Same loop emulation: per cell setup pack, PTM renorm per (cell, species), per (y, phi, eta) item.
+extern "C" long hostcheck_spectra_feqmod(const char *root, double *out, long capacity, long *stats4)
+{
+  Loaded L;
+  L.load(root);
+  is3d::FeqmodFlags fl;
+  fl.df_mode = L.par.getVal("df_mode"); fl.dimension = L.par.getVal("dimension");
+  fl.include_baryon = L.par.getVal("include_baryon"); fl.include_bulk = L.par.getVal("include_bulk_deltaf");
+  fl.include_shear = L.par.getVal("include_shear_deltaf"); fl.include_baryondiff = L.par.getVal("include_baryondiff_deltaf");
+  fl.deta_min = L.par.getVal("deta_min"); fl.mass_pion0 = L.par.getVal("mass_pion0");
+  fl.bulkPi_over_P_max = L.df->bulkPi_over_Peq_max;
+  const bool reg = (int)L.par.getVal("regulate_deltaf"), outflow = (int)L.par.getVal("outflow");
+  if (fl.df_mode != 3 && fl.df_mode != 4) return 0;
+  const bool species_renorm = fl.df_mode == 3 && fl.include_bulk;
+  HostDfView view(*L.df);
+  Gauss_Laguerre gla;
+  gla.load_roots_and_weights("tables/gauss/gla_roots_weights.txt");
+  const int ns = (int)L.chosen.size(), npT = (int)L.pT.getNumberOfRows(), nphi = (int)L.phi.getNumberOfRows();
+  const int ny = fl.dimension == 3 ? (int)L.y.getNumberOfRows() : 1;
+  const int neta = fl.dimension == 3 ? 1 : (int)L.eta.getNumberOfRows();
+  const long total = (long)ns * npT * nphi * ny;
+  if (total > capacity) return -total;
+  std::vector<double> acc(total, 0.0);
+  is3d::SurfaceView sv;
+  for (int k = 0; k < 25; k++) sv.col[k] = L.surf.col[k].data();
+  sv.n = L.surf.size();
+  long nbreak = 0, npl = 0, nskip = 0;
+  for (int64_t ic = 0; ic < sv.n; ic++) {
+    is3d::Cell c = is3d::load_cell(sv, ic, fl.include_baryon != 0);
+    double pack[is3d::FP_SIZE];
+    int st = is3d::feqmod_setup_cell(c, view.tb, fl, gla.root.data(), gla.weight.data(), gla.points, pack);
+    if (st == is3d::CELL_OUT_OF_TABLE) { printf("hostcheck: cell %ld out of table\n", (long)ic); return 0; }
+    if (st == is3d::CELL_SKIPPED) { nskip++; continue; }
+    if (st & is3d::CELL_BREAKDOWN) nbreak++;
+    if (st & is3d::CELL_PL_NEGATIVE) npl++;
+    auto pk = [&](int k) { return pack[k]; };
+    std::vector<double> rn(ns, pack[is3d::FP_RENORM]);
+    if (species_renorm)
+      for (int s = 0; s < ns; s++) {
+        const particle_info &p = L.pdg[L.chosen[s]];
+        rn[s] = is3d::feqmod_renorm_ptm(pk, p.mass, (double)p.gspin, (double)p.baryon, (double)p.sign, gla.root.data(), gla.weight.data(), gla.points);
+      }
+    for (int iy = 0; iy < ny; iy++) {
+      double yv = fl.dimension == 3 ? L.y.get(1, iy + 1) : 0.0;
+      for (int ie = 0; ie < neta; ie++) {
+        double etav = fl.dimension == 3 ? pack[is3d::DP_ETA] : L.eta.get(1, ie + 1);
+        double w = fl.dimension == 3 ? 1.0 : L.eta.get(2, ie + 1);
+        bool linear = pack[is3d::FP_BREAKDOWN] != 0.0;
+        if (fl.dimension == 3 && !linear && pack[is3d::FP_DETA] < 0.01 && fabs(yv - etav) < pack[is3d::FP_DETA]) linear = true;
+        double d = linear ? (yv - etav) : (yv - pack[is3d::FP_ETA_SCALE] * etav);
+        double sh = sinh(d), ch = cosh(d);
+        for (int ip = 0; ip < nphi; ip++) {
+          double ph = L.phi.get(1, ip + 1);
+          is3d::DfItem lin;
+          is3d::FeqmodItem mod;
+          if (linear) lin = is3d::feqmod_make_linear_item(pk, sh, ch, cos(ph), sin(ph), w);
+          else mod = is3d::feqmod_make_item(pk, sh, ch, cos(ph), sin(ph), w);
+          for (int s = 0; s < ns; s++) {
+            const particle_info &p = L.pdg[L.chosen[s]];
+            for (int ipT = 0; ipT < npT; ipT++) {
+              double pTv = L.pT.get(1, ipT + 1), m2 = p.mass * p.mass, mT = sqrt(m2 + pTv * pTv);
+              is3d::DfBin b{mT, pTv, mT * mT, mT * pTv, pTv * pTv, m2, (double)p.baryon, (double)p.sign};
+              double v;
+              if (!linear) {
+                if (fl.include_baryon) v = outflow ? is3d::feqmod_eval<true, true>(mod, b, rn[s]) : is3d::feqmod_eval<true, false>(mod, b, rn[s]);
+                else v = outflow ? is3d::feqmod_eval<false, true>(mod, b, rn[s]) : is3d::feqmod_eval<false, false>(mod, b, rn[s]);
+              } else {
+                v = fl.include_baryon ? eval_dispatch<2, true>(reg, outflow, lin, b) : eval_dispatch<2, false>(reg, outflow, lin, b);
+                if (rn[s] == 0.0) v = 0.0;
+              }
+              acc[iy + (long)ny * (ip + (long)nphi * (ipT + (long)npT * s))] += v;
+            }
+          }
+        }
+      }
+    }
+  }
+  for (int s = 0; s < ns; s++) {
+    double g = (double)L.pdg[L.chosen[s]].gspin;
+    for (long k = 0; k < (long)npT * nphi * ny; k++) out[(long)s * npT * nphi * ny + k] = is3d::kCooperFryePrefactor * g * acc[(long)s * npT * nphi * ny + k];
+  }
+  if (stats4) { stats4[0] = nskip; stats4[1] = nbreak; stats4[2] = npl; stats4[3] = 0; }
   return total;
 }
