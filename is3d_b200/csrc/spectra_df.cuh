@@ -126,12 +126,11 @@ struct DfBin {
   double mT, pT, mT2, mTpT, pT2, m2, baryon, sign;
 };
 
-// One integrand evaluation: returns w * p.dsigma * feq (1 + df)   (MomentumSpectra.cpp:304-361)
-template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
-IS3D_HD double df_eval(const DfItem &it, const DfBin &b)
+// The distribution feq (1 + df) at one momentum (MomentumSpectra.cpp:317-359)
+template <int MODE, bool BARYON, bool REGULATE>
+IS3D_HD double df_distribution(const DfItem &it, const DfBin &b)
 {
   double xE = fma(b.mT, it.aT, -b.pT * it.bT);
-  double pds = fma(b.mT, it.c1, b.pT * it.d1);
   double x = xE;
   if (BARYON) x = fma(-b.baryon, it.alphaB, xE);
   double feq = fast_rcp(fast_exp(x) + b.sign);
@@ -158,8 +157,15 @@ IS3D_HD double df_eval(const DfItem &it, const DfBin &b)
   }
   double df = fma(feqbar, dfv, it.pad);   // pad = 0 except for the PTB fallback's additive delta_z - 3 delta_lambda
   if (REGULATE) df = fmax(-1.0, fmin(df, 1.0));
-  double f = fma(feq, df, feq);
-  double contrib = pds * f;
+  return fma(feq, df, feq);
+}
+
+// One integrand evaluation: returns w * p.dsigma * feq (1 + df)   (MomentumSpectra.cpp:304-361)
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+IS3D_HD double df_eval(const DfItem &it, const DfBin &b)
+{
+  double pds = fma(b.mT, it.c1, b.pT * it.d1);
+  double contrib = pds * df_distribution<MODE, BARYON, REGULATE>(it, b);
   if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
   return contrib;
 }

@@ -30,6 +30,8 @@ struct FeqmodFlags {
   int dimension;
   int include_baryon, include_bulk, include_shear, include_baryondiff;
   double deta_min, mass_pion0, bulkPi_over_P_max;
+  int clamp_inclusive = 0;     // PTB bulk clamp: spectra use < / > (MomentumSpectra.cpp:607-614), dN/dX and the sampler
+                               // use <= / >= (SpacetimeDistribution.cpp:784-785, ParticleSampler.cpp:552-559)
 };
 
 enum { CELL_BREAKDOWN = 4, CELL_PL_NEGATIVE = 8 };
@@ -74,8 +76,13 @@ IS3D_HD int feqmod_setup_cell(const Cell &c, const DfTables &tb, const FeqmodFla
     ber = nB / (E + P);
   }
   if (fl.df_mode == 4) {        // keep Pi/P inside the PTB table (:603-615)
-    if (bulkPi < -P) bulkPi = -(1.0 - 1.e-5) * P;
-    else if (bulkPi / P > fl.bulkPi_over_P_max) bulkPi = P * (fl.bulkPi_over_P_max - 1.e-5);
+    if (fl.clamp_inclusive) {
+      if (bulkPi <= -P) bulkPi = -(1.0 - 1.e-5) * P;
+      else if (bulkPi / P >= fl.bulkPi_over_P_max) bulkPi = P * (fl.bulkPi_over_P_max - 1.e-5);
+    } else {
+      if (bulkPi < -P) bulkPi = -(1.0 - 1.e-5) * P;
+      else if (bulkPi / P > fl.bulkPi_over_P_max) bulkPi = P * (fl.bulkPi_over_P_max - 1.e-5);
+    }
   }
   double zt = tau * un / utperp, zn = ut / (tau * utperp);
   double pl = P + bulkPi + zt * zt * pi.tt + tau2 * tau2 * zn * zn * pi.nn + 2. * tau2 * zt * zn * pi.tn;
@@ -183,13 +190,14 @@ struct alignas(16) FeqmodItem {
   double h3, iT2, alphaB_mod, renorm;
 };
 
-// sh/ch = sinh, cosh of (y - eta_scale eta); eta weight placement of the feqmod path:
-// w (p^tau ds_tau + p^x ds_x + p^y ds_y) + p^eta ds_eta  (MomentumSpectra.cpp:883, :936)
+// sh/ch = sinh, cosh of (y - eta_scale eta); eta weight placement of the feqmod spectra path:
+// w (p^tau ds_tau + p^x ds_x + p^y ds_y) + p^eta ds_eta  (MomentumSpectra.cpp:883, :936); the dN/dX path weights the
+// whole p.dsigma (SpacetimeDistribution.cpp:1022, :1075) -> w_on_dan
 template <class PackFn>
-IS3D_HD FeqmodItem feqmod_make_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w)
+IS3D_HD FeqmodItem feqmod_make_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w, bool w_on_dan = false)
 {
   FeqmodItem it;
-  it.c1 = w * ch * pk(DP_DAT) + sh * pk(DP_DANT);
+  it.c1 = w * ch * pk(DP_DAT) + (w_on_dan ? w : 1.0) * sh * pk(DP_DANT);
   it.d1 = w * (cphi * pk(DP_DAX) + sphi * pk(DP_DAY));
   double g1[3], g2[3];
   for (int i = 0; i < 3; i++) {
@@ -207,10 +215,10 @@ IS3D_HD FeqmodItem feqmod_make_item(PackFn pk, double sh, double ch, double cphi
 
 // linear-df item of the breakdown branch: as df_make_item but with the feqmod weight placement
 template <class PackFn>
-IS3D_HD DfItem feqmod_make_linear_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w)
+IS3D_HD DfItem feqmod_make_linear_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w, bool w_on_dan = false)
 {
   DfItem it = df_make_item(pk, sh, ch, cphi, sphi, 1.0);
-  it.c1 = w * ch * pk(DP_DAT) + sh * pk(DP_DANT);
+  it.c1 = w * ch * pk(DP_DAT) + (w_on_dan ? w : 1.0) * sh * pk(DP_DANT);
   it.d1 = w * (cphi * pk(DP_DAX) + sphi * pk(DP_DAY));
   it.pad = pk(FP_ADD);
   return it;
@@ -234,16 +242,23 @@ IS3D_HD double fast_sqrt(double a)
 #endif
 }
 
-// f p.dsigma of the modified distribution (MomentumSpectra.cpp:932-982); renorm_sp = |renorm| of this (cell, species)
+// the modified distribution |renorm| / (exp(E'/T' - b alphaB') + sign) at one momentum (MomentumSpectra.cpp:941-979);
+// renorm_sp = |renorm| of this (cell, species)
+template <bool BARYON>
+IS3D_HD double feqmod_distribution(const FeqmodItem &it, const DfBin &b, double renorm_sp)
+{
+  double e2 = fma(b.m2, it.iT2, fma(b.mT2, it.h1, fma(b.mTpT, it.h2, b.pT2 * it.h3)));
+  double x = fast_sqrt(e2);
+  if (BARYON) x = fma(-b.baryon, it.alphaB_mod, x);
+  return renorm_sp * fast_rcp(fast_exp(x) + b.sign);
+}
+
+// f p.dsigma of the modified distribution (MomentumSpectra.cpp:932-982)
 template <bool BARYON, bool OUTFLOW>
 IS3D_HD double feqmod_eval(const FeqmodItem &it, const DfBin &b, double renorm_sp)
 {
   double pds = fma(b.mT, it.c1, b.pT * it.d1);
-  double e2 = fma(b.m2, it.iT2, fma(b.mT2, it.h1, fma(b.mTpT, it.h2, b.pT2 * it.h3)));
-  double x = fast_sqrt(e2);
-  if (BARYON) x = fma(-b.baryon, it.alphaB_mod, x);
-  double f = renorm_sp * fast_rcp(fast_exp(x) + b.sign);
-  double contrib = pds * f;
+  double contrib = pds * feqmod_distribution<BARYON>(it, b, renorm_sp);
   if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
   return contrib;
 }

@@ -6,6 +6,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <utility>
 
 #include "is3d_host.hpp"
@@ -170,6 +171,22 @@ void EmissionFunctionArray::calculate_dN_dX()
   dN_twopirdrdy.assign((size_t)ns * prm.r_bins, 0.0);
   dN_dphisdy.assign((size_t)ns * prm.phip_bins, 0.0);
   check(is3d_dndx(ctx, dN_taudtaudy.data(), dN_twopirdrdy.data(), dN_dphisdy.data(), &stats), "calculate_dN_dX");
+  if (prm.dndx_bug_compat) {
+    // The reference clears its per-species accumulators with memset(ptr, 0.0, CORES * bins): `bins` BYTES, i.e. only
+    // the first bins/8 doubles (SpacetimeDistribution.cpp:166-168, :671-673).  Every later bin keeps the previous
+    // species' sum, so its files are cumulative over species there (and a bin cut in half by the byte count keeps
+    // its upper 32 bits).  Serial build (CORES = 1) reproduced literally on the clean device histograms.
+    auto emulate = [&](std::vector<double> &h, int bins) {
+      std::vector<double> all(bins, 0.0);
+      for (int s = 0; s < ns; s++) {
+        memset(all.data(), 0, (size_t)bins);
+        for (int b = 0; b < bins; b++) { all[b] += h[(size_t)s * bins + b]; h[(size_t)s * bins + b] = all[b]; }
+      }
+    };
+    emulate(dN_taudtaudy, prm.tau_bins);
+    emulate(dN_twopirdrdy, prm.r_bins);
+    emulate(dN_dphisdy, prm.phip_bins);
+  }
 }
 
 double EmissionFunctionArray::calculate_total_yield()

@@ -523,6 +523,156 @@ extern "C" int cf_oracle_spectra(const cf_params *p, const cf_inputs *in, double
   }
 }
 
-extern "C" int cf_oracle_dndx(const cf_params *, const cf_inputs *, double *, double *, double *, cf_stats *) { return 4; }
 extern "C" int cf_oracle_total_yield(const cf_params *, const cf_inputs *, double *) { return 4; }
 extern "C" int cf_oracle_cell_yields(const cf_params *, const cf_inputs *, double *, double *) { return 4; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// calculate_dN_dX (df_mode 1,2; SpacetimeDistribution.cpp:31-517) and calculate_dN_dX_feqmod (df_mode 3,4; :520-1246)
+// Species-outer loop as in the reference.  The histograms returned are the CLEAN per-species sums; the reference's
+// partial memset (:166-168) is a property of its accumulator reuse and is emulated by the caller when needed.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int cf_oracle_dndx(const cf_params *p, const cf_inputs *in, double *tau_hist, double *r_hist, double *phi_hist, cf_stats *st)
+{
+  cf_stats local;
+  if (!st) st = &local;
+  memset(st, 0, sizeof(*st));
+  if (p->df_mode < 1 || p->df_mode > 4) return 4;
+  const bool feqmod = p->df_mode >= 3;
+  const double prefactor = pow(2.0 * M_PI * hbarC, -3);
+  Grids g(p, in);
+  DfData dfd(p, in);
+  const int npart = in->n_species, npT = in->n_pT, nphi = in->n_phi, ny = g.ny, pts = in->n_gla;
+  const double *r1 = in->gla_root + 1 * pts, *w1 = in->gla_weight + 1 * pts, *r2 = in->gla_root + 2 * pts, *w2 = in->gla_weight + 2 * pts;
+  const double TAU_WIDTH = (p->tau_max - p->tau_min) / (double)p->tau_bins, R_WIDTH = (p->r_max - p->r_min) / (double)p->r_bins;
+  const double PHIP_WIDTH = 2.0 * M_PI / (double)p->phip_bins;
+  memset(tau_hist, 0, sizeof(double) * (size_t)npart * p->tau_bins);
+  memset(r_hist, 0, sizeof(double) * (size_t)npart * p->r_bins);
+  memset(phi_hist, 0, sizeof(double) * (size_t)npart * p->phip_bins);
+  for (int ipart = 0; ipart < npart; ipart++) {
+    double mass = in->mass[ipart], mass2 = mass * mass, sign = in->sign[ipart], degeneracy = in->degeneracy[ipart], baryon = in->baryon[ipart];
+    for (long icell = 0; icell < in->n_cells; icell++) {
+      CellState c;
+      if (!load_cell(p, in, icell, false, true, &c)) { if (ipart == 0) st->cells_skipped++; continue; }
+      if (p->dimension == 3) g.eta[0] = c.eta;
+      double T = c.T, P = c.P, E = c.E, bulkPi = c.bulkPi, tau2 = c.tau2;
+      if (p->df_mode == 4) {                     // :784-785 (inclusive comparisons here)
+        if (bulkPi <= -P) bulkPi = -(1.0 - 1.e-5) * P;
+        else if (bulkPi / P >= in->ptb_x_max) bulkPi = P * (in->ptb_x_max - 1.e-5);
+      }
+      double chem = baryon * c.alphaB;
+      DfCoeff df;
+      if (!dfd.evaluate(T, c.muB, E, P, bulkPi, &df)) { st->cells_out_of_table++; return 3; }
+      double shear_coeff, bulk0, bulk1, bulk2;
+      if (p->df_mode == 1) { shear_coeff = 0.5 / (T * T * (E + P)); bulk0 = df.c0 - df.c2; bulk1 = df.c1; bulk2 = 4.0 * df.c2 - df.c0; }
+      else { shear_coeff = 0.5 / (df.betapi * T); bulk0 = df.F / (T * T * df.betabulk); bulk1 = df.G / df.betabulk; bulk2 = 1.0 / (3.0 * T * df.betabulk); }
+      // modified-distribution set-up (feqmod only)
+      Basis b{};
+      double A[9], A_inv[9], detA = 1.0, T_mod = T, alphaB_mod = c.alphaB, eta_scale = 1.0, renorm = 1.0;
+      bool breaks = false;
+      if (feqmod) {
+        b = milne_basis(c);
+        PiLRF l = boost_pi(c, b);
+        if (p->df_mode == 3) { T_mod = T + bulkPi * df.F / df.betabulk; alphaB_mod = c.alphaB + bulkPi * df.G / df.betabulk; }
+        double shear_mod = 0.5 / df.betapi, bulk_mod = (p->df_mode == 4) ? df.lambda : bulkPi / (3.0 * df.betabulk);
+        double Axx = 1.0 + l.xx * shear_mod + bulk_mod, Axy = l.xy * shear_mod, Axz = l.xz * shear_mod;
+        double Ayy = 1.0 + l.yy * shear_mod + bulk_mod, Ayz = l.yz * shear_mod, Azz = 1.0 + l.zz * shear_mod + bulk_mod;
+        detA = Axx * (Ayy * Azz - Ayz * Ayz) - Axy * (Axy * Azz - Ayz * Axz) + Axz * (Axy * Ayz - Ayy * Axz);
+        double detA_bulk_two_thirds = pow(1.0 + bulk_mod, 2);
+        breaks = does_feqmod_breakdown(in, p->mass_pion0, T, df.F, bulkPi, df.betabulk, detA, p->deta_min, df.z, p->df_mode);
+        double Am[9] = {Axx, Axy, Axz, Axy, Ayy, Ayz, Axz, Ayz, Azz};
+        memcpy(A, Am, sizeof(A));
+        lu_invert3(A, A_inv);
+        if (detA > p->deta_min && p->dimension == 2) eta_scale = detA / detA_bulk_two_thirds;
+        if (p->include_bulk_deltaf) {
+          if (p->df_mode == 3) {
+            double neq_fact = T * T * T / two_pi2_hbarC3, dn_fact = bulkPi / df.betabulk, J20_fact = T * neq_fact, N10_fact = neq_fact;
+            double nmod_fact = T_mod * T_mod * T_mod / two_pi2_hbarC3, mbar = mass / T, mbar_mod = mass / T_mod;
+            double neq = neq_fact * degeneracy * GaussThermal(neq_int, r1, w1, pts, mbar, c.alphaB, baryon, sign);
+            double N10 = baryon * N10_fact * degeneracy * GaussThermal(J10_int, r1, w1, pts, mbar, c.alphaB, baryon, sign);
+            double J20 = J20_fact * degeneracy * GaussThermal(J20_int, r2, w2, pts, mbar, c.alphaB, baryon, sign);
+            double n_linear = neq + dn_fact * (neq + N10 * df.G + J20 * df.F / T / T);
+            double n_mod = nmod_fact * degeneracy * GaussThermal(neq_int, r1, w1, pts, mbar_mod, alphaB_mod, baryon, sign);
+            renorm = n_linear / n_mod;
+          } else renorm = df.z;
+        }
+        if (p->dimension == 2) renorm /= detA_bulk_two_thirds; else renorm /= detA;
+        if (std::isnan(renorm) || std::isinf(renorm)) continue;
+      }
+      double chem_mod = baryon * alphaB_mod;
+      double dN_dy_cell = 0.0;
+      for (int ipT = 0; ipT < npT; ipT++) {
+        double pT = g.pT[ipT], mT = sqrt(mass2 + pT * pT), mT_over_tau = mT / c.tau, pT_weight = g.pTw[ipT];
+        for (int iphip = 0; iphip < nphi; iphip++) {
+          double px = pT * g.cosphi[iphip], py = pT * g.sinphi[iphip], phi_weight = g.phiw[iphip];
+          for (int iy = 0; iy < ny; iy++) {
+            double y = g.y[iy], eta_integral = 0.0;
+            for (int ieta = 0; ieta < g.neta; ieta++) {
+              double eta = g.eta[ieta], eta_weight = g.etaw[ieta];
+              bool linear = !feqmod || breaks;
+              if (feqmod && p->dimension == 3 && !breaks && detA < 0.01 && fabs(y - eta) < detA) linear = true;
+              double f, pdotdsigma;
+              if (linear) {
+                double pt = mT * cosh(y - eta), pn = mT_over_tau * sinh(y - eta), tau2_pn = tau2 * pn;
+                pdotdsigma = eta_weight * (pt * c.dat + px * c.dax + py * c.day + pn * c.dan);
+                if (p->outflow && pdotdsigma <= 0.0) continue;
+                double pdotu = pt * c.ut - px * c.ux - py * c.uy - tau2_pn * c.un;
+                double pimunu_pmu_pnu = c.pitt * pt * pt + c.pixx * px * px + c.piyy * py * py + c.pinn * tau2_pn * tau2_pn
+                    + 2.0 * (-(c.pitx * px + c.pity * py) * pt + c.pixy * px * py + tau2_pn * (c.pixn * px + c.piyn * py - c.pitn * pt));
+                double Vmu_pmu = c.Vt * pt - c.Vx * px - c.Vy * py - c.Vn * tau2_pn;
+                double dfv;
+                if (p->df_mode == 4) {
+                  double feq = 1.0 / (exp(pdotu / T) + sign), feqbar = 1.0 - sign * feq;
+                  double df_shear = feqbar * shear_coeff * pimunu_pmu_pnu / pdotu;
+                  double df_bulk = df.delta_z - 3.0 * df.delta_lambda + feqbar * df.delta_lambda * (pdotu - mass2 / pdotu) / T;
+                  dfv = df_shear + df_bulk;
+                  if (p->regulate_deltaf) dfv = fmax(-1.0, fmin(dfv, 1.0));
+                  f = feq * (1.0 + dfv);
+                } else {
+                  double feq = 1.0 / (exp(pdotu / T - chem) + sign), feqbar = 1.0 - sign * feq;
+                  if (p->df_mode == 1) {
+                    double df_shear = shear_coeff * pimunu_pmu_pnu;
+                    double df_bulk = (bulk0 * mass2 + (bulk1 * baryon + bulk2 * pdotu) * pdotu) * bulkPi;
+                    double df_diff = (df.c3 * baryon + df.c4 * pdotu) * Vmu_pmu;
+                    dfv = feqbar * (df_shear + df_bulk + df_diff);
+                  } else {
+                    double df_shear = shear_coeff * pimunu_pmu_pnu / pdotu;
+                    double df_bulk = (bulk0 * pdotu + bulk1 * baryon + bulk2 * (pdotu - mass2 / pdotu)) * bulkPi;
+                    double df_diff = (c.baryon_enthalpy_ratio - baryon / pdotu) * Vmu_pmu / df.betaV;
+                    dfv = feqbar * (df_shear + df_bulk + df_diff);
+                  }
+                  if (p->regulate_deltaf) dfv = fmax(-1.0, fmin(dfv, 1.0));
+                  f = feq * (1.0 + dfv);
+                }
+              } else {
+                double pt = mT * cosh(y - eta_scale * eta), pn = mT_over_tau * sinh(y - eta_scale * eta), tau2_pn = tau2 * pn;
+                pdotdsigma = eta_weight * (pt * c.dat + px * c.dax + py * c.day + pn * c.dan);
+                if (p->outflow && pdotdsigma <= 0.0) continue;
+                double pLRF[3] = {-b.Xt * pt + b.Xx * px + b.Xy * py + b.Xn * tau2_pn, b.Yx * px + b.Yy * py, -b.Zt * pt + b.Zn * tau2_pn};
+                double pmod[3];
+                for (int i = 0; i < 3; i++) pmod[i] = A_inv[3 * i] * pLRF[0] + A_inv[3 * i + 1] * pLRF[1] + A_inv[3 * i + 2] * pLRF[2];
+                for (int it = 0; it < 5; it++) {
+                  double prev[3] = {pmod[0], pmod[1], pmod[2]}, back[3], dp[3];
+                  for (int i = 0; i < 3; i++) back[i] = A[3 * i] * prev[0] + A[3 * i + 1] * prev[1] + A[3 * i + 2] * prev[2];
+                  for (int i = 0; i < 3; i++) dp[i] = pLRF[i] - back[i];
+                  if (sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) <= 1.e-16) break;
+                  for (int i = 0; i < 3; i++) pmod[i] = prev[i] + (A_inv[3 * i] * dp[0] + A_inv[3 * i + 1] * dp[1] + A_inv[3 * i + 2] * dp[2]);
+                }
+                double E_mod = sqrt(mass2 + pmod[0] * pmod[0] + pmod[1] * pmod[1] + pmod[2] * pmod[2]);
+                f = fabs(renorm) / (exp(E_mod / T_mod - chem_mod) + sign);
+              }
+              eta_integral += pdotdsigma * f;
+            }
+            dN_dy_cell += pT_weight * phi_weight * prefactor * degeneracy * eta_integral;
+          }
+        }
+      }
+      double r = sqrt(c.x * c.x + c.y * c.y), phi = atan2(c.y, c.x);     // binning, :413-440
+      if (phi < 0.0) phi += 2.0 * M_PI;
+      long itau = (int)floor((c.tau - p->tau_min) / TAU_WIDTH), ir = (int)floor((r - p->r_min) / R_WIDTH), iphi = (int)floor(phi / PHIP_WIDTH);
+      if (itau >= 0 && itau < p->tau_bins) tau_hist[(size_t)ipart * p->tau_bins + itau] += dN_dy_cell;
+      if (ir >= 0 && ir < p->r_bins) r_hist[(size_t)ipart * p->r_bins + ir] += dN_dy_cell;
+      if (iphi >= 0 && iphi < p->phip_bins) phi_hist[(size_t)ipart * p->phip_bins + iphi] += dN_dy_cell;
+    }
+  }
+  return 0;
+}

@@ -66,3 +66,17 @@ def make_surface(spec):
     if kind == "bundled":
         return synthetic.bundled_cell()
     return synthetic.s3d(**kw)
+
+# dN/dX (operation 0) parity cases: name -> same layout as SPECTRA_CASES (operation forced to 0)
+DNDX_CASES = {
+    "dndx_s3d_m1": dict(surface=("s3d", dict(n=200, seed=31)), params=_p(operation=0, df_mode=1), chosen="pikp"),
+    "dndx_s3d_m2_baryon": dict(surface=("s3d", dict(n=200, seed=32, baryon=True)),
+                               params=_p(operation=0, df_mode=2, include_baryon=1, include_baryondiff_deltaf=1), chosen="pikp"),
+    "dndx_s2d_m2_phi48": dict(surface=("s3d", dict(n=60, seed=33, dimension=2)), params=_p(operation=0, df_mode=2, dimension=2, hrg_eos=1),
+                              chosen="pikp", tables=dict(phi_table="phi_table_48pt.dat")),
+    "dndx_s3d_m3": dict(surface=("s3d", dict(n=200, seed=34, stress=0.3)), params=_p(operation=0, df_mode=3), chosen="pikp"),
+    "dndx_s3d_m4_reg_outflow": dict(surface=("s3d", dict(n=200, seed=35, stress=0.3)),
+                                    params=_p(operation=0, df_mode=4, regulate_deltaf=1, outflow=1), chosen="pikp"),
+    "dndx_s2d_m3": dict(surface=("s3d", dict(n=80, seed=36, dimension=2, stress=0.3)), params=_p(operation=0, df_mode=3, dimension=2), chosen="pikp"),
+    "dndx_s2d_m4": dict(surface=("s3d", dict(n=80, seed=37, dimension=2, stress=0.3)), params=_p(operation=0, df_mode=4, dimension=2, hrg_eos=1), chosen="pikp"),
+}

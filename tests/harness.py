@@ -52,3 +52,45 @@ def open_session(tmp: str, case: dict, surface: dict, overrides: dict | None = N
     h.set_surface(surface)
     h.prepare()
     return h
+
+
+# ---- dN/dX helpers -----------------------------------------------------------------------------------------------
+def load_golden_dndx(name: str):
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    surf = {k[4:]: z[k] for k in z.files if k.startswith("col_")}
+    return surf, {"tau": z["tau"], "r": z["r"], "phi": z["phi"]}
+
+
+def emulate_partial_memset(h: np.ndarray) -> np.ndarray:
+    """The reference reuses one accumulator per histogram for all species and clears it with
+    memset(ptr, 0.0, CORES * bins) -- `bins` BYTES (SpacetimeDistribution.cpp:166-168): serial build, literally."""
+    ns, bins = h.shape
+    acc = np.zeros(bins)
+    out = np.empty_like(h)
+    for s in range(ns):
+        acc.view(np.uint8)[:bins] = 0
+        acc += h[s]
+        out[s] = acc
+    return out
+
+
+def normalise_dndx(h: dict, params: dict) -> dict:
+    """Writer normalisation of SpacetimeDistribution.cpp:448-490."""
+    from is3d_b200 import workdir
+    p = workdir.default_parameters()
+    p.update({k: str(v) for k, v in params.items()})
+    tb, rb, pb = int(float(p["tau_bins"])), int(float(p["r_bins"])), int(float(p["phip_bins"]))
+    tw = (float(p["tau_max"]) - float(p["tau_min"])) / tb
+    rw = (float(p["r_max"]) - float(p["r_min"])) / rb
+    pw = 2.0 * np.pi / pb
+    tau_mid = float(p["tau_min"]) + tw * (np.arange(tb) + 0.5)
+    r_mid = float(p["r_min"]) + rw * (np.arange(rb) + 0.5)
+    return {"tau": h["tau"] / (tau_mid * tw), "r": h["r"] / (2.0 * np.pi * r_mid * rw), "phi": h["phi"] / pw}
+
+
+def assert_hist_close(got: np.ndarray, ref: np.ndarray, rtol: float = RTOL, what: str = ""):
+    assert got.shape == ref.shape
+    peak = np.abs(ref).max(axis=1, keepdims=True)
+    err = np.abs(got - ref)
+    bad = err > rtol * np.abs(ref) + ATOL_OF_SPECIES_PEAK * peak
+    assert not bad.any(), f"{what}: {bad.sum()} bins off; worst {np.max(err / (np.abs(ref) + 1e-300 + ATOL_OF_SPECIES_PEAK * peak)):.3e}"

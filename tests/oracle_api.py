@@ -152,3 +152,14 @@ class OracleProblem:
         st = CfStats()
         rc = lib().cf_oracle_spectra(C.byref(self.p), C.byref(self.inp), out.ctypes.data, C.byref(st))
         return rc, out, st
+
+
+def _dndx(self):
+    ns = self.inp.n_species
+    tau = np.zeros((ns, self.p.tau_bins)); r = np.zeros((ns, self.p.r_bins)); phi = np.zeros((ns, self.p.phip_bins))
+    st = CfStats()
+    rc = lib().cf_oracle_dndx(C.byref(self.p), C.byref(self.inp), tau.ctypes.data, r.ctypes.data, phi.ctypes.data, C.byref(st))
+    return rc, {"tau": tau, "r": r, "phi": phi}, st
+
+
+OracleProblem.dndx = _dndx

@@ -74,3 +74,16 @@ def read_dumps(root: str) -> dict:
     if os.path.exists(p):
         out["seconds"] = float(open(p).read().split()[0])
     return out
+
+
+def read_dndx_files(root: str, mcids) -> dict:
+    """results/continuous/{dN_taudtaudy,dN_2pirdrdy,dN_dphidy}_<mcid>.dat of a reference run (17 digits in
+    oracle/_ref): arrays [species][bins] of the NORMALISED values exactly as written."""
+    out = {}
+    for key, stem in (("tau", "dN_taudtaudy"), ("r", "dN_2pirdrdy"), ("phi", "dN_dphidy")):
+        rows = []
+        for m in mcids:
+            a = np.loadtxt(os.path.join(root, "results", "continuous", f"{stem}_{int(m)}.dat"), ndmin=2)
+            rows.append(a[:, 1])
+        out[key] = np.array(rows)
+    return out

@@ -23,3 +23,16 @@ def test_oracle_matches_reference_golden(libs, tmp_path, name):
     # amplified in the few bins where positive and negative p.dsigma contributions cancel
     worst = harness.assert_spectra_close(got, ref, rtol=1e-11, what=name)
     print(name, worst)
+
+
+@pytest.mark.parametrize("name", list(cases.DNDX_CASES))
+def test_oracle_dndx_matches_reference_golden(libs, tmp_path, name):
+    case = cases.DNDX_CASES[name]
+    surf, ref = harness.load_golden_dndx(name)
+    root = workdir.make_workdir(str(tmp_path), case["params"], chosen=case["chosen"], **case.get("tables", {}))
+    prob = oracle_api.OracleProblem(root, case["params"], surf)
+    rc, clean, st = prob.dndx()
+    assert rc == 0
+    got = harness.normalise_dndx({k: harness.emulate_partial_memset(v) for k, v in clean.items()}, case["params"])
+    for k in ("tau", "r", "phi"):
+        harness.assert_hist_close(got[k], ref[k], rtol=1e-11, what=f"{name}/{k}")
