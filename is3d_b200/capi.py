@@ -281,3 +281,54 @@ class HostSession:
         st = Stats()
         self.host.is3d_host_stats(self.h, C.byref(st))
         return st
+
+
+# ---- sampler conveniences (HostSession methods) ------------------------------------------------------------------
+def _abi_total_yield(self):
+    v = C.c_double()
+    st = Stats()
+    self._check(self.lib.is3d_total_yield(self.ctx, C.byref(v), C.byref(st)), "is3d_total_yield")
+    return v.value, st
+
+
+def _abi_cell_yields(self, n_cells: int, n_species: int, with_list: bool = True):
+    tot = np.zeros(n_cells)
+    lst = np.zeros((n_cells, n_species)) if with_list else None
+    st = Stats()
+    self._check(self.lib.is3d_cell_yields(self.ctx, _ptr(tot), _ptr(lst) if with_list else None, C.byref(st)), "is3d_cell_yields")
+    return tot, lst, st
+
+
+def _abi_sample(self, nevents: int):
+    """Returns (structured particle array grouped by event, counts per event, stats)."""
+    plist = C.c_void_p()
+    total = C.c_int64()
+    counts = np.zeros(nevents, dtype=np.int64)
+    st = Stats()
+    self._check(self.lib.is3d_sample(self.ctx, nevents, C.byref(plist), C.byref(total), _ptr(counts), C.byref(st)), "is3d_sample")
+    n = total.value
+    if plist.value and n:
+        buf = (C.c_char * (n * PARTICLE_DTYPE.itemsize)).from_address(plist.value)
+        arr = np.frombuffer(buf, dtype=PARTICLE_DTYPE).copy()
+    else:
+        arr = np.zeros(0, dtype=PARTICLE_DTYPE)
+    if plist.value:
+        self.lib.is3d_free_particles(plist)
+    return arr, counts, st
+
+
+def _abi_sample_histograms(self, ns: int, params: dict):
+    g = lambda k, d: int(float(params.get(k, d)))  # noqa: E731
+    yb, eb, pb, phb, tb, rb = g("y_bins", 100), g("eta_bins", 140), g("pT_bins", 100), g("phip_bins", 100), g("tau_bins", 120), g("r_bins", 60)
+    h = {"dN_dy": np.zeros((ns, yb)), "dN_deta": np.zeros((ns, eb)), "dN_dphip": np.zeros((ns, phb)), "dN_pT": np.zeros((ns, pb)),
+         "pT_count": np.zeros((ns, pb)), "vn_re": np.zeros((7, ns, pb)), "vn_im": np.zeros((7, ns, pb)), "dN_tau": np.zeros((ns, tb)),
+         "dN_r": np.zeros((ns, rb)), "dN_phis": np.zeros((ns, phb))}
+    order = ["dN_dy", "dN_deta", "dN_dphip", "dN_pT", "pT_count", "vn_re", "vn_im", "dN_tau", "dN_r", "dN_phis"]
+    self._check(self.lib.is3d_sample_histograms(self.ctx, *[_ptr(h[k]) for k in order]), "is3d_sample_histograms")
+    return h
+
+
+HostSession.abi_total_yield = _abi_total_yield
+HostSession.abi_cell_yields = _abi_cell_yields
+HostSession.abi_sample = _abi_sample
+HostSession.abi_sample_histograms = _abi_sample_histograms

@@ -523,8 +523,6 @@ extern "C" int cf_oracle_spectra(const cf_params *p, const cf_inputs *in, double
   }
 }
 
-extern "C" int cf_oracle_total_yield(const cf_params *, const cf_inputs *, double *) { return 4; }
-extern "C" int cf_oracle_cell_yields(const cf_params *, const cf_inputs *, double *, double *) { return 4; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // calculate_dN_dX (df_mode 1,2; SpacetimeDistribution.cpp:31-517) and calculate_dN_dX_feqmod (df_mode 3,4; :520-1246)
@@ -673,6 +671,106 @@ extern "C" int cf_oracle_dndx(const cf_params *p, const cf_inputs *in, double *t
       if (ir >= 0 && ir < p->r_bins) r_hist[(size_t)ipart * p->r_bins + ir] += dN_dy_cell;
       if (iphi >= 0 && iphi < p->phip_bins) phi_hist[(size_t)ipart * p->phip_bins + iphi] += dN_dy_cell;
     }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sampler yields.  calculate_total_yield (ParticleSampler.cpp:447-636) and the per-cell dn_list / dn_tot of
+// sample_dN_pTdpTdphidy in fast mode (:680-915, fast_max_particle_number :122-161), df_mode 1-4.
+// Note: the reference reads Surface_Element_Vector::dsigma_space in calculate_total_yield without ever calling
+// compute_dsigma_magnitude() (:606-609), i.e. an uninitialised value multiplies V.dsigma * dn_diff; the oracle (and
+// the product) use the intended sqrt(dsx^2 + dsy^2 + dsz^2).  The term is zero without baryon diffusion.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct YieldCell { bool valid; double ds_time, ds_space, ds_max, Vdsigma, bulkPi, z, delta_z; bool breaks_yield, breaks_sample; };
+
+YieldCell yield_cell(const cf_params *p, const cf_inputs *in, const DfData &dfd, long icell, double F_avg, double betabulk_avg, int *err)
+{
+  YieldCell y{};
+  CellState c;
+  if (!load_cell(p, in, icell, false, true, &c)) return y;
+  double Vdsigma = c.Vt * c.dat + c.Vx * c.dax + c.Vy * c.day + c.Vn * c.dan;
+  double bulkPi = c.bulkPi;
+  if (p->df_mode == 4) {
+    if (bulkPi <= -c.P) bulkPi = -(1.0 - 1.e-5) * c.P;
+    else if (bulkPi / c.P >= in->ptb_x_max) bulkPi = c.P * (in->ptb_x_max - 1.e-5);
+  }
+  DfCoeff df;
+  if (!dfd.evaluate(c.T, c.muB, c.E, c.P, bulkPi, &df)) { *err = 3; return y; }
+  Basis b = milne_basis(c);
+  double dst = c.dat * c.ut + c.dax * c.ux + c.day * c.uy + c.dan * c.un;
+  double dsx = -(c.dat * b.Xt + c.dax * b.Xx + c.day * b.Xy + c.dan * b.Xn);
+  double dsy = -(c.dax * b.Yx + c.day * b.Yy);
+  double dsz = -(c.dat * b.Zt + c.dan * b.Zn);
+  double ds_space = sqrt(dsx * dsx + dsy * dsy + dsz * dsz);
+  PiLRF l = boost_pi(c, b);
+  double shear_mod = 0, bulk_mod = 0;
+  if (p->df_mode == 3) { shear_mod = 0.5 / df.betapi; bulk_mod = bulkPi / (3. * df.betabulk); }
+  else if (p->df_mode == 4) { shear_mod = 0.5 / df.betapi; bulk_mod = df.lambda; }
+  double Axx = 1.0 + l.xx * shear_mod + bulk_mod, Axy = l.xy * shear_mod, Axz = l.xz * shear_mod;
+  double Ayy = 1.0 + l.yy * shear_mod + bulk_mod, Ayz = l.yz * shear_mod, Azz = 1.0 + l.zz * shear_mod + bulk_mod;
+  double detA = Axx * (Ayy * Azz - Ayz * Ayz) - Axy * (Axy * Azz - Ayz * Axz) + Axz * (Axy * Ayz - Ayy * Axz);
+  y.valid = true; y.ds_time = dst; y.ds_space = ds_space; y.ds_max = fabs(dst) + ds_space; y.Vdsigma = Vdsigma; y.bulkPi = bulkPi;
+  y.z = df.z; y.delta_z = df.delta_z;
+  y.breaks_yield = does_feqmod_breakdown(in, p->mass_pion0, c.T, df.F, bulkPi, df.betabulk, detA, p->deta_min, df.z, p->df_mode);
+  y.breaks_sample = y.breaks_yield;
+  if (p->df_mode == 3 && p->fast)   // does_feqmod_breakdown(..., FAST, Tavg, F_avg, betabulk_avg), ParticleSampler.cpp:874
+    y.breaks_sample = does_feqmod_breakdown(in, p->mass_pion0, in->T_avg, F_avg, bulkPi, betabulk_avg, detA, p->deta_min, df.z, p->df_mode);
+  return y;
+}
+}  // namespace
+
+extern "C" int cf_oracle_total_yield(const cf_params *p, const cf_inputs *in, double *ntotal)
+{
+  if (p->df_mode < 1 || p->df_mode > 4) return 4;
+  DfData dfd(p, in);
+  double Ntot = 0;
+  int err = 0;
+  for (long icell = 0; icell < in->n_cells; icell++) {
+    YieldCell y = yield_cell(p, in, dfd, icell, 0.0, 1.0, &err);
+    if (err) return err;
+    if (!y.valid) continue;
+    for (int s = 0; s < in->n_species; s++) {   // estimate_mean_particle_number, :75-119
+      double neq = in->equilibrium_density[s], bd = in->bulk_density[s], dd = in->diffusion_density[s];
+      if (p->df_mode == 4) Ntot += y.breaks_yield ? y.ds_time * (1.0 + y.delta_z) * neq : y.ds_time * y.z * neq;
+      else Ntot += y.ds_time * (neq + y.bulkPi * bd) - y.ds_space * y.Vdsigma * dd;
+    }
+  }
+  if (p->dimension == 2) Ntot *= (2.0 * p->y_cut);
+  *ntotal = Ntot;
+  return 0;
+}
+
+// dn_tot[cell] (after the 2 y_max ds_max volume factor) and dn_list[cell][species] (before it); fast mode only
+extern "C" int cf_oracle_cell_yields(const cf_params *p, const cf_inputs *in, double *dn_tot, double *dn_list)
+{
+  if (p->df_mode < 1 || p->df_mode > 4 || !p->fast) return 4;
+  DfData dfd(p, in);
+  double F_avg = 0.0, betabulk_avg = 1.0;
+  if (p->df_mode == 3) {
+    DfCoeff d;
+    if (!dfd.evaluate(in->T_avg, in->muB_avg, 0.0, 0.0, 0.0, &d)) return 3;
+    F_avg = d.F; betabulk_avg = d.betabulk;
+  }
+  double y_max = (p->dimension == 2) ? p->y_cut : 0.5;
+  int err = 0;
+  for (long icell = 0; icell < in->n_cells; icell++) {
+    YieldCell y = yield_cell(p, in, dfd, icell, F_avg, betabulk_avg, &err);
+    if (err) return err;
+    double tot = 0.0;
+    for (int s = 0; s < in->n_species; s++) {
+      double v = 0.0;
+      if (y.valid) {                             // fast_max_particle_number
+        double neq = in->equilibrium_density[s], bd = in->bulk_density[s];
+        if (p->df_mode <= 2 || y.breaks_sample) v = 2.0 * neq;
+        else if (p->df_mode == 3) v = neq + y.bulkPi * bd;
+        else v = y.z * neq;
+      }
+      if (dn_list) dn_list[(size_t)icell * in->n_species + s] = v;
+      tot += v;
+    }
+    dn_tot[icell] = (y.valid && tot > 0.0) ? tot * (2.0 * y_max * y.ds_max) : 0.0;
   }
   return 0;
 }

@@ -92,6 +92,39 @@ int main(int argc, char **argv)
 
   EmissionFunctionArray efa(paraRdr, &chosen_particles, &pT_tab, &phi_tab, &y_tab, &eta_tab, particle_data, Nparticle, surf_ptr, FO_length, df_data);
 
+  // exact mean total yield: call the reference's own public calculate_total_yield (EmissionFunction.h:172) on the
+  // same structure-of-arrays unpack that calculate_spectra builds (EmissionFunction.cpp:998-1161); the reference only
+  // prints it truncated to an integer (ParticleSampler.cpp:633)
+  if(operation == 2)
+  {
+    int ns = efa.number_of_chosen_particles;
+    std::vector<double> neq(ns), dnb(ns), dnd(ns);
+    for(int i = 0; i < ns; i++)
+    {
+      int k = efa.chosen_particles_sampling_table[i];
+      neq[i] = particle_data[k].equilibrium_density; dnb[i] = particle_data[k].bulk_density; dnd[i] = particle_data[k].diff_density;
+    }
+    std::vector<std::vector<double>> c(25, std::vector<double>(FO_length, 0.0));
+    for(long i = 0; i < FO_length; i++)
+    {
+      FO_surf &f = surf_ptr[i];
+      double v[25] = {f.tau, f.x, f.y, f.eta, f.dat, f.dax, f.day, f.dan, f.ux, f.uy, f.un, f.E, f.T, f.P, f.pixx, f.pixy, f.pixn,
+                      f.piyy, f.piyn, f.bulkPi, 0, 0, 0, 0, 0};
+      if(include_baryon) { v[20] = f.muB; v[21] = f.nB; v[22] = f.Vx; v[23] = f.Vy; v[24] = f.Vn; }
+      for(int k = 0; k < 25; k++) c[k][i] = v[k];
+    }
+    Gauss_Laguerre *gla = new Gauss_Laguerre;
+    gla->load_roots_and_weights("tables/gauss/gla_roots_weights.txt");
+    double Ntot = efa.calculate_total_yield(neq.data(), dnb.data(), dnd.data(), c[12].data(), c[13].data(), c[11].data(), c[0].data(),
+                                            c[8].data(), c[9].data(), c[10].data(), c[4].data(), c[5].data(), c[6].data(), c[7].data(),
+                                            c[14].data(), c[15].data(), c[16].data(), c[17].data(), c[18].data(), c[19].data(),
+                                            c[20].data(), c[21].data(), c[22].data(), c[23].data(), c[24].data(), df_data, gla);
+    FILE *f = fopen("ref_dump/total_yield.bin", "wb");
+    wr(f, &Ntot, sizeof(double));
+    fclose(f);
+    if(getenv("IS3D_REF_YIELD_ONLY")) { fflush(stdout); _Exit(0); }
+  }
+
   std::vector<std::vector<Sampled_Particle>> events;
   auto t0 = std::chrono::steady_clock::now();
   efa.calculate_spectra(events);
@@ -112,6 +145,12 @@ int main(int argc, char **argv)
     fclose(f);
   }
   if(operation == 2)
+  {
+    FILE *g = fopen("ref_dump/nevents.txt", "w");
+    fprintf(g, "%ld\n", efa.Nevents);
+    fclose(g);
+  }
+  if(operation == 2 && !(int)paraRdr->getVal("test_sampler"))
   {
     FILE *f = fopen("ref_dump/particles.bin", "wb");
     long nev = (long)events.size(); wr(f, &nev, sizeof(long));

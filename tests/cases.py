@@ -80,3 +80,15 @@ DNDX_CASES = {
     "dndx_s2d_m3": dict(surface=("s3d", dict(n=80, seed=36, dimension=2, stress=0.3)), params=_p(operation=0, df_mode=3, dimension=2), chosen="pikp"),
     "dndx_s2d_m4": dict(surface=("s3d", dict(n=80, seed=37, dimension=2, stress=0.3)), params=_p(operation=0, df_mode=4, dimension=2, hrg_eos=1), chosen="pikp"),
 }
+
+# sampler (operation 2) cases: the reference run behind each golden file samples ~2e6 hadrons with test_sampler = 1
+_S = dict(operation=2, oversample=1, fast=1, test_sampler=1, sampler_seed=1, min_num_hadrons=2.0e6, max_num_samples=1.0e7)
+SAMPLER_CASES = {
+    "smp_s3d_m1": dict(surface=("s3d", dict(n=300, seed=41)), params=_p(df_mode=1, **_S), chosen="pikp"),
+    "smp_s3d_m2_baryon": dict(surface=("s3d", dict(n=300, seed=42, baryon=True)),
+                              params=_p(df_mode=2, include_baryon=1, include_baryondiff_deltaf=1, **_S), chosen="pikp"),
+    "smp_s3d_m3": dict(surface=("s3d", dict(n=300, seed=43, stress=0.3)), params=_p(df_mode=3, **_S), chosen="pikp"),
+    "smp_s3d_m4": dict(surface=("s3d", dict(n=300, seed=44, stress=0.3)), params=_p(df_mode=4, **_S), chosen="pikp"),
+    "smp_s2d_m3": dict(surface=("s3d", dict(n=200, seed=45, dimension=2, stress=0.2)), params=_p(df_mode=3, dimension=2, hrg_eos=1, **_S), chosen="pikp"),
+    "smp_s3d_m2_smash": dict(surface=("s3d", dict(n=200, seed=46)), params=_p(df_mode=2, **_S), chosen="smash"),
+}

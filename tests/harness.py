@@ -94,3 +94,22 @@ def assert_hist_close(got: np.ndarray, ref: np.ndarray, rtol: float = RTOL, what
     err = np.abs(got - ref)
     bad = err > rtol * np.abs(ref) + ATOL_OF_SPECIES_PEAK * peak
     assert not bad.any(), f"{what}: {bad.sum()} bins off; worst {np.max(err / (np.abs(ref) + 1e-300 + ATOL_OF_SPECIES_PEAK * peak)):.3e}"
+
+
+# ---- sampler helpers ---------------------------------------------------------------------------------------------
+def load_golden_sampler(name: str):
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    surf = {k[4:]: z[k] for k in z.files if k.startswith("col_")}
+    ref = {k: z[k] for k in z.files if not k.startswith("col_")}
+    return surf, ref
+
+
+def chi2_two_sample(a, sa, b, sb, min_counts=100):
+    """Two-sample chi^2 of count histograms a (sa events) and b (sb events) with Poisson variances, over bins with at
+    least `min_counts` entries in total (below that the observed-variance estimate is biased)."""
+    a = np.asarray(a, dtype=float).ravel()
+    b = np.asarray(b, dtype=float).ravel()
+    m = (a + b) >= min_counts
+    d = a[m] / sa - b[m] / sb
+    v = a[m] / sa ** 2 + b[m] / sb ** 2
+    return float((d * d / v).sum()), int(m.sum())

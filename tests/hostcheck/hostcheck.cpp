@@ -201,3 +201,86 @@ extern "C" long hostcheck_spectra_feqmod(const char *root, double *out, long cap
   if (stats4) { stats4[0] = nskip; stats4[1] = nbreak; stats4[2] = npl; stats4[3] = 0; }
   return total;
 }
+
+// ---- sampler (K5/K6) emulation: same Philox streams, same per-cell / per-hadron functions, serial loops ----------
+#include "../../is3d_b200/csrc/sampler.cuh"
+
+// hists: dN_dy [ns][y_bins], dN_deta [ns][eta_bins], dN_pT [ns][pT_bins]; returns accepted hadrons, *yield = mean total
+extern "C" long hostcheck_sampler(const char *root, long nevents, double *dN_dy, double *dN_deta, double *dN_pT, double *yield_out,
+                                  long *proposed_out)
+{
+  Loaded L;
+  L.load(root);
+  is3d::SamplerFlags fl;
+  fl.df_mode = L.par.getVal("df_mode"); fl.dimension = L.par.getVal("dimension");
+  fl.include_baryon = L.par.getVal("include_baryon"); fl.include_bulk = L.par.getVal("include_bulk_deltaf");
+  fl.include_shear = L.par.getVal("include_shear_deltaf"); fl.include_baryondiff = L.par.getVal("include_baryondiff_deltaf");
+  fl.fast = L.par.getVal("fast"); fl.deta_min = L.par.getVal("deta_min"); fl.mass_pion0 = L.par.getVal("mass_pion0");
+  fl.bulkPi_over_P_max = L.df->bulkPi_over_Peq_max; fl.y_cut = L.par.getVal("y_cut");
+  const uint64_t seed = (uint64_t)L.par.getVal("sampler_seed");
+  HostDfView view(*L.df);
+  Plasma QGP;
+  QGP.load_thermodynamic_averages();
+  fl.T_avg = QGP.temperature; fl.F_avg = 0.0; fl.betabulk_avg = 1.0;
+  if (fl.df_mode == 3 && fl.fast) {
+    is3d::DfCoeff d;
+    is3d::evaluate_df_coefficients(view.tb, 3, fl.include_baryon, QGP.temperature, QGP.baryon_chemical_potential, 0.0, 0.0, 0.0, &d);
+    fl.F_avg = d.F; fl.betabulk_avg = d.betabulk;
+  }
+  Gauss_Laguerre gla;
+  gla.load_roots_and_weights("tables/gauss/gla_roots_weights.txt");
+  const int ns = (int)L.chosen.size();
+  std::vector<double> cumA(ns), cumB(ns);
+  double totA = 0, totB = 0, totD = 0;
+  for (int s = 0; s < ns; s++) {
+    const particle_info &p = L.pdg[L.chosen[s]];
+    totA += p.equilibrium_density; totB += p.bulk_density; totD += p.diff_density;
+    cumA[s] = totA; cumB[s] = totB;
+  }
+  const int y_bins = L.par.getVal("y_bins"), eta_bins = L.par.getVal("eta_bins"), pT_bins = L.par.getVal("pT_bins");
+  const double y_cut = fl.y_cut, y_w = 2.0 * y_cut / y_bins, eta_cut = L.par.getVal("eta_cut"), eta_w = 2.0 * eta_cut / eta_bins;
+  const double pT_min = L.par.getVal("pT_min"), pT_w = (L.par.getVal("pT_max") - pT_min) / pT_bins;
+  const double y_max = fl.dimension == 2 ? y_cut : 0.5;
+  is3d::SurfaceView sv;
+  for (int k = 0; k < 25; k++) sv.col[k] = L.surf.col[k].data();
+  sv.n = L.surf.size();
+  long accepted = 0, proposed = 0;
+  double yield = 0.0;
+  for (int64_t ic = 0; ic < sv.n; ic++) {
+    is3d::Cell c = is3d::load_cell(sv, ic, fl.include_baryon != 0);
+    double pack[is3d::SP_SIZE];
+    int st = is3d::sampler_setup_cell(c, view.tb, fl, gla.root.data(), gla.weight.data(), gla.points, totA, totB, pack);
+    if (st == is3d::CELL_SKIPPED || st == is3d::CELL_OUT_OF_TABLE) continue;
+    yield += is3d::cell_mean_yield(pack, fl.df_mode, totA, totB, totD);
+    if (!(pack[is3d::SP_DNTOT] > 0.0)) continue;
+    is3d::Philox rng;
+    rng.init(seed, (uint64_t)ic, 0xFFFFFFFFu);
+    long n = is3d::poisson_sample(rng, (double)nevents * pack[is3d::SP_DNTOT]);
+    auto pk = [&](int k) { return pack[k]; };
+    for (long h = 0; h < n; h++) {
+      proposed++;
+      is3d::Philox r;
+      r.init(seed, (uint64_t)ic, (uint32_t)h);
+      (void)r.canonical();     // event label
+      double target = r.canonical() * (pack[is3d::SP_WA] * totA + pack[is3d::SP_WB] * totB);
+      int a = 0, b = ns - 1;
+      while (a < b) { int m = (a + b) >> 1; if (pack[is3d::SP_WA] * cumA[m] + pack[is3d::SP_WB] * cumB[m] > target) b = m; else a = m + 1; }
+      const particle_info &p = L.pdg[L.chosen[a]];
+      long samples = 0;
+      is3d::LrfMomentum q;
+      if (!is3d::sample_hadron(r, pk, fl.df_mode, p.mass, (double)p.sign, (double)p.baryon, &samples, &q)) continue;
+      is3d::LabParticle lab = is3d::boost_to_lab(r, pk, q, p.mass, fl.dimension, y_max);
+      accepted++;
+      int iy = (int)floor((lab.rapidity + y_cut) / y_w);
+      if (iy >= 0 && iy < y_bins) dN_dy[(size_t)a * y_bins + iy] += 1.0;
+      int ie = (int)floor((lab.eta + eta_cut) / eta_w);
+      if (ie >= 0 && ie < eta_bins) dN_deta[(size_t)a * eta_bins + ie] += 1.0;
+      int ip = (int)floor((sqrt(lab.px * lab.px + lab.py * lab.py) - pT_min) / pT_w);
+      if (ip >= 0 && ip < pT_bins) dN_pT[(size_t)a * pT_bins + ip] += 1.0;
+    }
+  }
+  if (fl.dimension == 2) yield *= 2.0 * y_cut;
+  *yield_out = yield;
+  *proposed_out = proposed;
+  return accepted;
+}

@@ -163,3 +163,20 @@ def _dndx(self):
 
 
 OracleProblem.dndx = _dndx
+
+
+def _total_yield(self):
+    v = C.c_double()
+    rc = lib().cf_oracle_total_yield(C.byref(self.p), C.byref(self.inp), C.byref(v))
+    return rc, v.value
+
+
+def _cell_yields(self):
+    n, ns = self.inp.n_cells, self.inp.n_species
+    tot = np.zeros(n); lst = np.zeros((n, ns))
+    rc = lib().cf_oracle_cell_yields(C.byref(self.p), C.byref(self.inp), tot.ctypes.data, lst.ctypes.data)
+    return rc, tot, lst
+
+
+OracleProblem.total_yield = _total_yield
+OracleProblem.cell_yields = _cell_yields

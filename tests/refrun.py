@@ -87,3 +87,36 @@ def read_dndx_files(root: str, mcids) -> dict:
             rows.append(a[:, 1])
         out[key] = np.array(rows)
     return out
+
+
+def read_sampler_test_files(root: str, mcids, params: dict) -> dict:
+    """results/sampled/*_test.dat of a reference run with test_sampler = 1, converted back to integer COUNTS
+    (writers: EmissionFunction.cpp:685-975).  Also Nevents and the exact mean total yield dumped by the harness."""
+    from is3d_b200 import workdir
+    p = workdir.default_parameters()
+    p.update({k: str(v) for k, v in params.items()})
+    f = lambda k: float(p[k])  # noqa: E731
+    nev = int(open(os.path.join(root, "ref_dump", "nevents.txt")).read())
+    y_cut = f("y_cut")
+    yw = 2.0 * y_cut / f("y_bins")
+    ew = 2.0 * f("eta_cut") / f("eta_bins")
+    pw = (f("pT_max") - f("pT_min")) / f("pT_bins")
+    phw = 2.0 * np.pi / f("phip_bins")
+    tw = (f("tau_max") - f("tau_min")) / f("tau_bins")
+    rw = (f("r_max") - f("r_min")) / f("r_bins")
+    out = {k: [] for k in ("dN_dy", "dN_deta", "dN_pT", "dN_dphip", "dN_tau", "dN_r", "dN_phis")}
+    for m in mcids:
+        m = int(m)
+        def col(sub, stem):
+            return np.loadtxt(os.path.join(root, "results", "sampled", sub, f"{stem}_{m}_test.dat"), ndmin=2)
+        a = col("dN_dy", "dN_dy"); out["dN_dy"].append(a[:, 1] * yw * nev)
+        a = col("dN_deta", "dN_deta"); out["dN_deta"].append(a[:, 1] * ew * nev)
+        a = col("dN_2pipTdpTdy", "dN_2pipTdpTdy"); out["dN_pT"].append(a[:, 1] * (2.0 * np.pi * 2.0 * y_cut * pw * a[:, 0] * nev))
+        a = col("dN_dphipdy", "dN_dphipdy"); out["dN_dphip"].append(a[:, 1] * (2.0 * y_cut * phw * nev))
+        a = col("dN_taudtaudy", "dN_taudtaudy"); out["dN_tau"].append(a[:, 1] * (a[:, 0] * tw * nev * 2.0 * y_cut))
+        a = col("dN_2pirdrdy", "dN_2pirdrdy"); out["dN_r"].append(a[:, 1] * (2.0 * np.pi * a[:, 0] * rw * nev * 2.0 * y_cut))
+        a = col("dN_dphisdy", "dN_dphisdy"); out["dN_phis"].append(a[:, 1] * (phw * nev * 2.0 * y_cut))
+    res = {k: np.rint(np.array(v)) for k, v in out.items()}
+    res["nevents"] = nev
+    res["total_yield"] = float(np.fromfile(os.path.join(root, "ref_dump", "total_yield.bin"), dtype=np.float64)[0])
+    return res

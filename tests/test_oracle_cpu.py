@@ -36,3 +36,18 @@ def test_oracle_dndx_matches_reference_golden(libs, tmp_path, name):
     got = harness.normalise_dndx({k: harness.emulate_partial_memset(v) for k, v in clean.items()}, case["params"])
     for k in ("tau", "r", "phi"):
         harness.assert_hist_close(got[k], ref[k], rtol=1e-11, what=f"{name}/{k}")
+
+
+@pytest.mark.parametrize("name", list(cases.SAMPLER_CASES))
+def test_oracle_total_yield_matches_reference(libs, tmp_path, name):
+    """calculate_total_yield of the unmodified reference, dumped in full precision by oracle/ref_harness.cpp."""
+    case = cases.SAMPLER_CASES[name]
+    surf, ref = harness.load_golden_sampler(name)
+    root = workdir.make_workdir(str(tmp_path), case["params"], chosen=case["chosen"])
+    prob = oracle_api.OracleProblem(root, case["params"], surf)
+    rc, ntot = prob.total_yield()
+    assert rc == 0
+    # with baryon diffusion the reference multiplies V.dsigma by an UNINITIALISED dsigma_space (ParticleSampler.cpp
+    # :606-609 never calls compute_dsigma_magnitude); the diffusion term is ~1e-5 of the yield
+    tol = 1e-4 if case["params"].get("include_baryondiff_deltaf") else 1e-12
+    assert abs(ntot / float(ref["total_yield"]) - 1.0) < tol

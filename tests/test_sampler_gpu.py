@@ -1,0 +1,121 @@
+"""GPU tests of the sampler path (K5 yields, K6 Monte-Carlo sampling) through the C ABI.
+
+Parity with the reference is distributional (its std::default_random_engine / poisson / discrete distributions are
+implementation-defined): mean total yield and per-cell mean yields are compared to 1e-10, sampled per-species
+multiplicities and y / eta / pT / phi / tau / r histograms by two-sample chi^2 against histograms the unmodified
+reference produced over ~2e6 hadrons (tests/golden/make_golden_sampler.py)."""
+import numpy as np
+import pytest
+
+import cases
+import harness
+import oracle_api
+from is3d_b200 import workdir
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", list(cases.SAMPLER_CASES))
+def test_total_and_cell_yields(libs, tmp_path, name):
+    case = cases.SAMPLER_CASES[name]
+    surf, ref = harness.load_golden_sampler(name)
+    ns = ref["dN_dy"].shape[0]
+    with harness.open_session(str(tmp_path / "gpu"), case, surf) as h:
+        ntot, st = h.abi_total_yield()
+        dn_tot, dn_list, _ = h.abi_cell_yields(len(surf["tau"]), ns)
+    # reference: calculate_total_yield (see test_oracle_cpu.py for the baryon-diffusion caveat)
+    tol = 1e-4 if case["params"].get("include_baryondiff_deltaf") else 1e-10
+    assert abs(ntot / float(ref["total_yield"]) - 1.0) < tol
+    # oracle: per-cell dn_tot / dn_list of the sampler
+    root = workdir.make_workdir(str(tmp_path / "oracle"), case["params"], chosen=case["chosen"])
+    prob = oracle_api.OracleProblem(root, case["params"], surf)
+    rc, o_tot, o_list = prob.cell_yields()
+    assert rc == 0
+    np.testing.assert_allclose(dn_tot, o_tot, rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(dn_list, o_list, rtol=1e-10, atol=1e-300)
+    rc, o_ntot = prob.total_yield()
+    assert abs(ntot / o_ntot - 1.0) < 1e-10
+
+
+@pytest.mark.parametrize("name", list(cases.SAMPLER_CASES))
+def test_sampled_histograms_match_reference(libs, tmp_path, name):
+    case = cases.SAMPLER_CASES[name]
+    surf, ref = harness.load_golden_sampler(name)
+    ns = ref["dN_dy"].shape[0]
+    nev_ref = int(ref["nevents"])
+    nev = nev_ref                                  # same statistics as the reference run
+    with harness.open_session(str(tmp_path), case, surf) as h:
+        parts, counts, st = h.abi_sample(nev)
+        assert len(parts) == 0                     # test_sampler = 1: histograms only
+        hist = h.abi_sample_histograms(ns, case["params"])
+    accepted = hist["dN_deta"].sum()
+    ref_acc = ref["dN_deta"].sum()
+    # total multiplicity per event within 5 sigma (Poisson)
+    sigma = np.sqrt(accepted / nev ** 2 + ref_acc / nev_ref ** 2)
+    assert abs(accepted / nev - ref_acc / nev_ref) < 5 * sigma, (accepted / nev, ref_acc / nev_ref, sigma)
+    assert st.sampler_accepted >= accepted
+    for key in ("dN_dy", "dN_deta", "dN_pT", "dN_dphip", "dN_tau", "dN_r", "dN_phis"):
+        c2, ndf = harness.chi2_two_sample(hist[key], nev, ref[key], nev_ref)
+        assert ndf > 0
+        assert c2 < ndf + 5.0 * np.sqrt(2.0 * ndf), f"{name}/{key}: chi2 {c2:.1f} for {ndf} bins"
+    # per-species multiplicities (species with enough statistics)
+    mine, theirs = hist["dN_deta"].sum(axis=1), ref["dN_deta"].sum(axis=1).astype(float)
+    big = (mine + theirs) > 400
+    z = (mine[big] / nev - theirs[big] / nev_ref) / np.sqrt(mine[big] / nev ** 2 + theirs[big] / nev_ref ** 2)
+    assert np.abs(z).max() < 5.0, z
+
+
+def test_particle_lists_properties(libs, tmp_path):
+    """test_sampler = 0: records grouped by event, on mass shell, reproducible, and independent of cell sharding."""
+    name = "smp_s3d_m3"
+    case = cases.SAMPLER_CASES[name]
+    surf, ref = harness.load_golden_sampler(name)
+    nev = 4000
+    with harness.open_session(str(tmp_path), case, surf, overrides=dict(test_sampler=0)) as h:
+        parts, counts, st = h.abi_sample(nev)
+        again, counts2, _ = h.abi_sample(nev)
+        # two shards with their global offsets: same hadrons as the unsharded run
+        n = len(surf["tau"])
+        cut = n // 3
+        h.abi_set_surface({k: v[:cut] for k, v in surf.items()}, global_offset=0)
+        pa, ca, _ = h.abi_sample(nev)
+        h.abi_set_surface({k: v[cut:] for k, v in surf.items()}, global_offset=cut)
+        pb, cb, _ = h.abi_sample(nev)
+    assert counts.sum() == len(parts) > 0
+    assert np.array_equal(parts, again) and np.array_equal(counts, counts2)          # deterministic
+    assert np.all(np.diff(parts["event"]) >= 0)                                       # grouped by event
+    assert np.array_equal(np.bincount(parts["event"], minlength=nev), counts)
+    m2 = parts["E"] ** 2 - parts["px"] ** 2 - parts["py"] ** 2 - parts["pz"] ** 2
+    np.testing.assert_allclose(m2, parts["mass"] ** 2, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(parts["t"] ** 2 - parts["z"] ** 2, parts["tau"] ** 2, rtol=1e-12)
+    # mean multiplicity per event vs the reference's sampled mean
+    mean_ref = ref["dN_deta"].sum() / int(ref["nevents"])
+    assert abs(len(parts) / nev - mean_ref) < 5 * np.sqrt(mean_ref / nev + mean_ref / int(ref["nevents"]))
+    # sharding independence (Philox keyed by the global cell index)
+    both = np.concatenate([pa, pb])
+    key = lambda a: np.lexsort((a["pz"], a["px"], a["event"]))  # noqa: E731
+    assert len(both) == len(parts)
+    assert np.array_equal(np.sort(parts, order=["event", "px", "pz"]), np.sort(both, order=["event", "px", "pz"]))
+    assert np.array_equal(ca + cb, counts)
+
+
+def test_host_sampler_writes_oscar_lists(libs, tmp_path):
+    """operation 2 through the host layer: Nevents from the yield estimate, OSCAR files in results/."""
+    import os
+    name = "smp_s3d_m1"
+    case = cases.SAMPLER_CASES[name]
+    surf, ref = harness.load_golden_sampler(name)
+    with harness.open_session(str(tmp_path), case, surf, overrides=dict(test_sampler=0, min_num_hadrons=3000.0, max_num_samples=1000.0)) as h:
+        h.run()
+        nev = h.host.is3d_host_events(h.h)
+        n0 = h.host.is3d_host_event_particles(h.h, 0, None)
+    expect = int(min(np.ceil(3000.0 / float(ref["total_yield"])), 1000))
+    assert nev == expect
+    f = tmp_path / "results" / "particle_list_osc_1.dat"
+    lines = open(f).read().splitlines()
+    assert lines[0] == "n pid px py pz E m x y z t"
+    assert len(lines) == n0 + 1
+    if n0:
+        cols = lines[1].split()
+        assert len(cols) == 11 and cols[0] == "0"
+    assert os.path.exists(tmp_path / "results" / f"particle_list_osc_{nev}.dat")
