@@ -321,8 +321,7 @@ is3d_status is3d_spectra_device(is3d_ctx *ctx, double *out_dev, is3d_stats *stat
   }
   switch (ctx->prm.df_mode) {
     case 1: case 2: return run_spectra_df(ctx, out_dev, stats);
-    case 3: case 4: return run_spectra_feqmod(ctx, out_dev, stats);
-    case 5: return run_spectra_famod(ctx, out_dev, stats);
+    case 3: case 4: case 5: return run_spectra_feqmod(ctx, out_dev, stats);
   }
   return IS3D_ERR_INVALID;
 }

@@ -127,8 +127,7 @@ namespace is3d {
 
 // compute paths (one translation unit each)
 is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);        // df_mode 1,2
-is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);    // df_mode 3,4
-is3d_status run_spectra_famod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);     // df_mode 5
+is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);    // df_mode 3,4 and 5 (PTMA)
 is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_dev, is3d_stats *stats);
 is3d_status run_total_yield(is3d_ctx *ctx, double *ntotal, is3d_stats *stats);
 is3d_status run_cell_yields(is3d_ctx *ctx, double *dn_tot_host, double *dn_list_host, is3d_stats *stats);

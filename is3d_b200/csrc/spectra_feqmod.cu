@@ -20,6 +20,10 @@ is3d_status build_bin_arrays(is3d_ctx *ctx, const double **mT, const double **pT
                              const double **sign, const double **deg);
 void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
                    int64_t *cells_per_chunk);
+// df_mode 5 per-cell stage (spectra_famod.cu): fills the same pack layout, counters[8] = reconstruction failures,
+// counters[9] = Newton iterations
+is3d_status famod_setup_pass(is3d_ctx *ctx, int64_t begin, int64_t count, double *pack, int64_t stride, unsigned long long *counters,
+                             int64_t *launches);
 
 namespace {
 
@@ -67,6 +71,7 @@ struct FeqGrid {
   int nbins, NpT, ns;
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
+  bool w_on_dan;      // eta weight multiplies the whole p.dsigma (famod, MomentumSpectra.cpp:1617) instead of the feqmod placement
 };
 
 union ItemSlot {
@@ -136,10 +141,10 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
         const int slot = base + __popc(ballot & ((1u << lane) - 1u));
         if (linear) {
           double d = yval - eta;
-          items[slot].lin = feqmod_make_linear_item(pk, sinh(d), cosh(d), cphi, sphi, w);
+          items[slot].lin = feqmod_make_linear_item(pk, sinh(d), cosh(d), cphi, sphi, w, g.w_on_dan);
         } else {
           double d = yval - pk(FP_ETA_SCALE) * eta;
-          items[slot].mod = feqmod_make_item(pk, sinh(d), cosh(d), cphi, sphi, w);
+          items[slot].mod = feqmod_make_item(pk, sinh(d), cosh(d), cphi, sphi, w, g.w_on_dan);
         }
         item_linear[slot] = linear ? 1 : 0;
         item_cell[slot] = (int)(cell - 0);   // index inside this pass's pack / renorm arrays
@@ -197,7 +202,8 @@ void launch_feqmod(bool reg, bool outflow, dim3 grid, cudaStream_t st, const dou
 is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
 {
   const is3d_params &p = ctx->prm;
-  if (ctx->gla_pts <= 0) { ctx->set_error("Gauss-Laguerre tables not set"); return IS3D_ERR_INVALID; }
+  if (p.df_mode != 5 && ctx->gla_pts <= 0) { ctx->set_error("Gauss-Laguerre tables not set"); return IS3D_ERR_INVALID; }
+  if (p.df_mode == 5 && ctx->npdg <= 0) { ctx->set_error("PDG table not set (is3d_set_pdg)"); return IS3D_ERR_INVALID; }
   const int64_t n = ctx->surf.n;
   const int64_t total = (int64_t)ctx->ns * ctx->NpT * ctx->Nphi * ctx->Ny;
   const int nbins = ctx->ns * ctx->NpT;
@@ -214,6 +220,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   g.nbins = nbins; g.NpT = ctx->NpT; g.ns = ctx->ns;
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
   g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw;
+  g.w_on_dan = (p.df_mode == 5);
 
   const int nslices = (nbins + kThreads * kBins - 1) / (kThreads * kBins);
   const int64_t blocks_per_chunk = (int64_t)nslices * ctx->Ny * ctx->Nphi;
@@ -244,11 +251,15 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   for (int64_t begin = 0; begin < n; begin += macro) {
     int64_t count = n - begin < macro ? n - begin : macro;
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-    feqmod_setup_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
-        ctx->surf, begin, count, ctx->tb, fl, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts, (double *)pack, stride,
-        (unsigned long long *)counters);
-    IS3D_CUDA_TRY(ctx, cudaGetLastError());
-    launches++;
+    if (p.df_mode == 5) {
+      IS3D_TRY(famod_setup_pass(ctx, begin, count, (double *)pack, stride, (unsigned long long *)counters, &launches));
+    } else {
+      feqmod_setup_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
+          ctx->surf, begin, count, ctx->tb, fl, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts, (double *)pack, stride,
+          (unsigned long long *)counters);
+      IS3D_CUDA_TRY(ctx, cudaGetLastError());
+      launches++;
+    }
     if (species_renorm) {
       int64_t work = count * ctx->ns;
       feqmod_renorm_kernel<<<(unsigned)((work + 127) / 128), 128, 0, ctx->stream>>>(
@@ -295,6 +306,8 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
     if (h_counters[5]) IS3D_CUDA_TRY(ctx, cudaMemcpy(&tau_p, ctx->surf.col[0] + (h_counters[5] - 1), sizeof(double), cudaMemcpyDeviceToHost));
     stats->tau_breakdown = tau_b;
     stats->tau_pl_negative = tau_p;
+    stats->reconstruction_failures = (int64_t)h_counters[8];
+    stats->newton_iterations = (int64_t)h_counters[9];
     stats->kernel_ms = ms_total;
     stats->kernel_launches = launches;
   }

@@ -58,6 +58,16 @@ SPECTRA_CASES = {
     "s2d_m4_box_phi48": dict(surface=("s3d", dict(n=40, seed=3, dimension=2, stress=0.3)), params=_p(df_mode=4, dimension=2, hrg_eos=3),
                              chosen=os.path.join(_GOLDEN, "chosen_box_small.dat"), tables=dict(phi_table="phi_table_48pt.dat")),
     "s3d_m3_smash_9cells": dict(surface=("s3d", dict(n=9, seed=13, stress=0.3)), params=_p(df_mode=3), chosen="smash"),
+    # ---- K3: PTMA modified anisotropic distribution (df_mode 5), reference-faithful initial-guess chain ----
+    # BASELINE.json config 4: VAH-like surface (large P_L / P_T anisotropy) with df_mode 5
+    "vah_m5": dict(surface=("s3d", dict(n=200, seed=51, vah=True)), params=_p(df_mode=5), chosen="pikp"),
+    "s3d_m5": dict(surface=("s3d", dict(n=200, seed=52)), params=_p(df_mode=5), chosen="pikp"),
+    "s3d_m5_stress_outflow": dict(surface=("s3d", dict(n=200, seed=53, stress=0.3)), params=_p(df_mode=5, outflow=1), chosen="pikp"),
+    "s2d_m5_phi48": dict(surface=("s3d", dict(n=40, seed=54, dimension=2, vah=True)), params=_p(df_mode=5, dimension=2, hrg_eos=1),
+                         chosen="pikp", tables=dict(phi_table="phi_table_48pt.dat")),
+    "vah_m5_baryon": dict(surface=("s3d", dict(n=150, seed=55, vah=True, baryon=True)),
+                          params=_p(df_mode=5, include_baryon=1, include_baryondiff_deltaf=1), chosen="pikp"),
+    "vah_m5_smash_6cells": dict(surface=("s3d", dict(n=6, seed=56, vah=True)), params=_p(df_mode=5), chosen="smash"),
 }
 
 

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "../../is3d_b200/csrc/spectra_df.cuh"
@@ -283,4 +284,86 @@ extern "C" long hostcheck_sampler(const char *root, long nevents, double *dN_dy,
   *yield_out = yield;
   *proposed_out = proposed;
   return accepted;
+}
+
+// ---- df_mode 5 (K3): serial-reducer Newton solve per cell with the reference's chain, then the K2 momentum math ----
+#include "../../is3d_b200/csrc/aniso.cuh"
+
+extern "C" long hostcheck_spectra_famod(const char *root, int chain_on, double *out, long capacity, long *stats5)
+{
+  Loaded L;
+  L.load(root);
+  is3d::FamodFlags fl;
+  fl.dimension = L.par.getVal("dimension"); fl.include_baryon = L.par.getVal("include_baryon");
+  fl.include_shear = L.par.getVal("include_shear_deltaf"); fl.include_baryondiff = L.par.getVal("include_baryondiff_deltaf");
+  fl.deta_min = L.par.getVal("deta_min");
+  const bool outflow = (int)L.par.getVal("outflow");
+  const int ns = (int)L.chosen.size(), npT = (int)L.pT.getNumberOfRows(), nphi = (int)L.phi.getNumberOfRows();
+  const int ny = fl.dimension == 3 ? (int)L.y.getNumberOfRows() : 1;
+  const int neta = fl.dimension == 3 ? 1 : (int)L.eta.getNumberOfRows();
+  const long total = (long)ns * npT * nphi * ny;
+  if (total > capacity) return -total;
+  std::vector<double> acc(total, 0.0);
+  std::vector<double> pm, ps, pd;
+  for (auto &p : L.pdg) { pm.push_back(p.mass); ps.push_back(p.sign); pd.push_back(p.gspin); }
+  double gl16[96];
+  is3d::fill_gl16_table(gl16);
+  is3d::AnisoHadrons h{pm.data(), ps.data(), pd.data(), (int)std::min<size_t>(320, pm.size()), gl16};
+  is3d::SurfaceView sv;
+  for (int k = 0; k < 25; k++) sv.col[k] = L.surf.col[k].data();
+  sv.n = L.surf.size();
+  is3d::FamodChain chain{0, 0, 0, false};
+  is3d::SerialReducer red;
+  long nbreak = 0, npl = 0, nfail = 0, iters = 0;
+  for (int64_t ic = 0; ic < sv.n; ic++) {
+    is3d::Cell c = is3d::load_cell(sv, ic, fl.include_baryon != 0);
+    double pack[is3d::FP_SIZE];
+    int it;
+    int st = is3d::famod_setup_cell(red, c, fl, h, chain_on ? &chain : nullptr, pack, &it);
+    if (st == is3d::CELL_SKIPPED) continue;
+    iters += it;
+    if (st & is3d::CELL_BREAKDOWN) nbreak++;
+    if (st & is3d::CELL_PL_NEGATIVE) npl++;
+    if (st & is3d::CELL_RECONSTRUCTION_FAIL) nfail++;
+    auto pk = [&](int k) { return pack[k]; };
+    for (int iy = 0; iy < ny; iy++) {
+      double yv = fl.dimension == 3 ? L.y.get(1, iy + 1) : 0.0;
+      for (int ie = 0; ie < neta; ie++) {
+        double etav = fl.dimension == 3 ? pack[is3d::DP_ETA] : L.eta.get(1, ie + 1);
+        double w = fl.dimension == 3 ? 1.0 : L.eta.get(2, ie + 1);
+        bool linear = pack[is3d::FP_BREAKDOWN] != 0.0;
+        if (fl.dimension == 3 && !linear && pack[is3d::FP_DETA] < 0.01 && fabs(yv - etav) < pack[is3d::FP_DETA]) linear = true;
+        double d = linear ? (yv - etav) : (yv - pack[is3d::FP_ETA_SCALE] * etav);
+        double sh = sinh(d), ch = cosh(d);
+        for (int ip = 0; ip < nphi; ip++) {
+          double ph = L.phi.get(1, ip + 1);
+          is3d::DfItem lin;
+          is3d::FeqmodItem mod;
+          if (linear) lin = is3d::feqmod_make_linear_item(pk, sh, ch, cos(ph), sin(ph), w, true);
+          else mod = is3d::feqmod_make_item(pk, sh, ch, cos(ph), sin(ph), w, true);
+          for (int s = 0; s < ns; s++) {
+            const particle_info &p = L.pdg[L.chosen[s]];
+            for (int ipT = 0; ipT < npT; ipT++) {
+              double pTv = L.pT.get(1, ipT + 1), m2 = p.mass * p.mass, mT = sqrt(m2 + pTv * pTv);
+              is3d::DfBin b{mT, pTv, mT * mT, mT * pTv, pTv * pTv, m2, (double)p.baryon, (double)p.sign};
+              double v;
+              if (!linear) {
+                if (fl.include_baryon) v = outflow ? is3d::feqmod_eval<true, true>(mod, b, mod.renorm) : is3d::feqmod_eval<true, false>(mod, b, mod.renorm);
+                else v = outflow ? is3d::feqmod_eval<false, true>(mod, b, mod.renorm) : is3d::feqmod_eval<false, false>(mod, b, mod.renorm);
+              } else {
+                v = fl.include_baryon ? eval_dispatch<2, true>(false, outflow, lin, b) : eval_dispatch<2, false>(false, outflow, lin, b);
+              }
+              acc[iy + (long)ny * (ip + (long)nphi * (ipT + (long)npT * s))] += v;
+            }
+          }
+        }
+      }
+    }
+  }
+  for (int s = 0; s < ns; s++) {
+    double g = (double)L.pdg[L.chosen[s]].gspin;
+    for (long k = 0; k < (long)npT * nphi * ny; k++) out[(long)s * npT * nphi * ny + k] = is3d::kCooperFryePrefactor * g * acc[(long)s * npT * nphi * ny + k];
+  }
+  if (stats5) { stats5[0] = nbreak; stats5[1] = npl; stats5[2] = nfail; stats5[3] = iters; stats5[4] = 0; }
+  return total;
 }

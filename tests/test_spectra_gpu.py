@@ -1,4 +1,4 @@
-"""GPU parity of the continuous Cooper-Frye spectra (K1: df_mode 1, 2; K2: df_mode 3, 4) through the C ABI against the golden
+"""GPU parity of the continuous Cooper-Frye spectra (K1: df_mode 1, 2; K2: df_mode 3, 4; K3: df_mode 5) through the C ABI against the golden
 vectors produced by the unmodified reference (tests/golden/make_golden.py)."""
 import numpy as np
 import pytest
@@ -8,7 +8,7 @@ import harness
 
 pytestmark = pytest.mark.gpu
 
-DF_CASES = [n for n, c in cases.SPECTRA_CASES.items() if c["params"]["df_mode"] in (1, 2, 3, 4)]
+DF_CASES = [n for n, c in cases.SPECTRA_CASES.items() if c["params"]["df_mode"] in (1, 2, 3, 4, 5)]
 
 
 @pytest.mark.parametrize("name", DF_CASES)
