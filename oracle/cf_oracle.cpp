@@ -507,6 +507,8 @@ int spectra_feqmod(const cf_params *p, const cf_inputs *in, double *out, cf_stat
   return 0;
 }
 
+int spectra_famod(const cf_params *p, const cf_inputs *in, double *out, cf_stats *st);   // defined below
+
 }  // namespace
 
 extern "C" int cf_oracle_spectra(const cf_params *p, const cf_inputs *in, double *out, cf_stats *st)
@@ -519,6 +521,7 @@ extern "C" int cf_oracle_spectra(const cf_params *p, const cf_inputs *in, double
   switch (p->df_mode) {
     case 1: case 2: return spectra_df(p, in, out, st);
     case 3: case 4: return spectra_feqmod(p, in, out, st);
+    case 5: return spectra_famod(p, in, out, st);
     default: return 4;
   }
 }
@@ -774,3 +777,307 @@ extern "C" int cf_oracle_cell_yields(const cf_params *p, const cf_inputs *in, do
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// df_mode 5: PTMA modified anisotropic distribution.
+// AnisoVariables.cpp: compute_F :15-132, compute_J :134-300, line_backtrack :302-391, find_anisotropic_variables
+// :393-539, compute_famod_coefficient :541-643; calculate_dN_pTdpTdphidy_famod, MomentumSpectra.cpp:1049-1682.
+// The 16-point generalized Gauss-Laguerre rules (AnisoVariables.h:15-121) are regenerated here by Newton iteration on
+// the Laguerre recurrence instead of being pasted.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+const double four_pi2_hbarC3 = 4.0 * pow(M_PI, 2) * pow(hbarC, 3);
+
+struct GenLaguerre16 {
+  double root[4][16], weight[4][16];     // index by alpha = 1..3
+  static long double L(int n, int a, long double x, long double *Lnm1)
+  {
+    long double p0 = 1.0L, p1 = 1.0L + a - x;
+    if (n == 0) { *Lnm1 = 0; return p0; }
+    for (int k = 1; k < n; k++) { long double p2 = ((2 * k + 1 + a - x) * p1 - (k + a) * p0) / (k + 1); p0 = p1; p1 = p2; }
+    *Lnm1 = p0;
+    return p1;
+  }
+  GenLaguerre16()
+  {
+    const int n = 16;
+    for (int a = 1; a <= 3; a++) {
+      // initial guesses from the asymptotic formula, refined with Newton + deflation-free bracketing by ordering
+      long double x[16];
+      for (int i = 0; i < n; i++) {
+        if (i == 0) x[i] = (1.0L + a) * (3.0L + 0.92L * a) / (1.0L + 2.4L * n + 1.8L * a);
+        else if (i == 1) x[i] = x[0] + (15.0L + 6.25L * a) / (1.0L + 0.9L * a + 2.5L * n);
+        else { long double ai = i - 1; x[i] = x[i - 1] + ((1.0L + 2.55L * ai) / (1.9L * ai) + 1.26L * ai * a / (1.0L + 3.5L * ai)) * (x[i - 1] - x[i - 2]) / (1.0L + 0.3L * a); }
+        for (int it = 0; it < 100; it++) {
+          long double lm1, ln = L(n, a, x[i], &lm1);
+          long double dl = (n * ln - (n + a) * lm1) / x[i];      // derivative of L_n^a
+          long double dx = ln / dl;
+          x[i] -= dx;
+          if (fabsl(dx) <= 1e-19L * fabsl(x[i])) break;
+        }
+        long double lm1, ln = L(n, a, x[i], &lm1);
+        (void)ln;
+        long double dl = -(n + a) * lm1 / x[i];                   // L_n(x_i) = 0
+        // w_i = Gamma(n + a + 1) / (n! x_i [L_n'(x_i)]^2)
+        long double w = tgammal((long double)(n + a + 1)) / (tgammal((long double)(n + 1)) * x[i] * dl * dl);
+        root[a][i] = (double)x[i]; weight[a][i] = (double)w;
+      }
+    }
+  }
+};
+const GenLaguerre16 &gl16() { static GenLaguerre16 g; return g; }
+
+struct Hadrons { const double *mass, *sign, *deg; int n; };
+
+void t_functions(double z, double *t200, double *t220, double *t201, double *t402, double *t421, double *t440)
+{
+  const double delta = 0.01;
+  *t200 = *t220 = *t201 = *t402 = *t421 = *t440 = 0.0;
+  if (z > delta || (z < -delta && z > -1.)) {
+    double t = (z > 0) ? atan(sqrt(z)) / sqrt(z) : atanh(sqrt(-z)) / sqrt(-z), z2 = z * z;
+    *t200 = 1. + (1. + z) * t; *t220 = (-1. + (1. + z) * t) / z; *t201 = (1. + (z - 1.) * t) / z;
+    *t402 = (3. * (z - 1.) + (z * (3. * z - 2.) + 3.) * t) / (4. * z2);
+    *t421 = (3. + z + (1. + z) * (z - 3.) * t) / (4. * z2);
+    *t440 = (-(3. + 5. * z) + 3. * (z + 1.) * (z + 1.) * t) / (4. * z2);
+  } else if (fabs(z) <= delta) {     // Taylor series of the same functions
+    double z2 = z * z, z3 = z2 * z, z4 = z3 * z, z5 = z4 * z, z6 = z5 * z;
+    *t200 = 2. + 2. / 3. * z - 2. / 15. * z2 + 2. / 35. * z3 - 2. / 63. * z4 + 2. / 99. * z5 - 2. / 143. * z6;
+    *t220 = 2. / 3. - 2. / 15. * z + 2. / 35. * z2 - 2. / 63. * z3 + 2. / 99. * z4 - 2. / 143. * z5 + 2. / 195. * z6;
+    *t201 = 4. / 3. - 8. / 15. * z + 12. / 35. * z2 - 16. / 63. * z3 + 20. / 99. * z4 - 24. / 143. * z5 + 28. / 195. * z6;
+    *t402 = 16. / 15. - 16. / 35. * z + 32. / 105. * z2 - 160. / 693. * z3 + 80. / 429. * z4 - 112. / 715. * z5 + 448. / 3315. * z6;
+    *t421 = 4. / 15. - 8. / 105. * z + 4. / 105. * z2 - 16. / 693. * z3 + 20. / 1287. * z4 - 8. / 715. * z5 + 28. / 3315. * z6;
+    *t440 = 2. / 5. - 2. / 35. * z + 2. / 105. * z2 - 2. / 231. * z3 + 2. / 429. * z4 - 2. / 715. * z5 + 2. / 1105. * z6;
+  }
+}
+
+void compute_F(const Hadrons &h, double Ea, double PTa, double PLa, const double *X, double *F)
+{
+  double lambda = X[0], aT = X[1], aL = X[2], aT2 = aT * aT, aL2 = aL * aL;
+  double common_factor = aT2 * aL * lambda * lambda * lambda * lambda / four_pi2_hbarC3;
+  double I_200 = 0, I_220 = 0, I_201 = 0;
+  for (int n = 0; n < h.n; n++) {
+    if (h.mass[n] == 0) continue;
+    double mbar = h.mass[n] / lambda, mbar2 = mbar * mbar, a = 0, b = 0, c = 0;
+    for (int i = 0; i < 16; i++) {
+      double pbar = gl16().root[2][i], weight = gl16().weight[2][i];
+      double Ebar = sqrt(pbar * pbar + mbar2), w = sqrt(aL2 + mbar2 / (pbar * pbar)), z = (aT2 - aL2) / (w * w);
+      double t200, t220, t201, u1, u2, u3;
+      t_functions(z, &t200, &t220, &t201, &u1, &u2, &u3);
+      double cw = pbar * weight * exp(pbar) / (exp(Ebar) + h.sign[n]);
+      a += cw * t200 * w; b += cw * t220 / w; c += cw * t201 / w;
+    }
+    I_200 += a * h.deg[n]; I_220 += b * h.deg[n]; I_201 += c * h.deg[n];
+  }
+  I_200 *= common_factor; I_220 *= common_factor * aL2; I_201 *= common_factor * aT2 / 2.;
+  F[0] = I_200 - Ea; F[1] = I_201 - PTa; F[2] = I_220 - PLa;
+}
+
+void j_sums(const Hadrons &h, double lambda, double aT2, double aL2, double S[6])
+{
+  for (int k = 0; k < 6; k++) S[k] = 0;
+  for (int n = 0; n < h.n; n++) {
+    if (h.mass[n] == 0) continue;
+    double mbar = h.mass[n] / lambda, mbar2 = mbar * mbar, s[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 16; i++) {
+      double pbar = gl16().root[3][i], weight = gl16().weight[3][i], pbar2 = pbar * pbar;
+      double Ebar = sqrt(pbar2 + mbar2), w = sqrt(aL2 + mbar2 / pbar2), z = (aT2 - aL2) / (w * w);
+      double t200, t220, t201, t402, t421, t440;
+      t_functions(z, &t200, &t220, &t201, &t402, &t421, &t440);
+      double q = exp(Ebar) + h.sign[n], cw = weight * exp(pbar + Ebar) / (q * q);
+      s[0] += Ebar * cw * t200 * w; s[1] += Ebar * cw * t201 / w; s[2] += Ebar * cw * t220 / w;
+      s[3] += pbar2 / Ebar * cw * t402 / w; s[4] += pbar2 / Ebar * cw * t421 / w; s[5] += pbar2 / Ebar * cw * t440 / w;
+    }
+    for (int k = 0; k < 6; k++) S[k] += s[k] * h.deg[n];
+  }
+}
+
+void compute_J(const Hadrons &h, double Ea, double PTa, double PLa, const double *X, const double *F, double J[3][3])
+{
+  double lambda = X[0], aT = X[1], aL = X[2], aT2 = aT * aT, aL2 = aL * aL, lambda2 = lambda * lambda, lambda3 = lambda2 * lambda;
+  double lambda_aT3 = lambda * aT2 * aT, lambda_aL3 = lambda * aL2 * aL, cf = aT2 * aL * lambda2 * lambda3 / four_pi2_hbarC3;
+  double S[6];
+  j_sums(h, lambda, aT2, aL2, S);
+  double J_2001 = S[0] * cf, J_2011 = S[1] * cf * aT2 / 2., J_2201 = S[2] * cf * aL2;
+  double J_402m1 = S[3] * cf * aT2 * aT2 / 8., J_421m1 = S[4] * cf * aT2 * aL2 / 2., J_440m1 = S[5] * cf * aL2 * aL2;
+  double Eai = F[0] + Ea, PTai = F[1] + PTa, PLai = F[2] + PLa;
+  J[0][0] = J_2001 / lambda2; J[0][1] = 2. * (Eai + PTai) / aT;    J[0][2] = (Eai + PLai) / aL;
+  J[1][0] = J_2011 / lambda2; J[1][1] = 4. * J_402m1 / lambda_aT3; J[1][2] = J_421m1 / lambda_aL3;
+  J[2][0] = J_2201 / lambda2; J[2][1] = 2. * J_421m1 / lambda_aT3; J[2][2] = J_440m1 / lambda_aL3;
+}
+
+double line_backtrack(const Hadrons &h, double Ea, double PTa, double PLa, const double *Xc, const double *dX, double dX_abs, double g0, double *F)
+{
+  const double tol_dX = 1.e-4;
+  double X[3] = {Xc[0] + dX[0], Xc[1] + dX[1], Xc[2] + dX[2]};
+  compute_F(h, Ea, PTa, PLa, X, F);
+  double f = (F[0] * F[0] + F[1] * F[1] + F[2] * F[2]) / 2., gprime0 = -2. * g0, l = 1, alpha = 0.0001, lroot = 0, lprev = 0, fprev = 0;
+  for (int n = 0; n < 20; n++) {
+    if ((l * dX_abs) <= tol_dX) return l;
+    else if (f <= (g0 + l * alpha * gprime0)) return l;
+    else if (n == 0) lroot = -gprime0 / (2. * (f - g0 - gprime0));
+    else {
+      double a = ((f - g0 - l * gprime0) / (l * l) - (fprev - g0 - lprev * gprime0) / (lprev * lprev)) / (l - lprev);
+      double b = (-lprev * (f - g0 - l * gprime0) / (l * l) + l * (fprev - g0 - lprev * gprime0) / (lprev * lprev)) / (l - lprev);
+      if (a == 0) lroot = -gprime0 / (2. * b);
+      else {
+        double z = b * b - 3. * a * gprime0;
+        if (z < 0) lroot = 0.5 * l; else if (b <= 0) lroot = (-b + sqrt(z)) / (3. * a); else lroot = -gprime0 / (b + sqrt(z));
+      }
+      lroot = fmin(lroot, 0.5 * l);
+    }
+    lprev = l; fprev = f;
+    l = fmax(lroot, 0.5 * l);
+    for (int i = 0; i < 3; i++) X[i] = Xc[i] + l * dX[i];
+    compute_F(h, Ea, PTa, PLa, X, F);
+    f = (F[0] * F[0] + F[1] * F[1] + F[2] * F[2]) / 2.;
+  }
+  return l;
+}
+
+struct Aniso { double lambda, aT, aL; bool failed; int iterations; };
+
+// J dX = -F by LU with partial pivoting (gsl_linalg_LU_decomp / LU_solve)
+void lu_solve3(double A[3][3], const double rhs[3], double x[3])
+{
+  int perm[3] = {0, 1, 2};
+  for (int j = 0; j < 2; j++) {
+    int ip = j; double mx = fabs(A[j][j]);
+    for (int i = j + 1; i < 3; i++) if (fabs(A[i][j]) > mx) { mx = fabs(A[i][j]); ip = i; }
+    if (ip != j) { for (int k = 0; k < 3; k++) { double t = A[j][k]; A[j][k] = A[ip][k]; A[ip][k] = t; } int t = perm[j]; perm[j] = perm[ip]; perm[ip] = t; }
+    if (A[j][j] != 0.0) for (int i = j + 1; i < 3; i++) { double a = A[i][j] / A[j][j]; A[i][j] = a; for (int k = j + 1; k < 3; k++) A[i][k] -= a * A[j][k]; }
+  }
+  double b[3] = {rhs[perm[0]], rhs[perm[1]], rhs[perm[2]]};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < i; j++) b[i] -= A[i][j] * b[j];
+  for (int i = 2; i >= 0; i--) { for (int j = i + 1; j < 3; j++) b[i] -= A[i][j] * b[j]; b[i] /= A[i][i]; }
+  for (int i = 0; i < 3; i++) x[i] = b[i];
+}
+
+Aniso find_anisotropic_variables(const Hadrons &h, double E, double pl, double pt, double lambda_0, double aT_0, double aL_0)
+{
+  Aniso fail{lambda_0, aT_0, aL_0, true, 0};
+  double Ea = E, PTa = pt, PLa = pl;
+  if (Ea < 0 || PTa < 0 || PLa < 0) return fail;
+  double X[3] = {lambda_0, aT_0, aL_0}, dX[3], F[3], J[3][3];
+  compute_F(h, Ea, PTa, PLa, X, F);
+  double stepmax = 100. * fmax(sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2]), 3.);
+  for (int n = 0; n < 30; n++) {
+    compute_J(h, Ea, PTa, PLa, X, F, J);
+    double f = (F[0] * F[0] + F[1] * F[1] + F[2] * F[2]) / 2.;
+    for (int i = 0; i < 3; i++) F[i] *= -1.;
+    lu_solve3(J, F, dX);
+    double dX_abs = sqrt(dX[0] * dX[0] + dX[1] * dX[1] + dX[2] * dX[2]);
+    if (dX_abs > stepmax) { for (int i = 0; i < 3; i++) dX[i] *= stepmax / dX_abs; dX_abs = stepmax; }
+    double l = line_backtrack(h, Ea, PTa, PLa, X, dX, dX_abs, f, F);
+    for (int i = 0; i < 3; i++) X[i] += (l * dX[i]);
+    double F_abs = sqrt(F[0] * F[0] + F[1] * F[1] + F[2] * F[2]);
+    dX_abs *= l;
+    if (X[0] < 0 || X[1] < 0 || X[2] < 0) { fail.iterations = n + 1; return fail; }
+    else if (dX_abs <= 1.e-4 && F_abs <= 1.e-4) return Aniso{X[0], X[1], X[2], false, n + 1};
+  }
+  fail.iterations = 30;
+  return fail;
+}
+
+int spectra_famod(const cf_params *p, const cf_inputs *in, double *out, cf_stats *st)
+{
+  const double prefactor = pow(2.0 * M_PI * hbarC, -3);
+  Grids g(p, in);
+  const int npart = in->n_species, npT = in->n_pT, nphi = in->n_phi, ny = g.ny;
+  Hadrons h{in->pdg_mass, in->pdg_sign, in->pdg_degeneracy, (int)fmin(320, in->n_pdg)};
+  const double detB_min = p->deta_min;
+  double lambda_prev = 0, aT_prev = 0, aL_prev = 0;
+  bool previous_success = false;
+  for (long icell = 0; icell < in->n_cells; icell++) {
+    CellState c;
+    if (!load_cell(p, in, icell, true, false, &c)) { st->cells_skipped++; continue; }
+    if (p->dimension == 3) g.eta[0] = c.eta;
+    double T = c.T, tau2 = c.tau2;
+    Basis b = milne_basis(c);
+    PiLRF l = boost_pi(c, b);
+    double pl = c.P + c.bulkPi + l.zz, pt = c.P + c.bulkPi - l.zz / 2.;
+    double piTxx = 0, piTxy = 0, piTyy = 0, WTzx = 0, WTzy = 0;
+    if (p->include_shear_deltaf) { piTxx = (l.xx - l.yy) / 2.; piTxy = l.xy; piTyy = -piTxx; WTzx = l.xz; WTzy = l.yz; }
+    double lambda = T, aT = 1, aL = 1, upsilonB = c.alphaB;
+    bool breaks = false;
+    if (pl < 0 || pt < 0) { st->cells_pl_negative++; breaks = true; }
+    else {
+      const bool prev = p->famod_chain && previous_success;
+      if (prev) { lambda = lambda_prev; aT = aT_prev; aL = aL_prev; }
+      Aniso X = find_anisotropic_variables(h, c.E, pl, pt, lambda, aT, aL);
+      if (X.failed && prev) {
+        lambda = T; aT = 1; aL = 1;
+        X = find_anisotropic_variables(h, c.E, pl, pt, lambda, aT, aL);
+        if (X.failed) { breaks = true; st->reconstruction_failures++; previous_success = false; }
+        else { lambda = X.lambda; aT = X.aT; aL = X.aL; lambda_prev = lambda; aT_prev = aT; aL_prev = aL; previous_success = true; }
+      } else { lambda = X.lambda; aT = X.aT; aL = X.aL; lambda_prev = lambda; aT_prev = aT; aL_prev = aL; previous_success = true; }
+      st->newton_iterations += X.iterations;
+    }
+    // compute_famod_coefficient
+    double S[6], aT2 = aT * aT, aL2 = aL * aL, lambda2 = lambda * lambda, cf = aT2 * aL * lambda * lambda2 * lambda2 / four_pi2_hbarC3;
+    j_sums(h, lambda, aT2, aL2, S);
+    double betapiperp = (S[3] * cf * aT2 * aT2 / 8.) / (aT2 * lambda), betaWperp = (S[4] * cf * aT2 * aL2 / 2.) / (aT * aL * lambda);
+    double shear_coeff = 0.5 / betapiperp, diff_coeff = 1. / betaWperp, detA = aT * aT * aL;
+    double Cxx = 1. + shear_coeff * piTxx, Cxy = shear_coeff * piTxy, Cxz = diff_coeff * WTzx * aT / (aT + aL);
+    double Cyx = Cxy, Cyy = 1. + shear_coeff * piTyy, Cyz = diff_coeff * WTzy * aT / (aT + aL);
+    double Czx = diff_coeff * WTzx * aL / (aT + aL), Czy = diff_coeff * WTzy * aL / (aT + aL), Czz = 1.;
+    double detC = Cxx * (Cyy * Czz - Cyz * Czy) - Cxy * (Cyx * Czz - Cyz * Czx) + Cxz * (Cyx * Czy - Cyy * Czx);
+    double Bxx = aT + aT * shear_coeff * piTxx, Bxy = aT * shear_coeff * piTxy, Bxz = diff_coeff * WTzx * aT * aL / (aT + aL);
+    double Byy = aT + aT * shear_coeff * piTyy, Byz = diff_coeff * WTzy * aT * aL / (aT + aL), Bzz = aL;
+    double detB = detC * detA, detB_bulk_two_thirds = (2. * aT + aL) * (2. * aT + aL) / 9.;
+    double B[9] = {Bxx, Bxy, Bxz, Bxy, Byy, Byz, Bxz, Byz, Bzz}, B_inv[9];
+    lu_invert3(B, B_inv);
+    if (detB <= detB_min) breaks = true;
+    double eta_scale = 1;
+    if (detB > detB_min && p->dimension == 2) eta_scale = detB / detB_bulk_two_thirds;
+    double renorm = eta_scale / detC;
+    if (std::isnan(renorm) || std::isinf(renorm)) breaks = true;
+    if (breaks) st->cells_breakdown++;
+    for (int ipart = 0; ipart < npart; ipart++) {
+      double mass = in->mass[ipart], mass2 = mass * mass, sign = in->sign[ipart], degeneracy = in->degeneracy[ipart], baryon = in->baryon[ipart];
+      double chem = baryon * c.alphaB, chem_effect = baryon * upsilonB;
+      for (int ipT = 0; ipT < npT; ipT++) {
+        double pT = g.pT[ipT], mT = sqrt(mass2 + pT * pT), mT_over_tau = mT / c.tau;
+        for (int iphip = 0; iphip < nphi; iphip++) {
+          double px = pT * g.cosphi[iphip], py = pT * g.sinphi[iphip];
+          for (int iy = 0; iy < ny; iy++) {
+            double y = g.y[iy], eta_integral = 0;
+            for (int ieta = 0; ieta < g.neta; ieta++) {
+              double eta = g.eta[ieta], eta_weight = g.etaw[ieta];
+              bool narrow = (p->dimension == 3 && !breaks && detB < 0.01 && fabs(y - eta) < detB);
+              double p_dsigma, f;
+              if (breaks || narrow) {
+                double ptau = mT * cosh(y - eta), pn = mT_over_tau * sinh(y - eta), tau2_pn = tau2 * pn;
+                p_dsigma = ptau * c.dat + px * c.dax + py * c.day + pn * c.dan;
+                if (p->outflow && p_dsigma <= 0) continue;
+                double u_p = ptau * c.ut - px * c.ux - py * c.uy - tau2_pn * c.un;
+                f = 1. / (exp(u_p / T - chem) + sign);
+              } else {
+                double ptau = mT * cosh(y - eta_scale * eta), pn = mT_over_tau * sinh(y - eta_scale * eta), tau2_pn = tau2 * pn;
+                p_dsigma = ptau * c.dat + px * c.dax + py * c.day + pn * c.dan;
+                if (p->outflow && p_dsigma <= 0.0) continue;
+                double pLRF[3] = {-b.Xt * ptau + b.Xx * px + b.Xy * py + b.Xn * tau2_pn, b.Yx * px + b.Yy * py, -b.Zt * ptau + b.Zn * tau2_pn};
+                double pmod[3];
+                for (int i = 0; i < 3; i++) pmod[i] = B_inv[3 * i] * pLRF[0] + B_inv[3 * i + 1] * pLRF[1] + B_inv[3 * i + 2] * pLRF[2];
+                for (int it = 0; it < 5; it++) {
+                  double prev[3] = {pmod[0], pmod[1], pmod[2]}, back[3], dp[3];
+                  for (int i = 0; i < 3; i++) back[i] = B[3 * i] * prev[0] + B[3 * i + 1] * prev[1] + B[3 * i + 2] * prev[2];
+                  for (int i = 0; i < 3; i++) dp[i] = pLRF[i] - back[i];
+                  if (sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) <= 1.e-16) break;
+                  for (int i = 0; i < 3; i++) pmod[i] = prev[i] + (B_inv[3 * i] * dp[0] + B_inv[3 * i + 1] * dp[1] + B_inv[3 * i + 2] * dp[2]);
+                }
+                double E_mod = sqrt(mass2 + pmod[0] * pmod[0] + pmod[1] * pmod[1] + pmod[2] * pmod[2]);
+                f = fabs(renorm) / (exp(E_mod / lambda - chem_effect) + sign);
+              }
+              eta_integral += eta_weight * p_dsigma * f;
+            }
+            out[iy + (long)ny * (iphip + (long)nphi * (ipT + (long)npT * ipart))] += prefactor * degeneracy * eta_integral;
+          }
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace
