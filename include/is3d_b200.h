@@ -201,6 +201,11 @@ is3d_status is3d_sample_histograms(is3d_ctx *ctx, double *dN_dy, double *dN_deta
 /* sustained DFMA throughput of this GPU in TFLOP/s (2 flops per DFMA), measured with a register-resident
  * micro-kernel and CUDA events: the roofline denominator of the FP64-bound kernels. */
 is3d_status is3d_measure_fp64_peak(is3d_ctx *ctx, double *tflops);
+/* device-math probe: out_exp[i] = e^x[i], out_rcp[i] = 1/x[i], out_sqrt[i] = sqrt(x[i]) computed by the FP64-pipe
+ * approximations the kernels use in place of exp / division / sqrt (csrc/common.cuh); host buffers of n doubles.
+ * The parity tests bound their error against libm. */
+is3d_status is3d_probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp,
+                            double *out_sqrt);
 /* the CUDA stream all kernels of this context are launched on (as a void* cudaStream_t) */
 void       *is3d_stream(is3d_ctx *ctx);
 

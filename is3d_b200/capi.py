@@ -60,7 +60,7 @@ ABI_SYMBOLS = ["is3d_default_params", "is3d_create", "is3d_destroy", "is3d_last_
                "is3d_set_thermo_averages", "is3d_set_df_tables", "is3d_set_ptb_tables", "is3d_set_surface",
                "is3d_set_surface_device", "is3d_spectra_size", "is3d_spectra", "is3d_spectra_device", "is3d_dndx",
                "is3d_dndx_device", "is3d_total_yield", "is3d_cell_yields", "is3d_sample", "is3d_free_particles",
-               "is3d_sample_histograms", "is3d_measure_fp64_peak", "is3d_stream"]
+               "is3d_sample_histograms", "is3d_measure_fp64_peak", "is3d_probe_math", "is3d_stream"]
 HOST_SYMBOLS = ["is3d_host_open", "is3d_host_close", "is3d_host_read_surface", "is3d_host_set_surface",
                 "is3d_host_prepare", "is3d_host_prepare_tables", "is3d_host_context", "is3d_host_run",
                 "is3d_host_spectra", "is3d_host_dndx", "is3d_host_events", "is3d_host_event_particles",
@@ -100,6 +100,7 @@ def load_libraries():
     lib.is3d_free_particles.argtypes = [vp]
     lib.is3d_sample_histograms.argtypes = [vp] + [vp] * 10
     lib.is3d_measure_fp64_peak.argtypes = [vp, dp]
+    lib.is3d_probe_math.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
     lib.is3d_stream.restype = vp
     lib.is3d_stream.argtypes = [vp]
     host.is3d_host_open.restype = vp
@@ -249,6 +250,12 @@ class HostSession:
         v = C.c_double()
         self._check(self.lib.is3d_measure_fp64_peak(self.ctx, C.byref(v)), "is3d_measure_fp64_peak")
         return v.value
+
+    def abi_probe_math(self, x: np.ndarray):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        e, r, s = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+        self._check(self.lib.is3d_probe_math(self.ctx, x.size, _ptr(x), _ptr(e), _ptr(r), _ptr(s)), "is3d_probe_math")
+        return e, r, s
 
     # ---- results kept by the host layer ------------------------------------------------------------------
     def spectra(self) -> np.ndarray:

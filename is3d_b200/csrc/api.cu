@@ -61,6 +61,15 @@ is3d_status is3d_create(const is3d_params *p, is3d_ctx **out)
   ctx->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return IS3D_ERR_CUDA; }
+  {
+    std::vector<double> tab(kExpTableSize);
+    fill_exp_table(tab.data());
+    if (ctx->upload(&ctx->d_exptab, tab.data(), tab.size()) != IS3D_OK) {
+      g_create_error = ctx->err;
+      is3d_destroy(ctx);
+      return IS3D_ERR_CUDA;
+    }
+  }
   *out = ctx;
   return IS3D_OK;
 }
@@ -343,6 +352,13 @@ is3d_status is3d_measure_fp64_peak(is3d_ctx *ctx, double *tflops)
 {
   CTX_ENTER(ctx);
   return measure_fp64_peak(ctx, tflops);
+}
+
+is3d_status is3d_probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp, double *out_sqrt)
+{
+  CTX_ENTER(ctx);
+  if (n <= 0 || !x || !out_exp || !out_rcp || !out_sqrt) { ctx->set_error("probe_math: bad arguments"); return IS3D_ERR_INVALID; }
+  return probe_math(ctx, n, x, out_exp, out_rcp, out_sqrt);
 }
 
 }  // extern "C"

@@ -48,36 +48,55 @@ IS3D_HD int64_t as_int64(double d)
 // NaN or +-inf (portable between nvcc and g++)
 IS3D_HD bool not_finite(double x) { return !(fabs(x) <= 1.7976931348623157e308); }
 
-// exp(x) for the Bose/Fermi factor, kept entirely in the FP64 FMA pipe: Cody-Waite reduction x = n ln2 + r,
-// |r| <= ln2/2, degree-11 polynomial (Chebyshev-node fit, max relative error 1.7e-17 before rounding), exponent
-// patched by integer add.  x is clamped to [-700, 700] so the result stays normal: 1/(e^700 + s) ~ 1e-304 stands
-// in for the reference's exact 0 of 1/inf, far below any bin's rounding error.
-IS3D_HD double fast_exp(double x)
+// exp(x) for the Bose/Fermi factor, kept in the FP64 FMA pipe and short enough to leave the pipe to the physics:
+//   x = k (ln2/1024) + r,  |r| <= ln2/2048,   e^x = 2^(k >> 10) * T[k & 1023] * (1 + r + r^2/2 + r^3/6)
+// T[m] = 2^(m/1024) is a 1024-entry table (8 KB; shared memory on the device, filled by load_exp_table).
+// Truncation error r^4/24 < 5.5e-16; 4 reduction + 3 polynomial + 1 scaling FP64 instructions (the first version, a
+// degree-11 Horner form with FP64 clamps, needed 19).  The exponent is patched by an integer add on the high word.
+// Range: |x| >= 708 (beyond the double range of e^x) is caught on the integer pipe from the high word of x and
+// returns 1e300 / 0, which 1/(e^x + s) turns into the reference's 0 / (1/s); NaN input gives 1e300.
+// tools/gen_exp_table.py derives the constants and scans the error of the whole construction in 60-digit arithmetic.
+constexpr int kExpTableBits = 10;
+constexpr int kExpTableSize = 1 << kExpTableBits;
+
+IS3D_HD int hi_word(double d) { return (int)(as_int64(d) >> 32); }
+
+IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
 {
-  x = fmin(fmax(x, -700.0), 700.0);
-  const double kMagic = 6755399441055744.0;   // 1.5 * 2^52: rounds to nearest integer in the low mantissa bits
-  double t = fma(x, 1.4426950408889634, kMagic);
-  int64_t n = as_int64(t) - as_int64(kMagic);  // integer value of the rounded quotient (small, fits low bits)
+  const double kMagic = 6755399441055744.0;          // 1.5 * 2^52: rounds to nearest integer in the low mantissa bits
+  double t = fma(x, 1477.3197218702985, kMagic);     // 1024 / ln2
+  const int k = (int)as_int64(t);                    // low word of t = the integer (two's complement), |k| < 2^21 here
   t -= kMagic;
-  double r = fma(t, -6.93147180559945286e-01, x);
-  r = fma(t, -2.31904681384629956e-17, r);
-  double p = 2.5110049204818658e-08;
-  p = fma(p, r, 2.763265472252779e-07);
-  p = fma(p, r, 2.755724088722987e-06);
-  p = fma(p, r, 2.4801485441561313e-05);
-  p = fma(p, r, 0.00019841269890076403);
-  p = fma(p, r, 0.0013888888952352863);
-  p = fma(p, r, 0.008333333333319589);
-  p = fma(p, r, 0.04166666666648795);
-  p = fma(p, r, 0.1666666666666668);
-  p = fma(p, r, 0.5000000000000019);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return as_double(as_int64(p) + (n << 52));
+  double r = fma(t, -6.769015308236703e-04, x);      // ln2/1024 rounded to 26 significant bits: t * hi is exact
+  r = fma(t, -1.2691901263564344e-11, r);            // ln2/1024 - hi
+  double q = fma(r, 1.6666666666666666e-01, 0.5);
+  q = fma(q, r, 1.0);
+  q = q * r;                                         // r + r^2/2 + r^3/6
+  const double T = tab[k & (kExpTableSize - 1)];
+  const double v = fma(T, q, T);
+  double res = as_double(as_int64(v) + ((int64_t)(k >> kExpTableBits) << 52));
+  const int hx = hi_word(x);
+  if ((hx & 0x7fffffff) >= 0x40862000) res = hx < 0 ? 0.0 : 1e300;   // |x| >= 708 (or NaN)
+  return res;
 }
 
-// 1/d for d in the normal range (here d = e^x +- 1 >= ~0.1): hardware seed + Newton steps in the FMA pipe,
-// no division slow path.
+// host-side construction of the table (uploaded once per context; hostcheck uses it directly)
+inline void fill_exp_table(double *tab)
+{
+  for (int m = 0; m < kExpTableSize; m++) tab[m] = (double)exp2l((long double)m / (long double)kExpTableSize);
+}
+
+#if defined(__CUDACC__)
+// copies the table from global memory into the block's shared-memory copy; the caller synchronises
+__device__ __forceinline__ void load_exp_table(double *smem_tab, const double *__restrict__ gmem_tab)
+{
+  for (int m = threadIdx.x; m < kExpTableSize; m += blockDim.x) smem_tab[m] = gmem_tab[m];
+}
+#endif
+
+// 1/d for d in the normal range (here d = e^x +- 1 >= ~0.1, or d = E/T): hardware seed + one cubically convergent
+// step in the FMA pipe, no division slow path.  The seed (MUFU.RCP64H) sees only the upper 32 bits of d, i.e. it
+// carries ~20 bits: e = 1 - d y0 <= 2^-19, y = y0 (1 + e + e^2) leaves e^3 <= 2^-57.
 IS3D_HD double fast_rcp(double d)
 {
 #if defined(__CUDA_ARCH__)
@@ -85,8 +104,6 @@ IS3D_HD double fast_rcp(double d)
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
   double e = fma(-d, y, 1.0);
   e = fma(e, e, e);
-  y = fma(y, e, y);
-  e = fma(-d, y, 1.0);
   y = fma(y, e, y);
   return y;
 #else

@@ -33,6 +33,7 @@ struct is3d_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   int sm_count = 148;
+  double *d_exptab = nullptr;              // 2^(m/1024) table of fast_exp (common.cuh)
 
   // chosen species (host copies + device arrays)
   int ns = 0;
@@ -134,5 +135,6 @@ is3d_status run_cell_yields(is3d_ctx *ctx, double *dn_tot_host, double *dn_list_
 is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts,
                         is3d_stats *stats);
 is3d_status measure_fp64_peak(is3d_ctx *ctx, double *tflops);
+is3d_status probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp, double *out_sqrt);
 
 }  // namespace is3d

@@ -65,6 +65,9 @@ __global__ void __launch_bounds__(kDndxThreads)
 dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_block, SurfaceView surf,
                int64_t surf_begin, DndxGrid g)
 {
+  __shared__ double exptab[kExpTableSize];
+  load_exp_table(exptab, g.exptab);
+  __syncthreads();
   const int s = blockIdx.x * kDndxThreads + threadIdx.x;
   const double m2 = g.mass2[s], baryon = g.baryon[s], sign = g.sign[s], deg = g.deg[s];
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
@@ -88,7 +91,7 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
           for (int ipT = 0; ipT < g.NpT; ipT++) {
             const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
             const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-            double v = pds * df_distribution<MODE, BARYON, REGULATE>(it, bn.b);
+            double v = pds * df_distribution<MODE, BARYON, REGULATE>(it, bn.b, exptab);
             if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
             acc += v;
           }
@@ -109,6 +112,9 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
                    int64_t surf_begin, DndxGrid g, const double *__restrict__ gla_root, const double *__restrict__ gla_weight,
                    int gla_pts)
 {
+  __shared__ double exptab[kExpTableSize];
+  load_exp_table(exptab, g.exptab);
+  __syncthreads();
   const int s = blockIdx.x * kDndxThreads + threadIdx.x;
   const double m2 = g.mass2[s], baryon = g.baryon[s], sign = g.sign[s], deg = g.deg[s], mass = g.mass[s];
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
@@ -140,7 +146,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
             for (int ipT = 0; ipT < g.NpT; ipT++) {
               const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
               const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-              double v = pds * df_distribution<2, BARYON, REGULATE>(it, bn.b);
+              double v = pds * df_distribution<2, BARYON, REGULATE>(it, bn.b, exptab);
               if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
               acc += v;
             }
@@ -150,7 +156,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
             for (int ipT = 0; ipT < g.NpT; ipT++) {
               const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
               const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-              double v = pds * feqmod_distribution<BARYON>(it, bn.b, rn);
+              double v = pds * feqmod_distribution<BARYON>(it, bn.b, rn, exptab);
               if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
               acc += v;
             }
@@ -215,6 +221,7 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   DndxGrid g;
   IS3D_TRY(build_dndx_grid(ctx, &g));
   g.hist_tau = tau_dev; g.hist_r = r_dev; g.hist_phi = phi_dev;
+  g.exptab = ctx->d_exptab;
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(tau_dev, 0, (size_t)ctx->ns * p.tau_bins * sizeof(double), ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(r_dev, 0, (size_t)ctx->ns * p.r_bins * sizeof(double), ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(phi_dev, 0, (size_t)ctx->ns * p.phip_bins * sizeof(double), ctx->stream));

@@ -31,6 +31,7 @@ struct DndxGrid {
   double tau_min, tau_width, r_min, r_width, phi_width;
   int tau_bins, r_bins, phi_bins;
   double *hist_tau, *hist_r, *hist_phi;               // [ns][bins]
+  const double *exptab;                               // 2^(m/1024), global memory
 };
 
 // SpacetimeDistribution.cpp:413-440

@@ -1,5 +1,6 @@
 // DFMA micro-benchmark: the measured FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry).
 #include "ctx.h"
+#include "spectra_feqmod.cuh"
 
 namespace is3d {
 
@@ -25,7 +26,37 @@ __global__ void __launch_bounds__(256) dfma_kernel(double *out, double a, double
   for (int c = 0; c < kChains; c++) s += x[c];
   if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
 }
+
+// device-math probe: the three approximations every spectra kernel is built on, evaluated point-wise
+__global__ void probe_math_kernel(const double *__restrict__ x, int64_t n, const double *__restrict__ exptab_g,
+                                  double *__restrict__ out_exp, double *__restrict__ out_rcp, double *__restrict__ out_sqrt)
+{
+  __shared__ double exptab[kExpTableSize];
+  load_exp_table(exptab, exptab_g);
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    out_exp[i] = fast_exp(v, exptab);
+    out_rcp[i] = fast_rcp(v);
+    out_sqrt[i] = fast_sqrt(v);
+  }
+}
 }  // namespace
+
+is3d_status probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp, double *out_sqrt)
+{
+  void *d = nullptr;
+  IS3D_TRY(ctx->get_scratch("probe_math", (size_t)4 * n * sizeof(double), &d));
+  double *dx = (double *)d;
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  probe_math_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dx, n, ctx->d_exptab, dx + n, dx + 2 * n, dx + 3 * n);
+  IS3D_CUDA_TRY(ctx, cudaGetLastError());
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(out_exp, dx + n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(out_rcp, dx + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(out_sqrt, dx + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return IS3D_OK;
+}
 
 is3d_status measure_fp64_peak(is3d_ctx *ctx, double *tflops)
 {

@@ -40,6 +40,7 @@ struct DfGrid {
   int nbins;
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
+  const double *exptab;                               // 2^(m/1024), global memory (ctx->d_exptab)
 };
 
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, int R>
@@ -48,7 +49,9 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
                   double *__restrict__ partial, int64_t total)
 {
   __shared__ DfItem items[kTile];
+  __shared__ double exptab[kExpTableSize];
   __shared__ int warp_count[kThreads / 32];
+  load_exp_table(exptab, g.exptab);                 // visible after the first __syncthreads of the tile loop
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;
@@ -101,7 +104,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
       for (int k = 0; k < n_items; k++) {
         const DfItem it = items[k];
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[r] += df_eval<MODE, BARYON, REGULATE, OUTFLOW>(it, bin[r]);
+        for (int r = 0; r < R; r++) acc[r] += df_eval<MODE, BARYON, REGULATE, OUTFLOW>(it, bin[r], exptab);
       }
     }
   }
@@ -214,7 +217,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   DfGrid g;
   IS3D_TRY(build_bin_arrays(ctx, &g.mT, &g.pT, &g.m2, &g.baryon, &g.sign, &g.deg));
   g.nbins = nbins; g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
-  g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw;
+  g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw; g.exptab = ctx->d_exptab;
 
   const int nslices = (nbins + kThreads * kDfBinsPerThread - 1) / (kThreads * kDfBinsPerThread);
   const int64_t blocks_per_chunk = (int64_t)nslices * ctx->Ny * ctx->Nphi;

@@ -95,24 +95,28 @@ IS3D_HD int df_setup_cell(const Cell &c, const DfTables &tb, const DfFlags &fl, 
 // item constants: one (cell, eta-node) seen from a fixed (y, phi)
 struct alignas(16) DfItem {
   double aT, bT, c1, d1;
-  double q1, q2, q3, K0;
+  double q1, q2, q3, K0;       // q1, q3 carry the bulk m^2 term (see df_make_item)
   double K1, K2, alphaB, v1;
   double v2, G0, G1, pad;
 };
 
 // pk(k) returns pack entry k of this cell.  sh/ch = sinh, cosh of (y - eta); w = eta quadrature weight (1 in 3+1d).
+// The bulk term proportional to m^2 = mT^2 - pT^2 is folded into the shear quadratic form, so the momentum loop
+// never needs m^2:   mode 1:  K0 m^2 + pi.p.p  = mT^2 (q1 + K0) + mT pT q2 + pT^2 (q3 - K0)
+//                    mode 2:  pi.p.p - K2 m^2  = mT^2 (q1 - K2) + mT pT q2 + pT^2 (q3 + K2)
 template <class PackFn>
-IS3D_HD DfItem df_make_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w)
+IS3D_HD DfItem df_make_item(PackFn pk, int mode, double sh, double ch, double cphi, double sphi, double w)
 {
   DfItem it;
   it.aT = ch * pk(DP_UTT) - sh * pk(DP_TUNT);
   it.bT = cphi * pk(DP_UXT) + sphi * pk(DP_UYT);
   it.c1 = w * (ch * pk(DP_DAT) + sh * pk(DP_DANT));
   it.d1 = w * (cphi * pk(DP_DAX) + sphi * pk(DP_DAY));
-  it.q1 = ch * ch * pk(DP_PITT) + sh * sh * pk(DP_T2PINN) - 2.0 * ch * sh * pk(DP_TPITN);
-  it.q2 = 2.0 * (sh * (pk(DP_TPIXN) * cphi + pk(DP_TPIYN) * sphi) - ch * (pk(DP_PITX) * cphi + pk(DP_PITY) * sphi));
-  it.q3 = pk(DP_PIXX) * cphi * cphi + pk(DP_PIYY) * sphi * sphi + 2.0 * pk(DP_PIXY) * cphi * sphi;
   it.K0 = pk(DP_K0); it.K1 = pk(DP_K1); it.K2 = pk(DP_K2);
+  const double fold = (mode == 1) ? it.K0 : -it.K2;
+  it.q1 = ch * ch * pk(DP_PITT) + sh * sh * pk(DP_T2PINN) - 2.0 * ch * sh * pk(DP_TPITN) + fold;
+  it.q2 = 2.0 * (sh * (pk(DP_TPIXN) * cphi + pk(DP_TPIYN) * sphi) - ch * (pk(DP_PITX) * cphi + pk(DP_PITY) * sphi));
+  it.q3 = pk(DP_PIXX) * cphi * cphi + pk(DP_PIYY) * sphi * sphi + 2.0 * pk(DP_PIXY) * cphi * sphi - fold;
   it.alphaB = pk(DP_ALPHAB);
   it.v1 = pk(DP_VT) * ch - pk(DP_TVN) * sh;
   it.v2 = pk(DP_VX) * cphi + pk(DP_VY) * sphi;
@@ -121,37 +125,50 @@ IS3D_HD DfItem df_make_item(PackFn pk, double sh, double ch, double cphi, double
   return it;
 }
 
-// per-bin registers
+// per-bin registers.  The spectra kernels give one thread R species at ONE pT node, so everything that multiplies
+// pT alone (DfShared) is formed once per item and shared by the thread's R evaluations.
 struct DfBin {
-  double mT, pT, mT2, mTpT, pT2, m2, baryon, sign;
+  double mT, mT2, m2, baryon, sign;     // m2 is read by the modified-equilibrium path only
 };
+
+struct DfShared {
+  double pb, pd, pq2, pq3, pv;          // pT bT, pT d1, pT q2, pT^2 q3, pT v2
+};
+
+template <bool BARYON>
+IS3D_HD DfShared df_share(const DfItem &it, double pT, double pT2)
+{
+  DfShared s;
+  s.pb = pT * it.bT; s.pd = pT * it.d1; s.pq2 = pT * it.q2; s.pq3 = pT2 * it.q3;
+  s.pv = BARYON ? pT * it.v2 : 0.0;
+  return s;
+}
 
 // The distribution feq (1 + df) at one momentum (MomentumSpectra.cpp:317-359)
 template <int MODE, bool BARYON, bool REGULATE>
-IS3D_HD double df_distribution(const DfItem &it, const DfBin &b)
+IS3D_HD double df_distribution(const DfItem &it, const DfShared &s, const DfBin &b, const double *__restrict__ exptab)
 {
-  double xE = fma(b.mT, it.aT, -b.pT * it.bT);
+  double xE = fma(b.mT, it.aT, -s.pb);
   double x = xE;
   if (BARYON) x = fma(-b.baryon, it.alphaB, xE);
-  double feq = fast_rcp(fast_exp(x) + b.sign);
+  double feq = fast_rcp(fast_exp(x, exptab) + b.sign);
   double feqbar = fma(-b.sign, feq, 1.0);
-  double pipp = fma(b.mT2, it.q1, fma(b.mTpT, it.q2, b.pT2 * it.q3));
+  double pipp = fma(b.mT2, it.q1, fma(b.mT, s.pq2, s.pq3));      // shear + the folded bulk m^2 term
   double dfv;
   if (MODE == 1) {
     double lin = it.K2 * xE;                         // (K1 b + K2 xE)
     if (BARYON) lin = fma(it.K1, b.baryon, lin);
-    dfv = fma(lin, xE, fma(it.K0, b.m2, pipp));
+    dfv = fma(lin, xE, pipp);
     if (BARYON) {
-      double Vp = fma(b.mT, it.v1, -b.pT * it.v2);
+      double Vp = fma(b.mT, it.v1, -s.pv);
       dfv = fma(fma(it.G1, xE, it.G0 * b.baryon), Vp, dfv);
     }
   } else {
     double r = fast_rcp(xE);
-    double t = fma(-it.K2, b.m2, pipp);              // (pipp' - K2 m^2)
-    dfv = fma(t, r, it.K0 * xE);
+    dfv = fma(pipp, r, it.K0 * xE);
     if (BARYON) {
       dfv = fma(it.K1, b.baryon, dfv);
-      double Vp = fma(b.mT, it.v1, -b.pT * it.v2);
+      double Vp = fma(b.mT, it.v1, -s.pv);
       dfv = fma(fma(-it.G1 * b.baryon, r, it.G0), Vp, dfv);
     }
   }
@@ -162,10 +179,10 @@ IS3D_HD double df_distribution(const DfItem &it, const DfBin &b)
 
 // One integrand evaluation: returns w * p.dsigma * feq (1 + df)   (MomentumSpectra.cpp:304-361)
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
-IS3D_HD double df_eval(const DfItem &it, const DfBin &b)
+IS3D_HD double df_eval(const DfItem &it, const DfShared &s, const DfBin &b, const double *__restrict__ exptab)
 {
-  double pds = fma(b.mT, it.c1, b.pT * it.d1);
-  double contrib = pds * df_distribution<MODE, BARYON, REGULATE>(it, b);
+  double pds = fma(b.mT, it.c1, s.pd);
+  double contrib = pds * df_distribution<MODE, BARYON, REGULATE>(it, s, b, exptab);
   if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
   return contrib;
 }

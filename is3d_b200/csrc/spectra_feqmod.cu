@@ -71,6 +71,7 @@ struct FeqGrid {
   int nbins, NpT, ns;
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
+  const double *exptab;
   bool w_on_dan;      // eta weight multiplies the whole p.dsigma (famod, MomentumSpectra.cpp:1617) instead of the feqmod placement
 };
 
@@ -86,6 +87,8 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
                       const double *__restrict__ renorm, FeqGrid g, double *__restrict__ partial, int64_t total)
 {
   __shared__ ItemSlot items[kTile];
+  __shared__ double exptab[kExpTableSize];
+  load_exp_table(exptab, g.exptab);
   __shared__ int item_cell[kTile];
   __shared__ unsigned char item_linear[kTile];
   __shared__ int warp_count[kThreads / 32];
@@ -161,12 +164,12 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
         if (!item_linear[k]) {
           const FeqmodItem it = items[k].mod;
 #pragma unroll
-          for (int r = 0; r < R; r++) acc[r] += feqmod_eval<BARYON, OUTFLOW>(it, bin[r], SPECIES_RENORM ? rn[r] : it.renorm);
+          for (int r = 0; r < R; r++) acc[r] += feqmod_eval<BARYON, OUTFLOW>(it, bin[r], SPECIES_RENORM ? rn[r] : it.renorm, exptab);
         } else {
           const DfItem it = items[k].lin;
 #pragma unroll
           for (int r = 0; r < R; r++) {
-            double v = df_eval<2, BARYON, REGULATE, OUTFLOW>(it, bin[r]);
+            double v = df_eval<2, BARYON, REGULATE, OUTFLOW>(it, bin[r], exptab);
             if (SPECIES_RENORM) v = (rn[r] != 0.0) ? v : 0.0;   // NaN renorm: the reference skips the species (:828-832)
             acc[r] += v;
           }
@@ -221,6 +224,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
   g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw;
   g.w_on_dan = (p.df_mode == 5);
+  g.exptab = ctx->d_exptab;
 
   const int nslices = (nbins + kThreads * kBins - 1) / (kThreads * kBins);
   const int64_t blocks_per_chunk = (int64_t)nslices * ctx->Ny * ctx->Nphi;

@@ -217,14 +217,15 @@ IS3D_HD FeqmodItem feqmod_make_item(PackFn pk, double sh, double ch, double cphi
 template <class PackFn>
 IS3D_HD DfItem feqmod_make_linear_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w, bool w_on_dan = false)
 {
-  DfItem it = df_make_item(pk, sh, ch, cphi, sphi, 1.0);
+  DfItem it = df_make_item(pk, 2, sh, ch, cphi, sphi, 1.0);
   it.c1 = w * ch * pk(DP_DAT) + (w_on_dan ? w : 1.0) * sh * pk(DP_DANT);
   it.d1 = w * (cphi * pk(DP_DAX) + sphi * pk(DP_DAY));
   it.pad = pk(FP_ADD);
   return it;
 }
 
-// sqrt(a) for a > 0 in the FMA pipe: hardware rsqrt seed + two coupled Newton (Goldschmidt) steps + residual fix
+// sqrt(a) for a > 0 in the FMA pipe: hardware rsqrt seed (~20 bits) + one coupled Newton (Goldschmidt) step (-> 2^-39) +
+// residual fix g + (a - g^2) h (-> below 2^-60)
 IS3D_HD double fast_sqrt(double a)
 {
 #if defined(__CUDA_ARCH__)
@@ -233,8 +234,6 @@ IS3D_HD double fast_sqrt(double a)
   double g = a * y, h = 0.5 * y;
   double r = fma(-h, g, 0.5);
   g = fma(g, r, g); h = fma(h, r, h);
-  r = fma(-h, g, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
   double d = fma(-g, g, a);
   return fma(d, h, g);
 #else
@@ -242,23 +241,37 @@ IS3D_HD double fast_sqrt(double a)
 #endif
 }
 
+// per-item products with the thread's pT (shared by its R species, see DfShared)
+struct FeqmodShared {
+  double pd, ph2, ph3;                  // pT d1, pT h2, pT^2 h3
+};
+
+IS3D_HD FeqmodShared feqmod_share(const FeqmodItem &it, double pT, double pT2)
+{
+  FeqmodShared s;
+  s.pd = pT * it.d1; s.ph2 = pT * it.h2; s.ph3 = pT2 * it.h3;
+  return s;
+}
+
 // the modified distribution |renorm| / (exp(E'/T' - b alphaB') + sign) at one momentum (MomentumSpectra.cpp:941-979);
 // renorm_sp = |renorm| of this (cell, species)
 template <bool BARYON>
-IS3D_HD double feqmod_distribution(const FeqmodItem &it, const DfBin &b, double renorm_sp)
+IS3D_HD double feqmod_distribution(const FeqmodItem &it, const FeqmodShared &s, const DfBin &b, double renorm_sp,
+                                   const double *__restrict__ exptab)
 {
-  double e2 = fma(b.m2, it.iT2, fma(b.mT2, it.h1, fma(b.mTpT, it.h2, b.pT2 * it.h3)));
+  double e2 = fma(b.m2, it.iT2, fma(b.mT2, it.h1, fma(b.mT, s.ph2, s.ph3)));
   double x = fast_sqrt(e2);
   if (BARYON) x = fma(-b.baryon, it.alphaB_mod, x);
-  return renorm_sp * fast_rcp(fast_exp(x) + b.sign);
+  return renorm_sp * fast_rcp(fast_exp(x, exptab) + b.sign);
 }
 
 // f p.dsigma of the modified distribution (MomentumSpectra.cpp:932-982)
 template <bool BARYON, bool OUTFLOW>
-IS3D_HD double feqmod_eval(const FeqmodItem &it, const DfBin &b, double renorm_sp)
+IS3D_HD double feqmod_eval(const FeqmodItem &it, const FeqmodShared &s, const DfBin &b, double renorm_sp,
+                           const double *__restrict__ exptab)
 {
-  double pds = fma(b.mT, it.c1, b.pT * it.d1);
-  double contrib = pds * feqmod_distribution<BARYON>(it, b, renorm_sp);
+  double pds = fma(b.mT, it.c1, s.pd);
+  double contrib = pds * feqmod_distribution<BARYON>(it, s, b, renorm_sp, exptab);
   if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
   return contrib;
 }

@@ -15,6 +15,14 @@
 #include "../../is3d_b200/host/host_dfview.hpp"
 #include "../../is3d_b200/host/is3d_host.hpp"
 
+static const double *exp_table()
+{
+  static double tab[is3d::kExpTableSize];
+  static bool ready = false;
+  if (!ready) { is3d::fill_exp_table(tab); ready = true; }
+  return tab;
+}
+
 using namespace is3dhost;
 
 namespace {
@@ -52,10 +60,10 @@ struct Loaded {
 template <int MODE, bool BARYON>
 double eval_dispatch(bool reg, bool outflow, const is3d::DfItem &it, const is3d::DfBin &b)
 {
-  if (reg && outflow) return is3d::df_eval<MODE, BARYON, true, true>(it, b);
-  if (reg) return is3d::df_eval<MODE, BARYON, true, false>(it, b);
-  if (outflow) return is3d::df_eval<MODE, BARYON, false, true>(it, b);
-  return is3d::df_eval<MODE, BARYON, false, false>(it, b);
+  if (reg && outflow) return is3d::df_eval<MODE, BARYON, true, true>(it, b, exp_table());
+  if (reg) return is3d::df_eval<MODE, BARYON, true, false>(it, b, exp_table());
+  if (outflow) return is3d::df_eval<MODE, BARYON, false, true>(it, b, exp_table());
+  return is3d::df_eval<MODE, BARYON, false, false>(it, b, exp_table());
 }
 }  // namespace
 
@@ -182,8 +190,8 @@ extern "C" long hostcheck_spectra_feqmod(const char *root, double *out, long cap
               is3d::DfBin b{mT, pTv, mT * mT, mT * pTv, pTv * pTv, m2, (double)p.baryon, (double)p.sign};
               double v;
               if (!linear) {
-                if (fl.include_baryon) v = outflow ? is3d::feqmod_eval<true, true>(mod, b, rn[s]) : is3d::feqmod_eval<true, false>(mod, b, rn[s]);
-                else v = outflow ? is3d::feqmod_eval<false, true>(mod, b, rn[s]) : is3d::feqmod_eval<false, false>(mod, b, rn[s]);
+                if (fl.include_baryon) v = outflow ? is3d::feqmod_eval<true, true>(mod, b, rn[s], exp_table()) : is3d::feqmod_eval<true, false>(mod, b, rn[s], exp_table());
+                else v = outflow ? is3d::feqmod_eval<false, true>(mod, b, rn[s], exp_table()) : is3d::feqmod_eval<false, false>(mod, b, rn[s], exp_table());
               } else {
                 v = fl.include_baryon ? eval_dispatch<2, true>(reg, outflow, lin, b) : eval_dispatch<2, false>(reg, outflow, lin, b);
                 if (rn[s] == 0.0) v = 0.0;
@@ -348,8 +356,8 @@ extern "C" long hostcheck_spectra_famod(const char *root, int chain_on, double *
               is3d::DfBin b{mT, pTv, mT * mT, mT * pTv, pTv * pTv, m2, (double)p.baryon, (double)p.sign};
               double v;
               if (!linear) {
-                if (fl.include_baryon) v = outflow ? is3d::feqmod_eval<true, true>(mod, b, mod.renorm) : is3d::feqmod_eval<true, false>(mod, b, mod.renorm);
-                else v = outflow ? is3d::feqmod_eval<false, true>(mod, b, mod.renorm) : is3d::feqmod_eval<false, false>(mod, b, mod.renorm);
+                if (fl.include_baryon) v = outflow ? is3d::feqmod_eval<true, true>(mod, b, mod.renorm, exp_table()) : is3d::feqmod_eval<true, false>(mod, b, mod.renorm, exp_table());
+                else v = outflow ? is3d::feqmod_eval<false, true>(mod, b, mod.renorm, exp_table()) : is3d::feqmod_eval<false, false>(mod, b, mod.renorm, exp_table());
               } else {
                 v = fl.include_baryon ? eval_dispatch<2, true>(false, outflow, lin, b) : eval_dispatch<2, false>(false, outflow, lin, b);
               }

@@ -1,0 +1,33 @@
+"""GPU test of the FP64-pipe approximations behind every spectra kernel (csrc/common.cuh fast_exp / fast_rcp,
+csrc/spectra_feqmod.cuh fast_sqrt) against numpy/libm, through the C ABI's is3d_probe_math.
+
+The continuous paths promise 1e-10 relative per bin; these primitives are held to 4e-15 (exp: 1024-entry table +
+degree-3 polynomial, truncation 5.5e-16 plus the rounding of x itself at |x| ~ 50) and 4.5e-16 (rcp, sqrt: 2 ulp)."""
+import numpy as np
+import pytest
+
+import cases
+import harness
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fast_math_against_libm(libs, tmp_path):
+    name = "s3d_m1"
+    surf, _ = harness.load_golden(name)
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(-20.0, 60.0, 400_000), rng.uniform(60.0, 707.0, 50_000), rng.uniform(-707.0, -20.0, 50_000),
+                        np.array([0.0, 1e-300, -1e-300, 1e-9, -1e-9, 707.9, -707.9])])
+    pos = np.concatenate([np.exp(rng.uniform(-40.0, 700.0, 300_000)), rng.uniform(0.1, 10.0, 200_000), np.array([1.0, 2.0, 1e300, 0.1])])
+    with harness.open_session(str(tmp_path), cases.SPECTRA_CASES[name], surf) as h:
+        e, _, _ = h.abi_probe_math(x)
+        _, r, s = h.abi_probe_math(pos)
+        far, _, _ = h.abi_probe_math(np.array([708.5, 1e4, 1e8, 1e300, -708.5, -1e8, np.inf]))
+    with np.errstate(over="ignore"):
+        ref = np.exp(x.astype(np.longdouble))
+    err = np.abs((e - ref) / ref).astype(np.float64)
+    assert err.max() < 4e-15, (err.max(), x[np.argmax(err)])
+    assert np.abs(r * pos - 1.0).max() < 4.5e-16
+    assert np.abs(s / np.sqrt(pos) - 1.0).max() < 4.5e-16
+    # beyond the double range of e^x: "huge" (1/(e^x + s) -> the reference's 0) and exact 0
+    assert np.all(far[:4] >= 1e300) and far[6] >= 1e300 and np.all(far[4:6] == 0.0)
