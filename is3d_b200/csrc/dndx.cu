@@ -45,6 +45,7 @@ __global__ void dndx_feqmod_setup_kernel(SurfaceView surf, int64_t begin, int64_
 // per-(pT, species) momentum constants of one thread at one pT node
 struct DndxBin {
   DfBin b;
+  double pT, pT2;
   double mTw, pTw;     // mT * pT_weight, pT * pT_weight (p.dsigma carries the quadrature weights)
 };
 
@@ -53,7 +54,7 @@ __device__ __forceinline__ DndxBin dndx_load_bin(const DndxGrid &g, int ipT, int
   DndxBin d;
   const int idx = ipT * g.ns_pad + s;
   const double pT = g.pT[ipT], w = g.pTw[ipT];
-  d.b.mT = g.mT[idx]; d.b.pT = pT; d.b.mT2 = g.mT2[idx]; d.b.mTpT = g.mTpT[idx]; d.b.pT2 = pT * pT;
+  d.b.mT = g.mT[idx]; d.b.mT2 = g.mT2[idx]; d.pT = pT; d.pT2 = pT * pT;
   d.b.m2 = m2; d.b.baryon = baryon; d.b.sign = sign;
   d.mTw = g.mTw[idx]; d.pTw = pT * w;
   return d;
@@ -86,12 +87,12 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
         const double d = yval - eta, sh = sinh(d), ch = cosh(d);
         for (int iphi = 0; iphi < g.Nphi; iphi++) {
           // phi weight folded into the p.dsigma coefficients (weights are positive: the outflow test is unchanged)
-          const DfItem it = df_make_item(pk, sh, ch, g.cosphi[iphi], g.sinphi[iphi], w * g.phiw[iphi]);
+          const DfItem it = df_make_item(pk, MODE, sh, ch, g.cosphi[iphi], g.sinphi[iphi], w * g.phiw[iphi]);
 #pragma unroll 3
           for (int ipT = 0; ipT < g.NpT; ipT++) {
             const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
             const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-            double v = pds * df_distribution<MODE, BARYON, REGULATE>(it, bn.b, exptab);
+            double v = pds * df_distribution<MODE, BARYON, REGULATE>(it, df_share<BARYON>(it, bn.pT, bn.pT2), bn.b, exptab);
             if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
             acc += v;
           }
@@ -146,7 +147,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
             for (int ipT = 0; ipT < g.NpT; ipT++) {
               const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
               const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-              double v = pds * df_distribution<2, BARYON, REGULATE>(it, bn.b, exptab);
+              double v = pds * df_distribution<2, BARYON, REGULATE>(it, df_share<BARYON>(it, bn.pT, bn.pT2), bn.b, exptab);
               if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
               acc += v;
             }
@@ -156,7 +157,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
             for (int ipT = 0; ipT < g.NpT; ipT++) {
               const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
               const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-              double v = pds * feqmod_distribution<BARYON>(it, bn.b, rn, exptab);
+              double v = pds * feqmod_distribution<BARYON>(it, feqmod_share(it, bn.pT, bn.pT2), bn.b, rn, exptab);
               if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
               acc += v;
             }

@@ -4,11 +4,13 @@
 // Layout / schedule
 //   1. df_setup_kernel: one thread per cell; reads the 20-25 SoA surface columns (coalesced), evaluates the df
 //      coefficients and writes a 30-double "cell pack" as SoA into HBM (240 B / cell).
-//   2. df_spectra_kernel: output-stationary.  blockIdx.x = slice of (species, pT) bins, blockIdx.y = (iy, iphi),
-//      blockIdx.z = contiguous chunk of cells.  A block streams its chunk in tiles of 256 cells: each thread turns
-//      one cell pack into the 16-double item constants for the block's (y, phi) -- one sinh per cell per tile --
-//      with invalid (u.dsigma <= 0) cells compacted away by ballot/prefix; then every thread marches over the
-//      tile, reading the warp-uniform item with broadcast LDS.128 and updating its R register accumulators.
+//   2. df_spectra_kernel: output-stationary.  blockIdx.x = slice of (species group, pT) columns, blockIdx.y =
+//      (iy, iphi), blockIdx.z = contiguous chunk of cells.  A thread owns R consecutive species at ONE pT node, so
+//      every product of an item constant with pT alone is formed once per item and shared by its R evaluations.
+//      A block streams its chunk in tiles of 256 cells: each thread turns one cell pack into the 16-double item
+//      constants for the block's (y, phi) -- one sinh per cell per tile -- with invalid (u.dsigma <= 0) cells
+//      compacted away by ballot/prefix; then every thread marches over the tile, reading the warp-uniform item
+//      with broadcast LDS.128 and updating its R register accumulators.
 //      FP64-pipe bound: HBM traffic is 240 B per cell per block against >= 768 * ~40 DFMA per cell per block.
 //   3. reduce_partials_kernel: deterministic sum over the cell chunks.
 #include "ctx.h"
@@ -20,6 +22,7 @@ namespace {
 
 constexpr int kTile = 256;      // cells per shared-memory tile = threads per block
 constexpr int kThreads = 256;
+constexpr int kDfBinsPerThread = 3;   // species per thread (R)
 
 __global__ void df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, DfTables tb, DfFlags fl,
                                 double *__restrict__ pack, int64_t stride, unsigned long long *counters)
@@ -36,8 +39,8 @@ __global__ void df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, 
 }
 
 struct DfGrid {
-  const double *mT, *pT, *m2, *baryon, *sign, *deg;   // per (species, pT) bin, [nbins]
-  int nbins;
+  const double *mT, *pT, *m2, *baryon, *sign, *deg;   // per (species, pT) bin, [ns * NpT]
+  int ns, NpT, ncols;                                 // ncols = NpT * ceil(ns / R) thread columns
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
   const double *exptab;                               // 2^(m/1024), global memory (ctx->d_exptab)
@@ -57,19 +60,23 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;
   const double yval = g.yv[iy], cphi = g.cosphi[iphi], sphi = g.sinphi[iphi];
 
+  // column = (species group, pT node): R consecutive species share the thread's pT
+  const int col = blockIdx.x * kThreads + t;
+  const int colc = col < g.ncols ? col : g.ncols - 1;
+  const int grp = colc / g.NpT, ip = colc - grp * g.NpT;
   DfBin bin[R];
   double acc[R];
-  int jbin[R];
+  int jbin[R];                                          // (species, pT) bin index, -1 = padding
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    int j = blockIdx.x * (kThreads * R) + r * kThreads + t;
-    jbin[r] = j;
-    int jj = j < g.nbins ? j : g.nbins - 1;
-    double mT = g.mT[jj], pT = g.pT[jj];
-    bin[r].mT = mT; bin[r].pT = pT; bin[r].mT2 = mT * mT; bin[r].mTpT = mT * pT; bin[r].pT2 = pT * pT;
-    bin[r].m2 = g.m2[jj]; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
+    const int s = grp * R + r;
+    const int jj = (s < g.ns ? s : g.ns - 1) * g.NpT + ip;
+    jbin[r] = (col < g.ncols && s < g.ns) ? jj : -1;
+    const double mT = g.mT[jj];
+    bin[r].mT = mT; bin[r].mT2 = mT * mT; bin[r].m2 = g.m2[jj]; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
     acc[r] = 0.0;
   }
+  const double pT = g.pT[ip], pT2 = pT * pT;           // bin arrays are [species][pT]: entry ip = species 0
 
   const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
   int64_t chunk_end = chunk_begin + cells_per_chunk;
@@ -97,14 +104,15 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         double sh = sinh(yval - eta);
         double ch = sqrt(1.0 + sh * sh);     // the reference's cosh (MomentumSpectra.cpp:307-308)
         auto pk = [&](int k) { return pack[k * stride + cell]; };
-        items[base + __popc(ballot & ((1u << lane) - 1u))] = df_make_item(pk, sh, ch, cphi, sphi, w);
+        items[base + __popc(ballot & ((1u << lane) - 1u))] = df_make_item(pk, MODE, sh, ch, cphi, sphi, w);
       }
       __syncthreads();
 #pragma unroll 1
       for (int k = 0; k < n_items; k++) {
         const DfItem it = items[k];
+        const DfShared sh = df_share<BARYON>(it, pT, pT2);
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[r] += df_eval<MODE, BARYON, REGULATE, OUTFLOW>(it, bin[r], exptab);
+        for (int r = 0; r < R; r++) acc[r] += df_eval<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, bin[r], exptab);
       }
     }
   }
@@ -112,7 +120,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   const int64_t pbase = (int64_t)blockIdx.z * total;
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    if (jbin[r] < g.nbins) {
+    if (jbin[r] >= 0) {
       int64_t idx = iy + (int64_t)g.Ny * (iphi + (int64_t)g.Nphi * jbin[r]);
       partial[pbase + idx] += kCooperFryePrefactor * g.deg[jbin[r]] * acc[r];
     }
@@ -137,7 +145,7 @@ template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
 void launch_df(dim3 grid, cudaStream_t st, const double *pack, int64_t stride, int64_t n, int64_t cpc, const DfGrid &g,
                double *partial, int64_t total)
 {
-  df_spectra_kernel<MODE, BARYON, REGULATE, OUTFLOW, 3><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, g, partial, total);
+  df_spectra_kernel<MODE, BARYON, REGULATE, OUTFLOW, kDfBinsPerThread><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, g, partial, total);
 }
 
 template <int MODE, bool BARYON>
@@ -152,7 +160,6 @@ void dispatch_df2(bool reg, bool outflow, dim3 grid, cudaStream_t st, const doub
 
 }  // namespace
 
-constexpr int kDfBinsPerThread = 3;
 
 // Builds the per-(species, pT) bin arrays shared by all spectra kernels; returns device pointers in `out`.
 is3d_status build_bin_arrays(is3d_ctx *ctx, const double **mT, const double **pT, const double **m2, const double **baryon,
@@ -207,8 +214,6 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   const is3d_params &p = ctx->prm;
   const int64_t n = ctx->surf.n;
   const int64_t total = (int64_t)ctx->ns * ctx->NpT * ctx->Nphi * ctx->Ny;
-  const int nbins = ctx->ns * ctx->NpT;
-
   DfFlags fl;
   fl.df_mode = p.df_mode; fl.dimension = p.dimension; fl.include_baryon = p.include_baryon;
   fl.include_bulk = p.include_bulk_deltaf; fl.include_shear = p.include_shear_deltaf;
@@ -216,10 +221,11 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
 
   DfGrid g;
   IS3D_TRY(build_bin_arrays(ctx, &g.mT, &g.pT, &g.m2, &g.baryon, &g.sign, &g.deg));
-  g.nbins = nbins; g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
+  g.ns = ctx->ns; g.NpT = ctx->NpT; g.ncols = ctx->NpT * ((ctx->ns + kDfBinsPerThread - 1) / kDfBinsPerThread);
+  g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
   g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw; g.exptab = ctx->d_exptab;
 
-  const int nslices = (nbins + kThreads * kDfBinsPerThread - 1) / (kThreads * kDfBinsPerThread);
+  const int nslices = (g.ncols + kThreads - 1) / kThreads;
   const int64_t blocks_per_chunk = (int64_t)nslices * ctx->Ny * ctx->Nphi;
   if ((int64_t)ctx->Ny * ctx->Nphi > 65535) { ctx->set_error("Ny*Nphi exceeds 65535"); return IS3D_ERR_INVALID; }
 

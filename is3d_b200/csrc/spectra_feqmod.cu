@@ -68,7 +68,7 @@ __global__ void feqmod_renorm_kernel(const double *__restrict__ pack, int64_t st
 
 struct FeqGrid {
   const double *mT, *pT, *m2, *baryon, *sign, *deg;
-  int nbins, NpT, ns;
+  int ncols, NpT, ns;                   // ncols = NpT * ceil(ns / kBins) thread columns
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
   const double *exptab;
@@ -97,20 +97,24 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
   const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;
   const double yval = g.yv[iy], cphi = g.cosphi[iphi], sphi = g.sinphi[iphi];
 
+  // column = (species group, pT node): R consecutive species share the thread's pT (see spectra_df.cu)
+  const int col = blockIdx.x * kThreads + t;
+  const int colc = col < g.ncols ? col : g.ncols - 1;
+  const int grp = colc / g.NpT, ip = colc - grp * g.NpT;
   DfBin bin[R];
   double acc[R];
   int jbin[R], sp[R];
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    int j = blockIdx.x * (kThreads * R) + r * kThreads + t;
-    jbin[r] = j;
-    int jj = j < g.nbins ? j : g.nbins - 1;
-    sp[r] = jj / g.NpT;
-    double mT = g.mT[jj], pT = g.pT[jj];
-    bin[r].mT = mT; bin[r].pT = pT; bin[r].mT2 = mT * mT; bin[r].mTpT = mT * pT; bin[r].pT2 = pT * pT;
-    bin[r].m2 = g.m2[jj]; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
+    const int s = grp * R + r;
+    sp[r] = s < g.ns ? s : g.ns - 1;
+    const int jj = sp[r] * g.NpT + ip;
+    jbin[r] = (col < g.ncols && s < g.ns) ? jj : -1;
+    const double mT = g.mT[jj];
+    bin[r].mT = mT; bin[r].mT2 = mT * mT; bin[r].m2 = g.m2[jj]; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
     acc[r] = 0.0;
   }
+  const double pT = g.pT[ip], pT2 = pT * pT;
 
   const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
   int64_t chunk_end = chunk_begin + cells_per_chunk;
@@ -163,13 +167,15 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
         }
         if (!item_linear[k]) {
           const FeqmodItem it = items[k].mod;
+          const FeqmodShared sh = feqmod_share(it, pT, pT2);
 #pragma unroll
-          for (int r = 0; r < R; r++) acc[r] += feqmod_eval<BARYON, OUTFLOW>(it, bin[r], SPECIES_RENORM ? rn[r] : it.renorm, exptab);
+          for (int r = 0; r < R; r++) acc[r] += feqmod_eval<BARYON, OUTFLOW>(it, sh, bin[r], SPECIES_RENORM ? rn[r] : it.renorm, exptab);
         } else {
           const DfItem it = items[k].lin;
+          const DfShared sh = df_share<BARYON>(it, pT, pT2);
 #pragma unroll
           for (int r = 0; r < R; r++) {
-            double v = df_eval<2, BARYON, REGULATE, OUTFLOW>(it, bin[r], exptab);
+            double v = df_eval<2, BARYON, REGULATE, OUTFLOW>(it, sh, bin[r], exptab);
             if (SPECIES_RENORM) v = (rn[r] != 0.0) ? v : 0.0;   // NaN renorm: the reference skips the species (:828-832)
             acc[r] += v;
           }
@@ -181,7 +187,7 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
   const int64_t pbase = (int64_t)blockIdx.z * total;
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    if (jbin[r] < g.nbins) {
+    if (jbin[r] >= 0) {
       int64_t idx = iy + (int64_t)g.Ny * (iphi + (int64_t)g.Nphi * jbin[r]);
       partial[pbase + idx] += kCooperFryePrefactor * g.deg[jbin[r]] * acc[r];
     }
@@ -209,8 +215,6 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   if (p.df_mode == 5 && ctx->npdg <= 0) { ctx->set_error("PDG table not set (is3d_set_pdg)"); return IS3D_ERR_INVALID; }
   const int64_t n = ctx->surf.n;
   const int64_t total = (int64_t)ctx->ns * ctx->NpT * ctx->Nphi * ctx->Ny;
-  const int nbins = ctx->ns * ctx->NpT;
-
   FeqmodFlags fl;
   fl.df_mode = p.df_mode; fl.dimension = p.dimension; fl.include_baryon = p.include_baryon;
   fl.include_bulk = p.include_bulk_deltaf; fl.include_shear = p.include_shear_deltaf;
@@ -220,13 +224,13 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
 
   FeqGrid g;
   IS3D_TRY(build_bin_arrays(ctx, &g.mT, &g.pT, &g.m2, &g.baryon, &g.sign, &g.deg));
-  g.nbins = nbins; g.NpT = ctx->NpT; g.ns = ctx->ns;
+  g.NpT = ctx->NpT; g.ns = ctx->ns; g.ncols = ctx->NpT * ((ctx->ns + kBins - 1) / kBins);
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
   g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw;
   g.w_on_dan = (p.df_mode == 5);
   g.exptab = ctx->d_exptab;
 
-  const int nslices = (nbins + kThreads * kBins - 1) / (kThreads * kBins);
+  const int nslices = (g.ncols + kThreads - 1) / kThreads;
   const int64_t blocks_per_chunk = (int64_t)nslices * ctx->Ny * ctx->Nphi;
   if ((int64_t)ctx->Ny * ctx->Nphi > 65535) { ctx->set_error("Ny*Nphi exceeds 65535"); return IS3D_ERR_INVALID; }
 
