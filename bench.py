@@ -157,11 +157,86 @@ def cpu_baseline(args) -> dict:
             "sample": f"{cells} cells of the same S-3D workload, reference OpenMP build with {cores} threads, {sec:.2f} s inside calculate_spectra"}
 
 
+SAMPLER_PARAMS = dict(operation=2, mode=1, hrg_eos=2, dimension=3, df_mode=3, include_baryon=0, include_bulk_deltaf=1,
+                      include_shear_deltaf=1, include_baryondiff_deltaf=0, regulate_deltaf=0, outflow=0, oversample=1, fast=1,
+                      test_sampler=0, sampler_seed=1, min_num_hadrons=1.0e12, max_num_samples=1000)
+
+
+def sampler_bench(args, rank: int, world: int, local: int) -> dict:
+    """BASELINE.json config 3: particle sampler, full SMASH HRG, df_mode 3 (PTM), 1000 oversampled events, on this
+    rank's block of a synthetic 3+1D surface.  Timed end to end through is3d_sample (host surface already on the
+    device; particle records copied back to host memory inside the timed region).  No collective: ranks sample
+    disjoint cell blocks with Philox streams keyed by the global cell index."""
+    import torch
+    import torch.distributed as dist
+
+    from is3d_b200 import HostSession, shard
+
+    cells, nev = args.sampler_cells, args.sampler_events
+    surf = synthetic.s3d(cells, seed=3024 + rank, stress=0.3)
+    root = tempfile.mkdtemp(prefix=f"is3d_smp_r{rank}_")
+    try:
+        workdir.make_workdir(root, SAMPLER_PARAMS, chosen="smash")
+        with HostSession(root) as h:
+            h.set_surface(surf)
+            shard.set_global_thermo_averages(h)
+            h.prepare()
+            h.abi_set_surface(surf, global_offset=rank * cells)
+            ntot, _ = h.abi_total_yield()
+            h.abi_sample(max(1, nev // 50))                        # warm-up (allocations, clocks)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            parts, counts, st = h.abi_sample(nev)
+            torch.cuda.synchronize()
+            sec = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    acc = torch.tensor([float(len(parts)), float(st.sampler_proposals), sec, st.kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        sums = acc.clone()
+        dist.all_reduce(sums)
+        dist.all_reduce(acc, op=dist.ReduceOp.MAX)
+        hadrons, proposals, sec, kms = float(sums[0]), float(sums[1]), float(acc[2]), float(acc[3])
+    else:
+        hadrons, proposals, sec, kms = (float(v) for v in acc.tolist())
+    return {"metric": "sampled hadrons/s", "value": hadrons / sec, "unit": "hadrons/s", "hadrons": int(hadrons),
+            "proposals_per_s": proposals / sec, "acceptance": hadrons / max(proposals, 1.0), "seconds": sec,
+            "device_ms": kms, "d2h_bytes": int(hadrons) * 104, "mean_yield_per_event_rank0": ntot,
+            "workload": f"sampler, df_mode=3 PTM, fast=1, all SMASH species, {nev} events, S-3D(stress 0.3) {cells} cells per GPU x {world} GPU, "
+                        "particle lists returned to host memory"}
+
+
+def sampler_cpu_baseline(args) -> dict:
+    """The reference's (serial; it has no parallel sampler) sample_dN_pTdpTdphidy on a bounded sample."""
+    exe = os.path.join(REPO, "oracle", "_ref", "is3d_ref")
+    if not os.access(exe, os.X_OK):
+        return {"value": None, "unit": "hadrons/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref not built"}
+    cells, nev = args.ref_sampler_cells, args.sampler_events
+    surf = synthetic.s3d(cells, seed=3024, stress=0.3)
+    root = tempfile.mkdtemp(prefix="is3d_cpu_smp_")
+    try:
+        workdir.make_workdir(root, dict(SAMPLER_PARAMS, test_sampler=1), chosen="smash")
+        synthetic.write_mode1(os.path.join(root, "input", "surface.dat"), surf, baryon=False)
+        with open(os.path.join(root, "ref_stdout.log"), "w") as log:
+            subprocess.run([exe], cwd=root, stdout=log, stderr=subprocess.STDOUT, check=True)
+        sec = float(open(os.path.join(root, "ref_dump", "timing.txt")).read().split()[0])
+        ntot = float(np.fromfile(os.path.join(root, "ref_dump", "total_yield.bin"), dtype=np.float64)[0])
+        n_ev = int(open(os.path.join(root, "ref_dump", "nevents.txt")).read().split()[0])
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    hadrons = ntot * n_ev
+    return {"value": hadrons / sec, "unit": "hadrons/s", "cores": 1, "kind": "reference",
+            "sample": f"{cells} cells x {n_ev} events of the same workload (mean {hadrons:.3g} hadrons = events x calculate_total_yield), "
+                      f"serial reference, {sec:.2f} s inside calculate_spectra (histogram mode, no particle files)"}
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from is3d_b200 import HostSession
+    from is3d_b200 import HostSession, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -181,6 +256,7 @@ def run_ours(args) -> None:
     h = HostSession(root)
     # thermodynamic averages (only the sampler uses them) from a small prefix: the host loop is O(cells) python-free C++
     h.set_surface({k: v[:1000] for k, v in surf.items()})
+    shard.set_global_thermo_averages(h)
     h.prepare()
     shape = h.spectra_shape()
     total = int(np.prod(shape))
@@ -248,6 +324,7 @@ def run_ours(args) -> None:
         e2e_s = float(te.item())
 
     fp64_peak = h.abi_fp64_peak()
+    sampler = None if args.no_sampler else sampler_bench(args, rank, world, local)
     if rank == 0:
         ms_step = ms_total / args.steps
         value = evals_rank * world / (ms_step * 1e-3)
@@ -276,8 +353,12 @@ def run_ours(args) -> None:
                          "hbm_gbs_algorithmic": bytes_alg / kern_s / 1e9, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
             "clocks": clocks,
         }
+        if sampler is not None:
+            line["sampler"] = sampler
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
+            if sampler is not None:
+                line["sampler"]["cpu_baseline"] = sampler_cpu_baseline(args)
         print(json.dumps(line))
     h.close()
     shutil.rmtree(root, ignore_errors=True)
@@ -295,6 +376,10 @@ def main():
     ap.add_argument("--df-mode", type=int, default=2, choices=[1, 2])
     ap.add_argument("--ref-cells", type=int, default=2000, help="cells of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sampler", action="store_true", help="skip the sampler (hadrons/s) section")
+    ap.add_argument("--sampler-cells", type=int, default=100_000)
+    ap.add_argument("--sampler-events", type=int, default=1000)
+    ap.add_argument("--ref-sampler-cells", type=int, default=3000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

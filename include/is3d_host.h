@@ -28,6 +28,13 @@ void       is3d_host_close(is3d_host *h);
 int64_t    is3d_host_read_surface(is3d_host *h);
 int64_t    is3d_host_set_surface(is3d_host *h, int64_t n, const double *const cols[IS3D_SURFACE_COLUMNS]);
 
+/* Sharded surfaces (one cell block per rank): the surface averages behind the fast-mode densities and the PTB tables
+ * must be those of the WHOLE surface.  thermo_sums returns this block's six additive sums (T, E, P, muB, nB weighted
+ * by ds_max, and sum ds_max; readindata.cpp:330-360); after summing them over the ranks, set_thermo_averages writes
+ * avg[k] = sum[k] / sum[5] to the side file the later stages read.  Call both between set/read_surface and prepare. */
+void       is3d_host_thermo_sums(is3d_host *h, double sums6[6]);
+void       is3d_host_set_thermo_averages(is3d_host *h, const double avg5[5]);
+
 /* PDG + chosen particles + df tables + PTB tables + fast-mode densities + momentum tables, then the CUDA context */
 void       is3d_host_prepare(is3d_host *h);
 /* the table half of is3d_host_prepare only (no GPU needed): PDG, chosen particles, df/PTB tables, densities */

@@ -46,6 +46,7 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> None:
             objs.append(obj)
             if force or _newer(obj, deps):
                 cmd = [nvcc] + [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + \
+                      os.environ.get("IS3D_NVCC_EXTRA", "").split() + \
                       (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-c", src, "-o", obj]
                 print(" ".join(cmd), flush=True)
                 procs.append(subprocess.Popen(cmd))

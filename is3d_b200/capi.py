@@ -65,7 +65,7 @@ HOST_SYMBOLS = ["is3d_host_open", "is3d_host_close", "is3d_host_read_surface", "
                 "is3d_host_prepare", "is3d_host_prepare_tables", "is3d_host_context", "is3d_host_run",
                 "is3d_host_spectra", "is3d_host_dndx", "is3d_host_events", "is3d_host_event_particles",
                 "is3d_host_seconds", "is3d_host_stats", "is3d_host_pdg", "is3d_host_ptb",
-                "is3d_host_surface_column", "is3d_host_chosen"]
+                "is3d_host_surface_column", "is3d_host_chosen", "is3d_host_thermo_sums", "is3d_host_set_thermo_averages"]
 
 
 def load_libraries():
@@ -130,6 +130,8 @@ def load_libraries():
     host.is3d_host_pdg.argtypes = [vp, vp]
     host.is3d_host_ptb.restype = C.c_int64
     host.is3d_host_ptb.argtypes = [vp, vp, vp, vp, dp]
+    host.is3d_host_thermo_sums.argtypes = [vp, dp]
+    host.is3d_host_set_thermo_averages.argtypes = [vp, dp]
     host.is3d_host_surface_column.restype = C.c_int64
     host.is3d_host_surface_column.argtypes = [vp, C.c_int, C.POINTER(dp)]
     host.is3d_host_chosen.restype = C.c_int64
@@ -197,6 +199,16 @@ class HostSession:
         arr, keep = _cols(surface)
         n = len(keep[0])
         return self.host.is3d_host_set_surface(self.h, n, arr)
+
+    def thermo_sums(self) -> np.ndarray:
+        out = np.zeros(6)
+        self.host.is3d_host_thermo_sums(self.h, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def set_thermo_averages(self, avg5):
+        a = np.ascontiguousarray(avg5, dtype=np.float64)
+        assert a.size == 5
+        self.host.is3d_host_set_thermo_averages(self.h, a.ctypes.data_as(C.POINTER(C.c_double)))
 
     def prepare_tables(self):
         self.host.is3d_host_prepare_tables(self.h)

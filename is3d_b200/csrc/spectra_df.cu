@@ -20,9 +20,20 @@ namespace is3d {
 
 namespace {
 
-constexpr int kTile = 256;      // cells per shared-memory tile = threads per block
-constexpr int kThreads = 256;
-constexpr int kDfBinsPerThread = 3;   // species per thread (R)
+// launch shape (tunable at build time for the sweeps recorded in profiles/): threads per block, resident blocks per SM
+// the register allocation is bounded for, species per thread
+#ifndef IS3D_K1_THREADS
+#define IS3D_K1_THREADS 256
+#endif
+#ifndef IS3D_K1_MINBLOCKS
+#define IS3D_K1_MINBLOCKS 2
+#endif
+#ifndef IS3D_K1_R
+#define IS3D_K1_R 3
+#endif
+constexpr int kThreads = IS3D_K1_THREADS;
+constexpr int kTile = kThreads;  // cells per shared-memory tile = threads per block
+constexpr int kDfBinsPerThread = IS3D_K1_R;   // species per thread (R)
 
 __global__ void df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, DfTables tb, DfFlags fl,
                                 double *__restrict__ pack, int64_t stride, unsigned long long *counters)
@@ -47,7 +58,7 @@ struct DfGrid {
 };
 
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, int R>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, IS3D_K1_MINBLOCKS)
 df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk, DfGrid g,
                   double *__restrict__ partial, int64_t total)
 {
@@ -192,7 +203,7 @@ is3d_status build_bin_arrays(is3d_ctx *ctx, const double **mT, const double **pT
 void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
                    int64_t *cells_per_chunk)
 {
-  int64_t resident = 2 * (int64_t)ctx->sm_count;
+  int64_t resident = IS3D_K1_MINBLOCKS * (int64_t)ctx->sm_count;
   int64_t want = (16 * resident + blocks_per_chunk - 1) / blocks_per_chunk;
   int64_t max_by_cells = (ncells + tile - 1) / tile;
   int64_t max_by_mem = ((int64_t)1 << 30) / (total * 8);

@@ -148,6 +148,8 @@ is3d_host *is3d_host_open(const char *root, const char *const *overrides)
 void is3d_host_close(is3d_host *h) { delete h; }
 int64_t is3d_host_read_surface(is3d_host *h) { return h->s.read_surface(); }
 int64_t is3d_host_set_surface(is3d_host *h, int64_t n, const double *const cols[IS3D_SURFACE_COLUMNS]) { return h->s.set_surface(n, cols); }
+void is3d_host_thermo_sums(is3d_host *h, double sums6[6]) { compute_thermodynamic_sums(h->s.surf, sums6); }
+void is3d_host_set_thermo_averages(is3d_host *h, const double avg5[5]) { write_thermodynamic_averages(avg5); (void)h; }
 void is3d_host_prepare_tables(is3d_host *h) { h->s.prepare_tables(); }
 void is3d_host_prepare(is3d_host *h) { h->s.create_context(); }
 is3d_ctx *is3d_host_context(is3d_host *h) { return h->s.efa ? h->s.efa->context() : nullptr; }

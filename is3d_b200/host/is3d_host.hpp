@@ -99,6 +99,7 @@ struct FO_surface {
 
 // volume-weighted thermodynamic averages (readindata.cpp:330-366) + the side file the later stages re-read
 void compute_thermodynamic_averages(const FO_surface &s, double avg[5]);
+void compute_thermodynamic_sums(const FO_surface &s, double sums[6]);
 void write_thermodynamic_averages(const double avg[5]);
 
 class FO_data_reader {

@@ -20,6 +20,15 @@ void FO_surface::resize(int64_t n, bool with_vorticity)
 // ds_max-weighted averages, identical in all three readers (e.g. readindata.cpp:330-360)
 void compute_thermodynamic_averages(const FO_surface &s, double avg[5])
 {
+  double sums[6];
+  compute_thermodynamic_sums(s, sums);
+  for (int k = 0; k < 5; k++) avg[k] = sums[k] / sums[5];
+}
+
+// the numerators (T, E, P, muB, nB weighted by ds_max) and the denominator (sum of ds_max) of the averages: additive
+// over cell blocks, so ranks that each hold a block can all-reduce these six numbers to get the surface averages
+void compute_thermodynamic_sums(const FO_surface &s, double sums[6])
+{
   double T_avg = 0, E_avg = 0, P_avg = 0, muB_avg = 0, nB_avg = 0, max_volume = 0;
   const int64_t n = s.size();
   for (int64_t i = 0; i < n; i++) {
@@ -37,8 +46,7 @@ void compute_thermodynamic_averages(const FO_surface &s, double avg[5])
     muB_avg += (s.col[IS3D_COL_MUB][i] * ds_max);
     nB_avg += (s.col[IS3D_COL_NB][i] * ds_max);
   }
-  avg[0] = T_avg / max_volume; avg[1] = E_avg / max_volume; avg[2] = P_avg / max_volume;
-  avg[3] = muB_avg / max_volume; avg[4] = nB_avg / max_volume;
+  sums[0] = T_avg; sums[1] = E_avg; sums[2] = P_avg; sums[3] = muB_avg; sums[4] = nB_avg; sums[5] = max_volume;
 }
 
 // 15 significant digits, no trailing newline (readindata.cpp:363-366); later stages re-read this file, so the

@@ -78,7 +78,9 @@ def _df_table(path, include_baryon):
 class OracleProblem:
     """Everything cf_oracle needs, loaded with numpy from a working directory (tables) and the host layer (PDG)."""
 
-    def __init__(self, root: str, params: dict, surface: dict):
+    def __init__(self, root: str, params: dict, surface: dict, after_surface=None):
+        """after_surface(session): optional hook between set_surface and the table stage (sharded runs install the
+        whole-surface thermodynamic averages there)."""
         full = workdir.default_parameters()
         full.update({k: str(v) for k, v in params.items()})
         g = lambda k: float(full[k])  # noqa: E731
@@ -109,6 +111,8 @@ class OracleProblem:
             inp.col[k] = a.ctypes.data_as(dp)
         with HostSession(root) as h:
             h.set_surface(surface)
+            if after_surface is not None:
+                after_surface(h)
             h.prepare_tables()
             pdg = h.pdg()
             ptb = h.ptb()
