@@ -185,9 +185,11 @@ is3d_status is3d_total_yield(is3d_ctx *ctx, double *ntotal, is3d_stats *stats);
  * and, if dn_list != NULL, dn_list[cell*Ns + s] (ParticleSampler.cpp:876-911).  Host buffers. */
 is3d_status is3d_cell_yields(is3d_ctx *ctx, double *dn_tot, double *dn_list, is3d_stats *stats);
 
-/* sample_dN_pTdpTdphidy / _famod (EmissionFunction.h:175-179).  Particles of all events are returned in one
- * library-owned host array (event index in each record, grouped by event); counts[e] = hadrons in event e
- * (caller-owned, nevents entries).  Release with is3d_free_particles. */
+/* sample_dN_pTdpTdphidy / _famod (EmissionFunction.h:175-179), df_mode 1-5, fast = 0 or 1.  Particles of all events
+ * are returned in one library-owned, page-locked host array (event index in each record, grouped by event, within an
+ * event ordered by (cell, draw) -- independent of the launch geometry); counts[e] = hadrons in event e (caller-owned,
+ * nevents entries).  The array stays valid until is3d_free_particles, also across is3d_destroy; released buffers are
+ * reused by later calls on the same context. */
 is3d_status is3d_sample(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total,
                         int64_t *counts, is3d_stats *stats);
 void        is3d_free_particles(is3d_particle *particles);

@@ -318,8 +318,9 @@ def _abi_cell_yields(self, n_cells: int, n_species: int, with_list: bool = True)
     return tot, lst, st
 
 
-def _abi_sample(self, nevents: int):
-    """Returns (structured particle array grouped by event, counts per event, stats)."""
+def _abi_sample(self, nevents: int, copy: bool = True):
+    """Returns (structured particle array grouped by event, counts per event, stats).  copy=False returns a view of the
+    library-owned pinned list plus a release callable as a 4th item (the caller must call it when done)."""
     plist = C.c_void_p()
     total = C.c_int64()
     counts = np.zeros(nevents, dtype=np.int64)
@@ -328,12 +329,21 @@ def _abi_sample(self, nevents: int):
     n = total.value
     if plist.value and n:
         buf = (C.c_char * (n * PARTICLE_DTYPE.itemsize)).from_address(plist.value)
-        arr = np.frombuffer(buf, dtype=PARTICLE_DTYPE).copy()
+        arr = np.frombuffer(buf, dtype=PARTICLE_DTYPE)
+        if copy:
+            arr = arr.copy()
     else:
         arr = np.zeros(0, dtype=PARTICLE_DTYPE)
-    if plist.value:
-        self.lib.is3d_free_particles(plist)
-    return arr, counts, st
+    lib = self.lib
+
+    def release(ptr=plist):
+        if ptr.value:
+            lib.is3d_free_particles(ptr)
+            ptr.value = None
+    if copy:
+        release()
+        return arr, counts, st
+    return arr, counts, st, release
 
 
 def _abi_sample_histograms(self, ns: int, params: dict):

@@ -294,7 +294,13 @@ struct FamodFlags {
   int dimension;
   int include_baryon, include_shear, include_baryondiff;
   double deta_min;
+  int sampler = 0;             // 1: failure rules of sample_dN_pTdpTdphidy_famod (ParticleSampler.cpp:1335-1383): a failed first
+                               // attempt without a previous success IS a breakdown (the spectra path adopts (T,1,1) instead,
+                               // MomentumSpectra.cpp:1353-1364) and there is no renormalisation factor to go non-finite
 };
+
+// where the famod stage leaves its solution in the feqmod pack layout (slots the PTMA spectra kernel does not read)
+enum { FP_FAMOD_LAMBDA = FP_T, FP_FAMOD_AT = FP_TMOD, FP_FAMOD_AL = FP_DNFACT, FP_FAMOD_BETAPIPERP = FP_G, FP_FAMOD_BETAWPERP = FP_F_T2 };
 
 enum { CELL_RECONSTRUCTION_FAIL = 16 };
 
@@ -348,6 +354,11 @@ IS3D_HD int famod_setup_cell(const Reducer &red, const Cell &c, const FamodFlags
         lambda = X.lambda; aT = X.aT; aL = X.aL;
         if (chain) { chain->lambda_prev = lambda; chain->aT_prev = aT; chain->aL_prev = aL; chain->previous_success = true; }
       }
+    } else if (X.failed && fl.sampler) {
+      // sampler rule (ParticleSampler.cpp:1369-1374): breakdown, the variables stay at the initial guess (T, 1, 1)
+      breaks = true;
+      status |= CELL_RECONSTRUCTION_FAIL;
+      if (chain) chain->previous_success = false;
     } else {
       // also taken when the FIRST attempt fails without a previous success: the reference then adopts the returned
       // (lambda_0, aT_0, aL_0) = (T, 1, 1) as if it were a solution (:1353-1364)
@@ -376,7 +387,7 @@ IS3D_HD int famod_setup_cell(const Reducer &red, const Cell &c, const FamodFlags
   double eta_scale = 1;
   if (detB > fl.deta_min && fl.dimension == 2) eta_scale = detB / detB_bulk_two_thirds;
   double renorm = eta_scale / detC;
-  if (not_finite(renorm)) { breaks = true; renorm = 0.0; }
+  if (not_finite(renorm)) { if (!fl.sampler) breaks = true; renorm = 0.0; }
   if (breaks) status |= CELL_BREAKDOWN;
 
   // fallback: plain equilibrium distribution (no df), eta weight on the whole p.dsigma (:1540-1553, :1617)
@@ -402,7 +413,8 @@ IS3D_HD int famod_setup_cell(const Reducer &red, const Cell &c, const FamodFlags
     pack[FP_A3X + i] = iL * (Binv[3 * i] * vc[0] + Binv[3 * i + 1] * vc[1] + Binv[3 * i + 2] * vc[2]);
     pack[FP_A4X + i] = iL * (Binv[3 * i] * vd[0] + Binv[3 * i + 1] * vd[1] + Binv[3 * i + 2] * vd[2]);
   }
-  pack[FP_T] = lambda; pack[FP_TMOD] = aT; pack[FP_DNFACT] = aL;     // solution kept for inspection (unused by the kernel)
+  pack[FP_FAMOD_LAMBDA] = lambda; pack[FP_FAMOD_AT] = aT; pack[FP_FAMOD_AL] = aL;     // the solution and its coefficients:
+  pack[FP_FAMOD_BETAPIPERP] = betapiperp; pack[FP_FAMOD_BETAWPERP] = betaWperp;        // read by the PTMA sampler stage
   return status;
 }
 

@@ -80,6 +80,7 @@ void is3d_destroy(is3d_ctx *ctx)
   cudaSetDevice(ctx->prm.device);
   cudaStreamSynchronize(ctx->stream);
   for (void *p : ctx->owned) cudaFree(p);
+  release_host_lists_of(ctx);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

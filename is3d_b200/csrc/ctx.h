@@ -82,6 +82,10 @@ struct is3d_ctx {
   // sampler histograms (device)
   std::map<std::string, double *> hist;
 
+  // pinned host buffers holding particle lists handed to the caller (sampler.cu)
+  struct HostList { void *ptr = nullptr; size_t capacity = 0; bool in_use = false; is3d_ctx *owner = nullptr; };
+  std::vector<HostList *> host_lists;
+
   // every device allocation made by this context
   std::vector<void *> owned;
   // grow-only named scratch buffers
@@ -134,6 +138,7 @@ is3d_status run_total_yield(is3d_ctx *ctx, double *ntotal, is3d_stats *stats);
 is3d_status run_cell_yields(is3d_ctx *ctx, double *dn_tot_host, double *dn_list_host, is3d_stats *stats);
 is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts,
                         is3d_stats *stats);
+void release_host_lists_of(is3d_ctx *ctx);
 is3d_status measure_fp64_peak(is3d_ctx *ctx, double *tflops);
 is3d_status probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp, double *out_sqrt);
 

@@ -16,8 +16,10 @@
 #include <cub/cub.cuh>
 
 #include <cstring>
+#include <mutex>
 
 #include "ctx.h"
+#include "aniso.cuh"
 #include "sampler.cuh"
 
 namespace is3d {
@@ -29,6 +31,7 @@ struct SamplerTables {
   const double *mass, *sign, *baryon;
   const int *mcid;
   const double *cumA, *cumB;      // inclusive cumulative sums over species of neq and dn_bulk
+  const double *cell_cdf;         // [cell][ns] inclusive cumulative species densities of each cell, or NULL (fast mode)
   double totA, totB, totD;        // sums of neq, dn_bulk, dn_diff
 };
 
@@ -100,53 +103,89 @@ __device__ void bin_particle(const HistGrid &h, int s, const LabParticle &q, dou
   if (iphis >= 0 && iphis < h.phi_bins) atomicAdd(&h.dN_phis[(size_t)s * h.phi_bins + iphis], 1.0);
 }
 
+// accepted hadrons of one pass, compacted on the device
+struct SamplerOut {
+  is3d_particle *rec;                 // [capacity] records in acceptance (= scheduling) order
+  unsigned long long *key;            // [capacity] (event << 40) | proposal index: sorting by it gives a geometry-independent order
+  unsigned long long *nacc;           // running number of accepted records
+  unsigned long long *event_counts;   // [nevents] accepted hadrons per event (all passes)
+};
+
 __global__ void __launch_bounds__(128)
 sampler_hadron_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cell_global0,
-                      const unsigned long long *__restrict__ offsets, unsigned long long first, unsigned long long nprop,
+                      const unsigned long long *__restrict__ offsets, unsigned long long nprop,
                       SamplerTables st, int df_mode, int dimension, double y_cut, long nevents, uint64_t seed, HistGrid hg,
-                      is3d_particle *__restrict__ out, unsigned int *__restrict__ keys, unsigned long long *counters)
+                      SamplerOut out, unsigned long long *counters)
 {
-  unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nprop) return;
-  const unsigned long long jg = first + j;            // index in this pass's proposal numbering
-  // cell = last index with offsets[cell] <= jg
-  int64_t lo = 0, hi = ncells;
-  while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (offsets[mid] <= jg) lo = mid; else hi = mid; }
-  const int64_t cell = lo;
-  const uint32_t n = (uint32_t)(jg - offsets[cell]);
-  auto pk = [&](int k) { return pack[k * stride + cell]; };
-  Philox rng;
-  rng.init(seed, (uint64_t)(cell_global0 + cell), n);
-  int event = (int)(rng.canonical() * (double)nevents);
-  if (event >= nevents) event = (int)nevents - 1;
-  // species by inverse CDF of w_s = WA neq_s + WB dn_bulk_s (discrete_distribution, :919-931)
-  const double WA = pk(SP_WA), WB = pk(SP_WB);
-  const double target = rng.canonical() * (WA * st.totA + WB * st.totB);
-  int a = 0, b = st.ns - 1;
-  while (a < b) { int m = (a + b) >> 1; if (WA * st.cumA[m] + WB * st.cumB[m] > target) b = m; else a = m + 1; }
-  const int s = a;
-  const double mass = st.mass[s], sign = st.sign[s], baryon = st.baryon[s];
+  const unsigned long long jg = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;   // proposal index in this pass
+  bool accept = false;
   long samples = 0;
-  LrfMomentum p;
-  const bool accept = sample_hadron(rng, pk, df_mode, mass, sign, baryon, &samples, &p);
-  atomicAdd(&counters[6], (unsigned long long)samples);
-  unsigned int key = 0xFFFFFFFFu;
-  if (accept) {
-    atomicAdd(&counters[7], 1ull);
-    const double y_max = (dimension == 2) ? y_cut : 0.5;
-    LabParticle q = boost_to_lab(rng, pk, p, mass, dimension, y_max);
-    if (hg.test_sampler) {
-      bin_particle(hg, s, q, pk(SP_TAU), pk(SP_X), pk(SP_Y));
+  int event = 0;
+  is3d_particle r;
+  if (jg < nprop) {
+    // cell = last index with offsets[cell] <= jg
+    int64_t lo = 0, hi = ncells;
+    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (offsets[mid] <= jg) lo = mid; else hi = mid; }
+    const int64_t cell = lo;
+    const uint32_t n = (uint32_t)(jg - offsets[cell]);
+    auto pk = [&](int k) { return pack[k * stride + cell]; };
+    Philox rng;
+    rng.init(seed, (uint64_t)(cell_global0 + cell), n);
+    event = (int)(rng.canonical() * (double)nevents);
+    if (event >= nevents) event = (int)nevents - 1;
+    int s;
+    if (st.cell_cdf) {
+      // per-cell discrete distribution over species (fast = 0 and df_mode 5): inclusive cumulative row of this cell
+      const double *cdf = st.cell_cdf + (size_t)cell * st.ns;
+      const double target = rng.canonical() * cdf[st.ns - 1];
+      int a = 0, b = st.ns - 1;
+      while (a < b) { int m = (a + b) >> 1; if (cdf[m] > target) b = m; else a = m + 1; }
+      s = a;
     } else {
-      is3d_particle r;
-      r.chosen_index = s; r.mcid = st.mcid[s]; r.event = event; r.pad_ = 0;
-      r.mass = mass; r.tau = pk(SP_TAU); r.x = pk(SP_X); r.y = pk(SP_Y); r.eta = q.eta;
-      r.t = q.t; r.z = q.z; r.E = q.E; r.px = q.px; r.py = q.py; r.pz = q.pz;
-      out[j] = r;
-      key = (unsigned int)event;
+      // species by inverse CDF of w_s = WA neq_s + WB dn_bulk_s (discrete_distribution, :919-931)
+      const double WA = pk(SP_WA), WB = pk(SP_WB);
+      const double target = rng.canonical() * (WA * st.totA + WB * st.totB);
+      int a = 0, b = st.ns - 1;
+      while (a < b) { int m = (a + b) >> 1; if (WA * st.cumA[m] + WB * st.cumB[m] > target) b = m; else a = m + 1; }
+      s = a;
+    }
+    const double mass = st.mass[s], sign = st.sign[s], baryon = st.baryon[s];
+    LrfMomentum p;
+    accept = sample_hadron(rng, pk, df_mode, mass, sign, baryon, &samples, &p);
+    if (accept) {
+      const double y_max = (dimension == 2) ? y_cut : 0.5;
+      LabParticle q = boost_to_lab(rng, pk, p, mass, dimension, y_max);
+      if (hg.test_sampler) {
+        bin_particle(hg, s, q, pk(SP_TAU), pk(SP_X), pk(SP_Y));
+      } else {
+        r.chosen_index = s; r.mcid = st.mcid[s]; r.event = event; r.pad_ = 0;
+        r.mass = mass; r.tau = pk(SP_TAU); r.x = pk(SP_X); r.y = pk(SP_Y); r.eta = q.eta;
+        r.t = q.t; r.z = q.z; r.E = q.E; r.px = q.px; r.py = q.py; r.pz = q.pz;
+      }
     }
   }
-  if (keys) keys[j] = key;
+  // warp-aggregated counters: proposals of the rejection loops, accepted hadrons, output slots
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  unsigned long long wsamples = (unsigned long long)samples;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wsamples += __shfl_xor_sync(full, wsamples, o);
+  const unsigned amask = __ballot_sync(full, accept);
+  if (lane == 0) {
+    atomicAdd(&counters[6], wsamples);
+    if (amask) atomicAdd(&counters[7], (unsigned long long)__popc(amask));
+  }
+  if (!hg.test_sampler && amask) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(out.nacc, (unsigned long long)__popc(amask));
+    base = __shfl_sync(full, base, 0);
+    if (accept) {
+      const unsigned long long slot = base + __popc(amask & ((1u << lane) - 1u));
+      out.rec[slot] = r;
+      out.key[slot] = ((unsigned long long)event << 40) | jg;
+      atomicAdd(&out.event_counts[event], 1ull);
+    }
+  }
 }
 
 __global__ void iota_kernel(unsigned int *v, unsigned long long n)
@@ -182,8 +221,7 @@ struct SamplerSetup {
 is3d_status prepare_sampler(is3d_ctx *ctx, SamplerSetup *ss)
 {
   const is3d_params &p = ctx->prm;
-  if (p.df_mode == 5) { ctx->set_error("sampler df_mode 5 (PTMA): CUDA kernel not implemented in this build"); return IS3D_ERR_UNSUPPORTED; }
-  if (!p.fast) { ctx->set_error("sampler with fast = 0 (per-cell Gauss-Laguerre densities): CUDA kernel not implemented in this build"); return IS3D_ERR_UNSUPPORTED; }
+  if (p.df_mode == 5 && ctx->npdg <= 0) { ctx->set_error("PDG table not set (is3d_set_pdg)"); return IS3D_ERR_INVALID; }
   if (ctx->gla_pts <= 0) { ctx->set_error("Gauss-Laguerre tables not set"); return IS3D_ERR_INVALID; }
   if (!ctx->have_avg) { ctx->set_error("thermodynamic averages not set"); return IS3D_ERR_INVALID; }
   SamplerFlags &fl = ss->fl;
@@ -223,6 +261,7 @@ is3d_status prepare_sampler(is3d_ctx *ctx, SamplerSetup *ss)
   SamplerTables &st = ss->st;
   st.ns = ns; st.mass = ctx->d_mass; st.sign = ctx->d_sign; st.baryon = ctx->d_baryon; st.mcid = ctx->d_mcid;
   st.cumA = (const double *)dc; st.cumB = (const double *)dc + ns;
+  st.cell_cdf = nullptr;
   st.totA = a; st.totB = b; st.totD = d;
   return IS3D_OK;
 }
@@ -235,6 +274,7 @@ is3d_status fill_stats(is3d_ctx *ctx, void *counters, is3d_stats *stats, float m
   if (stats) {
     stats->cells_total = ctx->surf.n;
     stats->cells_skipped = (int64_t)h[0]; stats->cells_out_of_table = (int64_t)h[1]; stats->cells_breakdown = (int64_t)h[2];
+    stats->cells_pl_negative = (int64_t)h[3]; stats->reconstruction_failures = (int64_t)h[8]; stats->newton_iterations = (int64_t)h[9];
     stats->sampler_proposals = (int64_t)h[6]; stats->sampler_accepted = (int64_t)h[7];
     stats->kernel_ms = ms; stats->kernel_launches = launches;
   }
@@ -245,7 +285,204 @@ is3d_status fill_stats(is3d_ctx *ctx, void *counters, is3d_stats *stats, float m
   return IS3D_OK;
 }
 
-constexpr int64_t kSamplerMacro = 4 << 20;     // cells per pass (pack: 456 B / cell)
+// the famod stage counts into its own array (same slot meaning as the spectra path): pl < 0 cells -> [3], reconstruction
+// failures -> [8], Newton iterations -> [9]; breakdown cells are counted once, here
+__global__ void fold_famod_counters_kernel(const unsigned long long *__restrict__ f, unsigned long long *__restrict__ c)
+{
+  if (threadIdx.x == 0) { c[2] += f[2]; c[3] += f[3]; c[8] += f[8]; c[9] += f[9]; }
+}
+
+// ---- per-cell species densities (fast = 0, ParticleSampler.cpp:896-911 / max_particle_number :164-239; df_mode 5,
+// :1461-1499): the species weights differ from cell to cell, so each cell gets its own cumulative row cdf[cell][ns].
+struct DensityTables {
+  const double *mass, *sign, *deg, *baryon;
+  const double *gla_root, *gla_weight;
+  int gla_pts, ns, include_baryon;
+  const double *gl16;                 // 16-point Gauss-Laguerre table of the anisotropic path (aniso.cuh layout)
+};
+
+__global__ void sampler_density_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int df_mode, DensityTables t,
+                                       double *__restrict__ dens)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count * t.ns) return;
+  const int64_t cell = idx / t.ns;
+  const int s = (int)(idx - cell * t.ns);
+  double dn = 0.0;
+  if (pack[SP_VALID * stride + cell] != 0.0) {
+    auto pk = [&](int k) { return pack[k * stride + cell]; };
+    const double mass = t.mass[s], sign = t.sign[s], deg = t.deg[s], baryon = t.baryon[s];
+    if (df_mode == 5) {
+      // anisotropic density g Lambda^3 detA / (2 pi^2 hbarc^3) I_100 with the 16-point a = 1 rule; the chemical
+      // potential enters as exp(Ebar + chem) exactly as in the reference (:1490)
+      const double lambda = pk(SP_TSAMPLE), mbar = mass / lambda, mbar2 = mbar * mbar, chem = baryon * pk(SP_ALPHAB_SAMPLE);
+      double I_100 = 0.0;
+      for (int k = 0; k < 16; k++) {
+        const double pbar = t.gl16[k], w = t.gl16[16 + k];
+        const double Ebar = sqrt(pbar * pbar + mbar2);
+        I_100 += pbar * w * exp(pbar) / (exp(Ebar + chem) + sign);
+      }
+      dn = deg * pk(SP_C0) * I_100;
+    } else {
+      const double T = pk(SP_T), alphaB = pk(SP_ALPHAB), mbar = mass / T;
+      const double neq_fact = T * T * T / kTwoPi2HbarC3, J20_fact = T * neq_fact;
+      const double *r1 = t.gla_root + 1 * t.gla_pts, *w1 = t.gla_weight + 1 * t.gla_pts;
+      const double *r2 = t.gla_root + 2 * t.gla_pts, *w2 = t.gla_weight + 2 * t.gla_pts;
+      const bool breaks = pk(SP_BREAKDOWN) != 0.0;
+      if (df_mode == 3 && !breaks) {
+        const double neq = neq_fact * deg * gauss_thermal<TI_NEQ>(r1, w1, t.gla_pts, mbar, alphaB, baryon, sign);
+        double J10 = 0.0;
+        if (t.include_baryon) J10 = neq_fact * deg * gauss_thermal<TI_J10>(r1, w1, t.gla_pts, mbar, alphaB, baryon, sign);
+        const double J20 = J20_fact * deg * gauss_thermal<TI_J20>(r2, w2, t.gla_pts, mbar, alphaB, baryon, sign);
+        // SP_C1 = G, SP_C2 = F / T^2, SP_C4 = bulkPi / betabulk
+        dn = neq + pk(SP_C4) * (neq + (baryon * J10 * pk(SP_C1)) + (J20 * pk(SP_C2)));
+      } else if (df_mode == 4 && !breaks) {
+        dn = pk(SP_Z) * neq_fact * deg * gauss_thermal<TI_NEQ>(r1, w1, t.gla_pts, mbar, 0.0, 0.0, sign);
+      } else {
+        dn = 2.0 * neq_fact * deg * gauss_thermal<TI_NEQ>(r1, w1, t.gla_pts, mbar, alphaB, baryon, sign);
+      }
+    }
+  }
+  dens[idx] = dn;
+}
+
+// one warp per cell: in-place inclusive sum over species (serial order inside each lane's contiguous slice, slices
+// combined by a shuffle scan), total -> dn_tot with the volume factor (:913-915) and the Poisson proposal count
+__global__ void sampler_cdf_kernel(double *__restrict__ pack, int64_t stride, int64_t count, int64_t cell_global0, int ns,
+                                   double *__restrict__ cdf, double y_max, double nevents, uint64_t seed,
+                                   unsigned long long *__restrict__ ncount)
+{
+  const int64_t cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (cell >= count) return;
+  double *row = cdf + (size_t)cell * ns;
+  const int per = (ns + 31) / 32, s0 = lane * per, s1 = min(ns, s0 + per);
+  double local = 0.0;
+  for (int s = s0; s < s1; s++) { local += row[s]; row[s] = local; }
+  double incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { double v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  const double before = incl - local;
+  for (int s = s0; s < s1; s++) row[s] += before;
+  const double total = __shfl_sync(0xffffffffu, incl, 31);
+  if (lane == 0) {
+    const bool valid = pack[SP_VALID * stride + cell] != 0.0;
+    const double dn_tot = (valid && total > 0.0) ? total * (2.0 * y_max * pack[SP_DSMAX * stride + cell]) : 0.0;
+    pack[SP_DNTOT * stride + cell] = dn_tot;
+    unsigned long long n = 0;
+    if (nevents > 0.0 && dn_tot > 0.0) {
+      Philox rng;
+      rng.init(seed, (uint64_t)(cell_global0 + cell), 0xFFFFFFFFu);
+      n = (unsigned long long)poisson_sample(rng, nevents * dn_tot);
+    }
+    if (ncount) ncount[cell] = n;
+  }
+}
+
+// df_mode 5: fold the anisotropic solution left by the famod stage (feqmod pack layout) into the sampler pack:
+// sampling temperature Lambda, chemical potential upsilon_B = alpha_B, momentum map B_ij = C_ik A_kj (identity on
+// breakdown), density prefactor Lambda^3 detA / (2 pi^2 hbarc^3)   (ParticleSampler.cpp:1385-1470)
+__global__ void sampler_famod_fold_kernel(double *__restrict__ pack, int64_t stride, int64_t count, const double *__restrict__ fpack,
+                                          int64_t fstride, int include_shear)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  if (pack[SP_VALID * stride + i] == 0.0) return;
+  auto fp = [&](int k) { return fpack[k * fstride + i]; };
+  auto sp = [&](int k) -> double & { return pack[k * stride + i]; };
+  const double lambda = fp(FP_FAMOD_LAMBDA), aT = fp(FP_FAMOD_AT), aL = fp(FP_FAMOD_AL);
+  const double shear_coeff = 0.5 / fp(FP_FAMOD_BETAPIPERP), diff_coeff = 1.0 / fp(FP_FAMOD_BETAWPERP);
+  double piTxx = 0, piTxy = 0, piTyy = 0, WTzx = 0, WTzy = 0;
+  if (include_shear) {
+    piTxx = (sp(SP_PIXX) - sp(SP_PIYY)) / 2.; piTxy = sp(SP_PIXY); piTyy = -piTxx; WTzx = sp(SP_PIXZ); WTzy = sp(SP_PIYZ);
+  }
+  double Bxx = aT + aT * shear_coeff * piTxx, Bxy = aT * shear_coeff * piTxy, Bxz = diff_coeff * WTzx * aT * aL / (aT + aL);
+  double Byy = aT + aT * shear_coeff * piTyy, Byz = diff_coeff * WTzy * aT * aL / (aT + aL), Bzz = aL;
+  const bool breaks = fp(FP_BREAKDOWN) != 0.0;
+  if (breaks) { Bxx = 1; Bxy = 0; Bxz = 0; Byy = 1; Byz = 0; Bzz = 1; }
+  sp(SP_PIXX) = Bxx; sp(SP_PIXY) = Bxy; sp(SP_PIXZ) = Bxz; sp(SP_PIYY) = Byy; sp(SP_PIYZ) = Byz; sp(SP_PIZZ) = Bzz;
+  sp(SP_BREAKDOWN) = breaks ? 1.0 : 0.0;
+  sp(SP_TSAMPLE) = lambda;
+  sp(SP_ALPHAB_SAMPLE) = fp(FP_ALPHAB_MOD);
+  sp(SP_C0) = lambda * lambda * lambda * (aT * aT * aL) / kTwoPi2HbarC3;
+}
+
+// budget for the per-pass scratch (cell pack + per-cell species rows), in bytes
+constexpr int64_t kSamplerPassBytes = (int64_t)8 << 30;
+
+bool sampler_uses_cell_cdf(const is3d_ctx *ctx) { return ctx->prm.df_mode == 5 || !ctx->prm.fast; }
+
+int64_t sampler_cells_per_pass(const is3d_ctx *ctx)
+{
+  int64_t per_cell = SP_SIZE * 8;
+  if (sampler_uses_cell_cdf(ctx)) per_cell += 8 * (int64_t)ctx->ns;
+  if (ctx->prm.df_mode == 5) per_cell += FP_SIZE * 8;
+  int64_t cells = kSamplerPassBytes / per_cell;
+  cells = cells / 1024 * 1024;
+  if (cells > ((int64_t)16 << 20)) cells = (int64_t)16 << 20;
+  return cells < 1024 ? 1024 : cells;
+}
+
+}  // namespace
+
+is3d_status famod_setup_pass(is3d_ctx *ctx, int64_t begin, int64_t count, double *pack, int64_t stride, unsigned long long *counters,
+                             int64_t *launches, bool sampler_rules);
+
+namespace {
+
+// One pass of the per-cell stage: cell pack, mean yields, species rows (where the weights are cell dependent) and the
+// Poisson proposal counts.  nevents = 0 skips the Poisson draw (yield-only callers).
+is3d_status sampler_setup_pass(is3d_ctx *ctx, SamplerSetup &ss, int64_t begin, int64_t count, double nevents, double *pack,
+                               int64_t stride, unsigned long long *ncount, double *yield, unsigned long long *counters,
+                               int64_t *launches, bool with_species, double *dens_host = nullptr)
+{
+  const is3d_params &p = ctx->prm;
+  const bool cdf_mode = with_species && sampler_uses_cell_cdf(ctx);
+  ss.st.cell_cdf = nullptr;
+  sampler_setup_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
+      ctx->surf, begin, count, ctx->global_offset, ctx->tb, ss.fl, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts, ss.st,
+      cdf_mode ? 0.0 : nevents, (uint64_t)p.sampler_seed, pack, stride, cdf_mode ? nullptr : ncount, yield, counters);
+  IS3D_CUDA_TRY(ctx, cudaGetLastError());
+  (*launches)++;
+  if (!cdf_mode) return IS3D_OK;
+
+  void *cdf = nullptr, *gl = nullptr;
+  IS3D_TRY(ctx->get_scratch("sampler_cell_cdf", (size_t)stride * ctx->ns * sizeof(double), &cdf));
+  IS3D_TRY(ctx->get_scratch("gl16", 96 * sizeof(double), &gl));
+  if (p.df_mode == 5) {
+    void *fpack = nullptr, *fcounters = nullptr;
+    IS3D_TRY(ctx->get_scratch("famod_pack", (size_t)FP_SIZE * stride * sizeof(double), &fpack));
+    IS3D_TRY(ctx->get_scratch("famod_counters", 16 * sizeof(unsigned long long), &fcounters));
+    IS3D_CUDA_TRY(ctx, cudaMemsetAsync(fcounters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    IS3D_TRY(famod_setup_pass(ctx, begin, count, (double *)fpack, stride, (unsigned long long *)fcounters, launches, true));
+    sampler_famod_fold_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(pack, stride, count, (const double *)fpack, stride,
+                                                                                     p.include_shear_deltaf);
+    IS3D_CUDA_TRY(ctx, cudaGetLastError());
+    fold_famod_counters_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long *)fcounters, counters);
+    (*launches) += 2;
+  } else if (begin == 0) {
+    double t[96];
+    fill_gl16_table(t);       // unused by df_mode 1-4; keeps the pointer valid
+    IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(gl, t, sizeof(t), cudaMemcpyHostToDevice, ctx->stream));
+    IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  DensityTables dt;
+  dt.mass = ctx->d_mass; dt.sign = ctx->d_sign; dt.deg = ctx->d_deg; dt.baryon = ctx->d_baryon;
+  dt.gla_root = ctx->d_gla_root; dt.gla_weight = ctx->d_gla_weight; dt.gla_pts = ctx->gla_pts; dt.ns = ctx->ns;
+  dt.include_baryon = p.include_baryon; dt.gl16 = (const double *)gl;
+  const int64_t work = count * ctx->ns;
+  sampler_density_kernel<<<(unsigned)((work + 127) / 128), 128, 0, ctx->stream>>>(pack, stride, count, p.df_mode, dt, (double *)cdf);
+  IS3D_CUDA_TRY(ctx, cudaGetLastError());
+  if (dens_host)      // per-species densities before they are accumulated in place (is3d_cell_yields)
+    IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(dens_host, cdf, (size_t)work * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  const double y_max = (p.dimension == 2) ? p.y_cut : 0.5;
+  sampler_cdf_kernel<<<(unsigned)((count * 32 + 127) / 128), 128, 0, ctx->stream>>>(pack, stride, count, ctx->global_offset + begin, ctx->ns,
+                                                                                (double *)cdf, y_max, nevents, (uint64_t)p.sampler_seed, ncount);
+  IS3D_CUDA_TRY(ctx, cudaGetLastError());
+  (*launches) += 2;
+  ss.st.cell_cdf = (const double *)cdf;
+  return IS3D_OK;
+}
 
 }  // namespace
 
@@ -255,7 +492,8 @@ is3d_status run_total_yield(is3d_ctx *ctx, double *ntotal, is3d_stats *stats)
   SamplerSetup ss;
   IS3D_TRY(prepare_sampler(ctx, &ss));
   const int64_t n = ctx->surf.n;
-  const int64_t stride = n < kSamplerMacro ? n : kSamplerMacro;
+  const int64_t macro = sampler_cells_per_pass(ctx);
+  const int64_t stride = n < macro ? n : macro;
   void *pack = nullptr, *yield = nullptr, *counters = nullptr, *bsum = nullptr;
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)SP_SIZE * stride * sizeof(double), &pack));
   IS3D_TRY(ctx->get_scratch("cell_yield", (size_t)stride * sizeof(double), &yield));
@@ -264,56 +502,57 @@ is3d_status run_total_yield(is3d_ctx *ctx, double *ntotal, is3d_stats *stats)
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
   double total = 0.0;
   int64_t launches = 0;
-  for (int64_t begin = 0; begin < n; begin += kSamplerMacro) {
-    int64_t count = n - begin < kSamplerMacro ? n - begin : kSamplerMacro;
-    sampler_setup_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
-        ctx->surf, begin, count, ctx->global_offset, ctx->tb, ss.fl, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts, ss.st, 0.0,
-        (uint64_t)ctx->prm.sampler_seed, (double *)pack, stride, nullptr, (double *)yield, (unsigned long long *)counters);
-    IS3D_CUDA_TRY(ctx, cudaGetLastError());
+  for (int64_t begin = 0; begin < n; begin += macro) {
+    int64_t count = n - begin < macro ? n - begin : macro;
+    IS3D_TRY(sampler_setup_pass(ctx, ss, begin, count, 0.0, (double *)pack, stride, nullptr, (double *)yield,
+                                (unsigned long long *)counters, &launches, false));
     yield_reduce_kernel<<<1024, 256, 0, ctx->stream>>>((double *)yield, count, (double *)bsum);
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
     double h[1024];
     IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(h, bsum, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 1024; i++) total += h[i];
-    launches += 2;
+    launches += 1;
   }
   if (ctx->prm.dimension == 2) total *= (2.0 * ctx->prm.y_cut);     // :628-631
   *ntotal = total;
   return fill_stats(ctx, counters, stats, 0.f, launches);
 }
 
-// per-cell mean yields of the sampler (dn_tot after the volume factor; dn_list[cell][s] = WA neq_s + WB dn_bulk_s)
+// per-cell mean yields of the sampler: dn_tot after the volume factor; dn_list[cell][s] = fast-mode WA neq_s + WB dn_bulk_s,
+// or the cell's own Gauss-Laguerre densities for fast = 0 / df_mode 5
 is3d_status run_cell_yields(is3d_ctx *ctx, double *dn_tot_host, double *dn_list_host, is3d_stats *stats)
 {
   SamplerSetup ss;
   IS3D_TRY(prepare_sampler(ctx, &ss));
   const int64_t n = ctx->surf.n;
-  const int64_t stride = n < kSamplerMacro ? n : kSamplerMacro;
+  const int64_t macro = sampler_cells_per_pass(ctx);
+  const int64_t stride = n < macro ? n : macro;
+  const int ns = ctx->ns;
   void *pack = nullptr, *counters = nullptr;
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)SP_SIZE * stride * sizeof(double), &pack));
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
   std::vector<double> wa(stride), wb(stride);
   int64_t launches = 0;
-  for (int64_t begin = 0; begin < n; begin += kSamplerMacro) {
-    int64_t count = n - begin < kSamplerMacro ? n - begin : kSamplerMacro;
-    sampler_setup_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
-        ctx->surf, begin, count, ctx->global_offset, ctx->tb, ss.fl, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts, ss.st, 0.0,
-        (uint64_t)ctx->prm.sampler_seed, (double *)pack, stride, nullptr, nullptr, (unsigned long long *)counters);
-    IS3D_CUDA_TRY(ctx, cudaGetLastError());
-    launches++;
+  for (int64_t begin = 0; begin < n; begin += macro) {
+    int64_t count = n - begin < macro ? n - begin : macro;
+    const bool rows = dn_list_host && sampler_uses_cell_cdf(ctx);
+    IS3D_TRY(sampler_setup_pass(ctx, ss, begin, count, 0.0, (double *)pack, stride, nullptr, nullptr, (unsigned long long *)counters,
+                                &launches, true, rows ? dn_list_host + (size_t)begin * ns : nullptr));
     const double *pk = (const double *)pack;
     IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(dn_tot_host + begin, pk + (size_t)SP_DNTOT * stride, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (dn_list_host) {
+    if (rows) {
+      // dn_list came back from the density stage inside sampler_setup_pass
+    } else if (dn_list_host) {
       IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(wa.data(), pk + (size_t)SP_WA * stride, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(wb.data(), pk + (size_t)SP_WB * stride, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      for (int64_t i = 0; i < count; i++)
+        for (int s = 0; s < ns; s++)
+          dn_list_host[(size_t)(begin + i) * ns + s] = wa[i] * ctx->h_neq[s] + wb[i] * ctx->h_dnbulk[s];
     }
     IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (dn_list_host)
-      for (int64_t i = 0; i < count; i++)
-        for (int s = 0; s < ctx->ns; s++)
-          dn_list_host[(size_t)(begin + i) * ctx->ns + s] = wa[i] * ctx->h_neq[s] + wb[i] * ctx->h_dnbulk[s];
   }
   return fill_stats(ctx, counters, stats, 0.f, launches);
 }
@@ -342,41 +581,109 @@ static is3d_status ensure_hist(is3d_ctx *ctx, HistGrid *hg, bool zero)
   return IS3D_OK;
 }
 
+// Library-owned pinned host buffers for particle lists.  A list handed out by is3d_sample stays valid until
+// is3d_free_particles; released buffers are reused by later calls on the same context (page-locking gigabytes costs
+// more than sampling them).  The registry maps a list pointer back to its buffer for is3d_free_particles(ptr).
+static std::mutex g_list_mutex;
+static std::map<void *, is3d_ctx::HostList *> g_lists;
+
+static is3d_status acquire_host_list(is3d_ctx *ctx, size_t bytes, is3d_ctx::HostList **out)
+{
+  std::lock_guard<std::mutex> lock(g_list_mutex);
+  is3d_ctx::HostList *best = nullptr;
+  for (auto *h : ctx->host_lists)
+    if (!h->in_use && h->capacity >= bytes && (!best || h->capacity < best->capacity)) best = h;
+  if (!best) {
+    // drop released buffers that are too small, then page-lock a new one
+    for (size_t i = 0; i < ctx->host_lists.size();) {
+      auto *h = ctx->host_lists[i];
+      if (!h->in_use) { g_lists.erase(h->ptr); cudaFreeHost(h->ptr); delete h; ctx->host_lists.erase(ctx->host_lists.begin() + i); }
+      else i++;
+    }
+    best = new is3d_ctx::HostList;
+    best->capacity = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMallocHost(&best->ptr, best->capacity);
+    if (e != cudaSuccess) { delete best; ctx->set_error(std::string("cudaMallocHost (particle list): ") + cudaGetErrorString(e)); return IS3D_ERR_CUDA; }
+    best->owner = ctx;
+    ctx->host_lists.push_back(best);
+    g_lists[best->ptr] = best;
+  }
+  best->in_use = true;
+  *out = best;
+  return IS3D_OK;
+}
+
+void release_host_lists_of(is3d_ctx *ctx)
+{
+  std::lock_guard<std::mutex> lock(g_list_mutex);
+  for (auto *h : ctx->host_lists) {
+    if (h->in_use) { h->owner = nullptr; continue; }      // still held by the caller: freed by is3d_free_particles
+    g_lists.erase(h->ptr);
+    cudaFreeHost(h->ptr);
+    delete h;
+  }
+  ctx->host_lists.clear();
+}
+
+static bool release_host_list(void *ptr)
+{
+  std::lock_guard<std::mutex> lock(g_list_mutex);
+  auto it = g_lists.find(ptr);
+  if (it == g_lists.end()) return false;
+  is3d_ctx::HostList *h = it->second;
+  if (h->owner) { h->in_use = false; return true; }         // back to its context's pool
+  g_lists.erase(it);
+  cudaFreeHost(h->ptr);
+  delete h;
+  return true;
+}
+
+constexpr unsigned long long kMaxProposalsPerPass = 256ull << 20;    // bounds the record scratch to ~27 GB
+
 is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total_out, int64_t *counts,
                         is3d_stats *stats)
 {
   const is3d_params &p = ctx->prm;
-  if (nevents <= 0 || nevents > 0x7FFFFFFF) { ctx->set_error("sample: nevents out of range"); return IS3D_ERR_INVALID; }
+  if (nevents <= 0 || nevents > (1 << 24)) { ctx->set_error("sample: nevents out of range (1 .. 2^24)"); return IS3D_ERR_INVALID; }
   SamplerSetup ss;
   IS3D_TRY(prepare_sampler(ctx, &ss));
   HistGrid hg;
   IS3D_TRY(ensure_hist(ctx, &hg, true));
+  const bool lists = !p.test_sampler;
   const int64_t n = ctx->surf.n;
-  const int64_t stride = n < kSamplerMacro ? n : kSamplerMacro;
-  void *pack = nullptr, *counters = nullptr, *ncount = nullptr, *offsets = nullptr;
+  const int64_t macro = sampler_cells_per_pass(ctx);
+  const int64_t stride = n < macro ? n : macro;
+  void *pack = nullptr, *counters = nullptr, *ncount = nullptr, *offsets = nullptr, *evc = nullptr, *nacc_dev = nullptr;
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)SP_SIZE * stride * sizeof(double), &pack));
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
   IS3D_TRY(ctx->get_scratch("sampler_ncount", (size_t)(stride + 1) * sizeof(unsigned long long), &ncount));
   IS3D_TRY(ctx->get_scratch("sampler_offsets", (size_t)(stride + 1) * sizeof(unsigned long long), &offsets));
+  IS3D_TRY(ctx->get_scratch("sampler_event_counts", (size_t)nevents * sizeof(unsigned long long), &evc));
+  IS3D_TRY(ctx->get_scratch("sampler_nacc", sizeof(unsigned long long), &nacc_dev));
+  void *counters_backup = nullptr;
+  IS3D_TRY(ctx->get_scratch("counters_backup", 16 * sizeof(unsigned long long), &counters_backup));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(evc, 0, (size_t)nevents * sizeof(unsigned long long), ctx->stream));
 
-  std::vector<std::vector<is3d_particle>> passes;      // each pass: particles sorted by event
-  std::vector<int64_t> event_counts(nevents, 0);
-  const unsigned long long kMaxProposalsPerLaunch = 16ull << 20;
+  struct PassList { is3d_ctx::HostList *buf; unsigned long long n; };
+  std::vector<PassList> passes;                         // each pass: records sorted by (event, proposal index)
+  auto drop_passes = [&]() { for (auto &q : passes) release_host_list(q.buf->ptr); passes.clear(); };
   cudaEvent_t e0, e1;
   IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
   IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));
   float ms_total = 0.f;
   int64_t launches = 0;
+  int key_bits = 40;
+  while ((1ll << (key_bits - 40)) < nevents) key_bits++;
 
-  for (int64_t begin = 0; begin < n; begin += kSamplerMacro) {
-    int64_t count = n - begin < kSamplerMacro ? n - begin : kSamplerMacro;
+  int64_t begin = 0;
+  int64_t pass_cells = stride;
+  while (begin < n) {
+    int64_t count = n - begin < pass_cells ? n - begin : pass_cells;
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-    sampler_setup_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
-        ctx->surf, begin, count, ctx->global_offset, ctx->tb, ss.fl, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts, ss.st,
-        (double)nevents, (uint64_t)p.sampler_seed, (double *)pack, stride, (unsigned long long *)ncount, nullptr,
-        (unsigned long long *)counters);
-    IS3D_CUDA_TRY(ctx, cudaGetLastError());
+    IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(counters_backup, counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+    IS3D_TRY(sampler_setup_pass(ctx, ss, begin, count, (double)nevents, (double *)pack, stride, (unsigned long long *)ncount, nullptr,
+                                (unsigned long long *)counters, &launches, true));
     IS3D_CUDA_TRY(ctx, cudaMemsetAsync((unsigned long long *)ncount + count, 0, sizeof(unsigned long long), ctx->stream));
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (unsigned long long *)ncount, (unsigned long long *)offsets, (int)(count + 1), ctx->stream);
@@ -384,51 +691,57 @@ is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
     IS3D_TRY(ctx->get_scratch("cub_tmp", tmp_bytes, &tmp));
     cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (unsigned long long *)ncount, (unsigned long long *)offsets, (int)(count + 1), ctx->stream);
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
-    unsigned long long nprop_total = 0;
-    IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(&nprop_total, (unsigned long long *)offsets + count, sizeof(nprop_total), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long nprop = 0;
+    IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(&nprop, (unsigned long long *)offsets + count, sizeof(nprop), cudaMemcpyDeviceToHost, ctx->stream));
     IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    launches += 3;
-
-    for (unsigned long long first = 0; first < nprop_total; first += kMaxProposalsPerLaunch) {
-      unsigned long long np = nprop_total - first < kMaxProposalsPerLaunch ? nprop_total - first : kMaxProposalsPerLaunch;
-      void *rec = nullptr, *keys = nullptr, *keys2 = nullptr, *idx = nullptr, *idx2 = nullptr, *sorted = nullptr;
-      const bool lists = !p.test_sampler;
+    launches += 2;
+    if (nprop > kMaxProposalsPerPass && count > 1) {
+      // too many proposals for one pass: halve the cell block and redo its set-up (deterministic, so nothing is lost);
+      // the counters of the discarded attempt are rolled back by re-zeroing below
+      pass_cells = (count + 1) / 2;
+      IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(counters, counters_backup, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+      continue;
+    }
+    if (nprop > 0) {
+      SamplerOut out{nullptr, nullptr, (unsigned long long *)nacc_dev, (unsigned long long *)evc};
+      void *rec = nullptr, *key = nullptr;
       if (lists) {
-        IS3D_TRY(ctx->get_scratch("sampler_rec", np * sizeof(is3d_particle), &rec));
-        IS3D_TRY(ctx->get_scratch("sampler_keys", np * sizeof(unsigned int), &keys));
-        IS3D_TRY(ctx->get_scratch("sampler_keys2", np * sizeof(unsigned int), &keys2));
-        IS3D_TRY(ctx->get_scratch("sampler_idx", np * sizeof(unsigned int), &idx));
-        IS3D_TRY(ctx->get_scratch("sampler_idx2", np * sizeof(unsigned int), &idx2));
+        IS3D_TRY(ctx->get_scratch("sampler_rec", nprop * sizeof(is3d_particle), &rec));
+        IS3D_TRY(ctx->get_scratch("sampler_key", nprop * sizeof(unsigned long long), &key));
+        IS3D_CUDA_TRY(ctx, cudaMemsetAsync(nacc_dev, 0, sizeof(unsigned long long), ctx->stream));
+        out.rec = (is3d_particle *)rec; out.key = (unsigned long long *)key;
       }
-      sampler_hadron_kernel<<<(unsigned)((np + 127) / 128), 128, 0, ctx->stream>>>(
-          (double *)pack, stride, count, ctx->global_offset + begin, (unsigned long long *)offsets, first, np, ss.st, p.df_mode,
-          p.dimension, p.y_cut, (long)nevents, (uint64_t)p.sampler_seed, hg, (is3d_particle *)rec, (unsigned int *)keys,
-          (unsigned long long *)counters);
+      sampler_hadron_kernel<<<(unsigned)((nprop + 127) / 128), 128, 0, ctx->stream>>>(
+          (double *)pack, stride, count, ctx->global_offset + begin, (unsigned long long *)offsets, nprop, ss.st, p.df_mode,
+          p.dimension, p.y_cut, (long)nevents, (uint64_t)p.sampler_seed, hg, out, (unsigned long long *)counters);
       IS3D_CUDA_TRY(ctx, cudaGetLastError());
       launches++;
       if (lists) {
-        iota_kernel<<<(unsigned)((np + 255) / 256), 256, 0, ctx->stream>>>((unsigned int *)idx, np);
-        size_t sb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, sb, (unsigned int *)keys, (unsigned int *)keys2, (unsigned int *)idx, (unsigned int *)idx2, (int)np, 0, 32, ctx->stream);
-        void *stmp = nullptr;
-        IS3D_TRY(ctx->get_scratch("cub_tmp", sb, &stmp));
-        cub::DeviceRadixSort::SortPairs(stmp, sb, (unsigned int *)keys, (unsigned int *)keys2, (unsigned int *)idx, (unsigned int *)idx2, (int)np, 0, 32, ctx->stream);
-        IS3D_CUDA_TRY(ctx, cudaGetLastError());
-        // accepted hadrons sort to the front (rejected carry key 0xFFFFFFFF): count them on the host from the keys
-        std::vector<unsigned int> hk(np);
-        IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(hk.data(), keys2, np * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-        IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         unsigned long long nacc = 0;
-        while (nacc < np && hk[nacc] != 0xFFFFFFFFu) { event_counts[hk[nacc]]++; nacc++; }
-        launches += 3;
+        IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(&nacc, nacc_dev, sizeof(nacc), cudaMemcpyDeviceToHost, ctx->stream));
+        IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (nacc) {
+          void *key2 = nullptr, *idx = nullptr, *idx2 = nullptr, *sorted = nullptr, *stmp = nullptr;
+          IS3D_TRY(ctx->get_scratch("sampler_key2", nacc * sizeof(unsigned long long), &key2));
+          IS3D_TRY(ctx->get_scratch("sampler_idx", nacc * sizeof(unsigned int), &idx));
+          IS3D_TRY(ctx->get_scratch("sampler_idx2", nacc * sizeof(unsigned int), &idx2));
           IS3D_TRY(ctx->get_scratch("sampler_sorted", nacc * sizeof(is3d_particle), &sorted));
-          gather_particles_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, ctx->stream>>>((is3d_particle *)rec, (unsigned int *)idx2, nacc, (is3d_particle *)sorted);
+          iota_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, ctx->stream>>>((unsigned int *)idx, nacc);
+          size_t sb = 0;
+          cub::DeviceRadixSort::SortPairs(nullptr, sb, (unsigned long long *)key, (unsigned long long *)key2, (unsigned int *)idx,
+                                          (unsigned int *)idx2, (int)nacc, 0, key_bits, ctx->stream);
+          IS3D_TRY(ctx->get_scratch("cub_tmp", sb, &stmp));
+          cub::DeviceRadixSort::SortPairs(stmp, sb, (unsigned long long *)key, (unsigned long long *)key2, (unsigned int *)idx,
+                                          (unsigned int *)idx2, (int)nacc, 0, key_bits, ctx->stream);
+          gather_particles_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, ctx->stream>>>((is3d_particle *)rec, (unsigned int *)idx2, nacc,
+                                                                                         (is3d_particle *)sorted);
           IS3D_CUDA_TRY(ctx, cudaGetLastError());
-          passes.emplace_back(nacc);
-          IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(passes.back().data(), sorted, nacc * sizeof(is3d_particle), cudaMemcpyDeviceToHost, ctx->stream));
-          IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-          launches++;
+          launches += 3;
+          is3d_ctx::HostList *hb = nullptr;
+          is3d_status st = acquire_host_list(ctx, nacc * sizeof(is3d_particle), &hb);
+          if (st != IS3D_OK) { drop_passes(); return st; }
+          passes.push_back({hb, nacc});
+          IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(hb->ptr, sorted, nacc * sizeof(is3d_particle), cudaMemcpyDeviceToHost, ctx->stream));
         }
       }
     }
@@ -437,27 +750,46 @@ is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
     float ms = 0.f;
     IS3D_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
     ms_total += ms;
+    begin += count;
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  IS3D_TRY(fill_stats(ctx, counters, stats, ms_total, launches));
+  is3d_status fs = fill_stats(ctx, counters, stats, ms_total, launches);
+  if (fs != IS3D_OK) { drop_passes(); return fs; }
 
-  // merge the per-pass event-sorted lists into one array grouped by event
+  std::vector<unsigned long long> event_counts(nevents, 0);
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(event_counts.data(), evc, (size_t)nevents * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   int64_t total = 0;
-  for (int64_t e = 0; e < nevents; e++) total += event_counts[e];
-  is3d_particle *outp = nullptr;
+  for (int64_t e = 0; e < nevents; e++) total += (int64_t)event_counts[e];
   if (particles) {
-    outp = (is3d_particle *)malloc((size_t)(total > 0 ? total : 1) * sizeof(is3d_particle));
-    if (!outp) { ctx->set_error("sample: out of host memory"); return IS3D_ERR_INVALID; }
-    std::vector<int64_t> cursor(nevents, 0);
-    int64_t acc = 0;
-    for (int64_t e = 0; e < nevents; e++) { cursor[e] = acc; acc += event_counts[e]; }
-    for (auto &v : passes)
-      for (const is3d_particle &q : v) outp[cursor[q.event]++] = q;
-    *particles = outp;
+    if (passes.size() == 1) {
+      *particles = (is3d_particle *)passes[0].buf->ptr;          // the common case: one pass, already grouped by event
+    } else if (passes.empty()) {
+      is3d_ctx::HostList *hb = nullptr;
+      IS3D_TRY(acquire_host_list(ctx, sizeof(is3d_particle), &hb));
+      *particles = (is3d_particle *)hb->ptr;
+    } else {
+      // several passes (surface larger than one pass): merge the event-sorted pass lists, pass order within an event
+      is3d_ctx::HostList *hb = nullptr;
+      is3d_status st = acquire_host_list(ctx, (size_t)total * sizeof(is3d_particle), &hb);
+      if (st != IS3D_OK) { drop_passes(); return st; }
+      is3d_particle *outp = (is3d_particle *)hb->ptr;
+      std::vector<int64_t> cursor(nevents, 0);
+      int64_t acc = 0;
+      for (int64_t e = 0; e < nevents; e++) { cursor[e] = acc; acc += (int64_t)event_counts[e]; }
+      for (auto &q : passes) {
+        const is3d_particle *src = (const is3d_particle *)q.buf->ptr;
+        for (unsigned long long i = 0; i < q.n; i++) outp[cursor[src[i].event]++] = src[i];
+      }
+      drop_passes();
+      *particles = outp;
+    }
+  } else {
+    drop_passes();
   }
   if (total_out) *total_out = total;
-  if (counts) for (int64_t e = 0; e < nevents; e++) counts[e] = event_counts[e];
+  if (counts) for (int64_t e = 0; e < nevents; e++) counts[e] = (int64_t)event_counts[e];
   return IS3D_OK;
 }
 
@@ -506,7 +838,10 @@ is3d_status is3d_sample(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
   return is3d::run_sampler(ctx, nevents, particles, total, counts, stats);
 }
 
-void is3d_free_particles(is3d_particle *p) { free(p); }
+void is3d_free_particles(is3d_particle *p)
+{
+  if (p && !is3d::release_host_list((void *)p)) free(p);
+}
 
 is3d_status is3d_sample_histograms(is3d_ctx *ctx, double *dN_dy, double *dN_deta, double *dN_dphipdy, double *dN_2pipTdpTdy,
                                    double *pT_count, double *vn_real, double *vn_imag, double *dN_taudtaudy,

@@ -1,4 +1,4 @@
-// K5 / K6 math: per-cell mean yields and Monte-Carlo momentum sampling (operation 2), df_mode 1-4.
+// K5 / K6 math: per-cell mean yields and Monte-Carlo momentum sampling (operation 2), df_mode 1-5.
 // Reference: src/cpp/ParticleSampler.cpp -- estimate_mean_particle_number :75-119, fast_max_particle_number :122-161,
 // max_particle_number :164-239, sample_momentum :243-405, rescale_momentum :407-426, calculate_total_yield :447-636,
 // sample_dN_pTdpTdphidy :638-1134.
@@ -337,6 +337,15 @@ IS3D_HD bool sample_hadron(Philox &rng, PackFn pk, int df_mode, double mass, dou
     double px = iso * p.px + sm * (pk(SP_PIXX) * p.px + pk(SP_PIXY) * p.py + pk(SP_PIXZ) * p.pz) + dm * pk(SP_VX);
     double py = iso * p.py + sm * (pk(SP_PIXY) * p.px + pk(SP_PIYY) * p.py + pk(SP_PIYZ) * p.pz) + dm * pk(SP_VY);
     double pz = iso * p.pz + sm * (pk(SP_PIXZ) * p.px + pk(SP_PIYZ) * p.py + pk(SP_PIZZ) * p.pz) + dm * pk(SP_VZ);
+    p.px = px; p.py = py; p.pz = pz;
+    p.E = sqrt(mass_squared + px * px + py * py + pz * pz);
+  } else if (df_mode == 5) {
+    // PTMA (sample_dN_pTdpTdphidy_famod, ParticleSampler.cpp:1518-1531): thermal momentum at (Lambda, b upsilon_B), then
+    // p_i = B_ij p'_j (rescale_momentum_famod :428-445; the pack holds B, or the identity on breakdown); no df weight
+    p = sample_momentum(rng, samples, mass, sign, pk(SP_TSAMPLE), baryon * pk(SP_ALPHAB_SAMPLE));
+    double px = pk(SP_PIXX) * p.px + pk(SP_PIXY) * p.py + pk(SP_PIXZ) * p.pz;
+    double py = pk(SP_PIXY) * p.px + pk(SP_PIYY) * p.py + pk(SP_PIYZ) * p.pz;
+    double pz = pk(SP_PIXZ) * p.px + pk(SP_PIYZ) * p.py + pk(SP_PIZZ) * p.pz;
     p.px = px; p.py = py; p.pz = pz;
     p.E = sqrt(mass_squared + px * px + py * py + pz * pz);
   } else {   // df_mode 4

@@ -66,12 +66,13 @@ famod_setup_chain_kernel(SurfaceView surf, int64_t begin, int64_t count, FamodFl
 }  // namespace
 
 is3d_status famod_setup_pass(is3d_ctx *ctx, int64_t begin, int64_t count, double *pack, int64_t stride, unsigned long long *counters,
-                             int64_t *launches)
+                             int64_t *launches, bool sampler_rules)
 {
   const is3d_params &p = ctx->prm;
   FamodFlags fl;
   fl.dimension = p.dimension; fl.include_baryon = p.include_baryon; fl.include_shear = p.include_shear_deltaf;
   fl.include_baryondiff = p.include_baryondiff_deltaf; fl.deta_min = p.deta_min;
+  fl.sampler = sampler_rules ? 1 : 0;
   void *gl = nullptr, *chain = nullptr;
   IS3D_TRY(ctx->get_scratch("gl16", 96 * sizeof(double), &gl));
   IS3D_TRY(ctx->get_scratch("famod_chain_state", sizeof(FamodChain), &chain));

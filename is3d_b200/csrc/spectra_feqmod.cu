@@ -23,7 +23,7 @@ void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk
 // df_mode 5 per-cell stage (spectra_famod.cu): fills the same pack layout, counters[8] = reconstruction failures,
 // counters[9] = Newton iterations
 is3d_status famod_setup_pass(is3d_ctx *ctx, int64_t begin, int64_t count, double *pack, int64_t stride, unsigned long long *counters,
-                             int64_t *launches);
+                             int64_t *launches, bool sampler_rules);
 
 namespace {
 
@@ -260,7 +260,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
     int64_t count = n - begin < macro ? n - begin : macro;
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     if (p.df_mode == 5) {
-      IS3D_TRY(famod_setup_pass(ctx, begin, count, (double *)pack, stride, (unsigned long long *)counters, &launches));
+      IS3D_TRY(famod_setup_pass(ctx, begin, count, (double *)pack, stride, (unsigned long long *)counters, &launches, false));
     } else {
       feqmod_setup_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
           ctx->surf, begin, count, ctx->tb, fl, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts, (double *)pack, stride,

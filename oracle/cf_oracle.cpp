@@ -686,7 +686,8 @@ extern "C" int cf_oracle_dndx(const cf_params *p, const cf_inputs *in, double *t
 // the product) use the intended sqrt(dsx^2 + dsy^2 + dsz^2).  The term is zero without baryon diffusion.
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
-struct YieldCell { bool valid; double ds_time, ds_space, ds_max, Vdsigma, bulkPi, z, delta_z; bool breaks_yield, breaks_sample; };
+struct YieldCell { bool valid; double ds_time, ds_space, ds_max, Vdsigma, bulkPi, z, delta_z; bool breaks_yield, breaks_sample;
+                   double T, alphaB, F, G, betabulk; };
 
 YieldCell yield_cell(const cf_params *p, const cf_inputs *in, const DfData &dfd, long icell, double F_avg, double betabulk_avg, int *err)
 {
@@ -716,6 +717,7 @@ YieldCell yield_cell(const cf_params *p, const cf_inputs *in, const DfData &dfd,
   double detA = Axx * (Ayy * Azz - Ayz * Ayz) - Axy * (Axy * Azz - Ayz * Axz) + Axz * (Axy * Ayz - Ayy * Axz);
   y.valid = true; y.ds_time = dst; y.ds_space = ds_space; y.ds_max = fabs(dst) + ds_space; y.Vdsigma = Vdsigma; y.bulkPi = bulkPi;
   y.z = df.z; y.delta_z = df.delta_z;
+  y.T = c.T; y.alphaB = c.alphaB; y.F = df.F; y.G = df.G; y.betabulk = df.betabulk;
   y.breaks_yield = does_feqmod_breakdown(in, p->mass_pion0, c.T, df.F, bulkPi, df.betabulk, detA, p->deta_min, df.z, p->df_mode);
   y.breaks_sample = y.breaks_yield;
   if (p->df_mode == 3 && p->fast)   // does_feqmod_breakdown(..., FAST, Tavg, F_avg, betabulk_avg), ParticleSampler.cpp:874
@@ -726,7 +728,7 @@ YieldCell yield_cell(const cf_params *p, const cf_inputs *in, const DfData &dfd,
 
 extern "C" int cf_oracle_total_yield(const cf_params *p, const cf_inputs *in, double *ntotal)
 {
-  if (p->df_mode < 1 || p->df_mode > 4) return 4;
+  if (p->df_mode < 1 || p->df_mode > 5) return 4;      // df_mode 5 takes the Chapman-Enskog estimate (:105-110)
   DfData dfd(p, in);
   double Ntot = 0;
   int err = 0;
@@ -745,18 +747,22 @@ extern "C" int cf_oracle_total_yield(const cf_params *p, const cf_inputs *in, do
   return 0;
 }
 
-// dn_tot[cell] (after the 2 y_max ds_max volume factor) and dn_list[cell][species] (before it); fast mode only
+// dn_tot[cell] (after the 2 y_max ds_max volume factor) and dn_list[cell][species] (before it), df_mode 1-4:
+// fast = 1 fast_max_particle_number (ParticleSampler.cpp:122-161), fast = 0 max_particle_number (:164-239)
 extern "C" int cf_oracle_cell_yields(const cf_params *p, const cf_inputs *in, double *dn_tot, double *dn_list)
 {
-  if (p->df_mode < 1 || p->df_mode > 4 || !p->fast) return 4;
+  if (p->df_mode < 1 || p->df_mode > 4) return 4;
   DfData dfd(p, in);
   double F_avg = 0.0, betabulk_avg = 1.0;
-  if (p->df_mode == 3) {
+  if (p->df_mode == 3 && p->fast) {
     DfCoeff d;
     if (!dfd.evaluate(in->T_avg, in->muB_avg, 0.0, 0.0, 0.0, &d)) return 3;
     F_avg = d.F; betabulk_avg = d.betabulk;
   }
   double y_max = (p->dimension == 2) ? p->y_cut : 0.5;
+  const int pts = in->n_gla;
+  const double *r1 = in->gla_root + 1 * pts, *w1 = in->gla_weight + 1 * pts;
+  const double *r2 = in->gla_root + 2 * pts, *w2 = in->gla_weight + 2 * pts;
   int err = 0;
   for (long icell = 0; icell < in->n_cells; icell++) {
     YieldCell y = yield_cell(p, in, dfd, icell, F_avg, betabulk_avg, &err);
@@ -764,11 +770,28 @@ extern "C" int cf_oracle_cell_yields(const cf_params *p, const cf_inputs *in, do
     double tot = 0.0;
     for (int s = 0; s < in->n_species; s++) {
       double v = 0.0;
-      if (y.valid) {                             // fast_max_particle_number
+      if (y.valid && p->fast) {                  // fast_max_particle_number
         double neq = in->equilibrium_density[s], bd = in->bulk_density[s];
         if (p->df_mode <= 2 || y.breaks_sample) v = 2.0 * neq;
         else if (p->df_mode == 3) v = neq + y.bulkPi * bd;
         else v = y.z * neq;
+      } else if (y.valid) {                      // max_particle_number at the cell's own (T, alphaB)
+        double T = y.T, mbar = in->mass[s] / T, degeneracy = in->degeneracy[s], sign = in->sign[s], baryon = in->baryon[s];
+        double neq_fact = T * T * T / two_pi2_hbarC3, J20_fact = T * neq_fact;
+        if (p->df_mode <= 2 || y.breaks_sample) {
+          double equilibrium_density = neq_fact * degeneracy * GaussThermal(neq_int, r1, w1, pts, mbar, y.alphaB, baryon, sign);
+          v = 2.0 * equilibrium_density;
+        } else if (p->df_mode == 3) {
+          double equilibrium_density = neq_fact * degeneracy * GaussThermal(neq_int, r1, w1, pts, mbar, y.alphaB, baryon, sign);
+          double J10 = 0.0;
+          if (p->include_baryon) J10 = neq_fact * degeneracy * GaussThermal(J10_int, r1, w1, pts, mbar, y.alphaB, baryon, sign);
+          double J20 = J20_fact * degeneracy * GaussThermal(J20_int, r2, w2, pts, mbar, y.alphaB, baryon, sign);
+          double bulk_density = (equilibrium_density + (baryon * J10 * y.G) + (J20 * y.F / T / T)) / y.betabulk;
+          v = equilibrium_density + y.bulkPi * bulk_density;
+        } else {
+          double equilibrium_density = neq_fact * degeneracy * GaussThermal(neq_int, r1, w1, pts, mbar, 0.0, 0.0, sign);
+          v = y.z * equilibrium_density;
+        }
       }
       if (dn_list) dn_list[(size_t)icell * in->n_species + s] = v;
       tot += v;

@@ -101,4 +101,14 @@ SAMPLER_CASES = {
     "smp_s3d_m4": dict(surface=("s3d", dict(n=300, seed=44, stress=0.3)), params=_p(df_mode=4, **_S), chosen="pikp"),
     "smp_s2d_m3": dict(surface=("s3d", dict(n=200, seed=45, dimension=2, stress=0.2)), params=_p(df_mode=3, dimension=2, hrg_eos=1, **_S), chosen="pikp"),
     "smp_s3d_m2_smash": dict(surface=("s3d", dict(n=200, seed=46)), params=_p(df_mode=2, **_S), chosen="smash"),
+    # fast = 0: species densities from the cell's own (T, muB) by 32-point Gauss-Laguerre sums (max_particle_number)
+    "smp_s3d_m2_slow": dict(surface=("s3d", dict(n=300, seed=47)), params=_p(df_mode=2, **dict(_S, fast=0)), chosen="pikp"),
+    "smp_s3d_m3_slow": dict(surface=("s3d", dict(n=300, seed=48, stress=0.3)), params=_p(df_mode=3, **dict(_S, fast=0)), chosen="pikp"),
+    "smp_s3d_m4_slow_smash": dict(surface=("s3d", dict(n=200, seed=49, stress=0.3)), params=_p(df_mode=4, **dict(_S, fast=0)), chosen="smash"),
+    "smp_s3d_m3_slow_baryon": dict(surface=("s3d", dict(n=300, seed=50, baryon=True, stress=0.3)),
+                                   params=_p(df_mode=3, include_baryon=1, include_baryondiff_deltaf=1, **dict(_S, fast=0)), chosen="pikp"),
+    # df_mode 5 (PTMA): sample_dN_pTdpTdphidy_famod
+    "smp_vah_m5": dict(surface=("s3d", dict(n=300, seed=57, vah=True)), params=_p(df_mode=5, **_S), chosen="pikp"),
+    "smp_s3d_m5_stress": dict(surface=("s3d", dict(n=300, seed=58, stress=0.3)), params=_p(df_mode=5, **_S), chosen="pikp"),
+    "smp_s2d_m5": dict(surface=("s3d", dict(n=200, seed=59, dimension=2, vah=True)), params=_p(df_mode=5, dimension=2, hrg_eos=1, **_S), chosen="pikp"),
 }
