@@ -36,12 +36,15 @@ NS_SMASH, NPT, NPHI, NY = 444, 51, 1, 21
 
 
 def bench_params(df_mode: int) -> dict:
-    return dict(operation=1, mode=1, hrg_eos=2, dimension=3, df_mode=df_mode, include_baryon=1,
-                include_bulk_deltaf=1, include_shear_deltaf=1, include_baryondiff_deltaf=1, regulate_deltaf=0, outflow=0)
+    # PTB (df_mode 4) has no muB != 0 coefficient tables (reference DeltafData.cpp:480-484)
+    b = 0 if df_mode == 4 else 1
+    return dict(operation=1, mode=1, hrg_eos=2, dimension=3, df_mode=df_mode, include_baryon=b,
+                include_bulk_deltaf=1, include_shear_deltaf=1, include_baryondiff_deltaf=b, regulate_deltaf=0, outflow=0)
 
 
 def workload_name(df_mode: int, cells: int, n_gpus: int) -> str:
-    return (f"continuous spectra, all SMASH species (444), df_mode={df_mode} with bulk+shear+baryon diffusion, "
+    terms = "bulk+shear" if df_mode == 4 else "bulk+shear+baryon diffusion"
+    return (f"continuous spectra, all SMASH species (444), df_mode={df_mode} with {terms}, "
             f"51pT x 1phi x 21y, synthetic 3+1D surface S-3D, {cells} cells per GPU x {n_gpus} GPU")
 
 
@@ -248,6 +251,7 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py: no CUDA device; this repository has no CPU compute path")
     torch.cuda.set_device(local)
     os.environ["IS3D_DEVICE"] = str(local)
+    os.environ.setdefault("IS3D_FAMOD_CHAIN", "0")          # df_mode 5: chain-free (shardable) initial guesses
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -308,17 +312,27 @@ def run_ours(args) -> None:
         ms_total = float(t.item())
 
         # ---- end to end through the C ABI with HOST buffers: H2D of the 25 columns + compute + D2H of the spectra ----
+        # N = 1: is3d_set_surface + is3d_spectra (host in, host out).  N > 1: is3d_set_surface + is3d_spectra_device,
+        # one NCCL all-reduce of the device array, D2H into pinned memory -- the sequence INTEGRATION.md prescribes.
         host_np = {k: t_.numpy() for k, t_ in host_cols.items()}
-        e2e_steps = max(1, min(args.steps, 2))
+        out_host = torch.empty(total, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            h.abi_set_surface(host_np, global_offset=rank * cells)
+            if world > 1:
+                h.abi_spectra_device(out_dev.data_ptr())
+                dist.all_reduce(out_dev)
+                out_host.copy_(out_dev, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return out_host.numpy()
+            return h.abi_spectra()[0]
+
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_step()                                                       # untimed: first-use allocations
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            h.abi_set_surface(host_np, global_offset=rank * cells)
-            spec, _ = h.abi_spectra()
-            if world > 1:
-                tmp = torch.from_numpy(spec.reshape(-1)).cuda()
-                dist.all_reduce(tmp)
-                spec = tmp.cpu().numpy()
+            spec = e2e_step()
         barrier()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -350,7 +364,7 @@ def run_ours(args) -> None:
                     "d2h_bytes_per_step": int(total * 8)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": None, "kernel": "df_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
+                         "traffic": None, "kernel": "df_spectra_kernel" if args.df_mode <= 2 else "feqmod_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
                          "flops_per_eval_algorithmic": F_ALG[args.df_mode],
                          "peak_source": "DFMA micro-benchmark run live by is3d_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
                          "hbm_gbs_algorithmic": bytes_alg / kern_s / 1e9, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
@@ -376,7 +390,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells-per-gpu", type=int, default=1_250_000)
-    ap.add_argument("--df-mode", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--df-mode", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="2 = the headline workload; 1, 3, 4, 5 time the other df corrections on the same surface")
     ap.add_argument("--ref-cells", type=int, default=2000, help="cells of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampler", action="store_true", help="skip the sampler (hadrons/s) section")
