@@ -40,27 +40,87 @@ struct AnisoHadrons {
   const double *mass, *sign, *deg;
   int n;                                   // min(320, N_pdg)
   const double *gl16;                      // fill_gl16_table layout
+  const double *exptab;                    // 2^(m/1024) table of fast_exp (shared memory on the device)
+  int exact;                               // 1: the reference's own formulas with libm atan / exp / sqrt and true divisions
+                                           // (parity mode, see aniso_t_functions); 0: FP64-pipe approximations
 };
+
+// sqrt(a) and 1/sqrt(a) for a > 0 from one hardware seed + one coupled Goldschmidt step + residual fix (see fast_sqrt)
+IS3D_HD void fast_sqrt_rsqrt(double a, double *root, double *iroot)
+{
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  double d = fma(-g, g, a);
+  g = fma(d, h, g);                        // sqrt(a)
+  r = fma(-h, g, 0.5);
+  h = fma(h, r, h);
+  *root = g; *iroot = 2.0 * h;
+#else
+  *root = sqrt(a); *iroot = 1.0 / *root;
+#endif
+}
+
+// atan(s), s >= 0: three-range reduction to |x| <= 0.66 (selects, no divergent branches) and the degree-4 / degree-5
+// rational x + x z P(z)/Q(z) (Cephes atan.c coefficients, public domain; tools/gen_atan.py: max relative error 2e-16)
+IS3D_HD double fast_atan(double s)
+{
+#if defined(__CUDA_ARCH__)
+  const bool big = s > 2.414213562373095, mid = s > 0.66;
+  const double num = big ? -1.0 : (mid ? s - 1.0 : s), den = big ? s : (mid ? s + 1.0 : 1.0);
+  const double y0 = big ? 1.5707963267948966 : (mid ? 0.7853981633974483 : 0.0);
+  const double more = big ? 6.123233995736765886130e-17 : (mid ? 3.061616997868382943065e-17 : 0.0);
+  const double x = num * fast_rcp(den), z = x * x;
+  double pn = fma(-8.750608600031904122785e-1, z, -1.615753718733365076637e1);
+  pn = fma(pn, z, -7.500855792314704667340e1); pn = fma(pn, z, -1.228866684490136173410e2); pn = fma(pn, z, -6.485021904942025371773e1);
+  double qn = z + 2.485846490142306297962e1;
+  qn = fma(qn, z, 1.650270098316988542046e2); qn = fma(qn, z, 4.328810604912902668951e2); qn = fma(qn, z, 4.853903996359136964868e2);
+  qn = fma(qn, z, 1.945506571482613964425e2);
+  const double r = fma(x * z, pn * fast_rcp(qn), x) + more;
+  return y0 + r;
+#else
+  return atan(s);
+#endif
+}
 
 // hypergeometric-type angular functions of z = (aT^2 - aL^2) / w^2 (closed forms for |z| > delta, series inside)
 struct AnisoT { double t200, t220, t201, t402, t421, t440; };
 
-IS3D_HD AnisoT aniso_t_functions(double z, bool need_j)
+// The closed forms cancel catastrophically towards z -> delta (t402, t421, t440 lose a factor ~3/z^2 = 3e4 at z = 0.01),
+// so the reference's result carries the rounding of ITS atan to the 1e-11 level; bit-level agreement with it needs the same
+// libm call and the same division order (exact = true, used by the chain-faithful parity mode).
+IS3D_HD AnisoT aniso_t_functions(double z, bool need_j, bool exact)
 {
   AnisoT r;
   r.t200 = r.t220 = r.t201 = r.t402 = r.t421 = r.t440 = 0.0;     // reference leaves them unset when z <= -1
   if (z > kAnisoDelta || (z < -kAnisoDelta && z > -1.)) {
-    double t;
-    if (z > 0.0) { double s = sqrt(z); t = atan(s) / s; }
-    else { double s = sqrt(-z); t = atanh(s) / s; }
+    double t, iz;
+    if (z > 0.0 && !exact) { double s, is; fast_sqrt_rsqrt(z, &s, &is); t = fast_atan(s) * is; iz = is * is; }
+    else if (z > 0.0) { double s = sqrt(z); t = atan(s) / s; iz = 1.0 / z; }
+    else { double s = sqrt(-z); t = atanh(s) / s; iz = 1.0 / z; }
+    if (exact) {             // AnisoVariables.cpp:72-89, :206-231 verbatim (divisions, not reciprocal multiplies)
+      r.t200 = 1. + (1. + z) * t;
+      r.t220 = (-1. + (1. + z) * t) / z;
+      r.t201 = (1. + (z - 1.) * t) / z;
+      if (need_j) {
+        double z2 = z * z;
+        r.t402 = (3. * (z - 1.) + (z * (3. * z - 2.) + 3.) * t) / (4. * z2);
+        r.t421 = (3. + z + (1. + z) * (z - 3.) * t) / (4. * z2);
+        r.t440 = (-(3. + 5. * z) + 3. * (z + 1.) * (z + 1.) * t) / (4. * z2);
+      }
+      return r;
+    }
     r.t200 = 1. + (1. + z) * t;
-    r.t220 = (-1. + (1. + z) * t) / z;
-    r.t201 = (1. + (z - 1.) * t) / z;
+    r.t220 = (-1. + (1. + z) * t) * iz;
+    r.t201 = (1. + (z - 1.) * t) * iz;
     if (need_j) {
-      double z2 = z * z;
-      r.t402 = (3. * (z - 1.) + (z * (3. * z - 2.) + 3.) * t) / (4. * z2);
-      r.t421 = (3. + z + (1. + z) * (z - 3.) * t) / (4. * z2);
-      r.t440 = (-(3. + 5. * z) + 3. * (z + 1.) * (z + 1.) * t) / (4. * z2);
+      double iz2 = 0.25 * iz * iz;
+      r.t402 = (3. * (z - 1.) + (z * (3. * z - 2.) + 3.) * t) * iz2;
+      r.t421 = (3. + z + (1. + z) * (z - 3.) * t) * iz2;
+      r.t440 = (-(3. + 5. * z) + 3. * (z + 1.) * (z + 1.) * t) * iz2;
     }
   } else if (fabs(z) <= kAnisoDelta) {
     double z2 = z * z, z3 = z2 * z, z4 = z3 * z, z5 = z4 * z, z6 = z5 * z;
@@ -76,71 +136,143 @@ IS3D_HD AnisoT aniso_t_functions(double z, bool need_j)
   return r;
 }
 
-// one (hadron, node) term of compute_F (:36-107): out = {I_200, I_220, I_201} before the common factors
-IS3D_HD void aniso_F_term(const AnisoHadrons &h, int idx, double lambda, double aT2, double aL2, double out[3])
+// per-node constants: everything in a term that depends on the quadrature node alone (a lane of the device reducer
+// keeps ONE node for the whole sum: 32 lanes = 2 hadrons x 16 nodes per step)
+struct AnisoNode { double pbar, pbar2, ipbar2, cF, wJ; };   // cF = pbar w e^pbar (F terms) or w e^pbar (J terms); wJ = w
+
+IS3D_HD AnisoNode aniso_node_F(const AnisoHadrons &h, int i)
 {
-  const int n = idx / kAnisoPts, i = idx - n * kAnisoPts;
+  const double pbar = h.gl16[32 + i], weight = h.gl16[48 + i];
+  return AnisoNode{pbar, pbar * pbar, 1.0 / (pbar * pbar), pbar * weight * exp(pbar), weight};
+}
+IS3D_HD AnisoNode aniso_node_J(const AnisoHadrons &h, int i)
+{
+  const double pbar = h.gl16[64 + i], weight = h.gl16[80 + i];
+  return AnisoNode{pbar, pbar * pbar, 1.0 / (pbar * pbar), weight * exp(pbar), weight};
+}
+
+// one (hadron, node) term of compute_F (:36-107): out = {I_200, I_220, I_201} before the common factors
+IS3D_HD void aniso_F_term(const AnisoHadrons &h, int n, const AnisoNode &nd, double lambda, double ilambda, double aT2, double aL2,
+                          double out[3])
+{
   const double mass = h.mass[n];
   if (mass == 0) return;                   // photons skipped
-  const double mbar = mass / lambda, mbar2 = mbar * mbar;
-  const double pbar = h.gl16[32 + i], weight = h.gl16[48 + i];
-  const double Ebar = sqrt(pbar * pbar + mbar2);
-  const double w = sqrt(aL2 + mbar2 / (pbar * pbar));
-  const double z = (aT2 - aL2) / (w * w);
-  const AnisoT t = aniso_t_functions(z, false);
-  const double cw = h.deg[n] * (pbar * weight * exp(pbar) / (exp(Ebar) + h.sign[n]));
+  if (h.exact) {                           // reference expression order
+    const double mbar = mass / lambda, mbar2 = mbar * mbar;
+    const double Ebar = sqrt(nd.pbar2 + mbar2);
+    const double w = sqrt(aL2 + mbar2 / nd.pbar2);
+    const double z = (aT2 - aL2) / (w * w);
+    const AnisoT t = aniso_t_functions(z, false, true);
+    const double cw = h.deg[n] * (nd.cF / (exp(Ebar) + h.sign[n]));
+    out[0] += cw * t.t200 * w;
+    out[1] += cw * t.t220 / w;
+    out[2] += cw * t.t201 / w;
+    return;
+  }
+  const double mbar = mass * ilambda, mbar2 = mbar * mbar;
+  const double Ebar = fast_sqrt(nd.pbar2 + mbar2);
+  double w, iw;
+  fast_sqrt_rsqrt(fma(mbar2, nd.ipbar2, aL2), &w, &iw);
+  const double z = (aT2 - aL2) * (iw * iw);
+  const AnisoT t = aniso_t_functions(z, false, false);
+  const double cw = h.deg[n] * (nd.cF * fast_rcp(fast_exp(Ebar, h.exptab) + h.sign[n]));
   out[0] += cw * t.t200 * w;
-  out[1] += cw * t.t220 / w;
-  out[2] += cw * t.t201 / w;
+  out[1] += cw * t.t220 * iw;
+  out[2] += cw * t.t201 * iw;
 }
 
 // one term of compute_J (:175-258) / compute_famod_coefficient (:573-627): out = {J_2001, J_2011, J_2201, J_402m1, J_421m1, J_440m1}
-IS3D_HD void aniso_J_term(const AnisoHadrons &h, int idx, double lambda, double aT2, double aL2, double out[6])
+IS3D_HD void aniso_J_term(const AnisoHadrons &h, int n, const AnisoNode &nd, double lambda, double ilambda, double aT2, double aL2,
+                          double out[6])
 {
-  const int n = idx / kAnisoPts, i = idx - n * kAnisoPts;
   const double mass = h.mass[n];
   if (mass == 0) return;
-  const double mbar = mass / lambda, mbar2 = mbar * mbar;
-  const double pbar = h.gl16[64 + i], weight = h.gl16[80 + i], pbar2 = pbar * pbar;
-  const double Ebar = sqrt(pbar2 + mbar2);
-  const double w = sqrt(aL2 + mbar2 / pbar2);
-  const double z = (aT2 - aL2) / (w * w);
-  const AnisoT t = aniso_t_functions(z, true);
-  const double q = exp(Ebar) + h.sign[n];
-  const double cw = h.deg[n] * (weight * exp(pbar + Ebar) / (q * q));
-  out[0] += Ebar * cw * t.t200 * w;
-  out[1] += Ebar * cw * t.t201 / w;
-  out[2] += Ebar * cw * t.t220 / w;
-  out[3] += pbar2 / Ebar * cw * t.t402 / w;
-  out[4] += pbar2 / Ebar * cw * t.t421 / w;
-  out[5] += pbar2 / Ebar * cw * t.t440 / w;
+  if (h.exact) {
+    const double mbar = mass / lambda, mbar2 = mbar * mbar;
+    const double Ebar = sqrt(nd.pbar2 + mbar2);
+    const double w = sqrt(aL2 + mbar2 / nd.pbar2);
+    const double z = (aT2 - aL2) / (w * w);
+    const AnisoT t = aniso_t_functions(z, true, true);
+    const double q = exp(Ebar) + h.sign[n];
+    const double cw = h.deg[n] * (nd.wJ * exp(nd.pbar + Ebar) / (q * q));
+    out[0] += Ebar * cw * t.t200 * w;
+    out[1] += Ebar * cw * t.t201 / w;
+    out[2] += Ebar * cw * t.t220 / w;
+    out[3] += nd.pbar2 / Ebar * cw * t.t402 / w;
+    out[4] += nd.pbar2 / Ebar * cw * t.t421 / w;
+    out[5] += nd.pbar2 / Ebar * cw * t.t440 / w;
+    return;
+  }
+  const double mbar = mass * ilambda, mbar2 = mbar * mbar;
+  double Ebar, iEbar, w, iw;
+  fast_sqrt_rsqrt(nd.pbar2 + mbar2, &Ebar, &iEbar);
+  fast_sqrt_rsqrt(fma(mbar2, nd.ipbar2, aL2), &w, &iw);
+  const double z = (aT2 - aL2) * (iw * iw);
+  const AnisoT t = aniso_t_functions(z, true, false);
+  const double e = fast_exp(Ebar, h.exptab), iq = fast_rcp(e + h.sign[n]);
+  const double cw = h.deg[n] * (nd.cF * e * iq * iq);           // e^(pbar + Ebar) / (e^Ebar + sign)^2
+  const double ecw = Ebar * cw, pcw = nd.pbar2 * iEbar * cw * iw;
+  out[0] += ecw * t.t200 * w;
+  out[1] += ecw * t.t201 * iw;
+  out[2] += ecw * t.t220 * iw;
+  out[3] += pcw * t.t402;
+  out[4] += pcw * t.t421;
+  out[5] += pcw * t.t440;
 }
 
-// serial reducer (host / single thread)
+// serial reducer (host / single thread): hadron-major, node-minor like the reference's loops
 struct SerialReducer {
-  template <int K, class Fn>
-  IS3D_HD void sum(int nterms, Fn fn, double out[K]) const
+  IS3D_HD void sum_F(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[3]) const
   {
-    for (int k = 0; k < K; k++) out[k] = 0.0;
-    for (int idx = 0; idx < nterms; idx++) fn(idx, out);
+    for (int k = 0; k < 3; k++) out[k] = 0.0;
+    const double il = 1.0 / lambda;
+    for (int n = 0; n < h.n; n++)
+      for (int i = 0; i < kAnisoPts; i++) aniso_F_term(h, n, aniso_node_F(h, i), lambda, il, aT2, aL2, out);
+  }
+  IS3D_HD void sum_J(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[6]) const
+  {
+    for (int k = 0; k < 6; k++) out[k] = 0.0;
+    const double il = 1.0 / lambda;
+    for (int n = 0; n < h.n; n++)
+      for (int i = 0; i < kAnisoPts; i++) aniso_J_term(h, n, aniso_node_J(h, i), lambda, il, aT2, aL2, out);
   }
 };
 
 #if defined(__CUDACC__)
-// one warp: lane-strided partial sums, butterfly reduction -> every lane holds the same total
-struct WarpReducer {
-  template <int K, class Fn>
-  __device__ void sum(int nterms, Fn fn, double out[K]) const
-  {
-    const int lane = threadIdx.x & 31;
-    for (int k = 0; k < K; k++) out[k] = 0.0;
-    for (int idx = lane; idx < nterms; idx += 32) fn(idx, out);
+// one warp: lane = (hadron parity, node); partial sums over every second hadron, butterfly reduction -> every lane
+// holds the same total.  Not inlined: the Newton / line-search driver calls these from five places, and five inlined
+// copies of the term loops overflow the instruction cache (ncu: "no instruction" was the top stall).
+static __device__ __noinline__ void aniso_warp_sum_F(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[3])
+{
+  const int lane = threadIdx.x & 31;
+  const AnisoNode nd = aniso_node_F(h, lane & 15);
+  const double il = 1.0 / lambda;
+  double o[3] = {0.0, 0.0, 0.0};
+  for (int n = lane >> 4; n < h.n; n += 2) aniso_F_term(h, n, nd, lambda, il, aT2, aL2, o);
 #pragma unroll
-    for (int k = 0; k < K; k++) {
+  for (int k = 0; k < 3; k++) {
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) out[k] += __shfl_xor_sync(0xffffffffu, out[k], off);
-    }
+    for (int off = 16; off > 0; off >>= 1) o[k] += __shfl_xor_sync(0xffffffffu, o[k], off);
+    out[k] = o[k];
   }
+}
+static __device__ __noinline__ void aniso_warp_sum_J(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[6])
+{
+  const int lane = threadIdx.x & 31;
+  const AnisoNode nd = aniso_node_J(h, lane & 15);
+  const double il = 1.0 / lambda;
+  double o[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int n = lane >> 4; n < h.n; n += 2) aniso_J_term(h, n, nd, lambda, il, aT2, aL2, o);
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) o[k] += __shfl_xor_sync(0xffffffffu, o[k], off);
+    out[k] = o[k];
+  }
+}
+struct WarpReducer {
+  __device__ void sum_F(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[3]) const { aniso_warp_sum_F(h, lambda, aT2, aL2, out); }
+  __device__ void sum_J(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[6]) const { aniso_warp_sum_J(h, lambda, aT2, aL2, out); }
 };
 #endif
 
@@ -150,7 +282,7 @@ IS3D_HD void aniso_compute_F(const Reducer &red, const AnisoHadrons &h, double E
   const double lambda = X[0], aT2 = X[1] * X[1], aL2 = X[2] * X[2], aL = X[2];
   const double common_factor = aT2 * aL * lambda * lambda * lambda * lambda / kFourPi2HbarC3;
   double I[3];
-  red.template sum<3>(h.n * kAnisoPts, [&](int idx, double *o) { aniso_F_term(h, idx, lambda, aT2, aL2, o); }, I);
+  red.sum_F(h, lambda, aT2, aL2, I);
   F[0] = I[0] * common_factor - Ea;                       // I_200 - E
   F[1] = I[2] * (common_factor * aT2 / 2.) - PTa;          // I_201 - PT
   F[2] = I[1] * (common_factor * aL2) - PLa;               // I_220 - PL
@@ -165,7 +297,7 @@ IS3D_HD void aniso_compute_J(const Reducer &red, const AnisoHadrons &h, double E
   const double lambda_aT3 = lambda * aT2 * aT, lambda_aL3 = lambda * aL2 * aL;
   const double common_factor = aT2 * aL * lambda2 * lambda3 / kFourPi2HbarC3;
   double S[6];
-  red.template sum<6>(h.n * kAnisoPts, [&](int idx, double *o) { aniso_J_term(h, idx, lambda, aT2, aL2, o); }, S);
+  red.sum_J(h, lambda, aT2, aL2, S);
   const double J_2001 = S[0] * common_factor, J_2011 = S[1] * (common_factor * aT2 / 2.), J_2201 = S[2] * (common_factor * aL2);
   const double J_402m1 = S[3] * (common_factor * aT2 * aT2 / 8.), J_421m1 = S[4] * (common_factor * aT2 * aL2 / 2.);
   const double J_440m1 = S[5] * (common_factor * aL2 * aL2);
@@ -284,7 +416,7 @@ IS3D_HD void aniso_famod_coefficient(const Reducer &red, const AnisoHadrons &h, 
   const double lambda2 = lambda * lambda, aT2 = aT * aT, aL2 = aL * aL;
   const double common_factor = aT2 * aL * lambda * lambda2 * lambda2 / kFourPi2HbarC3;
   double S[6];
-  red.template sum<6>(h.n * kAnisoPts, [&](int idx, double *o) { aniso_J_term(h, idx, lambda, aT2, aL2, o); }, S);
+  red.sum_J(h, lambda, aT2, aL2, S);
   const double J_402m1 = S[3] * (common_factor * aT2 * aT2 / 8.), J_421m1 = S[4] * (common_factor * aT2 * aL2 / 2.);
   *betapiperp = J_402m1 / (aT2 * lambda);
   *betaWperp = J_421m1 / (aT * aL * lambda);

@@ -270,7 +270,6 @@ static is3d_status set_surface_impl(is3d_ctx *ctx, int64_t n, const double *cons
   const int ncol = ctx->prm.include_baryon ? 25 : 20;
   for (int k = 0; k < ncol; k++)
     if (!cols[k] && n > 0) { ctx->set_error("set_surface: NULL column " + std::to_string(k)); return IS3D_ERR_INVALID; }
-  if (ctx->surface_owned && ctx->d_surface_block) { ctx->dev_free(ctx->d_surface_block); ctx->d_surface_block = nullptr; }
   ctx->surface_owned = false;
   for (int k = 0; k < 25; k++) ctx->surf.col[k] = nullptr;
   ctx->surf.n = n;
@@ -279,10 +278,16 @@ static is3d_status set_surface_impl(is3d_ctx *ctx, int64_t n, const double *cons
     for (int k = 0; k < ncol; k++) ctx->surf.col[k] = cols[k];
   } else {
     // one block, columns padded to 256 B so every column start is aligned for vector loads
+    // the block is grow-only: cudaFree of a large allocation synchronises the device and can take hundreds of ms
     int64_t pitch = (n + 31) / 32 * 32;
-    void *blk = nullptr;
-    IS3D_TRY(ctx->dev_alloc(&blk, (size_t)ncol * pitch * sizeof(double)));
-    ctx->d_surface_block = (double *)blk;
+    const size_t need = (size_t)ncol * pitch * sizeof(double);
+    if (!ctx->d_surface_block || ctx->surface_block_bytes < need) {
+      if (ctx->d_surface_block) { ctx->dev_free(ctx->d_surface_block); ctx->d_surface_block = nullptr; ctx->surface_block_bytes = 0; }
+      void *blk = nullptr;
+      IS3D_TRY(ctx->dev_alloc(&blk, need));
+      ctx->d_surface_block = (double *)blk;
+      ctx->surface_block_bytes = need;
+    }
     ctx->surface_owned = true;
     for (int k = 0; k < ncol; k++) {
       double *dst = ctx->d_surface_block + (size_t)k * pitch;

@@ -72,7 +72,11 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
   double q = fma(r, 1.6666666666666666e-01, 0.5);
   q = fma(q, r, 1.0);
   q = q * r;                                         // r + r^2/2 + r^3/6
+#if defined(IS3D_PROBE_UNIFORM_EXP_TABLE)       // timing probe only (wrong results): every lane reads entry 0, no bank conflicts
+  const double T = tab[k & 0];
+#else
   const double T = tab[k & (kExpTableSize - 1)];
+#endif
   const double v = fma(T, q, T);
   double res = as_double(as_int64(v) + ((int64_t)(k >> kExpTableBits) << 52));
   const int hx = hi_word(x);

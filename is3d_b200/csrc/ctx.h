@@ -77,7 +77,8 @@ struct is3d_ctx {
   bool have_surface = false;
   bool surface_owned = false;
   int64_t global_offset = 0;
-  double *d_surface_block = nullptr;       // one allocation holding all owned columns
+  double *d_surface_block = nullptr;       // one (grow-only) allocation holding all owned columns
+  size_t surface_block_bytes = 0;
 
   // sampler histograms (device)
   std::map<std::string, double *> hist;

@@ -35,6 +35,10 @@ __global__ void __launch_bounds__(128)
 famod_setup_free_kernel(SurfaceView surf, int64_t begin, int64_t count, FamodFlags fl, AnisoHadrons h, double *__restrict__ pack,
                         int64_t stride, unsigned long long *counters)
 {
+  __shared__ double exptab[kExpTableSize];
+  load_exp_table(exptab, h.exptab);
+  __syncthreads();
+  h.exptab = exptab;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   WarpReducer red;
@@ -51,6 +55,10 @@ __global__ void __launch_bounds__(32)
 famod_setup_chain_kernel(SurfaceView surf, int64_t begin, int64_t count, FamodFlags fl, AnisoHadrons h, double *__restrict__ pack,
                          int64_t stride, unsigned long long *counters, FamodChain *chain_state)
 {
+  __shared__ double exptab[kExpTableSize];
+  load_exp_table(exptab, h.exptab);
+  __syncthreads();
+  h.exptab = exptab;
   WarpReducer red;
   FamodChain chain = *chain_state;          // carried across passes
   for (int64_t i = 0; i < count; i++) {
@@ -87,6 +95,8 @@ is3d_status famod_setup_pass(is3d_ctx *ctx, int64_t begin, int64_t count, double
   h.mass = ctx->d_pdg_mass; h.sign = ctx->d_pdg_sign; h.deg = ctx->d_pdg_deg;
   h.n = ctx->npdg < kAnisoMaxHadrons ? ctx->npdg : kAnisoMaxHadrons;
   h.gl16 = (const double *)gl;
+  h.exptab = ctx->d_exptab;
+  h.exact = p.famod_chain ? 1 : 0;          // the chain-faithful parity mode also keeps the reference's libm formulas
   if (p.famod_chain) {
     famod_setup_chain_kernel<<<1, 32, 0, ctx->stream>>>(ctx->surf, begin, count, fl, h, pack, stride, counters, (FamodChain *)chain);
   } else {

@@ -316,7 +316,7 @@ extern "C" long hostcheck_spectra_famod(const char *root, int chain_on, double *
   for (auto &p : L.pdg) { pm.push_back(p.mass); ps.push_back(p.sign); pd.push_back(p.gspin); }
   double gl16[96];
   is3d::fill_gl16_table(gl16);
-  is3d::AnisoHadrons h{pm.data(), ps.data(), pd.data(), (int)std::min<size_t>(320, pm.size()), gl16};
+  is3d::AnisoHadrons h{pm.data(), ps.data(), pd.data(), (int)std::min<size_t>(320, pm.size()), gl16, exp_table(), 1};
   is3d::SurfaceView sv;
   for (int k = 0; k < 25; k++) sv.col[k] = L.surf.col[k].data();
   sv.n = L.surf.size();

@@ -78,7 +78,7 @@ def _df_table(path, include_baryon):
 class OracleProblem:
     """Everything cf_oracle needs, loaded with numpy from a working directory (tables) and the host layer (PDG)."""
 
-    def __init__(self, root: str, params: dict, surface: dict, after_surface=None):
+    def __init__(self, root: str, params: dict, surface: dict, after_surface=None, famod_chain: int = 1):
         """after_surface(session): optional hook between set_surface and the table stage (sharded runs install the
         whole-surface thermodynamic averages there)."""
         full = workdir.default_parameters()
@@ -87,7 +87,7 @@ class OracleProblem:
         self.p = CfParams()
         for name, _ in CfParams._fields_:
             if name == "famod_chain":
-                self.p.famod_chain = 1
+                self.p.famod_chain = famod_chain
             elif name in ("deta_min", "mass_pion0", "y_cut", "tau_min", "tau_max", "r_min", "r_max"):
                 setattr(self.p, name, g(name))
             else:

@@ -26,6 +26,32 @@ def test_spectra_df_matches_reference(libs, tmp_path, name):
     print(f"{name}: max rel err {worst:.3e}")
 
 
+M5_CASES = [n for n, c in cases.SPECTRA_CASES.items() if c["params"]["df_mode"] == 5 and c["chosen"] == "pikp"]
+
+
+@pytest.mark.parametrize("name", M5_CASES)
+def test_famod_chain_free_fast_path_matches_oracle(libs, tmp_path, monkeypatch, name):
+    """df_mode 5 production mode (famod_chain = 0): every cell's Newton solve starts from (T, 1, 1) and the term sums use
+    the FP64-pipe approximations (fast_exp / fast_atan / rcp / rsqrt).  Checked against the CPU oracle run with the same
+    chain-free policy.  The closed-form angular functions cancel by up to 3e4 near z = 0.01, so two correct evaluations
+    with different 1-ulp roundings of atan differ at the 1e-11 level; the tolerance here is 5e-10 and the observed worst
+    case is printed (profiles/ records it)."""
+    import oracle_api
+    from is3d_b200 import workdir
+    case = cases.SPECTRA_CASES[name]
+    surf, _ = harness.load_golden(name)
+    monkeypatch.setenv("IS3D_FAMOD_CHAIN", "0")
+    with harness.open_session(str(tmp_path / "gpu"), case, surf) as h:
+        got, st = h.abi_spectra()
+    root = workdir.make_workdir(str(tmp_path / "oracle"), case["params"], chosen=case["chosen"], **case.get("tables", {}))
+    rc, ref, ost = oracle_api.OracleProblem(root, case["params"], surf, famod_chain=0).spectra()
+    assert rc == 0
+    worst = harness.assert_spectra_close(got, ref, rtol=5e-10, what=name + " chain-free")
+    assert st.newton_iterations == ost.newton_iterations
+    assert st.cells_breakdown == ost.cells_breakdown and st.reconstruction_failures == ost.reconstruction_failures
+    print(f"{name} chain-free fast path vs oracle: max rel err {worst:.3e}")
+
+
 def test_known_answer_static_cell(libs, tmp_path):
     """Ideal static cell: dN = g/(2 pi hbarc)^3 mT cosh(eta) dsigma_tau feq, and the reference's own
     printed value for pi+ at pT = 0 (1.37049908e+01)."""
