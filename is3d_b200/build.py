@@ -59,11 +59,11 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> None:
     hdeps = hs + [os.path.join(HOST, "is3d_host.hpp"), os.path.join(HERE, "..", "include", "is3d_host.h"), lib] + \
         [os.path.join(CSRC, f) for f in ("dftables.cuh", "gauss_thermal.cuh", "common.cuh")]
     if force or _newer(hostlib, hdeps):
-        _run([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-o", hostlib] + hs +
+        _run([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-pthread", "-o", hostlib] + hs +
              ["-L" + HERE, "-lis3d_b200", "-Wl,-rpath,$ORIGIN"])
     exe = os.path.join(HERE, "iS3D_b200.e")
     if force or _newer(exe, [os.path.join(HOST, "main.cpp"), hostlib]):
-        _run([CXX, "-std=c++17", "-O2", "-o", exe, os.path.join(HOST, "main.cpp"), "-L" + HERE, "-lis3d_host",
+        _run([CXX, "-std=c++17", "-O2", "-pthread", "-o", exe, os.path.join(HOST, "main.cpp"), "-L" + HERE, "-lis3d_host",
               "-lis3d_b200", "-Wl,-rpath,$ORIGIN"])
 
 

@@ -48,12 +48,29 @@ __global__ void feqmod_setup_kernel(SurfaceView surf, int64_t begin, int64_t cou
   if (st & CELL_PL_NEGATIVE) { atomicAdd(&counters[3], 1ull); atomicMax(&counters[5], (unsigned long long)(begin + i + 1)); }
 }
 
-__global__ void feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int ns,
-                                     const double *__restrict__ mass, const double *__restrict__ deg,
-                                     const double *__restrict__ baryon, const double *__restrict__ sign,
-                                     const double *__restrict__ gla_root, const double *__restrict__ gla_weight, int gla_pts,
-                                     double *__restrict__ renorm)
+// PTM renormalisation n_linear / n_mod per (cell, species): the four 32-point Gauss-Laguerre sums of
+// feqmod_renorm_ptm (MomentumSpectra.cpp:795-826) fused into one pass over the nodes -- neq and J10 share their
+// exp(Ebar - b alphaB); node constants w p e^p (alpha = 1) and w e^p (alpha = 2) are staged in shared memory; exp / sqrt /
+// reciprocals are the FP64-pipe versions of common.cuh.
+constexpr int kRenormMaxPts = 64;
+
+__global__ void __launch_bounds__(128)
+feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int ns,
+                     const double *__restrict__ mass, const double *__restrict__ deg,
+                     const double *__restrict__ baryon, const double *__restrict__ sign,
+                     const double *__restrict__ gla_root, const double *__restrict__ gla_weight, int gla_pts,
+                     const double *__restrict__ exptab_g, double *__restrict__ renorm)
 {
+  __shared__ double exptab[kExpTableSize];
+  __shared__ double p1sq[kRenormMaxPts], c1[kRenormMaxPts], p2sq[kRenormMaxPts], c2[kRenormMaxPts];
+  load_exp_table(exptab, exptab_g);
+  for (int k = threadIdx.x; k < gla_pts; k += blockDim.x) {
+    const double r1 = gla_root[1 * gla_pts + k], w1 = gla_weight[1 * gla_pts + k];
+    const double r2 = gla_root[2 * gla_pts + k], w2 = gla_weight[2 * gla_pts + k];
+    p1sq[k] = r1 * r1; c1[k] = w1 * (r1 * exp(r1));
+    p2sq[k] = r2 * r2; c2[k] = w2 * exp(r2);
+  }
+  __syncthreads();
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count * ns) return;
   int64_t cell = idx / ns;
@@ -61,7 +78,30 @@ __global__ void feqmod_renorm_kernel(const double *__restrict__ pack, int64_t st
   double r = 0.0;
   if (pack[DP_VALID * stride + cell] != 0.0) {
     auto pk = [&](int k) { return pack[k * stride + cell]; };
-    r = feqmod_renorm_ptm(pk, mass[s], deg[s], baryon[s], sign[s], gla_root, gla_weight, gla_pts);
+    const double T = pk(FP_T), T_mod = pk(FP_TMOD), alphaB = pk(DP_ALPHAB), alphaB_mod = pk(FP_ALPHAB_MOD);
+    const double m = mass[s], g = deg[s], b = baryon[s], sg = sign[s];
+    const double mbar = m / T, mbar_mod = m / T_mod, mb2 = mbar * mbar, mm2 = mbar_mod * mbar_mod;
+    const double chem = b * alphaB, chem_mod = b * alphaB_mod;
+    double sneq = 0.0, sJ10 = 0.0, sJ20 = 0.0, smod = 0.0;
+    for (int k = 0; k < gla_pts; k++) {
+      const double E1 = fast_sqrt(p1sq[k] + mb2);
+      const double e1 = fast_exp(E1 - chem, exptab), iq1 = fast_rcp(e1 + sg);
+      const double t1 = c1[k] * iq1;
+      sneq += t1;                                   // w p e^p / (e^(E - b alphaB) + sign)
+      sJ10 += t1 * (e1 * iq1);                      // w p e^(p + E - b alphaB) / q^2
+      const double E2 = fast_sqrt(p2sq[k] + mb2);
+      const double e2 = fast_exp(E2 - chem, exptab), iq2 = fast_rcp(e2 + sg);
+      sJ20 += c2[k] * E2 * (e2 * iq2 * iq2);        // w E e^(p + E - b alphaB) / q^2
+      const double Em = fast_sqrt(p1sq[k] + mm2);
+      smod += c1[k] * fast_rcp(fast_exp(Em - chem_mod, exptab) + sg);
+    }
+    const double neq_fact = T * T * T / kTwoPi2HbarC3, J20_fact = T * neq_fact;
+    const double nmod_fact = T_mod * T_mod * T_mod / kTwoPi2HbarC3;
+    const double neq = neq_fact * g * sneq, N10 = b * neq_fact * g * sJ10, J20 = J20_fact * g * sJ20;
+    const double n_linear = neq + pk(FP_DNFACT) * (neq + N10 * pk(FP_G) + J20 * pk(FP_F_T2));
+    const double n_mod = nmod_fact * g * smod;
+    r = (n_linear / n_mod) / pk(FP_RENORM_DIV);
+    r = not_finite(r) ? 0.0 : fabs(r);
   }
   renorm[idx] = r;
 }
@@ -212,6 +252,10 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
 {
   const is3d_params &p = ctx->prm;
   if (p.df_mode != 5 && ctx->gla_pts <= 0) { ctx->set_error("Gauss-Laguerre tables not set"); return IS3D_ERR_INVALID; }
+  if (p.df_mode != 5 && (ctx->gla_pts > kRenormMaxPts || ctx->gla_alpha < 3)) {
+    ctx->set_error("Gauss-Laguerre tables: need alpha = 0..2 with at most 64 points");
+    return IS3D_ERR_INVALID;
+  }
   if (p.df_mode == 5 && ctx->npdg <= 0) { ctx->set_error("PDG table not set (is3d_set_pdg)"); return IS3D_ERR_INVALID; }
   const int64_t n = ctx->surf.n;
   const int64_t total = (int64_t)ctx->ns * ctx->NpT * ctx->Nphi * ctx->Ny;
@@ -272,7 +316,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
       int64_t work = count * ctx->ns;
       feqmod_renorm_kernel<<<(unsigned)((work + 127) / 128), 128, 0, ctx->stream>>>(
           (double *)pack, stride, count, ctx->ns, ctx->d_mass, ctx->d_deg, ctx->d_baryon, ctx->d_sign, ctx->d_gla_root,
-          ctx->d_gla_weight, ctx->gla_pts, (double *)renorm);
+          ctx->d_gla_weight, ctx->gla_pts, ctx->d_exptab, (double *)renorm);
       IS3D_CUDA_TRY(ctx, cudaGetLastError());
       launches++;
     }

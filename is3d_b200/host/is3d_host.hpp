@@ -105,6 +105,7 @@ void write_thermodynamic_averages(const double avg[5]);
 class FO_data_reader {
  public:
   FO_data_reader(ParameterReader *paraRdr, const std::string &path_in);
+  ~FO_data_reader();
   long get_number_cells();
   void read_freezeout_surface(FO_surface &surf);
   void read_surface_cpu_vh(FO_surface &surf);         // mode 1 (5 = with thermal vorticity)
@@ -114,7 +115,10 @@ class FO_data_reader {
   std::vector<double> slurp(long columns);
   int mode, dimension, include_baryon;
   long number_of_cells = 0;
-  std::vector<char> text_;                            // surface.dat, read once
+  void unmap();
+  const char *map_ = nullptr;                         // surface.dat, memory-mapped once
+  size_t map_size_ = 0;
+  bool mapped_ = false;
 };
 
 class PDG_Data {

@@ -1,11 +1,19 @@
 // Freezeout-surface readers (modes 1/5/6/7) into a structure-of-arrays surface, plus the volume-weighted
 // thermodynamic averages.  Column contracts and unit conversions follow reference src/cpp/readindata.cpp:167-729.
+#include <charconv>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iomanip>
+#include <thread>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "is3d_host.hpp"
 
@@ -64,20 +72,130 @@ FO_data_reader::FO_data_reader(ParameterReader *paraRdr, const std::string &)
   include_baryon = paraRdr->getVal("include_baryon");
 }
 
-// number of cells = number of newline-terminated rows of input/surface.dat (Table rule, readindata.cpp:137-146)
+// ---- parallel text ingestion -----------------------------------------------------------------------
+// The reference reads surface.dat as one flat stream of numbers (`ifstream >> double`, readindata.cpp:222-295) after
+// counting newline-terminated rows for the cell count (readindata.cpp:137-146).  At 10^7 cells that is ~2.5e8 numbers and
+// 4-5 GB of text, minutes of serial strtod.  Here the file is read once, cut at whitespace into one slice per hardware
+// thread, tokens are counted per slice (pass 1), and every slice is parsed into its place of the flat array with
+// std::from_chars -- correctly rounded like strtod, several times faster (pass 2).  A token that is not a plain decimal
+// number falls back to strtod; the first token that does not parse at all ends the stream, as `>>` would, and everything
+// after it stays 0.
+namespace {
+
+// IS3D_READER_VERBOSE=1 prints the wall time of each ingestion phase
+struct PhaseTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  bool on = getenv("IS3D_READER_VERBOSE") != nullptr;
+  void lap(const char *what)
+  {
+    auto t1 = std::chrono::steady_clock::now();
+    if (on) printf("[reader] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
+inline bool is_space(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+int ingest_threads(size_t bytes)
+{
+  unsigned hw = std::thread::hardware_concurrency();
+  if (const char *v = getenv("IS3D_READER_THREADS")) hw = (unsigned)atoi(v);
+  size_t by_size = bytes / (1 << 20) + 1;              // at least ~1 MB of text per thread
+  size_t t = hw ? hw : 1;
+  if (t > by_size) t = by_size;
+  if (t > 256) t = 256;
+  return (int)(t < 1 ? 1 : t);
+}
+
+template <class Fn>
+void parallel_for(int nthreads, Fn fn)
+{
+  if (nthreads <= 1) { fn(0); return; }
+  std::vector<std::thread> pool;
+  pool.reserve(nthreads - 1);
+  for (int t = 1; t < nthreads; t++) pool.emplace_back(fn, t);
+  fn(0);
+  for (auto &th : pool) th.join();
+}
+
+// fn(i) for every row i in [0, n), rows split into contiguous blocks over the ingestion threads
+template <class Fn>
+void parallel_rows(long n, Fn fn)
+{
+  const int nt = ingest_threads((size_t)n * 256);
+  parallel_for(nt, [&](int t) {
+    const long b = n * t / nt, e = n * (t + 1) / nt;
+    for (long i = b; i < e; i++) fn(i);
+  });
+}
+
+// parses the token [p, e); returns 0 = whole token consumed, 1 = a number followed by junk (the NEXT extraction fails),
+// 2 = not a number at all
+int parse_token(const char *p, const char *e, double *out)
+{
+  const char *q = p;
+  if (q < e && *q == '+') q++;                         // from_chars takes no leading '+'
+  auto r = std::from_chars(q, e, *out);
+  if (r.ec == std::errc() && r.ptr == e) return 0;
+  char buf[128];
+  size_t len = (size_t)(e - p);
+  if (len >= sizeof(buf)) return 2;
+  memcpy(buf, p, len);
+  buf[len] = '\0';
+  char *end = nullptr;
+  double x = strtod(buf, &end);
+  if (end == buf) return 2;
+  *out = x;
+  return (size_t)(end - buf) == len ? 0 : 1;
+}
+
+}  // namespace
+
+FO_data_reader::~FO_data_reader() { unmap(); }
+
+void FO_data_reader::unmap()
+{
+  if (map_ && map_size_) munmap(const_cast<char *>(map_), map_size_);
+  map_ = nullptr;
+  map_size_ = 0;
+  mapped_ = false;
+}
+
+// number of cells = number of newline-terminated rows of input/surface.dat (Table rule, readindata.cpp:137-146).
+// The file is memory-mapped (no copy through a read buffer); the slices below fault their pages in in parallel.
 long FO_data_reader::get_number_cells()
 {
-  FILE *f = fopen(path("input/surface.dat").c_str(), "rb");
-  if (!f) fatal("Table::loadTableFromFile error: the data file input/surface.dat cannot be opened.");
-  fseek(f, 0, SEEK_END);
-  long sz = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  text_.resize(sz + 1);
-  if (sz > 0 && fread(text_.data(), 1, sz, f) != (size_t)sz) fatal("short read of input/surface.dat");
-  fclose(f);
-  text_[sz] = '\0';
+  unmap();
+  int fd = open(path("input/surface.dat").c_str(), O_RDONLY);
+  if (fd < 0) fatal("Table::loadTableFromFile error: the data file input/surface.dat cannot be opened.");
+  struct stat st;
+  if (fstat(fd, &st) != 0) fatal("cannot stat input/surface.dat");
+  const long sz = (long)st.st_size;
+  if (sz > 0) {
+    void *m = mmap(nullptr, (size_t)sz, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) fatal("cannot map input/surface.dat");
+    madvise(m, (size_t)sz, MADV_WILLNEED);
+    map_ = (const char *)m;
+    map_size_ = (size_t)sz;
+  }
+  close(fd);
+  mapped_ = true;
+  const int nt = ingest_threads((size_t)sz);
+  std::vector<long> part(nt, 0);
+  const char *base = map_;
+  parallel_for(nt, [&](int t) {
+    const char *p = base + (size_t)sz * t / nt, *e = base + (size_t)sz * (t + 1) / nt;
+    long rows = 0;
+    while (p < e) {
+      const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+      if (!q) break;
+      rows++;
+      p = q + 1;
+    }
+    part[t] = rows;
+  });
   long rows = 0;
-  for (long i = 0; i < sz; i++) rows += (text_[i] == '\n');
+  for (long r : part) rows += r;
   number_of_cells = rows;
   return rows;
 }
@@ -85,16 +203,99 @@ long FO_data_reader::get_number_cells()
 // the readers consume a flat stream of numbers (ifstream >> double), `columns` per cell
 std::vector<double> FO_data_reader::slurp(long columns)
 {
-  if (text_.empty()) get_number_cells();
-  std::vector<double> v((size_t)number_of_cells * columns, 0.0);
-  const char *p = text_.data();
-  for (size_t k = 0; k < v.size(); k++) {
-    char *e = nullptr;
-    double x = strtod(p, &e);
-    if (e == p) break;                                // stream failure: remaining values stay 0
-    v[k] = x;
-    p = e;
+  if (!mapped_) get_number_cells();
+  PhaseTimer timer;
+  const size_t total = (size_t)number_of_cells * columns;
+  std::vector<double> v(total, 0.0);
+  timer.lap("allocate flat array");
+  const char *base = map_;
+  const size_t sz = map_size_;
+  const int nt = ingest_threads(sz);
+  // slice boundaries moved forward to the next whitespace so that no token straddles two slices
+  std::vector<size_t> cut(nt + 1, sz);
+  cut[0] = 0;
+  for (int t = 1; t < nt; t++) {
+    size_t pos = sz * t / nt;
+    if (pos < cut[t - 1]) pos = cut[t - 1];
+    while (pos < sz && !is_space(base[pos])) pos++;
+    cut[t] = pos;
   }
+  auto count_tokens = [&](const char *p, const char *e) {
+    size_t n = 0;
+    while (p < e) {
+      while (p < e && is_space(*p)) p++;
+      if (p >= e) break;
+      n++;
+      while (p < e && !is_space(*p)) p++;
+    }
+    return n;
+  };
+  // index of the first token of every slice.  Fast path: a well-formed file has exactly `columns` tokens per
+  // newline-terminated row, so first[t] = rows before the slice x columns + tokens of the partial row in front of it --
+  // one memchr pass for the newlines and a scan of at most one row per slice.  The parse below verifies the guess.
+  std::vector<size_t> first(nt + 1, 0), parsed(nt, 0), fail(nt, (size_t)-1);
+  {
+    std::vector<size_t> rows(nt, 0);
+    parallel_for(nt, [&](int t) {
+      const char *p = base + cut[t], *e = base + cut[t + 1];
+      size_t r = 0;
+      while (p < e) {
+        const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+        if (!q) break;
+        r++;
+        p = q + 1;
+      }
+      rows[t] = r;
+    });
+    size_t rows_before = 0;
+    for (int t = 0; t < nt; t++) {
+      size_t row_start = cut[t];
+      while (row_start > 0 && base[row_start - 1] != '\n') row_start--;
+      first[t] = rows_before * (size_t)columns + count_tokens(base + row_start, base + cut[t]);
+      rows_before += rows[t];
+    }
+    first[nt] = (size_t)-1;                              // the last slice may hold an unterminated partial row
+  }
+  timer.lap("slice offsets (fast path)");
+  auto parse_all = [&]() {
+    parallel_for(nt, [&](int t) {
+      const char *p = base + cut[t], *e = base + cut[t + 1];
+      size_t k = first[t], n = 0;
+      fail[t] = (size_t)-1;
+      while (p < e) {
+        while (p < e && is_space(*p)) p++;
+        if (p >= e) break;
+        const char *q = p;
+        while (q < e && !is_space(*q)) q++;
+        n++;
+        if (k < total && fail[t] == (size_t)-1) {
+          double x = 0.0;
+          int rc = parse_token(p, q, &x);
+          if (rc == 2) fail[t] = k;                      // the stream ends here; keep counting tokens for the check
+          else { v[k++] = x; if (rc == 1) fail[t] = k; }
+        }
+        p = q;
+      }
+      parsed[t] = n;
+    });
+  };
+  parse_all();
+  timer.lap("parse");
+  bool consistent = true;
+  for (int t = 0; t + 1 < nt; t++) consistent = consistent && (first[t] + parsed[t] == first[t + 1]);
+  if (!consistent) {
+    // rows of uneven length: exact token offsets from the counts just taken, then parse again
+    for (int t = 0; t < nt; t++) first[t + 1] = first[t] + parsed[t];
+    std::fill(v.begin(), v.end(), 0.0);
+    parse_all();
+    timer.lap("re-parse (uneven rows)");
+  }
+  size_t stop = (size_t)-1;
+  for (int t = 0; t < nt; t++) if (fail[t] < stop) stop = fail[t];
+  if (stop != (size_t)-1)
+    for (size_t k = stop; k < total; k++) v[k] = 0.0;
+  unmap();                                             // the text is not needed again
+  timer.lap("unmap");
   return v;
 }
 
@@ -112,7 +313,7 @@ void FO_data_reader::read_surface_cpu_vh(FO_surface &s)
   std::vector<double> v = slurp(ncol);
   const long n = number_of_cells;
   s.resize(n, mode == 5);
-  for (long i = 0; i < n; i++) {
+  parallel_rows(n, [&](long i) {
     const double *r = &v[(size_t)i * ncol];
     for (int k = 0; k <= IS3D_COL_UN; k++) s.col[k][i] = r[k];          // tau..un unchanged
     s.col[IS3D_COL_E][i] = r[11] * hbarC;
@@ -135,7 +336,7 @@ void FO_data_reader::read_surface_cpu_vh(FO_surface &s)
     }
     if (mode == 5) for (int w = 0; w < 6; w++) s.vorticity[w][i] = r[k + w];
     if (dimension == 2 && s.col[IS3D_COL_ETA][i] != 0) s.col[IS3D_COL_ETA][i] = 0;   // readindata.cpp:311-319
-  }
+  });
   double avg[5];
   compute_thermodynamic_averages(s, avg);
   write_thermodynamic_averages(avg);
@@ -149,7 +350,7 @@ void FO_data_reader::read_surface_music(FO_surface &s)
   std::vector<double> v = slurp(ncol);
   const long n = number_of_cells;
   s.resize(n);
-  for (long i = 0; i < n; i++) {
+  parallel_rows(n, [&](long i) {
     const double *r = &v[(size_t)i * ncol];
     double tau = r[0];
     s.col[IS3D_COL_TAU][i] = tau; s.col[IS3D_COL_X][i] = r[1]; s.col[IS3D_COL_Y][i] = r[2]; s.col[IS3D_COL_ETA][i] = r[3];
@@ -173,7 +374,7 @@ void FO_data_reader::read_surface_music(FO_surface &s)
       s.col[IS3D_COL_VN][i] = r[33] / tau;
     }
     if (dimension == 2 && s.col[IS3D_COL_ETA][i] != 0) s.col[IS3D_COL_ETA][i] = 0;
-  }
+  });
   double avg[5];
   compute_thermodynamic_averages(s, avg);
   write_thermodynamic_averages(avg);
@@ -189,7 +390,7 @@ void FO_data_reader::read_surface_hic_eventgen(FO_surface &s)
   std::vector<double> v = slurp(ncol);
   const long n = number_of_cells;
   s.resize(n);
-  for (long i = 0; i < n; i++) {
+  parallel_rows(n, [&](long i) {
     const double *r = &v[(size_t)i * ncol];
     double tau = r[0];
     s.col[IS3D_COL_TAU][i] = tau; s.col[IS3D_COL_X][i] = r[1]; s.col[IS3D_COL_Y][i] = r[2]; s.col[IS3D_COL_ETA][i] = 0;
@@ -203,7 +404,7 @@ void FO_data_reader::read_surface_hic_eventgen(FO_surface &s)
     s.col[IS3D_COL_BULKPI][i] = r[21];
     s.col[IS3D_COL_T][i] = r[22]; s.col[IS3D_COL_E][i] = r[23]; s.col[IS3D_COL_P][i] = r[24];
     s.col[IS3D_COL_MUB][i] = r[25];
-  }
+  });
   // the reference averages with its local ut (from v) and nB = 0; ut from u^x,u^y is the same number up to rounding
   double avg[5];
   compute_thermodynamic_averages(s, avg);

@@ -78,3 +78,85 @@ def test_missing_parameter_is_fatal(libs, tmp_path):
     r = subprocess.run([exe], cwd=root, capture_output=True, text=True)
     assert r.returncode != 0
     assert "hrg_eos" in r.stdout and "not found" in r.stdout
+
+
+def test_parallel_reader_is_thread_count_independent(libs, tmp_path, monkeypatch):
+    """The multi-threaded surface.dat parser delivers the same flat number stream as the serial
+    `ifstream >> double` loop of the reference: identical columns for 1, 3 and 8 threads on a file whose slices cut
+    through rows, with explicit '+' signs, exponents in both cases and irregular whitespace; every value equals
+    float(token) (correct rounding)."""
+    n = 60_000
+    s = synthetic.s3d(n, seed=77, baryon=True)
+    root = workdir.make_workdir(str(tmp_path), dict(hrg_eos=2, df_mode=2, dimension=3, mode=1, include_baryon=1), chosen="pikp")
+    p = os.path.join(root, "input", "surface.dat")
+    synthetic.write_mode1(p, s, baryon=True)
+    lines = open(p).read().split("\n")
+    # decorate a few rows: '+' sign, upper-case exponent, tabs and runs of blanks
+    lines[5] = "\t".join("+" + t if not t.startswith("-") else t for t in lines[5].split())
+    lines[6] = "   ".join(t.replace("e", "E") for t in lines[6].split()) + "   "
+    open(p, "w").write("\n".join(lines))
+    seen = synthetic.roundtrip_mode1(s, baryon=True)
+    cols = {}
+    for nt in (1, 3, 8):
+        monkeypatch.setenv("IS3D_READER_THREADS", str(nt))
+        with HostSession(root) as h:
+            assert h.read_surface() == n
+            cols[nt] = [h.surface_column(k).copy() for k in range(len(synthetic.SOA_COLUMNS))]
+    for k, name in enumerate(synthetic.SOA_COLUMNS):
+        np.testing.assert_array_equal(cols[1][k], seen[name], err_msg=name)
+        np.testing.assert_array_equal(cols[3][k], cols[1][k], err_msg=name)
+        np.testing.assert_array_equal(cols[8][k], cols[1][k], err_msg=name)
+
+
+def test_reader_stops_at_a_malformed_token(libs, tmp_path, monkeypatch):
+    """`ifstream >> double` fails at the first non-numeric token and every later value stays 0 (the reference keeps
+    looping with the stream in its failed state); the parallel parser reproduces that for any thread count."""
+    n = 4000
+    s = synthetic.s3d(n, seed=78)
+    root = workdir.make_workdir(str(tmp_path), dict(hrg_eos=2, df_mode=2, dimension=3, mode=1), chosen="pikp")
+    p = os.path.join(root, "input", "surface.dat")
+    synthetic.write_mode1(p, s)
+    lines = open(p).read().split("\n")
+    bad_row = 2500
+    toks = lines[bad_row].split()
+    toks[7] = "oops"
+    lines[bad_row] = " ".join(toks)
+    open(p, "w").write("\n".join(lines))
+    seen = synthetic.roundtrip_mode1(s)
+    for nt in (1, 5):
+        monkeypatch.setenv("IS3D_READER_THREADS", str(nt))
+        with HostSession(root) as h:
+            assert h.read_surface() == n
+            tau = h.surface_column(0).copy()
+            dan = h.surface_column(7).copy()
+            ux = h.surface_column(8).copy()
+        np.testing.assert_array_equal(tau[:bad_row + 1], seen["tau"][:bad_row + 1])
+        assert np.all(tau[bad_row + 1:] == 0.0)
+        np.testing.assert_array_equal(dan[:bad_row], seen["dan"][:bad_row])
+        assert np.all(dan[bad_row:] == 0.0) and np.all(ux[bad_row:] == 0.0)
+
+
+def test_reader_uneven_rows_follow_the_stream(libs, tmp_path, monkeypatch):
+    """Rows need not hold exactly `columns` numbers: the reference counts newline-terminated rows for the cell count and
+    then reads one flat stream.  A row wrapped onto two lines gives one more (partly empty) cell; the parallel parser
+    must notice that its per-slice offset guess is off and fall back to exact token offsets."""
+    n = 30_000
+    s = synthetic.s3d(n, seed=79)
+    root = workdir.make_workdir(str(tmp_path), dict(hrg_eos=2, df_mode=2, dimension=3, mode=1), chosen="pikp")
+    p = os.path.join(root, "input", "surface.dat")
+    synthetic.write_mode1(p, s)
+    lines = open(p).read().split("\n")
+    toks = lines[100].split()
+    lines[100] = " ".join(toks[:7]) + "\n" + " ".join(toks[7:])           # wrapped early in the file
+    open(p, "w").write("\n".join(lines))
+    flat = np.array(open(p).read().split(), dtype=np.float64)
+    want_tau = flat[0::20]
+    got = {}
+    for nt in (1, 6):
+        monkeypatch.setenv("IS3D_READER_THREADS", str(nt))
+        with HostSession(root) as h:
+            assert h.read_surface() == n + 1
+            got[nt] = h.surface_column(0).copy()
+    np.testing.assert_array_equal(got[1][:n], want_tau[:n])
+    assert got[1][n] == 0.0                                               # the stream ran dry before the extra cell
+    np.testing.assert_array_equal(got[6], got[1])
