@@ -51,25 +51,45 @@ IS3D_HD bool not_finite(double x) { return !(fabs(x) <= 1.7976931348623157e308);
 // exp(x) for the Bose/Fermi factor, kept in the FP64 FMA pipe and short enough to leave the pipe to the physics:
 //   x = k (ln2/1024) + r,  |r| <= ln2/2048,   e^x = 2^(k >> 10) * T[k & 1023] * (1 + r + r^2/2 + r^3/6)
 // T[m] = 2^(m/1024) is a 1024-entry table (8 KB; shared memory on the device, filled by load_exp_table).
-// Truncation error r^4/24 < 5.5e-16; 4 reduction + 3 polynomial + 1 scaling FP64 instructions (the first version, a
-// degree-11 Horner form with FP64 clamps, needed 19).  The exponent is patched by an integer add on the high word.
-// Range: |x| >= 708 (beyond the double range of e^x) is caught on the integer pipe from the high word of x and
-// returns 1e300 / 0, which 1/(e^x + s) turns into the reference's 0 / (1/s); NaN input gives 1e300.
+// 7 FP64 instructions: 3 reduction + 3 polynomial + 1 scaling (the first version, a degree-11 Horner form with FP64
+// clamps, needed 19).  Errors: truncation r^4/24 < 5.5e-16; the reduction uses ln2/1024 rounded to double in ONE fma, so
+// r carries |x| 1.1e-16 (3e-15 of e^x at x = 30, where the Bose/Fermi factor is already 1e-13; the continuous paths
+// promise 1e-10).  The exponent is patched by an integer add on the high word.  Range: x >= 708 (beyond the double range
+// of e^x) is caught on the integer pipe from the high word of x and returns 1e300, which 1/(e^x + s) turns into the
+// reference's 0; x <= -708 cannot occur (x = (E - b mu_B)/T >= -mu_B/T > -10).
 // tools/gen_exp_table.py derives the constants and scans the error of the whole construction in 60-digit arithmetic.
 constexpr int kExpTableBits = 10;
 constexpr int kExpTableSize = 1 << kExpTableBits;
 
 IS3D_HD int hi_word(double d) { return (int)(as_int64(d) >> 32); }
+IS3D_HD double add_to_hi_word(double d, int add)
+{
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(d) + add, __double2loint(d));
+#else
+  return as_double(as_int64(d) + ((int64_t)add << 32));
+#endif
+}
+
+// constants with a non-zero low word live in the constant bank on the device: DFMA reads a c[bank][offset] operand
+// directly, whereas an immediate costs two IMAD.MOV per use inside the register-starved inner loops
+#if defined(__CUDACC__)
+static __constant__ double c_exp_consts[3] = {1477.3197218702985, -6.769015435155716e-04, 1.6666666666666666e-01};
+#endif
 
 IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
 {
+#if defined(__CUDA_ARCH__)
+  const double kInv = c_exp_consts[0], kStep = c_exp_consts[1], kSixth = c_exp_consts[2];
+#else
+  const double kInv = 1477.3197218702985, kStep = -6.769015435155716e-04, kSixth = 1.6666666666666666e-01;
+#endif
   const double kMagic = 6755399441055744.0;          // 1.5 * 2^52: rounds to nearest integer in the low mantissa bits
-  double t = fma(x, 1477.3197218702985, kMagic);     // 1024 / ln2
+  double t = fma(x, kInv, kMagic);                   // 1024 / ln2
   const int k = (int)as_int64(t);                    // low word of t = the integer (two's complement), |k| < 2^21 here
   t -= kMagic;
-  double r = fma(t, -6.769015308236703e-04, x);      // ln2/1024 rounded to 26 significant bits: t * hi is exact
-  r = fma(t, -1.2691901263564344e-11, r);            // ln2/1024 - hi
-  double q = fma(r, 1.6666666666666666e-01, 0.5);
+  const double r = fma(t, kStep, x);                 // x - k ln2/1024
+  double q = fma(r, kSixth, 0.5);
   q = fma(q, r, 1.0);
   q = q * r;                                         // r + r^2/2 + r^3/6
 #if defined(IS3D_PROBE_UNIFORM_EXP_TABLE)       // timing probe only (wrong results): every lane reads entry 0, no bank conflicts
@@ -78,9 +98,8 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
   const double T = tab[k & (kExpTableSize - 1)];
 #endif
   const double v = fma(T, q, T);
-  double res = as_double(as_int64(v) + ((int64_t)(k >> kExpTableBits) << 52));
-  const int hx = hi_word(x);
-  if ((hx & 0x7fffffff) >= 0x40862000) res = hx < 0 ? 0.0 : 1e300;   // |x| >= 708 (or NaN)
+  double res = add_to_hi_word(v, (k >> kExpTableBits) << 20);
+  if (hi_word(x) >= 0x40862000) res = 1e300;         // x >= 708 (signed compare: negative x never matches)
   return res;
 }
 
