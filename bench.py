@@ -359,7 +359,10 @@ def run_ours(args) -> None:
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.df_mode, cells, world), "global_cells": cells * world,
                        "evals_per_step": evals_rank * world, "l2_policy": "inputs larger than L2 (cell packs: 240 B x cells per pass)",
-                       "parallelism": f"cells sharded x{world}, one NCCL all-reduce of {total} doubles" if world > 1 else "single GPU"},
+                       "parallelism": f"cells sharded x{world}, one NCCL all-reduce of {total} doubles" if world > 1 else "single GPU",
+                       "species_classes": "evaluations are counted per species (444); species with identical (mass, sign, baryon "
+                                          "number) share one integrand, computed once and scaled by each species' degeneracy "
+                                          "(193 classes for the SMASH list) -- every species' bins are delivered"},
             "e2e": {"value": evals_rank * world / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(cells * 25 * 8),
                     "d2h_bytes_per_step": int(total * 8)},
             "gpu_launches": int(launches),

@@ -131,6 +131,17 @@ struct is3d_ctx {
 
 namespace is3d {
 
+// Species classes: hadrons with the same (mass, quantum-statistics sign, baryon number) have the same Cooper-Frye
+// integrand and differ only by the degeneracy factor in front (the SMASH list's 444 species are 193 classes: isospin
+// multiplets share one mass).  The spectra kernels integrate one representative per class; the final reduction writes
+// every species' bins as degeneracy x class sum, so the output is exactly what a per-species loop delivers.
+struct SpeciesBins {
+  int nclass = 0;
+  const double *mT = nullptr, *pT = nullptr, *m2 = nullptr, *baryon = nullptr, *sign = nullptr;   // [nclass * NpT], device
+  const double *c_mass = nullptr, *c_deg = nullptr, *c_baryon = nullptr, *c_sign = nullptr;      // [nclass] representatives, device
+  const int *class_of = nullptr;                                                                 // [ns], device
+};
+
 // compute paths (one translation unit each)
 is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);        // df_mode 1,2
 is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);    // df_mode 3,4 and 5 (PTMA)

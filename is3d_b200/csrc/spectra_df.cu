@@ -50,8 +50,8 @@ __global__ void df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, 
 }
 
 struct DfGrid {
-  const double *mT, *pT, *m2, *baryon, *sign, *deg;   // per (species, pT) bin, [ns * NpT]
-  int ns, NpT, ncols;                                 // ncols = NpT * ceil(ns / R) thread columns
+  const double *mT, *pT, *m2, *baryon, *sign;         // per (species class, pT) bin, [ns * NpT]
+  int ns, NpT, ncols;                                 // ns = number of species CLASSES; ncols = NpT * ceil(ns / R) thread columns
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
   const double *exptab;                               // 2^(m/1024), global memory (ctx->d_exptab)
@@ -133,21 +133,25 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   for (int r = 0; r < R; r++) {
     if (jbin[r] >= 0) {
       int64_t idx = iy + (int64_t)g.Ny * (iphi + (int64_t)g.Nphi * jbin[r]);
-      partial[pbase + idx] += kCooperFryePrefactor * g.deg[jbin[r]] * acc[r];
+      partial[pbase + idx] += acc[r];
     }
   }
 }
 
 }  // namespace
 
-__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int64_t total,
+// Deterministic sum over the cell chunks and expansion of the species classes: species s takes the bins of its class,
+// times (2 pi hbarc)^-3 and its own degeneracy (MomentumSpectra.cpp:38, :399-401).
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int64_t total_class, int64_t per_species,
+                                       const int *__restrict__ class_of, const double *__restrict__ deg, int64_t total,
                                        double *__restrict__ out)
 {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  const int64_t sp = i / per_species, src = (int64_t)class_of[sp] * per_species + (i - sp * per_species);
   double s = 0.0;
-  for (int c = 0; c < nchunks; c++) s += partial[(int64_t)c * total + i];
-  out[i] = s;
+  for (int c = 0; c < nchunks; c++) s += partial[(int64_t)c * total_class + src];
+  out[i] = kCooperFryePrefactor * deg[sp] * s;
 }
 
 namespace {
@@ -172,30 +176,52 @@ void dispatch_df2(bool reg, bool outflow, dim3 grid, cudaStream_t st, const doub
 }  // namespace
 
 
-// Builds the per-(species, pT) bin arrays shared by all spectra kernels; returns device pointers in `out`.
-is3d_status build_bin_arrays(is3d_ctx *ctx, const double **mT, const double **pT, const double **m2, const double **baryon,
-                             const double **sign, const double **deg)
+// Builds the species classes and their per-(class, pT) bin arrays shared by all spectra kernels (device pointers in `out`).
+is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out)
 {
-  const int nb = ctx->ns * ctx->NpT;
-  std::vector<double> h(6 * (size_t)nb);
-  for (int s = 0; s < ctx->ns; s++)
-    for (int ip = 0; ip < ctx->NpT; ip++) {
-      int j = s * ctx->NpT + ip;
-      double m = ctx->h_mass[s], p = ctx->pT[ip];
-      double mass2 = m * m;
+  const int ns = ctx->ns, npT = ctx->NpT;
+  const bool baryon_on = ctx->prm.include_baryon != 0;
+  std::vector<int> class_of(ns), rep;                 // rep[c] = first species of class c
+  for (int s = 0; s < ns; s++) {
+    int c = -1;
+    const double bs = baryon_on ? ctx->h_baryon[s] : 0.0;
+    for (size_t k = 0; k < rep.size() && c < 0; k++) {
+      const int r = rep[k];
+      const double br = baryon_on ? ctx->h_baryon[r] : 0.0;
+      if (ctx->h_mass[r] == ctx->h_mass[s] && ctx->h_sign[r] == ctx->h_sign[s] && br == bs) c = (int)k;
+    }
+    if (c < 0) { c = (int)rep.size(); rep.push_back(s); }
+    class_of[s] = c;
+  }
+  const int nc = (int)rep.size(), nb = nc * npT;
+  std::vector<double> h(5 * (size_t)nb + 4 * (size_t)nc);
+  for (int c = 0; c < nc; c++) {
+    const int s = rep[c];
+    const double m = ctx->h_mass[s], mass2 = m * m;
+    for (int ip = 0; ip < npT; ip++) {
+      const int j = c * npT + ip;
+      const double p = ctx->pT[ip];
       h[0 * nb + j] = sqrt(mass2 + p * p);      // mT, MomentumSpectra.cpp:266
       h[1 * nb + j] = p;
       h[2 * nb + j] = mass2;
       h[3 * nb + j] = ctx->h_baryon[s];
       h[4 * nb + j] = ctx->h_sign[s];
-      h[5 * nb + j] = ctx->h_deg[s];
     }
-  void *d = nullptr;
+    double *cr = h.data() + 5 * (size_t)nb;
+    cr[0 * nc + c] = m; cr[1 * nc + c] = ctx->h_deg[s]; cr[2 * nc + c] = ctx->h_baryon[s]; cr[3 * nc + c] = ctx->h_sign[s];
+  }
+  void *d = nullptr, *dm = nullptr;
   IS3D_TRY(ctx->get_scratch("bin_arrays", h.size() * sizeof(double), &d));
+  IS3D_TRY(ctx->get_scratch("class_of", (size_t)ns * sizeof(int), &dm));
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(dm, class_of.data(), (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   const double *b = (const double *)d;
-  *mT = b; *pT = b + nb; *m2 = b + 2 * nb; *baryon = b + 3 * nb; *sign = b + 4 * nb; *deg = b + 5 * nb;
+  out->nclass = nc;
+  out->mT = b; out->pT = b + nb; out->m2 = b + 2 * nb; out->baryon = b + 3 * nb; out->sign = b + 4 * nb;
+  const double *cr = b + 5 * (size_t)nb;
+  out->c_mass = cr; out->c_deg = cr + nc; out->c_baryon = cr + 2 * nc; out->c_sign = cr + 3 * nc;
+  out->class_of = (const int *)dm;
   return IS3D_OK;
 }
 
@@ -231,8 +257,12 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   fl.include_baryondiff = p.include_baryondiff_deltaf;
 
   DfGrid g;
-  IS3D_TRY(build_bin_arrays(ctx, &g.mT, &g.pT, &g.m2, &g.baryon, &g.sign, &g.deg));
-  g.ns = ctx->ns; g.NpT = ctx->NpT; g.ncols = ctx->NpT * ((ctx->ns + kDfBinsPerThread - 1) / kDfBinsPerThread);
+  SpeciesBins sb;
+  IS3D_TRY(build_bin_arrays(ctx, &sb));
+  g.mT = sb.mT; g.pT = sb.pT; g.m2 = sb.m2; g.baryon = sb.baryon; g.sign = sb.sign;
+  g.ns = sb.nclass; g.NpT = ctx->NpT; g.ncols = ctx->NpT * ((sb.nclass + kDfBinsPerThread - 1) / kDfBinsPerThread);
+  const int64_t per_species = (int64_t)ctx->NpT * ctx->Nphi * ctx->Ny;
+  const int64_t total_class = (int64_t)sb.nclass * per_species;
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
   g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw; g.exptab = ctx->d_exptab;
 
@@ -243,13 +273,13 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   const int64_t macro = 4 << 20;                      // cells per pass: bounds the pack scratch to ~1 GB
   const int64_t stride = n < macro ? n : macro;
   int nchunks; int64_t cpc;
-  choose_chunks(ctx, stride, blocks_per_chunk, total, kTile, &nchunks, &cpc);
+  choose_chunks(ctx, stride, blocks_per_chunk, total_class, kTile, &nchunks, &cpc);
 
   void *pack = nullptr, *partial = nullptr, *counters = nullptr;
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)DP_SIZE * stride * sizeof(double), &pack));
-  IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total * sizeof(double), &partial));
+  IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total_class * sizeof(double), &partial));
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
-  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total * sizeof(double), ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total_class * sizeof(double), ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
 
   cudaEvent_t e0, e1;
@@ -268,11 +298,11 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0;
     if (p.df_mode == 1) {
-      if (p.include_baryon) dispatch_df2<1, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total);
-      else dispatch_df2<1, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total);
+      if (p.include_baryon) dispatch_df2<1, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
+      else dispatch_df2<1, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
     } else {
-      if (p.include_baryon) dispatch_df2<2, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total);
-      else dispatch_df2<2, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total);
+      if (p.include_baryon) dispatch_df2<2, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
+      else dispatch_df2<2, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
     }
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
@@ -282,7 +312,8 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     ms_total += ms;
     launches += 2;
   }
-  reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total, out_dev);
+  reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total_class, per_species,
+                                                                                sb.class_of, ctx->d_deg, total, out_dev);
   IS3D_CUDA_TRY(ctx, cudaGetLastError());
   launches += 1;
   unsigned long long h_counters[16];

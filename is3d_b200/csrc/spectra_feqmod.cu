@@ -15,9 +15,10 @@
 
 namespace is3d {
 
-__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int64_t total, double *__restrict__ out);
-is3d_status build_bin_arrays(is3d_ctx *ctx, const double **mT, const double **pT, const double **m2, const double **baryon,
-                             const double **sign, const double **deg);
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int64_t total_class, int64_t per_species,
+                                       const int *__restrict__ class_of, const double *__restrict__ deg, int64_t total,
+                                       double *__restrict__ out);
+is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out);
 void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
                    int64_t *cells_per_chunk);
 // df_mode 5 per-cell stage (spectra_famod.cu): fills the same pack layout, counters[8] = reconstruction failures,
@@ -107,8 +108,8 @@ feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t co
 }
 
 struct FeqGrid {
-  const double *mT, *pT, *m2, *baryon, *sign, *deg;
-  int ncols, NpT, ns;                   // ncols = NpT * ceil(ns / kBins) thread columns
+  const double *mT, *pT, *m2, *baryon, *sign;
+  int ncols, NpT, ns;                   // ns = number of species CLASSES; ncols = NpT * ceil(ns / kBins) thread columns
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
   const double *exptab;
@@ -229,7 +230,7 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
   for (int r = 0; r < R; r++) {
     if (jbin[r] >= 0) {
       int64_t idx = iy + (int64_t)g.Ny * (iphi + (int64_t)g.Nphi * jbin[r]);
-      partial[pbase + idx] += kCooperFryePrefactor * g.deg[jbin[r]] * acc[r];
+      partial[pbase + idx] += acc[r];
     }
   }
 }
@@ -267,8 +268,12 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   const bool species_renorm = (p.df_mode == 3 && p.include_bulk_deltaf);
 
   FeqGrid g;
-  IS3D_TRY(build_bin_arrays(ctx, &g.mT, &g.pT, &g.m2, &g.baryon, &g.sign, &g.deg));
-  g.NpT = ctx->NpT; g.ns = ctx->ns; g.ncols = ctx->NpT * ((ctx->ns + kBins - 1) / kBins);
+  SpeciesBins sb;
+  IS3D_TRY(build_bin_arrays(ctx, &sb));
+  g.mT = sb.mT; g.pT = sb.pT; g.m2 = sb.m2; g.baryon = sb.baryon; g.sign = sb.sign;
+  g.NpT = ctx->NpT; g.ns = sb.nclass; g.ncols = ctx->NpT * ((sb.nclass + kBins - 1) / kBins);
+  const int64_t per_species = (int64_t)ctx->NpT * ctx->Nphi * ctx->Ny;
+  const int64_t total_class = (int64_t)sb.nclass * per_species;
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
   g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw;
   g.w_on_dan = (p.df_mode == 5);
@@ -280,19 +285,19 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
 
   // cells per pass: bounds the pack (440 B/cell) and the PTM renorm table (8 Ns B/cell) to ~2 GB
   int64_t macro = 2 << 20;
-  if (species_renorm) { int64_t m2 = ((int64_t)1 << 31) / (8 * (int64_t)ctx->ns); if (m2 < macro) macro = m2; }
+  if (species_renorm) { int64_t m2 = ((int64_t)1 << 31) / (8 * (int64_t)sb.nclass); if (m2 < macro) macro = m2; }
   macro = macro / kTile * kTile;
   if (macro < kTile) macro = kTile;
   const int64_t stride = n < macro ? n : macro;
   int nchunks; int64_t cpc;
-  choose_chunks(ctx, stride, blocks_per_chunk, total, kTile, &nchunks, &cpc);
+  choose_chunks(ctx, stride, blocks_per_chunk, total_class, kTile, &nchunks, &cpc);
 
   void *pack = nullptr, *partial = nullptr, *counters = nullptr, *renorm = nullptr;
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)FP_SIZE * stride * sizeof(double), &pack));
-  IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total * sizeof(double), &partial));
+  IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total_class * sizeof(double), &partial));
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
-  if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm", (size_t)stride * ctx->ns * sizeof(double), &renorm));
-  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total * sizeof(double), ctx->stream));
+  if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm", (size_t)stride * sb.nclass * sizeof(double), &renorm));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total_class * sizeof(double), ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
 
   cudaEvent_t e0, e1;
@@ -313,9 +318,9 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
       launches++;
     }
     if (species_renorm) {
-      int64_t work = count * ctx->ns;
+      int64_t work = count * sb.nclass;
       feqmod_renorm_kernel<<<(unsigned)((work + 127) / 128), 128, 0, ctx->stream>>>(
-          (double *)pack, stride, count, ctx->ns, ctx->d_mass, ctx->d_deg, ctx->d_baryon, ctx->d_sign, ctx->d_gla_root,
+          (double *)pack, stride, count, sb.nclass, sb.c_mass, sb.c_deg, sb.c_baryon, sb.c_sign, ctx->d_gla_root,
           ctx->d_gla_weight, ctx->gla_pts, ctx->d_exptab, (double *)renorm);
       IS3D_CUDA_TRY(ctx, cudaGetLastError());
       launches++;
@@ -324,11 +329,11 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
     dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch);
     const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0;
     if (p.include_baryon) {
-      if (species_renorm) launch_feqmod<true, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total);
-      else launch_feqmod<true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total);
+      if (species_renorm) launch_feqmod<true, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total_class);
+      else launch_feqmod<true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total_class);
     } else {
-      if (species_renorm) launch_feqmod<false, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total);
-      else launch_feqmod<false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total);
+      if (species_renorm) launch_feqmod<false, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total_class);
+      else launch_feqmod<false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total_class);
     }
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
     launches++;
@@ -338,7 +343,8 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
     IS3D_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
     ms_total += ms;
   }
-  reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total, out_dev);
+  reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total_class, per_species,
+                                                                                sb.class_of, ctx->d_deg, total, out_dev);
   IS3D_CUDA_TRY(ctx, cudaGetLastError());
   launches++;
   unsigned long long h_counters[16];
