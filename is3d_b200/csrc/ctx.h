@@ -142,6 +142,8 @@ struct SpeciesBins {
   const int *class_of = nullptr;                                                                 // [ns], device
 };
 
+void species_classes(const is3d_ctx *ctx, std::vector<int> *class_of, std::vector<int> *rep);
+
 // compute paths (one translation unit each)
 is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);        // df_mode 1,2
 is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);    // df_mode 3,4 and 5 (PTMA)

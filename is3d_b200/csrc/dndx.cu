@@ -70,7 +70,7 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
   load_exp_table(exptab, g.exptab);
   __syncthreads();
   const int s = blockIdx.x * kDndxThreads + threadIdx.x;
-  const double m2 = g.mass2[s], baryon = g.baryon[s], sign = g.sign[s], deg = g.deg[s];
+  const double m2 = g.mass2[s], baryon = g.baryon[s], sign = g.sign[s];
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
   int64_t c1 = c0 + cells_per_block;
   if (c1 > ncells) c1 = ncells;
@@ -101,7 +101,7 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
     }
     if (s < g.ns) {
       const int64_t gc = surf_begin + cell;
-      dndx_scatter(g, s, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc], kCooperFryePrefactor * deg * acc);
+      dndx_scatter(g, s, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc], kCooperFryePrefactor * acc);
     }
   }
 }
@@ -117,7 +117,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
   load_exp_table(exptab, g.exptab);
   __syncthreads();
   const int s = blockIdx.x * kDndxThreads + threadIdx.x;
-  const double m2 = g.mass2[s], baryon = g.baryon[s], sign = g.sign[s], deg = g.deg[s], mass = g.mass[s];
+  const double m2 = g.mass2[s], baryon = g.baryon[s], sign = g.sign[s], deg = g.deg[s], mass = g.mass[s];   // deg cancels in the renorm ratio
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
   int64_t c1 = c0 + cells_per_block;
   if (c1 > ncells) c1 = ncells;
@@ -168,21 +168,33 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
     // a NaN / inf renormalisation skips the (cell, species) in both branches (SpacetimeDistribution.cpp:955-959)
     if (s < g.ns && rn != 0.0) {
       const int64_t gc = surf_begin + cell;
-      dndx_scatter(g, s, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc], kCooperFryePrefactor * deg * acc);
+      dndx_scatter(g, s, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc], kCooperFryePrefactor * acc);
     }
   }
 }
 
+__global__ void dndx_expand_kernel(const double *__restrict__ class_hist, const int *__restrict__ class_of, const double *__restrict__ deg,
+                                   int bins, int64_t total, double *__restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t s = i / bins;
+  out[i] = deg[s] * class_hist[(int64_t)class_of[s] * bins + (i - s * bins)];
+}
+
 // transposed momentum tables [ipT][ns_pad] and padded species arrays
-is3d_status build_dndx_grid(is3d_ctx *ctx, DndxGrid *g)
+is3d_status build_dndx_grid(is3d_ctx *ctx, DndxGrid *g, const int **class_of_dev)
 {
   const is3d_params &p = ctx->prm;
-  const int ns = ctx->ns, nsp = (ns + kDndxThreads - 1) / kDndxThreads * kDndxThreads, npT = ctx->NpT;
+  // one thread per species CLASS (ctx.h SpeciesBins): the histograms are filled per class and expanded to species at the end
+  std::vector<int> class_of, rep;
+  species_classes(ctx, &class_of, &rep);
+  const int ns = (int)rep.size(), nsp = (ns + kDndxThreads - 1) / kDndxThreads * kDndxThreads, npT = ctx->NpT;
   std::vector<double> h((size_t)4 * npT * nsp + 5 * nsp, 0.0);
   double *mTw = h.data(), *mT = mTw + (size_t)npT * nsp, *mT2 = mT + (size_t)npT * nsp, *mTpT = mT2 + (size_t)npT * nsp;
   double *mass2 = mTpT + (size_t)npT * nsp, *baryon = mass2 + nsp, *sign = baryon + nsp, *deg = sign + nsp, *mass = deg + nsp;
   for (int s = 0; s < nsp; s++) {
-    int ss = s < ns ? s : ns - 1;                         // padding lanes repeat the last species (never written)
+    int ss = rep[s < ns ? s : ns - 1];                    // class representative; padding lanes repeat the last class (never written)
     double m = ctx->h_mass[ss];
     mass[s] = m; mass2[s] = m * m; baryon[s] = ctx->h_baryon[ss]; sign[s] = ctx->h_sign[ss]; deg[s] = ctx->h_deg[ss];
     for (int ip = 0; ip < npT; ip++) {
@@ -191,9 +203,12 @@ is3d_status build_dndx_grid(is3d_ctx *ctx, DndxGrid *g)
       mT[idx] = v; mTw[idx] = v * ctx->pTw[ip]; mT2[idx] = v * v; mTpT[idx] = v * pT;
     }
   }
-  void *d = nullptr;
+  void *d = nullptr, *dm = nullptr;
   IS3D_TRY(ctx->get_scratch("dndx_tables", h.size() * sizeof(double), &d));
+  IS3D_TRY(ctx->get_scratch("class_of", (size_t)ctx->ns * sizeof(int), &dm));
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(dm, class_of.data(), (size_t)ctx->ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  *class_of_dev = (const int *)dm;
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   const double *b = (const double *)d;
   g->ns = ns; g->ns_pad = nsp; g->NpT = npT; g->Nphi = ctx->Nphi; g->Ny = ctx->Ny; g->Neta = ctx->Neta; g->dimension = p.dimension;
@@ -220,12 +235,14 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   if (feqmod && ctx->gla_pts <= 0) { ctx->set_error("Gauss-Laguerre tables not set"); return IS3D_ERR_INVALID; }
   const int64_t n = ctx->surf.n;
   DndxGrid g;
-  IS3D_TRY(build_dndx_grid(ctx, &g));
-  g.hist_tau = tau_dev; g.hist_r = r_dev; g.hist_phi = phi_dev;
+  const int *class_of_dev = nullptr;
+  IS3D_TRY(build_dndx_grid(ctx, &g, &class_of_dev));
+  const size_t class_bins = (size_t)g.ns * (p.tau_bins + p.r_bins + p.phip_bins);
+  void *class_hist = nullptr;
+  IS3D_TRY(ctx->get_scratch("dndx_class_hist", class_bins * sizeof(double), &class_hist));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(class_hist, 0, class_bins * sizeof(double), ctx->stream));
+  g.hist_tau = (double *)class_hist; g.hist_r = g.hist_tau + (size_t)g.ns * p.tau_bins; g.hist_phi = g.hist_r + (size_t)g.ns * p.r_bins;
   g.exptab = ctx->d_exptab;
-  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(tau_dev, 0, (size_t)ctx->ns * p.tau_bins * sizeof(double), ctx->stream));
-  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(r_dev, 0, (size_t)ctx->ns * p.r_bins * sizeof(double), ctx->stream));
-  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(phi_dev, 0, (size_t)ctx->ns * p.phip_bins * sizeof(double), ctx->stream));
 
   DfFlags dfl;
   dfl.df_mode = p.df_mode; dfl.dimension = p.dimension; dfl.include_baryon = p.include_baryon;
@@ -246,8 +263,8 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
 
   const int nslices = g.ns_pad / kDndxThreads;
-  // ~8 waves of blocks: 64-thread blocks, up to 8 resident per SM
-  int64_t want_blocks = 8LL * 8 * ctx->sm_count;
+  // ~8 waves of blocks: one-warp blocks, up to 16 resident per SM
+  int64_t want_blocks = 8LL * 16 * ctx->sm_count;
   cudaEvent_t e0, e1;
   IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
   IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));
@@ -290,6 +307,16 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
     ms_total += ms;
     launches += 2;
   }
+  // species s = degeneracy_s x its class (SpacetimeDistribution.cpp:408: dN_dy_cell carries the degeneracy)
+  const int bins3[3] = {p.tau_bins, p.r_bins, p.phip_bins};
+  const double *src3[3] = {g.hist_tau, g.hist_r, g.hist_phi};
+  double *dst3[3] = {tau_dev, r_dev, phi_dev};
+  for (int k = 0; k < 3; k++) {
+    const int64_t tot = (int64_t)ctx->ns * bins3[k];
+    dndx_expand_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(src3[k], class_of_dev, ctx->d_deg, bins3[k], tot, dst3[k]);
+    IS3D_CUDA_TRY(ctx, cudaGetLastError());
+  }
+  launches += 3;
   unsigned long long h_counters[16];
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

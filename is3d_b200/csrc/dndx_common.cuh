@@ -5,7 +5,7 @@
 // pT and phi table weights (the y nodes are summed UNweighted in 3+1d, :330-404) into one scalar dN_dy_cell and adds
 // it to three 1-D histograms selected by the cell's (tau, r, phi_s) (:413-440).
 //
-// GPU mapping: cell-stationary.  One thread = one species; a block of 64 threads walks a contiguous chunk of cells,
+// GPU mapping: cell-stationary.  One thread = one species class (ctx.h SpeciesBins); a one-warp block walks a contiguous chunk of cells,
 // all lanes on the same cell, so every per-cell / per-(y, phi) quantity is warp-uniform and is simply recomputed in
 // registers (a few % of the 51 x Nphi x Ny evaluations it feeds).  The per-(pT, species) momentum constants come
 // from four transposed tables [ipT][species] (coalesced, L1/L2 resident, 725 KB for 444 species).  The (cell,
@@ -17,7 +17,7 @@
 
 namespace is3d {
 
-constexpr int kDndxThreads = 64;
+constexpr int kDndxThreads = 32;    // one warp per block: species classes are padded to a multiple of this
 
 struct DndxGrid {
   int ns, ns_pad;                 // species, padded to a multiple of kDndxThreads

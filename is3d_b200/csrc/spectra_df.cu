@@ -176,23 +176,33 @@ void dispatch_df2(bool reg, bool outflow, dim3 grid, cudaStream_t st, const doub
 }  // namespace
 
 
+// class_of[s] = class of species s, rep[c] = first species of class c (classes numbered in order of first appearance).
+// The baryon number separates classes only when baryon terms are switched on.
+void species_classes(const is3d_ctx *ctx, std::vector<int> *class_of, std::vector<int> *rep)
+{
+  const int ns = ctx->ns;
+  const bool baryon_on = ctx->prm.include_baryon != 0;
+  class_of->assign(ns, 0);
+  rep->clear();
+  for (int s = 0; s < ns; s++) {
+    int c = -1;
+    const double bs = baryon_on ? ctx->h_baryon[s] : 0.0;
+    for (size_t k = 0; k < rep->size() && c < 0; k++) {
+      const int r = (*rep)[k];
+      const double br = baryon_on ? ctx->h_baryon[r] : 0.0;
+      if (ctx->h_mass[r] == ctx->h_mass[s] && ctx->h_sign[r] == ctx->h_sign[s] && br == bs) c = (int)k;
+    }
+    if (c < 0) { c = (int)rep->size(); rep->push_back(s); }
+    (*class_of)[s] = c;
+  }
+}
+
 // Builds the species classes and their per-(class, pT) bin arrays shared by all spectra kernels (device pointers in `out`).
 is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out)
 {
   const int ns = ctx->ns, npT = ctx->NpT;
-  const bool baryon_on = ctx->prm.include_baryon != 0;
-  std::vector<int> class_of(ns), rep;                 // rep[c] = first species of class c
-  for (int s = 0; s < ns; s++) {
-    int c = -1;
-    const double bs = baryon_on ? ctx->h_baryon[s] : 0.0;
-    for (size_t k = 0; k < rep.size() && c < 0; k++) {
-      const int r = rep[k];
-      const double br = baryon_on ? ctx->h_baryon[r] : 0.0;
-      if (ctx->h_mass[r] == ctx->h_mass[s] && ctx->h_sign[r] == ctx->h_sign[s] && br == bs) c = (int)k;
-    }
-    if (c < 0) { c = (int)rep.size(); rep.push_back(s); }
-    class_of[s] = c;
-  }
+  std::vector<int> class_of, rep;
+  species_classes(ctx, &class_of, &rep);
   const int nc = (int)rep.size(), nb = nc * npT;
   std::vector<double> h(5 * (size_t)nb + 4 * (size_t)nc);
   for (int c = 0; c < nc; c++) {
