@@ -241,38 +241,62 @@ struct SerialReducer {
 #if defined(__CUDACC__)
 // one warp: lane = (hadron parity, node); partial sums over every second hadron, butterfly reduction -> every lane
 // holds the same total.  Not inlined: the Newton / line-search driver calls these from five places, and five inlined
-// copies of the term loops overflow the instruction cache (ncu: "no instruction" was the top stall).
-static __device__ __noinline__ void aniso_warp_sum_F(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[3])
+// copies of the term loops overflow the instruction cache (ncu: "no instruction" was the top stall).  The hadron table
+// travels as a by-value struct of pointers and the sums come back by value, so the call keeps everything in registers
+// (a by-reference struct / output array lives in local memory and cost 5 500 local loads per cell).
+#ifndef IS3D_K3_UNROLL
+#define IS3D_K3_UNROLL 1
+#endif
+constexpr int kAnisoUnroll = IS3D_K3_UNROLL;    // hadrons per loop trip of a lane (independent dependency chains)
+struct AnisoSum3 { double v[3]; };
+struct AnisoSum6 { double v[6]; };
+
+static __device__ __noinline__ AnisoSum3 aniso_warp_sum_F(AnisoHadrons h, double lambda, double aT2, double aL2)
 {
   const int lane = threadIdx.x & 31;
   const AnisoNode nd = aniso_node_F(h, lane & 15);
   const double il = 1.0 / lambda;
   double o[3] = {0.0, 0.0, 0.0};
+#pragma unroll kAnisoUnroll
   for (int n = lane >> 4; n < h.n; n += 2) aniso_F_term(h, n, nd, lambda, il, aT2, aL2, o);
+  AnisoSum3 r;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) o[k] += __shfl_xor_sync(0xffffffffu, o[k], off);
-    out[k] = o[k];
+    r.v[k] = o[k];
   }
+  return r;
 }
-static __device__ __noinline__ void aniso_warp_sum_J(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[6])
+static __device__ __noinline__ AnisoSum6 aniso_warp_sum_J(AnisoHadrons h, double lambda, double aT2, double aL2)
 {
   const int lane = threadIdx.x & 31;
   const AnisoNode nd = aniso_node_J(h, lane & 15);
   const double il = 1.0 / lambda;
   double o[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll kAnisoUnroll
   for (int n = lane >> 4; n < h.n; n += 2) aniso_J_term(h, n, nd, lambda, il, aT2, aL2, o);
+  AnisoSum6 r;
 #pragma unroll
   for (int k = 0; k < 6; k++) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) o[k] += __shfl_xor_sync(0xffffffffu, o[k], off);
-    out[k] = o[k];
+    r.v[k] = o[k];
   }
+  return r;
 }
 struct WarpReducer {
-  __device__ void sum_F(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[3]) const { aniso_warp_sum_F(h, lambda, aT2, aL2, out); }
-  __device__ void sum_J(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[6]) const { aniso_warp_sum_J(h, lambda, aT2, aL2, out); }
+  __device__ void sum_F(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[3]) const
+  {
+    const AnisoSum3 r = aniso_warp_sum_F(h, lambda, aT2, aL2);
+    out[0] = r.v[0]; out[1] = r.v[1]; out[2] = r.v[2];
+  }
+  __device__ void sum_J(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[6]) const
+  {
+    const AnisoSum6 r = aniso_warp_sum_J(h, lambda, aT2, aL2);
+#pragma unroll
+    for (int k = 0; k < 6; k++) out[k] = r.v[k];
+  }
 };
 #endif
 

@@ -31,7 +31,10 @@ __device__ void famod_store(const double p[FP_SIZE], int status, int iterations,
   }
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef IS3D_K3_MINBLOCKS
+#define IS3D_K3_MINBLOCKS 6   // occupancy beats registers here: 128 regs -> 206 ms, 80 regs -> 199 ms per step (profiles/r01_k3_sweep.txt)
+#endif
+__global__ void __launch_bounds__(128, IS3D_K3_MINBLOCKS)
 famod_setup_free_kernel(SurfaceView surf, int64_t begin, int64_t count, FamodFlags fl, AnisoHadrons h, double *__restrict__ pack,
                         int64_t stride, unsigned long long *counters)
 {
@@ -101,7 +104,7 @@ is3d_status famod_setup_pass(is3d_ctx *ctx, int64_t begin, int64_t count, double
     famod_setup_chain_kernel<<<1, 32, 0, ctx->stream>>>(ctx->surf, begin, count, fl, h, pack, stride, counters, (FamodChain *)chain);
   } else {
     int64_t warps = count;
-    int64_t max_warps = (int64_t)ctx->sm_count * 16 * 4;     // a few waves of 4-warp blocks
+    int64_t max_warps = (int64_t)ctx->sm_count * 16 * 4;     // a few waves of 4-warp blocks (cells are strided over the warps)
     if (warps > max_warps) warps = max_warps;
     unsigned blocks = (unsigned)((warps + 3) / 4);
     famod_setup_free_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->surf, begin, count, fl, h, pack, stride, counters);

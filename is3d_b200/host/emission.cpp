@@ -9,6 +9,10 @@
 #include <cstring>
 #include <utility>
 
+#include <charconv>
+#include <string>
+
+#include "host_parallel.hpp"
 #include "is3d_host.hpp"
 
 namespace is3dhost {
@@ -411,18 +415,39 @@ void EmissionFunctionArray::write_dN_dX_toFile()
 
 void EmissionFunctionArray::write_particle_list_OSC()
 {
+  // one file per event (EmissionFunction.cpp:645-678): events are independent, so they are formatted and written by all
+  // host threads (IS3D_WRITER_THREADS overrides); each row is built with std::to_chars, which prints the same correctly
+  // rounded 17 significant digits as the reference's `scientific << setprecision(16)` stream
   printf("Writing sampled particles list to OSCAR File...\n");
-  for (long e = 0; e < Nevents; e++) {
-    FILE *f = open_result("results/particle_list_osc_%d.dat", (int)e + 1);
-    fprintf(f, "n pid px py pz E m x y z t\n");
-    const auto &ev = particle_event_list[e];
-    for (size_t i = 0; i < ev.size(); i++) {
-      const Sampled_Particle &p = ev[i];
-      fprintf(f, "%d %d %.16e %.16e %.16e %.16e %.16e %.16e %.16e %.16e %.16e\n", (int)i, p.mcID, p.px, p.py, p.pz, p.E, p.mass,
-              p.x, p.y, p.z, p.t);
+  const int nt = host_threads((size_t)(Nevents > 0 ? Nevents : 1), "IS3D_WRITER_THREADS");
+  parallel_for(nt, [&](int t) {
+    std::string buf;
+    char num[64];
+    for (long e = t; e < Nevents; e += nt) {
+      const auto &ev = particle_event_list[e];
+      buf.clear();
+      buf.reserve(ev.size() * 240 + 64);
+      buf += "n pid px py pz E m x y z t\n";
+      for (size_t i = 0; i < ev.size(); i++) {
+        const Sampled_Particle &p = ev[i];
+        auto r = std::to_chars(num, num + sizeof(num), (int)i);
+        buf.append(num, r.ptr);
+        buf += ' ';
+        r = std::to_chars(num, num + sizeof(num), p.mcID);
+        buf.append(num, r.ptr);
+        const double v[9] = {p.px, p.py, p.pz, p.E, p.mass, p.x, p.y, p.z, p.t};
+        for (double x : v) {
+          buf += ' ';
+          r = std::to_chars(num, num + sizeof(num), x, std::chars_format::scientific, 16);
+          buf.append(num, r.ptr);
+        }
+        buf += '\n';
+      }
+      FILE *f = open_result("results/particle_list_osc_%d.dat", (int)e + 1);
+      fwrite(buf.data(), 1, buf.size(), f);
+      fclose(f);
     }
-    fclose(f);
-  }
+  });
 }
 
 // EmissionFunction.cpp:685-975 (six writers): normalisations kept, histograms come from the device

@@ -15,6 +15,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include "host_parallel.hpp"
 #include "is3d_host.hpp"
 
 namespace is3dhost {
@@ -96,27 +97,8 @@ struct PhaseTimer {
 
 inline bool is_space(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
 
-int ingest_threads(size_t bytes)
-{
-  unsigned hw = std::thread::hardware_concurrency();
-  if (const char *v = getenv("IS3D_READER_THREADS")) hw = (unsigned)atoi(v);
-  size_t by_size = bytes / (1 << 20) + 1;              // at least ~1 MB of text per thread
-  size_t t = hw ? hw : 1;
-  if (t > by_size) t = by_size;
-  if (t > 256) t = 256;
-  return (int)(t < 1 ? 1 : t);
-}
-
-template <class Fn>
-void parallel_for(int nthreads, Fn fn)
-{
-  if (nthreads <= 1) { fn(0); return; }
-  std::vector<std::thread> pool;
-  pool.reserve(nthreads - 1);
-  for (int t = 1; t < nthreads; t++) pool.emplace_back(fn, t);
-  fn(0);
-  for (auto &th : pool) th.join();
-}
+// at least ~1 MB of text per thread
+int ingest_threads(size_t bytes) { return host_threads(bytes / (1 << 20) + 1, "IS3D_READER_THREADS"); }
 
 // fn(i) for every row i in [0, n), rows split into contiguous blocks over the ingestion threads
 template <class Fn>
