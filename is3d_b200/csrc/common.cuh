@@ -1,8 +1,8 @@
 // Shared device/host math helpers for the sm_100a Cooper-Frye kernels.
 //
-// Everything marked IS3D_HD is plain arithmetic that also compiles on the host, so tests/hostcheck can run the
-// exact per-cell / per-momentum formulas through g++ as a development sanity check.  The product never takes
-// that route: the C ABI (api.cu) only launches the CUDA kernels.
+// Everything marked IS3D_HD is plain arithmetic that also compiles on the host: the host layer reuses the table /
+// spline helpers (dftables.cuh, gauss_thermal.cuh) for its start-up tables.  The compute entry points never take that
+// route: the C ABI (api.cu) only launches the CUDA kernels.
 #pragma once
 
 #include <cmath>
@@ -103,7 +103,7 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
   return res;
 }
 
-// host-side construction of the table (uploaded once per context; hostcheck uses it directly)
+// host-side construction of the table (uploaded once per context)
 inline void fill_exp_table(double *tab)
 {
   for (int m = 0; m < kExpTableSize; m++) tab[m] = (double)exp2l((long double)m / (long double)kExpTableSize);

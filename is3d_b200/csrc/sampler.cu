@@ -111,10 +111,12 @@ struct SamplerOut {
   unsigned long long *event_counts;   // [nevents] accepted hadrons per event (all passes)
 };
 
+// one instantiation per df_mode: the branches of the other modes would only add instruction-cache pressure
+template <int DF_MODE>
 __global__ void __launch_bounds__(128)
 sampler_hadron_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cell_global0,
                       const unsigned long long *__restrict__ offsets, unsigned long long nprop,
-                      SamplerTables st, int df_mode, int dimension, double y_cut, long nevents, uint64_t seed, HistGrid hg,
+                      SamplerTables st, int dimension, double y_cut, long nevents, uint64_t seed, HistGrid hg,
                       SamplerOut out, unsigned long long *counters)
 {
   const unsigned long long jg = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;   // proposal index in this pass
@@ -151,7 +153,7 @@ sampler_hadron_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
     }
     const double mass = st.mass[s], sign = st.sign[s], baryon = st.baryon[s];
     LrfMomentum p;
-    accept = sample_hadron(rng, pk, df_mode, mass, sign, baryon, &samples, &p);
+    accept = sample_hadron<DF_MODE>(rng, pk, mass, sign, baryon, &samples, &p);
     if (accept) {
       const double y_max = (dimension == 2) ? y_cut : 0.5;
       LabParticle q = boost_to_lab(rng, pk, p, mass, dimension, y_max);
@@ -711,9 +713,17 @@ is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
         IS3D_CUDA_TRY(ctx, cudaMemsetAsync(nacc_dev, 0, sizeof(unsigned long long), ctx->stream));
         out.rec = (is3d_particle *)rec; out.key = (unsigned long long *)key;
       }
-      sampler_hadron_kernel<<<(unsigned)((nprop + 127) / 128), 128, 0, ctx->stream>>>(
-          (double *)pack, stride, count, ctx->global_offset + begin, (unsigned long long *)offsets, nprop, ss.st, p.df_mode,
-          p.dimension, p.y_cut, (long)nevents, (uint64_t)p.sampler_seed, hg, out, (unsigned long long *)counters);
+#define IS3D_HADRONS(M) sampler_hadron_kernel<M><<<(unsigned)((nprop + 127) / 128), 128, 0, ctx->stream>>>( \
+          (double *)pack, stride, count, ctx->global_offset + begin, (unsigned long long *)offsets, nprop, ss.st, \
+          p.dimension, p.y_cut, (long)nevents, (uint64_t)p.sampler_seed, hg, out, (unsigned long long *)counters)
+      switch (p.df_mode) {
+        case 1: IS3D_HADRONS(1); break;
+        case 2: IS3D_HADRONS(2); break;
+        case 3: IS3D_HADRONS(3); break;
+        case 4: IS3D_HADRONS(4); break;
+        default: IS3D_HADRONS(5); break;
+      }
+#undef IS3D_HADRONS
       IS3D_CUDA_TRY(ctx, cudaGetLastError());
       launches++;
       if (lists) {

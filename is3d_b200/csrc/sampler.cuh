@@ -37,7 +37,13 @@ struct Philox {
     ctr[0] = (uint32_t)cell; ctr[1] = (uint32_t)(cell >> 32); ctr[2] = hadron; ctr[3] = 0;
     have = 0;
   }
-  IS3D_HD void generate()
+  // not inlined on the device: ~25 call sites of canonical() would each carry the ten rounds, and the sampler kernel is
+  // instruction-cache bound (ncu: 15 "no instruction" stall cycles per issued instruction before this)
+#if defined(__CUDACC__)
+  __host__ __device__ __noinline__ void generate()
+#else
+  void generate()
+#endif
   {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
 #pragma unroll
@@ -236,7 +242,12 @@ struct LrfMomentum { double E, px, py, pz, feq; bool ok; };
 constexpr int kMaxRejectionIterations = 1000000;   // acceptance is O(0.5); only NaN inputs (e.g. T_mod <= 0) get here
 
 // thermal momentum in the local rest frame by rejection (:243-405); counts proposals in *samples
-IS3D_HD LrfMomentum sample_momentum(Philox &rng, long *samples, double mass, double sign, double T, double chem)
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+LrfMomentum sample_momentum(Philox &rng, long *samples, double mass, double sign, double T, double chem)
 {
   double mbar = mass / T, mbar_squared = mbar * mbar;
   double pbar = 0.0, Ebar = mbar, phi_over_2pi = 0.0, costheta = 1.0, feq = 0.0;
@@ -302,9 +313,8 @@ IS3D_HD LrfMomentum sample_momentum(Philox &rng, long *samples, double mass, dou
 
 // One proposed hadron of species (mass, sign, baryon) in the cell described by `pk`: momentum, viscous and flux
 // weights, acceptance (:929-1059).  Returns true when accepted; pLRF holds the (rescaled) rest-frame momentum.
-template <class PackFn>
-IS3D_HD bool sample_hadron(Philox &rng, PackFn pk, int df_mode, double mass, double sign, double baryon, long *samples,
-                           LrfMomentum *out)
+template <int df_mode, class PackFn>
+IS3D_HD bool sample_hadron(Philox &rng, PackFn pk, double mass, double sign, double baryon, long *samples, LrfMomentum *out)
 {
   const double mass_squared = mass * mass;
   const bool breakdown = pk(SP_BREAKDOWN) != 0.0;

@@ -1,5 +1,5 @@
 // Host-pointer view of Deltaf_Data in the layout of csrc/dftables.cuh (used for the one evaluation at the surface
-// averages, and by tests/hostcheck).
+// averages).
 #pragma once
 
 #include <vector>
