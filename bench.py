@@ -353,6 +353,11 @@ def run_ours(args) -> None:
         except OSError:
             pass
         bytes_alg = cells * 25 * 8.0 + total * 8.0
+        # DRAM bytes of ONE df_spectra_kernel launch from the ncu --set full capture of this command at the default size
+        # (profiles/r01_summary.md: 356.3 MB read + 31.8 MB written); null for any other configuration
+        default_cfg = (args.df_mode == 2 and cells == 1_250_000)
+        traffic = 388.1e6 if default_cfg else None
+        traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_summary.md" if default_cfg else None
         line = {
             "metric": "Cooper-Frye cell*species*momentum evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -367,7 +372,9 @@ def run_ours(args) -> None:
                     "d2h_bytes_per_step": int(total * 8)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": None, "kernel": "df_spectra_kernel" if args.df_mode <= 2 else "feqmod_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "df_spectra_kernel" if args.df_mode <= 2 else "feqmod_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
+                         "fp64_pipe_active_pct_ncu": 71.1 if args.df_mode == 2 else None,
                          "flops_per_eval_algorithmic": F_ALG[args.df_mode],
                          "peak_source": "DFMA micro-benchmark run live by is3d_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
                          "hbm_gbs_algorithmic": bytes_alg / kern_s / 1e9, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},

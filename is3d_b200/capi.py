@@ -282,6 +282,13 @@ class HostSession:
         self.host.is3d_host_pdg(self.h, _ptr(out))
         return out
 
+    def chosen(self) -> np.ndarray:
+        """MC ids of the chosen particles in output order."""
+        n = self.host.is3d_host_chosen(self.h, None)
+        out = np.zeros(n, dtype=np.int32)
+        self.host.is3d_host_chosen(self.h, out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out
+
     def ptb(self):
         x, l2, z = np.empty(301), np.empty(301), np.empty(301)
         xmax = C.c_double()
