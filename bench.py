@@ -255,12 +255,36 @@ def run_ours(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    cells = args.cells_per_gpu
-    surf = synthetic.s3d(cells, seed=2024 + rank, baryon=True)         # rank's shard of the surface
     params = bench_params(args.df_mode)
     root = tempfile.mkdtemp(prefix=f"is3d_bench_r{rank}_")
     workdir.make_workdir(root, params, chosen="smash")
     h = HostSession(root)
+    try:
+        line = _measure_ours(args, h, world, rank, local)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    finally:
+        # tear-down order matters: every torch tensor that touched the context's stream or NCCL must be released before
+        # the process group and the stream go away (a tensor freed afterwards aborts the rank with "context is destroyed")
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        h.close()
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def _measure_ours(args, h, world: int, rank: int, local: int):
+    import torch
+    import torch.distributed as dist
+
+    from is3d_b200 import shard
+
+    cells = args.cells_per_gpu
+    surf = synthetic.s3d(cells, seed=2024 + rank, baryon=True)         # rank's shard of the surface
     # thermodynamic averages (only the sampler uses them) from a small prefix: the host loop is O(cells) python-free C++
     h.set_surface({k: v[:1000] for k, v in surf.items()})
     shard.set_global_thermo_averages(h)
@@ -386,11 +410,8 @@ def run_ours(args) -> None:
             line["cpu_baseline"] = cpu_baseline(args)
             if sampler is not None:
                 line["sampler"]["cpu_baseline"] = sampler_cpu_baseline(args)
-        print(json.dumps(line))
-    h.close()
-    shutil.rmtree(root, ignore_errors=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def main():
