@@ -269,6 +269,15 @@ void EmissionFunctionArray::calculate_spectra(std::vector<std::vector<Sampled_Pa
 }
 
 // ---- writers ---------------------------------------------------------------------------------------------------
+// one result file set per species: the species are independent, so the writers run on all host threads
+// (IS3D_WRITER_THREADS overrides); every file's content is what the serial loop writes
+template <class Fn>
+static void parallel_species(int ns, Fn fn)
+{
+  const int nt = host_threads((size_t)(ns > 0 ? ns : 1), "IS3D_WRITER_THREADS");
+  parallel_for(nt, [&](int t) { for (int is = t; is < ns; is += nt) fn(is); });
+}
+
 static FILE *open_result(const char *fmt, int id, const char *mode = "w")
 {
   char name[300];
@@ -283,7 +292,7 @@ static FILE *open_result(const char *fmt, int id, const char *mode = "w")
 void EmissionFunctionArray::write_dN_pTdpTdphidy_toFile()
 {
   printf("Writing thermal spectra to file...\n");
-  for (int is = 0; is < number_of_chosen_particles; is++) {
+  parallel_species(number_of_chosen_particles, [&](int is) {
     FILE *f = open_result("results/continuous/dN_pTdpTdphidy_%d.dat", MCID[is]);
     fprintf(f, "y\tphip\tpT\tdN_pTdpTdphidy\n");
     for (long iy = 0; iy < y_tab_length; iy++) {
@@ -296,13 +305,13 @@ void EmissionFunctionArray::write_dN_pTdpTdphidy_toFile()
       }
     }
     fclose(f);
-  }
+  });
 }
 
 void EmissionFunctionArray::write_dN_dphidy_toFile()
 {
   printf("Writing thermal dN_dphidy to file...\n");
-  for (int is = 0; is < number_of_chosen_particles; is++) {
+  parallel_species(number_of_chosen_particles, [&](int is) {
     FILE *f = open_result("results/continuous/dN_dphidy_%d.dat", MCID[is]);
     for (long iy = 0; iy < y_tab_length; iy++) {
       double y = (DIMENSION == 3) ? y_tab->get(1, iy + 1) : 0.0;
@@ -314,13 +323,13 @@ void EmissionFunctionArray::write_dN_dphidy_toFile()
       if (iy < y_tab_length - 1) fprintf(f, "\n");
     }
     fclose(f);
-  }
+  });
 }
 
 void EmissionFunctionArray::write_dN_twopipTdpTdy_toFile()
 {
   printf("Writing thermal dN_twopipTdpTdy to file...\n");
-  for (int is = 0; is < number_of_chosen_particles; is++) {
+  parallel_species(number_of_chosen_particles, [&](int is) {
     FILE *f = open_result("results/continuous/dN_2pipTdpTdy_%d.dat", MCID[is]);
     for (long iy = 0; iy < y_tab_length; iy++) {
       double y = (DIMENSION == 3) ? y_tab->get(1, iy + 1) : 0.0;
@@ -332,13 +341,13 @@ void EmissionFunctionArray::write_dN_twopipTdpTdy_toFile()
       if (iy < y_tab_length - 1) fprintf(f, "\n");
     }
     fclose(f);
-  }
+  });
 }
 
 void EmissionFunctionArray::write_dN_dy_toFile()
 {
   printf("Writing thermal dN_dy to file...\n");
-  for (int is = 0; is < number_of_chosen_particles; is++) {
+  parallel_species(number_of_chosen_particles, [&](int is) {
     FILE *f = open_result("results/continuous/dN_dy_%d.dat", MCID[is]);
     for (long iy = 0; iy < y_tab_length; iy++) {
       double y = (DIMENSION == 3) ? y_tab->get(1, iy + 1) : 0.0;
@@ -349,14 +358,14 @@ void EmissionFunctionArray::write_dN_dy_toFile()
       fprintf(f, "%5.8g\t%.8g\n", y, sum);
     }
     fclose(f);
-  }
+  });
 }
 
 void EmissionFunctionArray::write_continuous_vn_toFile()
 {
   printf("Writing continuous vn(pT,y) to file (for testing vn's)...\n");
   const int k_max = 7;
-  for (int is = 0; is < number_of_chosen_particles; is++) {
+  parallel_species(number_of_chosen_particles, [&](int is) {
     FILE *f = open_result("results/continuous/vn_%d.dat", MCID[is]);
     for (long iy = 0; iy < y_tab_length; iy++) {
       double y = (DIMENSION == 3) ? y_tab->get(1, iy + 1) : 0.0;
@@ -382,7 +391,7 @@ void EmissionFunctionArray::write_continuous_vn_toFile()
       fprintf(f, "\n");
     }
     fclose(f);
-  }
+  });
 }
 
 // SpacetimeDistribution.cpp:448-490: bin mid-point and the histogram normalised by tau dtau / 2 pi r dr / dphi,

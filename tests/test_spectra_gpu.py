@@ -113,3 +113,43 @@ def test_out_of_table_cell_is_an_error(libs, tmp_path):
         h.abi_set_surface(bad)
         with pytest.raises(Is3dError, match="status 3"):
             h.abi_spectra()
+
+
+def test_host_writers_file_layout(libs, tmp_path):
+    """operation 1 through the host layer (EmissionFunctionArray::calculate_spectra + the five writers, reference
+    EmissionFunction.cpp:406-558, :804-878; layouts of SURVEY.md appendix C): every file is re-derived from the in-memory
+    spectra -- header, loop order iy -> iphi -> ipT, blank-line structure, quadrature sums, 9 significant digits."""
+    name = "s2d_m1_phi48"                                  # 48 phi points, 2+1d: y = 0 single row
+    case = cases.SPECTRA_CASES[name]
+    surf, ref = harness.load_golden(name)
+    with harness.open_session(str(tmp_path), case, surf) as h:
+        h.run()
+        spec = h.spectra()                                 # (Ns, NpT, Nphi, Ny)
+        mcid = h.chosen()
+    harness.assert_spectra_close(spec, ref, what="host run")
+    tab = lambda f: np.loadtxt(tmp_path / "tables" / "momentum" / f, ndmin=2)  # noqa: E731
+    pT, phi = tab("pT_table.dat"), tab("phi_table.dat")
+    ns, npT, nphi, ny = spec.shape
+    assert (nphi, ny) == (48, 1)
+    out = tmp_path / "results" / "continuous"
+    for s, m in enumerate(mcid):
+        lines = open(out / f"dN_pTdpTdphidy_{m}.dat").read().split("\n")
+        assert lines[0] == "y\tphip\tpT\tdN_pTdpTdphidy"
+        body = lines[1:]
+        assert len(body) == ny * nphi * (npT + 1) + 1 and body[npT] == "" and body[-1] == ""     # blank line after each phi block
+        rows = np.array([[float(v) for v in l.split("\t")] for l in body if l])
+        want = np.transpose(spec[s], (2, 1, 0)).reshape(-1)                                      # iy -> iphi -> ipT
+        np.testing.assert_allclose(rows[:, 3], want, rtol=1e-8, atol=1e-300)
+        np.testing.assert_allclose(rows[:npT, 2], pT[:, 0], rtol=1e-8)
+        np.testing.assert_allclose(rows[::npT, 1][:nphi], phi[:, 0], rtol=1e-8)
+        d = np.loadtxt(out / f"dN_2pipTdpTdy_{m}.dat", ndmin=2)
+        np.testing.assert_allclose(d[:, 2], (spec[s, :, :, 0] * phi[:, 1]).sum(axis=1) / (2 * np.pi), rtol=1e-8)
+        d = np.loadtxt(out / f"dN_dphidy_{m}.dat", ndmin=2)
+        np.testing.assert_allclose(d[:, 2], (spec[s, :, :, 0] * pT[:, 1][:, None]).sum(axis=0), rtol=1e-8)
+        d = np.loadtxt(out / f"dN_dy_{m}.dat", ndmin=2)
+        np.testing.assert_allclose(d[0, 1], (spec[s, :, :, 0] * pT[:, 1][:, None] * phi[:, 1][None, :]).sum(), rtol=1e-7)
+        d = np.loadtxt(out / f"vn_{m}.dat", ndmin=2)
+        assert d.shape == (npT, 9)
+        w = spec[s, :, :, 0] * phi[:, 1]
+        v2 = np.abs((w * np.exp(2j * phi[:, 0])).sum(axis=1)) / w.sum(axis=1)
+        np.testing.assert_allclose(d[:, 3], v2, rtol=1e-6, atol=1e-12)
