@@ -136,3 +136,28 @@ def write_mode6(path: str, s: dict, baryon: bool = False) -> None:
     if baryon:
         cols += [s["nB"], z, s["Vx"], s["Vy"], tau * s["Vn"]]
     np.savetxt(path, np.column_stack(cols), fmt="%.17e")
+
+
+def write_mode5(path: str, s: dict, baryon: bool = False, seed: int = 0) -> np.ndarray:
+    """mode 1 columns followed by the six thermal-vorticity components wtx wty wtn wxy wxn wyn (reference
+    src/cpp/readindata.cpp:299-307).  Returns the vorticity block that was written."""
+    cols = [s["tau"], s["x"], s["y"], s["eta"], s["dat"], s["dax"], s["day"], s["dan"], s["ux"], s["uy"], s["un"],
+            s["E"] / HBARC, s["T"] / HBARC, s["P"] / HBARC, s["pixx"] / HBARC, s["pixy"] / HBARC, s["pixn"] / HBARC,
+            s["piyy"] / HBARC, s["piyn"] / HBARC, s["bulkPi"] / HBARC]
+    if baryon:
+        cols += [s["muB"] / HBARC, s["nB"], s["Vx"], s["Vy"], s["Vn"]]
+    w = np.random.default_rng(seed).uniform(-0.05, 0.05, (len(s["tau"]), 6))
+    np.savetxt(path, np.column_stack(cols + [w[:, k] for k in range(6)]), fmt="%.17e")
+    return w
+
+
+def write_mode7(path: str, s: dict) -> None:
+    """surface.dat in the HIC-EventGen layout (2+1d, GeV units; reference src/cpp/readindata.cpp:589-690):
+    `t x y n ds_t/t ds_x/t ds_y/t ds_n/t v^x v^y t.v^n pi^tt pi^tx pi^ty t.pi^tn pi^xx pi^xy t.pi^xn pi^yy t.pi^yn
+    t2.pi^nn Pi T E P muB`."""
+    tau = s["tau"]
+    ut = np.sqrt(1.0 + s["ux"] ** 2 + s["uy"] ** 2)
+    z = np.zeros_like(tau)
+    cols = [tau, s["x"], s["y"], z, s["dat"] / tau, s["dax"] / tau, s["day"] / tau, z, s["ux"] / ut, s["uy"] / ut, z,
+            z, z, z, z, s["pixx"], s["pixy"], z, s["piyy"], z, z, s["bulkPi"], s["T"], s["E"], s["P"], z]
+    np.savetxt(path, np.column_stack(cols), fmt="%.17e")

@@ -8,6 +8,7 @@
 // reference's text writers truncate to 9 digits:
 //   ref_dump/spectra.bin      EmissionFunctionArray::dN_pTdpTdphidy (EmissionFunction.h:114)
 //   ref_dump/particles.bin    particle_event_list (EmissionFunction.h:121)
+//   ref_dump/surface.bin      the freezeout surface as parsed by the reference's reader (IS3D_REF_SURFACE_ONLY=1 stops there)
 //   ref_dump/species.bin      per-PDG-entry (mcid, mass, gspin, baryon, sign, neq, dn_bulk, dn_diff)
 //   ref_dump/jonah.bin        PTB tables bulkPi/P, lambda^2, z (DeltafData.h:72-79), include_baryon = 0 only
 //   ref_dump/timing.txt       seconds spent inside calculate_spectra (same region as the reference's
@@ -45,6 +46,20 @@ int main(int argc, char **argv)
   FO_surf *surf_ptr = new FO_surf[FO_length];
   freeze_out_data.read_freezeout_surface(surf_ptr);
   printf("Number of freezeout cells = %ld\n", FO_length);
+  {
+    // the surface exactly as the reference's readers leave it (FO_surf, readindata.h:79-91): 31 doubles per cell
+    FILE *f = fopen("ref_dump/surface.bin", "wb");
+    wr(f, &FO_length, sizeof(long));
+    for(long i = 0; i < FO_length; i++)
+    {
+      const FO_surf &c = surf_ptr[i];
+      double rec[31] = {c.tau, c.x, c.y, c.eta, c.dat, c.dax, c.day, c.dan, c.ux, c.uy, c.un, c.E, c.T, c.P, c.pixx, c.pixy, c.pixn,
+                        c.piyy, c.piyn, c.bulkPi, c.muB, c.nB, c.Vx, c.Vy, c.Vn, c.wtx, c.wty, c.wtn, c.wxy, c.wxn, c.wyn};
+      wr(f, rec, sizeof(rec));
+    }
+    fclose(f);
+    if(getenv("IS3D_REF_SURFACE_ONLY")) { fflush(stdout); _Exit(0); }
+  }
 
   particle_info *particle_data = new particle_info[Maxparticle];
   PDG_Data pdg(paraRdr);

@@ -38,6 +38,19 @@ def run_ref(root: str, surface: dict, params: dict, chosen: str = "pikp", baryon
     return read_dumps(root)
 
 
+def ref_surface(root: str, timeout: float = 600.0) -> np.ndarray:
+    """Run only the reference's surface reader in `root` (parameters and input/surface.dat already in place) and return the
+    parsed cells as an (n, 31) array in FO_surf field order (25 hot-path columns + 6 vorticity components)."""
+    env = dict(os.environ, IS3D_REF_SURFACE_ONLY="1")
+    with open(os.path.join(root, "ref_stdout.log"), "w") as log:
+        r = subprocess.run([REF_BIN], cwd=root, stdout=log, stderr=subprocess.STDOUT, env=env, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"reference reader exited {r.returncode}:\n" + open(os.path.join(root, "ref_stdout.log")).read()[-2000:])
+    raw = open(os.path.join(root, "ref_dump", "surface.bin"), "rb").read()
+    n = struct.unpack("l", raw[:8])[0]
+    return np.frombuffer(raw[8:], dtype=np.float64).reshape(n, 31).copy()
+
+
 def read_dumps(root: str) -> dict:
     out = {}
     d = os.path.join(root, "ref_dump")

@@ -160,3 +160,41 @@ def test_reader_uneven_rows_follow_the_stream(libs, tmp_path, monkeypatch):
     np.testing.assert_array_equal(got[1][:n], want_tau[:n])
     assert got[1][n] == 0.0                                               # the stream ran dry before the extra cell
     np.testing.assert_array_equal(got[6], got[1])
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("mode,dimension,baryon", [(1, 3, 1), (5, 3, 0), (5, 3, 1), (6, 3, 0), (6, 3, 1), (6, 2, 0), (7, 2, 0)])
+def test_surface_readers_match_reference(libs, tmp_path, mode, dimension, baryon):
+    """Column contracts and unit conversions of the four surface.dat layouts (reference
+    readindata.cpp:167-729): every cell field and the thermodynamic-average side file equal what the unmodified
+    reference's reader produces from the same text, bit for bit."""
+    n = 257
+    s = synthetic.s3d(n, seed=90 + mode, baryon=bool(baryon), dimension=dimension)
+    params = dict(operation=1, mode=mode, hrg_eos=2, dimension=dimension, df_mode=2, include_baryon=baryon,
+                  include_baryondiff_deltaf=baryon)
+    roots = {}
+    for who in ("ref", "mine"):
+        root = workdir.make_workdir(str(tmp_path / who), params, chosen="pikp")
+        p = os.path.join(root, "input", "surface.dat")
+        if mode == 1:
+            synthetic.write_mode1(p, s, baryon=bool(baryon))
+        elif mode == 5:
+            synthetic.write_mode5(p, s, baryon=bool(baryon), seed=3)
+        elif mode == 6:
+            synthetic.write_mode6(p, s, baryon=bool(baryon))
+        else:
+            synthetic.write_mode7(p, s)
+        roots[who] = root
+    ref = refrun.ref_surface(roots["ref"])
+    with HostSession(roots["mine"]) as h:
+        assert h.read_surface() == n
+        mine = np.stack([h.surface_column(k) for k in range(25)], axis=1)
+    assert ref.shape == (n, 31)
+    # without baryon columns the reference leaves muB, nB, V^mu of its `new FO_surf[]` uninitialised (modes 1, 5); the
+    # MUSIC and HIC-EventGen layouts always carry muB
+    ncmp = 25 if baryon else (21 if mode in (6, 7) else 20)
+    for k, name in enumerate(synthetic.SOA_COLUMNS[:ncmp]):
+        np.testing.assert_array_equal(mine[:, k], ref[:, k], err_msg=f"mode {mode}: {name}")
+    a = open(os.path.join(roots["ref"], "tables", "thermodynamic", "average_thermodynamic_quantities.dat")).read()
+    b = open(os.path.join(roots["mine"], "tables", "thermodynamic", "average_thermodynamic_quantities.dat")).read()
+    assert a == b
