@@ -54,20 +54,32 @@ IS3D_HD bool not_finite(double x) { return !(fabs(x) <= 1.7976931348623157e308);
 // 7 FP64 instructions: 3 reduction + 3 polynomial + 1 scaling (the first version, a degree-11 Horner form with FP64
 // clamps, needed 19).  Errors: truncation r^4/24 < 5.5e-16; the reduction uses ln2/1024 rounded to double in ONE fma, so
 // r carries |x| 1.1e-16 (3e-15 of e^x at x = 30, where the Bose/Fermi factor is already 1e-13; the continuous paths
-// promise 1e-10).  The exponent is patched by an integer add on the high word.  Range: x >= 708 (beyond the double range
-// of e^x) is caught on the integer pipe from the high word of x and returns 1e300, which 1/(e^x + s) turns into the
-// reference's 0; x <= -708 cannot occur (x = (E - b mu_B)/T >= -mu_B/T > -10).
+// promise 1e-10).  The exponent is patched by an integer multiply-add on the high word.  Range: the high word of x is
+// clamped (one integer min) so that x never exceeds 680: beyond that e^x is "huge" (>= 2e295) and 1/(e^x + s) is the
+// reference's 0 to more than 200 decades; the margin to the double range lets callers multiply e^x by E/T before
+// taking one reciprocal.  x <= -708 cannot occur (x = (E - b mu_B)/T >= -mu_B/T > -10); NaN input behaves like 680.
 // tools/gen_exp_table.py derives the constants and scans the error of the whole construction in 60-digit arithmetic.
 constexpr int kExpTableBits = 10;
 constexpr int kExpTableSize = 1 << kExpTableBits;
 
 IS3D_HD int hi_word(double d) { return (int)(as_int64(d) >> 32); }
-IS3D_HD double add_to_hi_word(double d, int add)
+// d with (k << 20) added to its high word, i.e. d * 2^k
+IS3D_HD double scale_by_pow2(double d, int k)
 {
 #if defined(__CUDA_ARCH__)
-  return __hiloint2double(__double2hiint(d) + add, __double2loint(d));
+  return __hiloint2double(k * 0x100000 + __double2hiint(d), __double2loint(d));     // one IMAD
 #else
-  return as_double(as_int64(d) + ((int64_t)add << 32));
+  return as_double(as_int64(d) + ((int64_t)k << 52));
+#endif
+}
+// x with its high word limited to that of 680.0 (signed compare: negative x is never touched)
+IS3D_HD double clamp_hi_word_680(double x)
+{
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(min(__double2hiint(x), 0x40854000), __double2loint(x));
+#else
+  const int hx = hi_word(x);
+  return hx > 0x40854000 ? as_double(((int64_t)0x40854000 << 32) | (as_int64(x) & 0xffffffffll)) : x;
 #endif
 }
 
@@ -85,6 +97,7 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
   const double kInv = 1477.3197218702985, kStep = -6.769015435155716e-04, kSixth = 1.6666666666666666e-01;
 #endif
   const double kMagic = 6755399441055744.0;          // 1.5 * 2^52: rounds to nearest integer in the low mantissa bits
+  x = clamp_hi_word_680(x);
   double t = fma(x, kInv, kMagic);                   // 1024 / ln2
   const int k = (int)as_int64(t);                    // low word of t = the integer (two's complement), |k| < 2^21 here
   t -= kMagic;
@@ -98,9 +111,7 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
   const double T = tab[k & (kExpTableSize - 1)];
 #endif
   const double v = fma(T, q, T);
-  double res = add_to_hi_word(v, (k >> kExpTableBits) << 20);
-  if (hi_word(x) >= 0x40862000) res = 1e300;         // x >= 708 (signed compare: negative x never matches)
-  return res;
+  return scale_by_pow2(v, k >> kExpTableBits);
 }
 
 // host-side construction of the table (uploaded once per context)

@@ -147,7 +147,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
             for (int ipT = 0; ipT < g.NpT; ipT++) {
               const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
               const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-              double v = pds * df_distribution<2, BARYON, REGULATE>(it, df_share<BARYON>(it, bn.pT, bn.pT2), bn.b, exptab);
+              double v = pds * df_distribution<2, BARYON, REGULATE, true>(it, df_share<BARYON>(it, bn.pT, bn.pT2), bn.b, exptab);
               if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
               acc += v;
             }

@@ -93,11 +93,14 @@ IS3D_HD int df_setup_cell(const Cell &c, const DfTables &tb, const DfFlags &fl, 
 }
 
 // item constants: one (cell, eta-node) seen from a fixed (y, phi)
+// Field order = read order of the momentum loop, so that the slots a kernel variant does not need sit at the end of
+// the struct and cost no LDS.128: KX is the bulk coefficient the mode multiplies by xE (mode 1: K2, mode 2: K0); the
+// other one is folded into q1 / q3 (see df_make_item); pad is read by the PTB fallback only.
 struct alignas(16) DfItem {
   double aT, bT, c1, d1;
-  double q1, q2, q3, K0;       // q1, q3 carry the bulk m^2 term (see df_make_item)
-  double K1, K2, alphaB, v1;
-  double v2, G0, G1, pad;
+  double q1, q2, q3, KX;
+  double K1, alphaB, v1, v2;
+  double G0, G1, pad, unused_;
 };
 
 // pk(k) returns pack entry k of this cell.  sh/ch = sinh, cosh of (y - eta); w = eta quadrature weight (1 in 3+1d).
@@ -112,8 +115,9 @@ IS3D_HD DfItem df_make_item(PackFn pk, int mode, double sh, double ch, double cp
   it.bT = cphi * pk(DP_UXT) + sphi * pk(DP_UYT);
   it.c1 = w * (ch * pk(DP_DAT) + sh * pk(DP_DANT));
   it.d1 = w * (cphi * pk(DP_DAX) + sphi * pk(DP_DAY));
-  it.K0 = pk(DP_K0); it.K1 = pk(DP_K1); it.K2 = pk(DP_K2);
-  const double fold = (mode == 1) ? it.K0 : -it.K2;
+  it.K1 = pk(DP_K1);
+  it.KX = (mode == 1) ? pk(DP_K2) : pk(DP_K0);
+  const double fold = (mode == 1) ? pk(DP_K0) : -pk(DP_K2);
   it.q1 = ch * ch * pk(DP_PITT) + sh * sh * pk(DP_T2PINN) - 2.0 * ch * sh * pk(DP_TPITN) + fold;
   it.q2 = 2.0 * (sh * (pk(DP_TPIXN) * cphi + pk(DP_TPIYN) * sphi) - ch * (pk(DP_PITX) * cphi + pk(DP_PITY) * sphi));
   it.q3 = pk(DP_PIXX) * cphi * cphi + pk(DP_PIYY) * sphi * sphi + 2.0 * pk(DP_PIXY) * cphi * sphi - fold;
@@ -121,7 +125,7 @@ IS3D_HD DfItem df_make_item(PackFn pk, int mode, double sh, double ch, double cp
   it.v1 = pk(DP_VT) * ch - pk(DP_TVN) * sh;
   it.v2 = pk(DP_VX) * cphi + pk(DP_VY) * sphi;
   it.G0 = pk(DP_G0); it.G1 = pk(DP_G1);
-  it.pad = 0.0;
+  it.pad = 0.0; it.unused_ = 0.0;
   return it;
 }
 
@@ -145,18 +149,29 @@ IS3D_HD DfShared df_share(const DfItem &it, double pT, double pT2)
 }
 
 // The distribution feq (1 + df) at one momentum (MomentumSpectra.cpp:317-359)
-template <int MODE, bool BARYON, bool REGULATE>
+// PAD: the item's additive term outside feqbar (PTB fallback only: delta_z - 3 delta_lambda); off = the slot is never read
+template <int MODE, bool BARYON, bool REGULATE, bool PAD = false>
 IS3D_HD double df_distribution(const DfItem &it, const DfShared &s, const DfBin &b, const double *__restrict__ exptab)
 {
   double xE = fma(b.mT, it.aT, -s.pb);
   double x = xE;
   if (BARYON) x = fma(-b.baryon, it.alphaB, xE);
-  double feq = fast_rcp(fast_exp(x, exptab) + b.sign);
+  const double q = fast_exp(x, exptab) + b.sign;                   // e^x + sign
+  double feq, rxE = 0.0;
+  if (MODE == 1) {
+    feq = fast_rcp(q);
+  } else {
+    // df_mode 2 also needs 1/xE: one reciprocal of the product serves both (e^x <= 2.1e295 by fast_exp's clamp, so the
+    // product stays finite for any xE a surface can produce)
+    const double y = fast_rcp(q * xE);
+    feq = y * xE;
+    rxE = y * q;
+  }
   double feqbar = fma(-b.sign, feq, 1.0);
   double pipp = fma(b.mT2, it.q1, fma(b.mT, s.pq2, s.pq3));      // shear + the folded bulk m^2 term
   double dfv;
   if (MODE == 1) {
-    double lin = it.K2 * xE;                         // (K1 b + K2 xE)
+    double lin = it.KX * xE;                         // (K1 b + K2 xE)
     if (BARYON) lin = fma(it.K1, b.baryon, lin);
     dfv = fma(lin, xE, pipp);
     if (BARYON) {
@@ -164,25 +179,25 @@ IS3D_HD double df_distribution(const DfItem &it, const DfShared &s, const DfBin 
       dfv = fma(fma(it.G1, xE, it.G0 * b.baryon), Vp, dfv);
     }
   } else {
-    double r = fast_rcp(xE);
-    dfv = fma(pipp, r, it.K0 * xE);
+    const double r = rxE;
+    dfv = fma(pipp, r, it.KX * xE);
     if (BARYON) {
       dfv = fma(it.K1, b.baryon, dfv);
       double Vp = fma(b.mT, it.v1, -s.pv);
       dfv = fma(fma(-it.G1 * b.baryon, r, it.G0), Vp, dfv);
     }
   }
-  double df = fma(feqbar, dfv, it.pad);   // pad = 0 except for the PTB fallback's additive delta_z - 3 delta_lambda
+  double df = PAD ? fma(feqbar, dfv, it.pad) : feqbar * dfv;
   if (REGULATE) df = fmax(-1.0, fmin(df, 1.0));
   return fma(feq, df, feq);
 }
 
 // One integrand evaluation: returns w * p.dsigma * feq (1 + df)   (MomentumSpectra.cpp:304-361)
-template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, bool PAD = false>
 IS3D_HD double df_eval(const DfItem &it, const DfShared &s, const DfBin &b, const double *__restrict__ exptab)
 {
   double pds = fma(b.mT, it.c1, s.pd);
-  double contrib = pds * df_distribution<MODE, BARYON, REGULATE>(it, s, b, exptab);
+  double contrib = pds * df_distribution<MODE, BARYON, REGULATE, PAD>(it, s, b, exptab);
   if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
   return contrib;
 }

@@ -216,7 +216,7 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
           const DfShared sh = df_share<BARYON>(it, pT, pT2);
 #pragma unroll
           for (int r = 0; r < R; r++) {
-            double v = df_eval<2, BARYON, REGULATE, OUTFLOW>(it, sh, bin[r], exptab);
+            double v = df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, bin[r], exptab);
             if (SPECIES_RENORM) v = (rn[r] != 0.0) ? v : 0.0;   // NaN renorm: the reference skips the species (:828-832)
             acc[r] += v;
           }
