@@ -8,6 +8,7 @@
 
 #include "../csrc/dftables.cuh"
 #include "../csrc/gauss_thermal.cuh"
+#include "host_parallel.hpp"
 #include "is3d_host.hpp"
 #include "host_dfview.hpp"
 
@@ -71,25 +72,36 @@ void Deltaf_Data::compute_jonah_coefficients(const std::vector<particle_info> &p
     for (int k = 0; k < pts; k++) sum += weight2[k] * fn(root2[k], mbar, lambda, sign);
     return sum;
   };
-  for (int i = 0; i < jonah_points; i++) {
-    double lambda = lambda_min + (double)i * delta_lambda;
-    double E = 0.0, P = 0.0, E_mod = 0.0, P_mod = 0.0;
-    for (const particle_info &p : particle_data) {
-      double degeneracy = (double)p.gspin, mass = p.mass, sign = (double)p.sign;
-      double mbar = mass / T;
-      if (mass == 0.0) continue;                          // photon skipped (:266)
-      E += degeneracy * gauss1d(is3d::E_mod_int, mbar, 0.0, sign);
-      P += (1.0 / 3.0) * degeneracy * gauss1d(is3d::P_mod_int, mbar, 0.0, sign);
-      E_mod += degeneracy * gauss1d(is3d::E_mod_int, mbar, lambda, sign);
-      P_mod += (1.0 / 3.0) * degeneracy * gauss1d(is3d::P_mod_int, mbar, lambda, sign);
-    }
-    double z = E / E_mod;
-    double bulkPi_over_Peq = (P_mod / P) * z - 1.0;
-    lambda_squared_array[i] = lambda * lambda;
-    z_array[i] = z;
-    bulkPi_over_Peq_array[i] = bulkPi_over_Peq;
-    bulkPi_over_Peq_max = fmax(bulkPi_over_Peq_max, bulkPi_over_Peq);
+  // The reference recomputes the lambda = 0 sums E, P inside the node loop (same value every time); here they are taken
+  // once, and the 301 nodes -- independent O(N_pdg x 64) Gauss-Laguerre sums each -- are spread over the host threads
+  // (the visible serial prefix of a run).  Every node's arithmetic is unchanged.
+  double E = 0.0, P = 0.0;
+  for (const particle_info &p : particle_data) {
+    double degeneracy = (double)p.gspin, mass = p.mass, sign = (double)p.sign;
+    double mbar = mass / T;
+    if (mass == 0.0) continue;                          // photon skipped (:266)
+    E += degeneracy * gauss1d(is3d::E_mod_int, mbar, 0.0, sign);
+    P += (1.0 / 3.0) * degeneracy * gauss1d(is3d::P_mod_int, mbar, 0.0, sign);
   }
+  const int nt = host_threads((size_t)jonah_points, "IS3D_TABLE_THREADS");
+  parallel_for(nt, [&](int t) {
+    for (int i = t; i < jonah_points; i += nt) {
+      double lambda = lambda_min + (double)i * delta_lambda;
+      double E_mod = 0.0, P_mod = 0.0;
+      for (const particle_info &p : particle_data) {
+        double degeneracy = (double)p.gspin, mass = p.mass, sign = (double)p.sign;
+        double mbar = mass / T;
+        if (mass == 0.0) continue;
+        E_mod += degeneracy * gauss1d(is3d::E_mod_int, mbar, lambda, sign);
+        P_mod += (1.0 / 3.0) * degeneracy * gauss1d(is3d::P_mod_int, mbar, lambda, sign);
+      }
+      double z = E / E_mod;
+      lambda_squared_array[i] = lambda * lambda;
+      z_array[i] = z;
+      bulkPi_over_Peq_array[i] = (P_mod / P) * z - 1.0;
+    }
+  });
+  for (int i = 0; i < jonah_points; i++) bulkPi_over_Peq_max = fmax(bulkPi_over_Peq_max, bulkPi_over_Peq_array[i]);
   have_jonah = true;
 }
 
