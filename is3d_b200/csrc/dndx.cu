@@ -60,6 +60,28 @@ __device__ __forceinline__ DndxBin dndx_load_bin(const DndxGrid &g, int ipT, int
   return d;
 }
 
+// Both kernels: one-warp blocks, lane = species class, all lanes on the same cell.  The (y, eta, phi) points of a cell are
+// taken in chunks of 32: lane j builds the item of point j (one sinh / cosh per lane instead of every lane rebuilding
+// every item), the warp then loops pT OUTER -- the lane's three momentum constants are loaded once per (chunk, pT) --
+// and the chunk's items INNER, read from shared memory with broadcast LDS.128.
+static_assert(kDndxThreads == 32, "the dN/dX kernels synchronise with __syncwarp");
+
+// flattened (iy, ie, iphi) point j of the cell's momentum-space quadrature
+struct DndxPoint { double yval, eta, w, cphi, sphi; };
+
+template <class PackFn>
+__device__ __forceinline__ DndxPoint dndx_point(const DndxGrid &g, PackFn pk, int j)
+{
+  const int iphi = j % g.Nphi, rest = j / g.Nphi, ie = rest % g.Neta, iy = rest / g.Neta;
+  DndxPoint p;
+  p.yval = g.yv[iy];
+  if (g.dimension == 3) { p.eta = pk(DP_ETA); p.w = 1.0; }
+  else { p.eta = g.etav[ie]; p.w = g.etaw[ie]; }
+  p.w *= g.phiw[iphi];        // phi weight folded into the p.dsigma coefficients (positive: the outflow test is unchanged)
+  p.cphi = g.cosphi[iphi]; p.sphi = g.sinphi[iphi];
+  return p;
+}
+
 // df_mode 1, 2 (SpacetimeDistribution.cpp:170-441)
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
 __global__ void __launch_bounds__(kDndxThreads)
@@ -67,10 +89,13 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
                int64_t surf_begin, DndxGrid g)
 {
   __shared__ double exptab[kExpTableSize];
+  __shared__ DfItem items[kDndxThreads];
   load_exp_table(exptab, g.exptab);
   __syncthreads();
-  const int s = blockIdx.x * kDndxThreads + threadIdx.x;
+  const int lane = threadIdx.x;
+  const int s = blockIdx.x * kDndxThreads + lane;
   const double m2 = g.mass2[s], baryon = g.baryon[s], sign = g.sign[s];
+  const int npoints = g.Ny * g.Neta * g.Nphi;
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
   int64_t c1 = c0 + cells_per_block;
   if (c1 > ncells) c1 = ncells;
@@ -78,26 +103,26 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
     if (pack[DP_VALID * stride + cell] == 0.0) continue;
     auto pk = [&](int k) { return pack[k * stride + cell]; };
     double acc = 0.0;
-    for (int iy = 0; iy < g.Ny; iy++) {
-      const double yval = g.yv[iy];
-      for (int ie = 0; ie < g.Neta; ie++) {
-        double eta, w;
-        if (g.dimension == 3) { eta = pk(DP_ETA); w = 1.0; }
-        else { eta = g.etav[ie]; w = g.etaw[ie]; }
-        const double d = yval - eta, sh = sinh(d), ch = cosh(d);
-        for (int iphi = 0; iphi < g.Nphi; iphi++) {
-          // phi weight folded into the p.dsigma coefficients (weights are positive: the outflow test is unchanged)
-          const DfItem it = df_make_item(pk, MODE, sh, ch, g.cosphi[iphi], g.sinphi[iphi], w * g.phiw[iphi]);
-#pragma unroll 3
-          for (int ipT = 0; ipT < g.NpT; ipT++) {
-            const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
-            const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-            double v = pds * df_distribution<MODE, BARYON, REGULATE>(it, df_share<BARYON>(it, bn.pT, bn.pT2), bn.b, exptab);
-            if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
-            acc += v;
-          }
+    for (int j0 = 0; j0 < npoints; j0 += kDndxThreads) {
+      if (j0 + lane < npoints) {
+        const DndxPoint pt = dndx_point(g, pk, j0 + lane);
+        const double d = pt.yval - pt.eta;
+        items[lane] = df_make_item(pk, MODE, sinh(d), cosh(d), pt.cphi, pt.sphi, pt.w);
+      }
+      __syncwarp();
+      const int nj = min(kDndxThreads, npoints - j0);
+      for (int ipT = 0; ipT < g.NpT; ipT++) {
+        const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
+#pragma unroll 2
+        for (int k = 0; k < nj; k++) {
+          const DfItem it = items[k];
+          const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
+          double v = pds * df_distribution<MODE, BARYON, REGULATE>(it, df_share<BARYON>(it, bn.pT, bn.pT2), bn.b, exptab);
+          if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
+          acc += v;
         }
       }
+      __syncwarp();
     }
     if (s < g.ns) {
       const int64_t gc = surf_begin + cell;
@@ -105,6 +130,12 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
     }
   }
 }
+
+union DndxItemSlot {
+  DfItem lin;
+  FeqmodItem mod;
+  __device__ DndxItemSlot() {}
+};
 
 // df_mode 3, 4 (SpacetimeDistribution.cpp:676-1160)
 template <bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM>
@@ -114,10 +145,16 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
                    int gla_pts)
 {
   __shared__ double exptab[kExpTableSize];
+  __shared__ DndxItemSlot items[kDndxThreads];
+  __shared__ unsigned char item_linear[kDndxThreads];
+  __shared__ RenormNodes nodes;
   load_exp_table(exptab, g.exptab);
+  if (SPECIES_RENORM) nodes.load(gla_root, gla_weight, gla_pts);
   __syncthreads();
-  const int s = blockIdx.x * kDndxThreads + threadIdx.x;
+  const int lane = threadIdx.x;
+  const int s = blockIdx.x * kDndxThreads + lane;
   const double m2 = g.mass2[s], baryon = g.baryon[s], sign = g.sign[s], deg = g.deg[s], mass = g.mass[s];   // deg cancels in the renorm ratio
+  const int npoints = g.Ny * g.Neta * g.Nphi;
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
   int64_t c1 = c0 + cells_per_block;
   if (c1 > ncells) c1 = ncells;
@@ -125,45 +162,41 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
     if (pack[DP_VALID * stride + cell] == 0.0) continue;
     auto pk = [&](int k) { return pack[k * stride + cell]; };
     double rn = pk(FP_RENORM);
-    if (SPECIES_RENORM) rn = feqmod_renorm_ptm(pk, mass, deg, baryon, sign, gla_root, gla_weight, gla_pts);
+    if (SPECIES_RENORM) rn = feqmod_renorm_ptm_fused(pk, mass, deg, baryon, sign, nodes, gla_pts, exptab);
     const bool breakdown = pk(FP_BREAKDOWN) != 0.0;
     const double detA = pk(FP_DETA), eta_scale = pk(FP_ETA_SCALE);
     double acc = 0.0;
-    for (int iy = 0; iy < g.Ny; iy++) {
-      const double yval = g.yv[iy];
-      for (int ie = 0; ie < g.Neta; ie++) {
-        double eta, w;
-        if (g.dimension == 3) { eta = pk(DP_ETA); w = 1.0; }
-        else { eta = g.etav[ie]; w = g.etaw[ie]; }
+    for (int j0 = 0; j0 < npoints; j0 += kDndxThreads) {
+      if (j0 + lane < npoints) {
+        const DndxPoint pt = dndx_point(g, pk, j0 + lane);
         bool linear = breakdown;
-        if (g.dimension == 3 && !linear && detA < 0.01 && fabs(yval - eta) < detA) linear = true;
-        const double d = linear ? (yval - eta) : (yval - eta_scale * eta);
+        if (g.dimension == 3 && !linear && detA < 0.01 && fabs(pt.yval - pt.eta) < detA) linear = true;
+        const double d = linear ? (pt.yval - pt.eta) : (pt.yval - eta_scale * pt.eta);
         const double sh = sinh(d), ch = cosh(d);
-        for (int iphi = 0; iphi < g.Nphi; iphi++) {
-          const double cphi = g.cosphi[iphi], sphi = g.sinphi[iphi], wq = w * g.phiw[iphi];
-          if (linear) {
-            const DfItem it = feqmod_make_linear_item(pk, sh, ch, cphi, sphi, wq, true);
-#pragma unroll 3
-            for (int ipT = 0; ipT < g.NpT; ipT++) {
-              const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
-              const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-              double v = pds * df_distribution<2, BARYON, REGULATE, true>(it, df_share<BARYON>(it, bn.pT, bn.pT2), bn.b, exptab);
-              if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
-              acc += v;
-            }
+        if (linear) items[lane].lin = feqmod_make_linear_item(pk, sh, ch, pt.cphi, pt.sphi, pt.w, true);
+        else items[lane].mod = feqmod_make_item(pk, sh, ch, pt.cphi, pt.sphi, pt.w, true);
+        item_linear[lane] = linear ? 1 : 0;
+      }
+      __syncwarp();
+      const int nj = min(kDndxThreads, npoints - j0);
+      for (int ipT = 0; ipT < g.NpT; ipT++) {
+        const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
+        for (int k = 0; k < nj; k++) {
+          double pds, v;
+          if (item_linear[k]) {
+            const DfItem it = items[k].lin;
+            pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
+            v = pds * df_distribution<2, BARYON, REGULATE, true>(it, df_share<BARYON>(it, bn.pT, bn.pT2), bn.b, exptab);
           } else {
-            const FeqmodItem it = feqmod_make_item(pk, sh, ch, cphi, sphi, wq, true);
-#pragma unroll 3
-            for (int ipT = 0; ipT < g.NpT; ipT++) {
-              const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
-              const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-              double v = pds * feqmod_distribution<BARYON>(it, feqmod_share(it, bn.pT, bn.pT2), bn.b, rn, exptab);
-              if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
-              acc += v;
-            }
+            const FeqmodItem it = items[k].mod;
+            pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
+            v = pds * feqmod_distribution<BARYON>(it, feqmod_share(it, bn.pT, bn.pT2), bn.b, rn, exptab);
           }
+          if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
+          acc += v;
         }
       }
+      __syncwarp();
     }
     // a NaN / inf renormalisation skips the (cell, species) in both branches (SpacetimeDistribution.cpp:955-959)
     if (s < g.ns && rn != 0.0) {
@@ -233,6 +266,10 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   if (p.df_mode == 5) { ctx->set_error("no spacetime distribution routine for famod yet (reference EmissionFunction.cpp:1184-1189)"); return IS3D_ERR_UNSUPPORTED; }
   const bool feqmod = (p.df_mode == 3 || p.df_mode == 4);
   if (feqmod && ctx->gla_pts <= 0) { ctx->set_error("Gauss-Laguerre tables not set"); return IS3D_ERR_INVALID; }
+  if (feqmod && (ctx->gla_pts > kRenormMaxPts || ctx->gla_alpha < 3)) {
+    ctx->set_error("Gauss-Laguerre tables: need alpha = 0..2 with at most 64 points");
+    return IS3D_ERR_INVALID;
+  }
   const int64_t n = ctx->surf.n;
   DndxGrid g;
   const int *class_of_dev = nullptr;

@@ -49,12 +49,7 @@ __global__ void feqmod_setup_kernel(SurfaceView surf, int64_t begin, int64_t cou
   if (st & CELL_PL_NEGATIVE) { atomicAdd(&counters[3], 1ull); atomicMax(&counters[5], (unsigned long long)(begin + i + 1)); }
 }
 
-// PTM renormalisation n_linear / n_mod per (cell, species): the four 32-point Gauss-Laguerre sums of
-// feqmod_renorm_ptm (MomentumSpectra.cpp:795-826) fused into one pass over the nodes -- neq and J10 share their
-// exp(Ebar - b alphaB); node constants w p e^p (alpha = 1) and w e^p (alpha = 2) are staged in shared memory; exp / sqrt /
-// reciprocals are the FP64-pipe versions of common.cuh.
-constexpr int kRenormMaxPts = 64;
-
+// PTM renormalisation n_linear / n_mod per (cell, class) (MomentumSpectra.cpp:795-826): feqmod_renorm_ptm_fused
 __global__ void __launch_bounds__(128)
 feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int ns,
                      const double *__restrict__ mass, const double *__restrict__ deg,
@@ -63,14 +58,9 @@ feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t co
                      const double *__restrict__ exptab_g, double *__restrict__ renorm)
 {
   __shared__ double exptab[kExpTableSize];
-  __shared__ double p1sq[kRenormMaxPts], c1[kRenormMaxPts], p2sq[kRenormMaxPts], c2[kRenormMaxPts];
+  __shared__ RenormNodes nodes;
   load_exp_table(exptab, exptab_g);
-  for (int k = threadIdx.x; k < gla_pts; k += blockDim.x) {
-    const double r1 = gla_root[1 * gla_pts + k], w1 = gla_weight[1 * gla_pts + k];
-    const double r2 = gla_root[2 * gla_pts + k], w2 = gla_weight[2 * gla_pts + k];
-    p1sq[k] = r1 * r1; c1[k] = w1 * (r1 * exp(r1));
-    p2sq[k] = r2 * r2; c2[k] = w2 * exp(r2);
-  }
+  nodes.load(gla_root, gla_weight, gla_pts);
   __syncthreads();
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count * ns) return;
@@ -79,30 +69,7 @@ feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t co
   double r = 0.0;
   if (pack[DP_VALID * stride + cell] != 0.0) {
     auto pk = [&](int k) { return pack[k * stride + cell]; };
-    const double T = pk(FP_T), T_mod = pk(FP_TMOD), alphaB = pk(DP_ALPHAB), alphaB_mod = pk(FP_ALPHAB_MOD);
-    const double m = mass[s], g = deg[s], b = baryon[s], sg = sign[s];
-    const double mbar = m / T, mbar_mod = m / T_mod, mb2 = mbar * mbar, mm2 = mbar_mod * mbar_mod;
-    const double chem = b * alphaB, chem_mod = b * alphaB_mod;
-    double sneq = 0.0, sJ10 = 0.0, sJ20 = 0.0, smod = 0.0;
-    for (int k = 0; k < gla_pts; k++) {
-      const double E1 = fast_sqrt(p1sq[k] + mb2);
-      const double e1 = fast_exp(E1 - chem, exptab), iq1 = fast_rcp(e1 + sg);
-      const double t1 = c1[k] * iq1;
-      sneq += t1;                                   // w p e^p / (e^(E - b alphaB) + sign)
-      sJ10 += t1 * (e1 * iq1);                      // w p e^(p + E - b alphaB) / q^2
-      const double E2 = fast_sqrt(p2sq[k] + mb2);
-      const double e2 = fast_exp(E2 - chem, exptab), iq2 = fast_rcp(e2 + sg);
-      sJ20 += c2[k] * E2 * (e2 * iq2 * iq2);        // w E e^(p + E - b alphaB) / q^2
-      const double Em = fast_sqrt(p1sq[k] + mm2);
-      smod += c1[k] * fast_rcp(fast_exp(Em - chem_mod, exptab) + sg);
-    }
-    const double neq_fact = T * T * T / kTwoPi2HbarC3, J20_fact = T * neq_fact;
-    const double nmod_fact = T_mod * T_mod * T_mod / kTwoPi2HbarC3;
-    const double neq = neq_fact * g * sneq, N10 = b * neq_fact * g * sJ10, J20 = J20_fact * g * sJ20;
-    const double n_linear = neq + pk(FP_DNFACT) * (neq + N10 * pk(FP_G) + J20 * pk(FP_F_T2));
-    const double n_mod = nmod_fact * g * smod;
-    r = (n_linear / n_mod) / pk(FP_RENORM_DIV);
-    r = not_finite(r) ? 0.0 : fabs(r);
+    r = feqmod_renorm_ptm_fused(pk, mass[s], deg[s], baryon[s], sign[s], nodes, gla_pts, exptab);
   }
   renorm[idx] = r;
 }

@@ -276,4 +276,54 @@ IS3D_HD double feqmod_eval(const FeqmodItem &it, const FeqmodShared &s, const Df
   return contrib;
 }
 
+#if defined(__CUDACC__)
+// ---- fused PTM renormalisation (device) ---------------------------------------------------------------------------
+// The four 32-point Gauss-Laguerre sums of feqmod_renorm_ptm in one pass over the nodes: neq and J10 share their
+// exp(Ebar - b alphaB); node constants w p e^p (alpha = 1) and w e^p (alpha = 2) are staged in shared memory by
+// RenormNodes::load; exp / sqrt / reciprocals are the FP64-pipe versions.
+constexpr int kRenormMaxPts = 64;
+
+struct RenormNodes {
+  double p1sq[kRenormMaxPts], c1[kRenormMaxPts], p2sq[kRenormMaxPts], c2[kRenormMaxPts];
+  __device__ void load(const double *__restrict__ gla_root, const double *__restrict__ gla_weight, int gla_pts)
+  {
+    for (int k = threadIdx.x; k < gla_pts; k += blockDim.x) {
+      const double r1 = gla_root[1 * gla_pts + k], w1 = gla_weight[1 * gla_pts + k];
+      const double r2 = gla_root[2 * gla_pts + k], w2 = gla_weight[2 * gla_pts + k];
+      p1sq[k] = r1 * r1; c1[k] = w1 * (r1 * exp(r1));
+      p2sq[k] = r2 * r2; c2[k] = w2 * exp(r2);
+    }
+  }
+};
+
+template <class PackFn>
+__device__ __forceinline__ double feqmod_renorm_ptm_fused(PackFn pk, double m, double g, double b, double sg, const RenormNodes &nd,
+                                                          int gla_pts, const double *__restrict__ exptab)
+{
+  const double T = pk(FP_T), T_mod = pk(FP_TMOD), alphaB = pk(DP_ALPHAB), alphaB_mod = pk(FP_ALPHAB_MOD);
+  const double mbar = m / T, mbar_mod = m / T_mod, mb2 = mbar * mbar, mm2 = mbar_mod * mbar_mod;
+  const double chem = b * alphaB, chem_mod = b * alphaB_mod;
+  double sneq = 0.0, sJ10 = 0.0, sJ20 = 0.0, smod = 0.0;
+  for (int k = 0; k < gla_pts; k++) {
+    const double E1 = fast_sqrt(nd.p1sq[k] + mb2);
+    const double e1 = fast_exp(E1 - chem, exptab), iq1 = fast_rcp(e1 + sg);
+    const double t1 = nd.c1[k] * iq1;
+    sneq += t1;                                   // w p e^p / (e^(E - b alphaB) + sign)
+    sJ10 += t1 * (e1 * iq1);                      // w p e^(p + E - b alphaB) / q^2
+    const double E2 = fast_sqrt(nd.p2sq[k] + mb2);
+    const double e2 = fast_exp(E2 - chem, exptab), iq2 = fast_rcp(e2 + sg);
+    sJ20 += nd.c2[k] * E2 * (e2 * iq2 * iq2);     // w E e^(p + E - b alphaB) / q^2
+    const double Em = fast_sqrt(nd.p1sq[k] + mm2);
+    smod += nd.c1[k] * fast_rcp(fast_exp(Em - chem_mod, exptab) + sg);
+  }
+  const double neq_fact = T * T * T / kTwoPi2HbarC3, J20_fact = T * neq_fact;
+  const double nmod_fact = T_mod * T_mod * T_mod / kTwoPi2HbarC3;
+  const double neq = neq_fact * g * sneq, N10 = b * neq_fact * g * sJ10, J20 = J20_fact * g * sJ20;
+  const double n_linear = neq + pk(FP_DNFACT) * (neq + N10 * pk(FP_G) + J20 * pk(FP_F_T2));
+  const double n_mod = nmod_fact * g * smod;
+  const double r = (n_linear / n_mod) / pk(FP_RENORM_DIV);
+  return not_finite(r) ? 0.0 : fabs(r);
+}
+#endif
+
 }  // namespace is3d
