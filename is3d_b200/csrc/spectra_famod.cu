@@ -100,6 +100,31 @@ is3d_status famod_setup_pass(is3d_ctx *ctx, int64_t begin, int64_t count, double
   h.gl16 = (const double *)gl;
   h.exptab = ctx->d_exptab;
   h.exact = p.famod_chain ? 1 : 0;          // the chain-faithful parity mode also keeps the reference's libm formulas
+  if (!h.exact) {
+    // Production mode: hadrons with the same (mass, sign) contribute identical terms to every F / J sum (no chemical
+    // potential enters them), so the first min(320, N_pdg) table entries are merged into classes with summed degeneracy --
+    // for the SMASH table 320 -> ~130 terms per quadrature node.  Same sums up to the order of the additions.
+    std::vector<double> cm, cs, cd;
+    for (int n = 0; n < h.n; n++) {
+      const double m = ctx->h_pdg_mass[n], sg = ctx->h_pdg_sign[n], g = ctx->h_pdg_deg[n];
+      if (m == 0.0) continue;                                       // photons are skipped by the sums anyway
+      size_t k = 0;
+      while (k < cm.size() && !(cm[k] == m && cs[k] == sg)) k++;
+      if (k == cm.size()) { cm.push_back(m); cs.push_back(sg); cd.push_back(g); }
+      else cd[k] += g;
+    }
+    const size_t nc = cm.size();
+    void *d = nullptr;
+    IS3D_TRY(ctx->get_scratch("aniso_merged_hadrons", 3 * (nc ? nc : 1) * sizeof(double), &d));
+    if (begin == 0 && nc) {
+      std::vector<double> hbuf(3 * nc);
+      for (size_t k = 0; k < nc; k++) { hbuf[k] = cm[k]; hbuf[nc + k] = cs[k]; hbuf[2 * nc + k] = cd[k]; }
+      IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d, hbuf.data(), hbuf.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    h.mass = (const double *)d; h.sign = h.mass + nc; h.deg = h.mass + 2 * nc;
+    h.n = (int)nc;
+  }
   if (p.famod_chain) {
     famod_setup_chain_kernel<<<1, 32, 0, ctx->stream>>>(ctx->surf, begin, count, fl, h, pack, stride, counters, (FamodChain *)chain);
   } else {
