@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -141,6 +142,14 @@ struct SpeciesBins {
   const double *c_mass = nullptr, *c_deg = nullptr, *c_baryon = nullptr, *c_sign = nullptr;      // [nclass] representatives, device
   const int *class_of = nullptr;                                                                 // [ns], device
 };
+
+// cells per pass of the continuous paths (bounds the cell-pack scratch); IS3D_PASS_CELLS is a test hook that forces
+// small passes so that the multi-pass accumulation is exercised on small surfaces (rounded up to the 256-cell tile)
+inline int64_t pass_cells(int64_t default_cells)
+{
+  if (const char *v = getenv("IS3D_PASS_CELLS")) { long long c = atoll(v); if (c > 0) return (c + 255) / 256 * 256; }
+  return default_cells;
+}
 
 void species_classes(const is3d_ctx *ctx, std::vector<int> *class_of, std::vector<int> *rep);
 

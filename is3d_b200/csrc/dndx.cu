@@ -292,7 +292,7 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   const bool species_renorm = (p.df_mode == 3 && p.include_bulk_deltaf);
   const int pack_size = feqmod ? (int)FP_SIZE : (int)DP_SIZE;
 
-  const int64_t macro = 2 << 20;
+  const int64_t macro = pass_cells(2 << 20);
   const int64_t stride = n < macro ? n : macro;
   void *pack = nullptr, *counters = nullptr;
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)pack_size * stride * sizeof(double), &pack));

@@ -15,6 +15,7 @@
 //      deterministic order that does not depend on the launch geometry.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -422,7 +423,10 @@ int64_t sampler_cells_per_pass(const is3d_ctx *ctx)
   int64_t cells = kSamplerPassBytes / per_cell;
   cells = cells / 1024 * 1024;
   if (cells > ((int64_t)16 << 20)) cells = (int64_t)16 << 20;
-  return cells < 1024 ? 1024 : cells;
+  if (cells < 1024) cells = 1024;
+  // test hook: force small passes so that the multi-pass merge is exercised on small surfaces
+  if (const char *v = getenv("IS3D_SAMPLER_PASS_CELLS")) { int64_t c = atoll(v); if (c > 0) cells = c; }
+  return cells;
 }
 
 }  // namespace
@@ -640,7 +644,12 @@ static bool release_host_list(void *ptr)
   return true;
 }
 
-constexpr unsigned long long kMaxProposalsPerPass = 256ull << 20;    // bounds the record scratch to ~27 GB
+// bounds the record scratch to ~27 GB (test hook: IS3D_SAMPLER_PASS_PROPOSALS)
+static unsigned long long max_proposals_per_pass()
+{
+  if (const char *v = getenv("IS3D_SAMPLER_PASS_PROPOSALS")) { long long c = atoll(v); if (c > 0) return (unsigned long long)c; }
+  return 256ull << 20;
+}
 
 is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total_out, int64_t *counts,
                         is3d_stats *stats)
@@ -697,7 +706,7 @@ is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
     IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(&nprop, (unsigned long long *)offsets + count, sizeof(nprop), cudaMemcpyDeviceToHost, ctx->stream));
     IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     launches += 2;
-    if (nprop > kMaxProposalsPerPass && count > 1) {
+    if (nprop > max_proposals_per_pass() && count > 1) {
       // too many proposals for one pass: halve the cell block and redo its set-up (deterministic, so nothing is lost);
       // the counters of the discarded attempt are rolled back by re-zeroing below
       pass_cells = (count + 1) / 2;

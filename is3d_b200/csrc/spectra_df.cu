@@ -280,7 +280,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   const int64_t blocks_per_chunk = (int64_t)nslices * ctx->Ny * ctx->Nphi;
   if ((int64_t)ctx->Ny * ctx->Nphi > 65535) { ctx->set_error("Ny*Nphi exceeds 65535"); return IS3D_ERR_INVALID; }
 
-  const int64_t macro = 4 << 20;                      // cells per pass: bounds the pack scratch to ~1 GB
+  const int64_t macro = pass_cells(4 << 20);          // cells per pass: bounds the pack scratch to ~1 GB
   const int64_t stride = n < macro ? n : macro;
   int nchunks; int64_t cpc;
   choose_chunks(ctx, stride, blocks_per_chunk, total_class, kTile, &nchunks, &cpc);

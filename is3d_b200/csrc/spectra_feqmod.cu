@@ -251,7 +251,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   if ((int64_t)ctx->Ny * ctx->Nphi > 65535) { ctx->set_error("Ny*Nphi exceeds 65535"); return IS3D_ERR_INVALID; }
 
   // cells per pass: bounds the pack (440 B/cell) and the PTM renorm table (8 Ns B/cell) to ~2 GB
-  int64_t macro = 2 << 20;
+  int64_t macro = pass_cells(2 << 20);
   if (species_renorm) { int64_t m2 = ((int64_t)1 << 31) / (8 * (int64_t)sb.nclass); if (m2 < macro) macro = m2; }
   macro = macro / kTile * kTile;
   if (macro < kTile) macro = kTile;

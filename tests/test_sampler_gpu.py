@@ -125,3 +125,24 @@ def test_host_sampler_writes_oscar_lists(libs, tmp_path):
         cols = lines[1].split()
         assert len(cols) == 11 and cols[0] == "0"
     assert os.path.exists(tmp_path / "results" / f"particle_list_osc_{nev}.dat")
+
+
+def test_multi_pass_and_split_passes_reproduce_the_single_pass_list(libs, tmp_path, monkeypatch):
+    """Surfaces larger than one pass (16 M cells) and passes whose proposal count exceeds the record budget are split;
+    the split must not change a single hadron: Philox streams are keyed by (global cell, draw) and the final order by
+    (event, cell, draw).  Forced here on a 300-cell surface through the pass-size test hooks."""
+    name = "smp_s3d_m3"
+    case = cases.SAMPLER_CASES[name]
+    surf, _ = harness.load_golden_sampler(name)
+    nev = 3000
+    with harness.open_session(str(tmp_path), case, surf, overrides=dict(test_sampler=0)) as h:
+        one, c1, _ = h.abi_sample(nev)
+        monkeypatch.setenv("IS3D_SAMPLER_PASS_CELLS", "64")                # 5 passes, host merge of the pass lists
+        many, c2, _ = h.abi_sample(nev)
+        monkeypatch.delenv("IS3D_SAMPLER_PASS_CELLS")
+        monkeypatch.setenv("IS3D_SAMPLER_PASS_PROPOSALS", "2000")          # the 300-cell pass is halved until it fits
+        split, c3, st = h.abi_sample(nev)
+    assert len(one) > 5000
+    assert np.array_equal(c1, c2) and np.array_equal(c1, c3)
+    assert np.array_equal(one, many) and np.array_equal(one, split)
+    assert st.cells_total == len(surf["tau"]) and st.sampler_accepted == len(one)

@@ -153,3 +153,19 @@ def test_host_writers_file_layout(libs, tmp_path):
         w = spec[s, :, :, 0] * phi[:, 1]
         v2 = np.abs((w * np.exp(2j * phi[:, 0])).sum(axis=1)) / w.sum(axis=1)
         np.testing.assert_allclose(d[:, 3], v2, rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["s3d_m2_baryon", "s3d_m3", "s3d_m4", "vah_m5"])
+def test_multi_pass_accumulation(libs, tmp_path, monkeypatch, name):
+    """Surfaces beyond one pass (2-4 M cells) are streamed pass by pass into the same partial sums; forced here with the
+    IS3D_PASS_CELLS test hook (256-cell passes over 200-300 cells, so the last pass is ragged).  Same bins up to the order
+    of the additions."""
+    case = cases.SPECTRA_CASES[name]
+    surf, ref = harness.load_golden(name)
+    with harness.open_session(str(tmp_path), case, surf) as h:
+        one, _ = h.abi_spectra()
+        monkeypatch.setenv("IS3D_PASS_CELLS", "256")
+        many, st = h.abi_spectra()
+    assert st.cells_total == len(surf["tau"])
+    harness.assert_spectra_close(many, one, rtol=1e-12, what=name + " multi-pass vs single pass")
+    harness.assert_spectra_close(many, ref, what=name + " multi-pass vs reference")
