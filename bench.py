@@ -28,7 +28,7 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-from is3d_b200 import synthetic, workdir  # noqa: E402
+from is3d2_b200 import synthetic, workdir  # noqa: E402
 
 # algorithmic FLOPs per integrand evaluation (SURVEY.md 8d / BASELINE.md 4; DESIGN.md restates the derivation)
 F_ALG = {1: 165.0, 2: 194.0, 3: 265.0, 4: 265.0, 5: 265.0}
@@ -173,7 +173,7 @@ def sampler_bench(args, rank: int, world: int, local: int) -> dict:
     import torch
     import torch.distributed as dist
 
-    from is3d_b200 import HostSession, shard
+    from is3d2_b200 import HostSession, shard
 
     cells, nev = args.sampler_cells, args.sampler_events
     surf = synthetic.s3d(cells, seed=3024 + rank, stress=0.3)
@@ -242,7 +242,7 @@ def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from is3d_b200 import HostSession, shard
+    from is3d2_b200 import HostSession, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -281,7 +281,7 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
     import torch
     import torch.distributed as dist
 
-    from is3d_b200 import shard
+    from is3d2_b200 import shard
 
     cells = args.cells_per_gpu
     surf = synthetic.s3d(cells, seed=2024 + rank, baryon=True)         # rank's shard of the surface

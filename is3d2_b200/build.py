@@ -1,7 +1,7 @@
 """Build the in-tree native libraries:
-  is3d_b200/libis3d_b200.so   CUDA kernels + C ABI (nvcc, sm_100a only)
-  is3d_b200/libis3d_host.so   C++ host layer (readers, tables, EmissionFunctionArray, IS3D)
-  is3d_b200/iS3D_b200.e       drop-in executable
+  is3d2_b200/libis3d_b200.so   CUDA kernels + C ABI (nvcc, sm_100a only)
+  is3d2_b200/libis3d_host.so   C++ host layer (readers, tables, EmissionFunctionArray, IS3D)
+  is3d2_b200/iS3D_b200.e       drop-in executable
 Built artefacts are git-ignored but travel to the GPU box with the snapshot."""
 from __future__ import annotations
 

@@ -69,14 +69,14 @@ HOST_SYMBOLS = ["is3d_host_open", "is3d_host_close", "is3d_host_read_surface", "
 
 
 def load_libraries():
-    """Load the in-tree shared libraries; fails loudly if they were not built (python -m is3d_b200.build)."""
+    """Load the in-tree shared libraries; fails loudly if they were not built (python -m is3d2_b200.build)."""
     global _lib, _host
     if _lib is not None:
         return _lib, _host
     p = os.path.join(HERE, "libis3d_b200.so")
     ph = os.path.join(HERE, "libis3d_host.so")
     if not os.path.exists(p) or not os.path.exists(ph):
-        raise Is3dError(f"{p} / {ph} not built: run `python -m is3d_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
+        raise Is3dError(f"{p} / {ph} not built: run `python -m is3d2_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
     lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
     host = C.CDLL(ph, mode=C.RTLD_GLOBAL)
     vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import os
 
-from is3d_b200 import synthetic
+from is3d2_b200 import synthetic
 
 _GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

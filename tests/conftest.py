@@ -16,7 +16,7 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def libs():
     """The in-tree native libraries; built on demand here (nvcc cross-compiles without a GPU)."""
-    from is3d_b200 import build, capi
-    if not os.path.exists(os.path.join(REPO, "is3d_b200", "libis3d_b200.so")):
+    from is3d2_b200 import build, capi
+    if not os.path.exists(os.path.join(REPO, "is3d2_b200", "libis3d_b200.so")):
         build.build()
     return capi.load_libraries()

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 import cases  # noqa: E402
 import refrun  # noqa: E402
-from is3d_b200 import synthetic  # noqa: E402
+from is3d2_b200 import synthetic  # noqa: E402
 
 
 def main():

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 import cases
-from is3d_b200 import HostSession, synthetic, workdir
+from is3d2_b200 import HostSession, synthetic, workdir
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -76,7 +76,7 @@ def emulate_partial_memset(h: np.ndarray) -> np.ndarray:
 
 def normalise_dndx(h: dict, params: dict) -> dict:
     """Writer normalisation of SpacetimeDistribution.cpp:448-490."""
-    from is3d_b200 import workdir
+    from is3d2_b200 import workdir
     p = workdir.default_parameters()
     p.update({k: str(v) for k, v in params.items()})
     tb, rb, pb = int(float(p["tau_bins"])), int(float(p["r_bins"])), int(float(p["phip_bins"]))

@@ -8,7 +8,7 @@ import subprocess
 
 import numpy as np
 
-from is3d_b200 import HostSession, workdir
+from is3d2_b200 import HostSession, workdir
 
 ORACLE_DIR = os.path.join(workdir.REPO, "oracle")
 _lib = None
@@ -104,7 +104,7 @@ class OracleProblem:
 
         n = len(surface["tau"])
         inp.n_cells = n
-        from is3d_b200.capi import SURFACE_COLUMNS
+        from is3d2_b200.capi import SURFACE_COLUMNS
         for k, name in enumerate(SURFACE_COLUMNS):
             a = np.ascontiguousarray(surface.get(name, np.zeros(n)), dtype=np.float64)
             self.keep.append(a)

@@ -8,7 +8,7 @@ import subprocess
 
 import numpy as np
 
-from is3d_b200 import synthetic, workdir
+from is3d2_b200 import synthetic, workdir
 
 REPO = workdir.REPO
 REF_BIN = os.path.join(REPO, "oracle", "_ref", "is3d_ref")
@@ -105,7 +105,7 @@ def read_dndx_files(root: str, mcids) -> dict:
 def read_sampler_test_files(root: str, mcids, params: dict) -> dict:
     """results/sampled/*_test.dat of a reference run with test_sampler = 1, converted back to integer COUNTS
     (writers: EmissionFunction.cpp:685-975).  Also Nevents and the exact mean total yield dumped by the harness."""
-    from is3d_b200 import workdir
+    from is3d2_b200 import workdir
     p = workdir.default_parameters()
     p.update({k: str(v) for k, v in params.items()})
     f = lambda k: float(p[k])  # noqa: E731

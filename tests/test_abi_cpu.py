@@ -5,7 +5,7 @@ import re
 
 import pytest
 
-from is3d_b200 import capi
+from is3d2_b200 import capi
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def _device_hists(h, ns, params):
     tb, rb, pb = (int(float(params.get(k, d))) for k, d in (("tau_bins", 120), ("r_bins", 60), ("phip_bins", 100)))
     tau, r, phi = np.zeros((ns, tb)), np.zeros((ns, rb)), np.zeros((ns, pb))
-    from is3d_b200 import Stats
+    from is3d2_b200 import Stats
     st = Stats()
     rc = h.lib.is3d_dndx(h.ctx, tau.ctypes.data, r.ctypes.data, phi.ctypes.data, C.byref(st))
     assert rc == 0, h.lib.is3d_last_error(h.ctx)

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import refrun
-from is3d_b200 import HostSession, synthetic, workdir
+from is3d2_b200 import HostSession, synthetic, workdir
 
 
 @pytest.mark.parametrize("hrg_eos,npdg", [(1, 327), (2, 493)])
@@ -74,7 +74,7 @@ def test_missing_parameter_is_fatal(libs, tmp_path):
     lines = [l for l in open(p) if not l.startswith("hrg_eos")]
     open(p, "w").writelines(lines)
     synthetic.write_mode1(os.path.join(root, "input", "surface.dat"), synthetic.s3d(2, seed=2))
-    exe = os.path.join(workdir.REPO, "is3d_b200", "iS3D_b200.e")
+    exe = os.path.join(workdir.REPO, "is3d2_b200", "iS3D_b200.e")
     r = subprocess.run([exe], cwd=root, capture_output=True, text=True)
     assert r.returncode != 0
     assert "hrg_eos" in r.stdout and "not found" in r.stdout

@@ -5,7 +5,7 @@ import pytest
 import cases
 import harness
 import oracle_api
-from is3d_b200 import workdir
+from is3d2_b200 import workdir
 
 ORACLE_CASES = [n for n, c in cases.SPECTRA_CASES.items()
                 if c["params"]["df_mode"] in (1, 2, 3, 4, 5) and c["chosen"] == "pikp" and c.get("tables") is None]

@@ -10,7 +10,7 @@ import pytest
 import cases
 import harness
 import oracle_api
-from is3d_b200 import workdir
+from is3d2_b200 import workdir
 
 pytestmark = pytest.mark.gpu
 

@@ -7,7 +7,7 @@ import pytest
 
 import bench
 import harness
-from is3d_b200 import HostSession, synthetic, workdir
+from is3d2_b200 import HostSession, synthetic, workdir
 
 pytestmark = pytest.mark.gpu
 

@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 import cases
 import harness
 import oracle_api
-from is3d_b200 import shard, workdir
+from is3d2_b200 import shard, workdir
 
 
 def test_cell_range_tiles_the_surface():

@@ -37,7 +37,7 @@ def test_famod_chain_free_fast_path_matches_oracle(libs, tmp_path, monkeypatch, 
     with different 1-ulp roundings of atan differ at the 1e-11 level; the tolerance here is 5e-10 and the observed worst
     case is printed (profiles/ records it)."""
     import oracle_api
-    from is3d_b200 import workdir
+    from is3d2_b200 import workdir
     case = cases.SPECTRA_CASES[name]
     surf, _ = harness.load_golden(name)
     monkeypatch.setenv("IS3D_FAMOD_CHAIN", "0")
@@ -104,7 +104,7 @@ def test_skipped_cells_and_empty_surface(libs, tmp_path):
 
 def test_out_of_table_cell_is_an_error(libs, tmp_path):
     """T outside [0.1, 0.2] GeV aborts the reference (GSL domain error); the ABI returns IS3D_ERR_TABLE_RANGE."""
-    from is3d_b200 import Is3dError
+    from is3d2_b200 import Is3dError
     case = cases.SPECTRA_CASES["s3d_m1"]
     surf, _ = harness.load_golden("s3d_m1")
     bad = {k: v.copy() for k, v in surf.items()}

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
 import bench  # noqa: E402
-from is3d_b200 import HostSession, Stats, synthetic, workdir  # noqa: E402
+from is3d2_b200 import HostSession, Stats, synthetic, workdir  # noqa: E402
 
 mode, cells = int(sys.argv[1]), int(sys.argv[2])
 chosen = sys.argv[3] if len(sys.argv) > 3 else "smash"

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import bench
-from is3d_b200 import HostSession, synthetic, workdir
+from is3d2_b200 import HostSession, synthetic, workdir
 mode, cells = int(sys.argv[1]), int(sys.argv[2])
 os.environ["IS3D_FAMOD_CHAIN"] = "0"
 surf = synthetic.s3d(cells, seed=2024, baryon=True)

@@ -9,7 +9,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
-from is3d_b200 import synthetic, workdir  # noqa: E402
+from is3d2_b200 import synthetic, workdir  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 operation = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -27,7 +27,7 @@ a[:, 11:20] /= 0.197327053                    # file columns are in fm^-1 units
 if baryon:
     a[:, 20] /= 0.197327053
 np.savetxt(os.path.join(root, "input", "surface.dat"), a, fmt="%.17g")
-exe = os.path.join(workdir.REPO, "is3d_b200", "iS3D_b200.e")
+exe = os.path.join(workdir.REPO, "is3d2_b200", "iS3D_b200.e")
 env = dict(os.environ, IS3D_READER_VERBOSE="1", IS3D_FAMOD_CHAIN="0")
 t0 = time.time()
 r = subprocess.run([exe], cwd=root, capture_output=True, text=True, env=env)

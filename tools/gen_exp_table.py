@@ -1,4 +1,4 @@
-"""Constants of fast_exp (is3d_b200/csrc/common.cuh): N/ln2 and ln2/N (N = 1024), plus an error scan of the whole
+"""Constants of fast_exp (is3d2_b200/csrc/common.cuh): N/ln2 and ln2/N (N = 1024), plus an error scan of the whole
 construction (one-fma reduction with ln2/N rounded to double, degree-3 polynomial, table entry rounded to double) in
 60-digit arithmetic, reported per range of x (the reduction error grows like |x| 1.1e-16)."""
 import mpmath as mp

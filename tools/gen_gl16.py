@@ -21,7 +21,7 @@ for a in (1, 2, 3):
     r64 = np.array([float(x) for x in r]); w64 = np.array([float(x) for x in w])
     print(a, "max rel diff roots", np.abs(r64/rr-1).max(), "weights", np.abs(w64/rw-1).max())
     out.append((a, r, w))
-with open("/tmp/gl16_tables.txt", "w") as f:  # pasted into is3d_b200/csrc/aniso_gl16.inc
+with open("/tmp/gl16_tables.txt", "w") as f:  # pasted into is3d2_b200/csrc/aniso_gl16.inc
     for a, r, w in out:
         f.write(f"// alpha = {a}\n")
         f.write("{" + ", ".join(mp.nstr(x, 20) for x in r) + "},\n")

@@ -9,7 +9,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
-from is3d_b200 import HostSession, synthetic, workdir  # noqa: E402
+from is3d2_b200 import HostSession, synthetic, workdir  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 s = synthetic.s3d(n, seed=5, baryon=True)
