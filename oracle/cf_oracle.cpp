@@ -747,10 +747,16 @@ extern "C" int cf_oracle_total_yield(const cf_params *p, const cf_inputs *in, do
   return 0;
 }
 
-// dn_tot[cell] (after the 2 y_max ds_max volume factor) and dn_list[cell][species] (before it), df_mode 1-4:
+// dn_tot[cell] (after the 2 y_max ds_max volume factor) and dn_list[cell][species] (before it), df_mode 1-4 (df_mode 5:
+// cell_yields_famod below):
 // fast = 1 fast_max_particle_number (ParticleSampler.cpp:122-161), fast = 0 max_particle_number (:164-239)
+namespace {
+int cell_yields_famod(const cf_params *p, const cf_inputs *in, double *dn_tot, double *dn_list);   // defined below
+}
+
 extern "C" int cf_oracle_cell_yields(const cf_params *p, const cf_inputs *in, double *dn_tot, double *dn_list)
 {
+  if (p->df_mode == 5) return cell_yields_famod(p, in, dn_tot, dn_list);
   if (p->df_mode < 1 || p->df_mode > 4) return 4;
   DfData dfd(p, in);
   double F_avg = 0.0, betabulk_avg = 1.0;
@@ -1099,6 +1105,62 @@ int spectra_famod(const cf_params *p, const cf_inputs *in, double *out, cf_stats
         }
       }
     }
+  }
+  return 0;
+}
+
+// Per-cell mean yields of sample_dN_pTdpTdphidy_famod (ParticleSampler.cpp:1138-1510): anisotropic variables with the
+// SAMPLER's failure rules (a failed first attempt without a previous success is a breakdown and leaves (T, 1, 1), :1369-1374),
+// densities g Lambda^3 detA / (2 pi^2 hbarc^3) I_100 with the 16-point a = 1 rule and exp(Ebar + chem) as written (:1490).
+int cell_yields_famod(const cf_params *p, const cf_inputs *in, double *dn_tot, double *dn_list)
+{
+  Hadrons h{in->pdg_mass, in->pdg_sign, in->pdg_degeneracy, (int)fmin(320, in->n_pdg)};
+  const GenLaguerre16 &gl = gl16();
+  const double y_max = (p->dimension == 2) ? p->y_cut : 0.5;
+  double lambda_prev = 0, aT_prev = 0, aL_prev = 0;
+  bool previous_success = false;
+  for (long icell = 0; icell < in->n_cells; icell++) {
+    dn_tot[icell] = 0.0;
+    if (dn_list) for (int s = 0; s < in->n_species; s++) dn_list[(size_t)icell * in->n_species + s] = 0.0;
+    CellState c;
+    if (!load_cell(p, in, icell, true, false, &c)) continue;
+    Basis b = milne_basis(c);
+    double dst = c.dat * c.ut + c.dax * c.ux + c.day * c.uy + c.dan * c.un;
+    double dsx = -(c.dat * b.Xt + c.dax * b.Xx + c.day * b.Xy + c.dan * b.Xn);
+    double dsy = -(c.dax * b.Yx + c.day * b.Yy);
+    double dsz = -(c.dat * b.Zt + c.dan * b.Zn);
+    double ds_max = fabs(dst) + sqrt(dsx * dsx + dsy * dsy + dsz * dsz);
+    PiLRF l = boost_pi(c, b);
+    double pl = c.P + c.bulkPi + l.zz, pt = c.P + c.bulkPi - l.zz / 2.;
+    double lambda = c.T, aT = 1, aL = 1, upsilonB = c.alphaB;
+    if (!(pl < 0 || pt < 0)) {
+      const bool prev = p->famod_chain && previous_success;
+      if (prev) { lambda = lambda_prev; aT = aT_prev; aL = aL_prev; }
+      Aniso X = find_anisotropic_variables(h, c.E, pl, pt, lambda, aT, aL);
+      if (X.failed) {
+        if (prev) {
+          lambda = c.T; aT = 1; aL = 1;
+          X = find_anisotropic_variables(h, c.E, pl, pt, lambda, aT, aL);
+          if (X.failed) previous_success = false;
+          else { lambda = X.lambda; aT = X.aT; aL = X.aL; lambda_prev = lambda; aT_prev = aT; aL_prev = aL; previous_success = true; }
+        } else previous_success = false;
+      } else { lambda = X.lambda; aT = X.aT; aL = X.aL; lambda_prev = lambda; aT_prev = aT; aL_prev = aL; previous_success = true; }
+    }
+    const double detA = aT * aT * aL, na_fact = lambda * lambda * lambda * detA / two_pi2_hbarC3;
+    double tot = 0.0;
+    for (int s = 0; s < in->n_species; s++) {
+      const double mbar = in->mass[s] / lambda, mbar2 = mbar * mbar, chem = in->baryon[s] * upsilonB, sign = in->sign[s];
+      double I_100 = 0;
+      for (int k = 0; k < 16; k++) {
+        const double pbar = gl.root[1][k], weight = gl.weight[1][k];
+        const double Ebar = sqrt(pbar * pbar + mbar2);
+        I_100 += pbar * weight * exp(pbar) / (exp(Ebar + chem) + sign);
+      }
+      const double v = in->degeneracy[s] * na_fact * I_100;
+      if (dn_list) dn_list[(size_t)icell * in->n_species + s] = v;
+      tot += v;
+    }
+    dn_tot[icell] = (tot > 0.0) ? tot * (2.0 * y_max * ds_max) : 0.0;
   }
   return 0;
 }

@@ -26,12 +26,6 @@ def test_total_and_cell_yields(libs, tmp_path, name):
     # reference: calculate_total_yield (see test_oracle_cpu.py for the baryon-diffusion caveat)
     tol = 1e-4 if case["params"].get("include_baryondiff_deltaf") else 1e-10
     assert abs(ntot / float(ref["total_yield"]) - 1.0) < tol
-    if case["params"]["df_mode"] == 5:
-        # PTMA: per-cell densities come out of the anisotropic Newton solve; they are pinned through the sampled
-        # multiplicities of the reference (test_sampled_histograms_match_reference), not through the oracle
-        assert np.all(np.isfinite(dn_tot)) and np.all(dn_tot >= 0.0) and dn_tot.max() > 0.0
-        assert np.all(dn_list >= 0.0) and np.all((dn_list.sum(axis=1) > 0.0) == (dn_tot > 0.0))
-        return
     # oracle: per-cell dn_tot / dn_list of the sampler
     root = workdir.make_workdir(str(tmp_path / "oracle"), case["params"], chosen=case["chosen"])
     prob = oracle_api.OracleProblem(root, case["params"], surf)
@@ -40,7 +34,7 @@ def test_total_and_cell_yields(libs, tmp_path, name):
     np.testing.assert_allclose(dn_tot, o_tot, rtol=1e-10, atol=1e-300)
     np.testing.assert_allclose(dn_list, o_list, rtol=1e-10, atol=1e-300)
     rc, o_ntot = prob.total_yield()
-    assert abs(ntot / o_ntot - 1.0) < 1e-10
+    assert rc == 0 and abs(ntot / o_ntot - 1.0) < 1e-10
 
 
 @pytest.mark.parametrize("name", list(cases.SAMPLER_CASES))
