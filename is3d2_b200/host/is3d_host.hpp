@@ -116,6 +116,8 @@ class FO_data_reader {
   int mode, dimension, include_baryon;
   long number_of_cells = 0;
   void unmap();
+  bool load_cache(FO_surface &surf);                  // IS3D_SURFACE_CACHE=1: input/surface.dat.soa
+  void store_cache(const FO_surface &surf);
   const char *map_ = nullptr;                         // surface.dat, memory-mapped once
   size_t map_size_ = 0;
   bool mapped_ = false;

@@ -281,11 +281,83 @@ std::vector<double> FO_data_reader::slurp(long columns)
   return v;
 }
 
+// ---- optional binary cache of the parsed surface ("parse once, cache as binary SoA") ------------------
+// IS3D_SURFACE_CACHE=1 keeps the structure-of-arrays columns, as the reader left them, in input/surface.dat.soa next to the
+// text.  The header records the reader settings and the size and modification time of surface.dat; a cache that does not
+// match is ignored and rewritten.  Off by default: the reference writes no such file.
+namespace {
+
+struct CacheHeader {
+  char magic[8];                 // "IS3DSOA1"
+  int64_t n;
+  int32_t mode, dimension, include_baryon, with_vorticity;
+  int64_t source_size, source_mtime_ns;
+};
+
+bool source_stamp(int64_t *size, int64_t *mtime_ns)
+{
+  struct stat st;
+  if (stat(path("input/surface.dat").c_str(), &st) != 0) return false;
+  *size = (int64_t)st.st_size;
+  *mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + (int64_t)st.st_mtim.tv_nsec;
+  return true;
+}
+
+}  // namespace
+
+bool FO_data_reader::load_cache(FO_surface &s)
+{
+  CacheHeader want{}, have{};
+  if (!source_stamp(&want.source_size, &want.source_mtime_ns)) return false;
+  FILE *f = fopen(path("input/surface.dat.soa").c_str(), "rb");
+  if (!f) return false;
+  bool ok = fread(&have, sizeof(have), 1, f) == 1 && memcmp(have.magic, "IS3DSOA1", 8) == 0 && have.n == number_of_cells &&
+            have.mode == mode && have.dimension == dimension && have.include_baryon == include_baryon &&
+            have.source_size == want.source_size && have.source_mtime_ns == want.source_mtime_ns;
+  if (ok) {
+    s.resize(have.n, have.with_vorticity != 0);
+    for (int k = 0; k < IS3D_SURFACE_COLUMNS && ok; k++) ok = fread(s.col[k].data(), sizeof(double), (size_t)have.n, f) == (size_t)have.n;
+    if (have.with_vorticity)
+      for (int k = 0; k < 6 && ok; k++) ok = fread(s.vorticity[k].data(), sizeof(double), (size_t)have.n, f) == (size_t)have.n;
+  }
+  fclose(f);
+  return ok;
+}
+
+void FO_data_reader::store_cache(const FO_surface &s)
+{
+  CacheHeader h{};
+  memcpy(h.magic, "IS3DSOA1", 8);
+  h.n = s.size(); h.mode = mode; h.dimension = dimension; h.include_baryon = include_baryon;
+  h.with_vorticity = s.vorticity[0].empty() ? 0 : 1;
+  if (!source_stamp(&h.source_size, &h.source_mtime_ns)) return;
+  FILE *f = fopen(path("input/surface.dat.soa").c_str(), "wb");
+  if (!f) return;                                        // read-only input directory: run without a cache
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  for (int k = 0; k < IS3D_SURFACE_COLUMNS && ok; k++) ok = fwrite(s.col[k].data(), sizeof(double), (size_t)h.n, f) == (size_t)h.n;
+  if (h.with_vorticity)
+    for (int k = 0; k < 6 && ok; k++) ok = fwrite(s.vorticity[k].data(), sizeof(double), (size_t)h.n, f) == (size_t)h.n;
+  fclose(f);
+  if (!ok) remove(path("input/surface.dat.soa").c_str());
+}
+
 void FO_data_reader::read_freezeout_surface(FO_surface &surf)
 {
+  const char *env = getenv("IS3D_SURFACE_CACHE");
+  const bool use_cache = env && atoi(env) != 0;
+  if (use_cache && mapped_ && load_cache(surf)) {
+    unmap();
+    printf("Freezeout surface taken from the binary cache input/surface.dat.soa\n");
+    double avg[5];
+    compute_thermodynamic_averages(surf, avg);
+    if (mode == 7) avg[4] = 0.0;
+    write_thermodynamic_averages(avg);
+    return;
+  }
   if (mode == 1 || mode == 5) read_surface_cpu_vh(surf);
   else if (mode == 6) read_surface_music(surf);
   else if (mode == 7) read_surface_hic_eventgen(surf);
+  if (use_cache) store_cache(surf);
 }
 
 // mode 1: t x y n ds_t ds_x ds_y ds_n u^x u^y u^n E T P pi^xx pi^xy pi^xn pi^yy pi^yn Pi [muB nB V^x V^y V^n] [6 wbar]

@@ -198,3 +198,39 @@ def test_surface_readers_match_reference(libs, tmp_path, mode, dimension, baryon
     a = open(os.path.join(roots["ref"], "tables", "thermodynamic", "average_thermodynamic_quantities.dat")).read()
     b = open(os.path.join(roots["mine"], "tables", "thermodynamic", "average_thermodynamic_quantities.dat")).read()
     assert a == b
+
+
+def test_surface_binary_cache(libs, tmp_path, monkeypatch):
+    """IS3D_SURFACE_CACHE=1: the first read parses the text and writes input/surface.dat.soa, the second read takes the
+    columns from it (bit-identical surface and average file); touching surface.dat or changing a reader setting
+    invalidates the cache."""
+    n = 5000
+    s = synthetic.s3d(n, seed=81, baryon=True)
+    params = dict(hrg_eos=2, df_mode=2, dimension=3, mode=1, include_baryon=1)
+    root = workdir.make_workdir(str(tmp_path), params, chosen="pikp")
+    p = os.path.join(root, "input", "surface.dat")
+    synthetic.write_mode1(p, s, baryon=True)
+    avg_file = os.path.join(root, "tables", "thermodynamic", "average_thermodynamic_quantities.dat")
+
+    def read():
+        with HostSession(root) as h:
+            assert h.read_surface() == n
+            return [h.surface_column(k).copy() for k in range(25)], open(avg_file).read()
+    plain, avg0 = read()
+    assert not os.path.exists(p + ".soa")
+    monkeypatch.setenv("IS3D_SURFACE_CACHE", "1")
+    first, avg1 = read()
+    assert os.path.exists(p + ".soa") and os.path.getsize(p + ".soa") > 25 * 8 * n
+    stamp = os.path.getmtime(p + ".soa")
+    second, avg2 = read()
+    assert os.path.getmtime(p + ".soa") == stamp                           # served from the cache, not rewritten
+    for a, b, c in zip(plain, first, second):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)
+    assert avg0 == avg1 == avg2
+    # a changed surface.dat (new cell values, same length) must not be served from the stale cache
+    s2 = synthetic.s3d(n, seed=82, baryon=True)
+    synthetic.write_mode1(p, s2, baryon=True)
+    os.utime(p, (stamp + 10, stamp + 10))
+    third, _ = read()
+    np.testing.assert_array_equal(third[0], synthetic.roundtrip_mode1(s2, baryon=True)["tau"])
