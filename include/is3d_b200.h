@@ -82,6 +82,9 @@ typedef struct {
                                     cell's solution, MomentumSpectra.cpp:1308-1364), 0 = chain-free (T,1,1) */
   int dndx_bug_compat;           /* 1 = reproduce the reference's partial memset (SpacetimeDistribution.cpp:166-168):
                                     histograms accumulate over species above bin CORES*bins/8 */
+  int polzn_chunk_compat;        /* 1 = spin polarization reads the thermal vorticity with the index INSIDE the reference's
+                                    10 000-cell chunk (Polarization.cpp:125-130 use wtx_fo[icell], not [icell_glb]); identical
+                                    to 0 for surfaces of up to 10 000 cells */
 } is3d_params;
 
 /* Counters the reference prints (MomentumSpectra.cpp:1039-1040, :1674-1679; ParticleSampler.cpp:1133). */
@@ -163,6 +166,10 @@ is3d_status is3d_set_surface(is3d_ctx *ctx, int64_t n, const double *const cols[
 is3d_status is3d_set_surface_device(is3d_ctx *ctx, int64_t n, const double *const cols[IS3D_SURFACE_COLUMNS],
                                     int64_t global_offset);
 
+/* thermal vorticity of a mode-5 surface (readindata.cpp:299-307): w[k] = host pointer to n doubles, k = wtx wty wtn wxy
+ * wxn wyn (FO_surf order, readindata.h:90); n must equal the surface set last.  Copied to HBM. */
+is3d_status is3d_set_vorticity(is3d_ctx *ctx, int64_t n, const double *const w[6]);
+
 /* ---- compute (reference: the eight compute members, EmissionFunction.h:147-179) ----------------------------- */
 /* number of doubles is3d_spectra writes: Ns * NpT * Nphi * Ny, index iy + Ny*(iphi + Nphi*(ipT + NpT*is))
  * (MomentumSpectra.cpp:252-295) */
@@ -178,6 +185,12 @@ is3d_status is3d_spectra_device(is3d_ctx *ctx, double *out_device, is3d_stats *s
 is3d_status is3d_dndx(is3d_ctx *ctx, double *tau_hist, double *r_hist, double *phi_hist, is3d_stats *stats);
 is3d_status is3d_dndx_device(is3d_ctx *ctx, double *tau_hist_dev, double *r_hist_dev, double *phi_hist_dev,
                              is3d_stats *stats);
+
+/* calculate_spin_polzn (EmissionFunction.h, src/cpp/Polarization.cpp:25-263; run by calculate_spectra for mode-5 surfaces,
+ * EmissionFunction.cpp:1304-1310): the four components of the polarization vector and its norm, each Ns NpT Nphi Ny doubles in
+ * the SPECTRA layout iy + Ny*(iphi + Nphi*(ipT + NpT*is)); host buffers.  (The reference stores them species-fastest and
+ * writes them with the spectra index; that file-level mix-up lives in the host layer's writer, not here.) */
+is3d_status is3d_polarization(is3d_ctx *ctx, double *St, double *Sx, double *Sy, double *Sn, double *Snorm, is3d_stats *stats);
 
 /* calculate_total_yield (EmissionFunction.h:172) */
 is3d_status is3d_total_yield(is3d_ctx *ctx, double *ntotal, is3d_stats *stats);

@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
-CU_SOURCES = ["api.cu", "spectra_df.cu", "spectra_feqmod.cu", "dndx.cu", "sampler.cu", "spectra_famod.cu", "fp64_peak.cu"]
+CU_SOURCES = ["api.cu", "spectra_df.cu", "spectra_feqmod.cu", "dndx.cu", "sampler.cu", "spectra_famod.cu", "polarization.cu",
+              "fp64_peak.cu"]
 HOST_SOURCES = ["io.cpp", "surface.cpp", "pdg.cpp", "deltaf.cpp", "emission.cpp", "is3d.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]

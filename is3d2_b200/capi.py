@@ -25,7 +25,7 @@ class Params(C.Structure):
                 ("phip_bins", C.c_int), ("eta_cut", C.c_double), ("eta_bins", C.c_int),
                 ("tau_min", C.c_double), ("tau_max", C.c_double), ("tau_bins", C.c_int),
                 ("r_min", C.c_double), ("r_max", C.c_double), ("r_bins", C.c_int),
-                ("device", C.c_int), ("famod_chain", C.c_int), ("dndx_bug_compat", C.c_int)]
+                ("device", C.c_int), ("famod_chain", C.c_int), ("dndx_bug_compat", C.c_int), ("polzn_chunk_compat", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -60,7 +60,8 @@ ABI_SYMBOLS = ["is3d_default_params", "is3d_create", "is3d_destroy", "is3d_last_
                "is3d_set_thermo_averages", "is3d_set_df_tables", "is3d_set_ptb_tables", "is3d_set_surface",
                "is3d_set_surface_device", "is3d_spectra_size", "is3d_spectra", "is3d_spectra_device", "is3d_dndx",
                "is3d_dndx_device", "is3d_total_yield", "is3d_cell_yields", "is3d_sample", "is3d_free_particles",
-               "is3d_sample_histograms", "is3d_measure_fp64_peak", "is3d_probe_math", "is3d_stream"]
+               "is3d_sample_histograms", "is3d_set_vorticity", "is3d_polarization", "is3d_measure_fp64_peak", "is3d_probe_math",
+               "is3d_stream"]
 HOST_SYMBOLS = ["is3d_host_open", "is3d_host_close", "is3d_host_read_surface", "is3d_host_set_surface",
                 "is3d_host_prepare", "is3d_host_prepare_tables", "is3d_host_context", "is3d_host_run",
                 "is3d_host_spectra", "is3d_host_dndx", "is3d_host_events", "is3d_host_event_particles",
@@ -100,6 +101,8 @@ def load_libraries():
     lib.is3d_free_particles.argtypes = [vp]
     lib.is3d_sample_histograms.argtypes = [vp] + [vp] * 10
     lib.is3d_measure_fp64_peak.argtypes = [vp, dp]
+    lib.is3d_set_vorticity.argtypes = [vp, C.c_int64, C.POINTER(vp)]
+    lib.is3d_polarization.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Stats)]
     lib.is3d_probe_math.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
     lib.is3d_stream.restype = vp
     lib.is3d_stream.argtypes = [vp]
@@ -262,6 +265,20 @@ class HostSession:
         v = C.c_double()
         self._check(self.lib.is3d_measure_fp64_peak(self.ctx, C.byref(v)), "is3d_measure_fp64_peak")
         return v.value
+
+    def abi_set_vorticity(self, w6):
+        """w6: six arrays wtx wty wtn wxy wxn wyn (length = cells of the surface set last)."""
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in w6]
+        arr = (C.c_void_p * 6)(*[a.ctypes.data for a in keep])
+        self._check(self.lib.is3d_set_vorticity(self.ctx, len(keep[0]), arr), "is3d_set_vorticity")
+
+    def abi_polarization(self):
+        """(St, Sx, Sy, Sn, Snorm) in the spectra layout (Ns, NpT, Nphi, Ny), stats."""
+        shape = self.spectra_shape()
+        outs = [np.zeros(int(np.prod(shape))) for _ in range(5)]
+        st = Stats()
+        self._check(self.lib.is3d_polarization(self.ctx, *[_ptr(o) for o in outs], C.byref(st)), "is3d_polarization")
+        return [o.reshape(shape) for o in outs], st
 
     def abi_probe_math(self, x: np.ndarray):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -23,7 +23,7 @@ void is3d_default_params(is3d_params *p)
   p->pT_min = 0.0; p->pT_max = 3.0; p->pT_bins = 100; p->y_bins = 100; p->phip_bins = 100;
   p->eta_cut = 7.0; p->eta_bins = 140; p->tau_min = 0.0; p->tau_max = 12.0; p->tau_bins = 120;
   p->r_min = 0.0; p->r_max = 12.0; p->r_bins = 60;
-  p->device = 0; p->famod_chain = 1; p->dndx_bug_compat = 0;
+  p->device = 0; p->famod_chain = 1; p->dndx_bug_compat = 0; p->polzn_chunk_compat = 1;
 }
 
 const char *is3d_last_error(const is3d_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -350,6 +350,42 @@ is3d_status is3d_spectra(is3d_ctx *ctx, double *out, is3d_stats *stats)
   IS3D_TRY(ctx->get_scratch("spectra_out", (size_t)(total > 0 ? total : 1) * sizeof(double), &d));
   IS3D_TRY(is3d_spectra_device(ctx, (double *)d, stats));
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(out, d, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return IS3D_OK;
+}
+
+is3d_status is3d_set_vorticity(is3d_ctx *ctx, int64_t n, const double *const w[6])
+{
+  CTX_ENTER(ctx);
+  if (n < 0 || !w) { ctx->set_error("set_vorticity: bad arguments"); return IS3D_ERR_INVALID; }
+  for (int k = 0; k < 6; k++) if (!w[k] && n > 0) { ctx->set_error("set_vorticity: NULL column " + std::to_string(k)); return IS3D_ERR_INVALID; }
+  if (!ctx->have_surface || ctx->surf.n != n) { ctx->set_error("set_vorticity: set the surface first (same number of cells)"); return IS3D_ERR_INVALID; }
+  const int64_t pitch = (n + 31) / 32 * 32;
+  if (ctx->d_vorticity) { ctx->dev_free(ctx->d_vorticity); ctx->d_vorticity = nullptr; }
+  void *blk = nullptr;
+  IS3D_TRY(ctx->dev_alloc(&blk, (size_t)6 * (pitch ? pitch : 32) * sizeof(double)));
+  ctx->d_vorticity = (double *)blk;
+  for (int k = 0; k < 6 && n; k++)
+    IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vorticity + (size_t)k * pitch, w[k], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->vorticity_n = n; ctx->vorticity_pitch = pitch; ctx->have_vorticity = true;
+  return IS3D_OK;
+}
+
+is3d_status is3d_polarization(is3d_ctx *ctx, double *St, double *Sx, double *Sy, double *Sn, double *Snorm, is3d_stats *stats)
+{
+  CTX_ENTER(ctx);
+  if (!St || !Sx || !Sy || !Sn || !Snorm) { ctx->set_error("polarization: NULL output"); return IS3D_ERR_INVALID; }
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (ctx->ns <= 0 || !ctx->have_momentum || !ctx->have_surface) { ctx->set_error("polarization: species / momentum tables / surface not set"); return IS3D_ERR_INVALID; }
+  const int64_t total = is3d_spectra_size(ctx);
+  double *outs[5] = {St, Sx, Sy, Sn, Snorm};
+  if (ctx->surf.n == 0) { for (double *o : outs) std::memset(o, 0, (size_t)total * sizeof(double)); return IS3D_OK; }
+  void *d = nullptr;
+  IS3D_TRY(ctx->get_scratch("pol_out", (size_t)5 * total * sizeof(double), &d));
+  IS3D_TRY(run_polarization(ctx, (double *)d, stats));
+  for (int k = 0; k < 5; k++)
+    IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(outs[k], (double *)d + (size_t)k * total, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return IS3D_OK;
 }

@@ -81,6 +81,11 @@ struct is3d_ctx {
   double *d_surface_block = nullptr;       // one (grow-only) allocation holding all owned columns
   size_t surface_block_bytes = 0;
 
+  // thermal vorticity (mode-5 surfaces): six columns, one allocation
+  bool have_vorticity = false;
+  int64_t vorticity_n = 0, vorticity_pitch = 0;
+  double *d_vorticity = nullptr;
+
   // sampler histograms (device)
   std::map<std::string, double *> hist;
 
@@ -162,6 +167,7 @@ is3d_status run_cell_yields(is3d_ctx *ctx, double *dn_tot_host, double *dn_list_
 is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts,
                         is3d_stats *stats);
 void release_host_lists_of(is3d_ctx *ctx);
+is3d_status run_polarization(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);
 is3d_status measure_fp64_peak(is3d_ctx *ctx, double *tflops);
 is3d_status probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp, double *out_sqrt);
 

@@ -79,6 +79,8 @@ EmissionFunctionArray::EmissionFunctionArray(ParameterReader *paraRdr_in, Table 
   if (const char *dev = getenv("IS3D_DEVICE")) prm.device = atoi(dev);
   if (const char *v = getenv("IS3D_FAMOD_CHAIN")) prm.famod_chain = atoi(v);
   if (const char *v = getenv("IS3D_DNDX_BUG_COMPAT")) prm.dndx_bug_compat = atoi(v);
+  if (const char *v = getenv("IS3D_POLZN_CHUNK_COMPAT")) prm.polzn_chunk_compat = atoi(v);
+  if (const char *v = getenv("IS3D_POLZN_FILE_COMPAT")) polzn_file_compat = atoi(v);
 
   // chosen species in file order, matched by Monte-Carlo id (EmissionFunction.cpp:357-372); the optional mass sort
   // of group_particles only affected the (removed) resonance-decay code
@@ -263,9 +265,65 @@ void EmissionFunctionArray::calculate_spectra(std::vector<std::vector<Sampled_Pa
     }
     default: fatal("calculate_spectra error: need to set operation = (0, 1, 2)");
   }
-  if (MODE == 5) printf("\nSpin polarization (mode 5 surfaces) is outside the scope of this build; skipped.\n");
+  if (MODE == 5) {                       // EmissionFunction.cpp:1304-1310
+    printf("\nComputing spin polarization...\n");
+    calculate_spin_polzn();
+    write_polzn_vector_toFile();
+  }
   seconds_compute = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printf("\nSpectra calculation took %g seconds\n\n", seconds_compute);
+}
+
+#define IDX(iy, iphi, ipT, is) ((iy) + y_tab_length * ((iphi) + phi_tab_length * ((ipT) + pT_tab_length * (long)(is))))
+
+static FILE *open_result(const char *fmt, int id, const char *mode);
+
+// calculate_spin_polzn (Polarization.cpp:25-263) through the C ABI; arrays come back in the spectra layout
+void EmissionFunctionArray::calculate_spin_polzn()
+{
+  if (surf->vorticity[0].size() != (size_t)surf->size()) fatal("calculate_spin_polzn error: the surface carries no thermal vorticity (mode 5 file needed)");
+  const double *w[6];
+  for (int k = 0; k < 6; k++) w[k] = surf->vorticity[k].data();
+  check(is3d_set_vorticity(ctx, surf->size(), w), "is3d_set_vorticity");
+  const size_t total = (size_t)is3d_spectra_size(ctx);
+  for (auto *v : {&St, &Sx, &Sy, &Sn, &Snorm}) v->assign(total, 0.0);
+  is3d_stats pst;
+  check(is3d_polarization(ctx, St.data(), Sx.data(), Sy.data(), Sn.data(), Snorm.data(), &pst), "calculate_spin_polzn");
+}
+
+// write_polzn_vector_toFile (EmissionFunction.cpp:561-609): results/{St,Sx,Sy,Sn}.dat, rows `y phip pT S/Snorm`, loop order
+// species -> y -> phi -> pT, blank line after each phi block.  The reference ACCUMULATES the arrays species-fastest
+// (iS3D = ipart + npart (ipT + NpT (iphip + Nphi iy)), Polarization.cpp:226) but READS them here with the spectra index
+// (iy + Ny (iphip + Nphi (ipT + NpT ipart)), :591), so the value printed next to (species, y, phi, pT) belongs to another
+// bin.  polzn_file_compat = 1 (default; IS3D_POLZN_FILE_COMPAT=0 switches it off) reproduces the files as the reference
+// writes them; 0 prints each bin's own value.
+void EmissionFunctionArray::write_polzn_vector_toFile()
+{
+  printf("Writing polarization vector to file...\n");
+  FILE *f[4] = {open_result("results/St.dat", 0, "w"), open_result("results/Sx.dat", 0, "w"), open_result("results/Sy.dat", 0, "w"),
+                open_result("results/Sn.dat", 0, "w")};
+  const std::vector<double> *S[4] = {&St, &Sx, &Sy, &Sn};
+  const long np = number_of_chosen_particles, npT = pT_tab_length, nphi = phi_tab_length, ny = y_tab_length;
+  for (long ipart = 0; ipart < np; ipart++)
+    for (long iy = 0; iy < ny; iy++) {
+      double y = (DIMENSION == 3) ? y_tab->get(1, iy + 1) : 0.0;
+      for (long iphip = 0; iphip < nphi; iphip++) {
+        double phip = phi_tab->get(1, iphip + 1);
+        for (long ipT = 0; ipT < npT; ipT++) {
+          long j = IDX(iy, iphip, ipT, ipart);               // the index the reference reads with
+          long src = j;
+          if (polzn_file_compat) {
+            // decode j in the storage order of the accumulation, then address that bin in our (spectra-layout) arrays
+            long sp = j % np, r = j / np, p2 = r % npT, r2 = r / npT, ph = r2 % nphi, yy = r2 / nphi;
+            src = IDX(yy, ph, p2, sp);
+          }
+          for (int k = 0; k < 4; k++)
+            fprintf(f[k], "%.8e\t%.8e\t%.8e\t%.8e\n", y, phip, pT_tab->get(1, ipT + 1), (*S[k])[src] / Snorm[src]);
+        }
+        for (int k = 0; k < 4; k++) fprintf(f[k], "\n");
+      }
+    }
+  for (int k = 0; k < 4; k++) fclose(f[k]);
 }
 
 // ---- writers ---------------------------------------------------------------------------------------------------
@@ -287,7 +345,6 @@ static FILE *open_result(const char *fmt, int id, const char *mode = "w")
   return f;
 }
 
-#define IDX(iy, iphi, ipT, is) ((iy) + y_tab_length * ((iphi) + phi_tab_length * ((ipT) + pT_tab_length * (long)(is))))
 
 void EmissionFunctionArray::write_dN_pTdpTdphidy_toFile()
 {

@@ -179,6 +179,8 @@ class EmissionFunctionArray {
   void write_dN_dy_toFile();
   void write_continuous_vn_toFile();
   void write_dN_dX_toFile();
+  void calculate_spin_polzn();
+  void write_polzn_vector_toFile();
   void write_particle_list_OSC();
   void write_sampled_tests_to_file();
 
@@ -186,6 +188,8 @@ class EmissionFunctionArray {
   void set_surface_on_device();             // (re)upload the SoA surface
 
   std::vector<double> dN_pTdpTdphidy;       // Ns*NpT*Nphi*Ny, same indexing as the reference
+  std::vector<double> St, Sx, Sy, Sn, Snorm; // spin polarization (mode-5 surfaces), spectra layout
+  int polzn_file_compat = 1;                // reproduce the reference's storage / read index mismatch in results/S*.dat
   std::vector<double> dN_taudtaudy, dN_twopirdrdy, dN_dphisdy;   // dN/dX histograms, Ns x bins
   std::vector<std::vector<Sampled_Particle>> particle_event_list;
   long Nevents = 1;

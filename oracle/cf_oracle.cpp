@@ -1166,3 +1166,67 @@ int cell_yields_famod(const cf_params *p, const cf_inputs *in, double *dn_tot, d
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// calculate_spin_polzn, Polarization.cpp:25-263.  f0 is taken at the surface-averaged temperature (:76, :186); cells
+// with u.dsigma <= 0 are not skipped; the vorticity index is the in-chunk index (:125-130) when chunk_compat is set.
+// Output in the spectra layout (the reference's own storage order, species fastest, :201, :226, is a relabelling).
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int cf_oracle_polarization(const cf_params *p, const cf_inputs *in, const double *const w[6], int chunk_compat,
+                                      double *St, double *Sx, double *Sy, double *Sn, double *Snorm)
+{
+  const int npart = in->n_species, npT = in->n_pT, nphi = in->n_phi;
+  const int y_pts = (p->dimension == 2) ? 1 : in->n_y, eta_pts = (p->dimension == 2) ? in->n_eta : 1;
+  const long FO_chunk = 10000;
+  const long total = (long)npart * npT * nphi * y_pts;
+  for (long i = 0; i < total; i++) St[i] = Sx[i] = Sy[i] = Sn[i] = Snorm[i] = 0.0;
+  std::vector<double> cosphi(nphi), sinphi(nphi), yv(y_pts, 0.0), etav(eta_pts, 0.0), etaw(eta_pts, 1.0);
+  for (int j = 0; j < nphi; j++) { cosphi[j] = cos(in->phi[j]); sinphi[j] = sin(in->phi[j]); }
+  const double delta_eta = (in->n_eta > 1) ? in->eta[1] - in->eta[0] : 0.0;
+  if (p->dimension == 2) for (int k = 0; k < eta_pts; k++) { etav[k] = in->eta[k]; etaw[k] = in->eta_w[k] * delta_eta; }
+  else for (int iy = 0; iy < y_pts; iy++) yv[iy] = in->y[iy];
+  const double T = in->T_avg;
+  for (long icell_glb = 0; icell_glb < in->n_cells; icell_glb++) {
+    const long icell = icell_glb % FO_chunk;
+    const long iw = chunk_compat ? icell : icell_glb;
+    const double tau = in->col[0][icell_glb], tau2 = tau * tau;
+    if (p->dimension == 3) etav[0] = in->col[3][icell_glb];
+    const double dat = in->col[4][icell_glb], dax = in->col[5][icell_glb], day = in->col[6][icell_glb], dan = in->col[7][icell_glb];
+    const double ux = in->col[8][icell_glb], uy = in->col[9][icell_glb], un = in->col[10][icell_glb];
+    const double ut = sqrt(fabs(1.0 + ux * ux + uy * uy + tau2 * un * un));
+    const double wtx = w[0][iw], wty = w[1][iw], wtn = w[2][iw], wxy = w[3][iw], wxn = w[4][iw], wyn = w[5][iw];
+    for (int ipart = 0; ipart < npart; ipart++) {
+      const double mass = in->mass[ipart], mass2 = mass * mass, sign = in->sign[ipart];
+      for (int ipT = 0; ipT < npT; ipT++) {
+        const double pT = in->pT[ipT], mT = sqrt(mass2 + pT * pT), mT_over_tau = mT / tau;
+        for (int iphip = 0; iphip < nphi; iphip++) {
+          const double px = pT * cosphi[iphip], py = pT * sinphi[iphip];
+          for (int iy = 0; iy < y_pts; iy++) {
+            const double y = yv[iy];
+            double st = 0, sx = 0, sy = 0, sn = 0, snorm = 0;
+            for (int ieta = 0; ieta < eta_pts; ieta++) {
+              const double eta = etav[ieta], wgt = etaw[ieta];
+              const double pt = mT * cosh(y - eta), pn = mT_over_tau * sinh(y - eta), tau2_pn = tau2 * pn;
+              const double pdotdsigma = pt * dat + px * dax + py * day + pn * dan;
+              const double pdotu = pt * ut - px * ux - py * uy - tau2_pn * un;
+              const double f0 = 1.0 / (exp(pdotu / T) + sign);
+              const double prefactor = -(1.0 / 8.0 / mass) * (1.0 - sign * f0);
+              const double spin_t = prefactor * 2.0 * (wxy * pn - wxn * py + wyn * px);
+              const double spin_x = prefactor * 2.0 * (wyn * pt - wtn * py + wty * pn);
+              const double spin_y = prefactor * 2.0 * (-wxn * pt + wtn * px - wtx * pn);
+              const double spin_n = prefactor * 2.0 * (wtx * py + wxy * pt - wty * px);
+              st += (wgt * pdotdsigma * f0 * spin_t);
+              sx += (wgt * pdotdsigma * f0 * spin_x);
+              sy += (wgt * pdotdsigma * f0 * spin_y);
+              sn += (wgt * pdotdsigma * f0 * spin_n);
+              snorm += (wgt * pdotdsigma * f0);
+            }
+            const long idx = iy + (long)y_pts * (iphip + (long)nphi * (ipT + (long)npT * ipart));
+            St[idx] += st; Sx[idx] += sx; Sy[idx] += sy; Sn[idx] += sn; Snorm[idx] += snorm;
+          }
+        }
+      }
+    }
+  }
+  return 0;
+}

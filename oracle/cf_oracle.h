@@ -76,6 +76,12 @@ int cf_oracle_dndx(const cf_params *p, const cf_inputs *in, double *tau_hist, do
 int cf_oracle_total_yield(const cf_params *p, const cf_inputs *in, double *ntotal);
 int cf_oracle_cell_yields(const cf_params *p, const cf_inputs *in, double *dn_tot, double *dn_list);
 
+/* calculate_spin_polzn (Polarization.cpp:25-263): w = thermal vorticity columns wtx wty wtn wxy wxn wyn; St..Snorm have
+ * n_species * n_pT * n_phi * Ny doubles each in the spectra layout.  chunk_compat = 1 reads the vorticity with the index
+ * inside the reference's 10 000-cell chunk (:125-130). */
+int cf_oracle_polarization(const cf_params *p, const cf_inputs *in, const double *const w[6], int chunk_compat, double *St,
+                           double *Sx, double *Sy, double *Sn, double *Snorm);
+
 #ifdef __cplusplus
 }
 #endif

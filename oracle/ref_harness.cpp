@@ -159,6 +159,18 @@ int main(int argc, char **argv)
     wr(f, efa.dN_pTdpTdphidy, sizeof(double) * dims[0] * dims[1] * dims[2] * dims[3]);
     fclose(f);
   }
+  if((int)paraRdr->getVal("mode") == 5)
+  {
+    // spin polarization (Polarization.cpp): the five arrays in the reference's STORAGE order, species fastest
+    // (iS3D = ipart + npart * (ipT + NpT * (iphip + Nphi * iy)), :226)
+    FILE *f = fopen("ref_dump/polarization.bin", "wb");
+    long dims[4] = {(long)efa.number_of_chosen_particles, efa.pT_tab_length, efa.phi_tab_length, efa.y_tab_length};
+    long ntot = dims[0] * dims[1] * dims[2] * dims[3];
+    wr(f, dims, sizeof(dims));
+    wr(f, efa.St, sizeof(double) * ntot); wr(f, efa.Sx, sizeof(double) * ntot); wr(f, efa.Sy, sizeof(double) * ntot);
+    wr(f, efa.Sn, sizeof(double) * ntot); wr(f, efa.Snorm, sizeof(double) * ntot);
+    fclose(f);
+  }
   if(operation == 2)
   {
     FILE *g = fopen("ref_dump/nevents.txt", "w");

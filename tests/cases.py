@@ -112,3 +112,13 @@ SAMPLER_CASES = {
     "smp_s3d_m5_stress": dict(surface=("s3d", dict(n=300, seed=58, stress=0.3)), params=_p(df_mode=5, **_S), chosen="pikp"),
     "smp_s2d_m5": dict(surface=("s3d", dict(n=200, seed=59, dimension=2, vah=True)), params=_p(df_mode=5, dimension=2, hrg_eos=1, **_S), chosen="pikp"),
 }
+
+# spin polarization (mode-5 surfaces: thermal vorticity columns; runs after any operation, reference EmissionFunction.cpp:1304-1310)
+_POL = dict(operation=1, mode=5, df_mode=2)
+POLZN_CASES = {
+    "pol_s3d": dict(surface=("s3d", dict(n=300, seed=61)), params=_p(**_POL), chosen="pikp"),
+    "pol_s2d_phi48": dict(surface=("s3d", dict(n=120, seed=62, dimension=2)), params=_p(dimension=2, hrg_eos=1, **_POL), chosen="pikp",
+                          tables=dict(phi_table="phi_table_48pt.dat")),
+    # more than one 10 000-cell chunk: the reference pairs cell 10 000 + k with the vorticity of cell k (Polarization.cpp:125-130)
+    "pol_s3d_10257cells": dict(surface=("s3d", dict(n=10257, seed=64)), params=_p(**_POL), chosen="pikp"),
+}

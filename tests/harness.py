@@ -113,3 +113,35 @@ def chi2_two_sample(a, sa, b, sb, min_counts=100):
     d = a[m] / sa - b[m] / sb
     v = a[m] / sa ** 2 + b[m] / sb ** 2
     return float((d * d / v).sum()), int(m.sum())
+
+
+# ---- spin polarization helpers -----------------------------------------------------------------------------------
+def load_golden_polzn(name: str):
+    """(surface columns, vorticity (6, n), reference arrays (5, Ns, NpT, Nphi, Ny)); large cases regenerate their inputs
+    from the seeds exactly as tests/golden/make_golden_polzn.py wrote them."""
+    import tempfile
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    if "vorticity" in z.files:
+        surf = {k[4:]: z[k] for k in z.files if k.startswith("col_")}
+        return surf, z["vorticity"], z["polarization"]
+    case = cases.POLZN_CASES[name]
+    s = cases.make_surface(case["surface"])
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "surface.dat")
+        synthetic.write_mode5(p, s, baryon=False, seed=len(s["tau"]))
+        flat = np.loadtxt(p, ndmin=2)
+    return synthetic.roundtrip_mode1(s, baryon=False), np.ascontiguousarray(flat[:, 20:26].T), z["polarization"]
+
+
+def assert_polzn_close(got: np.ndarray, ref: np.ndarray, rtol: float = RTOL, what: str = ""):
+    """Per component and species: |got - ref| <= rtol |ref| + 1e-13 of the component's largest bin of that species."""
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert np.all(np.isfinite(got)), f"{what}: non-finite values"
+    peak = np.abs(ref).reshape(ref.shape[0], ref.shape[1], -1).max(axis=2).reshape(ref.shape[:2] + (1, 1, 1))
+    err = np.abs(got - ref)
+    bad = err > rtol * np.abs(ref) + ATOL_OF_SPECIES_PEAK * peak
+    if bad.any():
+        i = np.unravel_index(np.argmax(err / (np.abs(ref) + ATOL_OF_SPECIES_PEAK * peak + 1e-300)), ref.shape)
+        raise AssertionError(f"{what}: {bad.sum()} of {ref.size} entries differ by more than {rtol:g}; worst at {i}: got {got[i]!r} ref {ref[i]!r}")
+    big = np.abs(ref) > 1e3 * ATOL_OF_SPECIES_PEAK * peak
+    return float((err[big] / np.abs(ref[big])).max()) if big.any() else 0.0

@@ -57,6 +57,7 @@ def lib():
         _lib.cf_oracle_dndx.argtypes = [C.POINTER(CfParams), C.POINTER(CfInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CfStats)]
         _lib.cf_oracle_total_yield.argtypes = [C.POINTER(CfParams), C.POINTER(CfInputs), dp]
         _lib.cf_oracle_cell_yields.argtypes = [C.POINTER(CfParams), C.POINTER(CfInputs), C.c_void_p, C.c_void_p]
+        _lib.cf_oracle_polarization.argtypes = [C.POINTER(CfParams), C.POINTER(CfInputs), C.POINTER(C.c_void_p), C.c_int] + [C.c_void_p] * 5
     return _lib
 
 
@@ -184,3 +185,16 @@ def _cell_yields(self):
 
 OracleProblem.total_yield = _total_yield
 OracleProblem.cell_yields = _cell_yields
+
+
+def _polarization(self, vorticity, chunk_compat: int = 1):
+    """(5, Ns, NpT, Nphi, Ny): St, Sx, Sy, Sn, Snorm in the spectra layout."""
+    shape = (self.inp.n_species, self.inp.n_pT, self.inp.n_phi, self.ny)
+    outs = [np.zeros(shape) for _ in range(5)]
+    keep = [np.ascontiguousarray(w, dtype=np.float64) for w in vorticity]
+    arr = (C.c_void_p * 6)(*[w.ctypes.data for w in keep])
+    rc = lib().cf_oracle_polarization(C.byref(self.p), C.byref(self.inp), arr, chunk_compat, *[o.ctypes.data for o in outs])
+    return rc, np.stack(outs)
+
+
+OracleProblem.polarization = _polarization

@@ -24,7 +24,10 @@ def run_ref(root: str, surface: dict, params: dict, chosen: str = "pikp", baryon
     if baryon is None:
         baryon = bool(int(params.get("include_baryon", 0)))
     workdir.make_workdir(root, params, chosen=chosen, **tables)
-    synthetic.write_mode1(os.path.join(root, "input", "surface.dat"), surface, baryon=baryon)
+    if int(params.get("mode", 1)) == 5:       # mode 1 columns + thermal vorticity (seeded by the cell count)
+        synthetic.write_mode5(os.path.join(root, "input", "surface.dat"), surface, baryon=baryon, seed=len(surface["tau"]))
+    else:
+        synthetic.write_mode1(os.path.join(root, "input", "surface.dat"), surface, baryon=baryon)
     env = dict(os.environ)
     exe = REF_BIN
     if omp_threads:
@@ -59,6 +62,12 @@ def read_dumps(root: str) -> dict:
         raw = open(p, "rb").read()
         dims = struct.unpack("4l", raw[:32])
         out["spectra"] = np.frombuffer(raw[32:], dtype=np.float64).reshape(dims).copy()
+    p = os.path.join(d, "polarization.bin")
+    if os.path.exists(p):
+        raw = open(p, "rb").read()
+        ns, npT, nphi, ny = struct.unpack("4l", raw[:32])
+        a = np.frombuffer(raw[32:], dtype=np.float64).reshape(5, ny, nphi, npT, ns)      # storage order: species fastest
+        out["polarization"] = np.ascontiguousarray(np.transpose(a, (0, 4, 3, 2, 1)))       # -> (5, Ns, NpT, Nphi, Ny)
     p = os.path.join(d, "species.bin")
     if os.path.exists(p):
         raw = open(p, "rb").read()

@@ -51,3 +51,20 @@ def test_oracle_total_yield_matches_reference(libs, tmp_path, name):
     # :606-609 never calls compute_dsigma_magnitude); the diffusion term is ~1e-5 of the yield
     tol = 1e-4 if case["params"].get("include_baryondiff_deltaf") else 1e-12
     assert abs(ntot / float(ref["total_yield"]) - 1.0) < tol
+
+
+@pytest.mark.parametrize("name", list(cases.POLZN_CASES))
+def test_oracle_polarization_matches_reference_golden(libs, tmp_path, name):
+    """cf_oracle_polarization against the arrays of the unmodified reference (Polarization.cpp), including the in-chunk
+    vorticity index for the surface with more than 10 000 cells."""
+    case = cases.POLZN_CASES[name]
+    surf, vort, ref = harness.load_golden_polzn(name)
+    root = workdir.make_workdir(str(tmp_path), case["params"], chosen=case["chosen"], **case.get("tables", {}))
+    prob = oracle_api.OracleProblem(root, case["params"], surf)
+    rc, got = prob.polarization(vort, chunk_compat=1)
+    assert rc == 0
+    worst = harness.assert_polzn_close(got, ref, rtol=1e-11, what=name)
+    print(name, worst)
+    if len(surf["tau"]) > 10000:
+        rc, fixed = prob.polarization(vort, chunk_compat=0)
+        assert rc == 0 and not np.allclose(fixed[0], ref[0], rtol=1e-6)      # the corrected index is a different result
