@@ -111,6 +111,11 @@ SAMPLER_CASES = {
     "smp_vah_m5": dict(surface=("s3d", dict(n=300, seed=57, vah=True)), params=_p(df_mode=5, **_S), chosen="pikp"),
     "smp_s3d_m5_stress": dict(surface=("s3d", dict(n=300, seed=58, stress=0.3)), params=_p(df_mode=5, **_S), chosen="pikp"),
     "smp_s2d_m5": dict(surface=("s3d", dict(n=200, seed=59, dimension=2, vah=True)), params=_p(df_mode=5, dimension=2, hrg_eos=1, **_S), chosen="pikp"),
+    # corners: 2+1d PTB with per-cell densities, Grad with the viscous corrections switched off, PTMA with a chemical potential
+    "smp_s2d_m4_slow": dict(surface=("s3d", dict(n=200, seed=65, dimension=2, stress=0.2)), params=_p(df_mode=4, dimension=2, hrg_eos=1, **dict(_S, fast=0)), chosen="pikp"),
+    "smp_s3d_m1_noshear_nobulk": dict(surface=("s3d", dict(n=300, seed=66)), params=_p(df_mode=1, include_bulk_deltaf=0, include_shear_deltaf=0, **_S), chosen="pikp"),
+    "smp_vah_m5_baryon": dict(surface=("s3d", dict(n=300, seed=67, vah=True, baryon=True)),
+                              params=_p(df_mode=5, include_baryon=1, include_baryondiff_deltaf=1, **_S), chosen="pikp"),
 }
 
 # spin polarization (mode-5 surfaces: thermal vorticity columns; runs after any operation, reference EmissionFunction.cpp:1304-1310)
