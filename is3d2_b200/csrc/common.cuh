@@ -89,6 +89,8 @@ IS3D_HD double clamp_hi_word_680(double x)
 static __constant__ double c_exp_consts[3] = {1477.3197218702985, -6.769015435155716e-04, 1.6666666666666666e-01};
 #endif
 
+// CLAMP = false: the caller has already passed x through clamp_hi_word_680 (and keeps using the clamped value)
+template <bool CLAMP = true>
 IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
 {
 #if defined(__CUDA_ARCH__)
@@ -97,7 +99,7 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
   const double kInv = 1477.3197218702985, kStep = -6.769015435155716e-04, kSixth = 1.6666666666666666e-01;
 #endif
   const double kMagic = 6755399441055744.0;          // 1.5 * 2^52: rounds to nearest integer in the low mantissa bits
-  x = clamp_hi_word_680(x);
+  if (CLAMP) x = clamp_hi_word_680(x);
   double t = fma(x, kInv, kMagic);                   // 1024 / ln2
   const int k = (int)as_int64(t);                    // low word of t = the integer (two's complement), |k| < 2^21 here
   t -= kMagic;

@@ -29,7 +29,7 @@ namespace {
 #define IS3D_K1_MINBLOCKS 2
 #endif
 #ifndef IS3D_K1_R
-#define IS3D_K1_R 3
+#define IS3D_K1_R 4
 #endif
 constexpr int kThreads = IS3D_K1_THREADS;
 constexpr int kTile = kThreads;  // cells per shared-memory tile = threads per block
@@ -51,7 +51,9 @@ __global__ void df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, 
 
 struct DfGrid {
   const double *mT, *pT, *m2, *baryon, *sign;         // per (species class, pT) bin, [ns * NpT]
-  int ns, NpT, ncols;                                 // ns = number of species CLASSES; ncols = NpT * ceil(ns / R) thread columns
+  int ns, NpT, ncols;                                 // ns = number of species CLASSES; ncols = NpT * ngroups thread columns
+  const int *slot_class;                              // [ngroups * R]: class of slot r of a thread group, -1 = padding; the
+                                                      // valid slots of a group carry ONE baryon number (build_slot_table)
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
   const double *exptab;                               // 2^(m/1024), global memory (ctx->d_exptab)
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, IS3D_K1_MINBLOCKS)
 df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk, DfGrid g,
                   double *__restrict__ partial, int64_t total)
 {
-  __shared__ DfItem items[kTile];
+  __shared__ DfItemU items[kTile];
   __shared__ double exptab[kExpTableSize];
   __shared__ int warp_count[kThreads / 32];
   load_exp_table(exptab, g.exptab);                 // visible after the first __syncthreads of the tile loop
@@ -71,23 +73,28 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;
   const double yval = g.yv[iy], cphi = g.cosphi[iphi], sphi = g.sinphi[iphi];
 
-  // column = (species group, pT node): R consecutive species share the thread's pT
+  // column = (thread group, pT node): the R classes of a group share the thread's pT and one baryon number
   const int col = blockIdx.x * kThreads + t;
   const int colc = col < g.ncols ? col : g.ncols - 1;
   const int grp = colc / g.NpT, ip = colc - grp * g.NpT;
-  DfBin bin[R];
+  double mT[R], mT2[R], sgn[R];
   double acc[R];
-  int jbin[R];                                          // (species, pT) bin index, -1 = padding
+  int jbin[R];                                          // (class, pT) bin index, -1 = padding
+  const int cls0 = g.slot_class[grp * R];               // slot 0 of a group is never padding
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    const int s = grp * R + r;
-    const int jj = (s < g.ns ? s : g.ns - 1) * g.NpT + ip;
-    jbin[r] = (col < g.ncols && s < g.ns) ? jj : -1;
-    const double mT = g.mT[jj];
-    bin[r].mT = mT; bin[r].mT2 = mT * mT; bin[r].m2 = g.m2[jj]; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
+    const int cls = g.slot_class[grp * R + r];
+    const int jj = (cls >= 0 ? cls : cls0) * g.NpT + ip;
+    jbin[r] = (col < g.ncols && cls >= 0) ? jj : -1;
+    const double m = g.mT[jj];
+    mT[r] = m; mT2[r] = m * m; sgn[r] = g.sign[jj];
     acc[r] = 0.0;
   }
-  const double pT = g.pT[ip], pT2 = pT * pT;           // bin arrays are [species][pT]: entry ip = species 0
+  DfThreadU th;
+  th.pT = g.pT[ip]; th.pT2 = th.pT * th.pT;            // bin arrays are [class][pT]: entry ip = class 0
+  th.b = BARYON ? g.baryon[cls0 * g.NpT + ip] : 0.0;
+  th.bpT = th.b * th.pT;
+  th.eslot = kMaxBaryon + (int)th.b;
 
   const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
   int64_t chunk_end = chunk_begin + cells_per_chunk;
@@ -115,15 +122,15 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         double sh = sinh(yval - eta);
         double ch = sqrt(1.0 + sh * sh);     // the reference's cosh (MomentumSpectra.cpp:307-308)
         auto pk = [&](int k) { return pack[k * stride + cell]; };
-        items[base + __popc(ballot & ((1u << lane) - 1u))] = df_make_item(pk, MODE, sh, ch, cphi, sphi, w);
+        items[base + __popc(ballot & ((1u << lane) - 1u))] = df_make_item_u<MODE, BARYON>(pk, sh, ch, cphi, sphi, w);
       }
       __syncthreads();
 #pragma unroll 1
       for (int k = 0; k < n_items; k++) {
-        const DfItem it = items[k];
-        const DfShared sh = df_share<BARYON>(it, pT, pT2);
+        const DfItemU &it = items[k];          // shared memory: fields arrive as broadcast LDS.128, eb[eslot] as one LDS.64
+        const DfSharedU sh = df_share_u<MODE, BARYON>(it, th);
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[r] += df_eval<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, bin[r], exptab);
+        for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], exptab);
       }
     }
   }
@@ -195,6 +202,31 @@ void species_classes(const is3d_ctx *ctx, std::vector<int> *class_of, std::vecto
     if (c < 0) { c = (int)rep->size(); rep->push_back(s); }
     (*class_of)[s] = c;
   }
+}
+
+// K1 thread groups: R class slots per group, the valid slots of a group carrying ONE baryon number (the kernel folds
+// b into per-(item, thread) coefficients, spectra_df.cuh).  Classes are taken per baryon number in order of first
+// appearance and each run is padded to a multiple of R with -1; without baryon terms all classes form one run.
+static bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots)
+{
+  std::vector<int> class_of, rep;
+  species_classes(ctx, &class_of, &rep);
+  const bool baryon_on = ctx->prm.include_baryon != 0;
+  std::vector<double> bvals;
+  for (int r : rep) {
+    const double b = baryon_on ? ctx->h_baryon[r] : 0.0;
+    bool seen = false;
+    for (double v : bvals) seen = seen || (v == b);
+    if (!seen) bvals.push_back(b);
+  }
+  slots->clear();
+  for (double b : bvals) {
+    if (fabs(b) > (double)kMaxBaryon || b != (double)(int)b) return false;
+    for (size_t c = 0; c < rep.size(); c++)
+      if ((baryon_on ? ctx->h_baryon[rep[c]] : 0.0) == b) slots->push_back((int)c);
+    while (slots->size() % (size_t)R) slots->push_back(-1);
+  }
+  return true;
 }
 
 // Builds the species classes and their per-(class, pT) bin arrays shared by all spectra kernels (device pointers in `out`).
@@ -270,7 +302,17 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   SpeciesBins sb;
   IS3D_TRY(build_bin_arrays(ctx, &sb));
   g.mT = sb.mT; g.pT = sb.pT; g.m2 = sb.m2; g.baryon = sb.baryon; g.sign = sb.sign;
-  g.ns = sb.nclass; g.NpT = ctx->NpT; g.ncols = ctx->NpT * ((sb.nclass + kDfBinsPerThread - 1) / kDfBinsPerThread);
+  std::vector<int> slots;
+  if (!build_slot_table(ctx, kDfBinsPerThread, &slots)) {
+    ctx->set_error("species list holds a baryon number outside -2..2 (the reference's PDG readers produce hadrons and the deuteron only)");
+    return IS3D_ERR_INVALID;
+  }
+  void *d_slots = nullptr;
+  IS3D_TRY(ctx->get_scratch("k1_slots", slots.size() * sizeof(int), &d_slots));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `slots` is pageable host memory
+  g.slot_class = (const int *)d_slots;
+  g.ns = sb.nclass; g.NpT = ctx->NpT; g.ncols = ctx->NpT * (int)(slots.size() / kDfBinsPerThread);
   const int64_t per_species = (int64_t)ctx->NpT * ctx->Nphi * ctx->Ny;
   const int64_t total_class = (int64_t)sb.nclass * per_species;
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;

@@ -24,6 +24,7 @@ enum DfPackIdx {
   DP_DAT, DP_DAX, DP_DAY, DP_DANT,
   DP_PITT, DP_T2PINN, DP_TPITN, DP_PITX, DP_PITY, DP_TPIXN, DP_TPIYN, DP_PIXX, DP_PIYY, DP_PIXY,
   DP_K0, DP_K1, DP_K2, DP_G0, DP_G1, DP_VT, DP_TVN, DP_VX, DP_VY,
+  DP_EBP, DP_EBM,              // exp(-alpha_B), exp(+alpha_B): the chemical-potential factor of the uniform-baryon path
   DP_SIZE
 };
 
@@ -83,6 +84,7 @@ IS3D_HD int df_setup_cell(const Cell &c, const DfTables &tb, const DfFlags &fl, 
   pack[DP_ETA] = c.eta;
   pack[DP_UTT] = ut * invT;  pack[DP_TUNT] = tau * un * invT;  pack[DP_UXT] = ux * invT;  pack[DP_UYT] = uy * invT;
   pack[DP_ALPHAB] = alphaB;
+  pack[DP_EBP] = exp(-alphaB); pack[DP_EBM] = exp(alphaB);
   pack[DP_DAT] = c.dat; pack[DP_DAX] = c.dax; pack[DP_DAY] = c.day; pack[DP_DANT] = c.dan / tau;
   pack[DP_PITT] = sc * pi.tt; pack[DP_T2PINN] = sc * tau2 * pi.nn; pack[DP_TPITN] = sc * tau * pi.tn;
   pack[DP_PITX] = sc * pi.tx; pack[DP_PITY] = sc * pi.ty; pack[DP_TPIXN] = sc * tau * pi.xn; pack[DP_TPIYN] = sc * tau * pi.yn;
@@ -198,6 +200,139 @@ IS3D_HD double df_eval(const DfItem &it, const DfShared &s, const DfBin &b, cons
 {
   double pds = fma(b.mT, it.c1, s.pd);
   double contrib = pds * df_distribution<MODE, BARYON, REGULATE, PAD>(it, s, b, exptab);
+  if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
+  return contrib;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1 production path: thread groups with ONE baryon number.
+//
+// df_spectra_kernel gives a thread R species classes at one pT node, and the host orders the classes so that the R
+// classes of a thread carry the same baryon number b (run_spectra_df, "slot table").  With b and pT both fixed per
+// thread, every term of df that is polynomial in (mT, pT) collapses into coefficients formed ONCE per (item, thread)
+// and shared by the thread's R evaluations:
+//   df_mode 1 (MomentumSpectra.cpp:325-338): the whole correction is a quadratic form,
+//       (K1 b + K2 xE) xE + K0 m^2 + pi.p.p + (G1 xE + G0 b) V.p  =  mT^2 Q1 + mT (pT Q2 + b M1) + (pT^2 Q3 - b pT M2)
+//       Q1 = q1 + K2 aT^2 + G1 aT v1,  Q2 = q2 - 2 K2 aT bT - G1 (aT v2 + bT v1),  Q3 = q3 + K2 bT^2 + G1 bT v2,
+//       M1 = K1 aT + G0 v1,  M2 = K1 bT + G0 v2                      (q1..q3 already hold the folded K0 m^2 term)
+//   df_mode 2 (:339-352): the terms over xE and the regular terms separate,
+//       (pi.p.p - K2 m^2 - G1 b V.p) / xE + K0 xE + K1 b + G0 V.p  =  [mT^2 q1 + mT A + B] / xE + (mT L1 + C)
+//       A = pT q2 - b G1 v1,  B = pT^2 q3 + b G1 pT v2,  L1 = K0 aT + G0 v1,  C = K1 b - pT (K0 bT + G0 v2)
+//   both: exp((u.p - b mu_B)/T) = exp(xE) exp(-b alpha_B); the second factor is an item constant selected by b, so the
+//       chemical-potential shift and the "+ sign" become one FMA.
+// FP64-pipe instructions per evaluation with baryon terms (R = 3): mode 1 28.7 -> 21, mode 2 31.7 -> 27.3.
+// eb[2 + b] = exp(-b alpha_B) for b = -2 .. 2: hadrons and the deuteron, the only nucleus the reference's PDG readers
+// produce (readindata.cpp:1098-1214); a thread reads the slot of its group's baryon number with one LDS.64.
+constexpr int kMaxBaryon = 2;
+struct alignas(16) DfItemU {
+  double aT, bT, c1, d1;
+  double q1, q2, q3, L1;         // mode 1: Q1, Q2, Q3, M1;  mode 2 without baryon terms: L1 = K0
+  double L2, K1, G1, v1;         // mode 1: L2 = M2;  K1, G1, v1, v2: mode 2 with baryon terms only
+  double v2, eb[2 * kMaxBaryon + 1];
+};
+
+template <int MODE, bool BARYON, class PackFn>
+IS3D_HD DfItemU df_make_item_u(PackFn pk, double sh, double ch, double cphi, double sphi, double w)
+{
+  DfItemU it;
+  const double aT = ch * pk(DP_UTT) - sh * pk(DP_TUNT);
+  const double bT = cphi * pk(DP_UXT) + sphi * pk(DP_UYT);
+  it.aT = aT; it.bT = bT;
+  it.c1 = w * (ch * pk(DP_DAT) + sh * pk(DP_DANT));
+  it.d1 = w * (cphi * pk(DP_DAX) + sphi * pk(DP_DAY));
+  const double fold = (MODE == 1) ? pk(DP_K0) : -pk(DP_K2);
+  const double q1 = ch * ch * pk(DP_PITT) + sh * sh * pk(DP_T2PINN) - 2.0 * ch * sh * pk(DP_TPITN) + fold;
+  const double q2 = 2.0 * (sh * (pk(DP_TPIXN) * cphi + pk(DP_TPIYN) * sphi) - ch * (pk(DP_PITX) * cphi + pk(DP_PITY) * sphi));
+  const double q3 = pk(DP_PIXX) * cphi * cphi + pk(DP_PIYY) * sphi * sphi + 2.0 * pk(DP_PIXY) * cphi * sphi - fold;
+  double v1 = 0.0, v2 = 0.0, G0 = 0.0, G1 = 0.0, K1 = 0.0;
+  for (int i = 0; i < 2 * kMaxBaryon + 1; i++) it.eb[i] = 1.0;
+  if (BARYON) {
+    v1 = pk(DP_VT) * ch - pk(DP_TVN) * sh;
+    v2 = pk(DP_VX) * cphi + pk(DP_VY) * sphi;
+    G0 = pk(DP_G0); G1 = pk(DP_G1); K1 = pk(DP_K1);
+    const double ebp = pk(DP_EBP), ebm = pk(DP_EBM);
+    it.eb[0] = ebm * ebm; it.eb[1] = ebm; it.eb[3] = ebp; it.eb[4] = ebp * ebp;
+  }
+  if (MODE == 1) {
+    const double K2 = pk(DP_K2);
+    it.q1 = q1 + K2 * aT * aT + G1 * aT * v1;
+    it.q2 = q2 - 2.0 * K2 * aT * bT - G1 * (aT * v2 + bT * v1);
+    it.q3 = q3 + K2 * bT * bT + G1 * bT * v2;
+    it.L1 = K1 * aT + G0 * v1;
+    it.L2 = K1 * bT + G0 * v2;
+  } else {
+    const double K0 = pk(DP_K0);
+    it.q1 = q1; it.q2 = q2; it.q3 = q3;
+    it.L1 = BARYON ? K0 * aT + G0 * v1 : K0;
+    it.L2 = K0 * bT + G0 * v2;
+  }
+  it.K1 = K1; it.G1 = G1; it.v1 = v1; it.v2 = v2;
+  return it;
+}
+
+// thread constants of the uniform-baryon path
+struct DfThreadU {
+  double pT, pT2, b, bpT;        // b = the group's baryon number, bpT = b pT
+  int eslot;                     // kMaxBaryon + b: the thread's slot of DfItemU::eb
+};
+
+// per (item, thread) coefficients shared by the thread's R evaluations
+struct DfSharedU {
+  double pb, pd, A, B, C, eb;
+};
+
+template <int MODE, bool BARYON>
+IS3D_HD DfSharedU df_share_u(const DfItemU &it, const DfThreadU &th)
+{
+  DfSharedU s;
+  s.pb = th.pT * it.bT;
+  s.pd = th.pT * it.d1;
+  s.eb = 1.0; s.C = 0.0;
+  if (MODE == 1) {
+    s.A = th.pT * it.q2;
+    s.B = th.pT2 * it.q3;
+    if (BARYON) { s.A = fma(th.b, it.L1, s.A); s.B = fma(-th.bpT, it.L2, s.B); }
+  } else {
+    s.A = th.pT * it.q2;
+    s.B = th.pT2 * it.q3;
+    if (BARYON) {
+      const double G1b = it.G1 * th.b;
+      s.A = fma(-G1b, it.v1, s.A);
+      s.B = fma(G1b * th.pT, it.v2, s.B);
+      s.C = fma(it.K1, th.b, -th.pT * it.L2);
+    }
+  }
+  if (BARYON) s.eb = it.eb[th.eslot];
+  return s;
+}
+
+// One integrand evaluation w p.dsigma feq (1 + df) on the uniform-baryon path (MomentumSpectra.cpp:304-361)
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign,
+                         const double *__restrict__ exptab)
+{
+  // clamped in place (x <= 680, common.cuh): beyond that feq < 1e-295 and every later use of xE multiplies feq
+  const double xE = clamp_hi_word_680(fma(mT, it.aT, -s.pb));
+  const double e = fast_exp<false>(xE, exptab);
+  const double q = BARYON ? fma(e, s.eb, sign) : e + sign;         // e^x + sign, x = xE - b alpha_B
+  const double quad = fma(mT2, it.q1, fma(mT, s.A, s.B));
+  double feq, dfv;
+  if (MODE == 1) {
+    feq = fast_rcp(q);
+    dfv = quad;
+  } else {
+    // one reciprocal serves 1/(e^x + sign) and 1/xE (e^x <= 2.1e295 by fast_exp's clamp and exp(|b| alpha_B) < 1e4, so
+    // the product stays finite for any xE a surface can produce)
+    const double y = fast_rcp(q * xE);
+    feq = y * xE;
+    const double r = y * q;
+    dfv = fma(quad, r, BARYON ? fma(mT, it.L1, s.C) : it.L1 * xE);
+  }
+  const double feqbar = fma(-sign, feq, 1.0);
+  double df = feqbar * dfv;
+  if (REGULATE) df = fmax(-1.0, fmin(df, 1.0));
+  const double pds = fma(mT, it.c1, s.pd);
+  double contrib = pds * fma(feq, df, feq);
   if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
   return contrib;
 }
