@@ -207,7 +207,7 @@ void species_classes(const is3d_ctx *ctx, std::vector<int> *class_of, std::vecto
 // K1 thread groups: R class slots per group, the valid slots of a group carrying ONE baryon number (the kernel folds
 // b into per-(item, thread) coefficients, spectra_df.cuh).  Classes are taken per baryon number in order of first
 // appearance and each run is padded to a multiple of R with -1; without baryon terms all classes form one run.
-static bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots)
+bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots)
 {
   std::vector<int> class_of, rep;
   species_classes(ctx, &class_of, &rep);

@@ -19,6 +19,7 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, int n
                                        const int *__restrict__ class_of, const double *__restrict__ deg, int64_t total,
                                        double *__restrict__ out);
 is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out);
+bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots);
 void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
                    int64_t *cells_per_chunk);
 // df_mode 5 per-cell stage (spectra_famod.cu): fills the same pack layout, counters[8] = reconstruction failures,
@@ -30,7 +31,10 @@ namespace {
 
 constexpr int kTile = 256;
 constexpr int kThreads = 256;
-constexpr int kBins = 3;
+#ifndef IS3D_K2_R
+#define IS3D_K2_R 4
+#endif
+constexpr int kBins = IS3D_K2_R;     // species classes per thread (R)
 
 __global__ void feqmod_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, DfTables tb, FeqmodFlags fl,
                                     const double *__restrict__ gla_root, const double *__restrict__ gla_weight, int gla_pts,
@@ -76,7 +80,9 @@ feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t co
 
 struct FeqGrid {
   const double *mT, *pT, *m2, *baryon, *sign;
-  int ncols, NpT, ns;                   // ns = number of species CLASSES; ncols = NpT * ceil(ns / kBins) thread columns
+  int ncols, NpT, ns;                   // ns = number of species CLASSES; ncols = NpT * ngroups thread columns
+  const int *slot_class;                // [ngroups * kBins]: class of slot r of a thread group (-1 = padding), one baryon
+                                        // number per group (build_slot_table, spectra_df.cu)
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
   const double *exptab;
@@ -105,24 +111,30 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
   const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;
   const double yval = g.yv[iy], cphi = g.cosphi[iphi], sphi = g.sinphi[iphi];
 
-  // column = (species group, pT node): R consecutive species share the thread's pT (see spectra_df.cu)
+  // column = (thread group, pT node): the R classes of a group share the thread's pT and one baryon number (spectra_df.cu)
   const int col = blockIdx.x * kThreads + t;
   const int colc = col < g.ncols ? col : g.ncols - 1;
   const int grp = colc / g.NpT, ip = colc - grp * g.NpT;
   DfBin bin[R];
   double acc[R];
   int jbin[R], sp[R];
+  const int cls0 = g.slot_class[grp * R];               // slot 0 of a group is never padding
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    const int s = grp * R + r;
-    sp[r] = s < g.ns ? s : g.ns - 1;
+    const int cls = g.slot_class[grp * R + r];
+    sp[r] = cls >= 0 ? cls : cls0;
     const int jj = sp[r] * g.NpT + ip;
-    jbin[r] = (col < g.ncols && s < g.ns) ? jj : -1;
+    jbin[r] = (col < g.ncols && cls >= 0) ? jj : -1;
     const double mT = g.mT[jj];
-    bin[r].mT = mT; bin[r].mT2 = mT * mT; bin[r].m2 = g.m2[jj]; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
+    bin[r].mT = mT; bin[r].mT2 = mT * mT; bin[r].m2 = 0.0; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
+    asm volatile("" : "+d"(bin[r].mT2));      // opaque: ptxas otherwise re-multiplies mT^2 (and pT^2) per item to save registers
     acc[r] = 0.0;
   }
-  const double pT = g.pT[ip], pT2 = pT * pT;
+  const double pT = g.pT[ip];
+  double pT2 = pT * pT;
+  asm volatile("" : "+d"(pT2));
+  int eslot = kMaxBaryon + (BARYON ? (int)bin[0].baryon : 0);
+  asm volatile("" : "+r"(eslot));      // opaque: keeps the slot index in a register (ptxas otherwise re-derives it with F2I per item)
 
   const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
   int64_t chunk_end = chunk_begin + cells_per_chunk;
@@ -159,25 +171,38 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
           items[slot].lin = feqmod_make_linear_item(pk, sinh(d), cosh(d), cphi, sphi, w, g.w_on_dan);
         } else {
           double d = yval - pk(FP_ETA_SCALE) * eta;
-          items[slot].mod = feqmod_make_item(pk, sinh(d), cosh(d), cphi, sphi, w, g.w_on_dan);
+          items[slot].mod = feqmod_make_item(pk, sinh(d), cosh(d), cphi, sphi, w, g.w_on_dan, BARYON, !SPECIES_RENORM);
         }
         item_linear[slot] = linear ? 1 : 0;
         item_cell[slot] = (int)(cell - 0);   // index inside this pass's pack / renorm arrays
       }
       __syncthreads();
+      // PTM: the (cell, class) renormalisations of item k + 1 are fetched (L2) while item k is evaluated
+      double rn_next[R];
+      if (SPECIES_RENORM && n_items > 0) {
+        const double *row = renorm + (int64_t)item_cell[0] * g.ns;
+#pragma unroll
+        for (int r = 0; r < R; r++) rn_next[r] = row[sp[r]];
+      }
 #pragma unroll 1
       for (int k = 0; k < n_items; k++) {
         double rn[R];
         if (SPECIES_RENORM) {
-          const double *row = renorm + (int64_t)item_cell[k] * g.ns;
 #pragma unroll
-          for (int r = 0; r < R; r++) rn[r] = row[sp[r]];
+          for (int r = 0; r < R; r++) rn[r] = rn_next[r];
+          if (k + 1 < n_items) {
+            const double *row = renorm + (int64_t)item_cell[k + 1] * g.ns;
+#pragma unroll
+            for (int r = 0; r < R; r++) rn_next[r] = row[sp[r]];
+          }
         }
         if (!item_linear[k]) {
-          const FeqmodItem it = items[k].mod;
+          const FeqmodItem &it = items[k].mod;        // shared memory: broadcast LDS.128 + one LDS.64 for eb[eslot]
           const FeqmodShared sh = feqmod_share(it, pT, pT2);
+          const double eb = BARYON ? it.eb[eslot] : 1.0;
 #pragma unroll
-          for (int r = 0; r < R; r++) acc[r] += feqmod_eval<BARYON, OUTFLOW>(it, sh, bin[r], SPECIES_RENORM ? rn[r] : it.renorm, exptab);
+          for (int r = 0; r < R; r++)
+            acc[r] += feqmod_eval_u<BARYON, OUTFLOW, !SPECIES_RENORM>(it, sh, eb, bin[r].mT, bin[r].mT2, bin[r].sign, SPECIES_RENORM ? rn[r] : 1.0, exptab);
         } else {
           const DfItem it = items[k].lin;
           const DfShared sh = df_share<BARYON>(it, pT, pT2);
@@ -238,7 +263,17 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   SpeciesBins sb;
   IS3D_TRY(build_bin_arrays(ctx, &sb));
   g.mT = sb.mT; g.pT = sb.pT; g.m2 = sb.m2; g.baryon = sb.baryon; g.sign = sb.sign;
-  g.NpT = ctx->NpT; g.ns = sb.nclass; g.ncols = ctx->NpT * ((sb.nclass + kBins - 1) / kBins);
+  std::vector<int> slots;
+  if (!build_slot_table(ctx, kBins, &slots)) {
+    ctx->set_error("species list holds a baryon number outside -2..2 (the reference's PDG readers produce hadrons and the deuteron only)");
+    return IS3D_ERR_INVALID;
+  }
+  void *d_slots = nullptr;
+  IS3D_TRY(ctx->get_scratch("k2_slots", slots.size() * sizeof(int), &d_slots));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `slots` is pageable host memory
+  g.slot_class = (const int *)d_slots;
+  g.NpT = ctx->NpT; g.ns = sb.nclass; g.ncols = ctx->NpT * (int)(slots.size() / kBins);
   const int64_t per_species = (int64_t)ctx->NpT * ctx->Nphi * ctx->Ny;
   const int64_t total_class = (int64_t)sb.nclass * per_species;
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;

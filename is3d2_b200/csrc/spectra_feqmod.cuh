@@ -185,16 +185,21 @@ IS3D_HD double feqmod_renorm_ptm(PackFn pk, double mass, double degeneracy, doub
 }
 
 // item constants of the modified branch
+// The mass term of E'^2 / T'^2 = m^2 / T'^2 + mT^2 h1 + mT pT h2 + pT^2 h3 is folded into the quadratic form with
+// m^2 = mT^2 - pT^2 (h1 += 1/T'^2, h3 -= 1/T'^2), so the momentum loop never needs m^2.
+// eb[kMaxBaryon + b] = exp(-b alphaB') for b = -2 .. 2 (K2's uniform-baryon thread groups, see DfItemU in spectra_df.cuh):
+// exp(E'/T' - b alphaB') + sign = exp(E'/T') eb + sign is one FMA.  Filled only when asked for (eb_slots).
 struct alignas(16) FeqmodItem {
   double c1, d1, h1, h2;
-  double h3, iT2, alphaB_mod, renorm;
+  double h3, renorm, alphaB_mod, eb[2 * kMaxBaryon + 1];
 };
 
 // sh/ch = sinh, cosh of (y - eta_scale eta); eta weight placement of the feqmod spectra path:
 // w (p^tau ds_tau + p^x ds_x + p^y ds_y) + p^eta ds_eta  (MomentumSpectra.cpp:883, :936); the dN/dX path weights the
 // whole p.dsigma (SpacetimeDistribution.cpp:1022, :1075) -> w_on_dan
 template <class PackFn>
-IS3D_HD FeqmodItem feqmod_make_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w, bool w_on_dan = false)
+IS3D_HD FeqmodItem feqmod_make_item(PackFn pk, double sh, double ch, double cphi, double sphi, double w, bool w_on_dan = false,
+                                    bool eb_slots = false, bool fold_renorm = false)
 {
   FeqmodItem it;
   it.c1 = w * ch * pk(DP_DAT) + (w_on_dan ? w : 1.0) * sh * pk(DP_DANT);
@@ -207,9 +212,16 @@ IS3D_HD FeqmodItem feqmod_make_item(PackFn pk, double sh, double ch, double cphi
   it.h1 = g1[0] * g1[0] + g1[1] * g1[1] + g1[2] * g1[2];
   it.h2 = 2.0 * (g1[0] * g2[0] + g1[1] * g2[1] + g1[2] * g2[2]);
   it.h3 = g2[0] * g2[0] + g2[1] * g2[1] + g2[2] * g2[2];
-  it.iT2 = pk(FP_IT2);
+  const double iT2 = pk(FP_IT2);
+  it.h1 += iT2; it.h3 -= iT2;
   it.alphaB_mod = pk(FP_ALPHAB_MOD);
   it.renorm = pk(FP_RENORM);
+  if (fold_renorm) { it.c1 *= it.renorm; it.d1 *= it.renorm; }     // the cell's |renorm| >= 0 rides on p.dsigma
+  for (int i = 0; i < 2 * kMaxBaryon + 1; i++) it.eb[i] = 1.0;
+  if (eb_slots) {
+    const double ebp = exp(-it.alphaB_mod), ebm = exp(it.alphaB_mod);
+    it.eb[0] = ebm * ebm; it.eb[1] = ebm; it.eb[3] = ebp; it.eb[4] = ebp * ebp;
+  }
   return it;
 }
 
@@ -224,18 +236,19 @@ IS3D_HD DfItem feqmod_make_linear_item(PackFn pk, double sh, double ch, double c
   return it;
 }
 
-// sqrt(a) for a > 0 in the FMA pipe: hardware rsqrt seed (~20 bits) + one coupled Newton (Goldschmidt) step (-> 2^-39) +
-// residual fix g + (a - g^2) h (-> below 2^-60)
+// sqrt(a) for a > 0 in the FMA pipe: hardware rsqrt seed y (sees the upper 32 bits of a: ~20 bits) and ONE third-order
+// step, g = a y, e = 1 - g y (<= 2^-18), sqrt(a) = g (1 - e)^(-1/2) = g (1 + e/2 + 3 e^2/8) + O(5/16 e^3 < 2^-56):
+// 5 FP64 instructions (the coupled Goldschmidt step + residual fix it replaces took 7)
 IS3D_HD double fast_sqrt(double a)
 {
 #if defined(__CUDA_ARCH__)
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double g = a * y, h = 0.5 * y;
-  double r = fma(-h, g, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  double d = fma(-g, g, a);
-  return fma(d, h, g);
+  const double g = a * y;
+  const double e = fma(-g, y, 1.0);
+  double p = fma(e, 0.375, 0.5);
+  p = p * e;
+  return fma(g, p, g);
 #else
   return sqrt(a);
 #endif
@@ -259,19 +272,25 @@ template <bool BARYON>
 IS3D_HD double feqmod_distribution(const FeqmodItem &it, const FeqmodShared &s, const DfBin &b, double renorm_sp,
                                    const double *__restrict__ exptab)
 {
-  double e2 = fma(b.m2, it.iT2, fma(b.mT2, it.h1, fma(b.mT, s.ph2, s.ph3)));
+  double e2 = fma(b.mT2, it.h1, fma(b.mT, s.ph2, s.ph3));
   double x = fast_sqrt(e2);
   if (BARYON) x = fma(-b.baryon, it.alphaB_mod, x);
   return renorm_sp * fast_rcp(fast_exp(x, exptab) + b.sign);
 }
 
-// f p.dsigma of the modified distribution (MomentumSpectra.cpp:932-982)
-template <bool BARYON, bool OUTFLOW>
-IS3D_HD double feqmod_eval(const FeqmodItem &it, const FeqmodShared &s, const DfBin &b, double renorm_sp,
-                           const double *__restrict__ exptab)
+// K2 production path (thread groups with one baryon number, see DfItemU): eb = it.eb[kMaxBaryon + b] read once per
+// (item, thread); with FOLDED the cell's renormalisation already multiplies c1 / d1 (feqmod_make_item fold_renorm),
+// otherwise renorm_sp = |renorm| of this (cell, class).  FP64-pipe instructions per evaluation: 3 (E'^2) + 5 (sqrt) +
+// 7 (exp) + 1 + 3 (rcp) + 2 (+ 1 unfolded) = 21 (22); the first version took 28 (29).
+template <bool BARYON, bool OUTFLOW, bool FOLDED>
+IS3D_HD double feqmod_eval_u(const FeqmodItem &it, const FeqmodShared &s, double eb, double mT, double mT2, double sign,
+                             double renorm_sp, const double *__restrict__ exptab)
 {
-  double pds = fma(b.mT, it.c1, s.pd);
-  double contrib = pds * feqmod_distribution<BARYON>(it, s, b, renorm_sp, exptab);
+  const double e2 = fma(mT2, it.h1, fma(mT, s.ph2, s.ph3));
+  const double e = fast_exp(fast_sqrt(e2), exptab);
+  const double f = fast_rcp(BARYON ? fma(e, eb, sign) : e + sign);
+  const double pds = fma(mT, it.c1, s.pd);
+  double contrib = FOLDED ? pds * f : (pds * f) * renorm_sp;
   if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
   return contrib;
 }
