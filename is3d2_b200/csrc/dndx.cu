@@ -9,6 +9,9 @@
 
 namespace is3d {
 
+is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out);
+bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots);
+
 namespace {
 
 __global__ void dndx_df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, DfTables tb, DfFlags fl,
@@ -42,30 +45,6 @@ __global__ void dndx_feqmod_setup_kernel(SurfaceView surf, int64_t begin, int64_
   if (st & CELL_PL_NEGATIVE) atomicAdd(&counters[3], 1ull);
 }
 
-// per-(pT, species) momentum constants of one thread at one pT node
-struct DndxBin {
-  DfBin b;
-  double pT, pT2;
-  double mTw, pTw;     // mT * pT_weight, pT * pT_weight (p.dsigma carries the quadrature weights)
-};
-
-__device__ __forceinline__ DndxBin dndx_load_bin(const DndxGrid &g, int ipT, int s, double m2, double baryon, double sign)
-{
-  DndxBin d;
-  const int idx = ipT * g.ns_pad + s;
-  const double pT = g.pT[ipT], w = g.pTw[ipT];
-  d.b.mT = g.mT[idx]; d.b.mT2 = g.mT2[idx]; d.pT = pT; d.pT2 = pT * pT;
-  d.b.m2 = m2; d.b.baryon = baryon; d.b.sign = sign;
-  d.mTw = g.mTw[idx]; d.pTw = pT * w;
-  return d;
-}
-
-// Both kernels: one-warp blocks, lane = species class, all lanes on the same cell.  The (y, eta, phi) points of a cell are
-// taken in chunks of 32: lane j builds the item of point j (one sinh / cosh per lane instead of every lane rebuilding
-// every item), the warp then loops pT OUTER -- the lane's three momentum constants are loaded once per (chunk, pT) --
-// and the chunk's items INNER, read from shared memory with broadcast LDS.128.
-static_assert(kDndxThreads == 32, "the dN/dX kernels synchronise with __syncwarp");
-
 // flattened (iy, ie, iphi) point j of the cell's momentum-space quadrature
 struct DndxPoint { double yval, eta, w, cphi, sphi; };
 
@@ -82,51 +61,133 @@ __device__ __forceinline__ DndxPoint dndx_point(const DndxGrid &g, PackFn pk, in
   return p;
 }
 
+// thread constants: column (thread group, pT node) of the block, see dndx_common.cuh
+template <int R>
+struct DndxThread {
+  bool active;                 // the column exists (group < ngroups, pT node < NpT)
+  int gl, ip;                  // group inside the block, pT node
+  double pT, pT2, wpT, b;      // b = the group's baryon number
+  double mT[R], mT2[R], sgn[R];
+  int eslot;
+
+  __device__ __forceinline__ void load(const DndxGrid &g, bool baryon_on)
+  {
+    const int t = threadIdx.x;
+    int gl_ = t / g.NpT;
+    ip = t - gl_ * g.NpT;
+    int grp = blockIdx.x * g.gpb + gl_;
+    active = gl_ < g.gpb && grp < g.ngroups;
+    if (!active) { gl_ = 0; grp = blockIdx.x * g.gpb; }          // idle threads shadow a valid column and are never summed
+    gl = gl_;
+    const int cls0 = g.slot_class[grp * R];                        // slot 0 of a group is never padding
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int cls = g.slot_class[grp * R + r];
+      const int jj = (cls >= 0 ? cls : cls0) * g.NpT + ip;
+      const double m = g.mT[jj];
+      mT[r] = m; mT2[r] = m * m; sgn[r] = g.sign[jj];
+    }
+    pT = g.pT[ip]; pT2 = pT * pT; wpT = g.pTw[ip];
+    b = baryon_on ? g.baryon[cls0 * g.NpT + ip] : 0.0;
+    eslot = kMaxBaryon + (int)b;
+    asm volatile("" : "+r"(eslot));
+  }
+};
+
+// End of a cell: thread partials (x pT weight x `gate`) -> sums over the NpT threads of every group -> histograms.
+// red is double-buffered by the caller (one __syncthreads per cell).
+template <int R>
+__device__ __forceinline__ void dndx_flush(double (&acc)[R], double factor, double (*red)[kDndxThreads], const DndxGrid &g,
+                                           const SurfaceView &surf, int64_t gcell)
+{
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+#pragma unroll
+  for (int r = 0; r < R; r++) { red[r][t] = acc[r] * factor; acc[r] = 0.0; }
+  __syncthreads();
+  const int nsum = g.gpb * R;
+  for (int j = warp; j < nsum; j += kDndxThreads / 32) {
+    const int gl = j / R, r = j - gl * R;
+    const int grp = blockIdx.x * g.gpb + gl;
+    if (grp >= g.ngroups) continue;
+    const int cls = g.slot_class[grp * R + r];
+    if (cls < 0) continue;
+    double v = 0.0;
+    for (int i = lane; i < g.NpT; i += 32) v += red[r][gl * g.NpT + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) dndx_scatter(g, cls, surf.col[0][gcell], surf.col[1][gcell], surf.col[2][gcell], kCooperFryePrefactor * v);
+  }
+}
+
+// tile geometry shared by both kernels: cells per tile and the (cell, point) a thread builds
+struct DndxTiling {
+  int npoints, cpt;
+  __device__ __forceinline__ DndxTiling(const DndxGrid &g)
+  {
+    npoints = g.Ny * g.Neta * g.Nphi;
+    cpt = npoints >= kDndxTile ? 1 : kDndxTile / npoints;
+    if (cpt > kDndxMaxCells) cpt = kDndxMaxCells;
+  }
+};
+
 // df_mode 1, 2 (SpacetimeDistribution.cpp:170-441)
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
-__global__ void __launch_bounds__(kDndxThreads)
+__global__ void __launch_bounds__(kDndxThreads, 2)
 dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_block, SurfaceView surf,
                int64_t surf_begin, DndxGrid g)
 {
+  constexpr int R = kDndxR;
   __shared__ double exptab[kExpTableSize];
-  __shared__ DfItem items[kDndxThreads];
+  __shared__ DfItemU items[kDndxTile];
+  __shared__ double red[2][R][kDndxThreads];
+  __shared__ int cell_ok[kDndxMaxCells];
   load_exp_table(exptab, g.exptab);
-  __syncthreads();
-  const int lane = threadIdx.x;
-  const int s = blockIdx.x * kDndxThreads + lane;
-  const double m2 = g.mass2[s], baryon = g.baryon[s], sign = g.sign[s];
-  const int npoints = g.Ny * g.Neta * g.Nphi;
+  const int t = threadIdx.x;
+  DndxThread<R> th;
+  th.load(g, BARYON);
+  DfThreadU tu;
+  tu.pT = th.pT; tu.pT2 = th.pT2; tu.b = th.b; tu.bpT = th.b * th.pT; tu.eslot = th.eslot;
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) acc[r] = 0.0;
+  const DndxTiling tl(g);
+  int buf = 0;
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
   int64_t c1 = c0 + cells_per_block;
   if (c1 > ncells) c1 = ncells;
-  for (int64_t cell = c0; cell < c1; cell++) {
-    if (pack[DP_VALID * stride + cell] == 0.0) continue;
-    auto pk = [&](int k) { return pack[k * stride + cell]; };
-    double acc = 0.0;
-    for (int j0 = 0; j0 < npoints; j0 += kDndxThreads) {
-      if (j0 + lane < npoints) {
-        const DndxPoint pt = dndx_point(g, pk, j0 + lane);
-        const double d = pt.yval - pt.eta;
-        items[lane] = df_make_item(pk, MODE, sinh(d), cosh(d), pt.cphi, pt.sphi, pt.w);
-      }
-      __syncwarp();
-      const int nj = min(kDndxThreads, npoints - j0);
-      for (int ipT = 0; ipT < g.NpT; ipT++) {
-        const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
-#pragma unroll 2
-        for (int k = 0; k < nj; k++) {
-          const DfItem it = items[k];
-          const double pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-          double v = pds * df_distribution<MODE, BARYON, REGULATE>(it, df_share<BARYON>(it, bn.pT, bn.pT2), bn.b, exptab);
-          if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
-          acc += v;
+  for (int64_t cell0 = c0; cell0 < c1; cell0 += tl.cpt) {
+    for (int p0 = 0; p0 < tl.npoints; p0 += kDndxTile) {
+      const int np_tile = min(kDndxTile, tl.npoints - p0);
+      __syncthreads();                                   // previous tile consumed (first pass: exp table loaded)
+      {
+        const int cl = t / np_tile, j = p0 + t - cl * np_tile;
+        const int64_t cell = cell0 + cl;
+        if (cl < tl.cpt && cell < c1) {
+          const bool ok = pack[DP_VALID * stride + cell] != 0.0;
+          if (j == p0) cell_ok[cl] = ok ? 1 : 0;
+          if (ok) {
+            auto pk = [&](int k) { return pack[k * stride + cell]; };
+            const DndxPoint pt = dndx_point(g, pk, j);
+            const double d = pt.yval - pt.eta;
+            items[t] = df_make_item_u<MODE, BARYON>(pk, sinh(d), cosh(d), pt.cphi, pt.sphi, pt.w);
+          }
         }
       }
-      __syncwarp();
-    }
-    if (s < g.ns) {
-      const int64_t gc = surf_begin + cell;
-      dndx_scatter(g, s, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc], kCooperFryePrefactor * acc);
+      __syncthreads();
+      const bool last_tile = p0 + kDndxTile >= tl.npoints;
+      for (int cl = 0; cl < tl.cpt && cell0 + cl < c1; cl++) {
+        if (!cell_ok[cl]) continue;
+        if (th.active) {
+#pragma unroll 1
+          for (int k = 0; k < np_tile; k++) {
+            const DfItemU &it = items[cl * np_tile + k];
+            const DfSharedU sh = df_share_u<MODE, BARYON>(it, tu);
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, th.mT[r], th.mT2[r], th.sgn[r], exptab);
+          }
+        }
+        if (last_tile) { dndx_flush<R>(acc, th.wpT, red[buf], g, surf, surf_begin + cell0 + cl); buf ^= 1; }
+      }
     }
   }
 }
@@ -139,69 +200,116 @@ union DndxItemSlot {
 
 // df_mode 3, 4 (SpacetimeDistribution.cpp:676-1160)
 template <bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM>
-__global__ void __launch_bounds__(kDndxThreads)
+__global__ void __launch_bounds__(kDndxThreads, 2)
 dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_block, SurfaceView surf,
                    int64_t surf_begin, DndxGrid g, const double *__restrict__ gla_root, const double *__restrict__ gla_weight,
                    int gla_pts)
 {
+  constexpr int R = kDndxR;
   __shared__ double exptab[kExpTableSize];
-  __shared__ DndxItemSlot items[kDndxThreads];
-  __shared__ unsigned char item_linear[kDndxThreads];
+  __shared__ DndxItemSlot items[kDndxTile];
+  __shared__ unsigned char item_linear[kDndxTile];
+  __shared__ double red[2][R][kDndxThreads];
+  __shared__ double cell_rn[kDndxMaxCells];                                   // the cell's |renorm| (0: skip the cell)
+  __shared__ double class_rn[SPECIES_RENORM ? kDndxMaxCells : 1][kDndxMaxGroups * R];   // PTM: |renorm| per (cell, class slot)
+  __shared__ int cell_ok[kDndxMaxCells];
   __shared__ RenormNodes nodes;
   load_exp_table(exptab, g.exptab);
   if (SPECIES_RENORM) nodes.load(gla_root, gla_weight, gla_pts);
   __syncthreads();
-  const int lane = threadIdx.x;
-  const int s = blockIdx.x * kDndxThreads + lane;
-  const double m2 = g.mass2[s], baryon = g.baryon[s], sign = g.sign[s], deg = g.deg[s], mass = g.mass[s];   // deg cancels in the renorm ratio
-  const int npoints = g.Ny * g.Neta * g.Nphi;
+  const int t = threadIdx.x;
+  DndxThread<R> th;
+  th.load(g, BARYON);
+  DfBin bin[R];                                         // linear-df fallback of breakdown cells
+#pragma unroll
+  for (int r = 0; r < R; r++) { bin[r].mT = th.mT[r]; bin[r].mT2 = th.mT2[r]; bin[r].m2 = 0.0; bin[r].baryon = th.b; bin[r].sign = th.sgn[r]; }
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) acc[r] = 0.0;
+  const DndxTiling tl(g);
+  const int nsum = g.gpb * R;
+  int buf = 0;
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
   int64_t c1 = c0 + cells_per_block;
   if (c1 > ncells) c1 = ncells;
-  for (int64_t cell = c0; cell < c1; cell++) {
-    if (pack[DP_VALID * stride + cell] == 0.0) continue;
-    auto pk = [&](int k) { return pack[k * stride + cell]; };
-    double rn = pk(FP_RENORM);
-    if (SPECIES_RENORM) rn = feqmod_renorm_ptm_fused(pk, mass, deg, baryon, sign, nodes, gla_pts, exptab);
-    const bool breakdown = pk(FP_BREAKDOWN) != 0.0;
-    const double detA = pk(FP_DETA), eta_scale = pk(FP_ETA_SCALE);
-    double acc = 0.0;
-    for (int j0 = 0; j0 < npoints; j0 += kDndxThreads) {
-      if (j0 + lane < npoints) {
-        const DndxPoint pt = dndx_point(g, pk, j0 + lane);
-        bool linear = breakdown;
-        if (g.dimension == 3 && !linear && detA < 0.01 && fabs(pt.yval - pt.eta) < detA) linear = true;
-        const double d = linear ? (pt.yval - pt.eta) : (pt.yval - eta_scale * pt.eta);
-        const double sh = sinh(d), ch = cosh(d);
-        if (linear) items[lane].lin = feqmod_make_linear_item(pk, sh, ch, pt.cphi, pt.sphi, pt.w, true);
-        else items[lane].mod = feqmod_make_item(pk, sh, ch, pt.cphi, pt.sphi, pt.w, true);
-        item_linear[lane] = linear ? 1 : 0;
-      }
-      __syncwarp();
-      const int nj = min(kDndxThreads, npoints - j0);
-      for (int ipT = 0; ipT < g.NpT; ipT++) {
-        const DndxBin bn = dndx_load_bin(g, ipT, s, m2, baryon, sign);
-        for (int k = 0; k < nj; k++) {
-          double pds, v;
-          if (item_linear[k]) {
-            const DfItem it = items[k].lin;
-            pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-            v = pds * df_distribution<2, BARYON, REGULATE, true>(it, df_share<BARYON>(it, bn.pT, bn.pT2), bn.b, exptab);
-          } else {
-            const FeqmodItem it = items[k].mod;
-            pds = fma(bn.mTw, it.c1, bn.pTw * it.d1);
-            v = pds * feqmod_distribution<BARYON>(it, feqmod_share(it, bn.pT, bn.pT2), bn.b, rn, exptab);
+  for (int64_t cell0 = c0; cell0 < c1; cell0 += tl.cpt) {
+    for (int p0 = 0; p0 < tl.npoints; p0 += kDndxTile) {
+      const int np_tile = min(kDndxTile, tl.npoints - p0);
+      __syncthreads();                                   // previous tile consumed
+      {
+        const int cl = t / np_tile, j = p0 + t - cl * np_tile;
+        const int64_t cell = cell0 + cl;
+        if (cl < tl.cpt && cell < c1) {
+          const bool ok = pack[DP_VALID * stride + cell] != 0.0;
+          auto pk = [&](int k) { return pack[k * stride + cell]; };
+          if (j == p0) { cell_ok[cl] = ok ? 1 : 0; cell_rn[cl] = ok ? pk(FP_RENORM) : 0.0; }
+          if (ok) {
+            const DndxPoint pt = dndx_point(g, pk, j);
+            bool linear = pk(FP_BREAKDOWN) != 0.0;
+            const double detA = pk(FP_DETA);
+            if (g.dimension == 3 && !linear && detA < 0.01 && fabs(pt.yval - pt.eta) < detA) linear = true;
+            const double d = linear ? (pt.yval - pt.eta) : (pt.yval - pk(FP_ETA_SCALE) * pt.eta);
+            const double sh = sinh(d), ch = cosh(d);
+            if (linear) items[t].lin = feqmod_make_linear_item(pk, sh, ch, pt.cphi, pt.sphi, pt.w, true);
+            else items[t].mod = feqmod_make_item(pk, sh, ch, pt.cphi, pt.sphi, pt.w, true, BARYON, !SPECIES_RENORM);
+            item_linear[t] = linear ? 1 : 0;
           }
-          if (OUTFLOW) v = (pds <= 0.0) ? 0.0 : v;
-          acc += v;
+        }
+        // PTM with bulk: n_linear / n_mod of every (cell, class slot) of this tile, once per cell (first tile of the cell)
+        if (SPECIES_RENORM && p0 == 0) {
+          for (int task = t; task < tl.cpt * nsum; task += kDndxThreads) {
+            const int tc = task / nsum, js = task - tc * nsum;
+            const int64_t rcell = cell0 + tc;
+            const int grp = blockIdx.x * g.gpb + js / R;
+            double rn = 0.0;
+            if (rcell < c1 && grp < g.ngroups && pack[DP_VALID * stride + rcell] != 0.0) {
+              const int cls = g.slot_class[grp * R + (js % R)];
+              if (cls >= 0) {
+                auto pkr = [&](int k) { return pack[k * stride + rcell]; };
+                rn = feqmod_renorm_ptm_fused(pkr, g.c_mass[cls], g.c_deg[cls], g.c_baryon[cls], g.c_sign[cls], nodes, gla_pts, exptab);
+              }
+            }
+            class_rn[tc][js] = rn;
+          }
         }
       }
-      __syncwarp();
-    }
-    // a NaN / inf renormalisation skips the (cell, species) in both branches (SpacetimeDistribution.cpp:955-959)
-    if (s < g.ns && rn != 0.0) {
-      const int64_t gc = surf_begin + cell;
-      dndx_scatter(g, s, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc], kCooperFryePrefactor * acc);
+      __syncthreads();
+      const bool last_tile = p0 + kDndxTile >= tl.npoints;
+      for (int cl = 0; cl < tl.cpt && cell0 + cl < c1; cl++) {
+        if (!cell_ok[cl]) continue;
+        double rn[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) rn[r] = SPECIES_RENORM ? class_rn[cl][th.gl * R + r] : 1.0;
+        if (th.active) {
+#pragma unroll 1
+          for (int k = 0; k < np_tile; k++) {
+            const int slot = cl * np_tile + k;
+            if (!item_linear[slot]) {
+              const FeqmodItem &it = items[slot].mod;
+              const FeqmodShared sh = feqmod_share(it, th.pT, th.pT2);
+              const double eb = BARYON ? it.eb[th.eslot] : 1.0;
+#pragma unroll
+              for (int r = 0; r < R; r++)
+                acc[r] += feqmod_eval_u<BARYON, OUTFLOW, !SPECIES_RENORM>(it, sh, eb, th.mT[r], th.mT2[r], th.sgn[r], rn[r], exptab);
+            } else {
+              const DfItem it = items[slot].lin;
+              const DfShared sh = df_share<BARYON>(it, th.pT, th.pT2);
+#pragma unroll
+              for (int r = 0; r < R; r++) acc[r] += df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, bin[r], exptab);
+            }
+          }
+        }
+        if (last_tile) {
+          // a NaN / inf renormalisation (stored as 0) skips the (cell, species) in both branches (SpacetimeDistribution.cpp:955-959)
+          if (SPECIES_RENORM) {
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = (rn[r] != 0.0) ? acc[r] : 0.0;
+          }
+          const double factor = (SPECIES_RENORM || cell_rn[cl] != 0.0) ? th.wpT : 0.0;
+          dndx_flush<R>(acc, factor, red[buf], g, surf, surf_begin + cell0 + cl);
+          buf ^= 1;
+        }
+      }
     }
   }
 }
@@ -215,39 +323,31 @@ __global__ void dndx_expand_kernel(const double *__restrict__ class_hist, const 
   out[i] = deg[s] * class_hist[(int64_t)class_of[s] * bins + (i - s * bins)];
 }
 
-// transposed momentum tables [ipT][ns_pad] and padded species arrays
+// species classes, their (class, pT) bin arrays and the uniform-baryon slot table (shared with the spectra kernels)
 is3d_status build_dndx_grid(is3d_ctx *ctx, DndxGrid *g, const int **class_of_dev)
 {
   const is3d_params &p = ctx->prm;
-  // one thread per species CLASS (ctx.h SpeciesBins): the histograms are filled per class and expanded to species at the end
-  std::vector<int> class_of, rep;
-  species_classes(ctx, &class_of, &rep);
-  const int ns = (int)rep.size(), nsp = (ns + kDndxThreads - 1) / kDndxThreads * kDndxThreads, npT = ctx->NpT;
-  std::vector<double> h((size_t)4 * npT * nsp + 5 * nsp, 0.0);
-  double *mTw = h.data(), *mT = mTw + (size_t)npT * nsp, *mT2 = mT + (size_t)npT * nsp, *mTpT = mT2 + (size_t)npT * nsp;
-  double *mass2 = mTpT + (size_t)npT * nsp, *baryon = mass2 + nsp, *sign = baryon + nsp, *deg = sign + nsp, *mass = deg + nsp;
-  for (int s = 0; s < nsp; s++) {
-    int ss = rep[s < ns ? s : ns - 1];                    // class representative; padding lanes repeat the last class (never written)
-    double m = ctx->h_mass[ss];
-    mass[s] = m; mass2[s] = m * m; baryon[s] = ctx->h_baryon[ss]; sign[s] = ctx->h_sign[ss]; deg[s] = ctx->h_deg[ss];
-    for (int ip = 0; ip < npT; ip++) {
-      double pT = ctx->pT[ip], v = sqrt(m * m + pT * pT);
-      size_t idx = (size_t)ip * nsp + s;
-      mT[idx] = v; mTw[idx] = v * ctx->pTw[ip]; mT2[idx] = v * v; mTpT[idx] = v * pT;
-    }
+  SpeciesBins sb;
+  IS3D_TRY(build_bin_arrays(ctx, &sb));
+  if (ctx->NpT > kDndxThreads) { ctx->set_error("dN/dX: pT table longer than 256 points"); return IS3D_ERR_UNSUPPORTED; }
+  std::vector<int> slots;
+  if (!build_slot_table(ctx, kDndxR, &slots)) {
+    ctx->set_error("species list holds a baryon number outside -2..2 (the reference's PDG readers produce hadrons and the deuteron only)");
+    return IS3D_ERR_INVALID;
   }
-  void *d = nullptr, *dm = nullptr;
-  IS3D_TRY(ctx->get_scratch("dndx_tables", h.size() * sizeof(double), &d));
-  IS3D_TRY(ctx->get_scratch("class_of", (size_t)ctx->ns * sizeof(int), &dm));
-  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(dm, class_of.data(), (size_t)ctx->ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  *class_of_dev = (const int *)dm;
-  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  const double *b = (const double *)d;
-  g->ns = ns; g->ns_pad = nsp; g->NpT = npT; g->Nphi = ctx->Nphi; g->Ny = ctx->Ny; g->Neta = ctx->Neta; g->dimension = p.dimension;
-  g->mTw = b; g->mT = b + (size_t)npT * nsp; g->mT2 = b + (size_t)2 * npT * nsp; g->mTpT = b + (size_t)3 * npT * nsp;
-  const double *tail = b + (size_t)4 * npT * nsp;
-  g->mass2 = tail; g->baryon = tail + nsp; g->sign = tail + 2 * nsp; g->deg = tail + 3 * nsp; g->mass = tail + 4 * nsp;
+  void *d_slots = nullptr;
+  IS3D_TRY(ctx->get_scratch("dndx_slots", slots.size() * sizeof(int), &d_slots));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `slots` is pageable host memory
+  *class_of_dev = sb.class_of;
+  g->ns = sb.nclass;
+  g->ngroups = (int)(slots.size() / kDndxR);
+  g->gpb = kDndxThreads / ctx->NpT;
+  if (g->gpb > kDndxMaxGroups) g->gpb = kDndxMaxGroups;
+  g->slot_class = (const int *)d_slots;
+  g->NpT = ctx->NpT; g->Nphi = ctx->Nphi; g->Ny = ctx->Ny; g->Neta = ctx->Neta; g->dimension = p.dimension;
+  g->mT = sb.mT; g->baryon = sb.baryon; g->sign = sb.sign;
+  g->c_mass = sb.c_mass; g->c_deg = sb.c_deg; g->c_baryon = sb.c_baryon; g->c_sign = sb.c_sign;
   g->pT = ctx->d_pT; g->pTw = ctx->d_pTw;
   g->cosphi = ctx->d_cosphi; g->sinphi = ctx->d_sinphi; g->phiw = ctx->d_phiw;
   g->yv = ctx->d_y; g->etav = ctx->d_eta; g->etaw = ctx->d_etaw;
@@ -299,9 +399,9 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
 
-  const int nslices = g.ns_pad / kDndxThreads;
-  // ~8 waves of blocks: one-warp blocks, up to 16 resident per SM
-  int64_t want_blocks = 8LL * 16 * ctx->sm_count;
+  const int nslices = (g.ngroups + g.gpb - 1) / g.gpb;
+  // ~8 waves of blocks, two 256-thread blocks resident per SM
+  int64_t want_blocks = 8LL * 2 * ctx->sm_count;
   cudaEvent_t e0, e1;
   IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
   IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));

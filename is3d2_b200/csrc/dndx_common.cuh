@@ -5,11 +5,15 @@
 // pT and phi table weights (the y nodes are summed UNweighted in 3+1d, :330-404) into one scalar dN_dy_cell and adds
 // it to three 1-D histograms selected by the cell's (tau, r, phi_s) (:413-440).
 //
-// GPU mapping: cell-stationary.  One thread = one species class (ctx.h SpeciesBins); a one-warp block walks a contiguous chunk of cells,
-// all lanes on the same cell, so every per-cell / per-(y, phi) quantity is warp-uniform and is simply recomputed in
-// registers (a few % of the 51 x Nphi x Ny evaluations it feeds).  The per-(pT, species) momentum constants come
-// from four transposed tables [ipT][species] (coalesced, L1/L2 resident, 725 KB for 444 species).  The (cell,
-// species) scalar is scattered with three FP64 atomicAdd into histograms [species][bin].
+// GPU mapping (K1's schedule turned cell-stationary).  A thread owns R species classes of ONE baryon number at ONE pT node
+// (the slot table of spectra_df.cu); a 256-thread block covers gpb = 256 / NpT thread groups (5 x 51 = 255 threads for
+// the shipped pT table) and walks a contiguous chunk of cells.  The (y, eta, phi) quadrature points of up to 16 cells are
+// built cooperatively -- one thread per (cell, point) -> 128-item tiles in shared memory -- then every thread marches
+// over a cell's items with broadcast LDS.128 exactly like the spectra kernels (df_eval_u / feqmod_eval_u: the pT
+// products are formed once per (item, thread) and shared by the R evaluations).  After the last item of a cell the
+// R partial sums of each thread are multiplied by the pT weight, reduced over the NpT threads of the group through
+// shared memory + warp shuffles, and the (cell, class) scalar is scattered with three FP64 atomicAdd into histograms
+// [class][bin], expanded to species x degeneracy at the end.
 #pragma once
 
 #include "cellmath.cuh"
@@ -17,20 +21,25 @@
 
 namespace is3d {
 
-constexpr int kDndxThreads = 32;    // one warp per block: species classes are padded to a multiple of this
+constexpr int kDndxThreads = 256;     // threads per block
+constexpr int kDndxTile = 128;        // items (cell x quadrature point) per shared-memory tile
+constexpr int kDndxR = 4;             // species classes per thread
+constexpr int kDndxMaxCells = 16;     // cells per tile
+constexpr int kDndxMaxGroups = 8;     // thread groups per block
 
 struct DndxGrid {
-  int ns, ns_pad;                 // species, padded to a multiple of kDndxThreads
+  int ns;                         // species CLASSES
+  int ngroups, gpb;               // thread groups (kDndxR class slots, one baryon number each); groups per block
+  const int *slot_class;          // [ngroups * kDndxR], -1 = padding
   int NpT, Nphi, Ny, Neta, dimension;
-  // [ipT][ns_pad]: mT * pT_weight, mT, mT^2, mT * pT
-  const double *mTw, *mT, *mT2, *mTpT;
+  const double *mT, *baryon, *sign;                       // [class * NpT + ipT]  (ctx.h SpeciesBins)
+  const double *c_mass, *c_deg, *c_baryon, *c_sign;       // [class]
   const double *pT, *pTw;         // [NpT]
   const double *cosphi, *sinphi, *phiw, *yv, *etav, *etaw;
-  const double *mass2, *baryon, *sign, *deg, *mass;   // [ns_pad]
   // histograms
   double tau_min, tau_width, r_min, r_width, phi_width;
   int tau_bins, r_bins, phi_bins;
-  double *hist_tau, *hist_r, *hist_phi;               // [ns][bins]
+  double *hist_tau, *hist_r, *hist_phi;               // [class][bins]
   const double *exptab;                               // 2^(m/1024), global memory
 };
 

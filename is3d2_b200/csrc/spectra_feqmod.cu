@@ -34,6 +34,9 @@ constexpr int kThreads = 256;
 #ifndef IS3D_K2_R
 #define IS3D_K2_R 4
 #endif
+#ifndef IS3D_K2_PREFETCH
+#define IS3D_K2_PREFETCH 0    // 1: software prefetch of the PTM renorm row of the next item (measured slower, profiles/)
+#endif
 constexpr int kBins = IS3D_K2_R;     // species classes per thread (R)
 
 __global__ void feqmod_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, DfTables tb, FeqmodFlags fl,
@@ -177,6 +180,7 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
         item_cell[slot] = (int)(cell - 0);   // index inside this pass's pack / renorm arrays
       }
       __syncthreads();
+#if IS3D_K2_PREFETCH
       // PTM: the (cell, class) renormalisations of item k + 1 are fetched (L2) while item k is evaluated
       double rn_next[R];
       if (SPECIES_RENORM && n_items > 0) {
@@ -184,10 +188,12 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
 #pragma unroll
         for (int r = 0; r < R; r++) rn_next[r] = row[sp[r]];
       }
+#endif
 #pragma unroll 1
       for (int k = 0; k < n_items; k++) {
         double rn[R];
         if (SPECIES_RENORM) {
+#if IS3D_K2_PREFETCH
 #pragma unroll
           for (int r = 0; r < R; r++) rn[r] = rn_next[r];
           if (k + 1 < n_items) {
@@ -195,6 +201,11 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
 #pragma unroll
             for (int r = 0; r < R; r++) rn_next[r] = row[sp[r]];
           }
+#else
+          const double *row = renorm + (int64_t)item_cell[k] * g.ns;
+#pragma unroll
+          for (int r = 0; r < R; r++) rn[r] = row[sp[r]];
+#endif
         }
         if (!item_linear[k]) {
           const FeqmodItem &it = items[k].mod;        // shared memory: broadcast LDS.128 + one LDS.64 for eb[eslot]

@@ -58,6 +58,17 @@ SPECTRA_CASES = {
     "s2d_m4_box_phi48": dict(surface=("s3d", dict(n=40, seed=3, dimension=2, stress=0.3)), params=_p(df_mode=4, dimension=2, hrg_eos=3),
                              chosen=os.path.join(_GOLDEN, "chosen_box_small.dat"), tables=dict(phi_table="phi_table_48pt.dat")),
     "s3d_m3_smash_9cells": dict(surface=("s3d", dict(n=9, seed=13, stress=0.3)), params=_p(df_mode=3), chosen="smash"),
+    # all SMASH species WITH baryon terms: mesons, baryons, antibaryons and the deuteron (b = 0, +1, -1, 2) -- the thread
+    # groups of one baryon number and the exp(-b alpha_B) slots of the spectra kernels (spectra_df.cuh DfItemU)
+    "s3d_m1_smash_baryon": dict(surface=("s3d", dict(n=11, seed=71, baryon=True)),
+                                params=_p(df_mode=1, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
+    "s3d_m2_smash_baryon": dict(surface=("s3d", dict(n=11, seed=72, baryon=True)),
+                                params=_p(df_mode=2, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
+    "s3d_m2_smash_baryon_reg_outflow": dict(surface=("s3d", dict(n=9, seed=73, baryon=True)),
+                                            params=_p(df_mode=2, include_baryon=1, include_baryondiff_deltaf=1, regulate_deltaf=1, outflow=1),
+                                            chosen="smash"),
+    "s3d_m3_smash_baryon": dict(surface=("s3d", dict(n=11, seed=74, baryon=True, stress=0.3)),
+                                params=_p(df_mode=3, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
     # ---- K3: PTMA modified anisotropic distribution (df_mode 5), reference-faithful initial-guess chain ----
     # BASELINE.json config 4: VAH-like surface (large P_L / P_T anisotropy) with df_mode 5
     "vah_m5": dict(surface=("s3d", dict(n=200, seed=51, vah=True)), params=_p(df_mode=5), chosen="pikp"),
@@ -88,6 +99,14 @@ DNDX_CASES = {
     "dndx_s3d_m4_reg_outflow": dict(surface=("s3d", dict(n=200, seed=35, stress=0.3)),
                                     params=_p(operation=0, df_mode=4, regulate_deltaf=1, outflow=1), chosen="pikp"),
     "dndx_s2d_m3": dict(surface=("s3d", dict(n=80, seed=36, dimension=2, stress=0.3)), params=_p(operation=0, df_mode=3, dimension=2), chosen="pikp"),
+    # all SMASH species with baryon terms (b = 0, +1, -1, 2): uniform-baryon thread groups of the dN/dX kernels
+    "dndx_s3d_m1_smash_baryon": dict(surface=("s3d", dict(n=12, seed=81, baryon=True)),
+                                     params=_p(operation=0, df_mode=1, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
+    "dndx_s3d_m2_smash_baryon": dict(surface=("s3d", dict(n=12, seed=82, baryon=True)),
+                                     params=_p(operation=0, df_mode=2, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
+    "dndx_s3d_m3_smash_baryon": dict(surface=("s3d", dict(n=12, seed=83, baryon=True, stress=0.3)),
+                                     params=_p(operation=0, df_mode=3, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
+    "dndx_s3d_m4_smash": dict(surface=("s3d", dict(n=12, seed=84, stress=0.3)), params=_p(operation=0, df_mode=4), chosen="smash"),
     "dndx_s2d_m4": dict(surface=("s3d", dict(n=80, seed=37, dimension=2, stress=0.3)), params=_p(operation=0, df_mode=4, dimension=2, hrg_eos=1), chosen="pikp"),
 }
 
