@@ -412,17 +412,23 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
         except OSError:
             pass
         bytes_alg = cells * 25 * 8.0 + total * 8.0
-        # DRAM bytes of ONE df_spectra_kernel launch from the ncu --set full capture of this command at the default size
-        # (profiles/r01_summary.md: 356.3 MB read + 31.8 MB written); null for any other configuration
-        default_cfg = (args.df_mode == 2 and cells == 1_250_000)
-        traffic = 388.1e6 if default_cfg else None
-        traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_summary.md" if default_cfg else None
+        # DRAM bytes and FP64-pipe utilisation of ONE df_spectra_kernel launch from the committed `ncu --set full` capture of
+        # this command at the default size (profiles/r01_ncu_k1_headline.json); null for any other configuration
+        traffic = traffic_src = fp64_pct = None
+        try:
+            cap = json.load(open(os.path.join(REPO, "profiles", "r01_ncu_k1_headline.json")))
+            if cap["config"] == {"df_mode": args.df_mode, "cells_per_gpu": cells}:
+                traffic = float(cap["dram_bytes_read"] + cap["dram_bytes_write"])
+                traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_k1_headline.json"
+                fp64_pct = cap["fp64_pipe_active_pct"]
+        except (OSError, KeyError, ValueError):
+            pass
         line = {
             "metric": "Cooper-Frye cell*species*momentum evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.df_mode, cells, world), "global_cells": cells * world,
-                       "evals_per_step": evals_rank * world, "l2_policy": "inputs larger than L2 (cell packs: 240 B x cells per pass)",
+                       "evals_per_step": evals_rank * world, "l2_policy": "inputs larger than L2 (cell packs: 256 B x cells per pass)",
                        "parallelism": f"cells sharded x{world}, one NCCL all-reduce of {total} doubles" if world > 1 else "single GPU",
                        "species_classes": "evaluations are counted per species (444); species with identical (mass, sign, baryon "
                                           "number) share one integrand, computed once and scaled by each species' degeneracy "
@@ -433,7 +439,7 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "df_spectra_kernel" if args.df_mode <= 2 else "feqmod_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
-                         "fp64_pipe_active_pct_ncu": 71.1 if args.df_mode == 2 else None,
+                         "fp64_pipe_active_pct_ncu": fp64_pct,
                          "flops_per_eval_algorithmic": F_ALG[args.df_mode],
                          "peak_source": "DFMA micro-benchmark run live by is3d_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
                          "hbm_gbs_algorithmic": bytes_alg / kern_s / 1e9, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},

@@ -95,10 +95,10 @@ struct DndxThread {
 };
 
 // End of a cell: thread partials (x pT weight x `gate`) -> sums over the NpT threads of every group -> histograms.
-// red is double-buffered by the caller (one __syncthreads per cell).
+// red is double-buffered by the caller (one __syncthreads per cell); bins = the cell's histogram bins (shared memory).
 template <int R>
 __device__ __forceinline__ void dndx_flush(double (&acc)[R], double factor, double (*red)[kDndxThreads], const DndxGrid &g,
-                                           const SurfaceView &surf, int64_t gcell)
+                                           const DndxCellBins &bins)
 {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 #pragma unroll
@@ -115,7 +115,7 @@ __device__ __forceinline__ void dndx_flush(double (&acc)[R], double factor, doub
     for (int i = lane; i < g.NpT; i += 32) v += red[r][gl * g.NpT + i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) dndx_scatter(g, cls, surf.col[0][gcell], surf.col[1][gcell], surf.col[2][gcell], kCooperFryePrefactor * v);
+    if (lane == 0) dndx_scatter(g, cls, bins, kCooperFryePrefactor * v);
   }
 }
 
@@ -141,6 +141,7 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
   __shared__ DfItemU items[kDndxTile];
   __shared__ double red[2][R][kDndxThreads];
   __shared__ int cell_ok[kDndxMaxCells];
+  __shared__ DndxCellBins cell_bins[kDndxMaxCells];
   load_exp_table(exptab, g.exptab);
   const int t = threadIdx.x;
   DndxThread<R> th;
@@ -164,7 +165,11 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
         const int64_t cell = cell0 + cl;
         if (cl < tl.cpt && cell < c1) {
           const bool ok = pack[DP_VALID * stride + cell] != 0.0;
-          if (j == p0) cell_ok[cl] = ok ? 1 : 0;
+          if (j == p0) {
+            cell_ok[cl] = ok ? 1 : 0;
+            const int64_t gc = surf_begin + cell;
+            if (ok) cell_bins[cl] = dndx_cell_bins(g, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc]);
+          }
           if (ok) {
             auto pk = [&](int k) { return pack[k * stride + cell]; };
             const DndxPoint pt = dndx_point(g, pk, j);
@@ -186,7 +191,7 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
             for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, th.mT[r], th.mT2[r], th.sgn[r], exptab);
           }
         }
-        if (last_tile) { dndx_flush<R>(acc, th.wpT, red[buf], g, surf, surf_begin + cell0 + cl); buf ^= 1; }
+        if (last_tile) { dndx_flush<R>(acc, th.wpT, red[buf], g, cell_bins[cl]); buf ^= 1; }
       }
     }
   }
@@ -213,6 +218,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
   __shared__ double cell_rn[kDndxMaxCells];                                   // the cell's |renorm| (0: skip the cell)
   __shared__ double class_rn[SPECIES_RENORM ? kDndxMaxCells : 1][kDndxMaxGroups * R];   // PTM: |renorm| per (cell, class slot)
   __shared__ int cell_ok[kDndxMaxCells];
+  __shared__ DndxCellBins cell_bins[kDndxMaxCells];
   __shared__ RenormNodes nodes;
   load_exp_table(exptab, g.exptab);
   if (SPECIES_RENORM) nodes.load(gla_root, gla_weight, gla_pts);
@@ -242,7 +248,11 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
         if (cl < tl.cpt && cell < c1) {
           const bool ok = pack[DP_VALID * stride + cell] != 0.0;
           auto pk = [&](int k) { return pack[k * stride + cell]; };
-          if (j == p0) { cell_ok[cl] = ok ? 1 : 0; cell_rn[cl] = ok ? pk(FP_RENORM) : 0.0; }
+          if (j == p0) {
+            cell_ok[cl] = ok ? 1 : 0; cell_rn[cl] = ok ? pk(FP_RENORM) : 0.0;
+            const int64_t gc = surf_begin + cell;
+            if (ok) cell_bins[cl] = dndx_cell_bins(g, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc]);
+          }
           if (ok) {
             const DndxPoint pt = dndx_point(g, pk, j);
             bool linear = pk(FP_BREAKDOWN) != 0.0;
@@ -306,7 +316,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
             for (int r = 0; r < R; r++) acc[r] = (rn[r] != 0.0) ? acc[r] : 0.0;
           }
           const double factor = (SPECIES_RENORM || cell_rn[cl] != 0.0) ? th.wpT : 0.0;
-          dndx_flush<R>(acc, factor, red[buf], g, surf, surf_begin + cell0 + cl);
+          dndx_flush<R>(acc, factor, red[buf], g, cell_bins[cl]);
           buf ^= 1;
         }
       }

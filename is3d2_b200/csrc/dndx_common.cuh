@@ -43,8 +43,10 @@ struct DndxGrid {
   const double *exptab;                               // 2^(m/1024), global memory
 };
 
-// SpacetimeDistribution.cpp:413-440
-IS3D_D void dndx_scatter(const DndxGrid &g, int s, double tau, double x, double y, double value)
+// histogram bins of a cell (SpacetimeDistribution.cpp:413-440), -1 = outside the histogram; evaluated once per cell
+struct DndxCellBins { int itau, ir, iphi; };
+
+IS3D_D DndxCellBins dndx_cell_bins(const DndxGrid &g, double tau, double x, double y)
 {
   double r = sqrt(x * x + y * y);
   double phi = atan2(y, x);
@@ -52,10 +54,19 @@ IS3D_D void dndx_scatter(const DndxGrid &g, int s, double tau, double x, double 
   long itau = (int)floor((tau - g.tau_min) / g.tau_width);
   long ir = (int)floor((r - g.r_min) / g.r_width);
   long iphi = (int)floor(phi / g.phi_width);
+  DndxCellBins b;
+  b.itau = (itau >= 0 && itau < g.tau_bins) ? (int)itau : -1;
+  b.ir = (ir >= 0 && ir < g.r_bins) ? (int)ir : -1;
+  b.iphi = (iphi >= 0 && iphi < g.phi_bins) ? (int)iphi : -1;
+  return b;
+}
+
+IS3D_D void dndx_scatter(const DndxGrid &g, int s, const DndxCellBins &b, double value)
+{
 #if defined(__CUDA_ARCH__)
-  if (itau >= 0 && itau < g.tau_bins) atomicAdd(&g.hist_tau[(size_t)s * g.tau_bins + itau], value);
-  if (ir >= 0 && ir < g.r_bins) atomicAdd(&g.hist_r[(size_t)s * g.r_bins + ir], value);
-  if (iphi >= 0 && iphi < g.phi_bins) atomicAdd(&g.hist_phi[(size_t)s * g.phi_bins + iphi], value);
+  if (b.itau >= 0) atomicAdd(&g.hist_tau[(size_t)s * g.tau_bins + b.itau], value);
+  if (b.ir >= 0) atomicAdd(&g.hist_r[(size_t)s * g.r_bins + b.ir], value);
+  if (b.iphi >= 0) atomicAdd(&g.hist_phi[(size_t)s * g.phi_bins + b.iphi], value);
 #endif
 }
 

@@ -6,7 +6,7 @@
 // equivalent to ONE Poisson draw of mean Nevents * dn_tot per cell followed by a uniform event label per hadron, so
 // the GPU pipeline is flat in (cell, hadron):
 //   1. sampler_setup_kernel   thread per cell: LRF quantities, df coefficients, breakdown test, mean yield dn_tot,
-//                             N ~ Poisson(Nevents dn_tot) with the cell's own Philox stream -> 57-double pack, count
+//                             N ~ Poisson(Nevents dn_tot) with the cell's own Philox stream -> 59-double pack, count
 //   2. exclusive scan of the counts (cub::DeviceScan, plumbing) -> proposal offsets
 //   3. sampler_hadron_kernel  thread per proposed hadron: cell by binary search in the offsets, event label, species
 //                             by inverse CDF over the (cell-independent) cumulative density tables, thermal momentum

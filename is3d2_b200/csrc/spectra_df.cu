@@ -3,15 +3,16 @@
 //
 // Layout / schedule
 //   1. df_setup_kernel: one thread per cell; reads the 20-25 SoA surface columns (coalesced), evaluates the df
-//      coefficients and writes a 30-double "cell pack" as SoA into HBM (240 B / cell).
-//   2. df_spectra_kernel: output-stationary.  blockIdx.x = slice of (species group, pT) columns, blockIdx.y =
-//      (iy, iphi), blockIdx.z = contiguous chunk of cells.  A thread owns R consecutive species at ONE pT node, so
-//      every product of an item constant with pT alone is formed once per item and shared by its R evaluations.
-//      A block streams its chunk in tiles of 256 cells: each thread turns one cell pack into the 16-double item
+//      coefficients and writes a 32-double "cell pack" as SoA into HBM (256 B / cell).
+//   2. df_spectra_kernel: output-stationary.  blockIdx.x = slice of (thread group, pT) columns, blockIdx.y =
+//      (iy, iphi), blockIdx.z = contiguous chunk of cells.  A thread owns R species classes of ONE baryon number at
+//      ONE pT node (build_slot_table), so every product of an item constant with pT or b is formed once per item and
+//      shared by its R evaluations (spectra_df.cuh: DfItemU, df_share_u, df_eval_u).
+//      A block streams its chunk in tiles of 256 cells: each thread turns one cell pack into the 18-double item
 //      constants for the block's (y, phi) -- one sinh per cell per tile -- with invalid (u.dsigma <= 0) cells
 //      compacted away by ballot/prefix; then every thread marches over the tile, reading the warp-uniform item
 //      with broadcast LDS.128 and updating its R register accumulators.
-//      FP64-pipe bound: HBM traffic is 240 B per cell per block against >= 768 * ~40 DFMA per cell per block.
+//      FP64-pipe bound: HBM traffic is 256 B per cell per block against >= 1024 * ~27 DFMA per cell per block.
 //   3. reduce_partials_kernel: deterministic sum over the cell chunks.
 #include "ctx.h"
 #include "spectra_df.cuh"

@@ -3,12 +3,13 @@
 //
 // Schedule (same output-stationary design as K1, see spectra_df.cu):
 //   1. feqmod_setup_kernel   one thread per cell: LRF boost, A_ij, refined inverse, breakdown test (two 32-point
-//                            Gauss-Laguerre sums for PTM), linear-df fallback coefficients -> 55-double cell pack
+//                            Gauss-Laguerre sums for PTM), linear-df fallback coefficients -> 57-double cell pack
 //   2. feqmod_renorm_kernel  PTM with bulk only: one thread per (cell, species): n_linear / n_mod from four
 //                            32-point Gauss-Laguerre sums -> renorm[cell][species]
-//   3. feqmod_spectra_kernel blocks = (species x pT slice, (y, phi), cell chunk); per 256-cell tile every thread
-//                            builds one cell's item for the block's (y, phi); the inner loop takes a warp-uniform
-//                            branch per item: modified distribution (4 FMA + sqrt + exp + rcp) or linear-df fallback
+//   3. feqmod_spectra_kernel blocks = ((thread group, pT) slice, (y, phi), cell chunk), a thread = 4 classes of one baryon
+//                            number at one pT node (build_slot_table); per 256-cell tile every thread builds one cell's
+//                            item for the block's (y, phi); the inner loop takes a warp-uniform branch per item:
+//                            modified distribution (3 FMA + sqrt + exp + FMA + rcp, feqmod_eval_u) or linear-df fallback
 //   4. reduce_partials_kernel (shared with K1)
 #include "ctx.h"
 #include "spectra_feqmod.cuh"
@@ -33,9 +34,6 @@ constexpr int kTile = 256;
 constexpr int kThreads = 256;
 #ifndef IS3D_K2_R
 #define IS3D_K2_R 4
-#endif
-#ifndef IS3D_K2_PREFETCH
-#define IS3D_K2_PREFETCH 0    // 1: software prefetch of the PTM renorm row of the next item (measured slower, profiles/)
 #endif
 constexpr int kBins = IS3D_K2_R;     // species classes per thread (R)
 
@@ -180,32 +178,13 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
         item_cell[slot] = (int)(cell - 0);   // index inside this pass's pack / renorm arrays
       }
       __syncthreads();
-#if IS3D_K2_PREFETCH
-      // PTM: the (cell, class) renormalisations of item k + 1 are fetched (L2) while item k is evaluated
-      double rn_next[R];
-      if (SPECIES_RENORM && n_items > 0) {
-        const double *row = renorm + (int64_t)item_cell[0] * g.ns;
-#pragma unroll
-        for (int r = 0; r < R; r++) rn_next[r] = row[sp[r]];
-      }
-#endif
 #pragma unroll 1
       for (int k = 0; k < n_items; k++) {
         double rn[R];
-        if (SPECIES_RENORM) {
-#if IS3D_K2_PREFETCH
-#pragma unroll
-          for (int r = 0; r < R; r++) rn[r] = rn_next[r];
-          if (k + 1 < n_items) {
-            const double *row = renorm + (int64_t)item_cell[k + 1] * g.ns;
-#pragma unroll
-            for (int r = 0; r < R; r++) rn_next[r] = row[sp[r]];
-          }
-#else
+        if (SPECIES_RENORM) {      // L2-resident row; a software prefetch of item k + 1's row measured 11 % slower (profiles/r01_summary.md)
           const double *row = renorm + (int64_t)item_cell[k] * g.ns;
 #pragma unroll
           for (int r = 0; r < R; r++) rn[r] = row[sp[r]];
-#endif
         }
         if (!item_linear[k]) {
           const FeqmodItem &it = items[k].mod;        // shared memory: broadcast LDS.128 + one LDS.64 for eb[eslot]
