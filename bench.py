@@ -28,6 +28,28 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
+# The C++ host layer keeps the reference's printf chatter ("Number of chosen particles = ...") on stdout.  The contract is
+# ONE JSON line on stdout, so fd 1 is pointed at stderr for the whole run and the line is written to the saved descriptor.
+_JSON_FD = None
+
+
+def _claim_stdout() -> None:
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
 from is3d2_b200 import synthetic, workdir  # noqa: E402
 
 # algorithmic FLOPs per integrand evaluation (SURVEY.md 8d / BASELINE.md 4; DESIGN.md restates the derivation)
@@ -136,7 +158,7 @@ def run_reference(args) -> None:
                 "config": {"workload": workload_name(args.df_mode, args.cells_per_gpu, args.gpus), "sample": sample},
                 "cpu_baseline": {"value": value, "unit": "evals/s", "cores": 1, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
     surf = synthetic.s3d(cells, seed=2024, baryon=True)
     params = bench_params(args.df_mode)
@@ -166,7 +188,7 @@ def run_reference(args) -> None:
             "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline(args) -> dict:
@@ -297,7 +319,7 @@ def run_ours(args) -> None:
     try:
         line = _measure_ours(args, h, world, rank, local)
         if rank == 0:
-            print(json.dumps(line), flush=True)
+            emit(line)
     finally:
         # tear-down order matters: every torch tensor that touched the context's stream or NCCL must be released before
         # the process group and the stream go away (a tensor freed afterwards aborts the rank with "context is destroyed")
@@ -471,6 +493,7 @@ def main():
     ap.add_argument("--sampler-events", type=int, default=1000)
     ap.add_argument("--ref-sampler-cells", type=int, default=3000)
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

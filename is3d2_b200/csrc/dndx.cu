@@ -300,7 +300,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
               const double eb = BARYON ? it.eb[th.eslot] : 1.0;
 #pragma unroll
               for (int r = 0; r < R; r++)
-                acc[r] += feqmod_eval_u<BARYON, OUTFLOW, !SPECIES_RENORM>(it, sh, eb, th.mT[r], th.mT2[r], th.sgn[r], rn[r], exptab);
+                feqmod_accum_u<BARYON, OUTFLOW, !SPECIES_RENORM>(acc[r], it, sh, eb, th.mT[r], th.mT2[r], th.sgn[r], rn[r], exptab);
             } else {
               const DfItem it = items[slot].lin;
               const DfShared sh = df_share<BARYON>(it, th.pT, th.pT2);

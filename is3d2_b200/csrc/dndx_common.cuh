@@ -9,7 +9,7 @@
 // (the slot table of spectra_df.cu); a 256-thread block covers gpb = 256 / NpT thread groups (5 x 51 = 255 threads for
 // the shipped pT table) and walks a contiguous chunk of cells.  The (y, eta, phi) quadrature points of up to 16 cells are
 // built cooperatively -- one thread per (cell, point) -> 128-item tiles in shared memory -- then every thread marches
-// over a cell's items with broadcast LDS.128 exactly like the spectra kernels (df_eval_u / feqmod_eval_u: the pT
+// over a cell's items with broadcast LDS.128 exactly like the spectra kernels (df_eval_u / feqmod_accum_u: the pT
 // products are formed once per (item, thread) and shared by the R evaluations).  After the last item of a cell the
 // R partial sums of each thread are multiplied by the pT weight, reduced over the NpT threads of the group through
 // shared memory + warp shuffles, and the (cell, class) scalar is scattered with three FP64 atomicAdd into histograms

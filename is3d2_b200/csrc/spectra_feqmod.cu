@@ -9,7 +9,7 @@
 //   3. feqmod_spectra_kernel blocks = ((thread group, pT) slice, (y, phi), cell chunk), a thread = 4 classes of one baryon
 //                            number at one pT node (build_slot_table); per 256-cell tile every thread builds one cell's
 //                            item for the block's (y, phi); the inner loop takes a warp-uniform branch per item:
-//                            modified distribution (3 FMA + sqrt + exp + FMA + rcp, feqmod_eval_u) or linear-df fallback
+//                            modified distribution (3 FMA + sqrt + exp + FMA + rcp, feqmod_accum_u) or linear-df fallback
 //   4. reduce_partials_kernel (shared with K1)
 #include "ctx.h"
 #include "spectra_feqmod.cuh"
@@ -54,9 +54,11 @@ __global__ void feqmod_setup_kernel(SurfaceView surf, int64_t begin, int64_t cou
   if (st & CELL_PL_NEGATIVE) { atomicAdd(&counters[3], 1ull); atomicMax(&counters[5], (unsigned long long)(begin + i + 1)); }
 }
 
-// PTM renormalisation n_linear / n_mod per (cell, class) (MomentumSpectra.cpp:795-826): feqmod_renorm_ptm_fused
+// PTM renormalisation n_linear / n_mod per (cell, class) (MomentumSpectra.cpp:795-826): feqmod_renorm_ptm_fused.
+// Rows are written in SLOT order, renorm[cell][group * R + r] (ns = number of slots, padding slots = 0), so that a thread
+// of the spectra kernel reads the R values of its group as one aligned 32-byte segment.
 __global__ void __launch_bounds__(128)
-feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int ns,
+feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int ns, const int *__restrict__ slot_class,
                      const double *__restrict__ mass, const double *__restrict__ deg,
                      const double *__restrict__ baryon, const double *__restrict__ sign,
                      const double *__restrict__ gla_root, const double *__restrict__ gla_weight, int gla_pts,
@@ -70,9 +72,9 @@ feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t co
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count * ns) return;
   int64_t cell = idx / ns;
-  int s = (int)(idx - cell * ns);
+  const int s = slot_class[(int)(idx - cell * ns)];
   double r = 0.0;
-  if (pack[DP_VALID * stride + cell] != 0.0) {
+  if (s >= 0 && pack[DP_VALID * stride + cell] != 0.0) {
     auto pk = [&](int k) { return pack[k * stride + cell]; };
     r = feqmod_renorm_ptm_fused(pk, mass[s], deg[s], baryon[s], sign[s], nodes, gla_pts, exptab);
   }
@@ -81,7 +83,7 @@ feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t co
 
 struct FeqGrid {
   const double *mT, *pT, *m2, *baryon, *sign;
-  int ncols, NpT, ns;                   // ns = number of species CLASSES; ncols = NpT * ngroups thread columns
+  int ncols, NpT, ns, nslots;           // ns = number of species CLASSES; ncols = NpT * ngroups thread columns; nslots = ngroups * kBins
   const int *slot_class;                // [ngroups * kBins]: class of slot r of a thread group (-1 = padding), one baryon
                                         // number per group (build_slot_table, spectra_df.cu)
   int Ny, Nphi, Neta, dimension;
@@ -182,9 +184,14 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
       for (int k = 0; k < n_items; k++) {
         double rn[R];
         if (SPECIES_RENORM) {      // L2-resident row; a software prefetch of item k + 1's row measured 11 % slower (profiles/r01_summary.md)
-          const double *row = renorm + (int64_t)item_cell[k] * g.ns;
+          const double *row = renorm + (int64_t)item_cell[k] * g.nslots + grp * R;
+          if (R % 2 == 0) {
 #pragma unroll
-          for (int r = 0; r < R; r++) rn[r] = row[sp[r]];
+            for (int r = 0; r < R; r += 2) { const double2 v = *reinterpret_cast<const double2 *>(row + r); rn[r] = v.x; rn[r + 1] = v.y; }
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) rn[r] = row[r];
+          }
         }
         if (!item_linear[k]) {
           const FeqmodItem &it = items[k].mod;        // shared memory: broadcast LDS.128 + one LDS.64 for eb[eslot]
@@ -192,7 +199,7 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
           const double eb = BARYON ? it.eb[eslot] : 1.0;
 #pragma unroll
           for (int r = 0; r < R; r++)
-            acc[r] += feqmod_eval_u<BARYON, OUTFLOW, !SPECIES_RENORM>(it, sh, eb, bin[r].mT, bin[r].mT2, bin[r].sign, SPECIES_RENORM ? rn[r] : 1.0, exptab);
+            feqmod_accum_u<BARYON, OUTFLOW, !SPECIES_RENORM>(acc[r], it, sh, eb, bin[r].mT, bin[r].mT2, bin[r].sign, SPECIES_RENORM ? rn[r] : 1.0, exptab);
         } else {
           const DfItem it = items[k].lin;
           const DfShared sh = df_share<BARYON>(it, pT, pT2);
@@ -263,7 +270,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `slots` is pageable host memory
   g.slot_class = (const int *)d_slots;
-  g.NpT = ctx->NpT; g.ns = sb.nclass; g.ncols = ctx->NpT * (int)(slots.size() / kBins);
+  g.NpT = ctx->NpT; g.ns = sb.nclass; g.nslots = (int)slots.size(); g.ncols = ctx->NpT * (int)(slots.size() / kBins);
   const int64_t per_species = (int64_t)ctx->NpT * ctx->Nphi * ctx->Ny;
   const int64_t total_class = (int64_t)sb.nclass * per_species;
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
@@ -277,7 +284,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
 
   // cells per pass: bounds the pack (440 B/cell) and the PTM renorm table (8 Ns B/cell) to ~2 GB
   int64_t macro = pass_cells(2 << 20);
-  if (species_renorm) { int64_t m2 = ((int64_t)1 << 31) / (8 * (int64_t)sb.nclass); if (m2 < macro) macro = m2; }
+  if (species_renorm) { int64_t m2 = ((int64_t)1 << 31) / (8 * (int64_t)g.nslots); if (m2 < macro) macro = m2; }
   macro = macro / kTile * kTile;
   if (macro < kTile) macro = kTile;
   const int64_t stride = n < macro ? n : macro;
@@ -288,7 +295,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)FP_SIZE * stride * sizeof(double), &pack));
   IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total_class * sizeof(double), &partial));
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
-  if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm", (size_t)stride * sb.nclass * sizeof(double), &renorm));
+  if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm", (size_t)stride * g.nslots * sizeof(double), &renorm));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total_class * sizeof(double), ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
 
@@ -310,9 +317,9 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
       launches++;
     }
     if (species_renorm) {
-      int64_t work = count * sb.nclass;
+      int64_t work = count * g.nslots;
       feqmod_renorm_kernel<<<(unsigned)((work + 127) / 128), 128, 0, ctx->stream>>>(
-          (double *)pack, stride, count, sb.nclass, sb.c_mass, sb.c_deg, sb.c_baryon, sb.c_sign, ctx->d_gla_root,
+          (double *)pack, stride, count, g.nslots, g.slot_class, sb.c_mass, sb.c_deg, sb.c_baryon, sb.c_sign, ctx->d_gla_root,
           ctx->d_gla_weight, ctx->gla_pts, ctx->d_exptab, (double *)renorm);
       IS3D_CUDA_TRY(ctx, cudaGetLastError());
       launches++;

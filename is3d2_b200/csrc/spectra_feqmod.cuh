@@ -282,17 +282,18 @@ IS3D_HD double feqmod_distribution(const FeqmodItem &it, const FeqmodShared &s, 
 // (item, thread); with FOLDED the cell's renormalisation already multiplies c1 / d1 (feqmod_make_item fold_renorm),
 // otherwise renorm_sp = |renorm| of this (cell, class).  FP64-pipe instructions per evaluation: 3 (E'^2) + 5 (sqrt) +
 // 7 (exp) + 1 + 3 (rcp) + 2 (+ 1 unfolded) = 21 (22); the first version took 28 (29).
+// Accumulates into acc with the final FMA inside the branch (returning the contribution lets the compiler merge the
+// "+=" of the modified and the linear branch behind their join, which costs a DMUL + DADD instead of one DFMA).
 template <bool BARYON, bool OUTFLOW, bool FOLDED>
-IS3D_HD double feqmod_eval_u(const FeqmodItem &it, const FeqmodShared &s, double eb, double mT, double mT2, double sign,
-                             double renorm_sp, const double *__restrict__ exptab)
+IS3D_HD void feqmod_accum_u(double &acc, const FeqmodItem &it, const FeqmodShared &s, double eb, double mT, double mT2, double sign,
+                            double renorm_sp, const double *__restrict__ exptab)
 {
   const double e2 = fma(mT2, it.h1, fma(mT, s.ph2, s.ph3));
   const double e = fast_exp(fast_sqrt(e2), exptab);
   const double f = fast_rcp(BARYON ? fma(e, eb, sign) : e + sign);
   const double pds = fma(mT, it.c1, s.pd);
-  double contrib = FOLDED ? pds * f : (pds * f) * renorm_sp;
-  if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
-  return contrib;
+  const double sum = FOLDED ? fma(pds, f, acc) : fma(pds * f, renorm_sp, acc);
+  acc = (OUTFLOW && pds <= 0.0) ? acc : sum;
 }
 
 #if defined(__CUDACC__)
