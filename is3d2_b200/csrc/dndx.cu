@@ -216,6 +216,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
   __shared__ unsigned char item_linear[kDndxTile];
   __shared__ double red[2][R][kDndxThreads];
   __shared__ double cell_rn[kDndxMaxCells];                                   // the cell's |renorm| (0: skip the cell)
+  __shared__ int cell_lin[kDndxMaxCells];                                     // the cell may hold linear-df items (breakdown / window)
   __shared__ double class_rn[SPECIES_RENORM ? kDndxMaxCells : 1][kDndxMaxGroups * R];   // PTM: |renorm| per (cell, class slot)
   __shared__ int cell_ok[kDndxMaxCells];
   __shared__ DndxCellBins cell_bins[kDndxMaxCells];
@@ -250,6 +251,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
           auto pk = [&](int k) { return pack[k * stride + cell]; };
           if (j == p0) {
             cell_ok[cl] = ok ? 1 : 0; cell_rn[cl] = ok ? pk(FP_RENORM) : 0.0;
+            cell_lin[cl] = (ok && (pk(FP_BREAKDOWN) != 0.0 || (g.dimension == 3 && pk(FP_DETA) < 0.01))) ? 1 : 0;
             const int64_t gc = surf_begin + cell;
             if (ok) cell_bins[cl] = dndx_cell_bins(g, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc]);
           }
@@ -290,7 +292,18 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
         double rn[R];
 #pragma unroll
         for (int r = 0; r < R; r++) rn[r] = SPECIES_RENORM ? class_rn[cl][th.gl * R + r] : 1.0;
-        if (th.active) {
+        if (th.active && !cell_lin[cl]) {
+          // common case, no linear-df item in this cell: lean loop, the R evaluations interleave
+#pragma unroll 1
+          for (int k = 0; k < np_tile; k++) {
+            const FeqmodItem &it = items[cl * np_tile + k].mod;
+            const FeqmodShared sh = feqmod_share(it, th.pT, th.pT2);
+            const double eb = BARYON ? it.eb[th.eslot] : 1.0;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+              feqmod_accum_u<BARYON, OUTFLOW, !SPECIES_RENORM>(acc[r], it, sh, eb, th.mT[r], th.mT2[r], th.sgn[r], rn[r], exptab);
+          }
+        } else if (th.active) {
 #pragma unroll 1
           for (int k = 0; k < np_tile; k++) {
             const int slot = cl * np_tile + k;

@@ -98,16 +98,35 @@ union ItemSlot {
   __device__ ItemSlot() {}
 };
 
-template <bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM, int R>
+// tile_linear[tile] != 0 <=> some cell of the 256-cell tile can take the linear-df branch for some y (breakdown cell, or
+// detA < 0.01 on a 3+1d surface: the narrow y - eta window); lets the LINEAR launch skip every other tile after one load
+__global__ void feqmod_tile_flags_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int dimension,
+                                         int *__restrict__ tile_linear)
+{
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool lin = false;
+  if (cell < count && pack[DP_VALID * stride + cell] != 0.0)
+    lin = pack[FP_BREAKDOWN * stride + cell] != 0.0 || (dimension == 3 && pack[FP_DETA * stride + cell] < 0.01);
+  const unsigned any = __ballot_sync(0xffffffffu, lin);
+  if ((threadIdx.x & 31) == 0 && any) atomicOr(&tile_linear[cell / kTile], 1);
+}
+
+// One instantiation per BRANCH of the reference's per-momentum choice (MomentumSpectra.cpp:932-1040): LINEAR = false takes the
+// items of the modified distribution, LINEAR = true the linear-df fallback items (breakdown cells and the narrow y - eta
+// window); each launch compacts the other kind away together with the u.dsigma <= 0 cells, both add into `partial`.
+// Two lean loops instead of one loop with a per-item branch: the modified loop alone needs far fewer registers, so ptxas
+// interleaves the R evaluations (with both branches in one body it fell back to two at a time) and the per-item flag
+// load / test / branch / reconvergence instructions disappear.
+template <bool LINEAR, bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM, int R>
 __global__ void __launch_bounds__(kThreads, 2)
 feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk,
-                      const double *__restrict__ renorm, FeqGrid g, double *__restrict__ partial, int64_t total)
+                      const double *__restrict__ renorm, const int *__restrict__ tile_linear, FeqGrid g,
+                      double *__restrict__ partial, int64_t total)
 {
   __shared__ ItemSlot items[kTile];
   __shared__ double exptab[kExpTableSize];
   load_exp_table(exptab, g.exptab);
   __shared__ int item_cell[kTile];
-  __shared__ unsigned char item_linear[kTile];
   __shared__ int warp_count[kThreads / 32];
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -144,8 +163,18 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
   if (chunk_end > ncells) chunk_end = ncells;
 
   for (int64_t tile = chunk_begin; tile < chunk_end; tile += kTile) {
+    if (LINEAR && tile_linear[tile / kTile] == 0) continue;      // chunks start on tile boundaries (choose_chunks)
     const int64_t cell = tile + t;
-    const bool valid = (cell < chunk_end) && (pack[DP_VALID * stride + cell] != 0.0);
+    bool valid = (cell < chunk_end) && (pack[DP_VALID * stride + cell] != 0.0);
+    if (valid) {
+      // which branch this (cell, y) takes; independent of the eta node (the window test applies to 3+1d surfaces only)
+      bool linear = pack[FP_BREAKDOWN * stride + cell] != 0.0;
+      if (g.dimension == 3 && !linear) {                         // narrow (y - eta) window, MomentumSpectra.cpp:865-871
+        const double detA = pack[FP_DETA * stride + cell];
+        if (detA < 0.01 && fabs(yval - pack[DP_ETA * stride + cell]) < detA) linear = true;
+      }
+      valid = (linear == LINEAR);
+    }
     const unsigned ballot = __ballot_sync(0xffffffffu, valid);
     for (int ie = 0; ie < g.Neta; ie++) {
       __syncthreads();
@@ -163,20 +192,14 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
         double eta, w;
         if (g.dimension == 3) { eta = pk(DP_ETA); w = 1.0; }
         else { eta = g.etav[ie]; w = g.etaw[ie]; }
-        bool linear = pk(FP_BREAKDOWN) != 0.0;
-        if (g.dimension == 3 && !linear) {                       // narrow (y - eta) window, MomentumSpectra.cpp:865-871
-          double detA = pk(FP_DETA);
-          if (detA < 0.01 && fabs(yval - eta) < detA) linear = true;
-        }
         const int slot = base + __popc(ballot & ((1u << lane) - 1u));
-        if (linear) {
+        if (LINEAR) {
           double d = yval - eta;
           items[slot].lin = feqmod_make_linear_item(pk, sinh(d), cosh(d), cphi, sphi, w, g.w_on_dan);
         } else {
           double d = yval - pk(FP_ETA_SCALE) * eta;
           items[slot].mod = feqmod_make_item(pk, sinh(d), cosh(d), cphi, sphi, w, g.w_on_dan, BARYON, !SPECIES_RENORM);
         }
-        item_linear[slot] = linear ? 1 : 0;
         item_cell[slot] = (int)(cell - 0);   // index inside this pass's pack / renorm arrays
       }
       __syncthreads();
@@ -193,7 +216,7 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
             for (int r = 0; r < R; r++) rn[r] = row[r];
           }
         }
-        if (!item_linear[k]) {
+        if (!LINEAR) {
           const FeqmodItem &it = items[k].mod;        // shared memory: broadcast LDS.128 + one LDS.64 for eb[eslot]
           const FeqmodShared sh = feqmod_share(it, pT, pT2);
           const double eb = BARYON ? it.eb[eslot] : 1.0;
@@ -226,13 +249,16 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
 
 template <bool BARYON, bool SPECIES_RENORM>
 void launch_feqmod(bool reg, bool outflow, dim3 grid, cudaStream_t st, const double *pack, int64_t stride, int64_t n, int64_t cpc,
-                   const double *renorm, const FeqGrid &g, double *partial, int64_t total)
+                   const double *renorm, const int *tile_linear, const FeqGrid &g, double *partial, int64_t total)
 {
-#define IS3D_LAUNCH(REG, OUT) feqmod_spectra_kernel<BARYON, REG, OUT, SPECIES_RENORM, kBins><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, renorm, g, partial, total)
-  if (reg && outflow) IS3D_LAUNCH(true, true);
-  else if (reg) IS3D_LAUNCH(true, false);
-  else if (outflow) IS3D_LAUNCH(false, true);
-  else IS3D_LAUNCH(false, false);
+  // modified-distribution items (regulate_deltaf does not reach them), then the linear-df fallback items
+#define IS3D_LAUNCH(LIN, REG, OUT) feqmod_spectra_kernel<LIN, BARYON, REG, OUT, SPECIES_RENORM, kBins><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, renorm, tile_linear, g, partial, total)
+  if (outflow) IS3D_LAUNCH(false, false, true);
+  else IS3D_LAUNCH(false, false, false);
+  if (reg && outflow) IS3D_LAUNCH(true, true, true);
+  else if (reg) IS3D_LAUNCH(true, true, false);
+  else if (outflow) IS3D_LAUNCH(true, false, true);
+  else IS3D_LAUNCH(true, false, false);
 #undef IS3D_LAUNCH
 }
 
@@ -291,7 +317,9 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   int nchunks; int64_t cpc;
   choose_chunks(ctx, stride, blocks_per_chunk, total_class, kTile, &nchunks, &cpc);
 
-  void *pack = nullptr, *partial = nullptr, *counters = nullptr, *renorm = nullptr;
+  void *pack = nullptr, *partial = nullptr, *counters = nullptr, *renorm = nullptr, *tile_linear = nullptr;
+  const size_t ntile_flags = (size_t)((stride + kTile - 1) / kTile);
+  IS3D_TRY(ctx->get_scratch("tile_linear", ntile_flags * sizeof(int), &tile_linear));
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)FP_SIZE * stride * sizeof(double), &pack));
   IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total_class * sizeof(double), &partial));
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
@@ -324,18 +352,22 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
       IS3D_CUDA_TRY(ctx, cudaGetLastError());
       launches++;
     }
+    IS3D_CUDA_TRY(ctx, cudaMemsetAsync(tile_linear, 0, ntile_flags * sizeof(int), ctx->stream));
+    feqmod_tile_flags_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>((double *)pack, stride, count, p.dimension, (int *)tile_linear);
+    IS3D_CUDA_TRY(ctx, cudaGetLastError());
+    launches++;
     int nch = (int)((count + cpc - 1) / cpc);
     dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch);
     const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0;
     if (p.include_baryon) {
-      if (species_renorm) launch_feqmod<true, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total_class);
-      else launch_feqmod<true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total_class);
+      if (species_renorm) launch_feqmod<true, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
+      else launch_feqmod<true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
     } else {
-      if (species_renorm) launch_feqmod<false, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total_class);
-      else launch_feqmod<false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, g, (double *)partial, total_class);
+      if (species_renorm) launch_feqmod<false, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
+      else launch_feqmod<false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
     }
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
-    launches++;
+    launches += 2;
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
     IS3D_CUDA_TRY(ctx, cudaEventSynchronize(e1));
     float ms = 0.f;
