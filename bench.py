@@ -486,7 +486,7 @@ def main():
     ap.add_argument("--cells-per-gpu", type=int, default=1_250_000)
     ap.add_argument("--df-mode", type=int, default=2, choices=[1, 2, 3, 4, 5],
                     help="2 = the headline workload; 1, 3, 4, 5 time the other df corrections on the same surface")
-    ap.add_argument("--ref-cells", type=int, default=2000, help="cells of the bounded CPU sample")
+    ap.add_argument("--ref-cells", type=int, default=5000, help="cells of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampler", action="store_true", help="skip the sampler (hadrons/s) section")
     ap.add_argument("--sampler-cells", type=int, default=100_000)

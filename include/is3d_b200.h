@@ -221,6 +221,15 @@ is3d_status is3d_measure_fp64_peak(is3d_ctx *ctx, double *tflops);
  * The parity tests bound their error against libm. */
 is3d_status is3d_probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp,
                             double *out_sqrt);
+/* Host-only helper (no context, no GPU): the species classes and thread groups the spectra and dN/dX kernels use.
+ * Hadrons with the same (mass, quantum-statistics sign[, baryon number when include_baryon]) form one class (their
+ * Cooper-Frye integrands differ only by the degeneracy, which the reference multiplies in front:
+ * MomentumSpectra.cpp:399-401); the classes are laid out in groups of slots_per_group slots with ONE baryon number per
+ * group (padding slots = -1).  class_of[ns] receives the class of every species, slot_class[capacity] the class of
+ * every slot, *nclass the number of classes.  Returns the number of slots written, -1 for bad arguments, -2 if capacity
+ * is too small, -3 for a baryon number outside -2 .. 2 (the reference's PDG readers produce hadrons and the deuteron). */
+int         is3d_species_groups(int ns, const double *mass, const double *sign, const double *baryon, int include_baryon,
+                                int slots_per_group, int *class_of, int *slot_class, int capacity, int *nclass);
 /* the CUDA stream all kernels of this context are launched on (as a void* cudaStream_t) */
 void       *is3d_stream(is3d_ctx *ctx);
 

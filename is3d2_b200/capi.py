@@ -61,7 +61,7 @@ ABI_SYMBOLS = ["is3d_default_params", "is3d_create", "is3d_destroy", "is3d_last_
                "is3d_set_surface_device", "is3d_spectra_size", "is3d_spectra", "is3d_spectra_device", "is3d_dndx",
                "is3d_dndx_device", "is3d_total_yield", "is3d_cell_yields", "is3d_sample", "is3d_free_particles",
                "is3d_sample_histograms", "is3d_set_vorticity", "is3d_polarization", "is3d_measure_fp64_peak", "is3d_probe_math",
-               "is3d_stream"]
+               "is3d_species_groups", "is3d_stream"]
 HOST_SYMBOLS = ["is3d_host_open", "is3d_host_close", "is3d_host_read_surface", "is3d_host_set_surface",
                 "is3d_host_prepare", "is3d_host_prepare_tables", "is3d_host_context", "is3d_host_run",
                 "is3d_host_spectra", "is3d_host_dndx", "is3d_host_events", "is3d_host_event_particles",

@@ -186,36 +186,38 @@ void dispatch_df2(bool reg, bool outflow, dim3 grid, cudaStream_t st, const doub
 
 // class_of[s] = class of species s, rep[c] = first species of class c (classes numbered in order of first appearance).
 // The baryon number separates classes only when baryon terms are switched on.
-void species_classes(const is3d_ctx *ctx, std::vector<int> *class_of, std::vector<int> *rep)
+void species_classes_core(int ns, const double *mass, const double *sign, const double *baryon, bool baryon_on,
+                          std::vector<int> *class_of, std::vector<int> *rep)
 {
-  const int ns = ctx->ns;
-  const bool baryon_on = ctx->prm.include_baryon != 0;
   class_of->assign(ns, 0);
   rep->clear();
   for (int s = 0; s < ns; s++) {
     int c = -1;
-    const double bs = baryon_on ? ctx->h_baryon[s] : 0.0;
+    const double bs = baryon_on ? baryon[s] : 0.0;
     for (size_t k = 0; k < rep->size() && c < 0; k++) {
       const int r = (*rep)[k];
-      const double br = baryon_on ? ctx->h_baryon[r] : 0.0;
-      if (ctx->h_mass[r] == ctx->h_mass[s] && ctx->h_sign[r] == ctx->h_sign[s] && br == bs) c = (int)k;
+      const double br = baryon_on ? baryon[r] : 0.0;
+      if (mass[r] == mass[s] && sign[r] == sign[s] && br == bs) c = (int)k;
     }
     if (c < 0) { c = (int)rep->size(); rep->push_back(s); }
     (*class_of)[s] = c;
   }
 }
 
-// K1 thread groups: R class slots per group, the valid slots of a group carrying ONE baryon number (the kernel folds
-// b into per-(item, thread) coefficients, spectra_df.cuh).  Classes are taken per baryon number in order of first
-// appearance and each run is padded to a multiple of R with -1; without baryon terms all classes form one run.
-bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots)
+void species_classes(const is3d_ctx *ctx, std::vector<int> *class_of, std::vector<int> *rep)
 {
-  std::vector<int> class_of, rep;
-  species_classes(ctx, &class_of, &rep);
-  const bool baryon_on = ctx->prm.include_baryon != 0;
+  species_classes_core(ctx->ns, ctx->h_mass.data(), ctx->h_sign.data(), ctx->h_baryon.data(), ctx->prm.include_baryon != 0, class_of, rep);
+}
+
+// Thread groups of the spectra / dN/dX kernels: R class slots per group, the valid slots of a group carrying ONE baryon
+// number (the kernels fold b into per-(item, thread) coefficients, spectra_df.cuh).  Classes are taken per baryon number in
+// order of first appearance and each run is padded to a multiple of R with -1; without baryon terms all classes form one
+// run.  false: a baryon number outside -kMaxBaryon .. kMaxBaryon (or not an integer).
+bool slot_table_core(const std::vector<int> &rep, const double *baryon, bool baryon_on, int R, std::vector<int> *slots)
+{
   std::vector<double> bvals;
   for (int r : rep) {
-    const double b = baryon_on ? ctx->h_baryon[r] : 0.0;
+    const double b = baryon_on ? baryon[r] : 0.0;
     bool seen = false;
     for (double v : bvals) seen = seen || (v == b);
     if (!seen) bvals.push_back(b);
@@ -224,10 +226,17 @@ bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots)
   for (double b : bvals) {
     if (fabs(b) > (double)kMaxBaryon || b != (double)(int)b) return false;
     for (size_t c = 0; c < rep.size(); c++)
-      if ((baryon_on ? ctx->h_baryon[rep[c]] : 0.0) == b) slots->push_back((int)c);
+      if ((baryon_on ? baryon[rep[c]] : 0.0) == b) slots->push_back((int)c);
     while (slots->size() % (size_t)R) slots->push_back(-1);
   }
   return true;
+}
+
+bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots)
+{
+  std::vector<int> class_of, rep;
+  species_classes(ctx, &class_of, &rep);
+  return slot_table_core(rep, ctx->h_baryon.data(), ctx->prm.include_baryon != 0, R, slots);
 }
 
 // Builds the species classes and their per-(class, pT) bin arrays shared by all spectra kernels (device pointers in `out`).
@@ -389,3 +398,17 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
 }
 
 }  // namespace is3d
+
+extern "C" int is3d_species_groups(int ns, const double *mass, const double *sign, const double *baryon, int include_baryon,
+                                   int slots_per_group, int *class_of, int *slot_class, int capacity, int *nclass)
+{
+  if (ns <= 0 || !mass || !sign || !baryon || slots_per_group <= 0 || !class_of || !slot_class || !nclass) return -1;
+  std::vector<int> cls, rep, slots;
+  is3d::species_classes_core(ns, mass, sign, baryon, include_baryon != 0, &cls, &rep);
+  if (!is3d::slot_table_core(rep, baryon, include_baryon != 0, slots_per_group, &slots)) return -3;
+  if ((int)slots.size() > capacity) return -2;
+  for (int s = 0; s < ns; s++) class_of[s] = cls[s];
+  for (size_t k = 0; k < slots.size(); k++) slot_class[k] = slots[k];
+  *nclass = (int)rep.size();
+  return (int)slots.size();
+}

@@ -53,3 +53,68 @@ def test_create_fails_loudly_without_gpu(libs):
     st = lib.is3d_create(C.byref(p), C.byref(ctx))
     assert st != 0 and not ctx.value
     assert b"no CPU path" in lib.is3d_last_error(None) or b"sm_" in lib.is3d_last_error(None)
+
+
+def _smash_species():
+    """(mass, sign, baryon) of the 444 chosen SMASH species through the host layer's PDG reader (no GPU involved)."""
+    import numpy as np
+    toks = open(os.path.join(REPO, "data", "PDG", "pdg_smash.dat")).read().split()
+    pdg, k = {}, 0
+    while k < len(toks):
+        mcid, mass, b, nd = int(toks[k]), float(toks[k + 2]), int(toks[k + 5]), int(toks[k + 11])
+        k += 12 + 8 * nd
+        pdg[mcid] = (mass, b)
+        if b > 0:
+            pdg[-mcid] = (mass, -b)
+    chosen = [int(l.split()[0]) for l in open(os.path.join(REPO, "data", "PDG", "chosen_particles_smash.dat")) if l.strip()]
+    mass = np.array([pdg[c][0] for c in chosen])
+    baryon = np.array([float(pdg[c][1]) for c in chosen])
+    sign = np.where(baryon.astype(int) % 2 == 0, -1.0, 1.0)
+    return mass, sign, baryon
+
+
+@pytest.mark.parametrize("include_baryon,R", [(1, 4), (1, 3), (0, 4), (1, 7)])
+def test_species_groups_have_one_baryon_number(libs, include_baryon, R):
+    """Host logic behind the kernels' thread groups (is3d_species_groups): every species lands in exactly one class with
+    its (mass, sign[, baryon number]); every class sits in exactly one slot; the valid slots of a group share ONE baryon
+    number; padding only at the end of a baryon-number run."""
+    import numpy as np
+    lib, _ = libs
+    mass, sign, baryon = _smash_species()
+    ns = len(mass)
+    assert ns == 444
+    class_of = np.zeros(ns, dtype=np.int32)
+    slots = np.full(4 * ns, -7, dtype=np.int32)
+    nclass = C.c_int()
+    lib.is3d_species_groups.restype = C.c_int
+    n = lib.is3d_species_groups(ns, mass.ctypes.data_as(C.c_void_p), sign.ctypes.data_as(C.c_void_p), baryon.ctypes.data_as(C.c_void_p),
+                                include_baryon, R, class_of.ctypes.data_as(C.c_void_p), slots.ctypes.data_as(C.c_void_p), len(slots),
+                                C.byref(nclass))
+    assert n > 0 and n % R == 0
+    nc = nclass.value
+    assert nc == (193 if include_baryon else len({(m, s) for m, s in zip(mass, sign)}))
+    # classes: same key <=> same class
+    key = {}
+    for s in range(ns):
+        k = (mass[s], sign[s], baryon[s] if include_baryon else 0.0)
+        assert key.setdefault(k, class_of[s]) == class_of[s]
+    assert len(key) == nc and sorted(set(class_of)) == list(range(nc))
+    # slots: a permutation of the classes plus padding
+    sl = slots[:n]
+    assert sorted(c for c in sl if c >= 0) == list(range(nc))
+    cls_b = {class_of[s]: (baryon[s] if include_baryon else 0.0) for s in range(ns)}
+    for g in range(n // R):
+        grp = sl[g * R:(g + 1) * R]
+        assert grp[0] >= 0
+        assert len({cls_b[c] for c in grp if c >= 0}) == 1
+        pad = [i for i, c in enumerate(grp) if c < 0]
+        assert pad == list(range(R - len(pad), R))
+    if include_baryon and R == 4:
+        assert n // R == 50        # 19 meson + 15 baryon + 15 antibaryon groups + the deuteron (DESIGN.md, K1)
+    # error paths: capacity, baryon number out of range
+    assert lib.is3d_species_groups(ns, mass.ctypes.data_as(C.c_void_p), sign.ctypes.data_as(C.c_void_p), baryon.ctypes.data_as(C.c_void_p),
+                                   include_baryon, R, class_of.ctypes.data_as(C.c_void_p), slots.ctypes.data_as(C.c_void_p), 3, C.byref(nclass)) == -2
+    bad = baryon.copy(); bad[5] = 3.0
+    rc = lib.is3d_species_groups(ns, mass.ctypes.data_as(C.c_void_p), sign.ctypes.data_as(C.c_void_p), bad.ctypes.data_as(C.c_void_p),
+                                 1, R, class_of.ctypes.data_as(C.c_void_p), slots.ctypes.data_as(C.c_void_p), len(slots), C.byref(nclass))
+    assert rc == -3
