@@ -45,20 +45,20 @@ struct AnisoHadrons {
                                            // (parity mode, see aniso_t_functions); 0: FP64-pipe approximations
 };
 
-// sqrt(a) and 1/sqrt(a) for a > 0 from one hardware seed + one coupled Goldschmidt step + residual fix (see fast_sqrt)
+// sqrt(a) and 1/sqrt(a) for a > 0 from one hardware seed y and ONE third-order step (see fast_sqrt): with g = a y and
+// e = 1 - g y, (1 - e)^(-1/2) = 1 + p + O(5/16 e^3), p = e (1/2 + 3/8 e); sqrt(a) = g (1 + p), 1/sqrt(a) = y (1 + p).
+// 6 FP64 instructions (the coupled Goldschmidt step + residual fix + second half-step it replaces took 10).
 IS3D_HD void fast_sqrt_rsqrt(double a, double *root, double *iroot)
 {
 #if defined(__CUDA_ARCH__)
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double g = a * y, h = 0.5 * y;
-  double r = fma(-h, g, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  double d = fma(-g, g, a);
-  g = fma(d, h, g);                        // sqrt(a)
-  r = fma(-h, g, 0.5);
-  h = fma(h, r, h);
-  *root = g; *iroot = 2.0 * h;
+  const double g = a * y;
+  const double e = fma(-g, y, 1.0);
+  double p = fma(e, 0.375, 0.5);
+  p = p * e;
+  *root = fma(g, p, g);
+  *iroot = fma(y, p, y);
 #else
   *root = sqrt(a); *iroot = 1.0 / *root;
 #endif
