@@ -11,6 +11,8 @@ namespace is3d {
 
 is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out);
 bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots);
+void pick_chunks(int64_t ncells, int64_t blocks_per_chunk, int64_t resident, int64_t granule, int64_t max_chunks,
+                 int *nchunks, int64_t *cells_per_chunk);
 
 namespace {
 
@@ -423,8 +425,7 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
 
   const int nslices = (g.ngroups + g.gpb - 1) / g.gpb;
-  // ~8 waves of blocks, two 256-thread blocks resident per SM
-  int64_t want_blocks = 8LL * 2 * ctx->sm_count;
+  const int64_t resident = 2LL * ctx->sm_count;      // two 256-thread blocks per SM (launch bounds)
   cudaEvent_t e0, e1;
   IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
   IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));
@@ -433,11 +434,15 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0, baryon = p.include_baryon != 0;
   for (int64_t begin = 0; begin < n; begin += macro) {
     int64_t count = n - begin < macro ? n - begin : macro;
-    int64_t nchunks = (want_blocks + nslices - 1) / nslices;
-    if (nchunks > count) nchunks = count;
-    if (nchunks > 65535) nchunks = 65535;
-    int64_t cpb = (count + nchunks - 1) / nchunks;
-    nchunks = (count + cpb - 1) / cpb;
+    // whole waves of equal blocks (spectra_df.cu pick_chunks); a chunk = whole cells, in multiples of the cells of one tile
+    int nchunks = 1;
+    int64_t cpb = count;
+    {
+      const int npoints = g.Ny * g.Neta * g.Nphi;
+      int64_t cpt = npoints >= kDndxTile ? 1 : kDndxTile / npoints;
+      if (cpt > kDndxMaxCells) cpt = kDndxMaxCells;
+      pick_chunks(count, nslices, resident, cpt, 65535, &nchunks, &cpb);
+    }
     dim3 grid(nslices, (unsigned)nchunks);
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     if (!feqmod) {

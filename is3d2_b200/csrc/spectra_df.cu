@@ -277,25 +277,42 @@ is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out)
   return IS3D_OK;
 }
 
-// chunking policy shared by the spectra kernels: enough blocks for ~16 waves, partial sums <= 1 GiB
+// Chunking policy shared by the spectra kernels.  All blocks of a launch do the same amount of work, so the grid runs in
+// waves of `resident` blocks and a partly filled last wave costs a whole block time (the first policy, "about 16 waves",
+// gave 4830 blocks = 16.3 waves for the headline launch: 17 block times for 16.3 of work).  Among the chunk counts that give
+// 32 .. 64 waves the one with the best wave efficiency blocks / (resident ceil(blocks / resident)) is taken (ties: fewer
+// chunks); partial sums stay <= 1 GiB and chunks start on tile boundaries.
+void pick_chunks(int64_t ncells, int64_t blocks_per_chunk, int64_t resident, int64_t granule, int64_t max_chunks,
+                 int *nchunks, int64_t *cells_per_chunk)
+{
+  if (max_chunks < 1) max_chunks = 1;
+  const int64_t by_cells = (ncells + granule - 1) / granule;
+  if (max_chunks > by_cells) max_chunks = by_cells < 1 ? 1 : by_cells;
+  int64_t lo = (32 * resident + blocks_per_chunk - 1) / blocks_per_chunk, hi = (64 * resident + blocks_per_chunk - 1) / blocks_per_chunk;
+  if (lo < 1) lo = 1;
+  if (lo > max_chunks) lo = max_chunks;
+  if (hi > max_chunks) hi = max_chunks;
+  double best_eff = -1.0;
+  int64_t best_nc = lo, best_cpc = ncells;
+  for (int64_t nc = lo; nc <= hi; nc++) {
+    int64_t cpc = (ncells + nc - 1) / nc;
+    cpc = (cpc + granule - 1) / granule * granule;
+    const int64_t nca = (ncells + cpc - 1) / cpc;
+    const int64_t blocks = nca * blocks_per_chunk, waves = (blocks + resident - 1) / resident;
+    const double eff = (double)blocks / (double)(waves * resident);
+    if (eff > best_eff + 1e-12) { best_eff = eff; best_nc = nca; best_cpc = cpc; }
+  }
+  *nchunks = (int)best_nc;
+  *cells_per_chunk = best_cpc;
+}
+
 void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
                    int64_t *cells_per_chunk)
 {
-  int64_t resident = IS3D_K1_MINBLOCKS * (int64_t)ctx->sm_count;
-  int64_t want = (16 * resident + blocks_per_chunk - 1) / blocks_per_chunk;
-  int64_t max_by_cells = (ncells + tile - 1) / tile;
+  const int64_t resident = IS3D_K1_MINBLOCKS * (int64_t)ctx->sm_count;
   int64_t max_by_mem = ((int64_t)1 << 30) / (total * 8);
-  if (max_by_mem < 1) max_by_mem = 1;
-  int64_t nc = want;
-  if (nc > max_by_cells) nc = max_by_cells;
-  if (nc > max_by_mem) nc = max_by_mem;
-  if (nc > 65535) nc = 65535;
-  if (nc < 1) nc = 1;
-  int64_t cpc = (ncells + nc - 1) / nc;
-  cpc = (cpc + tile - 1) / tile * tile;
-  nc = (ncells + cpc - 1) / cpc;
-  *nchunks = (int)nc;
-  *cells_per_chunk = cpc;
+  if (max_by_mem > 65535) max_by_mem = 65535;
+  pick_chunks(ncells, blocks_per_chunk, resident, tile, max_by_mem, nchunks, cells_per_chunk);
 }
 
 is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
