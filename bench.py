@@ -436,13 +436,15 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
         bytes_alg = cells * 25 * 8.0 + total * 8.0
         # DRAM bytes and FP64-pipe utilisation of ONE df_spectra_kernel launch from the committed `ncu --set full` capture of
         # this command at the default size (profiles/r01_ncu_k1_headline.json); null for any other configuration
-        traffic = traffic_src = fp64_pct = None
+        traffic = traffic_src = fp64_pct = executed = None
         try:
             cap = json.load(open(os.path.join(REPO, "profiles", "r01_ncu_k1_headline.json")))
             if cap["config"] == {"df_mode": args.df_mode, "cells_per_gpu": cells}:
                 traffic = float(cap["dram_bytes_read"] + cap["dram_bytes_write"])
                 traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_k1_headline.json"
                 fp64_pct = cap["fp64_pipe_active_pct"]
+                # executed work: FP64-pipe instructions of the SASS inner loop x 2 flops, per class slot actually evaluated
+                executed = (evals_rank * cap["class_slots"] / cap["species"]) * cap["fp64_instr_per_class_eval_sass"] * 2.0 / kern_s / 1e12
         except (OSError, KeyError, ValueError):
             pass
         line = {
@@ -462,6 +464,7 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
                          "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "df_spectra_kernel" if args.df_mode <= 2 else "feqmod_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
                          "fp64_pipe_active_pct_ncu": fp64_pct,
+                         "executed_tflops": executed, "frac_executed": (executed / fp64_peak) if executed else None,
                          "flops_per_eval_algorithmic": F_ALG[args.df_mode],
                          "peak_source": "DFMA micro-benchmark run live by is3d_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
                          "hbm_gbs_algorithmic": bytes_alg / kern_s / 1e9, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},

@@ -231,7 +231,7 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
   th.load(g, BARYON);
   DfBin bin[R];                                         // linear-df fallback of breakdown cells
 #pragma unroll
-  for (int r = 0; r < R; r++) { bin[r].mT = th.mT[r]; bin[r].mT2 = th.mT2[r]; bin[r].m2 = 0.0; bin[r].baryon = th.b; bin[r].sign = th.sgn[r]; }
+  for (int r = 0; r < R; r++) { bin[r].mT = th.mT[r]; bin[r].mT2 = th.mT2[r]; bin[r].baryon = th.b; bin[r].sign = th.sgn[r]; }
   double acc[R];
 #pragma unroll
   for (int r = 0; r < R; r++) acc[r] = 0.0;

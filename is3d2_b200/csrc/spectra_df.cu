@@ -51,7 +51,7 @@ __global__ void df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, 
 }
 
 struct DfGrid {
-  const double *mT, *pT, *m2, *baryon, *sign;         // per (species class, pT) bin, [ns * NpT]
+  const double *mT, *pT, *baryon, *sign;              // per (species class, pT) bin, [ns * NpT]
   int ns, NpT, ncols;                                 // ns = number of species CLASSES; ncols = NpT * ngroups thread columns
   const int *slot_class;                              // [ngroups * R]: class of slot r of a thread group, -1 = padding; the
                                                       // valid slots of a group carry ONE baryon number (build_slot_table)
@@ -328,7 +328,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   DfGrid g;
   SpeciesBins sb;
   IS3D_TRY(build_bin_arrays(ctx, &sb));
-  g.mT = sb.mT; g.pT = sb.pT; g.m2 = sb.m2; g.baryon = sb.baryon; g.sign = sb.sign;
+  g.mT = sb.mT; g.pT = sb.pT; g.baryon = sb.baryon; g.sign = sb.sign;
   std::vector<int> slots;
   if (!build_slot_table(ctx, kDfBinsPerThread, &slots)) {
     ctx->set_error("species list holds a baryon number outside -2..2 (the reference's PDG readers produce hadrons and the deuteron only)");

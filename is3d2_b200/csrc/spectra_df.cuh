@@ -134,7 +134,7 @@ IS3D_HD DfItem df_make_item(PackFn pk, int mode, double sh, double ch, double cp
 // per-bin registers.  The spectra kernels give one thread R species at ONE pT node, so everything that multiplies
 // pT alone (DfShared) is formed once per item and shared by the thread's R evaluations.
 struct DfBin {
-  double mT, mT2, m2, baryon, sign;     // m2 is read by the modified-equilibrium path only
+  double mT, mT2, baryon, sign;
 };
 
 struct DfShared {

@@ -82,7 +82,7 @@ feqmod_renorm_kernel(const double *__restrict__ pack, int64_t stride, int64_t co
 }
 
 struct FeqGrid {
-  const double *mT, *pT, *m2, *baryon, *sign;
+  const double *mT, *pT, *baryon, *sign;
   int ncols, NpT, ns, nslots;           // ns = number of species CLASSES; ncols = NpT * ngroups thread columns; nslots = ngroups * kBins
   const int *slot_class;                // [ngroups * kBins]: class of slot r of a thread group (-1 = padding), one baryon
                                         // number per group (build_slot_table, spectra_df.cu)
@@ -148,7 +148,7 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
     const int jj = sp[r] * g.NpT + ip;
     jbin[r] = (col < g.ncols && cls >= 0) ? jj : -1;
     const double mT = g.mT[jj];
-    bin[r].mT = mT; bin[r].mT2 = mT * mT; bin[r].m2 = 0.0; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
+    bin[r].mT = mT; bin[r].mT2 = mT * mT; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
     asm volatile("" : "+d"(bin[r].mT2));      // opaque: ptxas otherwise re-multiplies mT^2 (and pT^2) per item to save registers
     acc[r] = 0.0;
   }
@@ -285,7 +285,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   FeqGrid g;
   SpeciesBins sb;
   IS3D_TRY(build_bin_arrays(ctx, &sb));
-  g.mT = sb.mT; g.pT = sb.pT; g.m2 = sb.m2; g.baryon = sb.baryon; g.sign = sb.sign;
+  g.mT = sb.mT; g.pT = sb.pT; g.baryon = sb.baryon; g.sign = sb.sign;
   std::vector<int> slots;
   if (!build_slot_table(ctx, kBins, &slots)) {
     ctx->set_error("species list holds a baryon number outside -2..2 (the reference's PDG readers produce hadrons and the deuteron only)");
