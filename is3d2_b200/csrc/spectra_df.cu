@@ -285,6 +285,7 @@ is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out)
 void pick_chunks(int64_t ncells, int64_t blocks_per_chunk, int64_t resident, int64_t granule, int64_t max_chunks,
                  int *nchunks, int64_t *cells_per_chunk)
 {
+  if (ncells <= 0) { *nchunks = 1; *cells_per_chunk = granule; return; }
   if (max_chunks < 1) max_chunks = 1;
   const int64_t by_cells = (ncells + granule - 1) / granule;
   if (max_chunks > by_cells) max_chunks = by_cells < 1 ? 1 : by_cells;
