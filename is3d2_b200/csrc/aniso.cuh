@@ -92,19 +92,13 @@ struct AnisoT { double t200, t220, t201, t402, t421, t440; };
 // The closed forms cancel catastrophically towards z -> delta (t402, t421, t440 lose a factor ~3/z^2 = 3e4 at z = 0.01),
 // so the reference's result carries the rounding of ITS atan to the 1e-11 level; bit-level agreement with it needs the same
 // libm call and the same division order (exact = true, used by the chain-faithful parity mode).
-// s_in / is_in: sqrt(z) and 1 / sqrt(z) when the caller already has them (fast path: z = (aT^2 - aL^2) / w^2 with w and
-// 1 / w at hand, so sqrt(z) = sqrt(aT^2 - aL^2) / w costs two multiplies with the per-sum constant); 0 = derive them here
-IS3D_HD AnisoT aniso_t_functions(double z, bool need_j, bool exact, double s_in = 0.0, double is_in = 0.0)
+IS3D_HD AnisoT aniso_t_functions(double z, bool need_j, bool exact)
 {
   AnisoT r;
   r.t200 = r.t220 = r.t201 = r.t402 = r.t421 = r.t440 = 0.0;     // reference leaves them unset when z <= -1
   if (z > kAnisoDelta || (z < -kAnisoDelta && z > -1.)) {
     double t, iz;
-    if (z > 0.0 && !exact) {
-      double s = s_in, is = is_in;
-      if (!(s_in > 0.0)) fast_sqrt_rsqrt(z, &s, &is);
-      t = fast_atan(s) * is; iz = is * is;
-    }
+    if (z > 0.0 && !exact) { double s, is; fast_sqrt_rsqrt(z, &s, &is); t = fast_atan(s) * is; iz = is * is; }
     else if (z > 0.0) { double s = sqrt(z); t = atan(s) / s; iz = 1.0 / z; }
     else { double s = sqrt(-z); t = atanh(s) / s; iz = 1.0 / z; }
     if (exact) {             // AnisoVariables.cpp:72-89, :206-231 verbatim (divisions, not reciprocal multiplies)
@@ -157,20 +151,9 @@ IS3D_HD AnisoNode aniso_node_J(const AnisoHadrons &h, int i)
   return AnisoNode{pbar, pbar * pbar, 1.0 / (pbar * pbar), weight * exp(pbar), weight};
 }
 
-// sqrt(aT^2 - aL^2) and its reciprocal for aT > aL, zeros otherwise (then the t functions take their own square roots)
-struct AnisoSqrtDz { double s, is; };
-IS3D_HD AnisoSqrtDz aniso_sqrt_dz(double aT2, double aL2)
-{
-  const double dz = aT2 - aL2;
-  if (!(dz > 0.0)) return AnisoSqrtDz{0.0, 0.0};
-  const double r = sqrt(dz);
-  return AnisoSqrtDz{r, 1.0 / r};
-}
-
 // one (hadron, node) term of compute_F (:36-107): out = {I_200, I_220, I_201} before the common factors
-// sdz / isdz = sqrt(aT^2 - aL^2) and its reciprocal when aT > aL (0 otherwise): constants of the whole sum (fast path only)
 IS3D_HD void aniso_F_term(const AnisoHadrons &h, int n, const AnisoNode &nd, double lambda, double ilambda, double aT2, double aL2,
-                          double sdz, double isdz, double out[3])
+                          double out[3])
 {
   const double mass = h.mass[n];
   if (mass == 0) return;                   // photons skipped
@@ -191,7 +174,7 @@ IS3D_HD void aniso_F_term(const AnisoHadrons &h, int n, const AnisoNode &nd, dou
   double w, iw;
   fast_sqrt_rsqrt(fma(mbar2, nd.ipbar2, aL2), &w, &iw);
   const double z = (aT2 - aL2) * (iw * iw);
-  const AnisoT t = aniso_t_functions(z, false, false, sdz * iw, w * isdz);
+  const AnisoT t = aniso_t_functions(z, false, false);
   const double cw = h.deg[n] * (nd.cF * fast_rcp(fast_exp(Ebar, h.exptab) + h.sign[n]));
   out[0] += cw * t.t200 * w;
   out[1] += cw * t.t220 * iw;
@@ -200,7 +183,7 @@ IS3D_HD void aniso_F_term(const AnisoHadrons &h, int n, const AnisoNode &nd, dou
 
 // one term of compute_J (:175-258) / compute_famod_coefficient (:573-627): out = {J_2001, J_2011, J_2201, J_402m1, J_421m1, J_440m1}
 IS3D_HD void aniso_J_term(const AnisoHadrons &h, int n, const AnisoNode &nd, double lambda, double ilambda, double aT2, double aL2,
-                          double sdz, double isdz, double out[6])
+                          double out[6])
 {
   const double mass = h.mass[n];
   if (mass == 0) return;
@@ -225,7 +208,7 @@ IS3D_HD void aniso_J_term(const AnisoHadrons &h, int n, const AnisoNode &nd, dou
   fast_sqrt_rsqrt(nd.pbar2 + mbar2, &Ebar, &iEbar);
   fast_sqrt_rsqrt(fma(mbar2, nd.ipbar2, aL2), &w, &iw);
   const double z = (aT2 - aL2) * (iw * iw);
-  const AnisoT t = aniso_t_functions(z, true, false, sdz * iw, w * isdz);
+  const AnisoT t = aniso_t_functions(z, true, false);
   const double e = fast_exp(Ebar, h.exptab), iq = fast_rcp(e + h.sign[n]);
   const double cw = h.deg[n] * (nd.cF * e * iq * iq);           // e^(pbar + Ebar) / (e^Ebar + sign)^2
   const double ecw = Ebar * cw, pcw = nd.pbar2 * iEbar * cw * iw;
@@ -243,17 +226,15 @@ struct SerialReducer {
   {
     for (int k = 0; k < 3; k++) out[k] = 0.0;
     const double il = 1.0 / lambda;
-    const AnisoSqrtDz sd = aniso_sqrt_dz(aT2, aL2);
     for (int n = 0; n < h.n; n++)
-      for (int i = 0; i < kAnisoPts; i++) aniso_F_term(h, n, aniso_node_F(h, i), lambda, il, aT2, aL2, sd.s, sd.is, out);
+      for (int i = 0; i < kAnisoPts; i++) aniso_F_term(h, n, aniso_node_F(h, i), lambda, il, aT2, aL2, out);
   }
   IS3D_HD void sum_J(const AnisoHadrons &h, double lambda, double aT2, double aL2, double out[6]) const
   {
     for (int k = 0; k < 6; k++) out[k] = 0.0;
     const double il = 1.0 / lambda;
-    const AnisoSqrtDz sd = aniso_sqrt_dz(aT2, aL2);
     for (int n = 0; n < h.n; n++)
-      for (int i = 0; i < kAnisoPts; i++) aniso_J_term(h, n, aniso_node_J(h, i), lambda, il, aT2, aL2, sd.s, sd.is, out);
+      for (int i = 0; i < kAnisoPts; i++) aniso_J_term(h, n, aniso_node_J(h, i), lambda, il, aT2, aL2, out);
   }
 };
 
@@ -275,10 +256,9 @@ static __device__ __noinline__ AnisoSum3 aniso_warp_sum_F(AnisoHadrons h, double
   const int lane = threadIdx.x & 31;
   const AnisoNode nd = aniso_node_F(h, lane & 15);
   const double il = 1.0 / lambda;
-  const AnisoSqrtDz sd = aniso_sqrt_dz(aT2, aL2);
   double o[3] = {0.0, 0.0, 0.0};
 #pragma unroll kAnisoUnroll
-  for (int n = lane >> 4; n < h.n; n += 2) aniso_F_term(h, n, nd, lambda, il, aT2, aL2, sd.s, sd.is, o);
+  for (int n = lane >> 4; n < h.n; n += 2) aniso_F_term(h, n, nd, lambda, il, aT2, aL2, o);
   AnisoSum3 r;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
@@ -293,10 +273,9 @@ static __device__ __noinline__ AnisoSum6 aniso_warp_sum_J(AnisoHadrons h, double
   const int lane = threadIdx.x & 31;
   const AnisoNode nd = aniso_node_J(h, lane & 15);
   const double il = 1.0 / lambda;
-  const AnisoSqrtDz sd = aniso_sqrt_dz(aT2, aL2);
   double o[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll kAnisoUnroll
-  for (int n = lane >> 4; n < h.n; n += 2) aniso_J_term(h, n, nd, lambda, il, aT2, aL2, sd.s, sd.is, o);
+  for (int n = lane >> 4; n < h.n; n += 2) aniso_J_term(h, n, nd, lambda, il, aT2, aL2, o);
   AnisoSum6 r;
 #pragma unroll
   for (int k = 0; k < 6; k++) {
