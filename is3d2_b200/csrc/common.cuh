@@ -109,6 +109,16 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
   q = q * r;                                         // r + r^2/2 + r^3/6
 #if defined(IS3D_PROBE_UNIFORM_EXP_TABLE)       // timing probe only (wrong results): every lane reads entry 0, no bank conflicts
   const double T = tab[k & 0];
+#elif defined(__CUDA_ARCH__) && !defined(IS3D_EXP_TABLE_GENERIC)
+  // the table lives in shared memory (load_exp_table): mask, then ONE multiply-add forms the 32-bit shared address
+  // (nvcc's own sequence for tab[k & 1023] is shift + mask + add)
+  double T;
+  {
+    const unsigned base = (unsigned)__cvta_generic_to_shared(tab);
+    unsigned addr;
+    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"((unsigned)k & (unsigned)(kExpTableSize - 1)), "r"(base));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(addr));
+  }
 #else
   const double T = tab[k & (kExpTableSize - 1)];
 #endif
