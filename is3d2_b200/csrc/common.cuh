@@ -123,7 +123,15 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
   const double T = tab[k & (kExpTableSize - 1)];
 #endif
   const double v = fma(T, q, T);
+#if defined(__CUDA_ARCH__)
+  // the shift is hidden from the optimiser: it would otherwise rewrite (k >> 10) << 20 as (k << 10) & 0xfff00000 and need
+  // shift + mask + add; an opaque shift + ONE multiply-add on the high word is an instruction shorter
+  int e;
+  asm("shr.s32 %0, %1, %2;" : "=r"(e) : "r"(k), "n"(kExpTableBits));
+  return scale_by_pow2(v, e);
+#else
   return scale_by_pow2(v, k >> kExpTableBits);
+#endif
 }
 
 // host-side construction of the table (uploaded once per context)

@@ -32,6 +32,10 @@ namespace {
 #ifndef IS3D_K1_R
 #define IS3D_K1_R 4
 #endif
+#ifndef IS3D_K1_ITEM_UNROLL
+#define IS3D_K1_ITEM_UNROLL 1
+#endif
+constexpr int kItemUnroll = IS3D_K1_ITEM_UNROLL;   // items per trip of the momentum loop
 constexpr int kThreads = IS3D_K1_THREADS;
 constexpr int kTile = kThreads;  // cells per shared-memory tile = threads per block
 constexpr int kDfBinsPerThread = IS3D_K1_R;   // species per thread (R)
@@ -89,12 +93,14 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
     jbin[r] = (col < g.ncols && cls >= 0) ? jj : -1;
     const double m = g.mT[jj];
     mT[r] = m; mT2[r] = m * m; sgn[r] = g.sign[jj];
+    if (MODE == 2) asm volatile("" : "+d"(mT2[r]));   // opaque: ptxas otherwise re-multiplies mT^2 per item when registers are tight
     acc[r] = 0.0;
   }
   DfThreadU th;
   th.pT = g.pT[ip]; th.pT2 = th.pT * th.pT;            // bin arrays are [class][pT]: entry ip = class 0
   th.b = BARYON ? g.baryon[cls0 * g.NpT + ip] : 0.0;
   th.bpT = th.b * th.pT;
+  if (MODE == 2) asm volatile("" : "+d"(th.pT2), "+d"(th.bpT));
   th.eslot = kMaxBaryon + (int)th.b;
 
   const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
@@ -126,7 +132,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         items[base + __popc(ballot & ((1u << lane) - 1u))] = df_make_item_u<MODE, BARYON>(pk, sh, ch, cphi, sphi, w);
       }
       __syncthreads();
-#pragma unroll 1
+#pragma unroll kItemUnroll
       for (int k = 0; k < n_items; k++) {
         const DfItemU &it = items[k];          // shared memory: fields arrive as broadcast LDS.128, eb[eslot] as one LDS.64
         const DfSharedU sh = df_share_u<MODE, BARYON>(it, th);

@@ -217,7 +217,7 @@ IS3D_HD double df_eval(const DfItem &it, const DfShared &s, const DfBin &b, cons
 //       M1 = K1 aT + G0 v1,  M2 = K1 bT + G0 v2                      (q1..q3 already hold the folded K0 m^2 term)
 //   df_mode 2 (:339-352): the terms over xE and the regular terms separate,
 //       (pi.p.p - K2 m^2 - G1 b V.p) / xE + K0 xE + K1 b + G0 V.p  =  [mT^2 q1 + mT A + B] / xE + (mT L1 + C)
-//       A = pT q2 - b G1 v1,  B = pT^2 q3 + b G1 pT v2,  L1 = K0 aT + G0 v1,  C = K1 b - pT (K0 bT + G0 v2)
+//       A = pT q2 - b (G1 v1),  B = pT^2 q3 + b pT (G1 v2),  L1 = K0 aT + G0 v1,  C = K1 b - pT (K0 bT + G0 v2)
 //   both: exp((u.p - b mu_B)/T) = exp(xE) exp(-b alpha_B); the second factor is an item constant selected by b, so the
 //       chemical-potential shift and the "+ sign" become one FMA.
 // FP64-pipe instructions per evaluation with baryon terms (R = 3): mode 1 28.7 -> 21, mode 2 31.7 -> 27.3.
@@ -227,8 +227,8 @@ constexpr int kMaxBaryon = 2;
 struct alignas(16) DfItemU {
   double aT, bT, c1, d1;
   double q1, q2, q3, L1;         // mode 1: Q1, Q2, Q3, M1;  mode 2 without baryon terms: L1 = K0
-  double L2, K1, G1, v1;         // mode 1: L2 = M2;  K1, G1, v1, v2: mode 2 with baryon terms only
-  double v2, eb[2 * kMaxBaryon + 1];
+  double L2, K1, Gv1, Gv2;       // mode 1: L2 = M2;  K1, Gv1 = G1 v1, Gv2 = G1 v2: mode 2 with baryon terms only
+  double eb[2 * kMaxBaryon + 1];
 };
 
 template <int MODE, bool BARYON, class PackFn>
@@ -266,7 +266,7 @@ IS3D_HD DfItemU df_make_item_u(PackFn pk, double sh, double ch, double cphi, dou
     it.L1 = BARYON ? K0 * aT + G0 * v1 : K0;
     it.L2 = K0 * bT + G0 * v2;
   }
-  it.K1 = K1; it.G1 = G1; it.v1 = v1; it.v2 = v2;
+  it.K1 = K1; it.Gv1 = G1 * v1; it.Gv2 = G1 * v2;
   return it;
 }
 
@@ -296,9 +296,8 @@ IS3D_HD DfSharedU df_share_u(const DfItemU &it, const DfThreadU &th)
     s.A = th.pT * it.q2;
     s.B = th.pT2 * it.q3;
     if (BARYON) {
-      const double G1b = it.G1 * th.b;
-      s.A = fma(-G1b, it.v1, s.A);
-      s.B = fma(G1b * th.pT, it.v2, s.B);
+      s.A = fma(-th.b, it.Gv1, s.A);
+      s.B = fma(th.bpT, it.Gv2, s.B);
       s.C = fma(it.K1, th.b, -th.pT * it.L2);
     }
   }
