@@ -220,7 +220,7 @@ IS3D_HD double df_eval(const DfItem &it, const DfShared &s, const DfBin &b, cons
 //       A = pT q2 - b (G1 v1),  B = pT^2 q3 + b pT (G1 v2),  L1 = K0 aT + G0 v1,  C = K1 b - pT (K0 bT + G0 v2)
 //   both: exp((u.p - b mu_B)/T) = exp(xE) exp(-b alpha_B); the second factor is an item constant selected by b, so the
 //       chemical-potential shift and the "+ sign" become one FMA.
-// FP64-pipe instructions per evaluation with baryon terms (R = 3): mode 1 28.7 -> 21, mode 2 31.7 -> 27.3.
+// FP64-pipe instructions per evaluation with baryon terms (SASS, R = 4): mode 1 28.7 -> 20.5, mode 2 31.7 -> 26.
 // eb[2 + b] = exp(-b alpha_B) for b = -2 .. 2: hadrons and the deuteron, the only nucleus the reference's PDG readers
 // produce (readindata.cpp:1098-1214); a thread reads the slot of its group's baryon number with one LDS.64.
 constexpr int kMaxBaryon = 2;
