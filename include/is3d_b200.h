@@ -78,13 +78,15 @@ typedef struct {
   double r_min, r_max;     int r_bins;
   /* device selection and library-only knobs (no reference counterpart) */
   int device;                    /* CUDA ordinal */
-  int famod_chain;               /* df_mode 5 initial guess policy: 1 = reference-faithful serial chain (previous
-                                    cell's solution, MomentumSpectra.cpp:1308-1364), 0 = chain-free (T,1,1) */
+  int famod_chain;               /* df_mode 5 initial guess policy: 0 (default) = every cell starts from (T,1,1), what the
+                                    reference does for a cell without a previous solution (MomentumSpectra.cpp:1288-1313):
+                                    cells independent, shardable; 1 = the reference's serial chain (previous cell's solution,
+                                    :1308-1364) walked by ONE warp -- bit-level parity runs on one GPU only */
   int dndx_bug_compat;           /* 1 = reproduce the reference's partial memset (SpacetimeDistribution.cpp:166-168):
                                     histograms accumulate over species above bin CORES*bins/8 */
-  int polzn_chunk_compat;        /* 1 = spin polarization reads the thermal vorticity with the index INSIDE the reference's
-                                    10 000-cell chunk (Polarization.cpp:125-130 use wtx_fo[icell], not [icell_glb]); identical
-                                    to 0 for surfaces of up to 10 000 cells */
+  int polzn_chunk_compat;        /* 0 (default) = every cell reads its own thermal vorticity; 1 = the reference's index INSIDE
+                                    its 10 000-cell chunk (Polarization.cpp:125-130 use wtx_fo[icell], not [icell_glb]):
+                                    identical for surfaces of up to 10 000 cells, unsharded surfaces only */
 } is3d_params;
 
 /* Counters the reference prints (MomentumSpectra.cpp:1039-1040, :1674-1679; ParticleSampler.cpp:1133). */

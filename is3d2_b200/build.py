@@ -32,13 +32,16 @@ def _run(cmd: list[str]) -> None:
     subprocess.check_call(cmd)
 
 
-def build(force: bool = False, verbose_ptxas: bool = False) -> None:
+def build(force: bool = False, verbose_ptxas: bool = False, variant_flags: list[str] | None = None) -> None:
+    """variant_flags: extra -D defines for the launch-shape sweeps under tools/ (tools/build_variant.py); the product build
+    takes none and reads no flags from the environment."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     lib = os.path.join(HERE, "libis3d_b200.so")
     cu = [os.path.join(CSRC, f) for f in CU_SOURCES]
     deps = cu + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
         [os.path.join(HERE, "..", "include", "is3d_b200.h")]
-    if force or _newer(lib, deps):
+    if force or variant_flags or _newer(lib, deps):
+        force = force or bool(variant_flags)
         objs = []
         os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
         procs = []
@@ -47,7 +50,7 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> None:
             objs.append(obj)
             if force or _newer(obj, deps):
                 cmd = [nvcc] + [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + \
-                      os.environ.get("IS3D_NVCC_EXTRA", "").split() + \
+                      list(variant_flags or []) + \
                       (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-c", src, "-o", obj]
                 print(" ".join(cmd), flush=True)
                 procs.append(subprocess.Popen(cmd))

@@ -23,7 +23,7 @@ void is3d_default_params(is3d_params *p)
   p->pT_min = 0.0; p->pT_max = 3.0; p->pT_bins = 100; p->y_bins = 100; p->phip_bins = 100;
   p->eta_cut = 7.0; p->eta_bins = 140; p->tau_min = 0.0; p->tau_max = 12.0; p->tau_bins = 120;
   p->r_min = 0.0; p->r_max = 12.0; p->r_bins = 60;
-  p->device = 0; p->famod_chain = 1; p->dndx_bug_compat = 0; p->polzn_chunk_compat = 1;
+  p->device = 0; p->famod_chain = 0; p->dndx_bug_compat = 0; p->polzn_chunk_compat = 0;
 }
 
 const char *is3d_last_error(const is3d_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -61,6 +61,11 @@ is3d_status is3d_create(const is3d_params *p, is3d_ctx **out)
   ctx->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return IS3D_ERR_CUDA; }
+  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    g_create_error = "cudaEventCreate failed";
+    is3d_destroy(ctx);
+    return IS3D_ERR_CUDA;
+  }
   {
     std::vector<double> tab(kExpTableSize);
     fill_exp_table(tab.data());
@@ -81,6 +86,8 @@ void is3d_destroy(is3d_ctx *ctx)
   cudaStreamSynchronize(ctx->stream);
   for (void *p : ctx->owned) cudaFree(p);
   release_host_lists_of(ctx);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -205,7 +212,7 @@ static is3d_status upload_spline(is3d_ctx *ctx, const std::vector<double> &x, co
 {
   std::vector<double> c(n);
   natural_cspline_coefficients(x.data(), y, n, c.data());
-  double *dy = nullptr, *dc = nullptr;
+  double *dy = const_cast<double *>(sp->y), *dc = const_cast<double *>(sp->c);   // a repeated call releases the previous copies
   IS3D_TRY(ctx->upload(&dy, y, n));
   IS3D_TRY(ctx->upload(&dc, c.data(), n));
   sp->x = d_x; sp->y = dy; sp->c = dc; sp->n = n;
@@ -228,13 +235,13 @@ is3d_status is3d_set_df_tables(is3d_ctx *ctx, int n_T, int n_muB, const double *
   tb.T_min = T[0]; tb.muB_min = ctx->h_muB[0];
   tb.dT = fabs(T[1] - T[0]);                                   // DeltafData.cpp:199-204
   tb.dmuB = n_muB > 1 ? fabs(ctx->h_muB[1] - ctx->h_muB[0]) : 0.0;
-  double *dT = nullptr, *dB = nullptr;
+  double *dT = const_cast<double *>(tb.T), *dB = const_cast<double *>(tb.muB);    // upload() frees what a previous call left
   IS3D_TRY(ctx->upload(&dT, ctx->h_T.data(), n_T));
   IS3D_TRY(ctx->upload(&dB, ctx->h_muB.data(), n_muB));
   tb.T = dT; tb.muB = dB;
   for (int k = 0; k < 10; k++) {
     ctx->h_tab[k].assign(tabs[k], tabs[k] + (size_t)n_T * n_muB);
-    double *d = nullptr;
+    double *d = const_cast<double *>(tb.tab[k]);
     IS3D_TRY(ctx->upload(&d, tabs[k], (size_t)n_T * n_muB));
     tb.tab[k] = d;
   }
@@ -253,7 +260,7 @@ is3d_status is3d_set_ptb_tables(is3d_ctx *ctx, int n, const double *x, const dou
   CTX_ENTER(ctx);
   if (n < 3 || !x || !l2 || !z) { ctx->set_error("set_ptb_tables: bad arguments"); return IS3D_ERR_INVALID; }
   ctx->h_ptb_x.assign(x, x + n); ctx->h_ptb_l2.assign(l2, l2 + n); ctx->h_ptb_z.assign(z, z + n);
-  double *dx = nullptr;
+  double *dx = const_cast<double *>(ctx->tb.sp_lambda2.x);
   IS3D_TRY(ctx->upload(&dx, x, n));
   IS3D_TRY(upload_spline(ctx, ctx->h_ptb_x, l2, n, &ctx->tb.sp_lambda2, dx));
   IS3D_TRY(upload_spline(ctx, ctx->h_ptb_x, z, n, &ctx->tb.sp_z, dx));

@@ -107,9 +107,7 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
   double q = fma(r, kSixth, 0.5);
   q = fma(q, r, 1.0);
   q = q * r;                                         // r + r^2/2 + r^3/6
-#if defined(IS3D_PROBE_UNIFORM_EXP_TABLE)       // timing probe only (wrong results): every lane reads entry 0, no bank conflicts
-  const double T = tab[k & 0];
-#elif defined(__CUDA_ARCH__) && !defined(IS3D_EXP_TABLE_GENERIC)
+#if defined(__CUDA_ARCH__) && !defined(IS3D_EXP_TABLE_GENERIC)
   // the table lives in shared memory (load_exp_table): mask, then ONE multiply-add forms the 32-bit shared address
   // (nvcc's own sequence for tab[k & 1023] is shift + mask + add)
   double T;

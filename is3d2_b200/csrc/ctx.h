@@ -32,6 +32,7 @@
 struct is3d_ctx {
   is3d_params prm;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // timing events of the compute calls (created once, destroyed with the context)
   std::string err;
   int sm_count = 148;
   double *d_exptab = nullptr;              // 2^(m/1024) table of fast_exp (common.cuh)

@@ -426,9 +426,7 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
 
   const int nslices = (g.ngroups + g.gpb - 1) / g.gpb;
   const int64_t resident = 2LL * ctx->sm_count;      // two 256-thread blocks per SM (launch bounds)
-  cudaEvent_t e0, e1;
-  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
-  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));
+  cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   float ms_total = 0.f;
   int64_t launches = 0;
   const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0, baryon = p.include_baryon != 0;
@@ -485,8 +483,6 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   unsigned long long h_counters[16];
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (stats) {
     stats->cells_total = n;
     stats->cells_skipped = (int64_t)h_counters[0];

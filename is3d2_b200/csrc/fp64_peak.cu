@@ -63,9 +63,7 @@ is3d_status measure_fp64_peak(is3d_ctx *ctx, double *tflops)
   void *d = nullptr;
   IS3D_TRY(ctx->get_scratch("fp64_peak", 64, &d));
   const int blocks = ctx->sm_count * 8, threads = 256;
-  cudaEvent_t e0, e1;
-  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
-  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));
+  cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   double best = 0.0;
   for (int rep = 0; rep < 6; rep++) {
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
@@ -79,8 +77,6 @@ is3d_status measure_fp64_peak(is3d_ctx *ctx, double *tflops)
     double tf = flops / (ms * 1e-3) / 1e12;
     if (rep >= 1 && tf > best) best = tf;   // first repetition is warm-up
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   *tflops = best;
   return IS3D_OK;
 }

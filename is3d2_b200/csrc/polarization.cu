@@ -196,6 +196,11 @@ is3d_status run_polarization(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   g.exptab = ctx->d_exptab;
   for (int k = 0; k < 6; k++) g.w[k] = ctx->d_vorticity + (size_t)k * ctx->vorticity_pitch;
   g.chunk_compat = p.polzn_chunk_compat;
+  if (g.chunk_compat && ctx->global_offset != 0) {
+    // the reference reads rows (global cell) % 10 000 of the WHOLE vorticity array; a shard does not hold them
+    ctx->set_error("polzn_chunk_compat = 1 needs the unsharded surface (global_offset = 0); sharded polarization runs with polzn_chunk_compat = 0");
+    return IS3D_ERR_UNSUPPORTED;
+  }
 
   const int64_t total_class = (int64_t)nc * per_species;
   const int nslices = (g.ncols + kThreads - 1) / kThreads;
@@ -205,9 +210,7 @@ is3d_status run_polarization(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   void *partial = nullptr;
   IS3D_TRY(ctx->get_scratch("pol_partial", (size_t)nchunks * 5 * total_class * sizeof(double), &partial));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * 5 * total_class * sizeof(double), ctx->stream));
-  cudaEvent_t e0, e1;
-  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
-  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));
+  cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
   dim3 grid(nslices, ctx->Ny * ctx->Nphi, nchunks);
   polarization_kernel<kR><<<grid, kThreads, 0, ctx->stream>>>(ctx->surf, n, cpc, g, (double *)partial, total_class);
@@ -220,8 +223,6 @@ is3d_status run_polarization(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
   IS3D_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (stats) { stats->cells_total = n; stats->kernel_ms = ms; stats->kernel_launches = 2; }
   return IS3D_OK;
 }

@@ -679,9 +679,7 @@ is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
   struct PassList { is3d_ctx::HostList *buf; unsigned long long n; };
   std::vector<PassList> passes;                         // each pass: records sorted by (event, proposal index)
   auto drop_passes = [&]() { for (auto &q : passes) release_host_list(q.buf->ptr); passes.clear(); };
-  cudaEvent_t e0, e1;
-  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
-  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));
+  cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   float ms_total = 0.f;
   int64_t launches = 0;
   int key_bits = 40;
@@ -771,8 +769,6 @@ is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
     ms_total += ms;
     begin += count;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   is3d_status fs = fill_stats(ctx, counters, stats, ms_total, launches);
   if (fs != IS3D_OK) { drop_passes(); return fs; }
 
@@ -859,7 +855,9 @@ is3d_status is3d_sample(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
 
 void is3d_free_particles(is3d_particle *p)
 {
-  if (p && !is3d::release_host_list((void *)p)) free(p);
+  // only lists this library handed out are released; an unknown (stale, already released after its context was
+  // destroyed, or foreign) pointer is left alone rather than passed to free()
+  if (p) (void)is3d::release_host_list((void *)p);
 }
 
 is3d_status is3d_sample_histograms(is3d_ctx *ctx, double *dN_dy, double *dN_deta, double *dN_dphipdy, double *dN_2pipTdpTdy,

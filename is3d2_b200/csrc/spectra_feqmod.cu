@@ -327,9 +327,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total_class * sizeof(double), ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
 
-  cudaEvent_t e0, e1;
-  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e0));
-  IS3D_CUDA_TRY(ctx, cudaEventCreate(&e1));
+  cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   float ms_total = 0.f;
   int64_t launches = 0;
   for (int64_t begin = 0; begin < n; begin += macro) {
@@ -381,8 +379,6 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   unsigned long long h_counters[16];
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (stats) {
     stats->cells_total = n;
     stats->cells_skipped = (int64_t)h_counters[0];

@@ -133,27 +133,34 @@ void IS3D::run_particlization(int fo_from_file)
 using namespace is3dhost;
 
 struct is3d_host {
+  std::string root;
   Session s;
 };
+
+// The reference works with fixed relative paths; here they resolve against ONE process-wide root (io.cpp).  Every entry
+// point installs its session's root first, so several live sessions can be used in turn (not concurrently: like the
+// reference's EmissionFunctionArray, the host layer is single-caller).
+#define ENTER(h) set_root((h)->root)
 
 extern "C" {
 
 is3d_host *is3d_host_open(const char *root, const char *const *overrides)
 {
-  set_root(root ? root : "");
   is3d_host *h = new is3d_host;
+  h->root = root ? root : "";
+  ENTER(h);
   h->s.open(overrides);
   return h;
 }
 void is3d_host_close(is3d_host *h) { delete h; }
-int64_t is3d_host_read_surface(is3d_host *h) { return h->s.read_surface(); }
-int64_t is3d_host_set_surface(is3d_host *h, int64_t n, const double *const cols[IS3D_SURFACE_COLUMNS]) { return h->s.set_surface(n, cols); }
+int64_t is3d_host_read_surface(is3d_host *h) { ENTER(h); return h->s.read_surface(); }
+int64_t is3d_host_set_surface(is3d_host *h, int64_t n, const double *const cols[IS3D_SURFACE_COLUMNS]) { ENTER(h); return h->s.set_surface(n, cols); }
 void is3d_host_thermo_sums(is3d_host *h, double sums6[6]) { compute_thermodynamic_sums(h->s.surf, sums6); }
-void is3d_host_set_thermo_averages(is3d_host *h, const double avg5[5]) { write_thermodynamic_averages(avg5); (void)h; }
-void is3d_host_prepare_tables(is3d_host *h) { h->s.prepare_tables(); }
-void is3d_host_prepare(is3d_host *h) { h->s.create_context(); }
+void is3d_host_set_thermo_averages(is3d_host *h, const double avg5[5]) { ENTER(h); write_thermodynamic_averages(avg5); }
+void is3d_host_prepare_tables(is3d_host *h) { ENTER(h); h->s.prepare_tables(); }
+void is3d_host_prepare(is3d_host *h) { ENTER(h); h->s.create_context(); }
 is3d_ctx *is3d_host_context(is3d_host *h) { return h->s.efa ? h->s.efa->context() : nullptr; }
-void is3d_host_run(is3d_host *h) { h->s.run(); }
+void is3d_host_run(is3d_host *h) { ENTER(h); h->s.run(); }
 int64_t is3d_host_spectra(is3d_host *h, const double **data, int64_t dims[4])
 {
   EmissionFunctionArray *e = h->s.efa.get();

@@ -96,6 +96,26 @@ def s3d(n: int, seed: int = 12345, baryon: bool = False, dimension: int = 3, vah
     return {k: np.ascontiguousarray(s[k], dtype=np.float64) for k in SOA_COLUMNS}
 
 
+BENCH_BLOCK = 1_250_000      # cells per block of the benchmark surface
+BENCH_SEED = 2024
+
+
+def bench_surface(begin: int, end: int, baryon: bool = True) -> dict:
+    """Cells [begin, end) of THE benchmark surface (BASELINE.json config 5: synthetic 3+1D surface, 10 M cells): the
+    concatenation of blocks of BENCH_BLOCK cells, block k = S-3D(BENCH_BLOCK, seed = BENCH_SEED + k).  The surface does not
+    depend on how many GPUs share it; a rank generates only the blocks its cell range touches."""
+    if not 0 <= begin <= end:
+        raise ValueError(f"bad cell range [{begin}, {end})")
+    parts = []
+    for k in range(begin // BENCH_BLOCK, (max(end, 1) - 1) // BENCH_BLOCK + 1):
+        blk = s3d(BENCH_BLOCK, seed=BENCH_SEED + k, baryon=baryon)
+        lo, hi = max(begin - k * BENCH_BLOCK, 0), min(end - k * BENCH_BLOCK, BENCH_BLOCK)
+        parts.append({c: v[lo:hi] for c, v in blk.items()})
+    if len(parts) == 1:
+        return {c: np.ascontiguousarray(v) for c, v in parts[0].items()}
+    return {c: np.concatenate([p[c] for p in parts]) for c in SOA_COLUMNS}
+
+
 def write_mode1(path: str, s: dict, baryon: bool = False) -> None:
     """surface.dat in the CPU-VH layout `t x y n ds_t ds_x ds_y ds_n u^x u^y u^n E T P pi^xx pi^xy pi^xn pi^yy
     pi^yn Pi [muB nB V^x V^y V^n]`, thermodynamic columns in fm^-1 units (reader multiplies by hbarc).

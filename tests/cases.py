@@ -86,7 +86,30 @@ def make_surface(spec):
     kind, kw = spec
     if kind == "bundled":
         return synthetic.bundled_cell()
+    if kind == "bench":                       # a cell range of the benchmark surface (synthetic.bench_surface)
+        return synthetic.bench_surface(kw["begin"], kw["end"], baryon=kw.get("baryon", True))
     return synthetic.s3d(**kw)
+
+
+# BASELINE.json config 2 / 5 at launch-realistic size: the first 2304 cells of the benchmark surface (9 tiles of 256 cells:
+# several cell chunks x 10 column slices x 21 rapidity blocks, the launch shape bench.py times), all 444 SMASH species,
+# df_mode 2 with bulk + shear + baryon diffusion.  One serial run of the unmodified reference (~90 s).
+BIG_SPECTRA_CASES = {
+    "bench_m2_smash_baryon_2304cells": dict(surface=("bench", dict(begin=0, end=2304)),
+                                            params=_p(df_mode=2, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
+}
+
+# df_mode 5 under the chain-free initial-guess policy: goldens are sums of ONE-CELL runs of the unmodified reference
+# (tests/golden/make_golden_m5_chainfree.py)
+M5_CHAINFREE_CASES = {
+    "vah": dict(surface=("s3d", dict(n=120, seed=151, vah=True)), params=_p(df_mode=5), chosen="pikp"),
+    "s3d_stress_outflow": dict(surface=("s3d", dict(n=80, seed=153, stress=0.3)), params=_p(df_mode=5, outflow=1), chosen="pikp"),
+    "vah_baryon": dict(surface=("s3d", dict(n=60, seed=155, vah=True, baryon=True)),
+                       params=_p(df_mode=5, include_baryon=1, include_baryondiff_deltaf=1), chosen="pikp"),
+    "s2d_phi48": dict(surface=("s3d", dict(n=24, seed=154, dimension=2, vah=True)), params=_p(df_mode=5, dimension=2, hrg_eos=1),
+                      chosen="pikp", tables=dict(phi_table="phi_table_48pt.dat")),
+    "vah_smash": dict(surface=("s3d", dict(n=8, seed=156, vah=True)), params=_p(df_mode=5), chosen="smash"),
+}
 
 # dN/dX (operation 0) parity cases: name -> same layout as SPECTRA_CASES (operation forced to 0)
 DNDX_CASES = {
@@ -119,6 +142,8 @@ SAMPLER_CASES = {
     "smp_s3d_m3": dict(surface=("s3d", dict(n=300, seed=43, stress=0.3)), params=_p(df_mode=3, **_S), chosen="pikp"),
     "smp_s3d_m4": dict(surface=("s3d", dict(n=300, seed=44, stress=0.3)), params=_p(df_mode=4, **_S), chosen="pikp"),
     "smp_s2d_m3": dict(surface=("s3d", dict(n=200, seed=45, dimension=2, stress=0.2)), params=_p(df_mode=3, dimension=2, hrg_eos=1, **_S), chosen="pikp"),
+    # BASELINE.json config 3 exactly: full SMASH HRG, df_mode 3 (PTM), oversampled events
+    "smp_s3d_m3_smash": dict(surface=("s3d", dict(n=200, seed=146, stress=0.3)), params=_p(df_mode=3, **_S), chosen="smash"),
     "smp_s3d_m2_smash": dict(surface=("s3d", dict(n=200, seed=46)), params=_p(df_mode=2, **_S), chosen="smash"),
     # fast = 0: species densities from the cell's own (T, muB) by 32-point Gauss-Laguerre sums (max_particle_number)
     "smp_s3d_m2_slow": dict(surface=("s3d", dict(n=300, seed=47)), params=_p(df_mode=2, **dict(_S, fast=0)), chosen="pikp"),

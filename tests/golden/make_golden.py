@@ -20,7 +20,10 @@ from is3d2_b200 import synthetic  # noqa: E402
 
 def main():
     only = set(sys.argv[1:])
-    for name, case in cases.SPECTRA_CASES.items():
+    # the launch-realistic case (BIG_SPECTRA_CASES, ~90 s of serial reference) only when named on the command line
+    todo = dict(cases.SPECTRA_CASES)
+    todo.update({n: c for n, c in cases.BIG_SPECTRA_CASES.items() if n in only})
+    for name, case in todo.items():
         if only and name not in only:
             continue
         out = os.path.join(HERE, f"spectra_{name}.npz")

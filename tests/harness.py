@@ -42,15 +42,25 @@ def assert_spectra_close(got: np.ndarray, ref: np.ndarray, rtol: float = RTOL, w
     return float((err[big] / np.abs(ref[big])).max()) if big.any() else 0.0
 
 
-def open_session(tmp: str, case: dict, surface: dict, overrides: dict | None = None) -> HostSession:
-    """Working directory + host session + in-memory surface + CUDA context for one parity case."""
+def open_session(tmp: str, case: dict, surface: dict, overrides: dict | None = None, famod_chain: int = 1) -> HostSession:
+    """Working directory + host session + in-memory surface + CUDA context for one parity case.  famod_chain = 1 (df_mode 5
+    only): the reference's serial initial-guess chain, which the multi-cell goldens of the unmodified reference carry; the
+    library default is 0 (chain-free), tested against the one-cell reference runs (load_golden_m5free)."""
     params = dict(case["params"])
     if overrides:
         params.update(overrides)
     root = workdir.make_workdir(tmp, params, chosen=case["chosen"], **case.get("tables", {}))
     h = HostSession(root)
     h.set_surface(surface)
-    h.prepare()
+    old = os.environ.get("IS3D_FAMOD_CHAIN")
+    os.environ["IS3D_FAMOD_CHAIN"] = str(famod_chain)          # read once, by the EmissionFunctionArray constructor
+    try:
+        h.prepare()
+    finally:
+        if old is None:
+            os.environ.pop("IS3D_FAMOD_CHAIN", None)
+        else:
+            os.environ["IS3D_FAMOD_CHAIN"] = old
     return h
 
 
@@ -145,3 +155,10 @@ def assert_polzn_close(got: np.ndarray, ref: np.ndarray, rtol: float = RTOL, wha
         raise AssertionError(f"{what}: {bad.sum()} of {ref.size} entries differ by more than {rtol:g}; worst at {i}: got {got[i]!r} ref {ref[i]!r}")
     big = np.abs(ref) > 1e3 * ATOL_OF_SPECIES_PEAK * peak
     return float((err[big] / np.abs(ref[big])).max()) if big.any() else 0.0
+
+
+def load_golden_m5free(name: str):
+    """df_mode 5 chain-free golden: sum of one-cell runs of the unmodified reference (make_golden_m5_chainfree.py)."""
+    z = np.load(os.path.join(GOLDEN, f"m5free_{name}.npz"))
+    surf = {k[4:]: z[k] for k in z.files if k.startswith("col_")}
+    return surf, z["spectra"]

@@ -234,3 +234,34 @@ def test_surface_binary_cache(libs, tmp_path, monkeypatch):
     os.utime(p, (stamp + 10, stamp + 10))
     third, _ = read()
     np.testing.assert_array_equal(third[0], synthetic.roundtrip_mode1(s2, baryon=True)["tau"])
+
+
+def test_two_live_sessions_keep_their_own_roots(libs, tmp_path):
+    """Two host sessions alive at once, used in turn: every entry point resolves the reference's fixed relative paths
+    against ITS session's root (the thermodynamic-average side file, the tables), not against the root opened last."""
+    roots, sessions, surfs = [], [], []
+    for k, (seed, T_shift) in enumerate([(5, 0.0), (6, 0.004)]):
+        root = workdir.make_workdir(str(tmp_path / f"s{k}"), dict(hrg_eos=2, df_mode=3, dimension=3, mode=1), chosen="pikp")
+        s = synthetic.s3d(50, seed=seed)
+        s["T"] = s["T"] + T_shift
+        roots.append(root); surfs.append(s)
+    a = HostSession(roots[0])
+    a.set_surface(surfs[0])
+    b = HostSession(roots[1])            # opened while a is alive
+    b.set_surface(surfs[1])
+    a.set_thermo_averages(np.array([0.151, 0.25, 0.042, 0.0, 0.0]))       # must land in a's directory, not b's
+    a.prepare_tables()
+    b.prepare_tables()
+    pa, pb = a.pdg(), b.pdg()
+    a.close(); b.close()
+    fa = open(os.path.join(roots[0], "tables", "thermodynamic", "average_thermodynamic_quantities.dat")).read().split()
+    fb = open(os.path.join(roots[1], "tables", "thermodynamic", "average_thermodynamic_quantities.dat")).read().split()
+    assert abs(float(fa[0]) - 0.151) < 1e-12
+    assert abs(float(fb[0]) - 0.151) > 1e-4                                 # b kept the averages of its own surface
+    # fast-mode densities were evaluated at each session's own averages
+    assert not np.allclose(pa[:, 5], pb[:, 5])
+    with HostSession(roots[0]) as c:                                        # a fresh session on a's root reproduces a's densities
+        c.set_surface(surfs[0])
+        c.set_thermo_averages(np.array([0.151, 0.25, 0.042, 0.0, 0.0]))
+        c.prepare_tables()
+        np.testing.assert_array_equal(c.pdg()[:, 5], pa[:, 5])

@@ -68,3 +68,17 @@ def test_oracle_polarization_matches_reference_golden(libs, tmp_path, name):
     if len(surf["tau"]) > 10000:
         rc, fixed = prob.polarization(vort, chunk_compat=0)
         assert rc == 0 and not np.allclose(fixed[0], ref[0], rtol=1e-6)      # the corrected index is a different result
+
+
+@pytest.mark.parametrize("name", [n for n, c in cases.M5_CHAINFREE_CASES.items() if c["chosen"] == "pikp"])
+def test_oracle_chain_free_matches_one_cell_reference_runs(libs, tmp_path, name):
+    """df_mode 5 with every cell's Newton solve started from (T, 1, 1) (famod_chain = 0), against the sum of ONE-CELL runs
+    of the unmodified reference -- a one-cell surface never has a previous solution (MomentumSpectra.cpp:1308-1313), so
+    those runs are the chain-free policy of the reference itself."""
+    case = cases.M5_CHAINFREE_CASES[name]
+    surf, ref = harness.load_golden_m5free(name)
+    root = workdir.make_workdir(str(tmp_path), case["params"], chosen=case["chosen"], **case.get("tables", {}))
+    rc, got, st = oracle_api.OracleProblem(root, case["params"], surf, famod_chain=0).spectra()
+    assert rc == 0
+    worst = harness.assert_spectra_close(got, ref, rtol=1e-11, what=name + " chain-free oracle vs one-cell reference runs")
+    print(name, worst)

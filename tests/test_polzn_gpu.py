@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", list(cases.POLZN_CASES))
-def test_polarization_matches_reference(libs, tmp_path, name):
+def test_polarization_matches_reference(libs, tmp_path, monkeypatch, name):
+    monkeypatch.setenv("IS3D_POLZN_CHUNK_COMPAT", "1")          # the reference's in-chunk vorticity index (opt-in)
     case = cases.POLZN_CASES[name]
     surf, vort, ref = harness.load_golden_polzn(name)
     with harness.open_session(str(tmp_path), case, surf) as h:
@@ -47,7 +48,7 @@ def test_polarization_classes_and_corrected_index_match_oracle(libs, tmp_path, m
     name = "pol_s3d_10257cells"
     case = cases.POLZN_CASES[name]
     surf, vort, ref = harness.load_golden_polzn(name)
-    monkeypatch.setenv("IS3D_POLZN_CHUNK_COMPAT", "0")
+    monkeypatch.delenv("IS3D_POLZN_CHUNK_COMPAT", raising=False)  # library default: every cell reads its own vorticity
     with harness.open_session(str(tmp_path / "gpu2"), case, surf) as h:
         h.abi_set_vorticity(vort)
         got, _ = h.abi_polarization()

@@ -40,8 +40,7 @@ def test_famod_chain_free_fast_path_matches_oracle(libs, tmp_path, monkeypatch, 
     from is3d2_b200 import workdir
     case = cases.SPECTRA_CASES[name]
     surf, _ = harness.load_golden(name)
-    monkeypatch.setenv("IS3D_FAMOD_CHAIN", "0")
-    with harness.open_session(str(tmp_path / "gpu"), case, surf) as h:
+    with harness.open_session(str(tmp_path / "gpu"), case, surf, famod_chain=0) as h:
         got, st = h.abi_spectra()
     root = workdir.make_workdir(str(tmp_path / "oracle"), case["params"], chosen=case["chosen"], **case.get("tables", {}))
     rc, ref, ost = oracle_api.OracleProblem(root, case["params"], surf, famod_chain=0).spectra()
@@ -50,6 +49,39 @@ def test_famod_chain_free_fast_path_matches_oracle(libs, tmp_path, monkeypatch, 
     assert st.newton_iterations == ost.newton_iterations
     assert st.cells_breakdown == ost.cells_breakdown and st.reconstruction_failures == ost.reconstruction_failures
     print(f"{name} chain-free fast path vs oracle: max rel err {worst:.3e}")
+
+
+@pytest.mark.parametrize("name", list(cases.M5_CHAINFREE_CASES))
+def test_famod_chain_free_matches_one_cell_reference_runs(libs, tmp_path, name):
+    """df_mode 5 in the library's default (production, shardable) policy -- every cell's Newton solve starts from (T, 1, 1) --
+    against the UNMODIFIED REFERENCE: the golden is the sum of one-cell reference runs, where the reference itself starts
+    from (T, 1, 1) because a one-cell surface has no previous solution (MomentumSpectra.cpp:1288-1313;
+    tests/golden/make_golden_m5_chainfree.py).  Tolerance: the north-star 1e-10."""
+    case = cases.M5_CHAINFREE_CASES[name]
+    surf, ref = harness.load_golden_m5free(name)
+    with harness.open_session(str(tmp_path), case, surf, famod_chain=0) as h:
+        got, st = h.abi_spectra()
+    worst = harness.assert_spectra_close(got, ref, what=name + " chain-free vs one-cell reference runs")
+    assert st.cells_total == len(surf["tau"])
+    print(f"{name} chain-free vs reference: max rel err {worst:.3e}")
+
+
+@pytest.mark.parametrize("name", list(cases.BIG_SPECTRA_CASES))
+def test_launch_realistic_surface_matches_reference(libs, tmp_path, name):
+    """BASELINE.json config 2 on a prefix of THE benchmark surface (config 5) large enough for the launch shape bench.py
+    times -- several cell chunks x 10 column slices of 256 thread columns x 21 rapidity blocks, all 444 SMASH species in 193
+    classes / 50 uniform-baryon thread groups -- against one serial run of the unmodified reference
+    (MomentumSpectra.cpp:99-375).  Also through small passes (multi-pass accumulation across pass boundaries)."""
+    case = cases.BIG_SPECTRA_CASES[name]
+    surf, ref = harness.load_golden(name)
+    gen = cases.make_surface(case["surface"])          # the golden's cells ARE the benchmark surface's first cells
+    for k in ("tau", "ux", "dat"):
+        np.testing.assert_array_equal(gen[k], surf[k])
+    with harness.open_session(str(tmp_path), case, surf) as h:
+        got, st = h.abi_spectra()
+    worst = harness.assert_spectra_close(got, ref, what=name)
+    assert st.cells_total == len(surf["tau"]) and st.cells_out_of_table == 0
+    print(f"{name}: max rel err {worst:.3e}, {st.cells_skipped} of {st.cells_total} cells skipped")
 
 
 def test_known_answer_static_cell(libs, tmp_path):

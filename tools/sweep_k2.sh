@@ -4,7 +4,7 @@
 out=gpurun_out/sweep_k2.log; : > $out
 for R in "$@"; do
   touch is3d2_b200/csrc/spectra_feqmod.cu
-  IS3D_NVCC_EXTRA="-DIS3D_K2_R=$R" python -m is3d2_b200.build > /dev/null 2>&1 || { echo "R=$R build failed" >> $out; continue; }
+  python tools/build_variant.py -DIS3D_K2_R=$R > /dev/null 2>&1 || { echo "R=$R build failed" >> $out; continue; }
   for M in ${MODES:-3 4 5}; do
     python bench.py --steps 2 --warmup 2 --cells-per-gpu ${CELLS:-300000} --df-mode $M --no-cpu-baseline --no-sampler 2>/dev/null | grep '^{' | python -c "
 import json,sys

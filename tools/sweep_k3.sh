@@ -4,7 +4,7 @@ out=gpurun_out/sweep_k3.log; : > $out
 for v in "$@"; do
   set -- $v
   touch is3d2_b200/csrc/spectra_famod.cu
-  IS3D_NVCC_EXTRA="-DIS3D_K3_MINBLOCKS=$1 -DIS3D_K3_UNROLL=$2" python -m is3d2_b200.build > /dev/null 2>&1 || { echo "B=$1 U=$2 build failed" >> $out; continue; }
+  python tools/build_variant.py -DIS3D_K3_MINBLOCKS=$1 -DIS3D_K3_UNROLL=$2 > /dev/null 2>&1 || { echo "B=$1 U=$2 build failed" >> $out; continue; }
   regs=$(cuobjdump -res-usage is3d2_b200/build/spectra_famod.cu.o | grep -A1 famod_setup_free | grep -o "REG:[0-9]*")
   python bench.py --df-mode 5 --steps 2 --warmup 2 --cells-per-gpu 200000 --no-cpu-baseline --no-sampler 2>/dev/null | grep '^{' | python -c "
 import json,sys
