@@ -5,11 +5,12 @@
     python bench.py --impl reference ...                     # the reference's own CPU (OpenMP) path, bounded sample
     torchrun --nproc-per-node N ... bench.py --gpus N ...    # cells sharded over N GPUs + one NCCL all-reduce
 
-Workload (config.workload): continuous spectra, all 444 SMASH species, shipped 51 pT x 1 phi x 21 y grid,
-df_mode 2 (RTA Chapman-Enskog) with bulk + shear + baryon diffusion on the seeded synthetic 3+1D surface S-3D
-(SURVEY.md 8d), `--cells-per-gpu` cells per GPU (weak scaling; 1.25 M x 8 GPUs = the 10 M-cell surface of
-BASELINE.json config 5).  One "step" = one full Cooper-Frye pass over the rank's cells (per-cell set-up kernel +
-spectra kernel + partial reduction) followed, for N > 1, by the all-reduce of the spectra array.
+Workload (config.workload) = BASELINE.json config 2 on config 5's surface: continuous spectra, all 444 SMASH species,
+shipped 51 pT x 1 phi x 21 y grid, df_mode 2 (RTA Chapman-Enskog) with bulk + shear + baryon diffusion on THE synthetic
+3+1D surface of `--cells` cells (default 10 M; is3d2_b200/synthetic.py bench_surface: blocks S-3D(1.25 M, seed 2024 + k)).
+The surface is the same for every N: rank r integrates its contiguous block of cells (strong scaling).  One "step" = one
+full Cooper-Frye pass over the surface: per-cell set-up kernel + spectra kernel + partial reduction on every GPU, then (N > 1)
+ONE ncclAllReduce of the spectra issued by the product itself (is3d_comm_attach / is3d_spectra_device).
 """
 from __future__ import annotations
 
@@ -66,8 +67,8 @@ def bench_params(df_mode: int) -> dict:
 
 def workload_name(df_mode: int, cells: int, n_gpus: int) -> str:
     terms = "bulk+shear" if df_mode == 4 else "bulk+shear+baryon diffusion"
-    return (f"continuous spectra, all SMASH species (444), df_mode={df_mode} with {terms}, "
-            f"51pT x 1phi x 21y, synthetic 3+1D surface S-3D, {cells} cells per GPU x {n_gpus} GPU")
+    return (f"continuous spectra, all SMASH species (444), df_mode={df_mode} with {terms}, 51pT x 1phi x 21y, "
+            f"one synthetic 3+1D surface of {cells} cells (S-3D blocks, seeds 2024+k) sharded over {n_gpus} GPU")
 
 
 class ClockSampler:
@@ -122,7 +123,7 @@ def oracle_port_evals_per_s(args, cells: int) -> tuple[float, float]:
     the reference loop (oracle/cf_oracle.cpp, one thread) on `cells` cells of the same workload.  Returns (evals/s, s)."""
     sys.path.insert(0, os.path.join(REPO, "tests"))
     import oracle_api
-    surf = synthetic.s3d(cells, seed=2024, baryon=True)
+    surf = synthetic.bench_surface(0, cells, baryon=True)
     root = tempfile.mkdtemp(prefix="is3d_port_")
     try:
         params = bench_params(args.df_mode)
@@ -138,83 +139,89 @@ def oracle_port_evals_per_s(args, cells: int) -> tuple[float, float]:
     return float(cells) * NS_SMASH * NPT * NPHI * NY / sec, sec
 
 
+def reference_openmp_seconds(args, cells: int, runs: int) -> tuple[list[float], str, int]:
+    """The unmodified reference's OpenMP build (oracle/_ref) on the first `cells` cells of the benchmark surface, all host
+    threads; returns (seconds inside calculate_spectra per run, binary used, threads).  The -march=native build is tried
+    first ("native" = the build container's CPU) and dropped for the plain -O3 one if this host's CPU
+    rejects it."""
+    cores = os.cpu_count() or 1
+    surf = synthetic.bench_surface(0, cells, baryon=True)
+    params = bench_params(args.df_mode)
+    root = tempfile.mkdtemp(prefix="is3d_ref_")
+    times, used = [], None
+    try:
+        workdir.make_workdir(root, params, chosen="smash")
+        synthetic.write_mode1(os.path.join(root, "input", "surface.dat"), surf, baryon=True)
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+        for name in ("is3d_ref_omp_native", "is3d_ref_omp"):
+            exe = os.path.join(REPO, "oracle", "_ref", name)
+            if not os.access(exe, os.X_OK):
+                continue
+            try:
+                times = []
+                for _ in range(runs):
+                    with open(os.path.join(root, "ref_stdout.log"), "w") as log:
+                        subprocess.run([exe], cwd=root, stdout=log, stderr=subprocess.STDOUT, env=env, check=True)
+                    times.append(float(open(os.path.join(root, "ref_dump", "timing.txt")).read().split()[0]))
+                used = name
+                break
+            except (subprocess.CalledProcessError, OSError, ValueError) as ex:
+                print(f"bench.py: {name} failed on this host ({ex!r}); trying the next reference build", file=sys.stderr)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    if used is None:
+        raise RuntimeError("no runnable oracle/_ref OpenMP binary")
+    return times, used, cores
+
+
+def have_reference_binary() -> bool:
+    return any(os.access(os.path.join(REPO, "oracle", "_ref", n), os.X_OK) for n in ("is3d_ref_omp_native", "is3d_ref_omp"))
+
+
 def run_reference(args) -> None:
     """The reference's own CPU implementation (oracle/_ref, unmodified sources, OpenMP build) on a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    exe = os.path.join(REPO, "oracle", "_ref", "is3d_ref_omp")
-    cores = os.cpu_count() or 1
     cells = args.ref_cells
-    if not os.access(exe, os.X_OK):
+    evals = float(cells) * NS_SMASH * NPT * NPHI * NY
+    common = {"impl": "reference", "metric": "Cooper-Frye cell*species*momentum evals/s", "unit": "evals/s", "n_gpus": args.gpus,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "gpu_launches": 0}
+    if not have_reference_binary():
         # the compiled reference did not travel: time the oracle port instead (kind = "port", one core)
         pc = max(50, cells // 10)
         vals = [oracle_port_evals_per_s(args, pc) for _ in range(max(1, min(args.steps, 2)))]
         value, sec = float(np.mean([v[0] for v in vals])), float(np.mean([v[1] for v in vals]))
-        sample = f"{pc}-cell S-3D sample (seed 2024) of the same workload, oracle/cf_oracle.cpp (scalar restatement of the reference loop)"
-        line = {"impl": "reference", "metric": "Cooper-Frye cell*species*momentum evals/s", "value": value, "unit": "evals/s",
-                "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": sec * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.df_mode, args.cells_per_gpu, args.gpus), "sample": sample},
-                "cpu_baseline": {"value": value, "unit": "evals/s", "cores": 1, "kind": "port", "sample": sample},
-                "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        emit(line)
+        sample = f"first {pc} cells of the benchmark surface, oracle/cf_oracle.cpp (scalar restatement of the reference loop)"
+        emit(dict(common, value=value, steps=len(vals), warmup=0, ms_per_step=sec * 1e3,
+                  config={"workload": workload_name(args.df_mode, args.cells, args.gpus), "sample": sample},
+                  cpu_baseline={"value": value, "unit": "evals/s", "cores": 1, "kind": "port", "sample": sample},
+                  e2e={"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}))
         return
-    surf = synthetic.s3d(cells, seed=2024, baryon=True)
-    params = bench_params(args.df_mode)
-    root = tempfile.mkdtemp(prefix="is3d_ref_")
-    try:
-        workdir.make_workdir(root, params, chosen="smash")
-        synthetic.write_mode1(os.path.join(root, "input", "surface.dat"), surf, baryon=True)
-        env = dict(os.environ, OMP_NUM_THREADS=str(cores))
-        times = []
-        for i in range(args.warmup + args.steps):
-            with open(os.path.join(root, "ref_stdout.log"), "w") as log:
-                subprocess.run([exe], cwd=root, stdout=log, stderr=subprocess.STDOUT, env=env, check=True)
-            t = float(open(os.path.join(root, "ref_dump", "timing.txt")).read().split()[0])
-            if i >= args.warmup:
-                times.append(t)
-    finally:
-        shutil.rmtree(root, ignore_errors=True)
-    evals = float(cells) * NS_SMASH * NPT * NPHI * NY
-    sec = float(np.mean(times))
+    times, used, cores = reference_openmp_seconds(args, cells, args.warmup + args.steps)
+    sec = float(np.mean(times[args.warmup:]))
     value = evals / sec
-    sample = f"{cells}-cell prefix-sized S-3D sample (seed 2024) of the same workload, timed inside calculate_spectra"
-    line = {"impl": "reference", "metric": "Cooper-Frye cell*species*momentum evals/s", "value": value, "unit": "evals/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.df_mode, args.cells_per_gpu, args.gpus), "sample": sample,
-                       "note": "3+1D OpenMP loop of the reference is racy (shared etaValues[0]); timing only"},
-            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "reference", "sample": sample},
-            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    emit(line)
+    sample = (f"first {cells} cells of the benchmark surface (evals/s is linear in cells), oracle/_ref/{used} with {cores} OpenMP threads, "
+              "timed inside calculate_spectra")
+    emit(dict(common, value=value, steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3,
+              config={"workload": workload_name(args.df_mode, args.cells, args.gpus), "sample": sample,
+                      "note": "3+1D OpenMP loop of the reference is racy (shared etaValues[0]); timing only"},
+              cpu_baseline={"value": value, "unit": "evals/s", "cores": cores, "kind": "reference", "sample": sample},
+              e2e={"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}))
 
 
 def cpu_baseline(args) -> dict:
     """Bounded reference run beside the GPU number (rank 0, N = 1 only)."""
-    exe = os.path.join(REPO, "oracle", "_ref", "is3d_ref_omp")
-    cores = os.cpu_count() or 1
-    if not os.access(exe, os.X_OK):
+    if not have_reference_binary():
         pc = max(50, args.ref_cells // 10)
         value, sec = oracle_port_evals_per_s(args, pc)
         return {"value": value, "unit": "evals/s", "cores": 1, "kind": "port",
-                "sample": f"{pc} cells of the same S-3D workload, oracle/cf_oracle.cpp on one core, {sec:.2f} s (oracle/_ref not on this box)"}
+                "sample": f"first {pc} cells of the benchmark surface, oracle/cf_oracle.cpp on one core, {sec:.2f} s (oracle/_ref not on this box)"}
     cells = args.ref_cells
-    surf = synthetic.s3d(cells, seed=2024, baryon=True)
-    root = tempfile.mkdtemp(prefix="is3d_cpu_")
-    try:
-        workdir.make_workdir(root, bench_params(args.df_mode), chosen="smash")
-        synthetic.write_mode1(os.path.join(root, "input", "surface.dat"), surf, baryon=True)
-        env = dict(os.environ, OMP_NUM_THREADS=str(cores))
-        with open(os.path.join(root, "ref_stdout.log"), "w") as log:
-            subprocess.run([exe], cwd=root, stdout=log, stderr=subprocess.STDOUT, env=env, check=True)
-        sec = float(open(os.path.join(root, "ref_dump", "timing.txt")).read().split()[0])
-    finally:
-        shutil.rmtree(root, ignore_errors=True)
+    times, used, cores = reference_openmp_seconds(args, cells, 1)
     evals = float(cells) * NS_SMASH * NPT * NPHI * NY
-    return {"value": evals / sec, "unit": "evals/s", "cores": cores, "kind": "reference",
-            "sample": f"{cells} cells of the same S-3D workload, reference OpenMP build with {cores} threads, {sec:.2f} s inside calculate_spectra"}
+    return {"value": evals / times[0], "unit": "evals/s", "cores": cores, "kind": "reference",
+            "sample": f"first {cells} cells of the benchmark surface, oracle/_ref/{used} with {cores} OpenMP threads, {times[0]:.2f} s inside calculate_spectra"}
 
 
 SAMPLER_PARAMS = dict(operation=2, mode=1, hrg_eos=2, dimension=3, df_mode=3, include_baryon=0, include_bulk_deltaf=1,
@@ -223,18 +230,20 @@ SAMPLER_PARAMS = dict(operation=2, mode=1, hrg_eos=2, dimension=3, df_mode=3, in
 
 
 def sampler_bench(args, rank: int, world: int, local: int) -> dict:
-    """BASELINE.json config 3: particle sampler, full SMASH HRG, df_mode 3 (PTM), 1000 oversampled events, on this
-    rank's block of a synthetic 3+1D surface.  Timed end to end through is3d_sample (host surface already on the
-    device; particle records copied back to host memory inside the timed region).  No collective: ranks sample
-    disjoint cell blocks with Philox streams keyed by the global cell index."""
+    """BASELINE.json config 3: particle sampler, full SMASH HRG, df_mode 3 (PTM), 1000 oversampled events.  The surface is
+    the concatenation of `sampler_cells`-cell blocks S-3D(seed 3024 + k, stress 0.3), one block per GPU (weak: the sampler
+    shards cells and concatenates events, no collective; Philox streams keyed by the global cell index).  Timed end to end
+    through the C ABI over `sampler_calls` calls after one warm-up call: surface resident, particle records copied back to
+    (library-owned, pinned) host memory inside the timed region."""
     import torch
     import torch.distributed as dist
 
     from is3d2_b200 import HostSession, shard
 
-    cells, nev = args.sampler_cells, args.sampler_events
+    cells, nev, calls = args.sampler_cells, args.sampler_events, max(1, args.sampler_calls)
     surf = synthetic.s3d(cells, seed=3024 + rank, stress=0.3)
     root = tempfile.mkdtemp(prefix=f"is3d_smp_r{rank}_")
+    res = {}
     try:
         workdir.make_workdir(root, SAMPLER_PARAMS, chosen="smash")
         with HostSession(root) as h:
@@ -243,30 +252,46 @@ def sampler_bench(args, rank: int, world: int, local: int) -> dict:
             h.prepare()
             h.abi_set_surface(surf, global_offset=rank * cells)
             ntot, _ = h.abi_total_yield()
-            h.abi_sample(nev)                                      # warm-up: same size, so the pinned list buffer is reused
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            parts, counts, st, release = h.abi_sample(nev, copy=False)       # view of the library-owned pinned list
-            torch.cuda.synchronize()
-            sec = time.perf_counter() - t0
-            n_parts = len(parts)
-            del parts
-            release()
+            for mode in ("full", "compact") if hasattr(h, "abi_sample_compact") else ("full",):
+                sample = h.abi_sample if mode == "full" else h.abi_sample_compact
+                rec_bytes = 104 if mode == "full" else 64
+                out = sample(nev, copy=False)                          # warm-up: same size, so the pinned list buffer is reused
+                out[3]()
+                secs, kms = [], []
+                n_parts = proposals = 0
+                for _ in range(calls):
+                    if world > 1:
+                        dist.barrier()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    parts, counts, st, release = sample(nev, copy=False)       # view of the library-owned pinned list
+                    torch.cuda.synchronize()
+                    secs.append(time.perf_counter() - t0)
+                    kms.append(st.kernel_ms)
+                    n_parts, proposals = len(parts), st.sampler_proposals
+                    del parts
+                    release()
+                sec, dev_ms = float(np.median(secs)), float(np.median(kms))
+                acc = torch.tensor([float(n_parts), float(proposals), sec, dev_ms, min(secs), max(secs)], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    sums = acc.clone()
+                    dist.all_reduce(sums)
+                    dist.all_reduce(acc, op=dist.ReduceOp.MAX)
+                    hadrons, props = float(sums[0]), float(sums[1])
+                else:
+                    hadrons, props = float(acc[0]), float(acc[1])
+                sec, dev_ms, smin, smax = float(acc[2]), float(acc[3]), float(acc[4]), float(acc[5])
+                res[mode] = {"hadrons_per_s": hadrons / sec, "seconds_median": sec, "seconds_min": smin, "seconds_max": smax,
+                             "device_ms_median": dev_ms, "hadrons_per_s_device": hadrons / (dev_ms * 1e-3) if dev_ms > 0 else None,
+                             "record_bytes": rec_bytes, "d2h_bytes": int(hadrons) * rec_bytes,
+                             "d2h_gbs_of_wall": hadrons * rec_bytes / sec / 1e9, "hadrons": int(hadrons),
+                             "proposals_per_s": props / sec, "acceptance": hadrons / max(props, 1.0)}
     finally:
         shutil.rmtree(root, ignore_errors=True)
-    acc = torch.tensor([float(n_parts), float(st.sampler_proposals), sec, st.kernel_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        sums = acc.clone()
-        dist.all_reduce(sums)
-        dist.all_reduce(acc, op=dist.ReduceOp.MAX)
-        hadrons, proposals, sec, kms = float(sums[0]), float(sums[1]), float(acc[2]), float(acc[3])
-    else:
-        hadrons, proposals, sec, kms = (float(v) for v in acc.tolist())
-    return {"metric": "sampled hadrons/s", "value": hadrons / sec, "unit": "hadrons/s", "hadrons": int(hadrons),
-            "proposals_per_s": proposals / sec, "acceptance": hadrons / max(proposals, 1.0), "seconds": sec,
-            "device_ms": kms, "d2h_bytes": int(hadrons) * 104, "mean_yield_per_event_rank0": ntot,
+    best = res.get("compact", res["full"])
+    return {"metric": "sampled hadrons/s", "value": best["hadrons_per_s"], "unit": "hadrons/s", "calls": calls,
+            "records": "64-byte wire records through is3d_sample_compact (value); 104-byte Sampled_Particle records through is3d_sample beside it",
+            "compact": res.get("compact"), "full": res["full"], "mean_yield_per_event_rank0": ntot,
             "workload": f"sampler, df_mode=3 PTM, fast=1, all SMASH species, {nev} events, S-3D(stress 0.3) {cells} cells per GPU x {world} GPU, "
                         "particle lists returned to host memory"}
 
@@ -295,11 +320,41 @@ def sampler_cpu_baseline(args) -> dict:
                       f"serial reference, {sec:.2f} s inside calculate_spectra (histogram mode, no particle files)"}
 
 
+def oracle_spot_check(args, h, surf: dict) -> dict:
+    """Checker leg (rank 0, before any communicator is attached): the first `check_cells` cells of the benchmarked surface
+    through the SAME context and kernels against the CPU oracle (oracle/cf_oracle.cpp, pinned to the unmodified reference)."""
+    n = args.check_cells
+    try:
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+        import harness
+        import oracle_api
+        sl = {k: np.ascontiguousarray(v[:n]) for k, v in surf.items()}
+        h.abi_set_surface(sl, global_offset=0)
+        got, _ = h.abi_spectra()
+        root = tempfile.mkdtemp(prefix="is3d_check_")
+        try:
+            params = bench_params(args.df_mode)
+            workdir.make_workdir(root, params, chosen="smash")
+            rc, want, _ = oracle_api.OracleProblem(root, params, sl, famod_chain=0).spectra()
+        finally:
+            shutil.rmtree(root, ignore_errors=True)
+        if rc != 0:
+            return {"cells": n, "ok": False, "error": f"oracle status {rc}"}
+        tol = harness.RTOL
+        try:
+            worst = harness.assert_spectra_close(got, want, rtol=tol, what="bench spot check")
+            return {"cells": n, "max_rel_err": worst, "tolerance": tol, "ok": True, "against": "oracle/cf_oracle.cpp on the surface's first cells"}
+        except AssertionError as e:
+            return {"cells": n, "tolerance": tol, "ok": False, "error": str(e)[:300]}
+    except Exception as e:  # noqa: BLE001 -- the checker must not take the measurement down
+        return {"cells": n, "ok": None, "error": f"checker unavailable: {e!r}"[:300]}
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from is3d2_b200 import HostSession, shard
+    from is3d2_b200 import HostSession
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -308,7 +363,7 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py: no CUDA device; this repository has no CPU compute path")
     torch.cuda.set_device(local)
     os.environ["IS3D_DEVICE"] = str(local)
-    os.environ.setdefault("IS3D_FAMOD_CHAIN", "0")          # df_mode 5: chain-free (shardable) initial guesses
+    os.environ.pop("IS3D_DEVICES", None)                    # one process per GPU here; the group API is the other way in
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -327,42 +382,67 @@ def run_ours(args) -> None:
         gc.collect()
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
+        h.close()                                           # destroys the context and its communicator
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-        h.close()
         shutil.rmtree(root, ignore_errors=True)
 
 
+def attach_product_communicator(h, world: int, rank: int) -> None:
+    """The all-reduce of the path lives in the product (is3d_comm_attach -> ncclAllReduce inside is3d_spectra[_device]);
+    torch.distributed only ships the 128-byte NCCL id from rank 0 to the other ranks."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        st = h.lib.is3d_comm_unique_id(buf)
+        if st != 0:
+            raise RuntimeError("is3d_comm_unique_id: " + h.lib.is3d_comm_last_error().decode())
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, src=0)
+    ident = bytes(t.cpu().tolist())
+    h._check(h.lib.is3d_comm_attach(h.ctx, ident, world, rank), "is3d_comm_attach")
+
+
 def _measure_ours(args, h, world: int, rank: int, local: int):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
-    from is3d2_b200 import shard
+    from is3d2_b200 import sassinfo, shard
 
-    cells = args.cells_per_gpu
-    surf = synthetic.s3d(cells, seed=2024 + rank, baryon=True)         # rank's shard of the surface
-    # thermodynamic averages (only the sampler uses them) from a small prefix: the host loop is O(cells) python-free C++
-    h.set_surface({k: v[:1000] for k, v in surf.items()})
-    shard.set_global_thermo_averages(h)
+    # ONE surface, whatever the number of GPUs (strong scaling): rank r integrates the contiguous cell block [b, e)
+    G = args.cells
+    b, e = shard.cell_range(G, rank, world)
+    cells = e - b
+    surf = synthetic.bench_surface(b, e, baryon=True)
+    h.set_surface(surf)                                     # host layer: this block's thermodynamic sums ...
+    shard.set_global_thermo_averages(h)                     # ... -> averages of the WHOLE surface (set-up; torch.distributed)
     h.prepare()
     shape = h.spectra_shape()
     total = int(np.prod(shape))
-    evals_rank = float(cells) * total
+    evals_global = float(G) * total
+
+    check = oracle_spot_check(args, h, surf) if (rank == 0 and args.check_cells > 0) else None
+    if world > 1:
+        attach_product_communicator(h, world, rank)
 
     ext = torch.cuda.ExternalStream(h.lib.is3d_stream(h.ctx), device=torch.device("cuda", local))
     # pinned host copies (e2e path) and resident device copies (value path)
     host_cols = {k: torch.from_numpy(v).pin_memory() for k, v in surf.items()}
+    del surf
     dev_cols = {k: t.cuda(non_blocking=True) for k, t in host_cols.items()}
     torch.cuda.synchronize()
     out_dev = torch.zeros(total, dtype=torch.float64, device="cuda")
-    h.abi_set_surface_device({k: t.data_ptr() for k, t in dev_cols.items()}, cells, global_offset=rank * cells)
+    h.abi_set_surface_device({k: t.data_ptr() for k, t in dev_cols.items()}, cells, global_offset=b)
 
     def step():
-        st = h.abi_spectra_device(out_dev.data_ptr())
-        if world > 1:
-            dist.all_reduce(out_dev)                                      # the one collective of the path (NCCL / NVLink)
-        return st
+        # set-up kernel + spectra kernel + partial reduction + (N > 1) the product's own ncclAllReduce of the spectra
+        return h.abi_spectra_device(out_dev.data_ptr())
 
     def barrier():
         if world > 1:
@@ -377,35 +457,25 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
         if rank == 0:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kernel_ms, launches = 0.0, 0
+        kernel_ms, launches, skipped, executed = 0.0, 0, 0, 0
         ev0.record(ext)
         for _ in range(args.steps):
             st = step()
             kernel_ms += st.kernel_ms
             launches += st.kernel_launches
+            skipped, executed = st.cells_skipped, st.evals_executed
         ev1.record(ext)
         barrier()
         clocks = sampler.stop() if rank == 0 else None
         ms = ev0.elapsed_time(ev1)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        value_out = out_dev.cpu().numpy().copy()
+        collectives = int(h.lib.is3d_comm_collectives(h.ctx))
 
-        # ---- end to end through the C ABI with HOST buffers: H2D of the 25 columns + compute + D2H of the spectra ----
-        # N = 1: is3d_set_surface + is3d_spectra (host in, host out).  N > 1: is3d_set_surface + is3d_spectra_device,
-        # one NCCL all-reduce of the device array, D2H into pinned memory -- the sequence INTEGRATION.md prescribes.
+        # ---- end to end through the C ABI with HOST buffers: H2D of the 25 columns + compute (+ all-reduce) + D2H ----
         host_np = {k: t_.numpy() for k, t_ in host_cols.items()}
-        out_host = torch.empty(total, dtype=torch.float64).pin_memory()
 
         def e2e_step():
-            h.abi_set_surface(host_np, global_offset=rank * cells)
-            if world > 1:
-                h.abi_spectra_device(out_dev.data_ptr())
-                dist.all_reduce(out_dev)
-                out_host.copy_(out_dev, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                return out_host.numpy()
+            h.abi_set_surface(host_np, global_offset=b)
             return h.abi_spectra()[0]
 
         e2e_steps = max(1, min(args.steps, 3))
@@ -416,68 +486,94 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
             spec = e2e_step()
         barrier()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
-        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
+
+    # max over ranks of the two times, sums of the per-rank counters
+    t = torch.tensor([ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
+    c = torch.tensor([float(skipped), float(executed), float(cells)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c)
+    ms_total, e2e_s, kernel_ms = (float(v) for v in t.tolist())
+    skipped_all, executed_all, cells_all = (float(v) for v in c.tolist())
+    assert int(cells_all) == G
 
     fp64_peak = h.abi_fp64_peak()
     sampler = None if args.no_sampler else sampler_bench(args, rank, world, local)
-    if rank == 0:
-        ms_step = ms_total / args.steps
-        value = evals_rank * world / (ms_step * 1e-3)
-        kern_s = kernel_ms / args.steps * 1e-3
-        achieved = evals_rank * F_ALG[args.df_mode] / kern_s / 1e12
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        bytes_alg = cells * 25 * 8.0 + total * 8.0
-        # DRAM bytes and FP64-pipe utilisation of ONE df_spectra_kernel launch from the committed `ncu --set full` capture of
-        # this command at the default size (profiles/r01_ncu_k1_headline.json); null for any other configuration
-        traffic = traffic_src = fp64_pct = executed = None
-        try:
-            cap = json.load(open(os.path.join(REPO, "profiles", "r01_ncu_k1_headline.json")))
-            if cap["config"] == {"df_mode": args.df_mode, "cells_per_gpu": cells}:
-                traffic = float(cap["dram_bytes_read"] + cap["dram_bytes_write"])
-                traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_k1_headline.json"
-                fp64_pct = cap["fp64_pipe_active_pct"]
-                # executed work: FP64-pipe instructions of the SASS inner loop x 2 flops, per class slot actually evaluated
-                executed = (evals_rank * cap["class_slots"] / cap["species"]) * cap["fp64_instr_per_class_eval_sass"] * 2.0 / kern_s / 1e12
-        except (OSError, KeyError, ValueError):
-            pass
-        line = {
-            "metric": "Cooper-Frye cell*species*momentum evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.df_mode, cells, world), "global_cells": cells * world,
-                       "evals_per_step": evals_rank * world, "l2_policy": "inputs larger than L2 (cell packs: 256 B x cells per pass)",
-                       "parallelism": f"cells sharded x{world}, one NCCL all-reduce of {total} doubles" if world > 1 else "single GPU",
-                       "species_classes": "evaluations are counted per species (444); species with identical (mass, sign, baryon "
-                                          "number) share one integrand, computed once and scaled by each species' degeneracy "
-                                          "(193 classes for the SMASH list) -- every species' bins are delivered"},
-            "e2e": {"value": evals_rank * world / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(cells * 25 * 8),
-                    "d2h_bytes_per_step": int(total * 8)},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "df_spectra_kernel" if args.df_mode <= 2 else "feqmod_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
-                         "fp64_pipe_active_pct_ncu": fp64_pct,
-                         "executed_tflops": executed, "frac_executed": (executed / fp64_peak) if executed else None,
-                         "flops_per_eval_algorithmic": F_ALG[args.df_mode],
-                         "peak_source": "DFMA micro-benchmark run live by is3d_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
-                         "hbm_gbs_algorithmic": bytes_alg / kern_s / 1e9, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
-            "clocks": clocks,
-        }
+    if rank != 0:
+        return None
+
+    ms_step = ms_total / args.steps
+    kern_s = kernel_ms / args.steps * 1e-3                               # slowest rank's dominant-kernel time per step
+    value = evals_global / (ms_step * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    # ---- roofline of the dominant kernel, from what THIS run executed ----
+    # executed FP64-pipe work = class-evaluations the kernel ran (is3d_stats.evals_executed: padding slots and idle thread
+    # columns included) x FP64-pipe instructions per class-evaluation read from the SASS of the loaded library x 2 flops
+    label = {1: "df_spectra_kernel<1,1,0,0,4>", 2: "df_spectra_kernel<2,1,0,0,4>"}.get(args.df_mode)
+    mix = None
+    try:
+        mix = sassinfo.library_info()["kernels"].get(label) if label else None
+    except Exception as ex:  # noqa: BLE001
+        print(f"bench.py: SASS scan failed: {ex!r}", file=sys.stderr)
+    achieved = frac = per_eval = None
+    if mix and executed_all > 0:
+        per_eval = mix["fp64"] / mix["evals_per_trip"]
+        # all ranks run side by side: per-GPU rate = (executed on the slowest rank ~ executed_all / world) / its kernel time
+        achieved = executed_all / world * per_eval * 2.0 / kern_s / 1e12
+        frac = achieved / fp64_peak
+    # DRAM bytes of one launch: only from an `ncu --set full` capture of the SAME inner loop (listing hash) and the same launch
+    traffic = traffic_src = None
+    try:
+        cap = json.load(open(os.path.join(REPO, "profiles", "ncu_k1_headline.json")))
+        if mix and cap.get("listing_sha256") == mix["listing_sha256"] and cap.get("cells_per_launch"):
+            per_cell = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["cells_per_launch"]
+            traffic = per_cell * min(cells, 4 << 20)
+            traffic_src = f"ncu dram__bytes_read.sum + dram__bytes_write.sum per cell ({per_cell:.1f} B) x cells of one launch, profiles/ncu_k1_headline.json (same inner-loop SASS)"
+    except (OSError, KeyError, ValueError):
+        pass
+    bytes_alg = cells * 25 * 8.0 + total * 8.0
+    line = {
+        "metric": "Cooper-Frye cell*species*momentum evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.df_mode, G, world), "global_cells": G, "cells_per_gpu": cells if world == 1 else f"{G // world}..{-(-G // world)}",
+                   "evals_per_step": evals_global, "l2_policy": "inputs larger than L2 (cell packs: 256 B x cells per pass)",
+                   "parallelism": (f"one surface, cells sharded x{world} in contiguous blocks; the product all-reduces {total} doubles "
+                                   f"(ncclAllReduce inside is3d_spectra_device, {collectives} issued by rank 0)") if world > 1 else "single GPU",
+                   "species_classes": "evaluations are counted per species (444); species with identical (mass, sign, baryon "
+                                      "number) share one integrand, computed once and scaled by each species' degeneracy "
+                                      "(193 classes for the SMASH list) -- every species' bins are delivered"},
+        "e2e": {"value": evals_global / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(G * 25 * 8),
+                "d2h_bytes_per_step": int(total * 8 * world), "seconds_per_step": e2e_s,
+                "equals_value_path": bool(np.array_equal(spec.reshape(-1), value_out))},
+        "gpu_launches": int(launches),
+        "cells_skipped_frac": skipped_all / G,
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": label or "feqmod_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
+                     "what": "executed FP64-pipe instructions x 2 flops / kernel time / live DFMA peak, per GPU",
+                     "fp64_instr_per_class_eval": per_eval, "inner_loop_instructions": mix["instructions"] if mix else None,
+                     "inner_loop_sass_sha256": mix["listing_sha256"] if mix else None,
+                     "class_evals_executed_per_step": executed_all, "species_evals_delivered_per_step": evals_global * (1.0 - skipped_all / G),
+                     "peak_source": "DFMA micro-benchmark run live by is3d_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
+                     "reference_operation_count": {"flops_per_eval": F_ALG[args.df_mode], "tflops_equivalent": evals_global / world * F_ALG[args.df_mode] / kern_s / 1e12,
+                                                   "note": "SURVEY.md 8d's provisional count of the REFERENCE's loop per species-evaluation; not a roofline fraction "
+                                                           "(species classes, folded polynomials and table-driven exp execute far fewer instructions)"},
+                     "hbm_gbs_algorithmic": bytes_alg / kern_s / 1e9, "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
+        "check": check,
+        "clocks": clocks,
+    }
+    if sampler is not None:
+        line["sampler"] = sampler
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
         if sampler is not None:
-            line["sampler"] = sampler
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args)
-            if sampler is not None:
-                line["sampler"]["cpu_baseline"] = sampler_cpu_baseline(args)
-        return line
-    return None
+            line["sampler"]["cpu_baseline"] = sampler_cpu_baseline(args)
+    return line
 
 
 def main():
@@ -486,7 +582,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cells-per-gpu", type=int, default=1_250_000)
+    ap.add_argument("--cells", type=int, default=10_000_000,
+                    help="cells of THE benchmark surface (BASELINE.json config 5: 10 M), shared by all GPUs (strong scaling)")
+    ap.add_argument("--check-cells", type=int, default=64, help="cells of the oracle spot check (0 = off)")
+    ap.add_argument("--sampler-calls", type=int, default=5)
     ap.add_argument("--df-mode", type=int, default=2, choices=[1, 2, 3, 4, 5],
                     help="2 = the headline workload; 1, 3, 4, 5 time the other df corrections on the same surface")
     ap.add_argument("--ref-cells", type=int, default=5000, help="cells of the bounded CPU sample")

@@ -104,6 +104,9 @@ typedef struct {
   double  tau_pl_negative;
   double  kernel_ms;             /* device time of the dominant kernel(s) of the last call (CUDA events) */
   int64_t kernel_launches;       /* kernels launched by the last call */
+  int64_t evals_executed;        /* class-evaluations the dominant spectra kernel executed in the last call, padding slots and
+                                    idle thread columns included (df_mode 1, 2; 0 = not reported): x FP64 instructions per
+                                    evaluation (SASS) = the executed FP64-pipe work behind kernel_ms */
 } is3d_stats;
 
 /* One sampled hadron: the reference's Sampled_Particle (SampledParticle.h:32-54), same fields. */
@@ -124,6 +127,7 @@ is3d_status is3d_create(const is3d_params *p, is3d_ctx **out);
 void        is3d_destroy(is3d_ctx *ctx);
 const char *is3d_last_error(const is3d_ctx *ctx);          /* ctx may be NULL: last create error */
 const char *is3d_version(void);
+int         is3d_device_count(void);                       /* usable CUDA devices (0 when there is no driver / GPU) */
 
 /* ---- static inputs (reference: arrays built in EmissionFunction.cpp:998-1046) --------------------------------- */
 /* chosen species: Mass/Sign/Degeneracy/Baryon/MCID and the fast-mode densities (EmissionFunction.cpp:998-1021) */
@@ -213,6 +217,49 @@ void        is3d_free_particles(is3d_particle *particles);
 is3d_status is3d_sample_histograms(is3d_ctx *ctx, double *dN_dy, double *dN_deta, double *dN_dphipdy,
                                    double *dN_2pipTdpTdy, double *pT_count, double *vn_real, double *vn_imag,
                                    double *dN_taudtaudy, double *dN_twopirdrdy, double *dN_dphisdy);
+
+/* ---- multi-GPU: cells sharded, ONE all-reduce (no reference counterpart: iS3D.cpp:81-286 is one OpenMP process) --- */
+/* Every surface cell is an independent additive contribution to the spectra / dN/dX histograms / total yield and an
+ * independent Poisson source of the sampler (MomentumSpectra.cpp:99-375 sums over icell), so each GPU takes a contiguous
+ * block of cells (is3d_set_surface with global_offset) and the partial results are combined by one
+ * ncclAllReduce(sum, double) over NVLink.  NCCL is resolved at run time (dlopen libnccl.so.2); single-GPU use needs none.
+ *
+ * (1) One process per GPU (torchrun / MPI): rank 0 calls is3d_comm_unique_id, the caller ships the bytes to all ranks, every
+ *     rank calls is3d_comm_attach (collective).  Afterwards is3d_spectra[_device], is3d_dndx[_device], is3d_total_yield and
+ *     is3d_polarization return the SUM over all ranks on every rank; is3d_cell_yields and is3d_sample stay per-rank (the
+ *     sampler needs no exchange: its random streams are keyed by the global cell index). */
+#define IS3D_COMM_ID_BYTES 128
+is3d_status is3d_comm_unique_id(char id[IS3D_COMM_ID_BYTES]);
+is3d_status is3d_comm_attach(is3d_ctx *ctx, const char id[IS3D_COMM_ID_BYTES], int nranks, int rank);
+void        is3d_comm_detach(is3d_ctx *ctx);
+int         is3d_comm_size(const is3d_ctx *ctx);                 /* 1 = no communicator attached */
+int64_t     is3d_comm_collectives(const is3d_ctx *ctx);          /* all-reduces issued by this context so far */
+const char *is3d_comm_last_error(void);                          /* message of a failed is3d_comm_unique_id / is3d_group_create */
+
+/* (2) One process, several GPUs (the drop-in executable, an embedding C++ program): a group owns one context per device
+ *     and the communicator over them.  Static inputs are set per context (is3d_group_ctx(g, i), same calls as above); the
+ *     group calls split the surface into contiguous cell blocks (sizes differ by at most one cell), run one host thread per
+ *     device and return the combined result; stats are summed over the devices (kernel_ms: the slowest device). */
+typedef struct is3d_group is3d_group;
+is3d_status is3d_group_create(const is3d_params *p, int ndev, const int *devices /* NULL = 0..ndev-1 */, is3d_group **out);
+void        is3d_group_destroy(is3d_group *g);
+int         is3d_group_size(const is3d_group *g);
+is3d_ctx   *is3d_group_ctx(is3d_group *g, int i);
+const char *is3d_group_last_error(const is3d_group *g);          /* g may be NULL: last create error */
+void        is3d_group_cell_block(const is3d_group *g, int i, int64_t *begin, int64_t *count);
+is3d_status is3d_group_set_surface(is3d_group *g, int64_t n, const double *const cols[IS3D_SURFACE_COLUMNS], int64_t global_offset);
+is3d_status is3d_group_set_vorticity(is3d_group *g, int64_t n, const double *const w[6]);
+is3d_status is3d_group_spectra(is3d_group *g, double *out, is3d_stats *stats);
+is3d_status is3d_group_dndx(is3d_group *g, double *tau_hist, double *r_hist, double *phi_hist, is3d_stats *stats);
+is3d_status is3d_group_total_yield(is3d_group *g, double *ntotal, is3d_stats *stats);
+is3d_status is3d_group_polarization(is3d_group *g, double *St, double *Sx, double *Sy, double *Sn, double *Snorm, is3d_stats *stats);
+/* every device samples its cell block; the per-device lists are merged event by event in device order, which is the cell
+ * order a single GPU produces (same hadrons, same order).  The merged list is library-owned: is3d_free_particles. */
+is3d_status is3d_group_sample(is3d_group *g, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts,
+                              is3d_stats *stats);
+is3d_status is3d_group_sample_histograms(is3d_group *g, double *dN_dy, double *dN_deta, double *dN_dphipdy, double *dN_2pipTdpTdy,
+                                         double *pT_count, double *vn_real, double *vn_imag, double *dN_taudtaudy,
+                                         double *dN_twopirdrdy, double *dN_dphisdy);
 
 /* ---- measurement helpers (no reference counterpart) ---------------------------------------------------------- */
 /* sustained DFMA throughput of this GPU in TFLOP/s (2 flops per DFMA), measured with a register-resident

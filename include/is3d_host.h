@@ -39,7 +39,8 @@ void       is3d_host_set_thermo_averages(is3d_host *h, const double avg5[5]);
 void       is3d_host_prepare(is3d_host *h);
 /* the table half of is3d_host_prepare only (no GPU needed): PDG, chosen particles, df/PTB tables, densities */
 void       is3d_host_prepare_tables(is3d_host *h);
-is3d_ctx  *is3d_host_context(is3d_host *h);
+is3d_ctx  *is3d_host_context(is3d_host *h);      /* first (single-GPU runs: the only) context of the run */
+is3d_group *is3d_host_group(is3d_host *h);       /* all contexts of the run (IS3D_DEVICES) and their communicator */
 
 /* EmissionFunctionArray::calculate_spectra, writers included (results/ under root) */
 void       is3d_host_run(is3d_host *h);

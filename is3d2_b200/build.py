@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 CU_SOURCES = ["api.cu", "spectra_df.cu", "spectra_feqmod.cu", "dndx.cu", "sampler.cu", "spectra_famod.cu", "polarization.cu",
-              "fp64_peak.cu"]
+              "fp64_peak.cu", "comm.cu"]
 HOST_SOURCES = ["io.cpp", "surface.cpp", "pdg.cpp", "deltaf.cpp", "emission.cpp", "is3d.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]
@@ -57,7 +57,7 @@ def build(force: bool = False, verbose_ptxas: bool = False, variant_flags: list[
         for p in procs:
             if p.wait() != 0:
                 raise RuntimeError("nvcc failed")
-        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs)
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs + ["-ldl"])
     hostlib = os.path.join(HERE, "libis3d_host.so")
     hs = [os.path.join(HOST, f) for f in HOST_SOURCES]
     hdeps = hs + [os.path.join(HOST, "is3d_host.hpp"), os.path.join(HERE, "..", "include", "is3d_host.h"), lib] + \

@@ -34,7 +34,7 @@ class Stats(C.Structure):
                 ("newton_iterations", C.c_int64), ("cells_out_of_table", C.c_int64),
                 ("sampler_proposals", C.c_int64), ("sampler_accepted", C.c_int64),
                 ("tau_breakdown", C.c_double), ("tau_pl_negative", C.c_double), ("kernel_ms", C.c_double),
-                ("kernel_launches", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("evals_executed", C.c_int64)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -55,15 +55,20 @@ _lib = None
 _host = None
 
 # every symbol include/is3d_b200.h declares (the CPU test-suite checks the library exports all of them)
-ABI_SYMBOLS = ["is3d_default_params", "is3d_create", "is3d_destroy", "is3d_last_error", "is3d_version",
+ABI_SYMBOLS = ["is3d_default_params", "is3d_create", "is3d_destroy", "is3d_last_error", "is3d_version", "is3d_device_count",
                "is3d_set_species", "is3d_set_pdg", "is3d_set_momentum_tables", "is3d_set_gauss_tables",
                "is3d_set_thermo_averages", "is3d_set_df_tables", "is3d_set_ptb_tables", "is3d_set_surface",
                "is3d_set_surface_device", "is3d_spectra_size", "is3d_spectra", "is3d_spectra_device", "is3d_dndx",
                "is3d_dndx_device", "is3d_total_yield", "is3d_cell_yields", "is3d_sample", "is3d_free_particles",
                "is3d_sample_histograms", "is3d_set_vorticity", "is3d_polarization", "is3d_measure_fp64_peak", "is3d_probe_math",
-               "is3d_species_groups", "is3d_stream"]
+               "is3d_species_groups", "is3d_stream",
+               "is3d_comm_unique_id", "is3d_comm_attach", "is3d_comm_detach", "is3d_comm_size", "is3d_comm_collectives",
+               "is3d_comm_last_error", "is3d_group_create", "is3d_group_destroy", "is3d_group_size", "is3d_group_ctx",
+               "is3d_group_last_error", "is3d_group_cell_block", "is3d_group_set_surface", "is3d_group_set_vorticity",
+               "is3d_group_spectra", "is3d_group_dndx", "is3d_group_total_yield", "is3d_group_polarization",
+               "is3d_group_sample", "is3d_group_sample_histograms"]
 HOST_SYMBOLS = ["is3d_host_open", "is3d_host_close", "is3d_host_read_surface", "is3d_host_set_surface",
-                "is3d_host_prepare", "is3d_host_prepare_tables", "is3d_host_context", "is3d_host_run",
+                "is3d_host_prepare", "is3d_host_prepare_tables", "is3d_host_context", "is3d_host_group", "is3d_host_run",
                 "is3d_host_spectra", "is3d_host_dndx", "is3d_host_events", "is3d_host_event_particles",
                 "is3d_host_seconds", "is3d_host_stats", "is3d_host_pdg", "is3d_host_ptb",
                 "is3d_host_surface_column", "is3d_host_chosen", "is3d_host_thermo_sums", "is3d_host_set_thermo_averages"]
@@ -117,6 +122,22 @@ def load_libraries():
     host.is3d_host_prepare_tables.argtypes = [vp]
     host.is3d_host_context.restype = vp
     host.is3d_host_context.argtypes = [vp]
+    host.is3d_host_group.restype = vp
+    host.is3d_host_group.argtypes = [vp]
+    lib.is3d_device_count.restype = C.c_int
+    lib.is3d_comm_unique_id.argtypes = [vp]
+    lib.is3d_comm_attach.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.is3d_comm_detach.argtypes = [vp]
+    lib.is3d_comm_detach.restype = None
+    lib.is3d_comm_size.argtypes = [vp]
+    lib.is3d_comm_collectives.restype = C.c_int64
+    lib.is3d_comm_collectives.argtypes = [vp]
+    lib.is3d_comm_last_error.restype = C.c_char_p
+    lib.is3d_group_last_error.restype = C.c_char_p
+    lib.is3d_group_last_error.argtypes = [vp]
+    lib.is3d_group_size.argtypes = [vp]
+    lib.is3d_group_total_yield.argtypes = [vp, dp, C.POINTER(Stats)]
+    lib.is3d_group_spectra.argtypes = [vp, vp, C.POINTER(Stats)]
     host.is3d_host_run.argtypes = [vp]
     host.is3d_host_spectra.restype = C.c_int64
     host.is3d_host_spectra.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_int64)]

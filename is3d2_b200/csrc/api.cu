@@ -11,7 +11,13 @@ static thread_local std::string g_create_error;
 
 extern "C" {
 
-const char *is3d_version(void) { return "is3d_b200 0.1 (sm_100a)"; }
+const char *is3d_version(void) { return "is3d_b200 0.2 (sm_100a)"; }
+
+int is3d_device_count(void)
+{
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 void is3d_default_params(is3d_params *p)
 {
@@ -84,6 +90,7 @@ void is3d_destroy(is3d_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->prm.device);
   cudaStreamSynchronize(ctx->stream);
+  comm_release(ctx);
   for (void *p : ctx->owned) cudaFree(p);
   release_host_lists_of(ctx);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -336,16 +343,19 @@ is3d_status is3d_spectra_device(is3d_ctx *ctx, double *out_dev, is3d_stats *stat
   if (stats) std::memset(stats, 0, sizeof(*stats));
   IS3D_TRY(check_ready(ctx, ctx->prm.df_mode != 5 || true));
   const int64_t total = is3d_spectra_size(ctx);
+  is3d_status st = IS3D_OK;
   if (ctx->surf.n == 0) {
     IS3D_CUDA_TRY(ctx, cudaMemsetAsync(out_dev, 0, total * sizeof(double), ctx->stream));
-    IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return IS3D_OK;
+  } else if (ctx->prm.df_mode <= 2) {
+    st = run_spectra_df(ctx, out_dev, stats);
+  } else {
+    st = run_spectra_feqmod(ctx, out_dev, stats);
   }
-  switch (ctx->prm.df_mode) {
-    case 1: case 2: return run_spectra_df(ctx, out_dev, stats);
-    case 3: case 4: case 5: return run_spectra_feqmod(ctx, out_dev, stats);
-  }
-  return IS3D_ERR_INVALID;
+  // cells sharded over GPUs: ONE all-reduce of the spectra.  A rank that failed locally still joins the
+  // collective (its peers would otherwise wait forever) and then reports its own error.
+  const is3d_status sc = comm_allreduce(ctx, out_dev, total);
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return st != IS3D_OK ? st : sc;
 }
 
 is3d_status is3d_spectra(is3d_ctx *ctx, double *out, is3d_stats *stats)
@@ -387,10 +397,14 @@ is3d_status is3d_polarization(is3d_ctx *ctx, double *St, double *Sx, double *Sy,
   if (ctx->ns <= 0 || !ctx->have_momentum || !ctx->have_surface) { ctx->set_error("polarization: species / momentum tables / surface not set"); return IS3D_ERR_INVALID; }
   const int64_t total = is3d_spectra_size(ctx);
   double *outs[5] = {St, Sx, Sy, Sn, Snorm};
-  if (ctx->surf.n == 0) { for (double *o : outs) std::memset(o, 0, (size_t)total * sizeof(double)); return IS3D_OK; }
   void *d = nullptr;
   IS3D_TRY(ctx->get_scratch("pol_out", (size_t)5 * total * sizeof(double), &d));
-  IS3D_TRY(run_polarization(ctx, (double *)d, stats));
+  is3d_status st = IS3D_OK;
+  if (ctx->surf.n == 0) IS3D_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, (size_t)5 * total * sizeof(double), ctx->stream));
+  else st = run_polarization(ctx, (double *)d, stats);
+  const is3d_status sc = comm_allreduce(ctx, (double *)d, 5 * total);       // sharded surface: sums of the five arrays
+  if (st != IS3D_OK) return st;
+  IS3D_TRY(sc);
   for (int k = 0; k < 5; k++)
     IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(outs[k], (double *)d + (size_t)k * total, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

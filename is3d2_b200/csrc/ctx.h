@@ -35,6 +35,10 @@ struct is3d_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // timing events of the compute calls (created once, destroyed with the context)
   std::string err;
   int sm_count = 148;
+  // multi-GPU (comm.cu): NCCL communicator this context's results are summed over (nullptr = single GPU)
+  void *comm = nullptr;
+  int comm_size = 1, comm_rank = 0;
+  int64_t comm_collectives = 0;            // all-reduces issued so far
   double *d_exptab = nullptr;              // 2^(m/1024) table of fast_exp (common.cuh)
 
   // chosen species (host copies + device arrays)
@@ -91,7 +95,7 @@ struct is3d_ctx {
   std::map<std::string, double *> hist;
 
   // pinned host buffers holding particle lists handed to the caller (sampler.cu)
-  struct HostList { void *ptr = nullptr; size_t capacity = 0; bool in_use = false; is3d_ctx *owner = nullptr; };
+  struct HostList { void *ptr = nullptr; size_t capacity = 0; bool in_use = false; is3d_ctx *owner = nullptr; bool pinned = true; };
   std::vector<HostList *> host_lists;
 
   // every device allocation made by this context
@@ -168,6 +172,12 @@ is3d_status run_cell_yields(is3d_ctx *ctx, double *dn_tot_host, double *dn_list_
 is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts,
                         is3d_stats *stats);
 void release_host_lists_of(is3d_ctx *ctx);
+// a plain (pageable) library-owned list, released by is3d_free_particles like the pinned ones (merged multi-GPU lists)
+void *alloc_plain_list(size_t bytes);
+// comm.cu: in-place SUM all-reduce over the attached communicator (no-op for a single GPU)
+is3d_status comm_allreduce(is3d_ctx *ctx, double *dev, int64_t n);
+is3d_status comm_allreduce_host(is3d_ctx *ctx, double *host, int n);
+void comm_release(is3d_ctx *ctx);
 is3d_status run_polarization(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);
 is3d_status measure_fp64_peak(is3d_ctx *ctx, double *tflops);
 is3d_status probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp, double *out_sqrt);

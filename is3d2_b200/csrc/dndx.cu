@@ -511,14 +511,21 @@ is3d_status is3d_dndx_device(is3d_ctx *ctx, double *tau_dev, double *r_dev, doub
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (ctx->ns <= 0 || !ctx->have_momentum || !ctx->have_surface || !ctx->have_df) { ctx->set_error("dndx: species / tables / surface not set"); return IS3D_ERR_INVALID; }
   if (ctx->prm.df_mode == 4 && !ctx->have_ptb) { ctx->set_error("PTB tables not set"); return IS3D_ERR_INVALID; }
+  const int64_t nt = (int64_t)ctx->ns * ctx->prm.tau_bins, nr = (int64_t)ctx->ns * ctx->prm.r_bins, np = (int64_t)ctx->ns * ctx->prm.phip_bins;
+  is3d_status st = IS3D_OK;
   if (ctx->surf.n == 0) {
-    IS3D_CUDA_TRY(ctx, cudaMemsetAsync(tau_dev, 0, (size_t)ctx->ns * ctx->prm.tau_bins * sizeof(double), ctx->stream));
-    IS3D_CUDA_TRY(ctx, cudaMemsetAsync(r_dev, 0, (size_t)ctx->ns * ctx->prm.r_bins * sizeof(double), ctx->stream));
-    IS3D_CUDA_TRY(ctx, cudaMemsetAsync(phi_dev, 0, (size_t)ctx->ns * ctx->prm.phip_bins * sizeof(double), ctx->stream));
-    IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return IS3D_OK;
+    IS3D_CUDA_TRY(ctx, cudaMemsetAsync(tau_dev, 0, (size_t)nt * sizeof(double), ctx->stream));
+    IS3D_CUDA_TRY(ctx, cudaMemsetAsync(r_dev, 0, (size_t)nr * sizeof(double), ctx->stream));
+    IS3D_CUDA_TRY(ctx, cudaMemsetAsync(phi_dev, 0, (size_t)np * sizeof(double), ctx->stream));
+  } else {
+    st = is3d::run_dndx(ctx, tau_dev, r_dev, phi_dev, stats);
   }
-  return is3d::run_dndx(ctx, tau_dev, r_dev, phi_dev, stats);
+  // sharded surface: the three histograms are summed over the GPUs (a failed rank still joins, see is3d_spectra_device)
+  is3d_status sc = is3d::comm_allreduce(ctx, tau_dev, nt);
+  if (sc == IS3D_OK) sc = is3d::comm_allreduce(ctx, r_dev, nr);
+  if (sc == IS3D_OK) sc = is3d::comm_allreduce(ctx, phi_dev, np);
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return st != IS3D_OK ? st : sc;
 }
 
 is3d_status is3d_dndx(is3d_ctx *ctx, double *tau_hist, double *r_hist, double *phi_hist, is3d_stats *stats)

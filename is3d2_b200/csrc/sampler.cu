@@ -639,9 +639,20 @@ static bool release_host_list(void *ptr)
   is3d_ctx::HostList *h = it->second;
   if (h->owner) { h->in_use = false; return true; }         // back to its context's pool
   g_lists.erase(it);
-  cudaFreeHost(h->ptr);
+  if (h->pinned) cudaFreeHost(h->ptr); else free(h->ptr);
   delete h;
   return true;
+}
+
+void *alloc_plain_list(size_t bytes)
+{
+  void *p = malloc(bytes ? bytes : 8);
+  if (!p) return nullptr;
+  auto *h = new is3d_ctx::HostList;
+  h->ptr = p; h->capacity = bytes; h->in_use = true; h->owner = nullptr; h->pinned = false;
+  std::lock_guard<std::mutex> lock(g_list_mutex);
+  g_lists[p] = h;
+  return p;
 }
 
 // bounds the record scratch to ~27 GB (test hook: IS3D_SAMPLER_PASS_PROPOSALS)
@@ -826,8 +837,12 @@ is3d_status is3d_total_yield(is3d_ctx *ctx, double *ntotal, is3d_stats *stats)
   if (!ntotal) { ctx->set_error("total_yield: NULL output"); return IS3D_ERR_INVALID; }
   if (stats) std::memset(stats, 0, sizeof(*stats));
   IS3D_TRY(sampler_ready(ctx));
-  if (ctx->surf.n == 0) { *ntotal = 0.0; return IS3D_OK; }
-  return is3d::run_total_yield(ctx, ntotal, stats);
+  is3d_status st = IS3D_OK;
+  *ntotal = 0.0;
+  if (ctx->surf.n != 0) st = is3d::run_total_yield(ctx, ntotal, stats);
+  // sharded surface: Nevents = f(total yield) must be the same on every GPU before sampling
+  const is3d_status sc = is3d::comm_allreduce_host(ctx, ntotal, 1);
+  return st != IS3D_OK ? st : sc;
 }
 
 is3d_status is3d_cell_yields(is3d_ctx *ctx, double *dn_tot, double *dn_list, is3d_stats *stats)

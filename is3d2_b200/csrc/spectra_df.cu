@@ -409,6 +409,9 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     stats->cells_out_of_table = (int64_t)h_counters[1];
     stats->kernel_ms = ms_total;
     stats->kernel_launches = launches;
+    // every valid cell is one item per (y, phi, eta) block row, evaluated by all nslices x kThreads thread columns x R slots
+    stats->evals_executed = (n - (int64_t)h_counters[0] - (int64_t)h_counters[1]) * (int64_t)nslices * kThreads * kDfBinsPerThread *
+                            ctx->Ny * ctx->Nphi * ctx->Neta;
   }
   if (h_counters[1] != 0) {
     ctx->set_error(std::to_string(h_counters[1]) + " cell(s) outside the df coefficient tables (the reference aborts here)");

@@ -21,7 +21,7 @@ void EmissionFunctionArray::check(is3d_status st, const char *what)
 {
   if (st == IS3D_OK) return;
   // the reference's convention: print and exit(-1) (GSL domain errors abort)
-  printf("%s error: %s\n", what, is3d_last_error(ctx));
+  printf("%s error: %s\n", what, grp && *is3d_group_last_error(grp) ? is3d_group_last_error(grp) : is3d_last_error(ctx));
   fflush(stdout);
   if (st == IS3D_ERR_TABLE_RANGE && !prm.include_baryon) abort();
   exit(-1);
@@ -101,9 +101,13 @@ EmissionFunctionArray::EmissionFunctionArray(ParameterReader *paraRdr_in, Table 
 
   dN_pTdpTdphidy.assign((size_t)number_of_chosen_particles * pT_tab_length * phi_tab_length * y_tab_length, 0.0);
 
-  // ---- one CUDA context holding every static input ----
-  is3d_status st = is3d_create(&prm, &ctx);
-  if (st != IS3D_OK) fatal(std::string("is3d_create error: ") + is3d_last_error(nullptr));
+  // ---- one CUDA context per GPU, each holding every static input; cells are sharded over them ----
+  // IS3D_DEVICES = "all" | "0-7" | "0,2,3" selects the GPUs of this run (default: the single device IS3D_DEVICE, else 0)
+  std::vector<int> devices = parse_device_list(getenv("IS3D_DEVICES"), prm.device);
+  is3d_status st = is3d_group_create(&prm, (int)devices.size(), devices.data(), &grp);
+  if (st != IS3D_OK) fatal(std::string("is3d_create error: ") + is3d_group_last_error(nullptr));
+  if (devices.size() > 1) printf("Sharding the freezeout surface over %d GPUs (one NCCL all-reduce per result)\n", (int)devices.size());
+  ctx = is3d_group_ctx(grp, 0);
 
   const int ns = number_of_chosen_particles;
   std::vector<double> Mass(ns), Sign(ns), Degeneracy(ns), Baryon(ns), Neq(ns), Dnb(ns), Dnd(ns);
@@ -113,52 +117,54 @@ EmissionFunctionArray::EmissionFunctionArray(ParameterReader *paraRdr_in, Table 
     Mass[i] = p.mass; Sign[i] = p.sign; Degeneracy[i] = p.gspin; Baryon[i] = p.baryon; MCID[i] = (int)p.mc_id;
     Neq[i] = p.equilibrium_density; Dnb[i] = p.bulk_density; Dnd[i] = p.diff_density;
   }
-  check(is3d_set_species(ctx, ns, Mass.data(), Sign.data(), Degeneracy.data(), Baryon.data(), MCID.data(), Neq.data(),
-                         Dnb.data(), Dnd.data()), "is3d_set_species");
-  const int np = (int)particles->size();
-  std::vector<double> Mp(np), Sp(np), Dp(np), Bp(np);
-  for (int i = 0; i < np; i++) { const particle_info &p = (*particles)[i]; Mp[i] = p.mass; Sp[i] = p.sign; Dp[i] = p.gspin; Bp[i] = p.baryon; }
-  check(is3d_set_pdg(ctx, np, Mp.data(), Sp.data(), Dp.data(), Bp.data()), "is3d_set_pdg");
-
-  check(is3d_set_momentum_tables(ctx, (int)pT_tab->getNumberOfRows(), pT_tab->column(1).data(), pT_tab->column(2).data(),
-                                 (int)phi_tab->getNumberOfRows(), phi_tab->column(1).data(), phi_tab->column(2).data(),
-                                 (int)y_tab->getNumberOfRows(), y_tab->column(1).data(), y_tab->column(2).data(),
-                                 (int)eta_tab->getNumberOfRows(), eta_tab->column(1).data(), eta_tab->column(2).data()),
-        "is3d_set_momentum_tables");
-
   Gauss_Laguerre gla;
   Gauss_Legendre legendre;
   gla.load_roots_and_weights("tables/gauss/gla_roots_weights.txt");
   legendre.load_roots_and_weights("tables/gauss/gauss_legendre.dat");
-  check(is3d_set_gauss_tables(ctx, gla.alpha, gla.points, gla.root.data(), gla.weight.data(), legendre.points,
-                              legendre.root.data(), legendre.weight.data()), "is3d_set_gauss_tables");
   Plasma QGP;
   QGP.load_thermodynamic_averages();
-  check(is3d_set_thermo_averages(ctx, QGP.temperature, QGP.energy_density, QGP.pressure, QGP.baryon_chemical_potential,
-                                 QGP.net_baryon_density), "is3d_set_thermo_averages");
-  check(is3d_set_df_tables(ctx, df_data->points_T, df_data->points_muB, df_data->T_array.data(), df_data->muB_array.data(),
-                           df_data->tab[0].data(), df_data->tab[1].data(), df_data->tab[2].data(), df_data->tab[3].data(),
-                           df_data->tab[4].data(), df_data->tab[5].data(), df_data->tab[6].data(), df_data->tab[7].data(),
-                           df_data->tab[8].data(), df_data->tab[9].data()), "is3d_set_df_tables");
-  if (df_data->have_jonah)
-    check(is3d_set_ptb_tables(ctx, Deltaf_Data::jonah_points, df_data->bulkPi_over_Peq_array.data(),
-                              df_data->lambda_squared_array.data(), df_data->z_array.data(), df_data->bulkPi_over_Peq_max),
-          "is3d_set_ptb_tables");
+  const int np = (int)particles->size();
+  std::vector<double> Mp(np), Sp(np), Dp(np), Bp(np);
+  for (int i = 0; i < np; i++) { const particle_info &p = (*particles)[i]; Mp[i] = p.mass; Sp[i] = p.sign; Dp[i] = p.gspin; Bp[i] = p.baryon; }
+  for (int d = 0; d < is3d_group_size(grp); d++) {
+    is3d_ctx *c = ctx = is3d_group_ctx(grp, d);      // `check` reports the failing context's message
+    check(is3d_set_species(c, ns, Mass.data(), Sign.data(), Degeneracy.data(), Baryon.data(), MCID.data(), Neq.data(),
+                           Dnb.data(), Dnd.data()), "is3d_set_species");
+    check(is3d_set_pdg(c, np, Mp.data(), Sp.data(), Dp.data(), Bp.data()), "is3d_set_pdg");
+    check(is3d_set_momentum_tables(c, (int)pT_tab->getNumberOfRows(), pT_tab->column(1).data(), pT_tab->column(2).data(),
+                                   (int)phi_tab->getNumberOfRows(), phi_tab->column(1).data(), phi_tab->column(2).data(),
+                                   (int)y_tab->getNumberOfRows(), y_tab->column(1).data(), y_tab->column(2).data(),
+                                   (int)eta_tab->getNumberOfRows(), eta_tab->column(1).data(), eta_tab->column(2).data()),
+          "is3d_set_momentum_tables");
+    check(is3d_set_gauss_tables(c, gla.alpha, gla.points, gla.root.data(), gla.weight.data(), legendre.points,
+                                legendre.root.data(), legendre.weight.data()), "is3d_set_gauss_tables");
+    check(is3d_set_thermo_averages(c, QGP.temperature, QGP.energy_density, QGP.pressure, QGP.baryon_chemical_potential,
+                                   QGP.net_baryon_density), "is3d_set_thermo_averages");
+    check(is3d_set_df_tables(c, df_data->points_T, df_data->points_muB, df_data->T_array.data(), df_data->muB_array.data(),
+                             df_data->tab[0].data(), df_data->tab[1].data(), df_data->tab[2].data(), df_data->tab[3].data(),
+                             df_data->tab[4].data(), df_data->tab[5].data(), df_data->tab[6].data(), df_data->tab[7].data(),
+                             df_data->tab[8].data(), df_data->tab[9].data()), "is3d_set_df_tables");
+    if (df_data->have_jonah)
+      check(is3d_set_ptb_tables(c, Deltaf_Data::jonah_points, df_data->bulkPi_over_Peq_array.data(),
+                                df_data->lambda_squared_array.data(), df_data->z_array.data(), df_data->bulkPi_over_Peq_max),
+            "is3d_set_ptb_tables");
+  }
+  ctx = is3d_group_ctx(grp, 0);
   if (surf) set_surface_on_device();
 }
 
-EmissionFunctionArray::~EmissionFunctionArray() { is3d_destroy(ctx); }
+EmissionFunctionArray::~EmissionFunctionArray() { is3d_group_destroy(grp); }
 
 void EmissionFunctionArray::set_surface_on_device()
 {
   const double *cols[IS3D_SURFACE_COLUMNS];
   for (int k = 0; k < IS3D_SURFACE_COLUMNS; k++) cols[k] = surf->col[k].data();
-  check(is3d_set_surface(ctx, surf->size(), cols, 0), "is3d_set_surface");
+  check(is3d_group_set_surface(grp, surf->size(), cols, 0), "is3d_set_surface");
 }
 
 void EmissionFunctionArray::calculate_dN_pTdpTdphidy()
 {
-  check(is3d_spectra(ctx, dN_pTdpTdphidy.data(), &stats), "calculate_dN_pTdpTdphidy");
+  check(is3d_group_spectra(grp, dN_pTdpTdphidy.data(), &stats), "calculate_dN_pTdpTdphidy");
   if (DF_MODE == 3 || DF_MODE == 4) {
     printf("\nfeqmod breaks down for %ld / %ld cells until t = %.3f fm/c\n", (long)stats.cells_breakdown, (long)stats.cells_total, stats.tau_breakdown);
     printf("pl went negative for %ld / %ld cells until t = %.3f fm/c\n\n", (long)stats.cells_pl_negative, (long)stats.cells_total, stats.tau_pl_negative);
@@ -176,7 +182,7 @@ void EmissionFunctionArray::calculate_dN_dX()
   dN_taudtaudy.assign((size_t)ns * prm.tau_bins, 0.0);
   dN_twopirdrdy.assign((size_t)ns * prm.r_bins, 0.0);
   dN_dphisdy.assign((size_t)ns * prm.phip_bins, 0.0);
-  check(is3d_dndx(ctx, dN_taudtaudy.data(), dN_twopirdrdy.data(), dN_dphisdy.data(), &stats), "calculate_dN_dX");
+  check(is3d_group_dndx(grp, dN_taudtaudy.data(), dN_twopirdrdy.data(), dN_dphisdy.data(), &stats), "calculate_dN_dX");
   if (prm.dndx_bug_compat) {
     // The reference clears its per-species accumulators with memset(ptr, 0.0, CORES * bins): `bins` BYTES, i.e. only
     // the first bins/8 doubles (SpacetimeDistribution.cpp:166-168, :671-673).  Every later bin keeps the previous
@@ -198,7 +204,7 @@ void EmissionFunctionArray::calculate_dN_dX()
 double EmissionFunctionArray::calculate_total_yield()
 {
   double ntot = 0.0;
-  check(is3d_total_yield(ctx, &ntot, &stats), "calculate_total_yield");
+  check(is3d_group_total_yield(grp, &ntot, &stats), "calculate_total_yield");
   return ntot;
 }
 
@@ -207,7 +213,7 @@ void EmissionFunctionArray::sample_dN_pTdpTdphidy()
   is3d_particle *plist = nullptr;
   int64_t total = 0;
   std::vector<int64_t> counts(Nevents, 0);
-  check(is3d_sample(ctx, Nevents, &plist, &total, counts.data(), &stats), "sample_dN_pTdpTdphidy");
+  check(is3d_group_sample(grp, Nevents, &plist, &total, counts.data(), &stats), "sample_dN_pTdpTdphidy");
   particle_event_list.assign(Nevents, {});
   for (long e = 0; e < Nevents; e++) particle_event_list[e].reserve(counts[e]);
   for (int64_t i = 0; i < total; i++) {
@@ -284,11 +290,11 @@ void EmissionFunctionArray::calculate_spin_polzn()
   if (surf->vorticity[0].size() != (size_t)surf->size()) fatal("calculate_spin_polzn error: the surface carries no thermal vorticity (mode 5 file needed)");
   const double *w[6];
   for (int k = 0; k < 6; k++) w[k] = surf->vorticity[k].data();
-  check(is3d_set_vorticity(ctx, surf->size(), w), "is3d_set_vorticity");
+  check(is3d_group_set_vorticity(grp, surf->size(), w), "is3d_set_vorticity");
   const size_t total = (size_t)is3d_spectra_size(ctx);
   for (auto *v : {&St, &Sx, &Sy, &Sn, &Snorm}) v->assign(total, 0.0);
   is3d_stats pst;
-  check(is3d_polarization(ctx, St.data(), Sx.data(), Sy.data(), Sn.data(), Snorm.data(), &pst), "calculate_spin_polzn");
+  check(is3d_group_polarization(grp, St.data(), Sx.data(), Sy.data(), Sn.data(), Snorm.data(), &pst), "calculate_spin_polzn");
 }
 
 // write_polzn_vector_toFile (EmissionFunction.cpp:561-609): results/{St,Sx,Sy,Sn}.dat, rows `y phip pT S/Snorm`, loop order
@@ -525,7 +531,7 @@ void EmissionFunctionArray::write_sampled_tests_to_file()
       dN_pT((size_t)ns * prm.pT_bins), pT_count((size_t)ns * prm.pT_bins), vn_re((size_t)K * ns * prm.pT_bins),
       vn_im((size_t)K * ns * prm.pT_bins), dN_tau((size_t)ns * prm.tau_bins), dN_r((size_t)ns * prm.r_bins),
       dN_phis((size_t)ns * prm.phip_bins);
-  check(is3d_sample_histograms(ctx, dN_dy.data(), dN_deta.data(), dN_dphip.data(), dN_pT.data(), pT_count.data(), vn_re.data(),
+  check(is3d_group_sample_histograms(grp, dN_dy.data(), dN_deta.data(), dN_dphip.data(), dN_pT.data(), pT_count.data(), vn_re.data(),
                                vn_im.data(), dN_tau.data(), dN_r.data(), dN_phis.data()), "is3d_sample_histograms");
   const double Y_CUT = prm.y_cut, nev = (double)Nevents;
   const double Y_WIDTH = 2.0 * Y_CUT / (double)prm.y_bins, ETA_WIDTH = 2.0 * prm.eta_cut / (double)prm.eta_bins;

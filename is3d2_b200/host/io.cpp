@@ -25,6 +25,36 @@ std::string path(const std::string &relative) { return g_root + relative; }
 
 double two_pi2_hbarC3() { return 2.0 * pow(M_PI, 2) * pow(hbarC, 3); }
 
+std::vector<int> parse_device_list(const char *spec, int fallback)
+{
+  std::vector<int> out;
+  if (!spec || !*spec) { out.push_back(fallback); return out; }
+  std::string s(spec);
+  if (s == "all") {
+    const int n = is3d_device_count();
+    for (int i = 0; i < (n > 0 ? n : 1); i++) out.push_back(i);
+    return out;
+  }
+  size_t pos = 0;
+  while (pos < s.size()) {
+    size_t comma = s.find(',', pos);
+    std::string tok = s.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+    size_t dash = tok.find('-');
+    if (tok.empty()) fatal("IS3D_DEVICES: empty entry in \"" + s + "\"");
+    if (dash != std::string::npos && dash > 0) {
+      int a = atoi(tok.substr(0, dash).c_str()), b = atoi(tok.substr(dash + 1).c_str());
+      if (b < a) fatal("IS3D_DEVICES: bad range \"" + tok + "\"");
+      for (int i = a; i <= b; i++) out.push_back(i);
+    } else {
+      out.push_back(atoi(tok.c_str()));
+    }
+    if (comma == std::string::npos) break;
+    pos = comma + 1;
+  }
+  if (out.empty()) out.push_back(fallback);
+  return out;
+}
+
 void fatal(const std::string &message)
 {
   printf("%s\n", message.c_str());

@@ -160,6 +160,7 @@ void is3d_host_set_thermo_averages(is3d_host *h, const double avg5[5]) { ENTER(h
 void is3d_host_prepare_tables(is3d_host *h) { ENTER(h); h->s.prepare_tables(); }
 void is3d_host_prepare(is3d_host *h) { ENTER(h); h->s.create_context(); }
 is3d_ctx *is3d_host_context(is3d_host *h) { return h->s.efa ? h->s.efa->context() : nullptr; }
+is3d_group *is3d_host_group(is3d_host *h) { return h->s.efa ? h->s.efa->group() : nullptr; }
 void is3d_host_run(is3d_host *h) { ENTER(h); h->s.run(); }
 int64_t is3d_host_spectra(is3d_host *h, const double **data, int64_t dims[4])
 {

@@ -30,6 +30,8 @@ void set_root(const std::string &root);
 std::string path(const std::string &relative);
 
 [[noreturn]] void fatal(const std::string &message);   // printf + exit(-1), the reference's error convention
+// "all" | "0-7" | "0,2,3" -> CUDA ordinals; NULL / empty -> {fallback}
+std::vector<int> parse_device_list(const char *spec, int fallback);
 
 class ParameterReader {
  public:
@@ -185,6 +187,7 @@ class EmissionFunctionArray {
   void write_sampled_tests_to_file();
 
   is3d_ctx *context() { return ctx; }
+  is3d_group *group() { return grp; }
   void set_surface_on_device();             // (re)upload the SoA surface
 
   std::vector<double> dN_pTdpTdphidy;       // Ns*NpT*Nphi*Ny, same indexing as the reference
@@ -203,7 +206,8 @@ class EmissionFunctionArray {
   void check(is3d_status st, const char *what);
   ParameterReader *paraRdr;
   is3d_params prm{};
-  is3d_ctx *ctx = nullptr;
+  is3d_group *grp = nullptr;                // one context per GPU of this run (IS3D_DEVICES); owns the communicator
+  is3d_ctx *ctx = nullptr;                  // the group's first context (single-GPU runs: the only one)
   int OPERATION, MODE, DF_MODE, DIMENSION, OVERSAMPLE, TEST_SAMPLER;
   double MIN_NUM_HADRONS, MAX_NUM_SAMPLES;
   Table *pT_tab, *phi_tab, *y_tab, *eta_tab;

@@ -9,7 +9,7 @@ bash tools/final_numbers.sh
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench_default.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 N="ncu --set full --clock-control none --import-source on -f"
 $N -k regex:df_spectra_kernel -s 3 -c 1 -o $O/prof_u_k1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sampler > /dev/null 2>&1
-$N -k regex:feqmod_spectra_kernel -s 3 -c 1 -o $O/prof_u_k2 python bench.py --df-mode 3 --steps 1 --warmup 3 --cells-per-gpu 200000 --no-cpu-baseline --no-sampler > /dev/null 2>&1
+$N -k regex:feqmod_spectra_kernel -s 3 -c 1 -o $O/prof_u_k2 python bench.py --df-mode 3 --steps 1 --warmup 3 --cells 200000 --no-cpu-baseline --no-sampler > /dev/null 2>&1
 $N -k regex:dndx_df_kernel -c 1 -o $O/prof_u_k4 python tools/dndx_probe.py 2 50000 > /dev/null 2>&1
 $N -k regex:dndx_feqmod_kernel -c 1 -o $O/prof_u_k4m3 python tools/dndx_probe.py 3 50000 > /dev/null 2>&1
 ls -la $O/*.ncu-rep

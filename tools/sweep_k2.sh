@@ -6,7 +6,7 @@ for R in "$@"; do
   touch is3d2_b200/csrc/spectra_feqmod.cu
   python tools/build_variant.py -DIS3D_K2_R=$R > /dev/null 2>&1 || { echo "R=$R build failed" >> $out; continue; }
   for M in ${MODES:-3 4 5}; do
-    python bench.py --steps 2 --warmup 2 --cells-per-gpu ${CELLS:-300000} --df-mode $M --no-cpu-baseline --no-sampler 2>/dev/null | grep '^{' | python -c "
+    python bench.py --steps 2 --warmup 2 --cells ${CELLS:-300000} --df-mode $M --no-cpu-baseline --no-sampler 2>/dev/null | grep '^{' | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('R=$R df_mode=$M', '%.4g evals/s' % d['value'], 'ms/step %.2f' % d['ms_per_step'], 'spectra kernel ms/step %.2f' % d['roofline']['kernel_ms_per_step'])" >> $out
   done

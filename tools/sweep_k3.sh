@@ -6,7 +6,7 @@ for v in "$@"; do
   touch is3d2_b200/csrc/spectra_famod.cu
   python tools/build_variant.py -DIS3D_K3_MINBLOCKS=$1 -DIS3D_K3_UNROLL=$2 > /dev/null 2>&1 || { echo "B=$1 U=$2 build failed" >> $out; continue; }
   regs=$(cuobjdump -res-usage is3d2_b200/build/spectra_famod.cu.o | grep -A1 famod_setup_free | grep -o "REG:[0-9]*")
-  python bench.py --df-mode 5 --steps 2 --warmup 2 --cells-per-gpu 200000 --no-cpu-baseline --no-sampler 2>/dev/null | grep '^{' | python -c "
+  python bench.py --df-mode 5 --steps 2 --warmup 2 --cells 200000 --no-cpu-baseline --no-sampler 2>/dev/null | grep '^{' | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('minblocks=$1 unroll=$2 $regs', '%.4g evals/s' % d['value'], 'ms/step %.1f' % d['ms_per_step'])" >> $out
 done
