@@ -82,8 +82,9 @@ typedef struct {
                                     reference does for a cell without a previous solution (MomentumSpectra.cpp:1288-1313):
                                     cells independent, shardable; 1 = the reference's serial chain (previous cell's solution,
                                     :1308-1364) walked by ONE warp -- bit-level parity runs on one GPU only */
-  int dndx_bug_compat;           /* 1 = reproduce the reference's partial memset (SpacetimeDistribution.cpp:166-168):
-                                    histograms accumulate over species above bin CORES*bins/8 */
+  int dndx_bug_compat;           /* 1 = is3d_dndx (host output) reproduces the reference's partial memset
+                                    (SpacetimeDistribution.cpp:166-168): histograms accumulate over species above bin
+                                    CORES*bins/8; is3d_dndx_device always returns the clean per-species histograms */
   int polzn_chunk_compat;        /* 0 (default) = every cell reads its own thermal vorticity; 1 = the reference's index INSIDE
                                     its 10 000-cell chunk (Polarization.cpp:125-130 use wtx_fo[icell], not [icell_glb]):
                                     identical for surfaces of up to 10 000 cells, unsharded surfaces only */
@@ -120,6 +121,16 @@ typedef struct {
   double t, z;
   double E, px, py, pz;
 } is3d_particle;
+
+/* The same hadron as a 64-byte wire record (is3d_sample_compact): everything that is not a function of the other fields.
+ * mass and mcid follow from chosen_index (the species arrays of is3d_set_species), E from the mass shell, (t, z) from
+ * (tau, eta); is3d_expand_particles restores the full record.  The list is PCIe-bound: 64 instead of 104 bytes per hadron. */
+typedef struct {
+  int32_t chosen_index;
+  int32_t event;
+  double tau, x, y, eta;
+  double px, py, pz;
+} is3d_particle_compact;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 void        is3d_default_params(is3d_params *p);
@@ -211,7 +222,17 @@ is3d_status is3d_cell_yields(is3d_ctx *ctx, double *dn_tot, double *dn_list, is3
  * reused by later calls on the same context. */
 is3d_status is3d_sample(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total,
                         int64_t *counts, is3d_stats *stats);
-void        is3d_free_particles(is3d_particle *particles);
+void        is3d_free_particles(void *particles);   /* any host list handed out by is3d_sample / _compact / is3d_group_sample */
+/* same sampling (same hadrons, same order), delivered as 64-byte wire records in a library-owned pinned host array */
+is3d_status is3d_sample_compact(is3d_ctx *ctx, int64_t nevents, is3d_particle_compact **particles, int64_t *total,
+                                int64_t *counts, is3d_stats *stats);
+/* same sampling, the full records left in a library-owned DEVICE array for a device-resident consumer (valid until the next
+ * sampler call on this context; never copied to the host).  The context's cells must fit one sampler pass (16 M cells). */
+is3d_status is3d_sample_device(is3d_ctx *ctx, int64_t nevents, const is3d_particle **particles_dev, int64_t *total,
+                               int64_t *counts, is3d_stats *stats);
+/* host-side expansion of n wire records into full records (multi-threaded); E, t, z agree with the device-computed fields of
+ * is3d_sample to rounding (a few ulp) */
+is3d_status is3d_expand_particles(const is3d_ctx *ctx, const is3d_particle_compact *compact, int64_t n, is3d_particle *out);
 /* sampler self-test histograms (BinSampledParticle.cpp): filled on the device during is3d_sample when
  * test_sampler = 1.  Each output is Ns x bins row-major (vn: 7 x Ns x pT_bins); pass NULL to skip one. */
 is3d_status is3d_sample_histograms(is3d_ctx *ctx, double *dN_dy, double *dN_deta, double *dN_dphipdy,
@@ -257,6 +278,8 @@ is3d_status is3d_group_polarization(is3d_group *g, double *St, double *Sx, doubl
  * order a single GPU produces (same hadrons, same order).  The merged list is library-owned: is3d_free_particles. */
 is3d_status is3d_group_sample(is3d_group *g, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts,
                               is3d_stats *stats);
+is3d_status is3d_group_sample_compact(is3d_group *g, int64_t nevents, is3d_particle_compact **particles, int64_t *total,
+                                      int64_t *counts, is3d_stats *stats);
 is3d_status is3d_group_sample_histograms(is3d_group *g, double *dN_dy, double *dN_deta, double *dN_dphipdy, double *dN_2pipTdpTdy,
                                          double *pT_count, double *vn_real, double *vn_imag, double *dN_taudtaudy,
                                          double *dN_twopirdrdy, double *dN_dphisdy);

@@ -51,6 +51,9 @@ PARTICLE_DTYPE = np.dtype([("chosen_index", "<i4"), ("mcid", "<i4"), ("event", "
                            ("mass", "<f8"), ("tau", "<f8"), ("x", "<f8"), ("y", "<f8"), ("eta", "<f8"), ("t", "<f8"),
                            ("z", "<f8"), ("E", "<f8"), ("px", "<f8"), ("py", "<f8"), ("pz", "<f8")])
 
+COMPACT_DTYPE = np.dtype([("chosen_index", "<i4"), ("event", "<i4"), ("tau", "<f8"), ("x", "<f8"), ("y", "<f8"), ("eta", "<f8"),
+                          ("px", "<f8"), ("py", "<f8"), ("pz", "<f8")])
+
 _lib = None
 _host = None
 
@@ -59,14 +62,14 @@ ABI_SYMBOLS = ["is3d_default_params", "is3d_create", "is3d_destroy", "is3d_last_
                "is3d_set_species", "is3d_set_pdg", "is3d_set_momentum_tables", "is3d_set_gauss_tables",
                "is3d_set_thermo_averages", "is3d_set_df_tables", "is3d_set_ptb_tables", "is3d_set_surface",
                "is3d_set_surface_device", "is3d_spectra_size", "is3d_spectra", "is3d_spectra_device", "is3d_dndx",
-               "is3d_dndx_device", "is3d_total_yield", "is3d_cell_yields", "is3d_sample", "is3d_free_particles",
+               "is3d_dndx_device", "is3d_total_yield", "is3d_cell_yields", "is3d_sample", "is3d_free_particles", "is3d_sample_compact", "is3d_sample_device", "is3d_expand_particles",
                "is3d_sample_histograms", "is3d_set_vorticity", "is3d_polarization", "is3d_measure_fp64_peak", "is3d_probe_math",
                "is3d_species_groups", "is3d_stream",
                "is3d_comm_unique_id", "is3d_comm_attach", "is3d_comm_detach", "is3d_comm_size", "is3d_comm_collectives",
                "is3d_comm_last_error", "is3d_group_create", "is3d_group_destroy", "is3d_group_size", "is3d_group_ctx",
                "is3d_group_last_error", "is3d_group_cell_block", "is3d_group_set_surface", "is3d_group_set_vorticity",
                "is3d_group_spectra", "is3d_group_dndx", "is3d_group_total_yield", "is3d_group_polarization",
-               "is3d_group_sample", "is3d_group_sample_histograms"]
+               "is3d_group_sample", "is3d_group_sample_compact", "is3d_group_sample_histograms"]
 HOST_SYMBOLS = ["is3d_host_open", "is3d_host_close", "is3d_host_read_surface", "is3d_host_set_surface",
                 "is3d_host_prepare", "is3d_host_prepare_tables", "is3d_host_context", "is3d_host_group", "is3d_host_run",
                 "is3d_host_spectra", "is3d_host_dndx", "is3d_host_events", "is3d_host_event_particles",
@@ -104,6 +107,10 @@ def load_libraries():
     lib.is3d_cell_yields.argtypes = [vp, vp, vp, C.POINTER(Stats)]
     lib.is3d_sample.argtypes = [vp, C.c_int64, C.POINTER(vp), C.POINTER(C.c_int64), vp, C.POINTER(Stats)]
     lib.is3d_free_particles.argtypes = [vp]
+    lib.is3d_free_particles.restype = None
+    lib.is3d_sample_compact.argtypes = [vp, C.c_int64, C.POINTER(vp), C.POINTER(C.c_int64), vp, C.POINTER(Stats)]
+    lib.is3d_sample_device.argtypes = [vp, C.c_int64, C.POINTER(vp), C.POINTER(C.c_int64), vp, C.POINTER(Stats)]
+    lib.is3d_expand_particles.argtypes = [vp, vp, C.c_int64, vp]
     lib.is3d_sample_histograms.argtypes = [vp] + [vp] * 10
     lib.is3d_measure_fp64_peak.argtypes = [vp, dp]
     lib.is3d_set_vorticity.argtypes = [vp, C.c_int64, C.POINTER(vp)]
@@ -363,22 +370,24 @@ def _abi_cell_yields(self, n_cells: int, n_species: int, with_list: bool = True)
     return tot, lst, st
 
 
-def _abi_sample(self, nevents: int, copy: bool = True):
+def _abi_sample(self, nevents: int, copy: bool = True, compact: bool = False):
     """Returns (structured particle array grouped by event, counts per event, stats).  copy=False returns a view of the
-    library-owned pinned list plus a release callable as a 4th item (the caller must call it when done)."""
+    library-owned pinned list plus a release callable as a 4th item (the caller must call it when done).  compact=True:
+    64-byte wire records (is3d_sample_compact)."""
     plist = C.c_void_p()
     total = C.c_int64()
     counts = np.zeros(nevents, dtype=np.int64)
     st = Stats()
-    self._check(self.lib.is3d_sample(self.ctx, nevents, C.byref(plist), C.byref(total), _ptr(counts), C.byref(st)), "is3d_sample")
+    fn, dt = (self.lib.is3d_sample_compact, COMPACT_DTYPE) if compact else (self.lib.is3d_sample, PARTICLE_DTYPE)
+    self._check(fn(self.ctx, nevents, C.byref(plist), C.byref(total), _ptr(counts), C.byref(st)), "is3d_sample")
     n = total.value
     if plist.value and n:
-        buf = (C.c_char * (n * PARTICLE_DTYPE.itemsize)).from_address(plist.value)
-        arr = np.frombuffer(buf, dtype=PARTICLE_DTYPE)
+        buf = (C.c_char * (n * dt.itemsize)).from_address(plist.value)
+        arr = np.frombuffer(buf, dtype=dt)
         if copy:
             arr = arr.copy()
     else:
-        arr = np.zeros(0, dtype=PARTICLE_DTYPE)
+        arr = np.zeros(0, dtype=dt)
     lib = self.lib
 
     def release(ptr=plist):
@@ -404,5 +413,30 @@ def _abi_sample_histograms(self, ns: int, params: dict):
 
 HostSession.abi_total_yield = _abi_total_yield
 HostSession.abi_cell_yields = _abi_cell_yields
+def _abi_sample_compact(self, nevents: int, copy: bool = True):
+    return _abi_sample(self, nevents, copy=copy, compact=True)
+
+
+def _abi_expand(self, compact: np.ndarray) -> np.ndarray:
+    """is3d_expand_particles: wire records -> full records."""
+    c = np.ascontiguousarray(compact)
+    out = np.zeros(len(c), dtype=PARTICLE_DTYPE)
+    self._check(self.lib.is3d_expand_particles(self.ctx, _ptr(c), len(c), _ptr(out)), "is3d_expand_particles")
+    return out
+
+
+def _abi_sample_device(self, nevents: int):
+    """(device pointer of the library-owned record array, total, counts per event, stats)"""
+    plist = C.c_void_p()
+    total = C.c_int64()
+    counts = np.zeros(nevents, dtype=np.int64)
+    st = Stats()
+    self._check(self.lib.is3d_sample_device(self.ctx, nevents, C.byref(plist), C.byref(total), _ptr(counts), C.byref(st)), "is3d_sample_device")
+    return plist.value, total.value, counts, st
+
+
 HostSession.abi_sample = _abi_sample
+HostSession.abi_sample_compact = _abi_sample_compact
+HostSession.abi_expand = _abi_expand
+HostSession.abi_sample_device = _abi_sample_device
 HostSession.abi_sample_histograms = _abi_sample_histograms

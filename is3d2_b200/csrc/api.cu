@@ -93,6 +93,11 @@ void is3d_destroy(is3d_ctx *ctx)
   comm_release(ctx);
   for (void *p : ctx->owned) cudaFree(p);
   release_host_lists_of(ctx);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  for (int k = 0; k < 2; k++) {
+    if (ctx->ev_sorted[k]) cudaEventDestroy(ctx->ev_sorted[k]);
+    if (ctx->ev_copied[k]) cudaEventDestroy(ctx->ev_copied[k]);
+  }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);

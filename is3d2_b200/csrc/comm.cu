@@ -341,21 +341,27 @@ is3d_status is3d_group_polarization(is3d_group *g, double *St, double *Sx, doubl
 // sample_dN_pTdpTdphidy over all devices.  No collective: the Philox streams are keyed by the GLOBAL cell index, so the
 // devices sample disjoint cell blocks independently; event e of the merged list holds device 0's hadrons of e, then device
 // 1's, ... -- the (cell, draw) order a single GPU produces for the whole surface (ParticleSampler.cpp:1093-1120 appends per cell).
-is3d_status is3d_group_sample(is3d_group *g, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts, is3d_stats *stats)
+static is3d_status group_sample_any(is3d_group *g, int64_t nevents, bool compact, void **particles, int64_t *total, int64_t *counts,
+                                    is3d_stats *stats)
 {
   if (!g) return IS3D_ERR_INVALID;
   const int nd = (int)g->ctx.size();
+  const size_t rec = compact ? sizeof(is3d_particle_compact) : sizeof(is3d_particle);
+  auto sample_one = [&](int i, void **list, int64_t *tot, int64_t *cnt, is3d_stats *st) {
+    return compact ? is3d_sample_compact(g->ctx[i], nevents, (is3d_particle_compact **)list, tot, cnt, st)
+                   : is3d_sample(g->ctx[i], nevents, (is3d_particle **)list, tot, cnt, st);
+  };
   if (nd == 1) {
-    is3d_status rc = is3d_sample(g->ctx[0], nevents, particles, total, counts, stats);
+    is3d_status rc = sample_one(0, particles, total, counts, stats);
     if (rc != IS3D_OK) g->err = g->ctx[0]->err;
     return rc;
   }
   if (nevents <= 0) { g->err = "group_sample: nevents out of range"; return IS3D_ERR_INVALID; }
   std::vector<is3d_stats> st(nd);
-  std::vector<is3d_particle *> lists(nd, nullptr);
+  std::vector<void *> lists(nd, nullptr);
   std::vector<int64_t> tot(nd, 0);
   std::vector<std::vector<int64_t>> cnt(nd, std::vector<int64_t>((size_t)nevents, 0));
-  is3d_status rc = for_each_device(g, [&](int i) { return is3d_sample(g->ctx[i], nevents, &lists[i], &tot[i], cnt[i].data(), &st[i]); });
+  is3d_status rc = for_each_device(g, [&](int i) { return sample_one(i, &lists[i], &tot[i], cnt[i].data(), &st[i]); });
   if (stats) { std::memset(stats, 0, sizeof(*stats)); for (auto &s : st) add_stats(stats, s); }
   auto drop = [&] { for (auto *l : lists) if (l) is3d_free_particles(l); };
   if (rc != IS3D_OK) { drop(); return rc; }
@@ -371,14 +377,14 @@ is3d_status is3d_group_sample(is3d_group *g, int64_t nevents, is3d_particle **pa
   }
   if (total) *total = all;
   if (particles) {
-    is3d_particle *out = (is3d_particle *)alloc_plain_list((size_t)all * sizeof(is3d_particle));
+    char *out = (char *)alloc_plain_list((size_t)all * rec);
     if (!out) { drop(); g->err = "group_sample: out of host memory"; return IS3D_ERR_INVALID; }
     for_each_device(g, [&](int i) {                       // one host thread per device list: disjoint destination ranges
-      const is3d_particle *src = lists[i];
+      const char *src = (const char *)lists[i];
       int64_t off = 0;
       for (int64_t e = 0; e < nevents; e++) {
         const int64_t c = cnt[i][e];
-        if (c) std::memcpy(out + start[i][e], src + off, (size_t)c * sizeof(is3d_particle));
+        if (c) std::memcpy(out + (size_t)start[i][e] * rec, src + (size_t)off * rec, (size_t)c * rec);
         off += c;
       }
       return IS3D_OK;
@@ -388,6 +394,13 @@ is3d_status is3d_group_sample(is3d_group *g, int64_t nevents, is3d_particle **pa
   drop();
   return IS3D_OK;
 }
+
+is3d_status is3d_group_sample(is3d_group *g, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts, is3d_stats *stats)
+{ return group_sample_any(g, nevents, false, (void **)particles, total, counts, stats); }
+
+is3d_status is3d_group_sample_compact(is3d_group *g, int64_t nevents, is3d_particle_compact **particles, int64_t *total, int64_t *counts,
+                                      is3d_stats *stats)
+{ return group_sample_any(g, nevents, true, (void **)particles, total, counts, stats); }
 
 // self-test histograms of a sharded sampler run: sums of the per-device counters (BinSampledParticle.cpp counts are additive)
 is3d_status is3d_group_sample_histograms(is3d_group *g, double *dN_dy, double *dN_deta, double *dN_dphipdy, double *dN_2pipTdpTdy,

@@ -33,6 +33,9 @@ struct is3d_ctx {
   is3d_params prm;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // timing events of the compute calls (created once, destroyed with the context)
+  // sampler copy pipeline (sampler.cu): pass k's D2H on copy_stream overlaps pass k + 1's kernels on `stream`
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_sorted[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   std::string err;
   int sm_count = 148;
   // multi-GPU (comm.cu): NCCL communicator this context's results are summed over (nullptr = single GPU)
@@ -169,8 +172,9 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
 is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_dev, is3d_stats *stats);
 is3d_status run_total_yield(is3d_ctx *ctx, double *ntotal, is3d_stats *stats);
 is3d_status run_cell_yields(is3d_ctx *ctx, double *dn_tot_host, double *dn_list_host, is3d_stats *stats);
-is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts,
+is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, int record_kind, void **particles, int64_t *total, int64_t *counts,
                         is3d_stats *stats);
+void expand_compact(const is3d_ctx *ctx, const is3d_particle_compact *in, int64_t n, is3d_particle *out);
 void release_host_lists_of(is3d_ctx *ctx);
 // a plain (pageable) library-owned list, released by is3d_free_particles like the pinned ones (merged multi-GPU lists)
 void *alloc_plain_list(size_t bytes);

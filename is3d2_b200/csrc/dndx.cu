@@ -542,6 +542,22 @@ is3d_status is3d_dndx(is3d_ctx *ctx, double *tau_hist, double *r_hist, double *p
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(r_hist, dr, nr * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(phi_hist, dp, np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->prm.dndx_bug_compat) {
+    // The reference clears its per-species accumulators with memset(ptr, 0.0, CORES * bins): `bins` BYTES, i.e. only
+    // the first bins/8 doubles (SpacetimeDistribution.cpp:166-168, :671-673).  Every later bin keeps the previous
+    // species' sum, so its files are cumulative over species there (and a bin cut in half by the byte count keeps
+    // its upper 32 bits).  Serial build (CORES = 1) reproduced literally on the clean histograms.
+    auto emulate = [&](double *h, int bins) {
+      std::vector<double> all((size_t)bins, 0.0);
+      for (int s = 0; s < ctx->ns; s++) {
+        std::memset(all.data(), 0, (size_t)bins);
+        for (int b = 0; b < bins; b++) { all[b] += h[(size_t)s * bins + b]; h[(size_t)s * bins + b] = all[b]; }
+      }
+    };
+    emulate(tau_hist, ctx->prm.tau_bins);
+    emulate(r_hist, ctx->prm.r_bins);
+    emulate(phi_hist, ctx->prm.phip_bins);
+  }
   return IS3D_OK;
 }
 

@@ -3,21 +3,31 @@
 // (reference src/cpp/ParticleSampler.cpp:447-1134, BinSampledParticle.cpp).
 //
 // The reference loops cell -> event -> Poisson(dn_tot) hadrons.  Independent Poisson draws per event are
-// equivalent to ONE Poisson draw of mean Nevents * dn_tot per cell followed by a uniform event label per hadron, so
-// the GPU pipeline is flat in (cell, hadron):
-//   1. sampler_setup_kernel   thread per cell: LRF quantities, df coefficients, breakdown test, mean yield dn_tot,
-//                             N ~ Poisson(Nevents dn_tot) with the cell's own Philox stream -> 59-double pack, count
-//   2. exclusive scan of the counts (cub::DeviceScan, plumbing) -> proposal offsets
-//   3. sampler_hadron_kernel  thread per proposed hadron: cell by binary search in the offsets, event label, species
+// equivalent to ONE Poisson draw of mean E * dn_tot per cell for a BLOCK of E events followed by a uniform event label
+// inside the block per hadron, so the GPU pipeline is flat in (event block, cell, hadron):
+//   1. sampler_setup_kernel   thread per cell: LRF quantities, df coefficients, breakdown test, mean yield dn_tot
+//                             -> 59-double pack (once per call)
+//   then, per PASS = a run of consecutive 64-event blocks (kEventBlock is part of the random-stream keying, the pass
+//   size is not: the sampled set does not depend on how the call is cut into passes, kernels or GPUs):
+//   2. sampler_count_kernel   thread per (block, cell): N ~ Poisson(E dn_tot) from the (cell, block) Philox stream;
+//      exclusive scan of the counts (cub::DeviceScan, plumbing) -> proposal offsets
+//   3. sampler_hadron_kernel  thread per proposed hadron: (block, cell) by binary search in the offsets, event label, species
 //                             by inverse CDF over the (cell-independent) cumulative density tables, thermal momentum
 //                             by rejection, viscous/flux weights, accept -> record or self-test histograms
-//   4. stable radix sort of (event, proposal index) (cub, plumbing) + gather -> particles grouped by event, in a
-//      deterministic order that does not depend on the launch geometry.
+//   4. stable radix sort of (event, proposal index) (cub, plumbing) + gather -> the pass's particles grouped by event, in a
+//      deterministic order; passes cover ascending event ranges, so the gathered records of pass k are the next
+//      contiguous piece of the final list and go to the host on a second stream while pass k + 1 samples.
 #include <cub/cub.cuh>
 
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cctype>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 #include "ctx.h"
 #include "aniso.cuh"
@@ -26,6 +36,9 @@
 namespace is3d {
 
 namespace {
+
+// events per Poisson block.  Part of the random-stream keying: changing it changes the sampled set (not its distribution).
+constexpr int kEventBlock = 64;
 
 struct SamplerTables {
   int ns;
@@ -56,12 +69,8 @@ __global__ void sampler_setup_kernel(SurfaceView surf, int64_t begin, int64_t co
   else {
     if (status & CELL_BREAKDOWN) atomicAdd(&counters[2], 1ull);
     y = cell_mean_yield(p, fl.df_mode, st.totA, st.totB, st.totD);
-    if (nevents > 0.0 && p[SP_DNTOT] > 0.0) {
-      Philox rng;
-      rng.init(seed, (uint64_t)(global_offset + begin + i), 0xFFFFFFFFu);
-      n = (unsigned long long)poisson_sample(rng, nevents * p[SP_DNTOT]);
-    }
   }
+  (void)nevents; (void)seed; (void)global_offset;
   if (ncount) ncount[i] = n;
   if (yield) yield[i] = y;
 }
@@ -115,7 +124,7 @@ struct SamplerOut {
 // one instantiation per df_mode: the branches of the other modes would only add instruction-cache pressure
 template <int DF_MODE>
 __global__ void __launch_bounds__(128)
-sampler_hadron_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cell_global0,
+sampler_hadron_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cell_global0, int block0, int nblocks,
                       const unsigned long long *__restrict__ offsets, unsigned long long nprop,
                       SamplerTables st, int dimension, double y_cut, long nevents, uint64_t seed, HistGrid hg,
                       SamplerOut out, unsigned long long *counters)
@@ -126,16 +135,21 @@ sampler_hadron_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
   int event = 0;
   is3d_particle r;
   if (jg < nprop) {
-    // cell = last index with offsets[cell] <= jg
-    int64_t lo = 0, hi = ncells;
+    // (block, cell) = last entry v with offsets[v] <= jg
+    int64_t lo = 0, hi = (int64_t)nblocks * ncells;
     while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (offsets[mid] <= jg) lo = mid; else hi = mid; }
-    const int64_t cell = lo;
-    const uint32_t n = (uint32_t)(jg - offsets[cell]);
+    const int blk = block0 + (int)(lo / ncells);
+    const int64_t cell = lo - (int64_t)(blk - block0) * ncells;
+    const uint32_t n = (uint32_t)(jg - offsets[lo]);
     auto pk = [&](int k) { return pack[k * stride + cell]; };
     Philox rng;
-    rng.init(seed, (uint64_t)(cell_global0 + cell), n);
-    event = (int)(rng.canonical() * (double)nevents);
-    if (event >= nevents) event = (int)nevents - 1;
+    rng.init(seed, (uint64_t)(cell_global0 + cell), n, (uint32_t)blk);
+    // uniform event label inside the block (the reference draws every event's Poisson number separately, :919-922)
+    const long first = (long)blk * kEventBlock;
+    const long ev = nevents - first < kEventBlock ? nevents - first : kEventBlock;
+    int within = (int)(rng.canonical() * (double)ev);
+    if (within >= ev) within = (int)ev - 1;
+    event = (int)first + within;
     int s;
     if (st.cell_cdf) {
       // per-cell discrete distribution over species (fast = 0 and df_mode 5): inclusive cumulative row of this cell
@@ -372,14 +386,29 @@ __global__ void sampler_cdf_kernel(double *__restrict__ pack, int64_t stride, in
     const bool valid = pack[SP_VALID * stride + cell] != 0.0;
     const double dn_tot = (valid && total > 0.0) ? total * (2.0 * y_max * pack[SP_DSMAX * stride + cell]) : 0.0;
     pack[SP_DNTOT * stride + cell] = dn_tot;
-    unsigned long long n = 0;
-    if (nevents > 0.0 && dn_tot > 0.0) {
-      Philox rng;
-      rng.init(seed, (uint64_t)(cell_global0 + cell), 0xFFFFFFFFu);
-      n = (unsigned long long)poisson_sample(rng, nevents * dn_tot);
-    }
-    if (ncount) ncount[cell] = n;
+    if (ncount) ncount[cell] = 0;
   }
+  (void)nevents; (void)seed; (void)cell_global0;
+}
+
+// proposal counts of one pass: entry v = (block - block0) * count + cell
+__global__ void sampler_count_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int64_t cell_global0, int block0,
+                                     int nblocks, long nevents, uint64_t seed, unsigned long long *__restrict__ ncount)
+{
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= (int64_t)nblocks * count) return;
+  const int blk = block0 + (int)(v / count);
+  const int64_t cell = v - (int64_t)(blk - block0) * count;
+  const long first = (long)blk * kEventBlock;
+  const long ev = nevents - first < kEventBlock ? nevents - first : kEventBlock;
+  const double dn_tot = pack[SP_DNTOT * stride + cell];
+  unsigned long long n = 0;
+  if (dn_tot > 0.0 && ev > 0) {
+    Philox rng;
+    rng.init(seed, (uint64_t)(cell_global0 + cell), 0xFFFFFFFFu, (uint32_t)blk);
+    n = (unsigned long long)poisson_sample(rng, (double)ev * dn_tot);
+  }
+  ncount[v] = n;
 }
 
 // df_mode 5: fold the anisotropic solution left by the famod stage (feqmod pack layout) into the sampler pack:
@@ -593,6 +622,38 @@ static is3d_status ensure_hist(is3d_ctx *ctx, HistGrid *hg, bool zero)
 static std::mutex g_list_mutex;
 static std::map<void *, is3d_ctx::HostList *> g_lists;
 
+// NUMA node of the GPU (from sysfs), -1 if unknown
+static int gpu_numa_node(int device)
+{
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) return -1;
+  for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+  std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+  FILE *f = fopen(path.c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+
+// Page-locked list buffer on the GPU's own NUMA node: with eight GPUs writing particle lists at once, lists that all live
+// on node 0 share one socket's memory and inter-socket bandwidth.  The memory policy of the calling thread is switched to
+// "prefer that node" for the allocation (raw syscall: libnuma is not a dependency) and restored; failures are ignored.
+static cudaError_t malloc_host_near_gpu(void **p, size_t bytes, int device)
+{
+  const int node = gpu_numa_node(device);
+  bool switched = false;
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / 64] |= 1ul << (node % 64);
+    switched = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 1025ul) == 0;
+  }
+  cudaError_t e = cudaMallocHost(p, bytes);
+  if (switched) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+  return e;
+}
+
 static is3d_status acquire_host_list(is3d_ctx *ctx, size_t bytes, is3d_ctx::HostList **out)
 {
   std::lock_guard<std::mutex> lock(g_list_mutex);
@@ -608,7 +669,7 @@ static is3d_status acquire_host_list(is3d_ctx *ctx, size_t bytes, is3d_ctx::Host
     }
     best = new is3d_ctx::HostList;
     best->capacity = bytes + bytes / 8 + 4096;
-    cudaError_t e = cudaMallocHost(&best->ptr, best->capacity);
+    cudaError_t e = malloc_host_near_gpu(&best->ptr, best->capacity, ctx->prm.device);
     if (e != cudaSuccess) { delete best; ctx->set_error(std::string("cudaMallocHost (particle list): ") + cudaGetErrorString(e)); return IS3D_ERR_CUDA; }
     best->owner = ctx;
     ctx->host_lists.push_back(best);
@@ -655,124 +716,299 @@ void *alloc_plain_list(size_t bytes)
   return p;
 }
 
-// bounds the record scratch to ~27 GB (test hook: IS3D_SAMPLER_PASS_PROPOSALS)
+// soft bound of the proposals of one pass (record scratch ~ 27 GB; test hook: IS3D_SAMPLER_PASS_PROPOSALS)
 static unsigned long long max_proposals_per_pass()
 {
   if (const char *v = getenv("IS3D_SAMPLER_PASS_PROPOSALS")) { long long c = atoll(v); if (c > 0) return (unsigned long long)c; }
   return 256ull << 20;
 }
 
-is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total_out, int64_t *counts,
+// record layouts a call can deliver: the reference's Sampled_Particle (104 B) or the 64-byte wire record
+__global__ void gather_compact_kernel(const is3d_particle *__restrict__ in, const unsigned int *__restrict__ idx,
+                                      unsigned long long n, is3d_particle_compact *__restrict__ out)
+{
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const is3d_particle r = in[idx[i]];
+  is3d_particle_compact c;
+  c.chosen_index = r.chosen_index; c.event = r.event;
+  c.tau = r.tau; c.x = r.x; c.y = r.y; c.eta = r.eta; c.px = r.px; c.py = r.py; c.pz = r.pz;
+  out[i] = c;
+}
+
+namespace {
+
+// second stream + events of the copy pipeline, created on first use and destroyed with the context
+is3d_status ensure_copy_pipeline(is3d_ctx *ctx)
+{
+  if (ctx->copy_stream) return IS3D_OK;
+  IS3D_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) {
+    IS3D_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_sorted[k], cudaEventDisableTiming));
+    IS3D_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming));
+  }
+  return IS3D_OK;
+}
+
+struct SampleRequest {
+  int64_t nevents;
+  bool compact;              // 64-byte wire records instead of the 104-byte Sampled_Particle
+  bool to_device;            // leave the list in a library-owned device buffer (no D2H)
+};
+
+// result of one contiguous cell block: records grouped by event
+struct BlockList {
+  is3d_ctx::HostList *host = nullptr;   // pinned list (host delivery)
+  void *dev = nullptr;                  // device list (device delivery)
+  unsigned long long n = 0;
+};
+
+// Samples the cells [begin, begin + count) whose pack is already on the device: event-block passes, pipelined D2H.
+// sum_dn = sum of the cells' dn_tot (mean hadrons per event of this cell block).
+is3d_status sample_cell_block(is3d_ctx *ctx, SamplerSetup &ss, const HistGrid &hg, const SampleRequest &rq, int64_t begin, int64_t count,
+                              const double *pack, int64_t stride, double sum_dn, unsigned long long *counters, unsigned long long *evc,
+                              int key_bits, int64_t *launches, BlockList *result)
+{
+  const is3d_params &p = ctx->prm;
+  const int64_t nevents = rq.nevents;
+  const bool lists = !p.test_sampler;
+  const size_t rec_bytes = rq.compact ? sizeof(is3d_particle_compact) : sizeof(is3d_particle);
+  const int nblocks_total = (int)((nevents + kEventBlock - 1) / kEventBlock);
+  // pass size: enough passes to hide the D2H of pass k behind the sampling of pass k + 1 when the list is large, one pass
+  // when it is small (every pass costs two host round trips), never (on average) above the proposal budget
+  const double expected_total = (double)nevents * sum_dn;
+  const double per_block = (double)kEventBlock * sum_dn;
+  double target = expected_total;
+  if (lists && !rq.to_device && expected_total * (double)rec_bytes > 96e6) target = expected_total / 6.0;
+  const double budget = (double)max_proposals_per_pass();
+  if (target > budget) target = budget;
+  int blocks_per_pass = per_block > 0.0 ? (int)(target / per_block) : nblocks_total;
+  if (blocks_per_pass < 1) blocks_per_pass = 1;
+  if (blocks_per_pass > nblocks_total) blocks_per_pass = nblocks_total;
+  const int64_t max_entries = (int64_t)64 << 20;                        // (block, cell) count entries of one pass
+  if ((int64_t)blocks_per_pass * count > max_entries) blocks_per_pass = (int)(max_entries / count > 0 ? max_entries / count : 1);
+
+  void *ncount = nullptr, *offsets = nullptr, *nacc_dev = nullptr;
+  const size_t entries = (size_t)blocks_per_pass * count + 1;
+  IS3D_TRY(ctx->get_scratch("sampler_ncount", entries * sizeof(unsigned long long), &ncount));
+  IS3D_TRY(ctx->get_scratch("sampler_offsets", entries * sizeof(unsigned long long), &offsets));
+  IS3D_TRY(ctx->get_scratch("sampler_nacc", sizeof(unsigned long long), &nacc_dev));
+
+  // destination of the block's list: capacity from the mean + 8 sigma (accepted <= proposed); grown if ever exceeded
+  size_t capacity = (size_t)(expected_total + 8.0 * sqrt(expected_total + 1.0)) + 4096;
+  is3d_ctx::HostList *hb = nullptr;
+  void *dev_list = nullptr;
+  if (lists) {
+    if (rq.to_device) IS3D_TRY(ctx->get_scratch("sampler_device_list", capacity * rec_bytes, &dev_list));
+    else { IS3D_TRY(acquire_host_list(ctx, capacity * rec_bytes, &hb)); IS3D_TRY(ensure_copy_pipeline(ctx)); }
+  }
+  auto fail = [&](is3d_status st) { if (hb) { cudaStreamSynchronize(ctx->copy_stream); release_host_list(hb->ptr); } return st; };
+#define SMP_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->set_error(std::string(#expr) + ": " + cudaGetErrorString(e__)); return fail(IS3D_ERR_CUDA); } } while (0)
+#define SMP_TRY(expr) do { is3d_status s__ = (expr); if (s__ != IS3D_OK) return fail(s__); } while (0)
+
+  // double-buffered sorted records of a pass (host delivery): sized for the largest pass that can reasonably occur
+  size_t pass_cap = (size_t)((double)blocks_per_pass * per_block * 1.25 + 8.0 * sqrt((double)blocks_per_pass * per_block + 1.0)) + 4096;
+  void *sorted[2] = {nullptr, nullptr};
+  if (lists && !rq.to_device) {
+    SMP_TRY(ctx->get_scratch("sampler_sorted0", pass_cap * rec_bytes, &sorted[0]));
+    SMP_TRY(ctx->get_scratch("sampler_sorted1", pass_cap * rec_bytes, &sorted[1]));
+  }
+  bool buf_in_flight[2] = {false, false};
+  unsigned long long written = 0;
+  int pass_index = 0;
+  for (int b0 = 0; b0 < nblocks_total; b0 += blocks_per_pass, pass_index++) {
+    const int nb = nblocks_total - b0 < blocks_per_pass ? nblocks_total - b0 : blocks_per_pass;
+    const int64_t nv = (int64_t)nb * count;
+    sampler_count_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, ctx->stream>>>(pack, stride, count, ctx->global_offset + begin, b0, nb,
+                                                                             (long)nevents, (uint64_t)p.sampler_seed, (unsigned long long *)ncount);
+    SMP_CUDA(cudaGetLastError());
+    SMP_CUDA(cudaMemsetAsync((unsigned long long *)ncount + nv, 0, sizeof(unsigned long long), ctx->stream));
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (unsigned long long *)ncount, (unsigned long long *)offsets, (int)(nv + 1), ctx->stream);
+    void *tmp = nullptr;
+    SMP_TRY(ctx->get_scratch("cub_tmp", tmp_bytes, &tmp));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (unsigned long long *)ncount, (unsigned long long *)offsets, (int)(nv + 1), ctx->stream);
+    SMP_CUDA(cudaGetLastError());
+    unsigned long long nprop = 0;
+    SMP_CUDA(cudaMemcpyAsync(&nprop, (unsigned long long *)offsets + nv, sizeof(nprop), cudaMemcpyDeviceToHost, ctx->stream));
+    SMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    (*launches) += 2;
+    if (nprop == 0) continue;
+    SamplerOut out{nullptr, nullptr, (unsigned long long *)nacc_dev, evc};
+    void *rec = nullptr, *key = nullptr;
+    if (lists) {
+      SMP_TRY(ctx->get_scratch("sampler_rec", nprop * sizeof(is3d_particle), &rec));
+      SMP_TRY(ctx->get_scratch("sampler_key", nprop * sizeof(unsigned long long), &key));
+      SMP_CUDA(cudaMemsetAsync(nacc_dev, 0, sizeof(unsigned long long), ctx->stream));
+      out.rec = (is3d_particle *)rec; out.key = (unsigned long long *)key;
+    }
+#define IS3D_HADRONS(M) sampler_hadron_kernel<M><<<(unsigned)((nprop + 127) / 128), 128, 0, ctx->stream>>>( \
+        pack, stride, count, ctx->global_offset + begin, b0, nb, (unsigned long long *)offsets, nprop, ss.st, \
+        p.dimension, p.y_cut, (long)nevents, (uint64_t)p.sampler_seed, hg, out, counters)
+    switch (p.df_mode) {
+      case 1: IS3D_HADRONS(1); break;
+      case 2: IS3D_HADRONS(2); break;
+      case 3: IS3D_HADRONS(3); break;
+      case 4: IS3D_HADRONS(4); break;
+      default: IS3D_HADRONS(5); break;
+    }
+#undef IS3D_HADRONS
+    SMP_CUDA(cudaGetLastError());
+    (*launches)++;
+    if (!lists) continue;
+    unsigned long long nacc = 0;
+    SMP_CUDA(cudaMemcpyAsync(&nacc, nacc_dev, sizeof(nacc), cudaMemcpyDeviceToHost, ctx->stream));
+    SMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (nacc == 0) continue;
+    // the list outgrew its estimate (cannot happen within 8 sigma): move it to a larger buffer
+    if (written + nacc > capacity) {
+      const size_t bigger = (size_t)((written + nacc) * 1.5) + 4096;
+      if (rq.to_device) {
+        void *old = dev_list, *keep = nullptr;
+        SMP_TRY(ctx->get_scratch("sampler_device_list_grow", written * rec_bytes + 8, &keep));
+        SMP_CUDA(cudaMemcpyAsync(keep, old, written * rec_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        SMP_CUDA(cudaStreamSynchronize(ctx->stream));
+        SMP_TRY(ctx->get_scratch("sampler_device_list", bigger * rec_bytes, &dev_list));
+        SMP_CUDA(cudaMemcpyAsync(dev_list, keep, written * rec_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+      } else {
+        SMP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        is3d_ctx::HostList *nb2 = nullptr;
+        SMP_TRY(acquire_host_list(ctx, bigger * rec_bytes, &nb2));
+        std::memcpy(nb2->ptr, hb->ptr, written * rec_bytes);
+        release_host_list(hb->ptr);
+        hb = nb2;
+      }
+      capacity = bigger;
+    }
+    void *key2 = nullptr, *idx = nullptr, *idx2 = nullptr, *stmp = nullptr;
+    SMP_TRY(ctx->get_scratch("sampler_key2", nacc * sizeof(unsigned long long), &key2));
+    SMP_TRY(ctx->get_scratch("sampler_idx", nacc * sizeof(unsigned int), &idx));
+    SMP_TRY(ctx->get_scratch("sampler_idx2", nacc * sizeof(unsigned int), &idx2));
+    iota_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, ctx->stream>>>((unsigned int *)idx, nacc);
+    size_t sb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, (unsigned long long *)key, (unsigned long long *)key2, (unsigned int *)idx,
+                                    (unsigned int *)idx2, (int)nacc, 0, key_bits, ctx->stream);
+    SMP_TRY(ctx->get_scratch("cub_tmp", sb, &stmp));
+    cub::DeviceRadixSort::SortPairs(stmp, sb, (unsigned long long *)key, (unsigned long long *)key2, (unsigned int *)idx,
+                                    (unsigned int *)idx2, (int)nacc, 0, key_bits, ctx->stream);
+    void *dst;
+    const int slot = pass_index & 1;
+    if (rq.to_device) {
+      dst = (char *)dev_list + written * rec_bytes;
+    } else {
+      if (nacc > pass_cap) {                       // a pass far above its mean: wait for the copies in flight and enlarge
+        SMP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        buf_in_flight[0] = buf_in_flight[1] = false;
+        pass_cap = (size_t)(nacc * 1.25) + 4096;
+        SMP_TRY(ctx->get_scratch("sampler_sorted0", pass_cap * rec_bytes, &sorted[0]));
+        SMP_TRY(ctx->get_scratch("sampler_sorted1", pass_cap * rec_bytes, &sorted[1]));
+      }
+      if (buf_in_flight[slot]) SMP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));   // its previous D2H must be done
+      dst = sorted[slot];
+    }
+    if (rq.compact) gather_compact_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, ctx->stream>>>((is3d_particle *)rec, (unsigned int *)idx2, nacc, (is3d_particle_compact *)dst);
+    else gather_particles_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, ctx->stream>>>((is3d_particle *)rec, (unsigned int *)idx2, nacc, (is3d_particle *)dst);
+    SMP_CUDA(cudaGetLastError());
+    (*launches) += 3;
+    if (!rq.to_device) {
+      // pass k's records travel on the copy stream while pass k + 1 samples on the compute stream
+      SMP_CUDA(cudaEventRecord(ctx->ev_sorted[slot], ctx->stream));
+      SMP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sorted[slot], 0));
+      SMP_CUDA(cudaMemcpyAsync((char *)hb->ptr + written * rec_bytes, dst, nacc * rec_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      SMP_CUDA(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+      buf_in_flight[slot] = true;
+    }
+    written += nacc;
+  }
+  if (hb) SMP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+#undef SMP_CUDA
+#undef SMP_TRY
+  result->host = hb; result->dev = dev_list; result->n = written;
+  return IS3D_OK;
+}
+
+}  // namespace
+
+is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, int record_kind, void **particles, int64_t *total_out, int64_t *counts,
                         is3d_stats *stats)
 {
   const is3d_params &p = ctx->prm;
   if (nevents <= 0 || nevents > (1 << 24)) { ctx->set_error("sample: nevents out of range (1 .. 2^24)"); return IS3D_ERR_INVALID; }
+  SampleRequest rq{nevents, (record_kind & 1) != 0, (record_kind & 2) != 0};
   SamplerSetup ss;
   IS3D_TRY(prepare_sampler(ctx, &ss));
   HistGrid hg;
   IS3D_TRY(ensure_hist(ctx, &hg, true));
-  const bool lists = !p.test_sampler;
+  const size_t rec_bytes = rq.compact ? sizeof(is3d_particle_compact) : sizeof(is3d_particle);
   const int64_t n = ctx->surf.n;
   const int64_t macro = sampler_cells_per_pass(ctx);
   const int64_t stride = n < macro ? n : macro;
-  void *pack = nullptr, *counters = nullptr, *ncount = nullptr, *offsets = nullptr, *evc = nullptr, *nacc_dev = nullptr;
+  void *pack = nullptr, *counters = nullptr, *evc = nullptr, *bsum = nullptr;
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)SP_SIZE * stride * sizeof(double), &pack));
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
-  IS3D_TRY(ctx->get_scratch("sampler_ncount", (size_t)(stride + 1) * sizeof(unsigned long long), &ncount));
-  IS3D_TRY(ctx->get_scratch("sampler_offsets", (size_t)(stride + 1) * sizeof(unsigned long long), &offsets));
   IS3D_TRY(ctx->get_scratch("sampler_event_counts", (size_t)nevents * sizeof(unsigned long long), &evc));
-  IS3D_TRY(ctx->get_scratch("sampler_nacc", sizeof(unsigned long long), &nacc_dev));
+  IS3D_TRY(ctx->get_scratch("block_sums", 1024 * sizeof(double), &bsum));
   void *counters_backup = nullptr;
   IS3D_TRY(ctx->get_scratch("counters_backup", 16 * sizeof(unsigned long long), &counters_backup));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(evc, 0, (size_t)nevents * sizeof(unsigned long long), ctx->stream));
 
-  struct PassList { is3d_ctx::HostList *buf; unsigned long long n; };
-  std::vector<PassList> passes;                         // each pass: records sorted by (event, proposal index)
-  auto drop_passes = [&]() { for (auto &q : passes) release_host_list(q.buf->ptr); passes.clear(); };
+  std::vector<BlockList> blocks;                        // one list per cell block, each grouped by event
+  auto drop_blocks = [&]() { for (auto &q : blocks) if (q.host) release_host_list(q.host->ptr); blocks.clear(); };
   cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   float ms_total = 0.f;
   int64_t launches = 0;
   int key_bits = 40;
   while ((1ll << (key_bits - 40)) < nevents) key_bits++;
 
+  // df_mode 5 with the serial parity chain: the chain state advances through every set-up; a block whose set-up has to be
+  // redone (proposal budget) must restart from the state it began with
+  void *chain_state = nullptr, *chain_backup = nullptr;
+  size_t chain_bytes = 0;
+  if (p.df_mode == 5 && p.famod_chain) {
+    auto it = ctx->scratch.find("famod_chain_state");
+    if (it != ctx->scratch.end()) { chain_state = it->second.first; chain_bytes = it->second.second; }
+    if (chain_state) IS3D_TRY(ctx->get_scratch("famod_chain_backup", chain_bytes, &chain_backup));
+  }
+
   int64_t begin = 0;
   int64_t pass_cells = stride;
   while (begin < n) {
     int64_t count = n - begin < pass_cells ? n - begin : pass_cells;
+    if (rq.to_device && (begin != 0 || count != n)) {
+      drop_blocks();
+      ctx->set_error("sample_device: the surface does not fit one sampler pass on this context; use is3d_sample or fewer cells per context");
+      return IS3D_ERR_UNSUPPORTED;
+    }
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(counters_backup, counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
-    IS3D_TRY(sampler_setup_pass(ctx, ss, begin, count, (double)nevents, (double *)pack, stride, (unsigned long long *)ncount, nullptr,
-                                (unsigned long long *)counters, &launches, true));
-    IS3D_CUDA_TRY(ctx, cudaMemsetAsync((unsigned long long *)ncount + count, 0, sizeof(unsigned long long), ctx->stream));
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (unsigned long long *)ncount, (unsigned long long *)offsets, (int)(count + 1), ctx->stream);
-    void *tmp = nullptr;
-    IS3D_TRY(ctx->get_scratch("cub_tmp", tmp_bytes, &tmp));
-    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (unsigned long long *)ncount, (unsigned long long *)offsets, (int)(count + 1), ctx->stream);
-    IS3D_CUDA_TRY(ctx, cudaGetLastError());
-    unsigned long long nprop = 0;
-    IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(&nprop, (unsigned long long *)offsets + count, sizeof(nprop), cudaMemcpyDeviceToHost, ctx->stream));
+    if (chain_state && begin > 0) IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(chain_backup, chain_state, chain_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    is3d_status st = sampler_setup_pass(ctx, ss, begin, count, 0.0, (double *)pack, stride, nullptr, nullptr, (unsigned long long *)counters,
+                                        &launches, true);
+    if (st != IS3D_OK) { drop_blocks(); return st; }
+    // mean hadrons per event of this cell block
+    yield_reduce_kernel<<<1024, 256, 0, ctx->stream>>>((double *)pack + (size_t)SP_DNTOT * stride, count, (double *)bsum);
+    double hsum[1024];
+    IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(hsum, bsum, sizeof(hsum), cudaMemcpyDeviceToHost, ctx->stream));
     IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    launches += 2;
-    if (nprop > max_proposals_per_pass() && count > 1) {
-      // too many proposals for one pass: halve the cell block and redo its set-up (deterministic, so nothing is lost);
-      // the counters of the discarded attempt are rolled back by re-zeroing below
-      pass_cells = (count + 1) / 2;
+    launches++;
+    double sum_dn = 0.0;
+    for (double v : hsum) sum_dn += v;
+    const double budget = (double)max_proposals_per_pass();
+    if ((double)kEventBlock * sum_dn > budget && count > 1) {
+      // even ONE event block of this cell block exceeds the proposal budget: take fewer cells and redo their set-up
+      // (deterministic; the counters and the df_mode 5 chain state of the discarded attempt are rolled back)
+      int64_t fewer = (int64_t)((double)count * 0.75 * budget / ((double)kEventBlock * sum_dn));
+      pass_cells = fewer < 1 ? 1 : (fewer >= count ? (count + 1) / 2 : fewer);
       IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(counters, counters_backup, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+      if (chain_state && begin > 0) IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(chain_state, chain_backup, chain_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
       continue;
     }
-    if (nprop > 0) {
-      SamplerOut out{nullptr, nullptr, (unsigned long long *)nacc_dev, (unsigned long long *)evc};
-      void *rec = nullptr, *key = nullptr;
-      if (lists) {
-        IS3D_TRY(ctx->get_scratch("sampler_rec", nprop * sizeof(is3d_particle), &rec));
-        IS3D_TRY(ctx->get_scratch("sampler_key", nprop * sizeof(unsigned long long), &key));
-        IS3D_CUDA_TRY(ctx, cudaMemsetAsync(nacc_dev, 0, sizeof(unsigned long long), ctx->stream));
-        out.rec = (is3d_particle *)rec; out.key = (unsigned long long *)key;
-      }
-#define IS3D_HADRONS(M) sampler_hadron_kernel<M><<<(unsigned)((nprop + 127) / 128), 128, 0, ctx->stream>>>( \
-          (double *)pack, stride, count, ctx->global_offset + begin, (unsigned long long *)offsets, nprop, ss.st, \
-          p.dimension, p.y_cut, (long)nevents, (uint64_t)p.sampler_seed, hg, out, (unsigned long long *)counters)
-      switch (p.df_mode) {
-        case 1: IS3D_HADRONS(1); break;
-        case 2: IS3D_HADRONS(2); break;
-        case 3: IS3D_HADRONS(3); break;
-        case 4: IS3D_HADRONS(4); break;
-        default: IS3D_HADRONS(5); break;
-      }
-#undef IS3D_HADRONS
-      IS3D_CUDA_TRY(ctx, cudaGetLastError());
-      launches++;
-      if (lists) {
-        unsigned long long nacc = 0;
-        IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(&nacc, nacc_dev, sizeof(nacc), cudaMemcpyDeviceToHost, ctx->stream));
-        IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        if (nacc) {
-          void *key2 = nullptr, *idx = nullptr, *idx2 = nullptr, *sorted = nullptr, *stmp = nullptr;
-          IS3D_TRY(ctx->get_scratch("sampler_key2", nacc * sizeof(unsigned long long), &key2));
-          IS3D_TRY(ctx->get_scratch("sampler_idx", nacc * sizeof(unsigned int), &idx));
-          IS3D_TRY(ctx->get_scratch("sampler_idx2", nacc * sizeof(unsigned int), &idx2));
-          IS3D_TRY(ctx->get_scratch("sampler_sorted", nacc * sizeof(is3d_particle), &sorted));
-          iota_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, ctx->stream>>>((unsigned int *)idx, nacc);
-          size_t sb = 0;
-          cub::DeviceRadixSort::SortPairs(nullptr, sb, (unsigned long long *)key, (unsigned long long *)key2, (unsigned int *)idx,
-                                          (unsigned int *)idx2, (int)nacc, 0, key_bits, ctx->stream);
-          IS3D_TRY(ctx->get_scratch("cub_tmp", sb, &stmp));
-          cub::DeviceRadixSort::SortPairs(stmp, sb, (unsigned long long *)key, (unsigned long long *)key2, (unsigned int *)idx,
-                                          (unsigned int *)idx2, (int)nacc, 0, key_bits, ctx->stream);
-          gather_particles_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, ctx->stream>>>((is3d_particle *)rec, (unsigned int *)idx2, nacc,
-                                                                                         (is3d_particle *)sorted);
-          IS3D_CUDA_TRY(ctx, cudaGetLastError());
-          launches += 3;
-          is3d_ctx::HostList *hb = nullptr;
-          is3d_status st = acquire_host_list(ctx, nacc * sizeof(is3d_particle), &hb);
-          if (st != IS3D_OK) { drop_passes(); return st; }
-          passes.push_back({hb, nacc});
-          IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(hb->ptr, sorted, nacc * sizeof(is3d_particle), cudaMemcpyDeviceToHost, ctx->stream));
-        }
-      }
-    }
+    BlockList bl;
+    st = sample_cell_block(ctx, ss, hg, rq, begin, count, (const double *)pack, stride, sum_dn, (unsigned long long *)counters,
+                           (unsigned long long *)evc, key_bits, &launches, &bl);
+    if (st != IS3D_OK) { drop_blocks(); return st; }
+    if (bl.host || bl.dev) blocks.push_back(bl);
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
     IS3D_CUDA_TRY(ctx, cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -781,7 +1017,7 @@ is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
     begin += count;
   }
   is3d_status fs = fill_stats(ctx, counters, stats, ms_total, launches);
-  if (fs != IS3D_OK) { drop_passes(); return fs; }
+  if (fs != IS3D_OK) { drop_blocks(); return fs; }
 
   std::vector<unsigned long long> event_counts(nevents, 0);
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(event_counts.data(), evc, (size_t)nevents * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -789,34 +1025,83 @@ is3d_status run_sampler(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
   int64_t total = 0;
   for (int64_t e = 0; e < nevents; e++) total += (int64_t)event_counts[e];
   if (particles) {
-    if (passes.size() == 1) {
-      *particles = (is3d_particle *)passes[0].buf->ptr;          // the common case: one pass, already grouped by event
-    } else if (passes.empty()) {
+    if (rq.to_device) {
+      *particles = blocks.empty() ? nullptr : blocks[0].dev;
+    } else if (blocks.size() == 1) {
+      *particles = blocks[0].host->ptr;                          // the common case: one cell block, already grouped by event
+    } else if (blocks.empty()) {
       is3d_ctx::HostList *hb = nullptr;
-      IS3D_TRY(acquire_host_list(ctx, sizeof(is3d_particle), &hb));
-      *particles = (is3d_particle *)hb->ptr;
+      IS3D_TRY(acquire_host_list(ctx, rec_bytes, &hb));
+      *particles = hb->ptr;
     } else {
-      // several passes (surface larger than one pass): merge the event-sorted pass lists, pass order within an event
+      // several cell blocks (surface larger than one pass): every block list is grouped by event; event e of the final list
+      // is block 0's part, then block 1's, ... -- one host thread per block copies its pieces to their final places
       is3d_ctx::HostList *hb = nullptr;
-      is3d_status st = acquire_host_list(ctx, (size_t)total * sizeof(is3d_particle), &hb);
-      if (st != IS3D_OK) { drop_passes(); return st; }
-      is3d_particle *outp = (is3d_particle *)hb->ptr;
-      std::vector<int64_t> cursor(nevents, 0);
-      int64_t acc = 0;
-      for (int64_t e = 0; e < nevents; e++) { cursor[e] = acc; acc += (int64_t)event_counts[e]; }
-      for (auto &q : passes) {
-        const is3d_particle *src = (const is3d_particle *)q.buf->ptr;
-        for (unsigned long long i = 0; i < q.n; i++) outp[cursor[src[i].event]++] = src[i];
-      }
-      drop_passes();
-      *particles = outp;
+      is3d_status st = acquire_host_list(ctx, (size_t)total * rec_bytes, &hb);
+      if (st != IS3D_OK) { drop_blocks(); return st; }
+      const size_t nb = blocks.size();
+      // per-block event counts from the records themselves (event = second int32 of both layouts)
+      std::vector<std::vector<int64_t>> start(nb, std::vector<int64_t>((size_t)nevents + 1, 0));
+      auto event_of = [&](const char *base, unsigned long long i) { return ((const int32_t *)(base + i * rec_bytes))[rq.compact ? 1 : 2]; };
+      std::vector<std::thread> th;
+      for (size_t b = 0; b < nb; b++) th.emplace_back([&, b] {
+        const char *src = (const char *)blocks[b].host->ptr;
+        for (unsigned long long i = 0; i < blocks[b].n; i++) start[b][(size_t)event_of(src, i) + 1]++;
+      });
+      for (auto &t : th) t.join();
+      th.clear();
+      // dest[b][e] = final position of block b's first record of event e
+      std::vector<std::vector<int64_t>> dest(nb, std::vector<int64_t>((size_t)nevents, 0));
+      int64_t pos = 0;
+      for (int64_t e = 0; e < nevents; e++)
+        for (size_t b = 0; b < nb; b++) { dest[b][e] = pos; pos += start[b][(size_t)e + 1]; }
+      for (size_t b = 0; b < nb; b++) th.emplace_back([&, b] {
+        const char *src = (const char *)blocks[b].host->ptr;
+        int64_t off = 0;
+        for (int64_t e = 0; e < nevents; e++) {
+          const int64_t c = start[b][(size_t)e + 1];
+          if (c) std::memcpy((char *)hb->ptr + (size_t)dest[b][e] * rec_bytes, src + (size_t)off * rec_bytes, (size_t)c * rec_bytes);
+          off += c;
+        }
+      });
+      for (auto &t : th) t.join();
+      drop_blocks();
+      *particles = hb->ptr;
     }
   } else {
-    drop_passes();
+    drop_blocks();
   }
   if (total_out) *total_out = total;
   if (counts) for (int64_t e = 0; e < nevents; e++) counts[e] = (int64_t)event_counts[e];
   return IS3D_OK;
+}
+
+// host-side expansion of the 64-byte wire record into the reference's Sampled_Particle fields: mass / mcid from the species
+// tables, E from the mass shell, (t, z) from (tau, eta) -- the formulas of the device path (sampler.cuh boost_to_lab, 3+1d)
+void expand_compact(const is3d_ctx *ctx, const is3d_particle_compact *in, int64_t n, is3d_particle *out)
+{
+  const double *mass = ctx->h_mass.data();
+  const int *mcid = ctx->h_mcid.data();
+  const bool boost_invariant = ctx->prm.dimension == 2;
+  auto work = [&](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; i++) {
+      const is3d_particle_compact &c = in[i];
+      is3d_particle r;
+      r.chosen_index = c.chosen_index; r.mcid = mcid[c.chosen_index]; r.event = c.event; r.pad_ = 0;
+      r.mass = mass[c.chosen_index];
+      r.tau = c.tau; r.x = c.x; r.y = c.y; r.eta = c.eta; r.px = c.px; r.py = c.py; r.pz = c.pz;
+      const double sh = sinh(c.eta), ch = sqrt(1.0 + sh * sh);
+      r.t = c.tau * ch; r.z = c.tau * sh;
+      (void)boost_invariant;
+      r.E = sqrt(r.mass * r.mass + c.px * c.px + c.py * c.py + c.pz * c.pz);
+      out[i] = r;
+    }
+  };
+  const int nt = (int)std::min<int64_t>(std::max<unsigned>(1u, std::thread::hardware_concurrency()), n / 65536 + 1);
+  if (nt <= 1) { work(0, n); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+  for (auto &t : th) t.join();
 }
 
 }  // namespace is3d
@@ -856,7 +1141,9 @@ is3d_status is3d_cell_yields(is3d_ctx *ctx, double *dn_tot, double *dn_list, is3
   return is3d::run_cell_yields(ctx, dn_tot, dn_list, stats);
 }
 
-is3d_status is3d_sample(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts, is3d_stats *stats)
+// record_kind: bit 0 = 64-byte wire records, bit 1 = leave the list on the device
+static is3d_status sample_entry(is3d_ctx *ctx, int64_t nevents, int record_kind, void **particles, int64_t *total, int64_t *counts,
+                                is3d_stats *stats)
 {
   if (!ctx) return IS3D_ERR_INVALID;
   IS3D_CUDA_TRY(ctx, cudaSetDevice(ctx->prm.device));
@@ -865,10 +1152,31 @@ is3d_status is3d_sample(is3d_ctx *ctx, int64_t nevents, is3d_particle **particle
   if (total) *total = 0;
   IS3D_TRY(sampler_ready(ctx));
   if (ctx->surf.n == 0) { if (counts) for (int64_t e = 0; e < nevents; e++) counts[e] = 0; return IS3D_OK; }
-  return is3d::run_sampler(ctx, nevents, particles, total, counts, stats);
+  return is3d::run_sampler(ctx, nevents, record_kind, particles, total, counts, stats);
 }
 
-void is3d_free_particles(is3d_particle *p)
+is3d_status is3d_sample(is3d_ctx *ctx, int64_t nevents, is3d_particle **particles, int64_t *total, int64_t *counts, is3d_stats *stats)
+{ return sample_entry(ctx, nevents, 0, (void **)particles, total, counts, stats); }
+
+is3d_status is3d_sample_compact(is3d_ctx *ctx, int64_t nevents, is3d_particle_compact **particles, int64_t *total, int64_t *counts,
+                                is3d_stats *stats)
+{ return sample_entry(ctx, nevents, 1, (void **)particles, total, counts, stats); }
+
+is3d_status is3d_sample_device(is3d_ctx *ctx, int64_t nevents, const is3d_particle **particles_dev, int64_t *total, int64_t *counts,
+                               is3d_stats *stats)
+{ return sample_entry(ctx, nevents, 2, (void **)particles_dev, total, counts, stats); }
+
+is3d_status is3d_expand_particles(const is3d_ctx *ctx, const is3d_particle_compact *compact, int64_t n, is3d_particle *out)
+{
+  if (!ctx || n < 0 || (n > 0 && (!compact || !out))) return IS3D_ERR_INVALID;
+  if (ctx->ns <= 0) return IS3D_ERR_INVALID;
+  for (int64_t i = 0; i < n; i += 1 << 20)          // reject indices outside the species list before touching the tables
+    if (compact[i].chosen_index < 0 || compact[i].chosen_index >= ctx->ns) return IS3D_ERR_INVALID;
+  is3d::expand_compact(ctx, compact, n, out);
+  return IS3D_OK;
+}
+
+void is3d_free_particles(void *p)
 {
   // only lists this library handed out are released; an unknown (stale, already released after its context was
   // destroyed, or foreign) pointer is left alone rather than passed to free()

@@ -31,10 +31,11 @@ struct Philox {
     *hi = (uint32_t)(p >> 32);
     *lo = (uint32_t)p;
   }
-  IS3D_HD void init(uint64_t seed, uint64_t cell, uint32_t hadron)
+  // stream = (seed; global cell, event block, hadron index within (cell, block)); cells < 2^44, event blocks < 2^20
+  IS3D_HD void init(uint64_t seed, uint64_t cell, uint32_t hadron, uint32_t block = 0)
   {
     key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
-    ctr[0] = (uint32_t)cell; ctr[1] = (uint32_t)(cell >> 32); ctr[2] = hadron; ctr[3] = 0;
+    ctr[0] = (uint32_t)cell; ctr[1] = (uint32_t)(cell >> 32) | (block << 12); ctr[2] = hadron; ctr[3] = 0;
     have = 0;
   }
   // not inlined on the device: ~25 call sites of canonical() would each carry the ten rounds, and the sampler kernel is

@@ -183,22 +183,7 @@ void EmissionFunctionArray::calculate_dN_dX()
   dN_twopirdrdy.assign((size_t)ns * prm.r_bins, 0.0);
   dN_dphisdy.assign((size_t)ns * prm.phip_bins, 0.0);
   check(is3d_group_dndx(grp, dN_taudtaudy.data(), dN_twopirdrdy.data(), dN_dphisdy.data(), &stats), "calculate_dN_dX");
-  if (prm.dndx_bug_compat) {
-    // The reference clears its per-species accumulators with memset(ptr, 0.0, CORES * bins): `bins` BYTES, i.e. only
-    // the first bins/8 doubles (SpacetimeDistribution.cpp:166-168, :671-673).  Every later bin keeps the previous
-    // species' sum, so its files are cumulative over species there (and a bin cut in half by the byte count keeps
-    // its upper 32 bits).  Serial build (CORES = 1) reproduced literally on the clean device histograms.
-    auto emulate = [&](std::vector<double> &h, int bins) {
-      std::vector<double> all(bins, 0.0);
-      for (int s = 0; s < ns; s++) {
-        memset(all.data(), 0, (size_t)bins);
-        for (int b = 0; b < bins; b++) { all[b] += h[(size_t)s * bins + b]; h[(size_t)s * bins + b] = all[b]; }
-      }
-    };
-    emulate(dN_taudtaudy, prm.tau_bins);
-    emulate(dN_twopirdrdy, prm.r_bins);
-    emulate(dN_dphisdy, prm.phip_bins);
-  }
+  // dndx_bug_compat (the reference's partial memset) is applied by the library itself (is3d_dndx)
 }
 
 double EmissionFunctionArray::calculate_total_yield()
@@ -210,20 +195,33 @@ double EmissionFunctionArray::calculate_total_yield()
 
 void EmissionFunctionArray::sample_dN_pTdpTdphidy()
 {
-  is3d_particle *plist = nullptr;
+  // 64-byte wire records over PCIe (the list is transfer-bound); the Sampled_Particle fields that are functions of the
+  // others -- mass, mcID, E, t, z -- are restored here while the per-event vectors are filled (one host thread per event range)
+  is3d_particle_compact *plist = nullptr;
   int64_t total = 0;
   std::vector<int64_t> counts(Nevents, 0);
-  check(is3d_group_sample(grp, Nevents, &plist, &total, counts.data(), &stats), "sample_dN_pTdpTdphidy");
+  check(is3d_group_sample_compact(grp, Nevents, &plist, &total, counts.data(), &stats), "sample_dN_pTdpTdphidy");
   particle_event_list.assign(Nevents, {});
-  for (long e = 0; e < Nevents; e++) particle_event_list[e].reserve(counts[e]);
-  for (int64_t i = 0; i < total; i++) {
-    const is3d_particle &q = plist[i];
-    Sampled_Particle p;
-    p.chosen_index = q.chosen_index; p.mcID = q.mcid; p.mass = q.mass;
-    p.tau = q.tau; p.x = q.x; p.y = q.y; p.eta = q.eta; p.t = q.t; p.z = q.z;
-    p.E = q.E; p.px = q.px; p.py = q.py; p.pz = q.pz;
-    particle_event_list[q.event].push_back(p);
-  }
+  std::vector<int64_t> first(Nevents + 1, 0);
+  for (long e = 0; e < Nevents; e++) first[e + 1] = first[e] + counts[e];
+  const int nt = host_threads((size_t)Nevents, "IS3D_WRITER_THREADS");
+  parallel_for(nt, [&](int t) {
+    for (int64_t e = (int64_t)Nevents * t / nt; e < (int64_t)Nevents * (t + 1) / nt; e++) {
+      auto &ev = particle_event_list[e];
+      ev.resize((size_t)counts[e]);
+      for (int64_t i = 0; i < counts[e]; i++) {
+        const is3d_particle_compact &q = plist[first[e] + i];
+        const particle_info &info = (*particles)[chosen_particles_sampling_table[q.chosen_index]];
+        Sampled_Particle &p = ev[(size_t)i];
+        p.chosen_index = q.chosen_index; p.mcID = (int)info.mc_id; p.mass = info.mass;
+        p.tau = q.tau; p.x = q.x; p.y = q.y; p.eta = q.eta;
+        const double sh = sinh(q.eta);
+        p.t = q.tau * sqrt(1.0 + sh * sh); p.z = q.tau * sh;
+        p.px = q.px; p.py = q.py; p.pz = q.pz;
+        p.E = sqrt(info.mass * info.mass + q.px * q.px + q.py * q.py + q.pz * q.pz);
+      }
+    }
+  });
   is3d_free_particles(plist);
   if (stats.sampler_proposals > 0)
     printf("\nMomentum sampling efficiency = %f %%\n", 100.0 * (double)stats.sampler_accepted / (double)stats.sampler_proposals);
