@@ -293,6 +293,10 @@ is3d_status is3d_measure_fp64_peak(is3d_ctx *ctx, double *tflops);
  * The parity tests bound their error against libm. */
 is3d_status is3d_probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp,
                             double *out_sqrt);
+/* same for the angular primitives of the df_mode 5 (PTMA) solve: for x > 0, atan(sqrt x)/sqrt x, atanh(sqrt x)/sqrt x (x < 1;
+ * 0 is returned for x >= 1) and ln x, computed by the FP64-pipe approximations of csrc/aniso.cuh */
+is3d_status is3d_probe_aniso_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_atan_over_s, double *out_atanh_over_s,
+                                  double *out_log);
 /* Host-only helper (no context, no GPU): the species classes and thread groups the spectra and dN/dX kernels use.
  * Hadrons with the same (mass, quantum-statistics sign[, baryon number when include_baryon]) form one class (their
  * Cooper-Frye integrands differ only by the degeneracy, which the reference multiplies in front:
@@ -302,6 +306,8 @@ is3d_status is3d_probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *o
  * is too small, -3 for a baryon number outside -2 .. 2 (the reference's PDG readers produce hadrons and the deuteron). */
 int         is3d_species_groups(int ns, const double *mass, const double *sign, const double *baryon, int include_baryon,
                                 int slots_per_group, int *class_of, int *slot_class, int capacity, int *nclass);
+/* device -> host copy on the context's stream (e.g. to inspect the list of is3d_sample_device without a CUDA runtime of one's own) */
+is3d_status is3d_copy_from_device(is3d_ctx *ctx, void *host, const void *device, size_t bytes);
 /* the CUDA stream all kernels of this context are launched on (as a void* cudaStream_t) */
 void       *is3d_stream(is3d_ctx *ctx);
 

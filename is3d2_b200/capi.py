@@ -63,8 +63,8 @@ ABI_SYMBOLS = ["is3d_default_params", "is3d_create", "is3d_destroy", "is3d_last_
                "is3d_set_thermo_averages", "is3d_set_df_tables", "is3d_set_ptb_tables", "is3d_set_surface",
                "is3d_set_surface_device", "is3d_spectra_size", "is3d_spectra", "is3d_spectra_device", "is3d_dndx",
                "is3d_dndx_device", "is3d_total_yield", "is3d_cell_yields", "is3d_sample", "is3d_free_particles", "is3d_sample_compact", "is3d_sample_device", "is3d_expand_particles",
-               "is3d_sample_histograms", "is3d_set_vorticity", "is3d_polarization", "is3d_measure_fp64_peak", "is3d_probe_math",
-               "is3d_species_groups", "is3d_stream",
+               "is3d_sample_histograms", "is3d_set_vorticity", "is3d_polarization", "is3d_measure_fp64_peak", "is3d_probe_math", "is3d_probe_aniso_math",
+               "is3d_species_groups", "is3d_stream", "is3d_copy_from_device",
                "is3d_comm_unique_id", "is3d_comm_attach", "is3d_comm_detach", "is3d_comm_size", "is3d_comm_collectives",
                "is3d_comm_last_error", "is3d_group_create", "is3d_group_destroy", "is3d_group_size", "is3d_group_ctx",
                "is3d_group_last_error", "is3d_group_cell_block", "is3d_group_set_surface", "is3d_group_set_vorticity",
@@ -116,6 +116,8 @@ def load_libraries():
     lib.is3d_set_vorticity.argtypes = [vp, C.c_int64, C.POINTER(vp)]
     lib.is3d_polarization.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Stats)]
     lib.is3d_probe_math.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+    lib.is3d_probe_aniso_math.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+    lib.is3d_copy_from_device.argtypes = [vp, vp, vp, C.c_size_t]
     lib.is3d_stream.restype = vp
     lib.is3d_stream.argtypes = [vp]
     host.is3d_host_open.restype = vp
@@ -313,6 +315,12 @@ class HostSession:
         e, r, s = np.empty_like(x), np.empty_like(x), np.empty_like(x)
         self._check(self.lib.is3d_probe_math(self.ctx, x.size, _ptr(x), _ptr(e), _ptr(r), _ptr(s)), "is3d_probe_math")
         return e, r, s
+
+    def abi_probe_aniso_math(self, x: np.ndarray):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        a, b, c = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+        self._check(self.lib.is3d_probe_aniso_math(self.ctx, x.size, _ptr(x), _ptr(a), _ptr(b), _ptr(c)), "is3d_probe_aniso_math")
+        return a, b, c
 
     # ---- results kept by the host layer ------------------------------------------------------------------
     def spectra(self) -> np.ndarray:

@@ -86,6 +86,48 @@ IS3D_HD double fast_atan(double s)
 #endif
 }
 
+// ln(v) for normal v > 0 in the FP64 FMA pipe: v = 2^k m with m in [0.75, 1.5), ln m = 2 atanh(f), f = (m - 1)/(m + 1),
+// |f| <= 0.2, odd series to f^23 (truncation f^24/25 < 7e-19 relative to 2f); one reciprocal seed, no libm.
+IS3D_HD double fast_log(double v)
+{
+#if defined(__CUDA_ARCH__)
+  int hi = __double2hiint(v);
+  const int lo = __double2loint(v);
+  int k = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;                   // m in [1, 2)
+  if (hi >= 0x3ff80000) { hi -= 0x00100000; k++; }       // m >= 1.5: halve it
+  const double m = __hiloint2double(hi, lo);
+  const double f = (m - 1.0) * fast_rcp(m + 1.0), f2 = f * f;
+  double p = fma(f2, 1.0 / 23.0, 1.0 / 21.0);
+  p = fma(p, f2, 1.0 / 19.0); p = fma(p, f2, 1.0 / 17.0); p = fma(p, f2, 1.0 / 15.0); p = fma(p, f2, 1.0 / 13.0);
+  p = fma(p, f2, 1.0 / 11.0); p = fma(p, f2, 1.0 / 9.0); p = fma(p, f2, 1.0 / 7.0); p = fma(p, f2, 1.0 / 5.0);
+  p = fma(p, f2, 1.0 / 3.0);
+  const double lnm = fma(2.0 * f, f2 * p, 2.0 * f);
+  // k ln2 in two pieces (hi part exact for |k| < 2^11): ln v = k ln2_hi + (k ln2_lo + ln m)
+  const double kd = (double)k;
+  return fma(kd, 6.93147180369123816490e-01, fma(kd, 1.90821492927058770002e-10, lnm));
+#else
+  return log(v);
+#endif
+}
+
+// atanh(s) / s for 0 < s < 1 given s and 1/s: atanh(s) = ln((1 + s)/(1 - s)) / 2 through log1p(u), u = 2 s / (1 - s), with the
+// rounding of 1 + u compensated (ln(1 + u) = ln(v) + (u - (v - 1)) / v, v = fl(1 + u)) so that small s keeps its relative
+// accuracy: the closed forms of the angular functions divide by z = -s^2 once or twice (AnisoVariables.cpp:72-89).
+IS3D_HD double fast_atanh_over_s(double s, double is)
+{
+#if defined(__CUDA_ARCH__)
+  const double u = 2.0 * s * fast_rcp(1.0 - s);
+  const double v = 1.0 + u;
+  const double c = u - (v - 1.0);
+  const double l = fma(c, fast_rcp(v), fast_log(v));
+  return 0.5 * l * is;
+#else
+  (void)is;
+  return atanh(s) / s;
+#endif
+}
+
 // hypergeometric-type angular functions of z = (aT^2 - aL^2) / w^2 (closed forms for |z| > delta, series inside)
 struct AnisoT { double t200, t220, t201, t402, t421, t440; };
 
@@ -100,6 +142,7 @@ IS3D_HD AnisoT aniso_t_functions(double z, bool need_j, bool exact)
     double t, iz;
     if (z > 0.0 && !exact) { double s, is; fast_sqrt_rsqrt(z, &s, &is); t = fast_atan(s) * is; iz = is * is; }
     else if (z > 0.0) { double s = sqrt(z); t = atan(s) / s; iz = 1.0 / z; }
+    else if (!exact) { double s, is; fast_sqrt_rsqrt(-z, &s, &is); t = fast_atanh_over_s(s, is); iz = -(is * is); }
     else { double s = sqrt(-z); t = atanh(s) / s; iz = 1.0 / z; }
     if (exact) {             // AnisoVariables.cpp:72-89, :206-231 verbatim (divisions, not reciprocal multiplies)
       r.t200 = 1. + (1. + z) * t;

@@ -93,6 +93,7 @@ void is3d_destroy(is3d_ctx *ctx)
   comm_release(ctx);
   for (void *p : ctx->owned) cudaFree(p);
   release_host_lists_of(ctx);
+  if (ctx->h_words) cudaFreeHost((void *)ctx->h_words);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (int k = 0; k < 2; k++) {
     if (ctx->ev_sorted[k]) cudaEventDestroy(ctx->ev_sorted[k]);
@@ -416,6 +417,15 @@ is3d_status is3d_polarization(is3d_ctx *ctx, double *St, double *Sx, double *Sy,
   return IS3D_OK;
 }
 
+is3d_status is3d_copy_from_device(is3d_ctx *ctx, void *host, const void *device, size_t bytes)
+{
+  CTX_ENTER(ctx);
+  if (bytes && (!host || !device)) { ctx->set_error("copy_from_device: NULL pointer"); return IS3D_ERR_INVALID; }
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(host, device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return IS3D_OK;
+}
+
 is3d_status is3d_measure_fp64_peak(is3d_ctx *ctx, double *tflops)
 {
   CTX_ENTER(ctx);
@@ -427,6 +437,13 @@ is3d_status is3d_probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *o
   CTX_ENTER(ctx);
   if (n <= 0 || !x || !out_exp || !out_rcp || !out_sqrt) { ctx->set_error("probe_math: bad arguments"); return IS3D_ERR_INVALID; }
   return probe_math(ctx, n, x, out_exp, out_rcp, out_sqrt);
+}
+
+is3d_status is3d_probe_aniso_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_atan_over_s, double *out_atanh_over_s, double *out_log)
+{
+  CTX_ENTER(ctx);
+  if (n <= 0 || !x || !out_atan_over_s || !out_atanh_over_s || !out_log) { ctx->set_error("probe_aniso_math: bad arguments"); return IS3D_ERR_INVALID; }
+  return probe_aniso_math(ctx, n, x, out_atan_over_s, out_atanh_over_s, out_log);
 }
 
 }  // extern "C"

@@ -34,6 +34,8 @@ struct is3d_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // timing events of the compute calls (created once, destroyed with the context)
   // sampler copy pipeline (sampler.cu): pass k's D2H on copy_stream overlaps pass k + 1's kernels on `stream`
+  volatile unsigned long long *h_words = nullptr;   // mapped pinned words: control scalars the device publishes to the host
+  unsigned long long *d_words = nullptr;            // their device address
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_sorted[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   std::string err;
@@ -185,5 +187,6 @@ void comm_release(is3d_ctx *ctx);
 is3d_status run_polarization(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);
 is3d_status measure_fp64_peak(is3d_ctx *ctx, double *tflops);
 is3d_status probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp, double *out_sqrt);
+is3d_status probe_aniso_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_atan, double *out_atanh, double *out_log);
 
 }  // namespace is3d

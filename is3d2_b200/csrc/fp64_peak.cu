@@ -1,5 +1,6 @@
 // DFMA micro-benchmark: the measured FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry).
 #include "ctx.h"
+#include "aniso.cuh"
 #include "spectra_feqmod.cuh"
 
 namespace is3d {
@@ -41,7 +42,37 @@ __global__ void probe_math_kernel(const double *__restrict__ x, int64_t n, const
     out_sqrt[i] = fast_sqrt(v);
   }
 }
+
+// angular primitives of the df_mode 5 solve (aniso.cuh): atan(sqrt(x))/sqrt(x) and atanh(sqrt(x))/sqrt(x) as the term sums
+// form them, and ln(x)
+__global__ void probe_aniso_math_kernel(const double *__restrict__ x, int64_t n, double *__restrict__ out_atan, double *__restrict__ out_atanh,
+                                        double *__restrict__ out_log)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double z = x[i];
+    double s, is;
+    fast_sqrt_rsqrt(z, &s, &is);
+    out_atan[i] = fast_atan(s) * is;
+    out_atanh[i] = (z < 1.0) ? fast_atanh_over_s(s, is) : 0.0;
+    out_log[i] = fast_log(z);
+  }
+}
 }  // namespace
+
+is3d_status probe_aniso_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_atan, double *out_atanh, double *out_log)
+{
+  void *d = nullptr;
+  IS3D_TRY(ctx->get_scratch("probe_math", (size_t)4 * n * sizeof(double), &d));
+  double *dx = (double *)d;
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  probe_aniso_math_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dx, n, dx + n, dx + 2 * n, dx + 3 * n);
+  IS3D_CUDA_TRY(ctx, cudaGetLastError());
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(out_atan, dx + n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(out_atanh, dx + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(out_log, dx + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return IS3D_OK;
+}
 
 is3d_status probe_math(is3d_ctx *ctx, int64_t n, const double *x, double *out_exp, double *out_rcp, double *out_sqrt)
 {

@@ -34,3 +34,29 @@ def test_fast_math_against_libm(libs, tmp_path):
     # x is clamped at 680 (and NaN behaves like it): "huge" and finite, so that 1/(e^x + s) is the reference's 0 to more
     # than 200 decades and e^x times an energy ratio still fits a double
     assert np.all(far >= 2e295) and np.all(far <= 3e295)
+
+
+def test_aniso_angular_primitives_against_libm(libs, tmp_path):
+    """df_mode 5 (PTMA) term sums: atan(s)/s for z = s^2 > 0 and atanh(s)/s for z = -s^2 in (-1, 0), and ln (csrc/aniso.cuh
+    fast_atan / fast_atanh_over_s / fast_log) against long-double libm.  The closed forms of the angular functions divide by
+    z up to twice, so t = atan(s)/s resp. atanh(s)/s must be good to a few ulp RELATIVE down to |z| = 0.01."""
+    name = "s3d_m1"
+    surf, _ = harness.load_golden(name)
+    rng = np.random.default_rng(11)
+    z = np.concatenate([rng.uniform(0.01, 0.999999, 300_000), np.exp(rng.uniform(np.log(0.01), 0.0, 100_000)) * 0.999999,
+                        np.array([0.01, 0.0100001, 0.25, 0.5, 0.9, 0.99, 0.999999])])
+    big = np.concatenate([np.exp(rng.uniform(-30.0, 30.0, 200_000)), rng.uniform(0.5, 2.0, 100_000), np.array([1.0, 1.5, 0.75, 2.0, 1e-300, 1e300])])
+    with harness.open_session(str(tmp_path), cases.SPECTRA_CASES[name], surf) as h:
+        a, b, _ = h.abi_probe_aniso_math(z)
+        a2, _, lg = h.abi_probe_aniso_math(big)
+    zl = z.astype(np.longdouble)
+    s = np.sqrt(zl)
+    ref_atan = np.arctan(s) / s
+    ref_atanh = np.arctanh(s) / s
+    assert np.abs((a - ref_atan) / ref_atan).astype(np.float64).max() < 1e-15
+    assert np.abs((b - ref_atanh) / ref_atanh).astype(np.float64).max() < 1e-15
+    sb = np.sqrt(big.astype(np.longdouble))
+    assert np.abs((a2 - np.arctan(sb) / sb) / (np.arctan(sb) / sb)).astype(np.float64).max() < 1e-15
+    ref_log = np.log(big.astype(np.longdouble))
+    err = np.abs(lg - ref_log).astype(np.float64)
+    assert np.all(err <= 4e-16 * np.maximum(np.abs(ref_log.astype(np.float64)), 1e-2)), err.max()

@@ -158,13 +158,9 @@ def test_wire_records_device_list_and_full_records_are_the_same_hadrons(libs, tm
         wire, cw, _ = h.abi_sample_compact(nev)
         back = h.abi_expand(wire)
         dev_ptr, total, cd, _ = h.abi_sample_device(nev)
-        # read the device list back with a plain cudaMemcpy through torch
-        import torch
         n = int(total)
-        raw = torch.empty(n * capi.PARTICLE_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-        cudart = torch.cuda.cudart()
-        assert int(cudart.cudaMemcpy(raw.data_ptr(), dev_ptr, raw.numel(), 3)) == 0           # cudaMemcpyDeviceToDevice
-        dev = np.frombuffer(raw.cpu().numpy().tobytes(), dtype=capi.PARTICLE_DTYPE)
+        dev = np.zeros(n, dtype=capi.PARTICLE_DTYPE)
+        h._check(h.lib.is3d_copy_from_device(h.ctx, dev.ctypes.data, dev_ptr, n * capi.PARTICLE_DTYPE.itemsize), "is3d_copy_from_device")
     assert len(full) == len(wire) == len(dev) > 5000 and st.sampler_accepted == len(full)
     assert np.array_equal(cf, cw) and np.array_equal(cf, cd)
     assert np.array_equal(full, dev)
@@ -186,8 +182,8 @@ def test_streamed_passes_do_not_change_the_list(libs, tmp_path, monkeypatch):
     nev = 2500
     with harness.open_session(str(tmp_path), case, surf, overrides=dict(test_sampler=0)) as h:
         one, c1, s1 = h.abi_sample_compact(nev)
-        monkeypatch.setenv("IS3D_SAMPLER_PASS_PROPOSALS", "3000")
+        monkeypatch.setenv("IS3D_SAMPLER_PASS_PROPOSALS", "1000")       # a few 64-event blocks per pass
         many, c2, s2 = h.abi_sample_compact(nev)
-    assert len(one) > 20000
-    assert s2.kernel_launches > 3 * s1.kernel_launches          # really many passes
+    assert len(one) > 2000, len(one)
+    assert s2.kernel_launches > 3 * s1.kernel_launches, (s1.kernel_launches, s2.kernel_launches)   # really many passes
     assert np.array_equal(c1, c2) and np.array_equal(one, many)
