@@ -77,13 +77,14 @@ HOST_SYMBOLS = ["is3d_host_open", "is3d_host_close", "is3d_host_read_surface", "
                 "is3d_host_surface_column", "is3d_host_chosen", "is3d_host_thermo_sums", "is3d_host_set_thermo_averages"]
 
 
-def load_libraries():
-    """Load the in-tree shared libraries; fails loudly if they were not built (python -m is3d2_b200.build)."""
+def load_libraries(libdir: str | None = None):
+    """Load the in-tree shared libraries; fails loudly if they were not built (python -m is3d2_b200.build).
+    libdir: directory holding another build of the two libraries (launch-shape variants under tools/; first call only)."""
     global _lib, _host
     if _lib is not None:
         return _lib, _host
-    p = os.path.join(HERE, "libis3d_b200.so")
-    ph = os.path.join(HERE, "libis3d_host.so")
+    p = os.path.join(libdir or HERE, "libis3d_b200.so")
+    ph = os.path.join(libdir or HERE, "libis3d_host.so")
     if not os.path.exists(p) or not os.path.exists(ph):
         raise Is3dError(f"{p} / {ph} not built: run `python -m is3d2_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
     lib = C.CDLL(p, mode=C.RTLD_GLOBAL)

@@ -176,7 +176,7 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
             auto pk = [&](int k) { return pack[k * stride + cell]; };
             const DndxPoint pt = dndx_point(g, pk, j);
             const double d = pt.yval - pt.eta;
-            items[t] = df_make_item_u<MODE, BARYON>(pk, sinh(d), cosh(d), pt.cphi, pt.sphi, pt.w);
+            items[t] = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sinh(d), cosh(d), pt.cphi, pt.sphi, pt.w);
           }
         }
       }
@@ -188,7 +188,7 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
 #pragma unroll 1
           for (int k = 0; k < np_tile; k++) {
             const DfItemU &it = items[cl * np_tile + k];
-            const DfSharedU sh = df_share_u<MODE, BARYON>(it, tu);
+            const DfSharedU sh = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, tu);
 #pragma unroll
             for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, th.mT[r], th.mT2[r], th.sgn[r], exptab);
           }

@@ -35,6 +35,9 @@ namespace {
 #ifndef IS3D_K1_ITEM_UNROLL
 #define IS3D_K1_ITEM_UNROLL 1
 #endif
+#ifndef IS3D_K1_PREFETCH
+#define IS3D_K1_PREFETCH 0      // 1: the head of item k + 1 (aT bT c1 d1) is loaded while item k is evaluated
+#endif
 constexpr int kItemUnroll = IS3D_K1_ITEM_UNROLL;   // items per trip of the momentum loop
 constexpr int kThreads = IS3D_K1_THREADS;
 constexpr int kTile = kThreads;  // cells per shared-memory tile = threads per block
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, IS3D_K1_MINBLOCKS)
 df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk, DfGrid g,
                   double *__restrict__ partial, int64_t total)
 {
-  __shared__ DfItemU items[kTile];
+  __shared__ DfItemU items[kTile + IS3D_K1_PREFETCH];
   __shared__ double exptab[kExpTableSize];
   __shared__ int warp_count[kThreads / 32];
   load_exp_table(exptab, g.exptab);                 // visible after the first __syncthreads of the tile loop
@@ -129,16 +132,31 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         double sh = sinh(yval - eta);
         double ch = sqrt(1.0 + sh * sh);     // the reference's cosh (MomentumSpectra.cpp:307-308)
         auto pk = [&](int k) { return pack[k * stride + cell]; };
-        items[base + __popc(ballot & ((1u << lane) - 1u))] = df_make_item_u<MODE, BARYON>(pk, sh, ch, cphi, sphi, w);
+        items[base + __popc(ballot & ((1u << lane) - 1u))] = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sh, ch, cphi, sphi, w);
       }
       __syncthreads();
+#if IS3D_K1_PREFETCH
+      // the head of the dependency chain of item k + 1 (x_E = mT aT - pT bT) is in registers before item k is finished
+      double n_aT = items[0].aT, n_pb = th.pT * items[0].bT;
+#pragma unroll 1
+      for (int k = 0; k < n_items; k++) {
+        const DfItemU &it = items[k];
+        DfSharedU sh = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, th);
+        sh.pb = n_pb;
+        const double aT = n_aT;
+        n_aT = items[k + 1].aT; n_pb = th.pT * items[k + 1].bT;          // slot n_items exists (never evaluated)
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], exptab, aT);
+      }
+#else
 #pragma unroll kItemUnroll
       for (int k = 0; k < n_items; k++) {
         const DfItemU &it = items[k];          // shared memory: fields arrive as broadcast LDS.128, eb[eslot] as one LDS.64
-        const DfSharedU sh = df_share_u<MODE, BARYON>(it, th);
+        const DfSharedU sh = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, th);
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], exptab);
       }
+#endif
     }
   }
 

@@ -223,6 +223,14 @@ IS3D_HD double df_eval(const DfItem &it, const DfShared &s, const DfBin &b, cons
 // FP64-pipe instructions per evaluation with baryon terms (SASS, R = 4): mode 1 28.7 -> 20.5, mode 2 31.7 -> 26.
 // eb[2 + b] = exp(-b alpha_B) for b = -2 .. 2: hadrons and the deuteron, the only nucleus the reference's PDG readers
 // produce (readindata.cpp:1098-1214); a thread reads the slot of its group's baryon number with one LDS.64.
+//
+// df_mode 2 without regulate_deltaf goes one step further (FOLD): with y = 1/((e^x + sign) xE), feq = y xE and 1/xE = y (e^x + sign),
+//       feq (1 + df) = y xE + y feqbar [quad + lin xE] = y (xE + feqbar quad'),   quad' = quad + lin xE,
+// and quad' is again a quadratic form in mT whose coefficients are formed per (item, thread):
+//       q1' = q1 + L1 aT (per item),  A' = A + C aT - L1 pT bT,  B' = B - C pT bT       (lin = mT L1 + C)
+// without baryon terms (lin = K0 xE):  q1' = q1 + K0 aT^2,  A' = A - 2 K0 aT pT bT,  B' = B + K0 (pT bT)^2.
+// The evaluation then needs neither 1/xE nor df itself: 24 instead of 26 FP64-pipe instructions (regulate_deltaf clamps
+// df, so that variant keeps the explicit form).
 constexpr int kMaxBaryon = 2;
 struct alignas(16) DfItemU {
   double aT, bT, c1, d1;
@@ -231,7 +239,7 @@ struct alignas(16) DfItemU {
   double eb[2 * kMaxBaryon + 1];
 };
 
-template <int MODE, bool BARYON, class PackFn>
+template <int MODE, bool BARYON, bool FOLD = false, class PackFn>
 IS3D_HD DfItemU df_make_item_u(PackFn pk, double sh, double ch, double cphi, double sphi, double w)
 {
   DfItemU it;
@@ -265,6 +273,10 @@ IS3D_HD DfItemU df_make_item_u(PackFn pk, double sh, double ch, double cphi, dou
     it.q1 = q1; it.q2 = q2; it.q3 = q3;
     it.L1 = BARYON ? K0 * aT + G0 * v1 : K0;
     it.L2 = K0 * bT + G0 * v2;
+    if (FOLD) {
+      it.q1 = fma(it.L1, aT, q1);                                   // q1 + L1 aT
+      if (!BARYON) { it.q1 = fma(K0 * aT, aT, q1); it.L2 = 2.0 * K0 * aT; }   // L2 slot: 2 K0 aT
+    }
   }
   it.K1 = K1; it.Gv1 = G1 * v1; it.Gv2 = G1 * v2;
   return it;
@@ -281,7 +293,7 @@ struct DfSharedU {
   double pb, pd, A, B, C, eb;
 };
 
-template <int MODE, bool BARYON>
+template <int MODE, bool BARYON, bool FOLD = false>
 IS3D_HD DfSharedU df_share_u(const DfItemU &it, const DfThreadU &th)
 {
   DfSharedU s;
@@ -300,21 +312,44 @@ IS3D_HD DfSharedU df_share_u(const DfItemU &it, const DfThreadU &th)
       s.B = fma(th.bpT, it.Gv2, s.B);
       s.C = fma(it.K1, th.b, -th.pT * it.L2);
     }
+    if (FOLD) {                                  // quad' = quad + lin xE (see above)
+      if (BARYON) {
+        s.A = fma(-it.L1, s.pb, fma(s.C, it.aT, s.A));
+        s.B = fma(-s.C, s.pb, s.B);
+      } else {
+        s.A = fma(-it.L2, s.pb, s.A);              // L2 slot = 2 K0 aT
+        s.B = fma(it.L1 * s.pb, s.pb, s.B);        // L1 = K0
+      }
+    }
   }
   if (BARYON) s.eb = it.eb[th.eslot];
   return s;
 }
 
-// One integrand evaluation w p.dsigma feq (1 + df) on the uniform-baryon path (MomentumSpectra.cpp:304-361)
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, const double *__restrict__ exptab);
+
+// One integrand evaluation w p.dsigma feq (1 + df) on the uniform-baryon path (MomentumSpectra.cpp:304-361); aT = the item's
+// aT, passed separately so that a caller can hold it in a register ahead of the rest of the item
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
 IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign,
-                         const double *__restrict__ exptab)
+                         const double *__restrict__ exptab, double aT)
 {
   // clamped in place (x <= 680, common.cuh): beyond that feq < 1e-295 and every later use of xE multiplies feq
-  const double xE = clamp_hi_word_680(fma(mT, it.aT, -s.pb));
+  const double xE = clamp_hi_word_680(fma(mT, aT, -s.pb));
   const double e = fast_exp<false>(xE, exptab);
   const double q = BARYON ? fma(e, s.eb, sign) : e + sign;         // e^x + sign, x = xE - b alpha_B
   const double quad = fma(mT2, it.q1, fma(mT, s.A, s.B));
+  if (MODE == 2 && !REGULATE) {
+    // folded form: (it.q1, s.A, s.B) hold quad' = quad + lin xE (df_make_item_u / df_share_u with FOLD = true)
+    const double y = fast_rcp(q * xE);
+    const double feq = y * xE;
+    const double feqbar = fma(-sign, feq, 1.0);
+    const double pds = fma(mT, it.c1, s.pd);
+    double contrib = (pds * y) * fma(feqbar, quad, xE);
+    if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
+    return contrib;
+  }
   double feq, dfv;
   if (MODE == 1) {
     feq = fast_rcp(q);
@@ -334,6 +369,12 @@ IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, doubl
   double contrib = pds * fma(feq, df, feq);
   if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
   return contrib;
+}
+
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, const double *__restrict__ exptab)
+{
+  return df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, s, mT, mT2, sign, exptab, it.aT);
 }
 
 }  // namespace is3d

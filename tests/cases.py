@@ -99,6 +99,11 @@ BIG_SPECTRA_CASES = {
                                             params=_p(df_mode=2, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
 }
 
+# executable-level golden (tests/golden/make_golden_exe_tree.py): BASELINE.json config 5 in miniature -- MUSIC-format
+# (mode 6) surface.dat of the benchmark surface's first 256 cells, all SMASH species, df_mode 2 + baryon diffusion
+EXE_TREE_CASE = dict(surface=("bench", dict(begin=0, end=256)),
+                     params=_p(mode=6, df_mode=2, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash")
+
 # df_mode 5 under the chain-free initial-guess policy: goldens are sums of ONE-CELL runs of the unmodified reference
 # (tests/golden/make_golden_m5_chainfree.py)
 M5_CHAINFREE_CASES = {

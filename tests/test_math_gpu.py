@@ -53,10 +53,20 @@ def test_aniso_angular_primitives_against_libm(libs, tmp_path):
     s = np.sqrt(zl)
     ref_atan = np.arctan(s) / s
     ref_atanh = np.arctanh(s) / s
-    assert np.abs((a - ref_atan) / ref_atan).astype(np.float64).max() < 1e-15
-    assert np.abs((b - ref_atanh) / ref_atanh).astype(np.float64).max() < 1e-15
+    e_atan = np.abs((a - ref_atan) / ref_atan).astype(np.float64)
+    e_atanh = np.abs((b - ref_atanh) / ref_atanh).astype(np.float64)
+    # atanh is ill-conditioned towards s -> 1: the (correctly rounded or not) sqrt's last bit is amplified by
+    # kappa = s / ((1 - s^2) atanh s); the reference's own sqrt + atanh carries the same factor
+    kappa = (s / ((1 - zl) * np.arctanh(s))).astype(np.float64)
+    print(f"atan(s)/s max rel err {e_atan.max():.2e}; atanh(s)/s max rel err / (1 + kappa) {(e_atanh / (1 + kappa)).max():.2e}")
+    assert e_atan.max() < 1e-15, (e_atan.max(), z[np.argmax(e_atan)])
+    assert np.all(e_atanh <= 6e-16 * (1.0 + kappa)), (float((e_atanh / (1 + kappa)).max()), z[np.argmax(e_atanh / (1 + kappa))])
     sb = np.sqrt(big.astype(np.longdouble))
-    assert np.abs((a2 - np.arctan(sb) / sb) / (np.arctan(sb) / sb)).astype(np.float64).max() < 1e-15
+    e2 = np.abs((a2 - np.arctan(sb) / sb) / (np.arctan(sb) / sb)).astype(np.float64)
+    assert e2.max() < 1e-15, (e2.max(), big[np.argmax(e2)])
     ref_log = np.log(big.astype(np.longdouble))
     err = np.abs(lg - ref_log).astype(np.float64)
-    assert np.all(err <= 4e-16 * np.maximum(np.abs(ref_log.astype(np.float64)), 1e-2)), err.max()
+    # relative 4e-16 away from ln 1 = 0; near v = 1 the absolute error is bounded by the rounding of v - 1 itself
+    bound = 4e-16 * np.maximum(np.abs(ref_log.astype(np.float64)), 1e-3)
+    print(f"ln max err / bound {(err / bound).max():.2e}")
+    assert np.all(err <= bound), (float((err / bound).max()), big[np.argmax(err / bound)])
