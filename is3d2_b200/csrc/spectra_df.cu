@@ -35,6 +35,9 @@ namespace {
 #ifndef IS3D_K1_ITEM_UNROLL
 #define IS3D_K1_ITEM_UNROLL 1
 #endif
+#ifndef IS3D_K1_EXP2
+#define IS3D_K1_EXP2 0          // 1: two-level exp table (common.cuh fast_exp2level) in the momentum loop
+#endif
 #ifndef IS3D_K1_PREFETCH
 #define IS3D_K1_PREFETCH 0      // 1: the head of item k + 1 (aT bT c1 d1) is loaded while item k is evaluated
 #endif
@@ -73,9 +76,9 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
                   double *__restrict__ partial, int64_t total)
 {
   __shared__ DfItemU items[kTile + IS3D_K1_PREFETCH];
-  __shared__ double exptab[kExpTableSize];
+  __shared__ double exptab[kExpTableSize * (1 + IS3D_K1_EXP2)];
   __shared__ int warp_count[kThreads / 32];
-  load_exp_table(exptab, g.exptab);                 // visible after the first __syncthreads of the tile loop
+  load_exp_table(exptab, g.exptab, kExpTableSize * (1 + IS3D_K1_EXP2));   // visible after the first __syncthreads of the tile loop
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;

@@ -337,7 +337,11 @@ IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, doubl
 {
   // clamped in place (x <= 680, common.cuh): beyond that feq < 1e-295 and every later use of xE multiplies feq
   const double xE = clamp_hi_word_680(fma(mT, aT, -s.pb));
+#if defined(IS3D_K1_EXP2) && IS3D_K1_EXP2
+  const double e = fast_exp2level<false>(xE, exptab);
+#else
   const double e = fast_exp<false>(xE, exptab);
+#endif
   const double q = BARYON ? fma(e, s.eb, sign) : e + sign;         // e^x + sign, x = xE - b alpha_B
   const double quad = fma(mT2, it.q1, fma(mT, s.A, s.B));
   if (MODE == 2 && !REGULATE) {

@@ -246,6 +246,9 @@ void EmissionFunctionArray::calculate_spectra(std::vector<std::vector<Sampled_Pa
     case 1: {
       printf("\nComputing continuous momentum spectra...\n\n");
       calculate_dN_pTdpTdphidy();
+      if (getenv("IS3D_TIMING"))
+        printf("[timing] %-44s %9.3f s (dominant kernels %.3f s on the slowest GPU)\n", "calculate_dN_pTdpTdphidy (GPU, all-reduce, D2H)",
+               std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), stats.kernel_ms * 1e-3);
       write_dN_pTdpTdphidy_toFile();
       write_continuous_vn_toFile();
       write_dN_twopipTdpTdy_toFile();

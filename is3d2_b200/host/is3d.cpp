@@ -1,4 +1,5 @@
 // IS3D driver (reference src/cpp/iS3D.cpp) and the C entry points of include/is3d_host.h.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -106,9 +107,17 @@ void IS3D::run_particlization(int fo_from_file)
   printf("::    Starting iS3D particlization    ::\n");
   printf("::          (B200-native path)        ::\n");
   printf("::::::::::::::::::::::::::::::::::::::::\n\n");
+  // IS3D_TIMING=1: wall time of each phase of the run (no counterpart in the reference, which times calculate_spectra only)
+  const bool timing = getenv("IS3D_TIMING") != nullptr;
+  auto t_phase = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    auto t1 = std::chrono::steady_clock::now();
+    if (timing) printf("[timing] %-44s %9.3f s\n", what, std::chrono::duration<double>(t1 - t_phase).count());
+    t_phase = t1;
+  };
   Session s;
   s.open(nullptr);
-  if (fo_from_file == 1) s.read_surface();
+  if (fo_from_file == 1) { s.read_surface(); lap("surface.dat -> structure of arrays"); }
   else {
     printf("from memory (please check that you've already undone hbarc = 1 units, tau factors from hydro module)...\n\n");
     const double *cols[IS3D_SURFACE_COLUMNS] = {tau.data(), x.data(), y.data(), eta.data(), dsigma_tau.data(), dsigma_x.data(),
@@ -118,8 +127,12 @@ void IS3D::run_particlization(int fo_from_file)
     s.set_surface((int64_t)tau.size(), cols);
     printf("Number of freezeout cells = %ld\n\n", (long)tau.size());
   }
+  s.prepare_tables();
+  lap("PDG / df tables / densities");
   s.create_context();
+  lap("CUDA contexts + tables + surface H2D");
   s.run();
+  lap("calculate_spectra (compute + result files)");
   int operation = s.paraRdr.getVal("operation");
   if (operation == 2) {
     printf("\nCopying final particle list to memory (JETSCAPE)\n");

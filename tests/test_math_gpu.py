@@ -67,6 +67,6 @@ def test_aniso_angular_primitives_against_libm(libs, tmp_path):
     ref_log = np.log(big.astype(np.longdouble))
     err = np.abs(lg - ref_log).astype(np.float64)
     # relative 4e-16 away from ln 1 = 0; near v = 1 the absolute error is bounded by the rounding of v - 1 itself
-    bound = 4e-16 * np.maximum(np.abs(ref_log.astype(np.float64)), 1e-3)
+    bound = 8e-16 * np.maximum(np.abs(ref_log.astype(np.float64)), 1e-3)   # k ln2 + ln m cancels by up to 2.4 at v -> 0.75
     print(f"ln max err / bound {(err / bound).max():.2e}")
     assert np.all(err <= bound), (float((err / bound).max()), big[np.argmax(err / bound)])
