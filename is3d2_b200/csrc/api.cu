@@ -73,9 +73,8 @@ is3d_status is3d_create(const is3d_params *p, is3d_ctx **out)
     return IS3D_ERR_CUDA;
   }
   {
-    std::vector<double> tab(2 * kExpTableSize);          // [0, 1024): 2^(m/1024); [1024, 2048): 2^(i/2^20) (fast_exp2level)
+    std::vector<double> tab(kExpTableSize);
     fill_exp_table(tab.data());
-    fill_exp_table2(tab.data() + kExpTableSize);
     if (ctx->upload(&ctx->d_exptab, tab.data(), tab.size()) != IS3D_OK) {
       g_create_error = ctx->err;
       is3d_destroy(ctx);

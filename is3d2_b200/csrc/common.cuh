@@ -132,44 +132,6 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
 #endif
 }
 
-// Two-level variant for the df_mode 1 / 2 momentum loops (experimental, IS3D_K1_EXP2): x = k (ln2 / 2^20) + r with
-// |r| <= ln2 / 2^21 = 3.3e-7, e^x = 2^(k >> 20) T[(k >> 10) & 1023] U[k & 1023] (1 + r), U[i] = 2^(i / 2^20) in a second
-// 1024-entry table.  5 FP64 instructions instead of 7 (no polynomial) for one more table read; the dropped r^2/2 is at most
-// 5.5e-14 relative (mean 1.8e-14, one-sided).  tab2 = tab + kExpTableSize.
-template <bool CLAMP = true>
-IS3D_HD double fast_exp2level(double x, const double *__restrict__ tab)
-{
-  const double kInv = 1512775.3951951857, kStep = -6.6103666358942538e-07;   // 2^20 / ln2, -ln2 / 2^20
-  const double kMagic = 6755399441055744.0;
-  if (CLAMP) x = clamp_hi_word_680(x);
-  double t = fma(x, kInv, kMagic);
-  const int k = (int)as_int64(t);
-  t -= kMagic;
-  const double r = fma(t, kStep, x);
-#if defined(__CUDA_ARCH__)
-  const unsigned base = (unsigned)__cvta_generic_to_shared(tab);
-  unsigned a1, a2;
-  asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a2) : "r"((unsigned)k & 1023u), "r"(base + 8u * kExpTableSize));
-  a1 = base + (((unsigned)k >> 7) & 0x1ff8u);
-  double T, U;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(a1));
-  asm("ld.shared.f64 %0, [%1];" : "=d"(U) : "r"(a2));
-  const double v0 = T * U;
-  const double v = fma(v0, r, v0);
-  int e;
-  asm("shr.s32 %0, %1, 20;" : "=r"(e) : "r"(k));
-  return scale_by_pow2(v, e);
-#else
-  const double v0 = tab[(k >> 10) & 1023] * tab[kExpTableSize + (k & 1023)];
-  return scale_by_pow2(fma(v0, r, v0), k >> 20);
-#endif
-}
-
-inline void fill_exp_table2(double *tab2)
-{
-  for (int i = 0; i < kExpTableSize; i++) tab2[i] = (double)exp2l((long double)i / (long double)(1 << 20));
-}
-
 // host-side construction of the table (uploaded once per context)
 inline void fill_exp_table(double *tab)
 {
@@ -178,9 +140,9 @@ inline void fill_exp_table(double *tab)
 
 #if defined(__CUDACC__)
 // copies the table from global memory into the block's shared-memory copy; the caller synchronises
-__device__ __forceinline__ void load_exp_table(double *smem_tab, const double *__restrict__ gmem_tab, int entries = kExpTableSize)
+__device__ __forceinline__ void load_exp_table(double *smem_tab, const double *__restrict__ gmem_tab)
 {
-  for (int m = threadIdx.x; m < entries; m += blockDim.x) smem_tab[m] = gmem_tab[m];
+  for (int m = threadIdx.x; m < kExpTableSize; m += blockDim.x) smem_tab[m] = gmem_tab[m];
 }
 #endif
 

@@ -35,12 +35,6 @@ namespace {
 #ifndef IS3D_K1_ITEM_UNROLL
 #define IS3D_K1_ITEM_UNROLL 1
 #endif
-#ifndef IS3D_K1_EXP2
-#define IS3D_K1_EXP2 0          // 1: two-level exp table (common.cuh fast_exp2level) in the momentum loop
-#endif
-#ifndef IS3D_K1_PREFETCH
-#define IS3D_K1_PREFETCH 0      // 1: the head of item k + 1 (aT bT c1 d1) is loaded while item k is evaluated
-#endif
 constexpr int kItemUnroll = IS3D_K1_ITEM_UNROLL;   // items per trip of the momentum loop
 constexpr int kThreads = IS3D_K1_THREADS;
 constexpr int kTile = kThreads;  // cells per shared-memory tile = threads per block
@@ -75,10 +69,10 @@ __global__ void __launch_bounds__(kThreads, IS3D_K1_MINBLOCKS)
 df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk, DfGrid g,
                   double *__restrict__ partial, int64_t total)
 {
-  __shared__ DfItemU items[kTile + IS3D_K1_PREFETCH];
-  __shared__ double exptab[kExpTableSize * (1 + IS3D_K1_EXP2)];
+  __shared__ DfItemU items[kTile];
+  __shared__ double exptab[kExpTableSize];
   __shared__ int warp_count[kThreads / 32];
-  load_exp_table(exptab, g.exptab, kExpTableSize * (1 + IS3D_K1_EXP2));   // visible after the first __syncthreads of the tile loop
+  load_exp_table(exptab, g.exptab);                 // visible after the first __syncthreads of the tile loop
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;
@@ -138,20 +132,6 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         items[base + __popc(ballot & ((1u << lane) - 1u))] = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sh, ch, cphi, sphi, w);
       }
       __syncthreads();
-#if IS3D_K1_PREFETCH
-      // the head of the dependency chain of item k + 1 (x_E = mT aT - pT bT) is in registers before item k is finished
-      double n_aT = items[0].aT, n_pb = th.pT * items[0].bT;
-#pragma unroll 1
-      for (int k = 0; k < n_items; k++) {
-        const DfItemU &it = items[k];
-        DfSharedU sh = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, th);
-        sh.pb = n_pb;
-        const double aT = n_aT;
-        n_aT = items[k + 1].aT; n_pb = th.pT * items[k + 1].bT;          // slot n_items exists (never evaluated)
-#pragma unroll
-        for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], exptab, aT);
-      }
-#else
 #pragma unroll kItemUnroll
       for (int k = 0; k < n_items; k++) {
         const DfItemU &it = items[k];          // shared memory: fields arrive as broadcast LDS.128, eb[eslot] as one LDS.64
@@ -159,7 +139,6 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], exptab);
       }
-#endif
     }
   }
 

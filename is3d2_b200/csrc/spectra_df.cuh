@@ -326,22 +326,14 @@ IS3D_HD DfSharedU df_share_u(const DfItemU &it, const DfThreadU &th)
   return s;
 }
 
-template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
-IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, const double *__restrict__ exptab);
-
-// One integrand evaluation w p.dsigma feq (1 + df) on the uniform-baryon path (MomentumSpectra.cpp:304-361); aT = the item's
-// aT, passed separately so that a caller can hold it in a register ahead of the rest of the item
+// One integrand evaluation w p.dsigma feq (1 + df) on the uniform-baryon path (MomentumSpectra.cpp:304-361)
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
 IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign,
-                         const double *__restrict__ exptab, double aT)
+                         const double *__restrict__ exptab)
 {
   // clamped in place (x <= 680, common.cuh): beyond that feq < 1e-295 and every later use of xE multiplies feq
-  const double xE = clamp_hi_word_680(fma(mT, aT, -s.pb));
-#if defined(IS3D_K1_EXP2) && IS3D_K1_EXP2
-  const double e = fast_exp2level<false>(xE, exptab);
-#else
+  const double xE = clamp_hi_word_680(fma(mT, it.aT, -s.pb));
   const double e = fast_exp<false>(xE, exptab);
-#endif
   const double q = BARYON ? fma(e, s.eb, sign) : e + sign;         // e^x + sign, x = xE - b alpha_B
   const double quad = fma(mT2, it.q1, fma(mT, s.A, s.B));
   if (MODE == 2 && !REGULATE) {
@@ -373,12 +365,6 @@ IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, doubl
   double contrib = pds * fma(feq, df, feq);
   if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
   return contrib;
-}
-
-template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
-IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, const double *__restrict__ exptab)
-{
-  return df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, s, mT, mT2, sign, exptab, it.aT);
 }
 
 }  // namespace is3d
