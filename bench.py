@@ -252,9 +252,13 @@ def sampler_bench(args, rank: int, world: int, local: int) -> dict:
             h.prepare()
             h.abi_set_surface(surf, global_offset=rank * cells)
             ntot, _ = h.abi_total_yield()
-            for mode in ("full", "compact") if hasattr(h, "abi_sample_compact") else ("full",):
-                sample = h.abi_sample if mode == "full" else h.abi_sample_compact
-                rec_bytes = 104 if mode == "full" else 64
+            def device_sample(nev_, copy=False):
+                ptr, total, counts, st = h.abi_sample_device(nev_)          # list stays in HBM (device-resident consumer)
+                return np.empty(int(total), dtype=np.uint8), counts, st, (lambda: None)
+
+            for mode in ("full", "compact", "device"):
+                sample = {"full": h.abi_sample, "compact": h.abi_sample_compact, "device": device_sample}[mode]
+                rec_bytes = {"full": 104, "compact": 64, "device": 0}[mode]
                 out = sample(nev, copy=False)                          # warm-up: same size, so the pinned list buffer is reused
                 out[3]()
                 secs, kms = [], []
@@ -288,10 +292,33 @@ def sampler_bench(args, rank: int, world: int, local: int) -> dict:
                              "proposals_per_s": props / sec, "acceptance": hadrons / max(props, 1.0)}
     finally:
         shutil.rmtree(root, ignore_errors=True)
-    best = res.get("compact", res["full"])
+    best = res["compact"]
+    # what this box can move device -> pinned host memory when all ranks copy at once: the ceiling of any list delivery
+    nbytes = max(int(best["d2h_bytes"] // world), 1 << 20)
+    dev_buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    host_buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    host_buf.copy_(dev_buf)
+    secs = []
+    for _ in range(calls):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        host_buf.copy_(dev_buf, non_blocking=True)
+        torch.cuda.synchronize()
+        secs.append(time.perf_counter() - t0)
+    tc = torch.tensor([float(np.median(secs))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    ceiling = nbytes * world / float(tc.item()) / 1e9
+    del dev_buf, host_buf
     return {"metric": "sampled hadrons/s", "value": best["hadrons_per_s"], "unit": "hadrons/s", "calls": calls,
-            "records": "64-byte wire records through is3d_sample_compact (value); 104-byte Sampled_Particle records through is3d_sample beside it",
-            "compact": res.get("compact"), "full": res["full"], "mean_yield_per_event_rank0": ntot,
+            "records": "value = 64-byte wire records delivered to host memory (is3d_sample_compact); beside it the 104-byte Sampled_Particle "
+                       "records (is3d_sample) and the list left in HBM (is3d_sample_device: no PCIe transfer)",
+            "compact": res["compact"], "full": res["full"], "device": res["device"],
+            "d2h_ceiling_gbs": ceiling,
+            "d2h_ceiling_note": f"plain cudaMemcpy of {nbytes} bytes per rank, HBM -> pinned host, all {world} ranks at once (aggregate GB/s)",
+            "mean_yield_per_event_rank0": ntot,
             "workload": f"sampler, df_mode=3 PTM, fast=1, all SMASH species, {nev} events, S-3D(stress 0.3) {cells} cells per GPU x {world} GPU, "
                         "particle lists returned to host memory"}
 
@@ -457,13 +484,13 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
         if rank == 0:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kernel_ms, launches, skipped, executed = 0.0, 0, 0, 0
+        kernel_ms, launches, skipped, executed, executed_pair = 0.0, 0, 0, 0, 0
         ev0.record(ext)
         for _ in range(args.steps):
             st = step()
             kernel_ms += st.kernel_ms
             launches += st.kernel_launches
-            skipped, executed = st.cells_skipped, st.evals_executed
+            skipped, executed, executed_pair = st.cells_skipped, st.evals_executed, st.pair_evals_executed
         ev1.record(ext)
         barrier()
         clocks = sampler.stop() if rank == 0 else None
@@ -489,12 +516,12 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
 
     # max over ranks of the two times, sums of the per-rank counters
     t = torch.tensor([ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
-    c = torch.tensor([float(skipped), float(executed), float(cells)], dtype=torch.float64, device="cuda")
+    c = torch.tensor([float(skipped), float(executed), float(cells), float(executed_pair)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c)
     ms_total, e2e_s, kernel_ms = (float(v) for v in t.tolist())
-    skipped_all, executed_all, cells_all = (float(v) for v in c.tolist())
+    skipped_all, executed_all, cells_all, pair_all = (float(v) for v in c.tolist())
     assert int(cells_all) == G
 
     fp64_peak = h.abi_fp64_peak()
@@ -513,17 +540,22 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
     # ---- roofline of the dominant kernel, from what THIS run executed ----
     # executed FP64-pipe work = class-evaluations the kernel ran (is3d_stats.evals_executed: padding slots and idle thread
     # columns included) x FP64-pipe instructions per class-evaluation read from the SASS of the loaded library x 2 flops
-    label = {1: "df_spectra_kernel<1,1,0,0,4>", 2: "df_spectra_kernel<2,1,0,0,4>"}.get(args.df_mode)
-    mix = None
+    # two launches per pass: single classes, and charge-conjugate pairs (two class-evaluations from one exponential)
+    label = {1: "df_spectra_kernel<1,1,0,0,4,0>", 2: "df_spectra_kernel<2,1,0,0,4,0>"}.get(args.df_mode)
+    label_pair = {1: "df_spectra_kernel<1,1,0,0,4,1>", 2: "df_spectra_kernel<2,1,0,0,4,1>"}.get(args.df_mode)
+    mix = mix_pair = None
     try:
-        mix = sassinfo.library_info()["kernels"].get(label) if label else None
+        kern = sassinfo.library_info()["kernels"]
+        mix, mix_pair = (kern.get(label), kern.get(label_pair)) if label else (None, None)
     except Exception as ex:  # noqa: BLE001
         print(f"bench.py: SASS scan failed: {ex!r}", file=sys.stderr)
-    achieved = frac = per_eval = None
-    if mix and executed_all > 0:
+    achieved = frac = per_eval = per_eval_pair = None
+    if mix and executed_all > 0 and (mix_pair or pair_all == 0):
         per_eval = mix["fp64"] / mix["evals_per_trip"]
-        # all ranks run side by side: per-GPU rate = (executed on the slowest rank ~ executed_all / world) / its kernel time
-        achieved = executed_all / world * per_eval * 2.0 / kern_s / 1e12
+        per_eval_pair = mix_pair["fp64"] / mix_pair["evals_per_trip"] if mix_pair else 0.0
+        fp64_instr = (executed_all - pair_all) * per_eval + pair_all * per_eval_pair
+        # all ranks run side by side: per-GPU rate = (executed on the slowest rank ~ total / world) / its kernel time
+        achieved = fp64_instr / world * 2.0 / kern_s / 1e12
         frac = achieved / fp64_peak
     # DRAM bytes of one launch: only from an `ncu --set full` capture of the SAME inner loop (listing hash) and the same launch
     traffic = traffic_src = None
@@ -554,11 +586,14 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
         "cells_skipped_frac": skipped_all / G,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac,
                      "traffic": traffic, "traffic_source": traffic_src,
-                     "kernel": label or "feqmod_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
+                     "kernel": (label + " + " + label_pair) if label else "feqmod_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
                      "what": "executed FP64-pipe instructions x 2 flops / kernel time / live DFMA peak, per GPU",
-                     "fp64_instr_per_class_eval": per_eval, "inner_loop_instructions": mix["instructions"] if mix else None,
+                     "fp64_instr_per_class_eval": per_eval, "fp64_instr_per_class_eval_in_pair_slots": per_eval_pair,
+                     "inner_loop_instructions": mix["instructions"] if mix else None,
+                     "inner_loop_instructions_pair_kernel": mix_pair["instructions"] if mix_pair else None,
                      "inner_loop_sass_sha256": mix["listing_sha256"] if mix else None,
-                     "class_evals_executed_per_step": executed_all, "species_evals_delivered_per_step": evals_global * (1.0 - skipped_all / G),
+                     "class_evals_executed_per_step": executed_all, "class_evals_in_pair_slots_per_step": pair_all,
+                     "species_evals_delivered_per_step": evals_global * (1.0 - skipped_all / G),
                      "peak_source": "DFMA micro-benchmark run live by is3d_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)",
                      "reference_operation_count": {"flops_per_eval": F_ALG[args.df_mode], "tflops_equivalent": evals_global / world * F_ALG[args.df_mode] / kern_s / 1e12,
                                                    "note": "SURVEY.md 8d's provisional count of the REFERENCE's loop per species-evaluation; not a roofline fraction "

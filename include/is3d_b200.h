@@ -108,6 +108,8 @@ typedef struct {
   int64_t evals_executed;        /* class-evaluations the dominant spectra kernel executed in the last call, padding slots and
                                     idle thread columns included (df_mode 1, 2; 0 = not reported): x FP64 instructions per
                                     evaluation (SASS) = the executed FP64-pipe work behind kernel_ms */
+  int64_t pair_evals_executed;   /* the part of evals_executed done in charge-conjugate pair slots (a baryon class and its
+                                    antibaryon class share x_E and its exponential) */
 } is3d_stats;
 
 /* One sampled hadron: the reference's Sampled_Particle (SampledParticle.h:32-54), same fields. */

@@ -140,6 +140,7 @@ void add_stats(is3d_stats *total, const is3d_stats &s)
   if (s.kernel_ms > total->kernel_ms) total->kernel_ms = s.kernel_ms;          // devices run side by side: the slowest one
   total->kernel_launches += s.kernel_launches;
   total->evals_executed += s.evals_executed;
+  total->pair_evals_executed += s.pair_evals_executed;
 }
 
 }  // namespace
@@ -202,13 +203,26 @@ is3d_status is3d_group_create(const is3d_params *p, int ndev, const int *devices
     for (int j = 0; j < i; j++)
       if (dev[i] == dev[j]) { g_comm_error = "group_create: device listed twice"; return IS3D_ERR_INVALID; }
   is3d_group *g = new is3d_group;
-  for (int i = 0; i < ndev; i++) {
-    is3d_params q = *p;
-    q.device = dev[i];
-    is3d_ctx *c = nullptr;
-    is3d_status st = is3d_create(&q, &c);
-    if (st != IS3D_OK) { g_comm_error = is3d_last_error(nullptr); is3d_group_destroy(g); return st; }
-    g->ctx.push_back(c);
+  {
+    // one host thread per device: creating a CUDA primary context costs a few hundred ms, eight in a row several seconds
+    std::vector<is3d_ctx *> made(ndev, nullptr);
+    std::vector<is3d_status> st(ndev, IS3D_OK);
+    std::vector<std::string> msg(ndev);
+    auto make = [&](int i) {
+      is3d_params q = *p;
+      q.device = dev[i];
+      st[i] = is3d_create(&q, &made[i]);
+      if (st[i] != IS3D_OK) msg[i] = is3d_last_error(nullptr);          // thread-local message of the failed create
+    };
+    if (ndev == 1) make(0);
+    else {
+      std::vector<std::thread> th;
+      for (int i = 0; i < ndev; i++) th.emplace_back(make, i);
+      for (auto &t : th) t.join();
+    }
+    for (int i = 0; i < ndev; i++) if (made[i]) g->ctx.push_back(made[i]);
+    for (int i = 0; i < ndev; i++)
+      if (st[i] != IS3D_OK) { g_comm_error = "device " + std::to_string(dev[i]) + ": " + msg[i]; is3d_group_destroy(g); return st[i]; }
   }
   g->begin.assign(ndev, 0); g->count.assign(ndev, 0);
   if (ndev > 1) {

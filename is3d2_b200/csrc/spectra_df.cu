@@ -64,11 +64,15 @@ struct DfGrid {
   const double *exptab;                               // 2^(m/1024), global memory (ctx->d_exptab)
 };
 
-template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, int R>
+// PAIR = true: a slot is a charge-conjugate PAIR of classes (baryon class, its antibaryon class: same mass, same statistics,
+// b and -b).  x_E = u.p/T and exp(x_E) do not depend on b, so one exponential (7 of the ~21 FP64 instructions and 6 of the 8
+// integer / shared-memory instructions of an evaluation) serves both; g.slot_class then holds two class ids per slot.
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, int R, bool PAIR>
 __global__ void __launch_bounds__(kThreads, IS3D_K1_MINBLOCKS)
 df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk, DfGrid g,
                   double *__restrict__ partial, int64_t total)
 {
+  static_assert(!PAIR || BARYON, "pairs exist only with baryon terms");
   __shared__ DfItemU items[kTile];
   __shared__ double exptab[kExpTableSize];
   __shared__ int warp_count[kThreads / 32];
@@ -82,19 +86,25 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   const int col = blockIdx.x * kThreads + t;
   const int colc = col < g.ncols ? col : g.ncols - 1;
   const int grp = colc / g.NpT, ip = colc - grp * g.NpT;
+  constexpr int S = PAIR ? 2 : 1;                       // class ids per slot
   double mT[R], mT2[R], sgn[R];
-  double acc[R];
-  int jbin[R];                                          // (class, pT) bin index, -1 = padding
-  const int cls0 = g.slot_class[grp * R];               // slot 0 of a group is never padding
+  double acc[R], accm[PAIR ? R : 1];                    // accm: the antibaryon partners of a pair slot
+  int jbin[R], jbinm[PAIR ? R : 1];                     // (class, pT) bin index, -1 = padding
+  const int cls0 = g.slot_class[S * grp * R];           // slot 0 of a group is never padding
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    const int cls = g.slot_class[grp * R + r];
+    const int cls = g.slot_class[S * (grp * R + r)];
     const int jj = (cls >= 0 ? cls : cls0) * g.NpT + ip;
     jbin[r] = (col < g.ncols && cls >= 0) ? jj : -1;
     const double m = g.mT[jj];
     mT[r] = m; mT2[r] = m * m; sgn[r] = g.sign[jj];
     if (MODE == 2) asm volatile("" : "+d"(mT2[r]));   // opaque: ptxas otherwise re-multiplies mT^2 per item when registers are tight
     acc[r] = 0.0;
+    if (PAIR) {
+      const int clsm = g.slot_class[S * (grp * R + r) + 1];
+      jbinm[r] = (col < g.ncols && clsm >= 0) ? clsm * g.NpT + ip : -1;
+      accm[r] = 0.0;
+    }
   }
   DfThreadU th;
   th.pT = g.pT[ip]; th.pT2 = th.pT * th.pT;            // bin arrays are [class][pT]: entry ip = class 0
@@ -102,6 +112,8 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   th.bpT = th.b * th.pT;
   if (MODE == 2) asm volatile("" : "+d"(th.pT2), "+d"(th.bpT));
   th.eslot = kMaxBaryon + (int)th.b;
+  DfThreadU thm = th;                                   // the antibaryon partners: b -> -b
+  if (PAIR) { thm.b = -th.b; thm.bpT = -th.bpT; thm.eslot = kMaxBaryon - (int)th.b; }
 
   const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
   int64_t chunk_end = chunk_begin + cells_per_chunk;
@@ -136,8 +148,19 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
       for (int k = 0; k < n_items; k++) {
         const DfItemU &it = items[k];          // shared memory: fields arrive as broadcast LDS.128, eb[eslot] as one LDS.64
         const DfSharedU sh = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, th);
+        if (!PAIR) {
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], exptab);
+          for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], exptab);
+        } else {
+          const DfSharedU shm = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, thm);   // common sub-expressions are shared by the compiler
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const double xE = df_eval_u_x(it, sh, mT[r]);
+            const double e = fast_exp<false>(xE, exptab);
+            acc[r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], xE, e);
+            accm[r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, shm, mT[r], mT2[r], sgn[r], xE, e);
+          }
+        }
       }
     }
   }
@@ -148,6 +171,10 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
     if (jbin[r] >= 0) {
       int64_t idx = iy + (int64_t)g.Ny * (iphi + (int64_t)g.Nphi * jbin[r]);
       partial[pbase + idx] += acc[r];
+    }
+    if (PAIR && jbinm[r] >= 0) {
+      int64_t idx = iy + (int64_t)g.Ny * (iphi + (int64_t)g.Nphi * jbinm[r]);
+      partial[pbase + idx] += accm[r];
     }
   }
 }
@@ -170,21 +197,21 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, int n
 
 namespace {
 
-template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, bool PAIR>
 void launch_df(dim3 grid, cudaStream_t st, const double *pack, int64_t stride, int64_t n, int64_t cpc, const DfGrid &g,
                double *partial, int64_t total)
 {
-  df_spectra_kernel<MODE, BARYON, REGULATE, OUTFLOW, kDfBinsPerThread><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, g, partial, total);
+  df_spectra_kernel<MODE, BARYON, REGULATE, OUTFLOW, kDfBinsPerThread, PAIR><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, g, partial, total);
 }
 
-template <int MODE, bool BARYON>
+template <int MODE, bool BARYON, bool PAIR>
 void dispatch_df2(bool reg, bool outflow, dim3 grid, cudaStream_t st, const double *pack, int64_t stride, int64_t n,
                   int64_t cpc, const DfGrid &g, double *partial, int64_t total)
 {
-  if (reg && outflow) launch_df<MODE, BARYON, true, true>(grid, st, pack, stride, n, cpc, g, partial, total);
-  else if (reg) launch_df<MODE, BARYON, true, false>(grid, st, pack, stride, n, cpc, g, partial, total);
-  else if (outflow) launch_df<MODE, BARYON, false, true>(grid, st, pack, stride, n, cpc, g, partial, total);
-  else launch_df<MODE, BARYON, false, false>(grid, st, pack, stride, n, cpc, g, partial, total);
+  if (reg && outflow) launch_df<MODE, BARYON, true, true, PAIR>(grid, st, pack, stride, n, cpc, g, partial, total);
+  else if (reg) launch_df<MODE, BARYON, true, false, PAIR>(grid, st, pack, stride, n, cpc, g, partial, total);
+  else if (outflow) launch_df<MODE, BARYON, false, true, PAIR>(grid, st, pack, stride, n, cpc, g, partial, total);
+  else launch_df<MODE, BARYON, false, false, PAIR>(grid, st, pack, stride, n, cpc, g, partial, total);
 }
 
 }  // namespace
@@ -234,6 +261,58 @@ bool slot_table_core(const std::vector<int> &rep, const double *baryon, bool bar
     for (size_t c = 0; c < rep.size(); c++)
       if ((baryon_on ? baryon[rep[c]] : 0.0) == b) slots->push_back((int)c);
     while (slots->size() % (size_t)R) slots->push_back(-1);
+  }
+  return true;
+}
+
+// Charge-conjugate pairs (df_spectra_kernel<..., PAIR = true>): with baryon terms a baryon class and its antibaryon class
+// -- same mass, same statistics, opposite baryon number -- differ only in the b-dependent pieces of df and in exp(-b alpha_B),
+// so they are evaluated together.  pairs = 2 class ids per slot (b > 0 first), groups of R slots with ONE |b|, padded with
+// (-1, -1); singles = the slot table of every class without a partner (mesons, the deuteron, unmatched baryons).
+bool pair_tables_core(const std::vector<int> &rep, const double *mass, const double *sign, const double *baryon, int R,
+                      std::vector<int> *singles, std::vector<int> *pairs)
+{
+  const size_t nc = rep.size();
+  std::vector<int> partner(nc, -1);
+  for (size_t c = 0; c < nc; c++) {
+    const int s = rep[c];
+    if (!(baryon[s] > 0.0) || partner[c] >= 0) continue;
+    for (size_t d = 0; d < nc; d++) {
+      const int t = rep[d];
+      if (partner[d] < 0 && d != c && baryon[t] == -baryon[s] && mass[t] == mass[s] && sign[t] == sign[s]) { partner[c] = (int)d; partner[d] = (int)c; break; }
+    }
+  }
+  // pairs, one run per |b|
+  pairs->clear();
+  std::vector<double> bvals;
+  for (size_t c = 0; c < nc; c++)
+    if (partner[c] >= 0 && baryon[rep[c]] > 0.0) {
+      const double b = baryon[rep[c]];
+      bool seen = false;
+      for (double v : bvals) seen = seen || (v == b);
+      if (!seen) bvals.push_back(b);
+    }
+  for (double b : bvals) {
+    if (b > (double)kMaxBaryon || b != (double)(int)b) return false;
+    for (size_t c = 0; c < nc; c++)
+      if (partner[c] >= 0 && baryon[rep[c]] == b) { pairs->push_back((int)c); pairs->push_back(partner[c]); }
+    while ((pairs->size() / 2) % (size_t)R) { pairs->push_back(-1); pairs->push_back(-1); }
+  }
+  // singles: the ordinary slot table over the classes without a partner
+  std::vector<double> sb;
+  for (size_t c = 0; c < nc; c++)
+    if (partner[c] < 0) {
+      const double b = baryon[rep[c]];
+      bool seen = false;
+      for (double v : sb) seen = seen || (v == b);
+      if (!seen) sb.push_back(b);
+    }
+  singles->clear();
+  for (double b : sb) {
+    if (fabs(b) > (double)kMaxBaryon || b != (double)(int)b) return false;
+    for (size_t c = 0; c < nc; c++)
+      if (partner[c] < 0 && baryon[rep[c]] == b) singles->push_back((int)c);
+    while (singles->size() % (size_t)R) singles->push_back(-1);
   }
   return true;
 }
@@ -336,24 +415,38 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   SpeciesBins sb;
   IS3D_TRY(build_bin_arrays(ctx, &sb));
   g.mT = sb.mT; g.pT = sb.pT; g.baryon = sb.baryon; g.sign = sb.sign;
-  std::vector<int> slots;
-  if (!build_slot_table(ctx, kDfBinsPerThread, &slots)) {
+  // thread groups: single classes (one baryon number per group) and, with baryon terms, charge-conjugate pairs
+  std::vector<int> slots, pair_slots;
+  bool ok;
+  if (p.include_baryon) {
+    std::vector<int> class_of, rep;
+    species_classes(ctx, &class_of, &rep);
+    ok = pair_tables_core(rep, ctx->h_mass.data(), ctx->h_sign.data(), ctx->h_baryon.data(), kDfBinsPerThread, &slots, &pair_slots);
+  } else {
+    ok = build_slot_table(ctx, kDfBinsPerThread, &slots);
+  }
+  if (!ok) {
     ctx->set_error("species list holds a baryon number outside -2..2 (the reference's PDG readers produce hadrons and the deuteron only)");
     return IS3D_ERR_INVALID;
   }
   void *d_slots = nullptr;
-  IS3D_TRY(ctx->get_scratch("k1_slots", slots.size() * sizeof(int), &d_slots));
-  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `slots` is pageable host memory
+  std::vector<int> both(slots);
+  both.insert(both.end(), pair_slots.begin(), pair_slots.end());
+  IS3D_TRY(ctx->get_scratch("k1_slots", (both.size() + 1) * sizeof(int), &d_slots));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `both` is pageable host memory
   g.slot_class = (const int *)d_slots;
   g.ns = sb.nclass; g.NpT = ctx->NpT; g.ncols = ctx->NpT * (int)(slots.size() / kDfBinsPerThread);
   const int64_t per_species = (int64_t)ctx->NpT * ctx->Nphi * ctx->Ny;
   const int64_t total_class = (int64_t)sb.nclass * per_species;
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
   g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw; g.exptab = ctx->d_exptab;
-
-  const int nslices = (g.ncols + kThreads - 1) / kThreads;
-  const int64_t blocks_per_chunk = (int64_t)nslices * ctx->Ny * ctx->Nphi;
+  DfGrid gp = g;                                                 // the pair launch: two class ids per slot
+  gp.slot_class = (const int *)d_slots + slots.size();
+  gp.ncols = ctx->NpT * (int)(pair_slots.size() / (2 * kDfBinsPerThread));
+  const int nslices = (g.ncols + kThreads - 1) / kThreads, nslices_pair = (gp.ncols + kThreads - 1) / kThreads;
+  // a pair block does about 1.6x the work of a single block; the wave policy counts blocks
+  const int64_t blocks_per_chunk = (int64_t)(nslices + nslices_pair) * ctx->Ny * ctx->Nphi;
   if ((int64_t)ctx->Ny * ctx->Nphi > 65535) { ctx->set_error("Ny*Nphi exceeds 65535"); return IS3D_ERR_INVALID; }
 
   const int64_t macro = pass_cells(4 << 20);          // cells per pass: bounds the pack scratch to ~1 GB
@@ -378,15 +471,18 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
         ctx->surf, begin, count, ctx->tb, fl, (double *)pack, stride, (unsigned long long *)counters);
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
     int nch = (int)((count + cpc - 1) / cpc);
-    dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch);
+    dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch), grid_pair(nslices_pair, ctx->Ny * ctx->Nphi, nch);
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0;
+    // the pair launch first: its blocks are the longer ones, the single blocks fill the tail of its last wave
     if (p.df_mode == 1) {
-      if (p.include_baryon) dispatch_df2<1, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
-      else dispatch_df2<1, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
+      if (p.include_baryon && nslices_pair) dispatch_df2<1, true, true>(reg, outflow, grid_pair, ctx->stream, (double *)pack, stride, count, cpc, gp, (double *)partial, total_class);
+      if (p.include_baryon && nslices) dispatch_df2<1, true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
+      if (!p.include_baryon) dispatch_df2<1, false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
     } else {
-      if (p.include_baryon) dispatch_df2<2, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
-      else dispatch_df2<2, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
+      if (p.include_baryon && nslices_pair) dispatch_df2<2, true, true>(reg, outflow, grid_pair, ctx->stream, (double *)pack, stride, count, cpc, gp, (double *)partial, total_class);
+      if (p.include_baryon && nslices) dispatch_df2<2, true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
+      if (!p.include_baryon) dispatch_df2<2, false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
     }
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
@@ -394,7 +490,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     float ms = 0.f;
     IS3D_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
     ms_total += ms;
-    launches += 2;
+    launches += 2 + (nslices_pair && nslices ? 1 : 0);
   }
   reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total_class, per_species,
                                                                                 sb.class_of, ctx->d_deg, total, out_dev);
@@ -410,8 +506,9 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     stats->kernel_ms = ms_total;
     stats->kernel_launches = launches;
     // every valid cell is one item per (y, phi, eta) block row, evaluated by all nslices x kThreads thread columns x R slots
-    stats->evals_executed = (n - (int64_t)h_counters[0] - (int64_t)h_counters[1]) * (int64_t)nslices * kThreads * kDfBinsPerThread *
-                            ctx->Ny * ctx->Nphi * ctx->Neta;
+    const int64_t per_slice = (n - (int64_t)h_counters[0] - (int64_t)h_counters[1]) * (int64_t)kThreads * kDfBinsPerThread * ctx->Ny * ctx->Nphi * ctx->Neta;
+    stats->pair_evals_executed = 2 * per_slice * nslices_pair;
+    stats->evals_executed = per_slice * nslices + stats->pair_evals_executed;
   }
   if (h_counters[1] != 0) {
     ctx->set_error(std::to_string(h_counters[1]) + " cell(s) outside the df coefficient tables (the reference aborts here)");

@@ -326,14 +326,30 @@ IS3D_HD DfSharedU df_share_u(const DfItemU &it, const DfThreadU &th)
   return s;
 }
 
-// One integrand evaluation w p.dsigma feq (1 + df) on the uniform-baryon path (MomentumSpectra.cpp:304-361)
+// One integrand evaluation w p.dsigma feq (1 + df) on the uniform-baryon path (MomentumSpectra.cpp:304-361), in two steps:
+// df_eval_u_x / fast_exp give xE = u.p/T and e^xE, which do NOT depend on the baryon number; df_eval_u_tail does the rest.
+// A baryon class and its antibaryon class (same mass, same statistics, b -> -b) therefore share xE and the exponential:
+// the pair path of df_spectra_kernel evaluates both tails from one exp (charge-conjugate pairs, spectra_df.cu).
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, double xE, double e);
+
+IS3D_HD double df_eval_u_x(const DfItemU &it, const DfSharedU &s, double mT)
+{
+  // clamped in place (x <= 680, common.cuh): beyond that feq < 1e-295 and every later use of xE multiplies feq
+  return clamp_hi_word_680(fma(mT, it.aT, -s.pb));
+}
+
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
 IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign,
                          const double *__restrict__ exptab)
 {
-  // clamped in place (x <= 680, common.cuh): beyond that feq < 1e-295 and every later use of xE multiplies feq
-  const double xE = clamp_hi_word_680(fma(mT, it.aT, -s.pb));
-  const double e = fast_exp<false>(xE, exptab);
+  const double xE = df_eval_u_x(it, s, mT);
+  return df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, s, mT, mT2, sign, xE, fast_exp<false>(xE, exptab));
+}
+
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, double xE, double e)
+{
   const double q = BARYON ? fma(e, s.eb, sign) : e + sign;         // e^x + sign, x = xE - b alpha_B
   const double quad = fma(mT2, it.q1, fma(mT, s.A, s.B));
   if (MODE == 2 && !REGULATE) {

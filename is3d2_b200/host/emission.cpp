@@ -27,28 +27,15 @@ void EmissionFunctionArray::check(is3d_status st, const char *what)
   exit(-1);
 }
 
-EmissionFunctionArray::EmissionFunctionArray(ParameterReader *paraRdr_in, Table *chosen_particles_in, Table *pT_tab_in,
-                                             Table *phi_tab_in, Table *y_tab_in, Table *eta_tab_in,
-                                             std::vector<particle_info> *particles_in, FO_surface *surf_in,
-                                             Deltaf_Data *df_data_in)
+is3d_params EmissionFunctionArray::params_from(ParameterReader *paraRdr, int *polzn_file_compat_out)
 {
-  paraRdr = paraRdr_in;
-  pT_tab = pT_tab_in; phi_tab = phi_tab_in; y_tab = y_tab_in; eta_tab = eta_tab_in;
-  particles = particles_in; surf = surf_in; df_data = df_data_in;
-  pT_tab_length = pT_tab->getNumberOfRows();
-  phi_tab_length = phi_tab->getNumberOfRows();
-  y_tab_length = y_tab->getNumberOfRows();
-  eta_tab_length = eta_tab->getNumberOfRows();
-
+  is3d_params prm;
   is3d_default_params(&prm);
-  OPERATION = prm.operation = paraRdr->getVal("operation");
-  MODE = paraRdr->getVal("mode");
-  DIMENSION = prm.dimension = paraRdr->getVal("dimension");
-  if (DIMENSION == 2) y_tab_length = 1;
-  else if (DIMENSION == 3) eta_tab_length = 1;
-  else fatal("EmissionFunctionArray error: need to set dimension = (2,3)");
-  DF_MODE = prm.df_mode = paraRdr->getVal("df_mode");
-  if (DF_MODE < 1 || DF_MODE > 5) fatal("EmissionFunctionArray error: need to set df_mode = (1,2,3,4,5)");
+  prm.operation = paraRdr->getVal("operation");
+  prm.dimension = paraRdr->getVal("dimension");
+  if (prm.dimension != 2 && prm.dimension != 3) fatal("EmissionFunctionArray error: need to set dimension = (2,3)");
+  prm.df_mode = paraRdr->getVal("df_mode");
+  if (prm.df_mode < 1 || prm.df_mode > 5) fatal("EmissionFunctionArray error: need to set df_mode = (1,2,3,4,5)");
   prm.include_baryon = paraRdr->getVal("include_baryon");
   prm.include_bulk_deltaf = paraRdr->getVal("include_bulk_deltaf");
   prm.include_shear_deltaf = paraRdr->getVal("include_shear_deltaf");
@@ -56,20 +43,12 @@ EmissionFunctionArray::EmissionFunctionArray(ParameterReader *paraRdr_in, Table 
   prm.regulate_deltaf = paraRdr->getVal("regulate_deltaf");
   prm.outflow = paraRdr->getVal("outflow");
   prm.deta_min = paraRdr->getVal("deta_min");
-  const int GROUP_PARTICLES = paraRdr->getVal("group_particles");
-  (void)paraRdr->getVal("particle_diff_tolerance");
   prm.mass_pion0 = paraRdr->getVal("mass_pion0");
-  (void)paraRdr->getVal("lightest_particle");
-  (void)paraRdr->getVal("do_resonance_decays");
-  OVERSAMPLE = paraRdr->getVal("oversample");
   prm.fast = paraRdr->getVal("fast");
-  MIN_NUM_HADRONS = paraRdr->getVal("min_num_hadrons");
-  MAX_NUM_SAMPLES = paraRdr->getVal("max_num_samples");
   long seed = (long)paraRdr->getVal("sampler_seed");
   if (seed < 0) seed = (long)std::chrono::system_clock::now().time_since_epoch().count();   // "< 0 => clock"
   prm.sampler_seed = seed;
-  if (OPERATION == 2) printf("Sampler seed set to %ld \n", seed);
-  TEST_SAMPLER = prm.test_sampler = paraRdr->getVal("test_sampler");
+  prm.test_sampler = paraRdr->getVal("test_sampler");
   prm.pT_min = paraRdr->getVal("pT_min"); prm.pT_max = paraRdr->getVal("pT_max"); prm.pT_bins = paraRdr->getVal("pT_bins");
   prm.y_cut = paraRdr->getVal("y_cut"); prm.y_bins = paraRdr->getVal("y_bins");
   prm.phip_bins = paraRdr->getVal("phip_bins");
@@ -80,7 +59,48 @@ EmissionFunctionArray::EmissionFunctionArray(ParameterReader *paraRdr_in, Table 
   if (const char *v = getenv("IS3D_FAMOD_CHAIN")) prm.famod_chain = atoi(v);
   if (const char *v = getenv("IS3D_DNDX_BUG_COMPAT")) prm.dndx_bug_compat = atoi(v);
   if (const char *v = getenv("IS3D_POLZN_CHUNK_COMPAT")) prm.polzn_chunk_compat = atoi(v);
-  if (const char *v = getenv("IS3D_POLZN_FILE_COMPAT")) polzn_file_compat = atoi(v);
+  if (polzn_file_compat_out)
+    if (const char *v = getenv("IS3D_POLZN_FILE_COMPAT")) *polzn_file_compat_out = atoi(v);
+  return prm;
+}
+
+// one CUDA context per GPU of the run: IS3D_DEVICES = "all" | "0-7" | "0,2,3" (default: the single device IS3D_DEVICE, else 0)
+is3d_group *EmissionFunctionArray::create_group(const is3d_params &prm)
+{
+  std::vector<int> devices = parse_device_list(getenv("IS3D_DEVICES"), prm.device);
+  is3d_group *g = nullptr;
+  is3d_status st = is3d_group_create(&prm, (int)devices.size(), devices.data(), &g);
+  if (st != IS3D_OK) fatal(std::string("is3d_create error: ") + is3d_group_last_error(nullptr));
+  return g;
+}
+
+EmissionFunctionArray::EmissionFunctionArray(ParameterReader *paraRdr_in, Table *chosen_particles_in, Table *pT_tab_in,
+                                             Table *phi_tab_in, Table *y_tab_in, Table *eta_tab_in,
+                                             std::vector<particle_info> *particles_in, FO_surface *surf_in,
+                                             Deltaf_Data *df_data_in, is3d_group *ready_group, const is3d_params *ready_params)
+{
+  paraRdr = paraRdr_in;
+  pT_tab = pT_tab_in; phi_tab = phi_tab_in; y_tab = y_tab_in; eta_tab = eta_tab_in;
+  particles = particles_in; surf = surf_in; df_data = df_data_in;
+  pT_tab_length = pT_tab->getNumberOfRows();
+  phi_tab_length = phi_tab->getNumberOfRows();
+  y_tab_length = y_tab->getNumberOfRows();
+  eta_tab_length = eta_tab->getNumberOfRows();
+
+  prm = params_from(paraRdr, &polzn_file_compat);
+  if (ready_group && ready_params) prm = *ready_params;       // the switches the ready contexts were created with (clock seeds!)
+  OPERATION = prm.operation; DIMENSION = prm.dimension; DF_MODE = prm.df_mode; TEST_SAMPLER = prm.test_sampler;
+  MODE = paraRdr->getVal("mode");
+  if (DIMENSION == 2) y_tab_length = 1;
+  else eta_tab_length = 1;
+  const int GROUP_PARTICLES = paraRdr->getVal("group_particles");
+  (void)paraRdr->getVal("particle_diff_tolerance");
+  (void)paraRdr->getVal("lightest_particle");
+  (void)paraRdr->getVal("do_resonance_decays");
+  OVERSAMPLE = paraRdr->getVal("oversample");
+  MIN_NUM_HADRONS = paraRdr->getVal("min_num_hadrons");
+  MAX_NUM_SAMPLES = paraRdr->getVal("max_num_samples");
+  if (OPERATION == 2) printf("Sampler seed set to %ld \n", (long)prm.sampler_seed);
 
   // chosen species in file order, matched by Monte-Carlo id (EmissionFunction.cpp:357-372); the optional mass sort
   // of group_particles only affected the (removed) resonance-decay code
@@ -102,11 +122,8 @@ EmissionFunctionArray::EmissionFunctionArray(ParameterReader *paraRdr_in, Table 
   dN_pTdpTdphidy.assign((size_t)number_of_chosen_particles * pT_tab_length * phi_tab_length * y_tab_length, 0.0);
 
   // ---- one CUDA context per GPU, each holding every static input; cells are sharded over them ----
-  // IS3D_DEVICES = "all" | "0-7" | "0,2,3" selects the GPUs of this run (default: the single device IS3D_DEVICE, else 0)
-  std::vector<int> devices = parse_device_list(getenv("IS3D_DEVICES"), prm.device);
-  is3d_status st = is3d_group_create(&prm, (int)devices.size(), devices.data(), &grp);
-  if (st != IS3D_OK) fatal(std::string("is3d_create error: ") + is3d_group_last_error(nullptr));
-  if (devices.size() > 1) printf("Sharding the freezeout surface over %d GPUs (one NCCL all-reduce per result)\n", (int)devices.size());
+  grp = ready_group ? ready_group : create_group(prm);
+  if (is3d_group_size(grp) > 1) printf("Sharding the freezeout surface over %d GPUs (one NCCL all-reduce per result)\n", is3d_group_size(grp));
   ctx = is3d_group_ctx(grp, 0);
 
   const int ns = number_of_chosen_particles;

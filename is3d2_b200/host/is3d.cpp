@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
 
 #include "../../include/is3d_host.h"
 #include "is3d_host.hpp"
@@ -21,6 +22,16 @@ struct Session {
   std::unique_ptr<EmissionFunctionArray> efa;
   std::vector<std::vector<Sampled_Particle>> events;
   bool have_surface = false, tables_ready = false;
+  // contexts created ahead of time (executable path: while surface.dat is parsed)
+  std::thread early;
+  is3d_group *early_group = nullptr;
+  is3d_params early_params{};
+  void start_contexts()
+  {
+    early_params = EmissionFunctionArray::params_from(&paraRdr);
+    early = std::thread([this] { early_group = EmissionFunctionArray::create_group(early_params); });
+  }
+  ~Session() { if (early.joinable()) early.join(); if (early_group && !efa) is3d_group_destroy(early_group); }
 
   void open(const char *const *overrides)
   {
@@ -75,8 +86,10 @@ struct Session {
   void create_context()
   {
     if (!tables_ready) prepare_tables();
+    if (early.joinable()) early.join();
     efa.reset(new EmissionFunctionArray(&paraRdr, chosen_particles.get(), pT_tab.get(), phi_tab.get(), y_tab.get(),
-                                        eta_tab.get(), &particle_data, have_surface ? &surf : nullptr, df_data.get()));
+                                        eta_tab.get(), &particle_data, have_surface ? &surf : nullptr, df_data.get(),
+                                        early_group, early_group ? &early_params : nullptr));
   }
   void run() { efa->calculate_spectra(events); }
 };
@@ -117,6 +130,7 @@ void IS3D::run_particlization(int fo_from_file)
   };
   Session s;
   s.open(nullptr);
+  s.start_contexts();          // CUDA contexts (+ the NCCL communicator of a multi-GPU run) come up while the surface is parsed
   if (fo_from_file == 1) { s.read_surface(); lap("surface.dat -> structure of arrays"); }
   else {
     printf("from memory (please check that you've already undone hbarc = 1 units, tau factors from hydro module)...\n\n");
@@ -130,7 +144,7 @@ void IS3D::run_particlization(int fo_from_file)
   s.prepare_tables();
   lap("PDG / df tables / densities");
   s.create_context();
-  lap("CUDA contexts + tables + surface H2D");
+  lap("wait for CUDA contexts + tables + surface H2D");
   s.run();
   lap("calculate_spectra (compute + result files)");
   int operation = s.paraRdr.getVal("operation");

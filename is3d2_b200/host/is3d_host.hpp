@@ -161,9 +161,15 @@ struct Sampled_Particle {
 
 class EmissionFunctionArray {
  public:
+  // `ready_group`: contexts created ahead of time with params_from(paraRdr) (the executable builds them while surface.dat is
+  // parsed); NULL = create them here
   EmissionFunctionArray(ParameterReader *paraRdr_in, Table *chosen_particles, Table *pT_tab_in, Table *phi_tab_in,
                         Table *y_tab_in, Table *eta_tab_in, std::vector<particle_info> *particles_in,
-                        FO_surface *surf_in, Deltaf_Data *df_data_in);
+                        FO_surface *surf_in, Deltaf_Data *df_data_in, is3d_group *ready_group = nullptr,
+                        const is3d_params *ready_params = nullptr);
+  // the run-time switches of iS3D_parameters.dat (+ the IS3D_* environment knobs) as the C ABI takes them
+  static is3d_params params_from(ParameterReader *paraRdr, int *polzn_file_compat = nullptr);
+  static is3d_group *create_group(const is3d_params &prm);      // IS3D_DEVICES / IS3D_DEVICE -> contexts (+ communicator)
   ~EmissionFunctionArray();
 
   void calculate_spectra(std::vector<std::vector<Sampled_Particle>> &particle_event_list_in);

@@ -19,11 +19,14 @@ CACHE = os.path.join(HERE, "libis3d_b200.sass.json")
 FP64_OPS = ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX")
 
 # kernels the benchmark can name: label -> (substring of the mangled name, class-evaluations per trip of the inner loop)
+# template arguments: <MODE, BARYON, REGULATE, OUTFLOW, R, PAIR>; a pair slot is two class-evaluations from one exponential
 KERNELS = {
-    "df_spectra_kernel<1,1,0,0,4>": ("df_spectra_kernelILi1ELb1ELb0ELb0ELi4EE", 4),
-    "df_spectra_kernel<2,1,0,0,4>": ("df_spectra_kernelILi2ELb1ELb0ELb0ELi4EE", 4),
-    "df_spectra_kernel<1,0,0,0,4>": ("df_spectra_kernelILi1ELb0ELb0ELb0ELi4EE", 4),
-    "df_spectra_kernel<2,0,0,0,4>": ("df_spectra_kernelILi2ELb0ELb0ELb0ELi4EE", 4),
+    "df_spectra_kernel<1,1,0,0,4,0>": ("df_spectra_kernelILi1ELb1ELb0ELb0ELi4ELb0EE", 4),
+    "df_spectra_kernel<2,1,0,0,4,0>": ("df_spectra_kernelILi2ELb1ELb0ELb0ELi4ELb0EE", 4),
+    "df_spectra_kernel<1,1,0,0,4,1>": ("df_spectra_kernelILi1ELb1ELb0ELb0ELi4ELb1EE", 8),
+    "df_spectra_kernel<2,1,0,0,4,1>": ("df_spectra_kernelILi2ELb1ELb0ELb0ELi4ELb1EE", 8),
+    "df_spectra_kernel<1,0,0,0,4,0>": ("df_spectra_kernelILi1ELb0ELb0ELb0ELi4ELb0EE", 4),
+    "df_spectra_kernel<2,0,0,0,4,0>": ("df_spectra_kernelILi2ELb0ELb0ELb0ELi4ELb0EE", 4),
 }
 
 

@@ -27,7 +27,7 @@ def num(name):
 
 
 kernel = vals[col["Kernel Name"]]
-label = "df_spectra_kernel<2,1,0,0,4>"
+label = "df_spectra_kernel<2,1,0,0,4,0>"
 mix = sassinfo.library_info()["kernels"][label]
 out = {"kernel": kernel, "label": label, "cells_per_launch": cells, "gpu_time_ms": num("gpu__time_duration.sum"),
        "dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
