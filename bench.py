@@ -347,7 +347,7 @@ def sampler_cpu_baseline(args) -> dict:
                       f"serial reference, {sec:.2f} s inside calculate_spectra (histogram mode, no particle files)"}
 
 
-def oracle_spot_check(args, h, surf: dict) -> dict:
+def oracle_spot_check(args, h, surf: dict, avg) -> dict:
     """Checker leg (rank 0, before any communicator is attached): the first `check_cells` cells of the benchmarked surface
     through the SAME context and kernels against the CPU oracle (oracle/cf_oracle.cpp, pinned to the unmodified reference)."""
     n = args.check_cells
@@ -362,7 +362,9 @@ def oracle_spot_check(args, h, surf: dict) -> dict:
         try:
             params = bench_params(args.df_mode)
             workdir.make_workdir(root, params, chosen="smash")
-            rc, want, _ = oracle_api.OracleProblem(root, params, sl, famod_chain=0).spectra()
+            # same surface-averaged thermodynamics as the benchmarked context (they fix the PTB tables of df_mode 4)
+            rc, want, _ = oracle_api.OracleProblem(root, params, sl, famod_chain=0,
+                                                   after_surface=lambda s: s.set_thermo_averages(avg)).spectra()
         finally:
             shutil.rmtree(root, ignore_errors=True)
         if rc != 0:
@@ -448,13 +450,13 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
     cells = e - b
     surf = synthetic.bench_surface(b, e, baryon=True)
     h.set_surface(surf)                                     # host layer: this block's thermodynamic sums ...
-    shard.set_global_thermo_averages(h)                     # ... -> averages of the WHOLE surface (set-up; torch.distributed)
+    avg = shard.set_global_thermo_averages(h)               # ... -> averages of the WHOLE surface (set-up; torch.distributed)
     h.prepare()
     shape = h.spectra_shape()
     total = int(np.prod(shape))
     evals_global = float(G) * total
 
-    check = oracle_spot_check(args, h, surf) if (rank == 0 and args.check_cells > 0) else None
+    check = oracle_spot_check(args, h, surf, avg) if (rank == 0 and args.check_cells > 0) else None
     if world > 1:
         attach_product_communicator(h, world, rank)
 

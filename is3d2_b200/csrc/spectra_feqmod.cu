@@ -21,6 +21,8 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, int n
                                        double *__restrict__ out);
 is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out);
 bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots);
+bool pair_tables_core(const std::vector<int> &rep, const double *mass, const double *sign, const double *baryon, int R,
+                      std::vector<int> *singles, std::vector<int> *pairs);
 void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
                    int64_t *cells_per_chunk);
 // df_mode 5 per-cell stage (spectra_famod.cu): fills the same pack layout, counters[8] = reconstruction failures,
@@ -117,7 +119,9 @@ __global__ void feqmod_tile_flags_kernel(const double *__restrict__ pack, int64_
 // Two lean loops instead of one loop with a per-item branch: the modified loop alone needs far fewer registers, so ptxas
 // interleaves the R evaluations (with both branches in one body it fell back to two at a time) and the per-item flag
 // load / test / branch / reconvergence instructions disappear.
-template <bool LINEAR, bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM, int R>
+// PAIR = true: a slot holds a charge-conjugate pair of classes (two class ids per slot, two renorm entries per slot; see
+// spectra_df.cu pair_tables_core and feqmod_accum_pair_u).
+template <bool LINEAR, bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM, int R, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 2)
 feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk,
                       const double *__restrict__ renorm, const int *__restrict__ tile_linear, FeqGrid g,
@@ -137,13 +141,15 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
   const int col = blockIdx.x * kThreads + t;
   const int colc = col < g.ncols ? col : g.ncols - 1;
   const int grp = colc / g.NpT, ip = colc - grp * g.NpT;
+  static_assert(!PAIR || BARYON, "pairs exist only with baryon terms");
+  constexpr int S = PAIR ? 2 : 1;                       // class ids (and renorm entries) per slot
   DfBin bin[R];
-  double acc[R];
-  int jbin[R], sp[R];
-  const int cls0 = g.slot_class[grp * R];               // slot 0 of a group is never padding
+  double acc[R], accm[PAIR ? R : 1];
+  int jbin[R], jbinm[PAIR ? R : 1], sp[R];
+  const int cls0 = g.slot_class[S * grp * R];           // slot 0 of a group is never padding
 #pragma unroll
   for (int r = 0; r < R; r++) {
-    const int cls = g.slot_class[grp * R + r];
+    const int cls = g.slot_class[S * (grp * R + r)];
     sp[r] = cls >= 0 ? cls : cls0;
     const int jj = sp[r] * g.NpT + ip;
     jbin[r] = (col < g.ncols && cls >= 0) ? jj : -1;
@@ -151,12 +157,19 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
     bin[r].mT = mT; bin[r].mT2 = mT * mT; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
     asm volatile("" : "+d"(bin[r].mT2));      // opaque: ptxas otherwise re-multiplies mT^2 (and pT^2) per item to save registers
     acc[r] = 0.0;
+    if (PAIR) {
+      const int clsm = g.slot_class[S * (grp * R + r) + 1];
+      jbinm[r] = (col < g.ncols && clsm >= 0) ? clsm * g.NpT + ip : -1;
+      accm[r] = 0.0;
+    }
   }
   const double pT = g.pT[ip];
   double pT2 = pT * pT;
   asm volatile("" : "+d"(pT2));
   int eslot = kMaxBaryon + (BARYON ? (int)bin[0].baryon : 0);
   asm volatile("" : "+r"(eslot));      // opaque: keeps the slot index in a register (ptxas otherwise re-derives it with F2I per item)
+  int eslotm = 2 * kMaxBaryon - eslot;  // the antibaryon partners of a pair slot
+  asm volatile("" : "+r"(eslotm));
 
   const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
   int64_t chunk_end = chunk_begin + cells_per_chunk;
@@ -205,10 +218,13 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
       __syncthreads();
 #pragma unroll 1
       for (int k = 0; k < n_items; k++) {
-        double rn[R];
+        double rn[R], rnm[PAIR ? R : 1];
         if (SPECIES_RENORM) {      // L2-resident row; a software prefetch of item k + 1's row measured 11 % slower (profiles/r01_summary.md)
-          const double *row = renorm + (int64_t)item_cell[k] * g.nslots + grp * R;
-          if (R % 2 == 0) {
+          const double *row = renorm + (int64_t)item_cell[k] * g.nslots + S * grp * R;
+          if (PAIR) {              // (member b > 0, member b < 0) of every slot side by side
+#pragma unroll
+            for (int r = 0; r < R; r++) { const double2 v = *reinterpret_cast<const double2 *>(row + 2 * r); rn[r] = v.x; rnm[r] = v.y; }
+          } else if (R % 2 == 0) {
 #pragma unroll
             for (int r = 0; r < R; r += 2) { const double2 v = *reinterpret_cast<const double2 *>(row + r); rn[r] = v.x; rn[r + 1] = v.y; }
           } else {
@@ -220,9 +236,17 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
           const FeqmodItem &it = items[k].mod;        // shared memory: broadcast LDS.128 + one LDS.64 for eb[eslot]
           const FeqmodShared sh = feqmod_share(it, pT, pT2);
           const double eb = BARYON ? it.eb[eslot] : 1.0;
+          if (PAIR) {
+            const double ebm = it.eb[eslotm];
 #pragma unroll
-          for (int r = 0; r < R; r++)
-            feqmod_accum_u<BARYON, OUTFLOW, !SPECIES_RENORM>(acc[r], it, sh, eb, bin[r].mT, bin[r].mT2, bin[r].sign, SPECIES_RENORM ? rn[r] : 1.0, exptab);
+            for (int r = 0; r < R; r++)
+              feqmod_accum_pair_u<OUTFLOW, !SPECIES_RENORM>(acc[r], accm[r], it, sh, eb, ebm, bin[r].mT, bin[r].mT2, bin[r].sign,
+                                                            SPECIES_RENORM ? rn[r] : 1.0, SPECIES_RENORM ? rnm[r] : 1.0, exptab);
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+              feqmod_accum_u<BARYON, OUTFLOW, !SPECIES_RENORM>(acc[r], it, sh, eb, bin[r].mT, bin[r].mT2, bin[r].sign, SPECIES_RENORM ? rn[r] : 1.0, exptab);
+          }
         } else {
           const DfItem it = items[k].lin;
           const DfShared sh = df_share<BARYON>(it, pT, pT2);
@@ -231,6 +255,13 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
             double v = df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, bin[r], exptab);
             if (SPECIES_RENORM) v = (rn[r] != 0.0) ? v : 0.0;   // NaN renorm: the reference skips the species (:828-832)
             acc[r] += v;
+            if (PAIR) {            // the rare fallback items: the partner is evaluated on its own
+              DfBin bm = bin[r];
+              bm.baryon = -bm.baryon;
+              double vm = df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, bm, exptab);
+              if (SPECIES_RENORM) vm = (rnm[r] != 0.0) ? vm : 0.0;
+              accm[r] += vm;
+            }
           }
         }
       }
@@ -244,15 +275,19 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
       int64_t idx = iy + (int64_t)g.Ny * (iphi + (int64_t)g.Nphi * jbin[r]);
       partial[pbase + idx] += acc[r];
     }
+    if (PAIR && jbinm[r] >= 0) {
+      int64_t idx = iy + (int64_t)g.Ny * (iphi + (int64_t)g.Nphi * jbinm[r]);
+      partial[pbase + idx] += accm[r];
+    }
   }
 }
 
-template <bool BARYON, bool SPECIES_RENORM>
+template <bool BARYON, bool SPECIES_RENORM, bool PAIR>
 void launch_feqmod(bool reg, bool outflow, dim3 grid, cudaStream_t st, const double *pack, int64_t stride, int64_t n, int64_t cpc,
                    const double *renorm, const int *tile_linear, const FeqGrid &g, double *partial, int64_t total)
 {
   // modified-distribution items (regulate_deltaf does not reach them), then the linear-df fallback items
-#define IS3D_LAUNCH(LIN, REG, OUT) feqmod_spectra_kernel<LIN, BARYON, REG, OUT, SPECIES_RENORM, kBins><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, renorm, tile_linear, g, partial, total)
+#define IS3D_LAUNCH(LIN, REG, OUT) feqmod_spectra_kernel<LIN, BARYON, REG, OUT, SPECIES_RENORM, kBins, PAIR><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, renorm, tile_linear, g, partial, total)
   if (outflow) IS3D_LAUNCH(false, false, true);
   else IS3D_LAUNCH(false, false, false);
   if (reg && outflow) IS3D_LAUNCH(true, true, true);
@@ -286,15 +321,26 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   SpeciesBins sb;
   IS3D_TRY(build_bin_arrays(ctx, &sb));
   g.mT = sb.mT; g.pT = sb.pT; g.baryon = sb.baryon; g.sign = sb.sign;
-  std::vector<int> slots;
-  if (!build_slot_table(ctx, kBins, &slots)) {
+  // thread groups: single classes and, with baryon terms, charge-conjugate pairs (spectra_df.cu pair_tables_core)
+  std::vector<int> slots, pair_slots;
+  bool ok;
+  if (p.include_baryon) {
+    std::vector<int> class_of, rep;
+    species_classes(ctx, &class_of, &rep);
+    ok = pair_tables_core(rep, ctx->h_mass.data(), ctx->h_sign.data(), ctx->h_baryon.data(), kBins, &slots, &pair_slots);
+  } else {
+    ok = build_slot_table(ctx, kBins, &slots);
+  }
+  if (!ok) {
     ctx->set_error("species list holds a baryon number outside -2..2 (the reference's PDG readers produce hadrons and the deuteron only)");
     return IS3D_ERR_INVALID;
   }
   void *d_slots = nullptr;
-  IS3D_TRY(ctx->get_scratch("k2_slots", slots.size() * sizeof(int), &d_slots));
-  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `slots` is pageable host memory
+  std::vector<int> both(slots);
+  both.insert(both.end(), pair_slots.begin(), pair_slots.end());
+  IS3D_TRY(ctx->get_scratch("k2_slots", (both.size() + 1) * sizeof(int), &d_slots));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `both` is pageable host memory
   g.slot_class = (const int *)d_slots;
   g.NpT = ctx->NpT; g.ns = sb.nclass; g.nslots = (int)slots.size(); g.ncols = ctx->NpT * (int)(slots.size() / kBins);
   const int64_t per_species = (int64_t)ctx->NpT * ctx->Nphi * ctx->Ny;
@@ -304,13 +350,18 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   g.w_on_dan = (p.df_mode == 5);
   g.exptab = ctx->d_exptab;
 
-  const int nslices = (g.ncols + kThreads - 1) / kThreads;
-  const int64_t blocks_per_chunk = (int64_t)nslices * ctx->Ny * ctx->Nphi;
+  FeqGrid gp = g;                                                // the pair launch: two class ids / renorm entries per slot
+  gp.slot_class = (const int *)d_slots + slots.size();
+  gp.nslots = (int)pair_slots.size();
+  gp.ncols = ctx->NpT * (int)(pair_slots.size() / (2 * kBins));
+  const int nslices = (g.ncols + kThreads - 1) / kThreads, nslices_pair = (gp.ncols + kThreads - 1) / kThreads;
+  const int64_t blocks_per_chunk = (int64_t)(nslices + nslices_pair) * ctx->Ny * ctx->Nphi;
   if ((int64_t)ctx->Ny * ctx->Nphi > 65535) { ctx->set_error("Ny*Nphi exceeds 65535"); return IS3D_ERR_INVALID; }
 
   // cells per pass: bounds the pack (440 B/cell) and the PTM renorm table (8 Ns B/cell) to ~2 GB
   int64_t macro = pass_cells(2 << 20);
-  if (species_renorm) { int64_t m2 = ((int64_t)1 << 31) / (8 * (int64_t)g.nslots); if (m2 < macro) macro = m2; }
+  const int64_t all_slots = (int64_t)g.nslots + gp.nslots;
+  if (species_renorm) { int64_t m2 = ((int64_t)1 << 31) / (8 * all_slots); if (m2 < macro) macro = m2; }
   macro = macro / kTile * kTile;
   if (macro < kTile) macro = kTile;
   const int64_t stride = n < macro ? n : macro;
@@ -323,7 +374,8 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)FP_SIZE * stride * sizeof(double), &pack));
   IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total_class * sizeof(double), &partial));
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
-  if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm", (size_t)stride * g.nslots * sizeof(double), &renorm));
+  if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm", (size_t)stride * all_slots * sizeof(double), &renorm));
+  double *renorm_pair = species_renorm ? (double *)renorm + (size_t)stride * g.nslots : nullptr;
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total_class * sizeof(double), ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
 
@@ -343,29 +395,42 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
       launches++;
     }
     if (species_renorm) {
-      int64_t work = count * g.nslots;
-      feqmod_renorm_kernel<<<(unsigned)((work + 127) / 128), 128, 0, ctx->stream>>>(
-          (double *)pack, stride, count, g.nslots, g.slot_class, sb.c_mass, sb.c_deg, sb.c_baryon, sb.c_sign, ctx->d_gla_root,
-          ctx->d_gla_weight, ctx->gla_pts, ctx->d_exptab, (double *)renorm);
-      IS3D_CUDA_TRY(ctx, cudaGetLastError());
-      launches++;
+      for (int pass = 0; pass < 2; pass++) {           // single slots, then the flat list of pair members
+        const FeqGrid &q = pass ? gp : g;
+        const int64_t work = count * q.nslots;
+        if (!work) continue;
+        feqmod_renorm_kernel<<<(unsigned)((work + 127) / 128), 128, 0, ctx->stream>>>(
+            (double *)pack, stride, count, q.nslots, q.slot_class, sb.c_mass, sb.c_deg, sb.c_baryon, sb.c_sign, ctx->d_gla_root,
+            ctx->d_gla_weight, ctx->gla_pts, ctx->d_exptab, pass ? renorm_pair : (double *)renorm);
+        IS3D_CUDA_TRY(ctx, cudaGetLastError());
+        launches++;
+      }
     }
     IS3D_CUDA_TRY(ctx, cudaMemsetAsync(tile_linear, 0, ntile_flags * sizeof(int), ctx->stream));
     feqmod_tile_flags_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>((double *)pack, stride, count, p.dimension, (int *)tile_linear);
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
     launches++;
     int nch = (int)((count + cpc - 1) / cpc);
-    dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch);
+    dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch), grid_pair(nslices_pair, ctx->Ny * ctx->Nphi, nch);
     const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0;
     if (p.include_baryon) {
-      if (species_renorm) launch_feqmod<true, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
-      else launch_feqmod<true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
+      // the pair launch first: its blocks are the longer ones
+      if (nslices_pair) {
+        if (species_renorm) launch_feqmod<true, true, true>(reg, outflow, grid_pair, ctx->stream, (double *)pack, stride, count, cpc, renorm_pair, (const int *)tile_linear, gp, (double *)partial, total_class);
+        else launch_feqmod<true, false, true>(reg, outflow, grid_pair, ctx->stream, (double *)pack, stride, count, cpc, renorm_pair, (const int *)tile_linear, gp, (double *)partial, total_class);
+        launches += 2;
+      }
+      if (nslices) {
+        if (species_renorm) launch_feqmod<true, true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
+        else launch_feqmod<true, false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
+        launches += 2;
+      }
     } else {
-      if (species_renorm) launch_feqmod<false, true>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
-      else launch_feqmod<false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
+      if (species_renorm) launch_feqmod<false, true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
+      else launch_feqmod<false, false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
+      launches += 2;
     }
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
-    launches += 2;
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
     IS3D_CUDA_TRY(ctx, cudaEventSynchronize(e1));
     float ms = 0.f;
