@@ -308,6 +308,14 @@ is3d_status is3d_probe_aniso_math(is3d_ctx *ctx, int64_t n, const double *x, dou
  * is too small, -3 for a baryon number outside -2 .. 2 (the reference's PDG readers produce hadrons and the deuteron). */
 int         is3d_species_groups(int ns, const double *mass, const double *sign, const double *baryon, int include_baryon,
                                 int slots_per_group, int *class_of, int *slot_class, int capacity, int *nclass);
+/* Host-only helper: the layout the spectra kernels use WITH baryon terms (include_baryon = 1).  A baryon class and its
+ * antibaryon class (same mass, same statistics, opposite baryon number) form a charge-conjugate PAIR that is evaluated from one
+ * exponential; every other class is a single.  single_slots = groups of slots_per_group class ids with one baryon number
+ * per group; pair_slots = (class with b > 0, its partner) per slot, groups of slots_per_group slots with one |b|; padding =
+ * -1.  Class ids are those of is3d_species_groups with include_baryon = 1.  Returns the number of classes, -1 / -2 / -3 as
+ * is3d_species_groups. */
+int         is3d_species_pairs(int ns, const double *mass, const double *sign, const double *baryon, int slots_per_group,
+                               int *single_slots, int single_capacity, int *pair_slots, int pair_capacity, int *n_single, int *n_pair);
 /* device -> host copy on the context's stream (e.g. to inspect the list of is3d_sample_device without a CUDA runtime of one's own) */
 is3d_status is3d_copy_from_device(is3d_ctx *ctx, void *host, const void *device, size_t bytes);
 /* the CUDA stream all kernels of this context are launched on (as a void* cudaStream_t) */

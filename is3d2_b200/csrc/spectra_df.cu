@@ -269,6 +269,9 @@ bool slot_table_core(const std::vector<int> &rep, const double *baryon, bool bar
 // -- same mass, same statistics, opposite baryon number -- differ only in the b-dependent pieces of df and in exp(-b alpha_B),
 // so they are evaluated together.  pairs = 2 class ids per slot (b > 0 first), groups of R slots with ONE |b|, padded with
 // (-1, -1); singles = the slot table of every class without a partner (mesons, the deuteron, unmatched baryons).
+void species_classes_core(int ns, const double *mass, const double *sign, const double *baryon, bool baryon_on,
+                          std::vector<int> *class_of, std::vector<int> *rep);
+
 bool pair_tables_core(const std::vector<int> &rep, const double *mass, const double *sign, const double *baryon, int R,
                       std::vector<int> *singles, std::vector<int> *pairs)
 {
@@ -518,6 +521,21 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
 }
 
 }  // namespace is3d
+
+extern "C" int is3d_species_pairs(int ns, const double *mass, const double *sign, const double *baryon, int slots_per_group,
+                                  int *single_slots, int single_capacity, int *pair_slots, int pair_capacity, int *n_single, int *n_pair)
+{
+  if (ns <= 0 || !mass || !sign || !baryon || slots_per_group <= 0 || !single_slots || !pair_slots || !n_single || !n_pair) return -1;
+  std::vector<int> cls, rep, singles, pairs;
+  is3d::species_classes_core(ns, mass, sign, baryon, true, &cls, &rep);
+  if (!is3d::pair_tables_core(rep, mass, sign, baryon, slots_per_group, &singles, &pairs)) return -3;
+  if ((int)singles.size() > single_capacity || (int)pairs.size() > pair_capacity) return -2;
+  for (size_t k = 0; k < singles.size(); k++) single_slots[k] = singles[k];
+  for (size_t k = 0; k < pairs.size(); k++) pair_slots[k] = pairs[k];
+  *n_single = (int)singles.size();
+  *n_pair = (int)pairs.size();
+  return (int)rep.size();
+}
 
 extern "C" int is3d_species_groups(int ns, const double *mass, const double *sign, const double *baryon, int include_baryon,
                                    int slots_per_group, int *class_of, int *slot_class, int capacity, int *nclass)

@@ -118,3 +118,50 @@ def test_species_groups_have_one_baryon_number(libs, include_baryon, R):
     rc = lib.is3d_species_groups(ns, mass.ctypes.data_as(C.c_void_p), sign.ctypes.data_as(C.c_void_p), bad.ctypes.data_as(C.c_void_p),
                                  1, R, class_of.ctypes.data_as(C.c_void_p), slots.ctypes.data_as(C.c_void_p), len(slots), C.byref(nclass))
     assert rc == -3
+
+
+def test_charge_conjugate_pairs_layout(libs):
+    """Host logic behind the PAIR launches of the spectra kernels (is3d_species_pairs): every class is either a single or a
+    member of exactly one pair; the members of a pair have the same mass and statistics and opposite baryon number (b > 0
+    first); groups carry one baryon number (singles) resp. one |b| (pairs); SMASH: 58 pairs + 77 singles."""
+    import numpy as np
+    lib, _ = libs
+    mass, sign, baryon = _smash_species()
+    ns, R = len(mass), 4
+    class_of = np.zeros(ns, dtype=np.int32)
+    slots = np.full(4 * ns, -7, dtype=np.int32)
+    nclass = C.c_int()
+    lib.is3d_species_groups.restype = C.c_int
+    lib.is3d_species_groups(ns, mass.ctypes.data_as(C.c_void_p), sign.ctypes.data_as(C.c_void_p), baryon.ctypes.data_as(C.c_void_p),
+                            1, R, class_of.ctypes.data_as(C.c_void_p), slots.ctypes.data_as(C.c_void_p), len(slots), C.byref(nclass))
+    singles = np.full(4 * ns, -7, dtype=np.int32)
+    pairs = np.full(8 * ns, -7, dtype=np.int32)
+    n1, n2 = C.c_int(), C.c_int()
+    lib.is3d_species_pairs.restype = C.c_int
+    nc = lib.is3d_species_pairs(ns, mass.ctypes.data_as(C.c_void_p), sign.ctypes.data_as(C.c_void_p), baryon.ctypes.data_as(C.c_void_p), R,
+                                singles.ctypes.data_as(C.c_void_p), len(singles), pairs.ctypes.data_as(C.c_void_p), len(pairs),
+                                C.byref(n1), C.byref(n2))
+    assert nc == nclass.value == 193
+    s1, p2 = singles[:n1.value], pairs[:n2.value].reshape(-1, 2)
+    assert n1.value % R == 0 and len(p2) % R == 0
+    prop = {class_of[s]: (mass[s], sign[s], baryon[s]) for s in range(ns)}
+    used = [c for c in s1 if c >= 0] + [c for c in p2.ravel() if c >= 0]
+    assert sorted(used) == list(range(nc))                         # every class exactly once
+    real = p2[p2[:, 0] >= 0]
+    assert len(real) == 58 and len([c for c in s1 if c >= 0]) == 77
+    for a, b in real:
+        assert b >= 0 and prop[a][0] == prop[b][0] and prop[a][1] == prop[b][1] and prop[a][2] > 0 and prop[b][2] == -prop[a][2]
+    assert np.all((p2[:, 0] >= 0) == (p2[:, 1] >= 0))
+    for g in range(len(p2) // R):
+        grp = p2[g * R:(g + 1) * R]
+        assert grp[0, 0] >= 0 and len({prop[c][2] for c in grp[:, 0] if c >= 0}) == 1
+    for g in range(len(s1) // R):
+        grp = s1[g * R:(g + 1) * R]
+        assert grp[0] >= 0 and len({prop[c][2] for c in grp if c >= 0}) == 1
+    # a list without antiparticles has no pairs
+    keep = baryon >= 0
+    nc2 = lib.is3d_species_pairs(int(keep.sum()), np.ascontiguousarray(mass[keep]).ctypes.data_as(C.c_void_p),
+                                 np.ascontiguousarray(sign[keep]).ctypes.data_as(C.c_void_p),
+                                 np.ascontiguousarray(baryon[keep]).ctypes.data_as(C.c_void_p), R, singles.ctypes.data_as(C.c_void_p), len(singles),
+                                 pairs.ctypes.data_as(C.c_void_p), len(pairs), C.byref(n1), C.byref(n2))
+    assert nc2 > 0 and n2.value == 0
