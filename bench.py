@@ -563,10 +563,12 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
     traffic = traffic_src = None
     try:
         cap = json.load(open(os.path.join(REPO, "profiles", "ncu_k1_headline.json")))
-        if mix and cap.get("listing_sha256") == mix["listing_sha256"] and cap.get("cells_per_launch"):
+        have = {label: mix["listing_sha256"] if mix else None, label_pair: mix_pair["listing_sha256"] if mix_pair else None}
+        if mix and cap.get("listing_sha256") == have and cap.get("cells_per_launch"):
             per_cell = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["cells_per_launch"]
             traffic = per_cell * min(cells, 4 << 20)
-            traffic_src = f"ncu dram__bytes_read.sum + dram__bytes_write.sum per cell ({per_cell:.1f} B) x cells of one launch, profiles/ncu_k1_headline.json (same inner-loop SASS)"
+            traffic_src = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of the pair + single launches of one pass, per cell ({per_cell:.1f} B) "
+                           "x cells of one pass, profiles/ncu_k1_headline.json (same inner-loop SASS as the loaded library)")
     except (OSError, KeyError, ValueError):
         pass
     bytes_alg = cells * 25 * 8.0 + total * 8.0

@@ -67,7 +67,10 @@ is3d_status is3d_create(const is3d_params *p, is3d_ctx **out)
   ctx->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return IS3D_ERR_CUDA; }
-  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     g_create_error = "cudaEventCreate failed";
     is3d_destroy(ctx);
     return IS3D_ERR_CUDA;
@@ -99,6 +102,9 @@ void is3d_destroy(is3d_ctx *ctx)
     if (ctx->ev_sorted[k]) cudaEventDestroy(ctx->ev_sorted[k]);
     if (ctx->ev_copied[k]) cudaEventDestroy(ctx->ev_copied[k]);
   }
+  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);

@@ -33,6 +33,9 @@ struct is3d_ctx {
   is3d_params prm;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // timing events of the compute calls (created once, destroyed with the context)
+  // second compute stream: the single-class launch of the spectra kernels runs beside the pair launch and fills its tail
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // sampler copy pipeline (sampler.cu): pass k's D2H on copy_stream overlaps pass k + 1's kernels on `stream`
   volatile unsigned long long *h_words = nullptr;   // mapped pinned words: control scalars the device publishes to the host
   unsigned long long *d_words = nullptr;            // their device address

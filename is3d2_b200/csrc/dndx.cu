@@ -11,6 +11,8 @@ namespace is3d {
 
 is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out);
 bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots);
+bool pair_tables_core(const std::vector<int> &rep, const double *mass, const double *sign, const double *baryon, int R, int R_pair,
+                      std::vector<int> *singles, std::vector<int> *pairs);
 void pick_chunks(int64_t ncells, int64_t blocks_per_chunk, int64_t resident, int64_t granule, int64_t max_chunks,
                  int *nchunks, int64_t *cells_per_chunk);
 
@@ -64,7 +66,9 @@ __device__ __forceinline__ DndxPoint dndx_point(const DndxGrid &g, PackFn pk, in
 }
 
 // thread constants: column (thread group, pT node) of the block, see dndx_common.cuh
-template <int R>
+// PAIR: a slot is a charge-conjugate pair of classes (two class ids per slot; spectra_df.cu pair_tables_core): the thread's
+// constants are those of the b > 0 member, the partner differs by b -> -b only
+template <int R, bool PAIR = false>
 struct DndxThread {
   bool active;                 // the column exists (group < ngroups, pT node < NpT)
   int gl, ip;                  // group inside the block, pT node
@@ -74,6 +78,7 @@ struct DndxThread {
 
   __device__ __forceinline__ void load(const DndxGrid &g, bool baryon_on)
   {
+    constexpr int S = PAIR ? 2 : 1;
     const int t = threadIdx.x;
     int gl_ = t / g.NpT;
     ip = t - gl_ * g.NpT;
@@ -81,10 +86,10 @@ struct DndxThread {
     active = gl_ < g.gpb && grp < g.ngroups;
     if (!active) { gl_ = 0; grp = blockIdx.x * g.gpb; }          // idle threads shadow a valid column and are never summed
     gl = gl_;
-    const int cls0 = g.slot_class[grp * R];                        // slot 0 of a group is never padding
+    const int cls0 = g.slot_class[S * grp * R];                    // slot 0 of a group is never padding
 #pragma unroll
     for (int r = 0; r < R; r++) {
-      const int cls = g.slot_class[grp * R + r];
+      const int cls = g.slot_class[S * (grp * R + r)];
       const int jj = (cls >= 0 ? cls : cls0) * g.NpT + ip;
       const double m = g.mT[jj];
       mT[r] = m; mT2[r] = m * m; sgn[r] = g.sign[jj];
@@ -98,10 +103,13 @@ struct DndxThread {
 
 // End of a cell: thread partials (x pT weight x `gate`) -> sums over the NpT threads of every group -> histograms.
 // red is double-buffered by the caller (one __syncthreads per cell); bins = the cell's histogram bins (shared memory).
-template <int R>
-__device__ __forceinline__ void dndx_flush(double (&acc)[R], double factor, double (*red)[kDndxThreads], const DndxGrid &g,
+// N = values per thread = class ids per thread group: R (single classes) or 2 R (pairs, acc[2 r] = the b > 0 member of slot r,
+// acc[2 r + 1] = its partner -- the order of the flat slot list)
+template <int N>
+__device__ __forceinline__ void dndx_flush(double (&acc)[N], double factor, double (*red)[kDndxThreads], const DndxGrid &g,
                                            const DndxCellBins &bins)
 {
+  constexpr int R = N;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 #pragma unroll
   for (int r = 0; r < R; r++) { red[r][t] = acc[r] * factor; acc[r] = 0.0; }
@@ -133,26 +141,30 @@ struct DndxTiling {
 };
 
 // df_mode 1, 2 (SpacetimeDistribution.cpp:170-441)
-template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, bool PAIR>
 __global__ void __launch_bounds__(kDndxThreads, 2)
 dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_block, SurfaceView surf,
                int64_t surf_begin, DndxGrid g)
 {
-  constexpr int R = kDndxR;
+  static_assert(!PAIR || BARYON, "pairs exist only with baryon terms");
+  constexpr int R = PAIR ? kDndxPairR : kDndxR;       // slots per thread
+  constexpr int N = PAIR ? 2 * R : R;                   // classes (accumulators) per thread
   __shared__ double exptab[kExpTableSize];
   __shared__ DfItemU items[kDndxTile];
-  __shared__ double red[2][R][kDndxThreads];
+  __shared__ double red[2][N][kDndxThreads];
   __shared__ int cell_ok[kDndxMaxCells];
   __shared__ DndxCellBins cell_bins[kDndxMaxCells];
   load_exp_table(exptab, g.exptab);
   const int t = threadIdx.x;
-  DndxThread<R> th;
+  DndxThread<R, PAIR> th;
   th.load(g, BARYON);
   DfThreadU tu;
   tu.pT = th.pT; tu.pT2 = th.pT2; tu.b = th.b; tu.bpT = th.b * th.pT; tu.eslot = th.eslot;
-  double acc[R];
+  DfThreadU tum = tu;                                   // the antibaryon partners of a pair slot
+  if (PAIR) { tum.b = -tu.b; tum.bpT = -tu.bpT; tum.eslot = 2 * kMaxBaryon - tu.eslot; }
+  double acc[N];
 #pragma unroll
-  for (int r = 0; r < R; r++) acc[r] = 0.0;
+  for (int r = 0; r < N; r++) acc[r] = 0.0;
   const DndxTiling tl(g);
   int buf = 0;
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
@@ -189,11 +201,22 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
           for (int k = 0; k < np_tile; k++) {
             const DfItemU &it = items[cl * np_tile + k];
             const DfSharedU sh = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, tu);
+            if (!PAIR) {
 #pragma unroll
-            for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, th.mT[r], th.mT2[r], th.sgn[r], exptab);
+              for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, th.mT[r], th.mT2[r], th.sgn[r], exptab);
+            } else {
+              const DfSharedU shm = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, tum);
+#pragma unroll
+              for (int r = 0; r < R; r++) {           // one x_E and one exponential per pair (spectra_df.cuh)
+                const double xE = df_eval_u_x(it, sh, th.mT[r]);
+                const double e = fast_exp<false>(xE, exptab);
+                acc[2 * r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, th.mT[r], th.mT2[r], th.sgn[r], xE, e);
+                acc[2 * r + 1] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, shm, th.mT[r], th.mT2[r], th.sgn[r], xE, e);
+              }
+            }
           }
         }
-        if (last_tile) { dndx_flush<R>(acc, th.wpT, red[buf], g, cell_bins[cl]); buf ^= 1; }
+        if (last_tile) { dndx_flush<N>(acc, th.wpT, red[buf], g, cell_bins[cl]); buf ^= 1; }
       }
     }
   }
@@ -206,20 +229,22 @@ union DndxItemSlot {
 };
 
 // df_mode 3, 4 (SpacetimeDistribution.cpp:676-1160)
-template <bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM>
+template <bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM, bool PAIR>
 __global__ void __launch_bounds__(kDndxThreads, 2)
 dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_block, SurfaceView surf,
                    int64_t surf_begin, DndxGrid g, const double *__restrict__ gla_root, const double *__restrict__ gla_weight,
                    int gla_pts)
 {
-  constexpr int R = kDndxR;
+  static_assert(!PAIR || BARYON, "pairs exist only with baryon terms");
+  constexpr int R = PAIR ? kDndxPairR : kDndxR;       // slots per thread
+  constexpr int N = PAIR ? 2 * R : R;                   // classes (accumulators, renorm entries) per thread
   __shared__ double exptab[kExpTableSize];
   __shared__ DndxItemSlot items[kDndxTile];
   __shared__ unsigned char item_linear[kDndxTile];
-  __shared__ double red[2][R][kDndxThreads];
+  __shared__ double red[2][N][kDndxThreads];
   __shared__ double cell_rn[kDndxMaxCells];                                   // the cell's |renorm| (0: skip the cell)
   __shared__ int cell_lin[kDndxMaxCells];                                     // the cell may hold linear-df items (breakdown / window)
-  __shared__ double class_rn[SPECIES_RENORM ? kDndxMaxCells : 1][kDndxMaxGroups * R];   // PTM: |renorm| per (cell, class slot)
+  __shared__ double class_rn[SPECIES_RENORM ? kDndxMaxCells : 1][kDndxMaxGroups * N];   // PTM: |renorm| per (cell, class of the flat slot list)
   __shared__ int cell_ok[kDndxMaxCells];
   __shared__ DndxCellBins cell_bins[kDndxMaxCells];
   __shared__ RenormNodes nodes;
@@ -227,16 +252,17 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
   if (SPECIES_RENORM) nodes.load(gla_root, gla_weight, gla_pts);
   __syncthreads();
   const int t = threadIdx.x;
-  DndxThread<R> th;
+  DndxThread<R, PAIR> th;
   th.load(g, BARYON);
+  const int eslotm = 2 * kMaxBaryon - th.eslot;         // the antibaryon partners of a pair slot
   DfBin bin[R];                                         // linear-df fallback of breakdown cells
 #pragma unroll
   for (int r = 0; r < R; r++) { bin[r].mT = th.mT[r]; bin[r].mT2 = th.mT2[r]; bin[r].baryon = th.b; bin[r].sign = th.sgn[r]; }
-  double acc[R];
+  double acc[N];
 #pragma unroll
-  for (int r = 0; r < R; r++) acc[r] = 0.0;
+  for (int r = 0; r < N; r++) acc[r] = 0.0;
   const DndxTiling tl(g);
-  const int nsum = g.gpb * R;
+  const int nsum = g.gpb * N;
   int buf = 0;
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
   int64_t c1 = c0 + cells_per_block;
@@ -274,10 +300,10 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
           for (int task = t; task < tl.cpt * nsum; task += kDndxThreads) {
             const int tc = task / nsum, js = task - tc * nsum;
             const int64_t rcell = cell0 + tc;
-            const int grp = blockIdx.x * g.gpb + js / R;
+            const int grp = blockIdx.x * g.gpb + js / N;
             double rn = 0.0;
             if (rcell < c1 && grp < g.ngroups && pack[DP_VALID * stride + rcell] != 0.0) {
-              const int cls = g.slot_class[grp * R + (js % R)];
+              const int cls = g.slot_class[grp * N + (js % N)];
               if (cls >= 0) {
                 auto pkr = [&](int k) { return pack[k * stride + rcell]; };
                 rn = feqmod_renorm_ptm_fused(pkr, g.c_mass[cls], g.c_deg[cls], g.c_baryon[cls], g.c_sign[cls], nodes, gla_pts, exptab);
@@ -291,36 +317,47 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
       const bool last_tile = p0 + kDndxTile >= tl.npoints;
       for (int cl = 0; cl < tl.cpt && cell0 + cl < c1; cl++) {
         if (!cell_ok[cl]) continue;
-        double rn[R];
+        double rn[N];                                    // index = accumulator index (pairs: 2 r = the b > 0 member, 2 r + 1 = its partner)
 #pragma unroll
-        for (int r = 0; r < R; r++) rn[r] = SPECIES_RENORM ? class_rn[cl][th.gl * R + r] : 1.0;
-        if (th.active && !cell_lin[cl]) {
-          // common case, no linear-df item in this cell: lean loop, the R evaluations interleave
-#pragma unroll 1
-          for (int k = 0; k < np_tile; k++) {
-            const FeqmodItem &it = items[cl * np_tile + k].mod;
-            const FeqmodShared sh = feqmod_share(it, th.pT, th.pT2);
-            const double eb = BARYON ? it.eb[th.eslot] : 1.0;
+        for (int r = 0; r < N; r++) rn[r] = SPECIES_RENORM ? class_rn[cl][th.gl * N + r] : 1.0;
+        // one modified-distribution item for the thread's slots
+        auto modified = [&](const FeqmodItem &it) {
+          const FeqmodShared sh = feqmod_share(it, th.pT, th.pT2);
+          const double eb = BARYON ? it.eb[th.eslot] : 1.0;
+          if (PAIR) {
+            const double ebm = it.eb[eslotm];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+              feqmod_accum_pair_u<OUTFLOW, !SPECIES_RENORM>(acc[PAIR ? 2 * r : r], acc[PAIR ? 2 * r + 1 : r], it, sh, eb, ebm, th.mT[r], th.mT2[r],
+                                                            th.sgn[r], rn[PAIR ? 2 * r : r], rn[PAIR ? 2 * r + 1 : r], exptab);
+          } else {
 #pragma unroll
             for (int r = 0; r < R; r++)
               feqmod_accum_u<BARYON, OUTFLOW, !SPECIES_RENORM>(acc[r], it, sh, eb, th.mT[r], th.mT2[r], th.sgn[r], rn[r], exptab);
           }
+        };
+        if (th.active && !cell_lin[cl]) {
+          // common case, no linear-df item in this cell: lean loop, the R evaluations interleave
+#pragma unroll 1
+          for (int k = 0; k < np_tile; k++) modified(items[cl * np_tile + k].mod);
         } else if (th.active) {
 #pragma unroll 1
           for (int k = 0; k < np_tile; k++) {
             const int slot = cl * np_tile + k;
             if (!item_linear[slot]) {
-              const FeqmodItem &it = items[slot].mod;
-              const FeqmodShared sh = feqmod_share(it, th.pT, th.pT2);
-              const double eb = BARYON ? it.eb[th.eslot] : 1.0;
-#pragma unroll
-              for (int r = 0; r < R; r++)
-                feqmod_accum_u<BARYON, OUTFLOW, !SPECIES_RENORM>(acc[r], it, sh, eb, th.mT[r], th.mT2[r], th.sgn[r], rn[r], exptab);
+              modified(items[slot].mod);
             } else {
               const DfItem it = items[slot].lin;
               const DfShared sh = df_share<BARYON>(it, th.pT, th.pT2);
 #pragma unroll
-              for (int r = 0; r < R; r++) acc[r] += df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, bin[r], exptab);
+              for (int r = 0; r < R; r++) {
+                acc[PAIR ? 2 * r : r] += df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, bin[r], exptab);
+                if (PAIR) {                             // the rare fallback items: the partner is evaluated on its own
+                  DfBin bm = bin[r];
+                  bm.baryon = -bm.baryon;
+                  acc[PAIR ? 2 * r + 1 : r] += df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, bm, exptab);
+                }
+              }
             }
           }
         }
@@ -328,10 +365,10 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
           // a NaN / inf renormalisation (stored as 0) skips the (cell, species) in both branches (SpacetimeDistribution.cpp:955-959)
           if (SPECIES_RENORM) {
 #pragma unroll
-            for (int r = 0; r < R; r++) acc[r] = (rn[r] != 0.0) ? acc[r] : 0.0;
+            for (int r = 0; r < N; r++) acc[r] = (rn[r] != 0.0) ? acc[r] : 0.0;
           }
           const double factor = (SPECIES_RENORM || cell_rn[cl] != 0.0) ? th.wpT : 0.0;
-          dndx_flush<R>(acc, factor, red[buf], g, cell_bins[cl]);
+          dndx_flush<N>(acc, factor, red[buf], g, cell_bins[cl]);
           buf ^= 1;
         }
       }
@@ -349,21 +386,33 @@ __global__ void dndx_expand_kernel(const double *__restrict__ class_hist, const 
 }
 
 // species classes, their (class, pT) bin arrays and the uniform-baryon slot table (shared with the spectra kernels)
-is3d_status build_dndx_grid(is3d_ctx *ctx, DndxGrid *g, const int **class_of_dev)
+// *g: the single-class launch; *gp: the charge-conjugate pair launch (gp->ngroups = 0 without baryon terms / without pairs),
+// whose slot list holds two class ids per slot and kDndxPairR slots per thread group
+is3d_status build_dndx_grid(is3d_ctx *ctx, DndxGrid *g, DndxGrid *gp, const int **class_of_dev)
 {
   const is3d_params &p = ctx->prm;
   SpeciesBins sb;
   IS3D_TRY(build_bin_arrays(ctx, &sb));
   if (ctx->NpT > kDndxThreads) { ctx->set_error("dN/dX: pT table longer than 256 points"); return IS3D_ERR_UNSUPPORTED; }
-  std::vector<int> slots;
-  if (!build_slot_table(ctx, kDndxR, &slots)) {
+  std::vector<int> slots, pair_slots;
+  bool ok;
+  if (p.include_baryon) {
+    std::vector<int> class_of, rep;
+    species_classes(ctx, &class_of, &rep);
+    ok = pair_tables_core(rep, ctx->h_mass.data(), ctx->h_sign.data(), ctx->h_baryon.data(), kDndxR, kDndxPairR, &slots, &pair_slots);
+  } else {
+    ok = build_slot_table(ctx, kDndxR, &slots);
+  }
+  if (!ok) {
     ctx->set_error("species list holds a baryon number outside -2..2 (the reference's PDG readers produce hadrons and the deuteron only)");
     return IS3D_ERR_INVALID;
   }
   void *d_slots = nullptr;
-  IS3D_TRY(ctx->get_scratch("dndx_slots", slots.size() * sizeof(int), &d_slots));
-  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `slots` is pageable host memory
+  std::vector<int> both(slots);
+  both.insert(both.end(), pair_slots.begin(), pair_slots.end());
+  IS3D_TRY(ctx->get_scratch("dndx_slots", (both.size() + 1) * sizeof(int), &d_slots));
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `both` is pageable host memory
   *class_of_dev = sb.class_of;
   g->ns = sb.nclass;
   g->ngroups = (int)(slots.size() / kDndxR);
@@ -379,6 +428,9 @@ is3d_status build_dndx_grid(is3d_ctx *ctx, DndxGrid *g, const int **class_of_dev
   g->tau_min = p.tau_min; g->tau_width = (p.tau_max - p.tau_min) / (double)p.tau_bins; g->tau_bins = p.tau_bins;
   g->r_min = p.r_min; g->r_width = (p.r_max - p.r_min) / (double)p.r_bins; g->r_bins = p.r_bins;
   g->phi_width = kTwoPi / (double)p.phip_bins; g->phi_bins = p.phip_bins;
+  *gp = *g;
+  gp->slot_class = (const int *)d_slots + slots.size();
+  gp->ngroups = (int)(pair_slots.size() / (2 * kDndxPairR));
   return IS3D_OK;
 }
 
@@ -396,15 +448,16 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
     return IS3D_ERR_INVALID;
   }
   const int64_t n = ctx->surf.n;
-  DndxGrid g;
+  DndxGrid g, gp;
   const int *class_of_dev = nullptr;
-  IS3D_TRY(build_dndx_grid(ctx, &g, &class_of_dev));
+  IS3D_TRY(build_dndx_grid(ctx, &g, &gp, &class_of_dev));
   const size_t class_bins = (size_t)g.ns * (p.tau_bins + p.r_bins + p.phip_bins);
   void *class_hist = nullptr;
   IS3D_TRY(ctx->get_scratch("dndx_class_hist", class_bins * sizeof(double), &class_hist));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(class_hist, 0, class_bins * sizeof(double), ctx->stream));
   g.hist_tau = (double *)class_hist; g.hist_r = g.hist_tau + (size_t)g.ns * p.tau_bins; g.hist_phi = g.hist_r + (size_t)g.ns * p.r_bins;
   g.exptab = ctx->d_exptab;
+  gp.hist_tau = g.hist_tau; gp.hist_r = g.hist_r; gp.hist_phi = g.hist_phi; gp.exptab = g.exptab;
 
   DfFlags dfl;
   dfl.df_mode = p.df_mode; dfl.dimension = p.dimension; dfl.include_baryon = p.include_baryon;
@@ -424,7 +477,7 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
 
-  const int nslices = (g.ngroups + g.gpb - 1) / g.gpb;
+  const int nslices = (g.ngroups + g.gpb - 1) / g.gpb, nslices_pair = (gp.ngroups + gp.gpb - 1) / gp.gpb;
   const int64_t resident = 2LL * ctx->sm_count;      // two 256-thread blocks per SM (launch bounds)
   cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   float ms_total = 0.f;
@@ -439,26 +492,36 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
       const int npoints = g.Ny * g.Neta * g.Nphi;
       int64_t cpt = npoints >= kDndxTile ? 1 : kDndxTile / npoints;
       if (cpt > kDndxMaxCells) cpt = kDndxMaxCells;
-      pick_chunks(count, nslices, resident, cpt, 65535, &nchunks, &cpb);
+      pick_chunks(count, nslices + nslices_pair, resident, cpt, 65535, &nchunks, &cpb);
     }
-    dim3 grid(nslices, (unsigned)nchunks);
+    dim3 grid(nslices, (unsigned)nchunks), grid_pair(nslices_pair, (unsigned)nchunks);
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     if (!feqmod) {
       dndx_df_setup_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(ctx->surf, begin, count, ctx->tb, dfl, (double *)pack, stride, (unsigned long long *)counters);
       IS3D_CUDA_TRY(ctx, cudaGetLastError());
-#define IS3D_DNDX_DF(M, B, R, O) dndx_df_kernel<M, B, R, O><<<grid, kDndxThreads, 0, ctx->stream>>>((double *)pack, stride, count, cpb, ctx->surf, begin, g)
-#define IS3D_DNDX_DF2(M, B) do { if (reg && outflow) IS3D_DNDX_DF(M, B, true, true); else if (reg) IS3D_DNDX_DF(M, B, true, false); else if (outflow) IS3D_DNDX_DF(M, B, false, true); else IS3D_DNDX_DF(M, B, false, false); } while (0)
-      if (p.df_mode == 1) { if (baryon) IS3D_DNDX_DF2(1, true); else IS3D_DNDX_DF2(1, false); }
-      else { if (baryon) IS3D_DNDX_DF2(2, true); else IS3D_DNDX_DF2(2, false); }
+      // charge-conjugate pairs first (longer blocks), then the single classes: disjoint class histograms
+#define IS3D_DNDX_DF(M, B, R, O, P, GRID, G) dndx_df_kernel<M, B, R, O, P><<<GRID, kDndxThreads, 0, ctx->stream>>>((double *)pack, stride, count, cpb, ctx->surf, begin, G)
+#define IS3D_DNDX_DF2(M, B, P, GRID, G) do { if (reg && outflow) IS3D_DNDX_DF(M, B, true, true, P, GRID, G); else if (reg) IS3D_DNDX_DF(M, B, true, false, P, GRID, G); else if (outflow) IS3D_DNDX_DF(M, B, false, true, P, GRID, G); else IS3D_DNDX_DF(M, B, false, false, P, GRID, G); } while (0)
+      if (p.df_mode == 1) {
+        if (baryon) { if (nslices_pair) IS3D_DNDX_DF2(1, true, true, grid_pair, gp); if (nslices) IS3D_DNDX_DF2(1, true, false, grid, g); }
+        else IS3D_DNDX_DF2(1, false, false, grid, g);
+      } else {
+        if (baryon) { if (nslices_pair) IS3D_DNDX_DF2(2, true, true, grid_pair, gp); if (nslices) IS3D_DNDX_DF2(2, true, false, grid, g); }
+        else IS3D_DNDX_DF2(2, false, false, grid, g);
+      }
 #undef IS3D_DNDX_DF2
 #undef IS3D_DNDX_DF
     } else {
       dndx_feqmod_setup_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(ctx->surf, begin, count, ctx->tb, ffl, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts, (double *)pack, stride, (unsigned long long *)counters);
       IS3D_CUDA_TRY(ctx, cudaGetLastError());
-#define IS3D_DNDX_FM(B, R, O, S) dndx_feqmod_kernel<B, R, O, S><<<grid, kDndxThreads, 0, ctx->stream>>>((double *)pack, stride, count, cpb, ctx->surf, begin, g, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts)
-#define IS3D_DNDX_FM2(B, S) do { if (reg && outflow) IS3D_DNDX_FM(B, true, true, S); else if (reg) IS3D_DNDX_FM(B, true, false, S); else if (outflow) IS3D_DNDX_FM(B, false, true, S); else IS3D_DNDX_FM(B, false, false, S); } while (0)
-      if (baryon) { if (species_renorm) IS3D_DNDX_FM2(true, true); else IS3D_DNDX_FM2(true, false); }
-      else { if (species_renorm) IS3D_DNDX_FM2(false, true); else IS3D_DNDX_FM2(false, false); }
+#define IS3D_DNDX_FM(B, R, O, S, P, GRID, G) dndx_feqmod_kernel<B, R, O, S, P><<<GRID, kDndxThreads, 0, ctx->stream>>>((double *)pack, stride, count, cpb, ctx->surf, begin, G, ctx->d_gla_root, ctx->d_gla_weight, ctx->gla_pts)
+#define IS3D_DNDX_FM2(B, S, P, GRID, G) do { if (reg && outflow) IS3D_DNDX_FM(B, true, true, S, P, GRID, G); else if (reg) IS3D_DNDX_FM(B, true, false, S, P, GRID, G); else if (outflow) IS3D_DNDX_FM(B, false, true, S, P, GRID, G); else IS3D_DNDX_FM(B, false, false, S, P, GRID, G); } while (0)
+      if (baryon) {
+        if (nslices_pair) { if (species_renorm) IS3D_DNDX_FM2(true, true, true, grid_pair, gp); else IS3D_DNDX_FM2(true, false, true, grid_pair, gp); }
+        if (nslices) { if (species_renorm) IS3D_DNDX_FM2(true, true, false, grid, g); else IS3D_DNDX_FM2(true, false, false, grid, g); }
+      } else {
+        if (species_renorm) IS3D_DNDX_FM2(false, true, false, grid, g); else IS3D_DNDX_FM2(false, false, false, grid, g);
+      }
 #undef IS3D_DNDX_FM2
 #undef IS3D_DNDX_FM
     }

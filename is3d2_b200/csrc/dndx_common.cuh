@@ -24,6 +24,7 @@ namespace is3d {
 constexpr int kDndxThreads = 256;     // threads per block
 constexpr int kDndxTile = 128;        // items (cell x quadrature point) per shared-memory tile
 constexpr int kDndxR = 4;             // species classes per thread
+constexpr int kDndxPairR = 2;         // charge-conjugate pair slots per thread of the pair launches (= 4 classes per thread)
 constexpr int kDndxMaxCells = 16;     // cells per tile
 constexpr int kDndxMaxGroups = 8;     // thread groups per block
 

@@ -272,7 +272,7 @@ bool slot_table_core(const std::vector<int> &rep, const double *baryon, bool bar
 void species_classes_core(int ns, const double *mass, const double *sign, const double *baryon, bool baryon_on,
                           std::vector<int> *class_of, std::vector<int> *rep);
 
-bool pair_tables_core(const std::vector<int> &rep, const double *mass, const double *sign, const double *baryon, int R,
+bool pair_tables_core(const std::vector<int> &rep, const double *mass, const double *sign, const double *baryon, int R, int R_pair,
                       std::vector<int> *singles, std::vector<int> *pairs)
 {
   const size_t nc = rep.size();
@@ -299,7 +299,7 @@ bool pair_tables_core(const std::vector<int> &rep, const double *mass, const dou
     if (b > (double)kMaxBaryon || b != (double)(int)b) return false;
     for (size_t c = 0; c < nc; c++)
       if (partner[c] >= 0 && baryon[rep[c]] == b) { pairs->push_back((int)c); pairs->push_back(partner[c]); }
-    while ((pairs->size() / 2) % (size_t)R) { pairs->push_back(-1); pairs->push_back(-1); }
+    while ((pairs->size() / 2) % (size_t)R_pair) { pairs->push_back(-1); pairs->push_back(-1); }
   }
   // singles: the ordinary slot table over the classes without a partner
   std::vector<double> sb;
@@ -424,7 +424,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   if (p.include_baryon) {
     std::vector<int> class_of, rep;
     species_classes(ctx, &class_of, &rep);
-    ok = pair_tables_core(rep, ctx->h_mass.data(), ctx->h_sign.data(), ctx->h_baryon.data(), kDfBinsPerThread, &slots, &pair_slots);
+    ok = pair_tables_core(rep, ctx->h_mass.data(), ctx->h_sign.data(), ctx->h_baryon.data(), kDfBinsPerThread, kDfBinsPerThread, &slots, &pair_slots);
   } else {
     ok = build_slot_table(ctx, kDfBinsPerThread, &slots);
   }
@@ -477,17 +477,28 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch), grid_pair(nslices_pair, ctx->Ny * ctx->Nphi, nch);
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0;
-    // the pair launch first: its blocks are the longer ones, the single blocks fill the tail of its last wave
+    // the pair launch first (its blocks are the longer ones); the single-class launch runs beside it on a second stream and
+    // fills the tail of its last wave (disjoint bins of `partial`)
+    const bool two = p.include_baryon && nslices_pair && nslices;
+    cudaStream_t s_single = two ? ctx->side_stream : ctx->stream;
+    if (two) {
+      IS3D_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+      IS3D_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    }
     if (p.df_mode == 1) {
       if (p.include_baryon && nslices_pair) dispatch_df2<1, true, true>(reg, outflow, grid_pair, ctx->stream, (double *)pack, stride, count, cpc, gp, (double *)partial, total_class);
-      if (p.include_baryon && nslices) dispatch_df2<1, true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
+      if (p.include_baryon && nslices) dispatch_df2<1, true, false>(reg, outflow, grid, s_single, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
       if (!p.include_baryon) dispatch_df2<1, false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
     } else {
       if (p.include_baryon && nslices_pair) dispatch_df2<2, true, true>(reg, outflow, grid_pair, ctx->stream, (double *)pack, stride, count, cpc, gp, (double *)partial, total_class);
-      if (p.include_baryon && nslices) dispatch_df2<2, true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
+      if (p.include_baryon && nslices) dispatch_df2<2, true, false>(reg, outflow, grid, s_single, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
       if (!p.include_baryon) dispatch_df2<2, false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, g, (double *)partial, total_class);
     }
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
+    if (two) {
+      IS3D_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+      IS3D_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
     IS3D_CUDA_TRY(ctx, cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -528,7 +539,7 @@ extern "C" int is3d_species_pairs(int ns, const double *mass, const double *sign
   if (ns <= 0 || !mass || !sign || !baryon || slots_per_group <= 0 || !single_slots || !pair_slots || !n_single || !n_pair) return -1;
   std::vector<int> cls, rep, singles, pairs;
   is3d::species_classes_core(ns, mass, sign, baryon, true, &cls, &rep);
-  if (!is3d::pair_tables_core(rep, mass, sign, baryon, slots_per_group, &singles, &pairs)) return -3;
+  if (!is3d::pair_tables_core(rep, mass, sign, baryon, slots_per_group, slots_per_group, &singles, &pairs)) return -3;
   if ((int)singles.size() > single_capacity || (int)pairs.size() > pair_capacity) return -2;
   for (size_t k = 0; k < singles.size(); k++) single_slots[k] = singles[k];
   for (size_t k = 0; k < pairs.size(); k++) pair_slots[k] = pairs[k];

@@ -21,7 +21,7 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, int n
                                        double *__restrict__ out);
 is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out);
 bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots);
-bool pair_tables_core(const std::vector<int> &rep, const double *mass, const double *sign, const double *baryon, int R,
+bool pair_tables_core(const std::vector<int> &rep, const double *mass, const double *sign, const double *baryon, int R, int R_pair,
                       std::vector<int> *singles, std::vector<int> *pairs);
 void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
                    int64_t *cells_per_chunk);
@@ -327,7 +327,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   if (p.include_baryon) {
     std::vector<int> class_of, rep;
     species_classes(ctx, &class_of, &rep);
-    ok = pair_tables_core(rep, ctx->h_mass.data(), ctx->h_sign.data(), ctx->h_baryon.data(), kBins, &slots, &pair_slots);
+    ok = pair_tables_core(rep, ctx->h_mass.data(), ctx->h_sign.data(), ctx->h_baryon.data(), kBins, kBins, &slots, &pair_slots);
   } else {
     ok = build_slot_table(ctx, kBins, &slots);
   }
@@ -414,16 +414,27 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
     dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch), grid_pair(nslices_pair, ctx->Ny * ctx->Nphi, nch);
     const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0;
     if (p.include_baryon) {
-      // the pair launch first: its blocks are the longer ones
+      // the pair launch first (its blocks are the longer ones); the single-class launches run beside it on a second stream
+      const bool two = nslices_pair && nslices;
+      cudaStream_t s_single = two ? ctx->side_stream : ctx->stream;
+      if (two) {
+        IS3D_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        IS3D_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+      }
       if (nslices_pair) {
         if (species_renorm) launch_feqmod<true, true, true>(reg, outflow, grid_pair, ctx->stream, (double *)pack, stride, count, cpc, renorm_pair, (const int *)tile_linear, gp, (double *)partial, total_class);
         else launch_feqmod<true, false, true>(reg, outflow, grid_pair, ctx->stream, (double *)pack, stride, count, cpc, renorm_pair, (const int *)tile_linear, gp, (double *)partial, total_class);
         launches += 2;
       }
       if (nslices) {
-        if (species_renorm) launch_feqmod<true, true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
-        else launch_feqmod<true, false, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
+        if (species_renorm) launch_feqmod<true, true, false>(reg, outflow, grid, s_single, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
+        else launch_feqmod<true, false, false>(reg, outflow, grid, s_single, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);
         launches += 2;
+      }
+      if (two) {
+        IS3D_CUDA_TRY(ctx, cudaGetLastError());
+        IS3D_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        IS3D_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
       }
     } else {
       if (species_renorm) launch_feqmod<false, true, false>(reg, outflow, grid, ctx->stream, (double *)pack, stride, count, cpc, (double *)renorm, (const int *)tile_linear, g, (double *)partial, total_class);

@@ -16,8 +16,9 @@ cat $O/r2_final_numbers.txt
 # launch list of the default bench command (cold-cache, serialised per-launch times: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r2_launches_bench_default.csv python bench.py --no-cpu-baseline > /dev/null 2>&1
 python tools/launch_shares.py $O/r2_launches_bench_default.csv | head -12
-# one full capture of the dominant kernel: the first 4 194 304-cell launch of the 10 M-cell step (after 3 warm-up steps = 9 launches)
-ncu --set full --clock-control none --import-source on -f -k regex:df_spectra_kernel -s 9 -c 1 -o $O/r2_prof_k1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sampler --check-cells 0 > /dev/null 2>&1
+# one full capture of the dominant kernels: the pair launch and the single-class launch of the first 4 194 304-cell pass of the
+# timed 10 M-cell step (3 warm-up steps x 3 passes x 2 launches = 18 launches skipped)
+ncu --set full --clock-control none --import-source on -f -k regex:df_spectra_kernel -s 18 -c 2 -o $O/r2_prof_k1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sampler --check-cells 0 > /dev/null 2>&1
 python tools/ncu_summary.py $O/r2_prof_k1.ncu-rep > $O/r2_ncu_k1_summary.txt; cat $O/r2_ncu_k1_summary.txt
 python tools/make_ncu_headline.py $O/r2_prof_k1.ncu-rep 4194304 > /dev/null && cp profiles/ncu_k1_headline.json $O/
 ncu -i $O/r2_prof_k1.ncu-rep --page source --csv > $O/r2_k1_source.csv 2>/dev/null; wc -l $O/r2_k1_source.csv
