@@ -85,3 +85,33 @@ def test_dndx_sweep_matches_oracle(libs, tmp_path, name, p, n, smash, seed):
     for k in ("tau", "r", "phi"):
         assert got[k].shape == (ns, want[k].shape[1])
         harness.assert_hist_close(got[k], want[k], what=f"{name}/{k}")
+
+
+@pytest.mark.parametrize("df_mode,operation", [(2, 1), (3, 1), (1, 0)])
+def test_urqmd_list_with_baryon_terms_matches_oracle(libs, tmp_path, df_mode, operation):
+    """All 305 UrQMD species with baryon terms: another particle list for the class / charge-conjugate pair layout (its baryon
+    and antibaryon multiplets pair up differently from SMASH's), spectra and dN/dX against the CPU oracle."""
+    import ctypes as C
+    from is3d2_b200 import Stats
+    p = dict(df_mode=df_mode, dimension=3, include_baryon=1, include_baryondiff_deltaf=1, hrg_eos=1, operation=operation)
+    params = cases._p(**p)
+    case = dict(params=params, chosen="urqmd_v3.3+")
+    surf = synthetic.roundtrip_mode1(synthetic.s3d(7, seed=4242 + df_mode, baryon=True, stress=0.3 if df_mode == 3 else 0.0), baryon=True)
+    root = workdir.make_workdir(str(tmp_path / "oracle"), params, chosen=case["chosen"])
+    prob = oracle_api.OracleProblem(root, params, surf)
+    with harness.open_session(str(tmp_path / "gpu"), case, surf) as h:
+        if operation == 1:
+            got, st = h.abi_spectra()
+            rc, want, _ = prob.spectra()
+            assert rc == 0 and got.shape[0] == 305
+            worst = harness.assert_spectra_close(got, want, what=f"urqmd df_mode {df_mode}")
+            assert st.pair_evals_executed > 0 or df_mode > 2          # K1 reports its pair slots
+        else:
+            rc, want, _ = prob.dndx()
+            assert rc == 0
+            got = {k: np.zeros_like(v) for k, v in want.items()}
+            stt = Stats()
+            h._check(h.lib.is3d_dndx(h.ctx, got["tau"].ctypes.data_as(C.c_void_p), got["r"].ctypes.data_as(C.c_void_p),
+                                     got["phi"].ctypes.data_as(C.c_void_p), C.byref(stt)), "is3d_dndx")
+            for k in ("tau", "r", "phi"):
+                harness.assert_hist_close(got[k], want[k], what=f"urqmd dN/dX {k}")
