@@ -39,6 +39,10 @@ constexpr int kItemUnroll = IS3D_K1_ITEM_UNROLL;   // items per trip of the mome
 constexpr int kThreads = IS3D_K1_THREADS;
 constexpr int kTile = kThreads;  // cells per shared-memory tile = threads per block
 constexpr int kDfBinsPerThread = IS3D_K1_R;   // species per thread (R)
+#ifndef IS3D_K1_PAIR_R
+#define IS3D_K1_PAIR_R IS3D_K1_R
+#endif
+constexpr int kDfPairsPerThread = IS3D_K1_PAIR_R;   // charge-conjugate pair slots per thread of the pair launch
 
 __global__ void df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, DfTables tb, DfFlags fl,
                                 double *__restrict__ pack, int64_t stride, unsigned long long *counters)
@@ -201,7 +205,7 @@ template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, bool PAIR>
 void launch_df(dim3 grid, cudaStream_t st, const double *pack, int64_t stride, int64_t n, int64_t cpc, const DfGrid &g,
                double *partial, int64_t total)
 {
-  df_spectra_kernel<MODE, BARYON, REGULATE, OUTFLOW, kDfBinsPerThread, PAIR><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, g, partial, total);
+  df_spectra_kernel<MODE, BARYON, REGULATE, OUTFLOW, (PAIR ? kDfPairsPerThread : kDfBinsPerThread), PAIR><<<grid, kThreads, 0, st>>>(pack, stride, n, cpc, g, partial, total);
 }
 
 template <int MODE, bool BARYON, bool PAIR>
@@ -424,7 +428,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   if (p.include_baryon) {
     std::vector<int> class_of, rep;
     species_classes(ctx, &class_of, &rep);
-    ok = pair_tables_core(rep, ctx->h_mass.data(), ctx->h_sign.data(), ctx->h_baryon.data(), kDfBinsPerThread, kDfBinsPerThread, &slots, &pair_slots);
+    ok = pair_tables_core(rep, ctx->h_mass.data(), ctx->h_sign.data(), ctx->h_baryon.data(), kDfBinsPerThread, kDfPairsPerThread, &slots, &pair_slots);
   } else {
     ok = build_slot_table(ctx, kDfBinsPerThread, &slots);
   }
@@ -446,7 +450,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw; g.exptab = ctx->d_exptab;
   DfGrid gp = g;                                                 // the pair launch: two class ids per slot
   gp.slot_class = (const int *)d_slots + slots.size();
-  gp.ncols = ctx->NpT * (int)(pair_slots.size() / (2 * kDfBinsPerThread));
+  gp.ncols = ctx->NpT * (int)(pair_slots.size() / (2 * kDfPairsPerThread));
   const int nslices = (g.ncols + kThreads - 1) / kThreads, nslices_pair = (gp.ncols + kThreads - 1) / kThreads;
   // a pair block does about 1.6x the work of a single block; the wave policy counts blocks
   const int64_t blocks_per_chunk = (int64_t)(nslices + nslices_pair) * ctx->Ny * ctx->Nphi;
@@ -520,9 +524,9 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     stats->kernel_ms = ms_total;
     stats->kernel_launches = launches;
     // every valid cell is one item per (y, phi, eta) block row, evaluated by all nslices x kThreads thread columns x R slots
-    const int64_t per_slice = (n - (int64_t)h_counters[0] - (int64_t)h_counters[1]) * (int64_t)kThreads * kDfBinsPerThread * ctx->Ny * ctx->Nphi * ctx->Neta;
-    stats->pair_evals_executed = 2 * per_slice * nslices_pair;
-    stats->evals_executed = per_slice * nslices + stats->pair_evals_executed;
+    const int64_t per_column = (n - (int64_t)h_counters[0] - (int64_t)h_counters[1]) * (int64_t)kThreads * ctx->Ny * ctx->Nphi * ctx->Neta;
+    stats->pair_evals_executed = 2 * per_column * kDfPairsPerThread * nslices_pair;
+    stats->evals_executed = per_column * kDfBinsPerThread * nslices + stats->pair_evals_executed;
   }
   if (h_counters[1] != 0) {
     ctx->set_error(std::to_string(h_counters[1]) + " cell(s) outside the df coefficient tables (the reference aborts here)");

@@ -351,7 +351,7 @@ template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
 IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, double xE, double e)
 {
   const double q = BARYON ? fma(e, s.eb, sign) : e + sign;         // e^x + sign, x = xE - b alpha_B
-  const double quad = fma(mT2, it.q1, fma(mT, s.A, s.B));
+  const double quad = fma(mT2, it.q1, fma(mT, s.A, s.B));      // Horner form without mT^2: same speed (profiles/r02_k1_variants_horner_pairR.txt)
   if (MODE == 2 && !REGULATE) {
     // folded form: (it.q1, s.A, s.B) hold quad' = quad + lin xE (df_make_item_u / df_share_u with FOLD = true)
     const double y = fast_rcp(q * xE);

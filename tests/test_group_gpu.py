@@ -172,3 +172,35 @@ def test_comm_attach_two_ranks_in_one_process(libs, tmp_path, monkeypatch):
     assert not errors, errors
     np.testing.assert_array_equal(results[0], results[1])            # every rank holds the same sum
     harness.assert_spectra_close(results[0], ref, what="2 ranks, product all-reduce, vs reference")
+
+
+@need2
+def test_sampler_self_test_histograms_sharded_over_two_gpus(libs, tmp_path, monkeypatch):
+    """test_sampler = 1 through the host layer: the self-test histogram files of a 2-GPU run (per-device counters summed by
+    is3d_group_sample_histograms) are the files of the 1-GPU run -- the same hadrons are sampled, counts are integers."""
+    import os
+    name = "smp_s3d_m3"
+    case = cases.SAMPLER_CASES[name]
+    surf, _ = harness.load_golden_sampler(name)
+    ov = dict(test_sampler=1, min_num_hadrons=60000.0, max_num_samples=3000.0)
+
+    def run(root):
+        with harness.open_session(root, case, surf, overrides=ov) as h:
+            h.run()
+        out = {}
+        base = os.path.join(root, "results", "sampled")
+        for sub in sorted(os.listdir(base)):
+            for f in sorted(os.listdir(os.path.join(base, sub))):
+                out[sub + "/" + f] = open(os.path.join(base, sub, f)).read()
+        return out
+    one = run(str(tmp_path / "one"))
+    monkeypatch.setenv("IS3D_DEVICES", "0,1")
+    two = run(str(tmp_path / "two"))
+    assert len(one) > 10 and sorted(one) == sorted(two)
+    differ = [k for k in one if one[k] != two[k]]
+    # the flow-coefficient files hold sums of cos / sin in FP64 (order of the atomic adds): compare those numerically
+    for k in differ:
+        assert k.startswith("vn/"), k
+        a = np.array([[float(v) for v in l.split()] for l in one[k].splitlines() if l.strip() and l[0] != "#"])
+        b = np.array([[float(v) for v in l.split()] for l in two[k].splitlines() if l.strip() and l[0] != "#"])
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
