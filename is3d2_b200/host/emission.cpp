@@ -65,12 +65,17 @@ is3d_params EmissionFunctionArray::params_from(ParameterReader *paraRdr, int *po
 }
 
 // one CUDA context per GPU of the run: IS3D_DEVICES = "all" | "0-7" | "0,2,3" (default: the single device IS3D_DEVICE, else 0)
-is3d_group *EmissionFunctionArray::create_group(const is3d_params &prm)
+is3d_group *EmissionFunctionArray::create_group(const is3d_params &prm, std::string *error)
 {
   std::vector<int> devices = parse_device_list(getenv("IS3D_DEVICES"), prm.device);
   is3d_group *g = nullptr;
   is3d_status st = is3d_group_create(&prm, (int)devices.size(), devices.data(), &g);
-  if (st != IS3D_OK) fatal(std::string("is3d_create error: ") + is3d_group_last_error(nullptr));
+  if (st != IS3D_OK) {
+    const std::string msg = std::string("is3d_create error: ") + is3d_group_last_error(nullptr);
+    if (!error) fatal(msg);
+    *error = msg;
+    return nullptr;
+  }
   return g;
 }
 

@@ -26,10 +26,11 @@ struct Session {
   std::thread early;
   is3d_group *early_group = nullptr;
   is3d_params early_params{};
+  std::string early_error;                  // reported where the contexts are needed, in the order the reference reports errors
   void start_contexts()
   {
     early_params = EmissionFunctionArray::params_from(&paraRdr);
-    early = std::thread([this] { early_group = EmissionFunctionArray::create_group(early_params); });
+    early = std::thread([this] { early_group = EmissionFunctionArray::create_group(early_params, &early_error); });
   }
   ~Session() { if (early.joinable()) early.join(); if (early_group && !efa) is3d_group_destroy(early_group); }
 
@@ -87,6 +88,7 @@ struct Session {
   {
     if (!tables_ready) prepare_tables();
     if (early.joinable()) early.join();
+    if (!early_error.empty()) fatal(early_error);
     efa.reset(new EmissionFunctionArray(&paraRdr, chosen_particles.get(), pT_tab.get(), phi_tab.get(), y_tab.get(),
                                         eta_tab.get(), &particle_data, have_surface ? &surf : nullptr, df_data.get(),
                                         early_group, early_group ? &early_params : nullptr));

@@ -169,7 +169,8 @@ class EmissionFunctionArray {
                         const is3d_params *ready_params = nullptr);
   // the run-time switches of iS3D_parameters.dat (+ the IS3D_* environment knobs) as the C ABI takes them
   static is3d_params params_from(ParameterReader *paraRdr, int *polzn_file_compat = nullptr);
-  static is3d_group *create_group(const is3d_params &prm);      // IS3D_DEVICES / IS3D_DEVICE -> contexts (+ communicator)
+  // IS3D_DEVICES / IS3D_DEVICE -> contexts (+ communicator); a failure is fatal unless `error` is given (then NULL + message)
+  static is3d_group *create_group(const is3d_params &prm, std::string *error = nullptr);
   ~EmissionFunctionArray();
 
   void calculate_spectra(std::vector<std::vector<Sampled_Particle>> &particle_event_list_in);
