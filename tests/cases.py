@@ -97,6 +97,15 @@ def make_surface(spec):
 BIG_SPECTRA_CASES = {
     "bench_m2_smash_baryon_2304cells": dict(surface=("bench", dict(begin=0, end=2304)),
                                             params=_p(df_mode=2, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
+    # the same for the modified-equilibrium kernels (K2): PTM with bulk, per-(cell, class) renormalisation, charge-conjugate pairs
+    "bench_m3_smash_baryon_1024cells": dict(surface=("bench", dict(begin=0, end=1024)),
+                                            params=_p(df_mode=3, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
+}
+
+# dN/dX at a size with several cell chunks per block column (GPU test only; ~1 min of serial reference)
+BIG_DNDX_CASES = {
+    "dndx_bench_m2_smash_baryon_512cells": dict(surface=("bench", dict(begin=0, end=512)),
+                                                params=_p(operation=0, df_mode=2, include_baryon=1, include_baryondiff_deltaf=1), chosen="smash"),
 }
 
 # executable-level golden (tests/golden/make_golden_exe_tree.py): BASELINE.json config 5 in miniature -- MUSIC-format

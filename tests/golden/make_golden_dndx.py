@@ -19,7 +19,9 @@ from is3d2_b200 import synthetic  # noqa: E402
 
 def main():
     only = set(sys.argv[1:])
-    for name, case in cases.DNDX_CASES.items():
+    todo = dict(cases.DNDX_CASES)
+    todo.update({n: c for n, c in cases.BIG_DNDX_CASES.items() if n in only})      # the large case only when named
+    for name, case in todo.items():
         if only and name not in only:
             continue
         surf = cases.make_surface(case["surface"])

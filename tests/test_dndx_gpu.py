@@ -21,9 +21,9 @@ def _device_hists(h, ns, params):
     return {"tau": tau, "r": r, "phi": phi}, st
 
 
-@pytest.mark.parametrize("name", list(cases.DNDX_CASES))
+@pytest.mark.parametrize("name", list(cases.DNDX_CASES) + list(cases.BIG_DNDX_CASES))
 def test_dndx_matches_reference(libs, tmp_path, name):
-    case = cases.DNDX_CASES[name]
+    case = cases.DNDX_CASES.get(name) or cases.BIG_DNDX_CASES[name]
     surf, ref = harness.load_golden_dndx(name)
     ns = ref["tau"].shape[0]
     with harness.open_session(str(tmp_path), case, surf) as h:
