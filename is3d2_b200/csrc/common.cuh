@@ -89,9 +89,15 @@ IS3D_HD double clamp_hi_word_680(double x)
 static __constant__ double c_exp_consts[3] = {1477.3197218702985, -6.769015435155716e-04, 1.6666666666666666e-01};
 #endif
 
-// CLAMP = false: the caller has already passed x through clamp_hi_word_680 (and keeps using the clamped value)
+// CLAMP = false: the caller has already passed x through clamp_hi_word_680 (and keeps using the clamped value), or knows
+// x <= 680 some other way (the spectra kernels' per-tile range flag)
+//
+// The table is stored PRE-COMPENSATED for the exponent patch: entry m holds the bits of 2^(m/1024) with (m << 10) subtracted
+// from the high word, so that ONE integer multiply-add  hi = k * 1024 + hi'  restores the mantissa and adds (k >> 10) to the
+// exponent field in the same instruction (k * 1024 = (k >> 10) << 20 + (k & 1023) << 10; the arithmetic is modulo 2^32).
+// The first version patched the exponent of the RESULT with shift + multiply-add.
 template <bool CLAMP = true>
-IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
+IS3D_HD double fast_exp_k(double x, const double *__restrict__ tab, int &spare)
 {
 #if defined(__CUDA_ARCH__)
   const double kInv = c_exp_consts[0], kStep = c_exp_consts[1], kSixth = c_exp_consts[2];
@@ -110,32 +116,39 @@ IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
 #if defined(__CUDA_ARCH__) && !defined(IS3D_EXP_TABLE_GENERIC)
   // the table lives in shared memory (load_exp_table): mask, then ONE multiply-add forms the 32-bit shared address
   // (nvcc's own sequence for tab[k & 1023] is shift + mask + add)
-  double T;
+  double Tc;
   {
     const unsigned base = (unsigned)__cvta_generic_to_shared(tab);
     unsigned addr;
     asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"((unsigned)k & (unsigned)(kExpTableSize - 1)), "r"(base));
-    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(addr));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(Tc) : "r"(addr));
+    spare = (int)addr;
   }
 #else
-  const double T = tab[k & (kExpTableSize - 1)];
+  const double Tc = tab[k & (kExpTableSize - 1)];
+  spare = 0;
 #endif
-  const double v = fma(T, q, T);
 #if defined(__CUDA_ARCH__)
-  // the shift is hidden from the optimiser: it would otherwise rewrite (k >> 10) << 20 as (k << 10) & 0xfff00000 and need
-  // shift + mask + add; an opaque shift + ONE multiply-add on the high word is an instruction shorter
-  int e;
-  asm("shr.s32 %0, %1, %2;" : "=r"(e) : "r"(k), "n"(kExpTableBits));
-  return scale_by_pow2(v, e);
+  const double T = __hiloint2double(k * (1 << kExpTableBits) + __double2hiint(Tc), __double2loint(Tc));     // one IMAD
 #else
-  return scale_by_pow2(v, k >> kExpTableBits);
+  const double T = as_double(as_int64(Tc) + (int64_t)((uint64_t)(int64_t)k << (32 + kExpTableBits)));
 #endif
+  return fma(T, q, T);
+}
+template <bool CLAMP = true>
+IS3D_HD double fast_exp(double x, const double *__restrict__ tab)
+{
+  int spare;
+  return fast_exp_k<CLAMP>(x, tab, spare);
 }
 
-// host-side construction of the table (uploaded once per context)
+// host-side construction of the (pre-compensated, see fast_exp) table, uploaded once per context
 inline void fill_exp_table(double *tab)
 {
-  for (int m = 0; m < kExpTableSize; m++) tab[m] = (double)exp2l((long double)m / (long double)kExpTableSize);
+  for (int m = 0; m < kExpTableSize; m++) {
+    const double v = (double)exp2l((long double)m / (long double)kExpTableSize);
+    tab[m] = as_double(as_int64(v) - ((int64_t)m << (32 + kExpTableBits)));
+  }
 }
 
 #if defined(__CUDACC__)
@@ -148,19 +161,25 @@ __device__ __forceinline__ void load_exp_table(double *smem_tab, const double *_
 
 // 1/d for d in the normal range (here d = e^x +- 1 >= ~0.1, or d = E/T): hardware seed + one cubically convergent
 // step in the FMA pipe, no division slow path.  The seed (MUFU.RCP64H) sees only the upper 32 bits of d, i.e. it
-// carries ~20 bits: e = 1 - d y0 <= 2^-19, y = y0 (1 + e + e^2) leaves e^3 <= 2^-57.
-IS3D_HD double fast_rcp(double d)
+// carries ~20 bits: e = 1 - d y0 <= 1.5 * 2^-19, y = y0 (1 + e + e^2) leaves e^3 <= 2^-55.
+// lo_any: any 32-bit value the caller has at hand (fast_exp_k's spare word): only the high word of the seed carries
+// information, and taking its low word from a register that is already live saves the register clear (one IMAD.MOV per
+// reciprocal in the inner loops) that the architectural "low word = 0" costs; the seed moves by < 2^-20.
+IS3D_HD double fast_rcp(double d, int lo_any)
 {
 #if defined(__CUDA_ARCH__)
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+  double y = __hiloint2double(__double2hiint(y0), lo_any);
   double e = fma(-d, y, 1.0);
   e = fma(e, e, e);
   y = fma(y, e, y);
   return y;
 #else
+  (void)lo_any;
   return 1.0 / d;
 #endif
 }
+IS3D_HD double fast_rcp(double d) { return fast_rcp(d, 0); }
 
 }  // namespace is3d

@@ -66,7 +66,35 @@ struct DfGrid {
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
   const double *exptab;                               // 2^(m/1024), global memory (ctx->d_exptab)
+  double mT_max, pT_max;                              // largest entries of mT[] and pT[]: range test of the exp argument
 };
+
+// The momentum loop over the items of one tile.  CLAMP = false: no item of the tile can reach the exp range guard.
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, int R, bool PAIR, bool CLAMP>
+__device__ __forceinline__ void df_item_loop(const DfItemU *__restrict__ items, int n_items, const DfThreadU &th, const DfThreadU &thm,
+                                             const double (&mT)[R], const double (&mT2)[R], const double (&sgn)[R],
+                                             double (&acc)[R], double (&accm)[PAIR ? R : 1], const double *__restrict__ exptab)
+{
+#pragma unroll kItemUnroll
+  for (int k = 0; k < n_items; k++) {
+    const DfItemU &it = items[k];          // shared memory: fields arrive as broadcast LDS.128, eb[eslot] as one LDS.64
+    const DfSharedU sh = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, th);
+    if (!PAIR) {
+#pragma unroll
+      for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW, CLAMP>(it, sh, mT[r], mT2[r], sgn[r], exptab);
+    } else {
+      const DfSharedU shm = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, thm);   // common sub-expressions are shared by the compiler
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const double xE = df_eval_u_x<CLAMP>(it, sh, mT[r]);
+        int spare;
+        const double e = fast_exp_k<false>(xE, exptab, spare);
+        acc[r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], xE, e, spare);
+        accm[r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, shm, mT[r], mT2[r], sgn[r], xE, e, spare);
+      }
+    }
+  }
+}
 
 // PAIR = true: a slot is a charge-conjugate PAIR of classes (baryon class, its antibaryon class: same mass, same statistics,
 // b and -b).  x_E = u.p/T and exp(x_E) do not depend on b, so one exponential (7 of the ~21 FP64 instructions and 6 of the 8
@@ -138,6 +166,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         if (w < warp) base += c;
         n_items += c;
       }
+      int hot = 0;
       if (valid) {
         double eta, w;
         if (g.dimension == 3) { eta = pack[DP_ETA * stride + cell]; w = 1.0; }
@@ -145,27 +174,14 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         double sh = sinh(yval - eta);
         double ch = sqrt(1.0 + sh * sh);     // the reference's cosh (MomentumSpectra.cpp:307-308)
         auto pk = [&](int k) { return pack[k * stride + cell]; };
-        items[base + __popc(ballot & ((1u << lane) - 1u))] = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sh, ch, cphi, sphi, w);
+        const DfItemU item = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sh, ch, cphi, sphi, w);
+        hot = df_item_needs_clamp(item.aT, item.bT, g.mT_max, g.pT_max);
+        items[base + __popc(ballot & ((1u << lane) - 1u))] = item;
       }
-      __syncthreads();
-#pragma unroll kItemUnroll
-      for (int k = 0; k < n_items; k++) {
-        const DfItemU &it = items[k];          // shared memory: fields arrive as broadcast LDS.128, eb[eslot] as one LDS.64
-        const DfSharedU sh = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, th);
-        if (!PAIR) {
-#pragma unroll
-          for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], exptab);
-        } else {
-          const DfSharedU shm = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, thm);   // common sub-expressions are shared by the compiler
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            const double xE = df_eval_u_x(it, sh, mT[r]);
-            const double e = fast_exp<false>(xE, exptab);
-            acc[r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], xE, e);
-            accm[r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, shm, mT[r], mT2[r], sgn[r], xE, e);
-          }
-        }
-      }
+      // one barrier publishes the items and tells the block whether any of them can reach the exp range guard (cold cells,
+      // T < mT_max / 600): the common loop carries no clamp (one integer min per evaluation less)
+      if (__syncthreads_or(hot)) df_item_loop<MODE, BARYON, REGULATE, OUTFLOW, R, PAIR, true>(items, n_items, th, thm, mT, mT2, sgn, acc, accm, exptab);
+      else df_item_loop<MODE, BARYON, REGULATE, OUTFLOW, R, PAIR, false>(items, n_items, th, thm, mT, mT2, sgn, acc, accm, exptab);
     }
   }
 
@@ -448,6 +464,12 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   const int64_t total_class = (int64_t)sb.nclass * per_species;
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
   g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw; g.exptab = ctx->d_exptab;
+  {
+    double m_max = 0.0, pT_max = 0.0;
+    for (int s = 0; s < ctx->ns; s++) m_max = fmax(m_max, fabs(ctx->h_mass[s]));
+    for (double v : ctx->pT) pT_max = fmax(pT_max, fabs(v));
+    g.pT_max = pT_max; g.mT_max = sqrt(m_max * m_max + pT_max * pT_max);
+  }
   DfGrid gp = g;                                                 // the pair launch: two class ids per slot
   gp.slot_class = (const int *)d_slots + slots.size();
   gp.ncols = ctx->NpT * (int)(pair_slots.size() / (2 * kDfPairsPerThread));

@@ -331,30 +331,44 @@ IS3D_HD DfSharedU df_share_u(const DfItemU &it, const DfThreadU &th)
 // A baryon class and its antibaryon class (same mass, same statistics, b -> -b) therefore share xE and the exponential:
 // the pair path of df_spectra_kernel evaluates both tails from one exp (charge-conjugate pairs, spectra_df.cu).
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
-IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, double xE, double e);
+IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, double xE, double e,
+                              int spare = 0);
 
+// CLAMP = false: the caller knows that no xE of this item can reach 680 (df_item_needs_clamp)
+template <bool CLAMP = true>
 IS3D_HD double df_eval_u_x(const DfItemU &it, const DfSharedU &s, double mT)
 {
   // clamped in place (x <= 680, common.cuh): beyond that feq < 1e-295 and every later use of xE multiplies feq
-  return clamp_hi_word_680(fma(mT, it.aT, -s.pb));
+  const double xE = fma(mT, it.aT, -s.pb);
+  return CLAMP ? clamp_hi_word_680(xE) : xE;
 }
 
-template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+// true when some (class, pT) bin of the launch could see xE = mT aT - pT bT above 600 for this item (mT_max, pT_max: the
+// largest table entries; aT > 0 for a time-like flow velocity).  NaN coefficients also say true.
+IS3D_HD bool df_item_needs_clamp(double aT, double bT, double mT_max, double pT_max)
+{
+  return !(fma(mT_max, aT, pT_max * fabs(bT)) < 600.0);
+}
+
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, bool CLAMP = true>
 IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign,
                          const double *__restrict__ exptab)
 {
-  const double xE = df_eval_u_x(it, s, mT);
-  return df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, s, mT, mT2, sign, xE, fast_exp<false>(xE, exptab));
+  const double xE = df_eval_u_x<CLAMP>(it, s, mT);
+  int spare;
+  const double e = fast_exp_k<false>(xE, exptab, spare);
+  return df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, s, mT, mT2, sign, xE, e, spare);
 }
 
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
-IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, double xE, double e)
+IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, double xE, double e,
+                              int spare)
 {
   const double q = BARYON ? fma(e, s.eb, sign) : e + sign;         // e^x + sign, x = xE - b alpha_B
   const double quad = fma(mT2, it.q1, fma(mT, s.A, s.B));      // Horner form without mT^2: same speed (profiles/r02_k1_variants_horner_pairR.txt)
   if (MODE == 2 && !REGULATE) {
     // folded form: (it.q1, s.A, s.B) hold quad' = quad + lin xE (df_make_item_u / df_share_u with FOLD = true)
-    const double y = fast_rcp(q * xE);
+    const double y = fast_rcp(q * xE, spare);
     const double feq = y * xE;
     const double feqbar = fma(-sign, feq, 1.0);
     const double pds = fma(mT, it.c1, s.pd);
@@ -364,12 +378,12 @@ IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, 
   }
   double feq, dfv;
   if (MODE == 1) {
-    feq = fast_rcp(q);
+    feq = fast_rcp(q, spare);
     dfv = quad;
   } else {
     // one reciprocal serves 1/(e^x + sign) and 1/xE (e^x <= 2.1e295 by fast_exp's clamp and exp(|b| alpha_B) < 1e4, so
     // the product stays finite for any xE a surface can produce)
-    const double y = fast_rcp(q * xE);
+    const double y = fast_rcp(q * xE, spare);
     feq = y * xE;
     const double r = y * q;
     dfv = fma(quad, r, BARYON ? fma(mT, it.L1, s.C) : it.L1 * xE);
