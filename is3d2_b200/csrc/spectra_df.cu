@@ -14,6 +14,8 @@
 //      with broadcast LDS.128 and updating its R register accumulators.
 //      FP64-pipe bound: HBM traffic is 256 B per cell per block against >= 1024 * ~27 DFMA per cell per block.
 //   3. reduce_partials_kernel: deterministic sum over the cell chunks.
+#include <algorithm>
+
 #include "ctx.h"
 #include "spectra_df.cuh"
 
@@ -43,6 +45,9 @@ constexpr int kDfBinsPerThread = IS3D_K1_R;   // species per thread (R)
 #define IS3D_K1_PAIR_R IS3D_K1_R
 #endif
 constexpr int kDfPairsPerThread = IS3D_K1_PAIR_R;   // charge-conjugate pair slots per thread of the pair launch
+// range classes of an item's xE = u.p/T over the columns of a block (df_spectra_kernel)
+constexpr double kXeNegligible = 680.0;             // = fast_exp's range guard: feq < 1e-295 beyond, the reference's exp overflows at 709.8
+constexpr double kXeCold = 600.0;                   // below: no range guard needed
 
 __global__ void df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, DfTables tb, DfFlags fl,
                                 double *__restrict__ pack, int64_t stride, unsigned long long *counters)
@@ -66,7 +71,9 @@ struct DfGrid {
   int Ny, Nphi, Neta, dimension;
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
   const double *exptab;                               // 2^(m/1024), global memory (ctx->d_exptab)
-  double mT_max, pT_max;                              // largest entries of mT[] and pT[]: range test of the exp argument
+  const int *col_map;                                 // [ncols]: thread column -> group * NpT + ip, sorted by the column's smallest
+                                                      // mT so that the columns of a block see the same cells as negligible
+  unsigned long long *items_done;                     // += items a block has marched over (executed-work statistic)
 };
 
 // The momentum loop over the items of one tile.  CLAMP = false: no item of the tile can reach the exp range guard.
@@ -107,7 +114,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   static_assert(!PAIR || BARYON, "pairs exist only with baryon terms");
   __shared__ DfItemU items[kTile];
   __shared__ double exptab[kExpTableSize];
-  __shared__ int warp_count[kThreads / 32];
+  __shared__ int warp_count[2][kThreads / 32];      // double-buffered: two barriers per tile
   load_exp_table(exptab, g.exptab);                 // visible after the first __syncthreads of the tile loop
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -116,7 +123,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
 
   // column = (thread group, pT node): the R classes of a group share the thread's pT and one baryon number
   const int col = blockIdx.x * kThreads + t;
-  const int colc = col < g.ncols ? col : g.ncols - 1;
+  const int colc = g.col_map[col < g.ncols ? col : g.ncols - 1];
   const int grp = colc / g.NpT, ip = colc - grp * g.NpT;
   constexpr int S = PAIR ? 2 : 1;                       // class ids per slot
   double mT[R], mT2[R], sgn[R];
@@ -147,6 +154,35 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   DfThreadU thm = th;                                   // the antibaryon partners: b -> -b
   if (PAIR) { thm.b = -th.b; thm.bpT = -th.bpT; thm.eslot = kMaxBaryon - (int)th.b; }
 
+  // range of the block's columns: every xE = mT aT - pT bT the block can form for an item lies in [mT_lo (aT - max(bT, 0)),
+  // mT_hi aT + pT_hi max(-bT, 0)]  (aT >= |bT| for a time-like flow velocity, pT <= mT)
+  // (kept in shared memory and re-read per tile: the momentum loop needs every register)
+  __shared__ double blk_range[3 * (kThreads / 32)];
+  __shared__ double blk_lohi[3];
+  __shared__ unsigned long long blk_items;
+  {
+    double lo = mT[0], hi = mT[0], ph = th.pT;
+#pragma unroll
+    for (int r = 1; r < R; r++) { lo = fmin(lo, mT[r]); hi = fmax(hi, mT[r]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      ph = fmax(ph, __shfl_xor_sync(0xffffffffu, ph, o));
+    }
+    if (lane == 0) { blk_range[3 * warp] = lo; blk_range[3 * warp + 1] = hi; blk_range[3 * warp + 2] = ph; }
+    __syncthreads();
+    if (t == 0) {
+      for (int w = 1; w < kThreads / 32; w++) {
+        lo = fmin(lo, blk_range[3 * w]); hi = fmax(hi, blk_range[3 * w + 1]); ph = fmax(ph, blk_range[3 * w + 2]);
+      }
+      blk_lohi[0] = lo; blk_lohi[1] = hi; blk_lohi[2] = ph;
+      blk_items = 0;
+    }
+    __syncthreads();
+  }
+  int flip = 0;
+
   const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
   int64_t chunk_end = chunk_begin + cells_per_chunk;
   if (chunk_end > ncells) chunk_end = ncells;
@@ -154,36 +190,53 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   for (int64_t tile = chunk_begin; tile < chunk_end; tile += kTile) {
     const int64_t cell = tile + t;
     const bool valid = (cell < chunk_end) && (pack[DP_VALID * stride + cell] != 0.0);
-    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
     for (int ie = 0; ie < g.Neta; ie++) {
-      __syncthreads();                       // previous tile fully consumed
-      if (lane == 0) warp_count[warp] = __popc(ballot);
-      __syncthreads();
-      int base = 0, n_items = 0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; w++) {
-        int c = warp_count[w];
-        if (w < warp) base += c;
-        n_items += c;
-      }
-      int hot = 0;
+      // The cell's item for this block's (y, phi), classified by the range of xE over the block's columns:
+      //   negligible: every xE >= kXeNegligible -- the Bose/Fermi factor of every evaluation is below 1e-295 (where fast_exp's range
+      //               guard saturates and the reference's exp overflows to feq = 0): the item is dropped like a u.dsigma <= 0 cell;
+      //   cold:       every xE < kXeCold: the loop without the range guard;      hot: the rest, the guarded loop.
+      // Cold items fill the tile from the front, hot items from the back.
+      bool cold = false, hot = false;
+      double sh = 0.0, ch = 1.0, w = 1.0;
       if (valid) {
-        double eta, w;
+        double eta;
         if (g.dimension == 3) { eta = pack[DP_ETA * stride + cell]; w = 1.0; }
         else { eta = g.etav[ie]; w = g.etaw[ie]; }
-        double sh = sinh(yval - eta);
-        double ch = sqrt(1.0 + sh * sh);     // the reference's cosh (MomentumSpectra.cpp:307-308)
-        auto pk = [&](int k) { return pack[k * stride + cell]; };
-        const DfItemU item = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sh, ch, cphi, sphi, w);
-        hot = df_item_needs_clamp(item.aT, item.bT, g.mT_max, g.pT_max);
-        items[base + __popc(ballot & ((1u << lane) - 1u))] = item;
+        sh = sinh(yval - eta);
+        ch = sqrt(1.0 + sh * sh);            // the reference's cosh (MomentumSpectra.cpp:307-308)
+        // aT, bT exactly as df_make_item_u forms them
+        const double aT = ch * pack[DP_UTT * stride + cell] - sh * pack[DP_TUNT * stride + cell];
+        const double bT = cphi * pack[DP_UXT * stride + cell] + sphi * pack[DP_UYT * stride + cell];
+        const volatile double *range = blk_lohi;
+        const double xe_lo = range[0] * (aT - fmax(bT, 0.0)), xe_hi = fma(range[1], aT, range[2] * fmax(-bT, 0.0));
+        const bool negligible = xe_lo >= kXeNegligible;          // NaN: false (kept, and hot)
+        cold = xe_hi < kXeCold;
+        hot = !negligible && !cold;
       }
-      // one barrier publishes the items and tells the block whether any of them can reach the exp range guard (cold cells,
-      // T < mT_max / 600): the common loop carries no clamp (one integer min per evaluation less)
-      if (__syncthreads_or(hot)) df_item_loop<MODE, BARYON, REGULATE, OUTFLOW, R, PAIR, true>(items, n_items, th, thm, mT, mT2, sgn, acc, accm, exptab);
-      else df_item_loop<MODE, BARYON, REGULATE, OUTFLOW, R, PAIR, false>(items, n_items, th, thm, mT, mT2, sgn, acc, accm, exptab);
+      const unsigned b_cold = __ballot_sync(0xffffffffu, cold), b_hot = __ballot_sync(0xffffffffu, hot);
+      if (lane == 0) warp_count[flip][warp] = __popc(b_cold) | (__popc(b_hot) << 16);
+      __syncthreads();                       // previous tile fully consumed, counts visible
+      int base_cold = 0, base_hot = 0, n_cold = 0, n_hot = 0;
+#pragma unroll
+      for (int w_ = 0; w_ < kThreads / 32; w_++) {
+        const int c = warp_count[flip][w_], cc = c & 0xffff, ch_ = c >> 16;
+        if (w_ < warp) { base_cold += cc; base_hot += ch_; }
+        n_cold += cc; n_hot += ch_;
+      }
+      if (cold || hot) {
+        const unsigned below = (1u << lane) - 1u;
+        auto pk = [&](int k) { return pack[k * stride + cell]; };
+        const int slot = cold ? base_cold + __popc(b_cold & below) : kTile - 1 - (base_hot + __popc(b_hot & below));
+        items[slot] = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sh, ch, cphi, sphi, w);
+      }
+      __syncthreads();
+      df_item_loop<MODE, BARYON, REGULATE, OUTFLOW, R, PAIR, false>(items, n_cold, th, thm, mT, mT2, sgn, acc, accm, exptab);
+      if (n_hot) df_item_loop<MODE, BARYON, REGULATE, OUTFLOW, R, PAIR, true>(items + (kTile - n_hot), n_hot, th, thm, mT, mT2, sgn, acc, accm, exptab);
+      if (t == 0) blk_items += (unsigned)(n_cold + n_hot);
+      flip ^= 1;
     }
   }
+  if (t == 0) atomicAdd(g.items_done, blk_items);
 
   const int64_t pbase = (int64_t)blockIdx.z * total;
 #pragma unroll
@@ -452,26 +505,44 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     ctx->set_error("species list holds a baryon number outside -2..2 (the reference's PDG readers produce hadrons and the deuteron only)");
     return IS3D_ERR_INVALID;
   }
+  // thread columns (group, pT) in order of their smallest mT: the columns of a block then agree on which cells are negligible
+  std::vector<int> class_of_all, rep_all;
+  species_classes(ctx, &class_of_all, &rep_all);
+  auto column_order = [&](const std::vector<int> &sl, int ids_per_group) {
+    const int ngroups = (int)(sl.size() / ids_per_group), NpT = ctx->NpT;
+    std::vector<double> key((size_t)ngroups * NpT);
+    for (int gi = 0; gi < ngroups; gi++) {
+      double m_min = 1e300;
+      for (int k = 0; k < ids_per_group; k++) {
+        const int cls = sl[(size_t)gi * ids_per_group + k];
+        if (cls >= 0) m_min = fmin(m_min, fabs(ctx->h_mass[rep_all[cls]]));
+      }
+      for (int ip = 0; ip < NpT; ip++) key[(size_t)gi * NpT + ip] = sqrt(m_min * m_min + ctx->pT[ip] * ctx->pT[ip]);
+    }
+    std::vector<int> order(key.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    return order;
+  };
+  const std::vector<int> order_single = column_order(slots, kDfBinsPerThread), order_pair = column_order(pair_slots, 2 * kDfPairsPerThread);
   void *d_slots = nullptr;
   std::vector<int> both(slots);
   both.insert(both.end(), pair_slots.begin(), pair_slots.end());
+  both.insert(both.end(), order_single.begin(), order_single.end());
+  both.insert(both.end(), order_pair.begin(), order_pair.end());
   IS3D_TRY(ctx->get_scratch("k1_slots", (both.size() + 1) * sizeof(int), &d_slots));
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `both` is pageable host memory
   g.slot_class = (const int *)d_slots;
+  g.col_map = (const int *)d_slots + slots.size() + pair_slots.size();
   g.ns = sb.nclass; g.NpT = ctx->NpT; g.ncols = ctx->NpT * (int)(slots.size() / kDfBinsPerThread);
   const int64_t per_species = (int64_t)ctx->NpT * ctx->Nphi * ctx->Ny;
   const int64_t total_class = (int64_t)sb.nclass * per_species;
   g.Ny = ctx->Ny; g.Nphi = ctx->Nphi; g.Neta = ctx->Neta; g.dimension = p.dimension;
   g.yv = ctx->d_y; g.cosphi = ctx->d_cosphi; g.sinphi = ctx->d_sinphi; g.etav = ctx->d_eta; g.etaw = ctx->d_etaw; g.exptab = ctx->d_exptab;
-  {
-    double m_max = 0.0, pT_max = 0.0;
-    for (int s = 0; s < ctx->ns; s++) m_max = fmax(m_max, fabs(ctx->h_mass[s]));
-    for (double v : ctx->pT) pT_max = fmax(pT_max, fabs(v));
-    g.pT_max = pT_max; g.mT_max = sqrt(m_max * m_max + pT_max * pT_max);
-  }
   DfGrid gp = g;                                                 // the pair launch: two class ids per slot
   gp.slot_class = (const int *)d_slots + slots.size();
+  gp.col_map = g.col_map + order_single.size();
   gp.ncols = ctx->NpT * (int)(pair_slots.size() / (2 * kDfPairsPerThread));
   const int nslices = (g.ncols + kThreads - 1) / kThreads, nslices_pair = (gp.ncols + kThreads - 1) / kThreads;
   // a pair block does about 1.6x the work of a single block; the wave policy counts blocks
@@ -490,6 +561,8 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total_class * sizeof(double), ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
 
+  g.items_done = (unsigned long long *)counters + 2;
+  gp.items_done = (unsigned long long *)counters + 3;
   cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   float ms_total = 0.f;
   int64_t launches = 0;
@@ -545,10 +618,9 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     stats->cells_out_of_table = (int64_t)h_counters[1];
     stats->kernel_ms = ms_total;
     stats->kernel_launches = launches;
-    // every valid cell is one item per (y, phi, eta) block row, evaluated by all nslices x kThreads thread columns x R slots
-    const int64_t per_column = (n - (int64_t)h_counters[0] - (int64_t)h_counters[1]) * (int64_t)kThreads * ctx->Ny * ctx->Nphi * ctx->Neta;
-    stats->pair_evals_executed = 2 * per_column * kDfPairsPerThread * nslices_pair;
-    stats->evals_executed = per_column * kDfBinsPerThread * nslices + stats->pair_evals_executed;
+    // items the blocks marched over (negligible items are dropped at tile-build time) x kThreads thread columns x R slots
+    stats->pair_evals_executed = 2 * (int64_t)h_counters[3] * kThreads * kDfPairsPerThread;
+    stats->evals_executed = (int64_t)h_counters[2] * kThreads * kDfBinsPerThread + stats->pair_evals_executed;
   }
   if (h_counters[1] != 0) {
     ctx->set_error(std::to_string(h_counters[1]) + " cell(s) outside the df coefficient tables (the reference aborts here)");
