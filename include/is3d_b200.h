@@ -88,6 +88,13 @@ typedef struct {
   int polzn_chunk_compat;        /* 0 (default) = every cell reads its own thermal vorticity; 1 = the reference's index INSIDE
                                     its 10 000-cell chunk (Polarization.cpp:125-130 use wtx_fo[icell], not [icell_glb]):
                                     identical for surfaces of up to 10 000 cells, unsharded surfaces only */
+  double negligible_margin;      /* continuous spectra, df_mode 1 / 2: (cell, y, phi) items whose every exponent (u.p - b mu_B)/T
+                                    in a block of momentum columns exceeds the block row's smallest possible exponent by more
+                                    than this margin are dropped before the momentum loop -- their terms are below e^-margin of
+                                    the bins' leading terms.  A speed heuristic, not a precision knob: the library sums a
+                                    rigorous bound of everything it dropped and compares it with each finished bin (bound <=
+                                    1e-13 |bin|); if any bin fails, the call is repeated without the margin
+                                    (is3d_stats.prune_reruns).  <= 0: off.  Default 80 */
 } is3d_params;
 
 /* Counters the reference prints (MomentumSpectra.cpp:1039-1040, :1674-1679; ParticleSampler.cpp:1133). */
@@ -110,6 +117,7 @@ typedef struct {
                                     evaluation (SASS) = the executed FP64-pipe work behind kernel_ms */
   int64_t pair_evals_executed;   /* the part of evals_executed done in charge-conjugate pair slots (a baryon class and its
                                     antibaryon class share x_E and its exponential) */
+  int64_t prune_reruns;          /* 1 = the dropped-term bound test failed and the spectra were recomputed without negligible_margin */
 } is3d_stats;
 
 /* One sampled hadron: the reference's Sampled_Particle (SampledParticle.h:32-54), same fields. */

@@ -25,7 +25,8 @@ class Params(C.Structure):
                 ("phip_bins", C.c_int), ("eta_cut", C.c_double), ("eta_bins", C.c_int),
                 ("tau_min", C.c_double), ("tau_max", C.c_double), ("tau_bins", C.c_int),
                 ("r_min", C.c_double), ("r_max", C.c_double), ("r_bins", C.c_int),
-                ("device", C.c_int), ("famod_chain", C.c_int), ("dndx_bug_compat", C.c_int), ("polzn_chunk_compat", C.c_int)]
+                ("device", C.c_int), ("famod_chain", C.c_int), ("dndx_bug_compat", C.c_int), ("polzn_chunk_compat", C.c_int),
+                ("negligible_margin", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -34,7 +35,8 @@ class Stats(C.Structure):
                 ("newton_iterations", C.c_int64), ("cells_out_of_table", C.c_int64),
                 ("sampler_proposals", C.c_int64), ("sampler_accepted", C.c_int64),
                 ("tau_breakdown", C.c_double), ("tau_pl_negative", C.c_double), ("kernel_ms", C.c_double),
-                ("kernel_launches", C.c_int64), ("evals_executed", C.c_int64), ("pair_evals_executed", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("evals_executed", C.c_int64), ("pair_evals_executed", C.c_int64),
+                ("prune_reruns", C.c_int64)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

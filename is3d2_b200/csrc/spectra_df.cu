@@ -21,6 +21,9 @@
 
 namespace is3d {
 
+// bounds below this are the < 1e-295 items dropped by the range guard itself (e^-680 times any prefactor a surface can produce)
+constexpr double kPruneFloor = 1e-280;
+
 namespace {
 
 // launch shape (tunable at build time for the sweeps recorded in profiles/): threads per block, resident blocks per SM
@@ -48,6 +51,7 @@ constexpr int kDfPairsPerThread = IS3D_K1_PAIR_R;   // charge-conjugate pair slo
 // range classes of an item's xE = u.p/T over the columns of a block (df_spectra_kernel)
 constexpr double kXeNegligible = 680.0;             // = fast_exp's range guard: feq < 1e-295 beyond, the reference's exp overflows at 709.8
 constexpr double kXeCold = 600.0;                   // below: no range guard needed
+constexpr double kPruneEps = 1e-13;                 // a-posteriori test of the dropped items: bound <= kPruneEps |bin| for every bin
 
 __global__ void df_setup_kernel(SurfaceView surf, int64_t begin, int64_t count, DfTables tb, DfFlags fl,
                                 double *__restrict__ pack, int64_t stride, unsigned long long *counters)
@@ -74,7 +78,62 @@ struct DfGrid {
   const int *col_map;                                 // [ncols]: thread column -> group * NpT + ip, sorted by the column's smallest
                                                       // mT so that the columns of a block see the same cells as negligible
   unsigned long long *items_done;                     // += items a block has marched over (executed-work statistic)
+  // dropping of negligible items (see df_spectra_kernel)
+  const unsigned long long *amin_bits;                // [Ny + 1] from df_amin_kernel: per y the smallest A = aT + |u_perp|/T of the pass
+                                                      // (bits of a positive double), then the largest |alpha_B|
+  double margin;                                      // Delta: items whose xE exceeds the row's smallest possible xE by more are dropped; <= 0: off
+  double *bsum;                                       // [slices of this launch][Ny * Nphi] += bounds of the dropped terms
 };
+
+constexpr unsigned long long kHugeBits = 0x7f7f7f7f7f7f7f7full;   // 1.4e306: what cudaMemset(0x7f) leaves
+
+// Per y: the smallest A_i = aT_i + |u_perp,i| / T_i over the valid cells (and eta nodes) of the pass, where aT_i = (u^tau cosh(y - eta)
+// - tau u^eta sinh(y - eta)) / T.  For a block whose columns have mT <= mT_hi, mT_hi A_min (+ kMaxBaryon max|alpha_B|) is an upper
+// bound of the smallest exponent x = xE - b alpha_B any of its bins sees: the scale of the bins' dominant terms.
+__global__ void df_amin_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int Ny, const double *__restrict__ yv,
+                               int dimension, int Neta, const double *__restrict__ etav, unsigned long long *__restrict__ amin_bits)
+{
+  extern __shared__ unsigned long long s_min[];       // [Ny + 1]
+  for (int k = threadIdx.x; k <= Ny; k += blockDim.x) s_min[k] = k < Ny ? kHugeBits : 0ull;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x, rounded = (count + 31) / 32 * 32;
+  for (int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cell < rounded; cell += step) {
+    const bool valid = cell < count && pack[DP_VALID * stride + cell] != 0.0;
+    double utt = 0, tunt = 0, uperp = 0, eta = 0, alpha = 0;
+    if (valid) {
+      utt = pack[DP_UTT * stride + cell]; tunt = pack[DP_TUNT * stride + cell];
+      const double uxt = pack[DP_UXT * stride + cell], uyt = pack[DP_UYT * stride + cell];
+      uperp = sqrt(uxt * uxt + uyt * uyt);
+      eta = pack[DP_ETA * stride + cell];
+      alpha = fabs(pack[DP_ALPHAB * stride + cell]);
+    }
+    unsigned long long am = (unsigned long long)__double_as_longlong(alpha);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, am, o); am = v > am ? v : am; }
+    if (lane == 0 && am) atomicMax(&s_min[Ny], am);
+    for (int iy = 0; iy < Ny; iy++) {
+      double A = __longlong_as_double((long long)kHugeBits);
+      if (valid) {
+        for (int ie = 0; ie < (dimension == 3 ? 1 : Neta); ie++) {
+          const double sh = sinh(yv[iy] - (dimension == 3 ? eta : etav[ie])), ch = sqrt(1.0 + sh * sh);
+          const double a = ch * utt - sh * tunt + uperp;
+          if (a < A) A = a;                            // NaN: ignored
+        }
+        if (!(A > 0.0)) A = 0.0;
+      }
+      unsigned long long b = (unsigned long long)__double_as_longlong(A);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, b, o); b = v < b ? v : b; }
+      if (lane == 0 && b != kHugeBits) atomicMin(&s_min[iy], b);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k <= Ny; k += blockDim.x) {
+    if (k < Ny) { if (s_min[k] != kHugeBits) atomicMin(&amin_bits[k], s_min[k]); }
+    else if (s_min[k]) atomicMax(&amin_bits[k], s_min[k]);
+  }
+}
 
 // The momentum loop over the items of one tile.  CLAMP = false: no item of the tile can reach the exp range guard.
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW, int R, bool PAIR, bool CLAMP>
@@ -158,8 +217,9 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   // mT_hi aT + pT_hi max(-bT, 0)]  (aT >= |bT| for a time-like flow velocity, pT <= mT)
   // (kept in shared memory and re-read per tile: the momentum loop needs every register)
   __shared__ double blk_range[3 * (kThreads / 32)];
-  __shared__ double blk_lohi[3];
+  __shared__ double blk_lohi[4];                      // mT_lo, mT_hi, pT_hi of the block's columns; the drop threshold of this row
   __shared__ unsigned long long blk_items;
+  __shared__ double blk_bound;                        // sum of the term bounds of the items this block dropped
   {
     double lo = mT[0], hi = mT[0], ph = th.pT;
 #pragma unroll
@@ -177,7 +237,19 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         lo = fmin(lo, blk_range[3 * w]); hi = fmax(hi, blk_range[3 * w + 1]); ph = fmax(ph, blk_range[3 * w + 2]);
       }
       blk_lohi[0] = lo; blk_lohi[1] = hi; blk_lohi[2] = ph;
-      blk_items = 0;
+      // Items are dropped when every exponent x = xE - b alpha_B they can produce in this block is >= the threshold:
+      //   kXeNegligible always (feq < 1e-295), and, with g.margin > 0, the row's dominant exponent + margin: such terms are
+      //   < e^-margin of the bins' leading terms.  The bounds of everything dropped are summed per row (g.bsum) and compared
+      //   with the finished spectra by reduce_partials_kernel; run_spectra_df repeats the call without the margin if any bin
+      //   fails that test, so the margin is a speed heuristic, not a precision knob.
+      double thr = kXeNegligible;
+      if (g.margin > 0.0) {
+        const double amin = __longlong_as_double((long long)g.amin_bits[iy]);
+        const double amax = __longlong_as_double((long long)g.amin_bits[g.Ny]);
+        thr = fmin(thr, fma(hi, amin, (BARYON ? kMaxBaryon * amax : 0.0) + g.margin));
+      }
+      blk_lohi[3] = thr;
+      blk_items = 0; blk_bound = 0.0;
     }
     __syncthreads();
   }
@@ -197,7 +269,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
       //   cold:       every xE < kXeCold: the loop without the range guard;      hot: the rest, the guarded loop.
       // Cold items fill the tile from the front, hot items from the back.
       bool cold = false, hot = false;
-      double sh = 0.0, ch = 1.0, w = 1.0;
+      double sh = 0.0, ch = 1.0, w = 1.0, dropped_bound = 0.0;
       if (valid) {
         double eta;
         if (g.dimension == 3) { eta = pack[DP_ETA * stride + cell]; w = 1.0; }
@@ -208,12 +280,24 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         const double aT = ch * pack[DP_UTT * stride + cell] - sh * pack[DP_TUNT * stride + cell];
         const double bT = cphi * pack[DP_UXT * stride + cell] + sphi * pack[DP_UYT * stride + cell];
         const volatile double *range = blk_lohi;
-        const double xe_lo = range[0] * (aT - fmax(bT, 0.0)), xe_hi = fma(range[1], aT, range[2] * fmax(-bT, 0.0));
-        const bool negligible = xe_lo >= kXeNegligible;          // NaN: false (kept, and hot)
-        cold = xe_hi < kXeCold;
+        const double mT_hi = range[1], pT_hi = range[2];
+        const double xe_lo = range[0] * (aT - fmax(bT, 0.0)), xe_hi = fma(mT_hi, aT, pT_hi * fmax(-bT, 0.0));
+        const double shift = BARYON ? kMaxBaryon * fabs(pack[DP_ALPHAB * stride + cell]) : 0.0;
+        const bool negligible = xe_lo - shift >= range[3];       // NaN: false (kept, and hot)
+        cold = !negligible && xe_hi < kXeCold;
         hot = !negligible && !cold;
+        if (negligible) {
+          auto pk = [&](int k) { return pack[k * stride + cell]; };
+          const DfItemU item = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sh, ch, cphi, sphi, w);
+          dropped_bound = df_item_term_bound<MODE, BARYON, REGULATE>(item, xe_lo, mT_hi, pT_hi, exptab);
+        }
       }
       const unsigned b_cold = __ballot_sync(0xffffffffu, cold), b_hot = __ballot_sync(0xffffffffu, hot);
+      if (__any_sync(0xffffffffu, dropped_bound != 0.0)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dropped_bound += __shfl_xor_sync(0xffffffffu, dropped_bound, o);
+        if (lane == 0) atomicAdd(&blk_bound, dropped_bound);
+      }
       if (lane == 0) warp_count[flip][warp] = __popc(b_cold) | (__popc(b_hot) << 16);
       __syncthreads();                       // previous tile fully consumed, counts visible
       int base_cold = 0, base_hot = 0, n_cold = 0, n_hot = 0;
@@ -237,6 +321,8 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
     }
   }
   if (t == 0) atomicAdd(g.items_done, blk_items);
+  __syncthreads();
+  if (t == 0 && blk_bound != 0.0) atomicAdd(&g.bsum[(int64_t)blockIdx.x * gridDim.y + blockIdx.y], blk_bound);
 
   const int64_t pbase = (int64_t)blockIdx.z * total;
 #pragma unroll
@@ -258,7 +344,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
 // times (2 pi hbarc)^-3 and its own degeneracy (MomentumSpectra.cpp:38, :399-401).
 __global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int64_t total_class, int64_t per_species,
                                        const int *__restrict__ class_of, const double *__restrict__ deg, int64_t total,
-                                       double *__restrict__ out)
+                                       double *__restrict__ out, PruneCheck chk)
 {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -266,6 +352,14 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, int n
   double s = 0.0;
   for (int c = 0; c < nchunks; c++) s += partial[(int64_t)c * total_class + src];
   out[i] = kCooperFryePrefactor * deg[sp] * s;
+  if (chk.bsum) {
+    // a-posteriori test of the dropped items: the bounds of everything dropped for this bin's block row must vanish against the
+    // bin itself (src = iy + Ny (iphi + Nphi (class NpT + ipT)); rows are numbered iy Nphi + iphi like blockIdx.y)
+    const int64_t jbin = src / chk.NyNphi;
+    const int rem = (int)(src - jbin * chk.NyNphi), iy = rem % chk.Ny, iphi = rem / chk.Ny;
+    const double b = chk.bsum[(int64_t)chk.bin_row[jbin] * chk.NyNphi + (iy * (chk.NyNphi / chk.Ny) + iphi)];
+    if (!(b <= chk.eps * fabs(s) + kPruneFloor)) atomicAdd(chk.violations, 1ull);
+  }
 }
 
 namespace {
@@ -480,6 +574,7 @@ void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk
 is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
 {
   const is3d_params &p = ctx->prm;
+  int64_t prune_reruns = 0;
   const int64_t n = ctx->surf.n;
   const int64_t total = (int64_t)ctx->ns * ctx->NpT * ctx->Nphi * ctx->Ny;
   DfFlags fl;
@@ -554,18 +649,46 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   int nchunks; int64_t cpc;
   choose_chunks(ctx, stride, blocks_per_chunk, total_class, kTile, &nchunks, &cpc);
 
-  void *pack = nullptr, *partial = nullptr, *counters = nullptr;
+  void *pack = nullptr, *partial = nullptr, *counters = nullptr, *prune = nullptr;
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)DP_SIZE * stride * sizeof(double), &pack));
   IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total_class * sizeof(double), &partial));
   IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
-  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total_class * sizeof(double), ctx->stream));
-  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
-
+  // dropping of negligible items: [Ny + 1] row scales from df_amin_kernel | bounds of the dropped terms per block row | bin -> row
+  const int NyNphi = ctx->Ny * ctx->Nphi, nrows = nslices + nslices_pair;
+  const size_t amin_bytes = (size_t)(ctx->Ny + 1) * 8, bsum_bytes = (size_t)nrows * NyNphi * 8;
+  std::vector<int> bin_row((size_t)sb.nclass * ctx->NpT, 0);
+  auto fill_rows = [&](const std::vector<int> &sl, int ids_per_group, const std::vector<int> &order, int row0) {
+    for (size_t c = 0; c < order.size(); c++) {
+      const int grp = order[c] / ctx->NpT, ip = order[c] - grp * ctx->NpT;
+      for (int k = 0; k < ids_per_group; k++) {
+        const int cls = sl[(size_t)grp * ids_per_group + k];
+        if (cls >= 0) bin_row[(size_t)cls * ctx->NpT + ip] = row0 + (int)(c / kThreads);
+      }
+    }
+  };
+  fill_rows(slots, kDfBinsPerThread, order_single, 0);
+  fill_rows(pair_slots, 2 * kDfPairsPerThread, order_pair, nslices);
+  IS3D_TRY(ctx->get_scratch("k1_prune", amin_bytes + bsum_bytes + bin_row.size() * sizeof(int), &prune));
+  unsigned long long *d_amin = (unsigned long long *)prune;
+  double *d_bsum = (double *)((char *)prune + amin_bytes);
+  int *d_bin_row = (int *)((char *)prune + amin_bytes + bsum_bytes);
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_bin_row, bin_row.data(), bin_row.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // pageable host memory
   g.items_done = (unsigned long long *)counters + 2;
   gp.items_done = (unsigned long long *)counters + 3;
+  g.amin_bits = gp.amin_bits = d_amin;
+  g.bsum = d_bsum; gp.bsum = d_bsum + (size_t)nslices * NyNphi;
   cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   float ms_total = 0.f;
   int64_t launches = 0;
+  unsigned long long h_counters[16];
+
+  // attempt 0 drops items below the margin; if the a-posteriori test fails for any bin, attempt 1 repeats the call without it
+  for (int attempt = 0; attempt < 2; attempt++) {
+  g.margin = gp.margin = attempt == 0 ? p.negligible_margin : 0.0;
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total_class * sizeof(double), ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(d_bsum, 0, bsum_bytes, ctx->stream));
 
   for (int64_t begin = 0; begin < n; begin += macro) {
     int64_t count = n - begin < macro ? n - begin : macro;
@@ -575,6 +698,14 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     int nch = (int)((count + cpc - 1) / cpc);
     dim3 grid(nslices, ctx->Ny * ctx->Nphi, nch), grid_pair(nslices_pair, ctx->Ny * ctx->Nphi, nch);
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    if (g.margin > 0.0) {
+      IS3D_CUDA_TRY(ctx, cudaMemsetAsync(d_amin, 0x7f, amin_bytes - 8, ctx->stream));
+      IS3D_CUDA_TRY(ctx, cudaMemsetAsync(d_amin + ctx->Ny, 0, 8, ctx->stream));
+      int64_t ab = (count + 255) / 256, ab_max = 8 * (int64_t)ctx->sm_count;
+      df_amin_kernel<<<(unsigned)(ab < ab_max ? ab : ab_max), 256, amin_bytes, ctx->stream>>>((double *)pack, stride, count, ctx->Ny, ctx->d_y, p.dimension, ctx->Neta, ctx->d_eta, d_amin);
+      IS3D_CUDA_TRY(ctx, cudaGetLastError());
+      launches += 1;
+    }
     const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0;
     // the pair launch first (its blocks are the longer ones); the single-class launch runs beside it on a second stream and
     // fills the tail of its last wave (disjoint bins of `partial`)
@@ -605,13 +736,19 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     ms_total += ms;
     launches += 2 + (nslices_pair && nslices ? 1 : 0);
   }
+  PruneCheck chk;                                      // without a margin only the < 1e-295 items are dropped: nothing to test
+  if (g.margin > 0.0) chk.bsum = d_bsum;
+  chk.bin_row = d_bin_row; chk.Ny = ctx->Ny; chk.NyNphi = NyNphi; chk.eps = kPruneEps;
+  chk.violations = (unsigned long long *)counters + 4;
   reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total_class, per_species,
-                                                                                sb.class_of, ctx->d_deg, total, out_dev);
+                                                                                sb.class_of, ctx->d_deg, total, out_dev, chk);
   IS3D_CUDA_TRY(ctx, cudaGetLastError());
   launches += 1;
-  unsigned long long h_counters[16];
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_counters[4] == 0 || h_counters[1] != 0 || !(g.margin > 0.0)) break;
+  prune_reruns++;
+  }
   if (stats) {
     stats->cells_total = n;
     stats->cells_skipped = (int64_t)h_counters[0];
@@ -621,6 +758,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     // items the blocks marched over (negligible items are dropped at tile-build time) x kThreads thread columns x R slots
     stats->pair_evals_executed = 2 * (int64_t)h_counters[3] * kThreads * kDfPairsPerThread;
     stats->evals_executed = (int64_t)h_counters[2] * kThreads * kDfBinsPerThread + stats->pair_evals_executed;
+    stats->prune_reruns = prune_reruns;
   }
   if (h_counters[1] != 0) {
     ctx->set_error(std::to_string(h_counters[1]) + " cell(s) outside the df coefficient tables (the reference aborts here)");

@@ -282,6 +282,56 @@ IS3D_HD DfItemU df_make_item_u(PackFn pk, double sh, double ch, double cphi, dou
   return it;
 }
 
+// Upper bound of |w p.dsigma feq (1 + df)| over every (class, pT) column a block can hold, for an item whose xE = u.p/T is at
+// least xe_lo > 0 on all of them (mT <= mT_hi, pT <= pT_hi, |b| <= kMaxBaryon).  Used for the items df_spectra_kernel drops as
+// negligible: the sum of these bounds per block row is compared with the finished spectra (a-posteriori check, spectra_df.cu).
+// Term by term from df_share_u / df_eval_u_tail with absolute values; feq <= 1 / (e^xE min_b e^(-b alphaB) - 1).  +inf when the
+// bound cannot be formed (the check then fails and the call is repeated without dropping anything).
+template <int MODE, bool BARYON, bool REGULATE>
+IS3D_HD double df_item_term_bound(const DfItemU &it, double xe_lo, double mT_hi, double pT_hi, const double *__restrict__ exptab)
+{
+  const double bm = BARYON ? (double)kMaxBaryon : 0.0;
+  double ebmin = 1.0;
+  if (BARYON) {
+    for (int i = 0; i < 2 * kMaxBaryon + 1; i++) ebmin = fmin(ebmin, it.eb[i]);
+  }
+  const double E = fast_exp(fmin(xe_lo, 680.0), exptab) * ebmin;
+  if (!(E > 4.0) || !(xe_lo > 0.0)) return as_double(0x7ff0000000000000ll);
+  const double feq_max = 1.0 / (E - 1.0);
+  const double P = mT_hi * fabs(it.c1) + pT_hi * fabs(it.d1);
+  const double pbmax = pT_hi * fabs(it.bT);
+  double df_max;
+  if (MODE == 1) {
+    const double A = pT_hi * fabs(it.q2) + bm * fabs(it.L1), B = pT_hi * pT_hi * fabs(it.q3) + bm * pT_hi * fabs(it.L2);
+    df_max = 2.0 * (mT_hi * mT_hi * fabs(it.q1) + mT_hi * A + B);            // |feqbar| <= 2
+    if (REGULATE) df_max = fmin(df_max, 1.0);
+  } else if (REGULATE) {
+    df_max = 1.0;
+  } else {
+    double A, B;
+    if (BARYON) {
+      const double C = fabs(it.K1) * bm + pT_hi * fabs(it.L2);
+      A = pT_hi * fabs(it.q2) + bm * fabs(it.Gv1) + C * fabs(it.aT) + fabs(it.L1) * pbmax;
+      B = pT_hi * pT_hi * fabs(it.q3) + bm * pT_hi * fabs(it.Gv2) + C * pbmax;
+    } else {
+      A = pT_hi * fabs(it.q2) + fabs(it.L2) * pbmax;                         // L2 slot: 2 K0 aT
+      B = pT_hi * pT_hi * fabs(it.q3) + fabs(it.L1) * pbmax * pbmax;         // L1 = K0
+    }
+    df_max = 2.0 * (mT_hi * mT_hi * fabs(it.q1) + mT_hi * A + B) / xe_lo;    // feqbar quad' / xE
+  }
+  const double bound = 1.001 * P * feq_max * (1.0 + df_max);
+  return bound == bound ? bound : as_double(0x7ff0000000000000ll);
+}
+
+// what reduce_partials_kernel needs to test the dropped items against the finished bins (bsum == nullptr: no test)
+struct PruneCheck {
+  const double *bsum = nullptr;        // [block row group][Ny * Nphi]: summed bounds of the dropped terms
+  const int *bin_row = nullptr;        // [(class, pT) bin] -> block row group of bsum
+  int Ny = 1, NyNphi = 1;
+  double eps = 0.0;                    // a bin passes when bound <= eps |bin|
+  unsigned long long *violations = nullptr;
+};
+
 // thread constants of the uniform-baryon path
 struct DfThreadU {
   double pT, pT2, b, bpT;        // b = the group's baryon number, bpT = b pT

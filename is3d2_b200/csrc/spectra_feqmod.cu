@@ -18,7 +18,7 @@ namespace is3d {
 
 __global__ void reduce_partials_kernel(const double *__restrict__ partial, int nchunks, int64_t total_class, int64_t per_species,
                                        const int *__restrict__ class_of, const double *__restrict__ deg, int64_t total,
-                                       double *__restrict__ out);
+                                       double *__restrict__ out, PruneCheck chk);
 is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out);
 bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots);
 bool pair_tables_core(const std::vector<int> &rep, const double *mass, const double *sign, const double *baryon, int R, int R_pair,
@@ -449,7 +449,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
     ms_total += ms;
   }
   reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total_class, per_species,
-                                                                                sb.class_of, ctx->d_deg, total, out_dev);
+                                                                                sb.class_of, ctx->d_deg, total, out_dev, PruneCheck());
   IS3D_CUDA_TRY(ctx, cudaGetLastError());
   launches++;
   unsigned long long h_counters[16];

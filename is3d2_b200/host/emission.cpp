@@ -59,6 +59,7 @@ is3d_params EmissionFunctionArray::params_from(ParameterReader *paraRdr, int *po
   if (const char *v = getenv("IS3D_FAMOD_CHAIN")) prm.famod_chain = atoi(v);
   if (const char *v = getenv("IS3D_DNDX_BUG_COMPAT")) prm.dndx_bug_compat = atoi(v);
   if (const char *v = getenv("IS3D_POLZN_CHUNK_COMPAT")) prm.polzn_chunk_compat = atoi(v);
+  if (const char *v = getenv("IS3D_NEGLIGIBLE_MARGIN")) prm.negligible_margin = atof(v);
   if (polzn_file_compat_out)
     if (const char *v = getenv("IS3D_POLZN_FILE_COMPAT")) *polzn_file_compat_out = atoi(v);
   return prm;

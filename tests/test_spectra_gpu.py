@@ -84,6 +84,33 @@ def test_launch_realistic_surface_matches_reference(libs, tmp_path, name):
     print(f"{name}: max rel err {worst:.3e}, {st.cells_skipped} of {st.cells_total} cells skipped")
 
 
+def test_negligible_margin_is_checked_a_posteriori(libs, tmp_path, monkeypatch):
+    """is3d_params.negligible_margin (K1): items far above a block row's smallest exponent are dropped before the momentum
+    loop, the bounds of what was dropped are compared with every finished bin, and the call is repeated without the margin
+    when a bin fails.  (a) default margin on the benchmark surface's first cells: fewer evaluations executed, no rerun, same
+    spectra as with the margin off to 1e-13; (b) an absurd margin that drops leading terms: the test fails, the rerun
+    delivers the margin-off result bit for bit."""
+    name = "bench_m2_smash_baryon_2304cells"
+    case = cases.BIG_SPECTRA_CASES[name]
+    surf, ref = harness.load_golden(name)
+    out = {}
+    for tag, margin in (("off", "0"), ("default", None), ("absurd", "1e-3")):
+        if margin is None:
+            monkeypatch.delenv("IS3D_NEGLIGIBLE_MARGIN", raising=False)
+        else:
+            monkeypatch.setenv("IS3D_NEGLIGIBLE_MARGIN", margin)
+        with harness.open_session(str(tmp_path / tag), case, surf) as h:
+            out[tag] = h.abi_spectra()
+    (off, st_off), (dflt, st_d), (absurd, st_a) = out["off"], out["default"], out["absurd"]
+    assert st_off.prune_reruns == 0 and st_d.prune_reruns == 0 and st_a.prune_reruns == 1
+    assert st_d.evals_executed < 0.9 * st_off.evals_executed, (st_d.evals_executed, st_off.evals_executed)
+    np.testing.assert_array_equal(absurd, off)
+    big = np.abs(off) > 1e-250
+    assert np.abs(dflt[big] / off[big] - 1.0).max() < 1e-13
+    harness.assert_spectra_close(dflt, ref, what=name + " default margin")
+    print(f"default margin executes {st_d.evals_executed / st_off.evals_executed:.3f} of the margin-off class evaluations")
+
+
 def test_known_answer_static_cell(libs, tmp_path):
     """Ideal static cell: dN = g/(2 pi hbarc)^3 mT cosh(eta) dsigma_tau feq, and the reference's own
     printed value for pi+ at pT = 0 (1.37049908e+01)."""
