@@ -436,6 +436,16 @@ def attach_product_communicator(h, world: int, rank: int) -> None:
     h._check(h.lib.is3d_comm_attach(h.ctx, ident, world, rank), "is3d_comm_attach")
 
 
+def _library_margin(h) -> float:
+    """is3d_params.negligible_margin the benchmarked context was created with (the host layer reads IS3D_NEGLIGIBLE_MARGIN)."""
+    import ctypes as C
+
+    from is3d2_b200 import capi
+    p = capi.Params()
+    h.lib.is3d_default_params(C.byref(p))
+    return float(os.environ.get("IS3D_NEGLIGIBLE_MARGIN", p.negligible_margin))
+
+
 def _measure_ours(args, h, world: int, rank: int, local: int):
     import ctypes as C
 
@@ -486,13 +496,14 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
         if rank == 0:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kernel_ms, launches, skipped, executed, executed_pair = 0.0, 0, 0, 0, 0
+        kernel_ms, launches, skipped, executed, executed_pair, dropped, reruns = 0.0, 0, 0, 0, 0, 0, 0
         ev0.record(ext)
         for _ in range(args.steps):
             st = step()
             kernel_ms += st.kernel_ms
             launches += st.kernel_launches
             skipped, executed, executed_pair = st.cells_skipped, st.evals_executed, st.pair_evals_executed
+            dropped, reruns = st.evals_dropped, reruns + st.prune_reruns
         ev1.record(ext)
         barrier()
         clocks = sampler.stop() if rank == 0 else None
@@ -518,12 +529,13 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
 
     # max over ranks of the two times, sums of the per-rank counters
     t = torch.tensor([ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
-    c = torch.tensor([float(skipped), float(executed), float(cells), float(executed_pair)], dtype=torch.float64, device="cuda")
+    c = torch.tensor([float(skipped), float(executed), float(cells), float(executed_pair), float(dropped), float(reruns)],
+                     dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c)
     ms_total, e2e_s, kernel_ms = (float(v) for v in t.tolist())
-    skipped_all, executed_all, cells_all, pair_all = (float(v) for v in c.tolist())
+    skipped_all, executed_all, cells_all, pair_all, dropped_all, reruns_all = (float(v) for v in c.tolist())
     assert int(cells_all) == G
 
     fp64_peak = h.abi_fp64_peak()
@@ -588,6 +600,15 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
                 "equals_value_path": bool(np.array_equal(spec.reshape(-1), value_out))},
         "gpu_launches": int(launches),
         "cells_skipped_frac": skipped_all / G,
+        "negligible_items": {
+            "margin": _library_margin(h), "class_evals_dropped_per_step": dropped_all,
+            "dropped_frac_of_thread_slots": dropped_all / (dropped_all + executed_all) if executed_all else None,
+            "reruns_in_timed_steps": int(reruns_all),
+            "what": "(cell, y, phi) items whose every exponent (u.p - b mu_B)/T over a block of momentum columns is >= 680 (Bose/Fermi "
+                    "factor < 1e-295, the reference's exp overflows at 709.8) or exceeds the block row's smallest possible exponent by "
+                    "more than `margin` are dropped before the momentum loop; the library sums a rigorous bound of every dropped term "
+                    "and tests it against each finished bin (bound <= 1e-13 |bin|), repeating the call without the margin if any bin "
+                    "fails (a rerun is inside the timed region). --negligible-margin 0 measures without the margin"},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": (label + " + " + label_pair) if label else "feqmod_spectra_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
@@ -618,6 +639,8 @@ def _measure_ours(args, h, world: int, rank: int, local: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--negligible-margin", type=float, default=None,
+                    help="is3d_params.negligible_margin of the benchmarked context (default: the library's, 80; 0 = off)")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -635,6 +658,8 @@ def main():
     ap.add_argument("--ref-sampler-cells", type=int, default=3000)
     args = ap.parse_args()
     _claim_stdout()
+    if args.negligible_margin is not None:
+        os.environ["IS3D_NEGLIGIBLE_MARGIN"] = repr(float(args.negligible_margin))      # read by the host layer at prepare()
     if args.impl == "reference":
         run_reference(args)
     else:

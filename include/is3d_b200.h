@@ -117,6 +117,8 @@ typedef struct {
                                     evaluation (SASS) = the executed FP64-pipe work behind kernel_ms */
   int64_t pair_evals_executed;   /* the part of evals_executed done in charge-conjugate pair slots (a baryon class and its
                                     antibaryon class share x_E and its exponential) */
+  int64_t evals_dropped;         /* class-evaluations NOT executed because their (cell, y, phi) item was dropped as negligible for the
+                                    whole block of momentum columns (range guard at x >= 680, and is3d_params.negligible_margin) */
   int64_t prune_reruns;          /* 1 = the dropped-term bound test failed and the spectra were recomputed without negligible_margin */
 } is3d_stats;
 

@@ -36,7 +36,7 @@ class Stats(C.Structure):
                 ("sampler_proposals", C.c_int64), ("sampler_accepted", C.c_int64),
                 ("tau_breakdown", C.c_double), ("tau_pl_negative", C.c_double), ("kernel_ms", C.c_double),
                 ("kernel_launches", C.c_int64), ("evals_executed", C.c_int64), ("pair_evals_executed", C.c_int64),
-                ("prune_reruns", C.c_int64)]
+                ("evals_dropped", C.c_int64), ("prune_reruns", C.c_int64)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

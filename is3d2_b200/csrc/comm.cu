@@ -141,6 +141,7 @@ void add_stats(is3d_stats *total, const is3d_stats &s)
   total->kernel_launches += s.kernel_launches;
   total->evals_executed += s.evals_executed;
   total->pair_evals_executed += s.pair_evals_executed;
+  total->evals_dropped += s.evals_dropped;
   total->prune_reruns += s.prune_reruns;
 }
 

@@ -77,7 +77,8 @@ struct DfGrid {
   const double *exptab;                               // 2^(m/1024), global memory (ctx->d_exptab)
   const int *col_map;                                 // [ncols]: thread column -> group * NpT + ip, sorted by the column's smallest
                                                       // mT so that the columns of a block see the same cells as negligible
-  unsigned long long *items_done;                     // += items a block has marched over (executed-work statistic)
+  const int *y_order;                                 // [Ny]: rapidity index of block row rank k
+  unsigned long long *items_done;                     // += items a block has marched over (executed-work statistic); [4]: += items dropped
   // dropping of negligible items (see df_spectra_kernel)
   const unsigned long long *amin_bits;                // [Ny + 1] from df_amin_kernel: per y the smallest A = aT + |u_perp|/T of the pass
                                                       // (bits of a positive double), then the largest |alpha_B|
@@ -177,7 +178,9 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   load_exp_table(exptab, g.exptab);                 // visible after the first __syncthreads of the tile loop
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;
+  // rapidity rows in order of decreasing expected work (y_order: |y - y_mid| ascending; far rapidities drop most items): the last
+  // blocks of the launch are then the short ones
+  const int iyr = blockIdx.y / g.Nphi, iphi = blockIdx.y - iyr * g.Nphi, iy = g.y_order[iyr];
   const double yval = g.yv[iy], cphi = g.cosphi[iphi], sphi = g.sinphi[iphi];
 
   // column = (thread group, pT node): the R classes of a group share the thread's pT and one baryon number
@@ -218,7 +221,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
   // (kept in shared memory and re-read per tile: the momentum loop needs every register)
   __shared__ double blk_range[3 * (kThreads / 32)];
   __shared__ double blk_lohi[4];                      // mT_lo, mT_hi, pT_hi of the block's columns; the drop threshold of this row
-  __shared__ unsigned long long blk_items;
+  __shared__ unsigned long long blk_items, blk_dropped;
   __shared__ double blk_bound;                        // sum of the term bounds of the items this block dropped
   {
     double lo = mT[0], hi = mT[0], ph = th.pT;
@@ -249,7 +252,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         thr = fmin(thr, fma(hi, amin, (BARYON ? kMaxBaryon * amax : 0.0) + g.margin));
       }
       blk_lohi[3] = thr;
-      blk_items = 0; blk_bound = 0.0;
+      blk_items = 0; blk_dropped = 0; blk_bound = 0.0;
     }
     __syncthreads();
   }
@@ -268,7 +271,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
       //               guard saturates and the reference's exp overflows to feq = 0): the item is dropped like a u.dsigma <= 0 cell;
       //   cold:       every xE < kXeCold: the loop without the range guard;      hot: the rest, the guarded loop.
       // Cold items fill the tile from the front, hot items from the back.
-      bool cold = false, hot = false;
+      bool cold = false, hot = false, dropped = false;
       double sh = 0.0, ch = 1.0, w = 1.0, dropped_bound = 0.0;
       if (valid) {
         double eta;
@@ -286,6 +289,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         const bool negligible = xe_lo - shift >= range[3];       // NaN: false (kept, and hot)
         cold = !negligible && xe_hi < kXeCold;
         hot = !negligible && !cold;
+        dropped = negligible;
         if (negligible) {
           auto pk = [&](int k) { return pack[k * stride + cell]; };
           const DfItemU item = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sh, ch, cphi, sphi, w);
@@ -293,10 +297,11 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         }
       }
       const unsigned b_cold = __ballot_sync(0xffffffffu, cold), b_hot = __ballot_sync(0xffffffffu, hot);
-      if (__any_sync(0xffffffffu, dropped_bound != 0.0)) {
+      const unsigned b_dropped = __ballot_sync(0xffffffffu, dropped);
+      if (b_dropped) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dropped_bound += __shfl_xor_sync(0xffffffffu, dropped_bound, o);
-        if (lane == 0) atomicAdd(&blk_bound, dropped_bound);
+        if (lane == 0) { atomicAdd(&blk_bound, dropped_bound); atomicAdd(&blk_dropped, (unsigned long long)__popc(b_dropped)); }
       }
       if (lane == 0) warp_count[flip][warp] = __popc(b_cold) | (__popc(b_hot) << 16);
       __syncthreads();                       // previous tile fully consumed, counts visible
@@ -320,9 +325,9 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
       flip ^= 1;
     }
   }
-  if (t == 0) atomicAdd(g.items_done, blk_items);
+  if (t == 0) { atomicAdd(g.items_done, blk_items); atomicAdd(g.items_done + 4, blk_dropped); }
   __syncthreads();
-  if (t == 0 && blk_bound != 0.0) atomicAdd(&g.bsum[(int64_t)blockIdx.x * gridDim.y + blockIdx.y], blk_bound);
+  if (t == 0 && blk_bound != 0.0) atomicAdd(&g.bsum[(int64_t)blockIdx.x * gridDim.y + (iy * g.Nphi + iphi)], blk_bound);
 
   const int64_t pbase = (int64_t)blockIdx.z * total;
 #pragma unroll
@@ -625,11 +630,19 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   both.insert(both.end(), pair_slots.begin(), pair_slots.end());
   both.insert(both.end(), order_single.begin(), order_single.end());
   both.insert(both.end(), order_pair.begin(), order_pair.end());
+  {
+    std::vector<int> yo(ctx->Ny);
+    double ymid = 0.0;
+    for (int k = 0; k < ctx->Ny; k++) { yo[k] = k; ymid += ctx->yv[k] / ctx->Ny; }
+    std::stable_sort(yo.begin(), yo.end(), [&](int a, int b) { return fabs(ctx->yv[a] - ymid) < fabs(ctx->yv[b] - ymid); });
+    both.insert(both.end(), yo.begin(), yo.end());
+  }
   IS3D_TRY(ctx->get_scratch("k1_slots", (both.size() + 1) * sizeof(int), &d_slots));
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `both` is pageable host memory
   g.slot_class = (const int *)d_slots;
   g.col_map = (const int *)d_slots + slots.size() + pair_slots.size();
+  g.y_order = g.col_map + order_single.size() + order_pair.size();
   g.ns = sb.nclass; g.NpT = ctx->NpT; g.ncols = ctx->NpT * (int)(slots.size() / kDfBinsPerThread);
   const int64_t per_species = (int64_t)ctx->NpT * ctx->Nphi * ctx->Ny;
   const int64_t total_class = (int64_t)sb.nclass * per_species;
@@ -739,7 +752,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   PruneCheck chk;                                      // without a margin only the < 1e-295 items are dropped: nothing to test
   if (g.margin > 0.0) chk.bsum = d_bsum;
   chk.bin_row = d_bin_row; chk.Ny = ctx->Ny; chk.NyNphi = NyNphi; chk.eps = kPruneEps;
-  chk.violations = (unsigned long long *)counters + 4;
+  chk.violations = (unsigned long long *)counters + 4;     // counters: 2, 3 items marched (single, pair launch), 6, 7 items dropped
   reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total_class, per_species,
                                                                                 sb.class_of, ctx->d_deg, total, out_dev, chk);
   IS3D_CUDA_TRY(ctx, cudaGetLastError());
@@ -758,6 +771,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
     // items the blocks marched over (negligible items are dropped at tile-build time) x kThreads thread columns x R slots
     stats->pair_evals_executed = 2 * (int64_t)h_counters[3] * kThreads * kDfPairsPerThread;
     stats->evals_executed = (int64_t)h_counters[2] * kThreads * kDfBinsPerThread + stats->pair_evals_executed;
+    stats->evals_dropped = ((int64_t)h_counters[6] * kDfBinsPerThread + 2 * (int64_t)h_counters[7] * kDfPairsPerThread) * kThreads;
     stats->prune_reruns = prune_reruns;
   }
   if (h_counters[1] != 0) {
