@@ -156,8 +156,12 @@ __device__ __forceinline__ void df_item_loop(const DfItemU *__restrict__ items, 
         const double xE = df_eval_u_x<CLAMP>(it, sh, mT[r]);
         int spare;
         const double e = fast_exp_k<false>(xE, exptab, spare);
-        acc[r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], xE, e, spare);
-        accm[r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, shm, mT[r], mT2[r], sgn[r], xE, e, spare);
+        if (!CLAMP) {              // cold items of the pair launch lie below kXePairShared: one reciprocal for both members
+          df_eval_u_pair_shared<MODE, REGULATE, OUTFLOW>(it, sh, shm, mT[r], mT2[r], sgn[r], xE, e, spare, acc[r], accm[r]);
+        } else {
+          acc[r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, mT[r], mT2[r], sgn[r], xE, e, spare);
+          accm[r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, shm, mT[r], mT2[r], sgn[r], xE, e, spare);
+        }
       }
     }
   }
@@ -287,7 +291,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
         const double xe_lo = range[0] * (aT - fmax(bT, 0.0)), xe_hi = fma(mT_hi, aT, pT_hi * fmax(-bT, 0.0));
         const double shift = BARYON ? kMaxBaryon * fabs(pack[DP_ALPHAB * stride + cell]) : 0.0;
         const bool negligible = xe_lo - shift >= range[3];       // NaN: false (kept, and hot)
-        cold = !negligible && xe_hi < kXeCold;
+        cold = !negligible && xe_hi + (PAIR ? shift : 0.0) < (PAIR ? kXePairShared : kXeCold);
         hot = !negligible && !cold;
         dropped = negligible;
         if (negligible) {

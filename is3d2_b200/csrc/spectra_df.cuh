@@ -410,15 +410,14 @@ IS3D_HD double df_eval_u(const DfItemU &it, const DfSharedU &s, double mT, doubl
   return df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, s, mT, mT2, sign, xE, e, spare);
 }
 
+// the part of an evaluation behind the reciprocal: rc = 1 / (q xE) (df_mode 2) or 1 / q (df_mode 1), q = e^x + sign
 template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
-IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, double xE, double e,
-                              int spare)
+IS3D_HD double df_eval_u_finish(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, double xE, double q, double rc)
 {
-  const double q = BARYON ? fma(e, s.eb, sign) : e + sign;         // e^x + sign, x = xE - b alpha_B
   const double quad = fma(mT2, it.q1, fma(mT, s.A, s.B));      // Horner form without mT^2: same speed (profiles/r02_k1_variants_horner_pairR.txt)
   if (MODE == 2 && !REGULATE) {
     // folded form: (it.q1, s.A, s.B) hold quad' = quad + lin xE (df_make_item_u / df_share_u with FOLD = true)
-    const double y = fast_rcp(q * xE, spare);
+    const double y = rc;
     const double feq = y * xE;
     const double feqbar = fma(-sign, feq, 1.0);
     const double pds = fma(mT, it.c1, s.pd);
@@ -428,12 +427,10 @@ IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, 
   }
   double feq, dfv;
   if (MODE == 1) {
-    feq = fast_rcp(q, spare);
+    feq = rc;
     dfv = quad;
   } else {
-    // one reciprocal serves 1/(e^x + sign) and 1/xE (e^x <= 2.1e295 by fast_exp's clamp and exp(|b| alpha_B) < 1e4, so
-    // the product stays finite for any xE a surface can produce)
-    const double y = fast_rcp(q * xE, spare);
+    const double y = rc;
     feq = y * xE;
     const double r = y * q;
     dfv = fma(quad, r, BARYON ? fma(mT, it.L1, s.C) : it.L1 * xE);
@@ -445,6 +442,32 @@ IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, 
   double contrib = pds * fma(feq, df, feq);
   if (OUTFLOW) contrib = (pds <= 0.0) ? 0.0 : contrib;
   return contrib;
+}
+
+template <int MODE, bool BARYON, bool REGULATE, bool OUTFLOW>
+IS3D_HD double df_eval_u_tail(const DfItemU &it, const DfSharedU &s, double mT, double mT2, double sign, double xE, double e,
+                              int spare)
+{
+  const double q = BARYON ? fma(e, s.eb, sign) : e + sign;         // e^x + sign, x = xE - b alpha_B
+  // df_mode 2: one reciprocal serves 1/(e^x + sign) and 1/xE (e^x <= 2.1e295 by fast_exp's clamp and exp(|b| alpha_B) < 1e4, so
+  // the product stays finite for any xE a surface can produce)
+  const double rc = fast_rcp(MODE == 1 ? q : q * xE, spare);
+  return df_eval_u_finish<MODE, BARYON, REGULATE, OUTFLOW>(it, s, mT, mT2, sign, xE, q, rc);
+}
+
+// A charge-conjugate pair (s: the baryon member, sm: its antibaryon partner) from ONE reciprocal: with D = q qm [xE],
+// 1 / (q [xE]) = qm / D and 1 / (qm [xE]) = q / D -- one FP64 instruction (df_mode 2) and one MUFU seed fewer than two
+// reciprocals.  Only where D cannot overflow: callers use it for items whose every xE is below kXePairShared.
+constexpr double kXePairShared = 340.0;
+template <int MODE, bool REGULATE, bool OUTFLOW>
+IS3D_HD void df_eval_u_pair_shared(const DfItemU &it, const DfSharedU &s, const DfSharedU &sm, double mT, double mT2, double sign,
+                                   double xE, double e, int spare, double &acc, double &accm)
+{
+  const double q = fma(e, s.eb, sign), qm = fma(e, sm.eb, sign);
+  const double qx = MODE == 1 ? q : q * xE;
+  const double Y = fast_rcp(qx * qm, spare);
+  acc += df_eval_u_finish<MODE, true, REGULATE, OUTFLOW>(it, s, mT, mT2, sign, xE, q, Y * qm);
+  accm += df_eval_u_finish<MODE, true, REGULATE, OUTFLOW>(it, sm, mT, mT2, sign, xE, qm, Y * q);
 }
 
 }  // namespace is3d
