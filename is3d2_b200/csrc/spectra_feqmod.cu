@@ -11,6 +11,8 @@
 //                            item for the block's (y, phi); the inner loop takes a warp-uniform branch per item:
 //                            modified distribution (3 FMA + sqrt + exp + FMA + rcp, feqmod_accum_u) or linear-df fallback
 //   4. reduce_partials_kernel (shared with K1)
+#include <algorithm>
+
 #include "ctx.h"
 #include "spectra_feqmod.cuh"
 
@@ -92,7 +94,85 @@ struct FeqGrid {
   const double *yv, *cosphi, *sinphi, *etav, *etaw;
   const double *exptab;
   bool w_on_dan;      // eta weight multiplies the whole p.dsigma (famod, MomentumSpectra.cpp:1617) instead of the feqmod placement
+  // as in K1 (spectra_df.cu): thread columns sorted by their smallest mT, rapidity rows by expected work, dropping of negligible items
+  const int *col_map, *y_order;
+  unsigned long long *items_done;       // [0] += items marched, [4] += items dropped
+  const unsigned long long *amin_bits;  // [Ny + 1] from feqmod_amin_kernel
+  double margin;
+  double *bsum;                         // [slices of this launch][Ny * Nphi]
+  const double *renorm_max;             // [cell]: largest PTM renormalisation of the cell's classes (SPECIES_RENORM), else nullptr
 };
+
+constexpr unsigned long long kHugeBits = 0x7f7f7f7f7f7f7f7full;   // 1.4e306: what cudaMemset(0x7f) leaves
+constexpr double kXeNegligible = 680.0;                           // fast_exp's range guard (see spectra_df.cu)
+
+// Per y: the smallest S = sqrt((|g1| + |A3| + |A4|)^2 + 1/T'^2) over the pass's valid cells that take the modified distribution;
+// mT_hi S (+ kMaxBaryon max|alphaB'|) bounds the smallest exponent E'/T' - b alphaB' of a block row from above (feqmod_item_range
+// with pT <= mT): the scale of the bins' leading terms, as df_amin_kernel does for K1.
+__global__ void feqmod_amin_kernel(const double *__restrict__ pack, int64_t stride, int64_t count, int Ny, const double *__restrict__ yv,
+                                   int dimension, int Neta, const double *__restrict__ etav, unsigned long long *__restrict__ amin_bits)
+{
+  extern __shared__ unsigned long long s_min[];       // [Ny + 1]
+  for (int k = threadIdx.x; k <= Ny; k += blockDim.x) s_min[k] = k < Ny ? kHugeBits : 0ull;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x, rounded = (count + 31) / 32 * 32;
+  for (int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cell < rounded; cell += step) {
+    const bool valid = cell < count && pack[DP_VALID * stride + cell] != 0.0 && pack[FP_BREAKDOWN * stride + cell] == 0.0;
+    double a1[3] = {0, 0, 0}, a2[3] = {0, 0, 0}, G2 = 0, iT2 = 0, eta = 0, scale = 1, alpha = 0;
+    if (valid) {
+      double n3 = 0, n4 = 0;
+      for (int i = 0; i < 3; i++) {
+        a1[i] = pack[(FP_A1X + i) * stride + cell]; a2[i] = pack[(FP_A2X + i) * stride + cell];
+        const double a3 = pack[(FP_A3X + i) * stride + cell], a4 = pack[(FP_A4X + i) * stride + cell];
+        n3 += a3 * a3; n4 += a4 * a4;
+      }
+      G2 = sqrt(n3) + sqrt(n4);
+      iT2 = pack[FP_IT2 * stride + cell];
+      eta = pack[DP_ETA * stride + cell]; scale = pack[FP_ETA_SCALE * stride + cell];
+      alpha = fabs(pack[FP_ALPHAB_MOD * stride + cell]);
+    }
+    unsigned long long am = (unsigned long long)__double_as_longlong(alpha);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, am, o); am = v > am ? v : am; }
+    if (lane == 0 && am) atomicMax(&s_min[Ny], am);
+    for (int iy = 0; iy < Ny; iy++) {
+      double S = __longlong_as_double((long long)kHugeBits);
+      if (valid) {
+        for (int ie = 0; ie < (dimension == 3 ? 1 : Neta); ie++) {
+          const double d = yv[iy] - scale * (dimension == 3 ? eta : etav[ie]), sh = sinh(d), ch = cosh(d);
+          double n1 = 0;
+          for (int i = 0; i < 3; i++) { const double v = ch * a1[i] + sh * a2[i]; n1 += v * v; }
+          const double g = sqrt(n1) + G2, v = sqrt(g * g + iT2);
+          if (v < S) S = v;
+        }
+        if (!(S > 0.0)) S = 0.0;
+      }
+      unsigned long long b = (unsigned long long)__double_as_longlong(S);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, b, o); b = v < b ? v : b; }
+      if (lane == 0 && b != kHugeBits) atomicMin(&s_min[iy], b);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k <= Ny; k += blockDim.x) {
+    if (k < Ny) { if (s_min[k] != kHugeBits) atomicMin(&amin_bits[k], s_min[k]); }
+    else if (s_min[k]) atomicMax(&amin_bits[k], s_min[k]);
+  }
+}
+
+// largest renormalisation of a cell over all class slots (single slots, then pair members)
+__global__ void feqmod_renorm_max_kernel(const double *__restrict__ renorm, int nslots, const double *__restrict__ renorm_pair, int nslots_pair,
+                                         int64_t count, double *__restrict__ out)
+{
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= count) return;
+  double m = 0.0;
+  for (int k = 0; k < nslots; k++) m = fmax(m, fabs(renorm[cell * nslots + k]));
+  for (int k = 0; k < nslots_pair; k++) m = fmax(m, fabs(renorm_pair[cell * nslots_pair + k]));
+  out[cell] = m;
+}
+
 
 union ItemSlot {
   DfItem lin;
@@ -113,6 +193,74 @@ __global__ void feqmod_tile_flags_kernel(const double *__restrict__ pack, int64_
   if ((threadIdx.x & 31) == 0 && any) atomicOr(&tile_linear[cell / kTile], 1);
 }
 
+// thread constants of feqmod_spectra_kernel's momentum loop
+template <int R, bool PAIR>
+struct FeqThread {
+  DfBin bin[R];
+  double pT, pT2;
+  int eslot, eslotm, grp;
+};
+
+// The momentum loop over n items starting at items[0] / item_cell[0].  CLAMP = false (modified branch only): every exponent of
+// these items is below kXePairShared on the block's columns -- no range guard, one reciprocal per charge-conjugate pair.
+template <bool LINEAR, bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM, int R, bool PAIR, bool CLAMP>
+__device__ __forceinline__ void feqmod_item_loop(const ItemSlot *__restrict__ items, const int *__restrict__ item_cell, int n_items,
+                                                 const FeqThread<R, PAIR> &th, const double *__restrict__ renorm, int nslots,
+                                                 double (&acc)[R], double (&accm)[PAIR ? R : 1], const double *__restrict__ exptab)
+{
+  constexpr int S = PAIR ? 2 : 1;
+#pragma unroll 1
+  for (int k = 0; k < n_items; k++) {
+    double rn[R], rnm[PAIR ? R : 1];
+    if (SPECIES_RENORM) {      // L2-resident row; a software prefetch of item k + 1's row measured 11 % slower (profiles/r01_summary.md)
+      const double *row = renorm + (int64_t)item_cell[k] * nslots + S * th.grp * R;
+      if (PAIR) {              // (member b > 0, member b < 0) of every slot side by side
+#pragma unroll
+        for (int r = 0; r < R; r++) { const double2 v = *reinterpret_cast<const double2 *>(row + 2 * r); rn[r] = v.x; rnm[r] = v.y; }
+      } else if (R % 2 == 0) {
+#pragma unroll
+        for (int r = 0; r < R; r += 2) { const double2 v = *reinterpret_cast<const double2 *>(row + r); rn[r] = v.x; rn[r + 1] = v.y; }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) rn[r] = row[r];
+      }
+    }
+    if (!LINEAR) {
+      const FeqmodItem &it = items[k].mod;        // shared memory: broadcast LDS.128 + one LDS.64 for eb[eslot]
+      const FeqmodShared sh = feqmod_share(it, th.pT, th.pT2);
+      const double eb = BARYON ? it.eb[th.eslot] : 1.0;
+      if (PAIR) {
+        const double ebm = it.eb[th.eslotm];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          feqmod_accum_pair_u<OUTFLOW, !SPECIES_RENORM, CLAMP>(acc[r], accm[r], it, sh, eb, ebm, th.bin[r].mT, th.bin[r].mT2, th.bin[r].sign,
+                                                               SPECIES_RENORM ? rn[r] : 1.0, SPECIES_RENORM ? rnm[r] : 1.0, exptab);
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          feqmod_accum_u<BARYON, OUTFLOW, !SPECIES_RENORM, CLAMP>(acc[r], it, sh, eb, th.bin[r].mT, th.bin[r].mT2, th.bin[r].sign,
+                                                                  SPECIES_RENORM ? rn[r] : 1.0, exptab);
+      }
+    } else {
+      const DfItem it = items[k].lin;
+      const DfShared sh = df_share<BARYON>(it, th.pT, th.pT2);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        double v = df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, th.bin[r], exptab);
+        if (SPECIES_RENORM) v = (rn[r] != 0.0) ? v : 0.0;   // NaN renorm: the reference skips the species (:828-832)
+        acc[r] += v;
+        if (PAIR) {            // the rare fallback items: the partner is evaluated on its own
+          DfBin bm = th.bin[r];
+          bm.baryon = -bm.baryon;
+          double vm = df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, bm, exptab);
+          if (SPECIES_RENORM) vm = (rnm[r] != 0.0) ? vm : 0.0;
+          accm[r] += vm;
+        }
+      }
+    }
+  }
+}
+
 // One instantiation per BRANCH of the reference's per-momentum choice (MomentumSpectra.cpp:932-1040): LINEAR = false takes the
 // items of the modified distribution, LINEAR = true the linear-df fallback items (breakdown cells and the narrow y - eta
 // window); each launch compacts the other kind away together with the u.dsigma <= 0 cells, both add into `partial`.
@@ -121,6 +269,8 @@ __global__ void feqmod_tile_flags_kernel(const double *__restrict__ pack, int64_
 // load / test / branch / reconvergence instructions disappear.
 // PAIR = true: a slot holds a charge-conjugate pair of classes (two class ids per slot, two renorm entries per slot; see
 // spectra_df.cu pair_tables_core and feqmod_accum_pair_u).
+// Modified-branch items are classified like K1's (spectra_df.cu): negligible for the whole block (dropped, bound summed into
+// g.bsum), cold (no range guard) at the front of the tile, hot at the back.
 template <bool LINEAR, bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM, int R, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 2)
 feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk,
@@ -131,31 +281,35 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
   __shared__ double exptab[kExpTableSize];
   load_exp_table(exptab, g.exptab);
   __shared__ int item_cell[kTile];
-  __shared__ int warp_count[kThreads / 32];
+  __shared__ int warp_count[2][kThreads / 32];
+  __shared__ double blk_range[4 * (kThreads / 32)];
+  __shared__ double blk_lohi[5];                        // mT_lo, mT_hi, pT_hi, m2_lo of the block's columns; the drop threshold
+  __shared__ unsigned long long blk_items, blk_dropped;
+  __shared__ double blk_bound;
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int iy = blockIdx.y / g.Nphi, iphi = blockIdx.y - iy * g.Nphi;
+  const int iyr = blockIdx.y / g.Nphi, iphi = blockIdx.y - iyr * g.Nphi, iy = g.y_order[iyr];
   const double yval = g.yv[iy], cphi = g.cosphi[iphi], sphi = g.sinphi[iphi];
 
   // column = (thread group, pT node): the R classes of a group share the thread's pT and one baryon number (spectra_df.cu)
   const int col = blockIdx.x * kThreads + t;
-  const int colc = col < g.ncols ? col : g.ncols - 1;
+  const int colc = g.col_map[col < g.ncols ? col : g.ncols - 1];
   const int grp = colc / g.NpT, ip = colc - grp * g.NpT;
   static_assert(!PAIR || BARYON, "pairs exist only with baryon terms");
   constexpr int S = PAIR ? 2 : 1;                       // class ids (and renorm entries) per slot
-  DfBin bin[R];
+  FeqThread<R, PAIR> th;
+  th.grp = grp;
   double acc[R], accm[PAIR ? R : 1];
-  int jbin[R], jbinm[PAIR ? R : 1], sp[R];
+  int jbin[R], jbinm[PAIR ? R : 1];
   const int cls0 = g.slot_class[S * grp * R];           // slot 0 of a group is never padding
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int cls = g.slot_class[S * (grp * R + r)];
-    sp[r] = cls >= 0 ? cls : cls0;
-    const int jj = sp[r] * g.NpT + ip;
+    const int jj = (cls >= 0 ? cls : cls0) * g.NpT + ip;
     jbin[r] = (col < g.ncols && cls >= 0) ? jj : -1;
     const double mT = g.mT[jj];
-    bin[r].mT = mT; bin[r].mT2 = mT * mT; bin[r].baryon = g.baryon[jj]; bin[r].sign = g.sign[jj];
-    asm volatile("" : "+d"(bin[r].mT2));      // opaque: ptxas otherwise re-multiplies mT^2 (and pT^2) per item to save registers
+    th.bin[r].mT = mT; th.bin[r].mT2 = mT * mT; th.bin[r].baryon = g.baryon[jj]; th.bin[r].sign = g.sign[jj];
+    asm volatile("" : "+d"(th.bin[r].mT2));   // opaque: ptxas otherwise re-multiplies mT^2 (and pT^2) per item to save registers
     acc[r] = 0.0;
     if (PAIR) {
       const int clsm = g.slot_class[S * (grp * R + r) + 1];
@@ -163,13 +317,45 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
       accm[r] = 0.0;
     }
   }
-  const double pT = g.pT[ip];
-  double pT2 = pT * pT;
-  asm volatile("" : "+d"(pT2));
-  int eslot = kMaxBaryon + (BARYON ? (int)bin[0].baryon : 0);
-  asm volatile("" : "+r"(eslot));      // opaque: keeps the slot index in a register (ptxas otherwise re-derives it with F2I per item)
-  int eslotm = 2 * kMaxBaryon - eslot;  // the antibaryon partners of a pair slot
-  asm volatile("" : "+r"(eslotm));
+  th.pT = g.pT[ip];
+  th.pT2 = th.pT * th.pT;
+  asm volatile("" : "+d"(th.pT2));
+  th.eslot = kMaxBaryon + (BARYON ? (int)th.bin[0].baryon : 0);
+  asm volatile("" : "+r"(th.eslot));   // opaque: keeps the slot index in a register (ptxas otherwise re-derives it with F2I per item)
+  th.eslotm = 2 * kMaxBaryon - th.eslot;  // the antibaryon partners of a pair slot
+  asm volatile("" : "+r"(th.eslotm));
+
+  {   // range of the block's columns (shared memory, re-read per tile) and the drop threshold of this block row
+    double lo = th.bin[0].mT, hi = th.bin[0].mT, ph = th.pT, m2 = th.bin[0].mT2 - th.pT2;
+#pragma unroll
+    for (int r = 1; r < R; r++) { lo = fmin(lo, th.bin[r].mT); hi = fmax(hi, th.bin[r].mT); m2 = fmin(m2, th.bin[r].mT2 - th.pT2); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      ph = fmax(ph, __shfl_xor_sync(0xffffffffu, ph, o));
+      m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if (lane == 0) { blk_range[4 * warp] = lo; blk_range[4 * warp + 1] = hi; blk_range[4 * warp + 2] = ph; blk_range[4 * warp + 3] = m2; }
+    __syncthreads();
+    if (t == 0) {
+      for (int w = 1; w < kThreads / 32; w++) {
+        lo = fmin(lo, blk_range[4 * w]); hi = fmax(hi, blk_range[4 * w + 1]); ph = fmax(ph, blk_range[4 * w + 2]); m2 = fmin(m2, blk_range[4 * w + 3]);
+      }
+      blk_lohi[0] = lo; blk_lohi[1] = hi; blk_lohi[2] = ph;
+      blk_lohi[3] = fmax(m2 * (1.0 - 1e-12) - 1e-12, 0.0);      // mT^2 - pT^2 carries the rounding of the two squares
+      double thr = kXeNegligible;
+      if (!LINEAR && g.margin > 0.0) {
+        const double amin = __longlong_as_double((long long)g.amin_bits[iy]);
+        const double amax = __longlong_as_double((long long)g.amin_bits[g.Ny]);
+        thr = fmin(thr, fma(hi, amin, (BARYON ? kMaxBaryon * amax : 0.0) + g.margin));
+      }
+      blk_lohi[4] = thr;
+      blk_items = 0; blk_dropped = 0; blk_bound = 0.0;
+    }
+    __syncthreads();
+  }
+  int flip = 0;
 
   const int64_t chunk_begin = (int64_t)blockIdx.z * cells_per_chunk;
   int64_t chunk_end = chunk_begin + cells_per_chunk;
@@ -188,84 +374,62 @@ feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t n
       }
       valid = (linear == LINEAR);
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
     for (int ie = 0; ie < g.Neta; ie++) {
-      __syncthreads();
-      if (lane == 0) warp_count[warp] = __popc(ballot);
-      __syncthreads();
-      int base = 0, n_items = 0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; w++) {
-        int c = warp_count[w];
-        if (w < warp) base += c;
-        n_items += c;
-      }
+      bool cold = false, hot = valid, dropped = false;
+      double sh = 0.0, ch = 1.0, w = 1.0, dropped_bound = 0.0;
+      auto pk = [&](int k) { return pack[k * stride + cell]; };
       if (valid) {
-        auto pk = [&](int k) { return pack[k * stride + cell]; };
-        double eta, w;
+        double eta;
         if (g.dimension == 3) { eta = pk(DP_ETA); w = 1.0; }
         else { eta = g.etav[ie]; w = g.etaw[ie]; }
-        const int slot = base + __popc(ballot & ((1u << lane) - 1u));
-        if (LINEAR) {
-          double d = yval - eta;
-          items[slot].lin = feqmod_make_linear_item(pk, sinh(d), cosh(d), cphi, sphi, w, g.w_on_dan);
-        } else {
-          double d = yval - pk(FP_ETA_SCALE) * eta;
-          items[slot].mod = feqmod_make_item(pk, sinh(d), cosh(d), cphi, sphi, w, g.w_on_dan, BARYON, !SPECIES_RENORM);
+        const double d = LINEAR ? yval - eta : yval - pk(FP_ETA_SCALE) * eta;
+        sh = sinh(d); ch = cosh(d);
+        if (!LINEAR) {
+          const FeqmodItem item = feqmod_make_item(pk, sh, ch, cphi, sphi, w, g.w_on_dan, BARYON, !SPECIES_RENORM);
+          const volatile double *range = blk_lohi;
+          const double mT_hi = range[1], pT_hi = range[2];
+          const double shift = BARYON ? kMaxBaryon * fabs(item.alphaB_mod) : 0.0;
+          const FeqmodRange x = feqmod_item_range(item, pk(FP_IT2), range[0], mT_hi, pT_hi, range[3], shift);
+          dropped = x.lo >= range[4];                              // NaN: false (kept, and hot)
+          cold = !dropped && x.hi < kXePairShared;
+          hot = !dropped && !cold;
+          if (dropped) dropped_bound = feqmod_item_term_bound(item, x.lo, mT_hi, pT_hi, SPECIES_RENORM ? g.renorm_max[cell] : 1.0, exptab);
         }
+      }
+      const unsigned b_cold = __ballot_sync(0xffffffffu, cold), b_hot = __ballot_sync(0xffffffffu, hot);
+      const unsigned b_dropped = __ballot_sync(0xffffffffu, dropped);
+      if (b_dropped) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dropped_bound += __shfl_xor_sync(0xffffffffu, dropped_bound, o);
+        if (lane == 0) { atomicAdd(&blk_bound, dropped_bound); atomicAdd(&blk_dropped, (unsigned long long)__popc(b_dropped)); }
+      }
+      if (lane == 0) warp_count[flip][warp] = __popc(b_cold) | (__popc(b_hot) << 16);
+      __syncthreads();                       // previous tile fully consumed, counts visible
+      int base_cold = 0, base_hot = 0, n_cold = 0, n_hot = 0;
+#pragma unroll
+      for (int w_ = 0; w_ < kThreads / 32; w_++) {
+        const int c = warp_count[flip][w_], cc = c & 0xffff, ch_ = c >> 16;
+        if (w_ < warp) { base_cold += cc; base_hot += ch_; }
+        n_cold += cc; n_hot += ch_;
+      }
+      if (cold || hot) {
+        const unsigned below = (1u << lane) - 1u;
+        const int slot = cold ? base_cold + __popc(b_cold & below) : kTile - 1 - (base_hot + __popc(b_hot & below));
+        if (LINEAR) items[slot].lin = feqmod_make_linear_item(pk, sh, ch, cphi, sphi, w, g.w_on_dan);
+        else items[slot].mod = feqmod_make_item(pk, sh, ch, cphi, sphi, w, g.w_on_dan, BARYON, !SPECIES_RENORM);
         item_cell[slot] = (int)(cell - 0);   // index inside this pass's pack / renorm arrays
       }
       __syncthreads();
-#pragma unroll 1
-      for (int k = 0; k < n_items; k++) {
-        double rn[R], rnm[PAIR ? R : 1];
-        if (SPECIES_RENORM) {      // L2-resident row; a software prefetch of item k + 1's row measured 11 % slower (profiles/r01_summary.md)
-          const double *row = renorm + (int64_t)item_cell[k] * g.nslots + S * grp * R;
-          if (PAIR) {              // (member b > 0, member b < 0) of every slot side by side
-#pragma unroll
-            for (int r = 0; r < R; r++) { const double2 v = *reinterpret_cast<const double2 *>(row + 2 * r); rn[r] = v.x; rnm[r] = v.y; }
-          } else if (R % 2 == 0) {
-#pragma unroll
-            for (int r = 0; r < R; r += 2) { const double2 v = *reinterpret_cast<const double2 *>(row + r); rn[r] = v.x; rn[r + 1] = v.y; }
-          } else {
-#pragma unroll
-            for (int r = 0; r < R; r++) rn[r] = row[r];
-          }
-        }
-        if (!LINEAR) {
-          const FeqmodItem &it = items[k].mod;        // shared memory: broadcast LDS.128 + one LDS.64 for eb[eslot]
-          const FeqmodShared sh = feqmod_share(it, pT, pT2);
-          const double eb = BARYON ? it.eb[eslot] : 1.0;
-          if (PAIR) {
-            const double ebm = it.eb[eslotm];
-#pragma unroll
-            for (int r = 0; r < R; r++)
-              feqmod_accum_pair_u<OUTFLOW, !SPECIES_RENORM>(acc[r], accm[r], it, sh, eb, ebm, bin[r].mT, bin[r].mT2, bin[r].sign,
-                                                            SPECIES_RENORM ? rn[r] : 1.0, SPECIES_RENORM ? rnm[r] : 1.0, exptab);
-          } else {
-#pragma unroll
-            for (int r = 0; r < R; r++)
-              feqmod_accum_u<BARYON, OUTFLOW, !SPECIES_RENORM>(acc[r], it, sh, eb, bin[r].mT, bin[r].mT2, bin[r].sign, SPECIES_RENORM ? rn[r] : 1.0, exptab);
-          }
-        } else {
-          const DfItem it = items[k].lin;
-          const DfShared sh = df_share<BARYON>(it, pT, pT2);
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            double v = df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, bin[r], exptab);
-            if (SPECIES_RENORM) v = (rn[r] != 0.0) ? v : 0.0;   // NaN renorm: the reference skips the species (:828-832)
-            acc[r] += v;
-            if (PAIR) {            // the rare fallback items: the partner is evaluated on its own
-              DfBin bm = bin[r];
-              bm.baryon = -bm.baryon;
-              double vm = df_eval<2, BARYON, REGULATE, OUTFLOW, true>(it, sh, bm, exptab);
-              if (SPECIES_RENORM) vm = (rnm[r] != 0.0) ? vm : 0.0;
-              accm[r] += vm;
-            }
-          }
-        }
-      }
+      if (!LINEAR) feqmod_item_loop<LINEAR, BARYON, REGULATE, OUTFLOW, SPECIES_RENORM, R, PAIR, false>(items, item_cell, n_cold, th, renorm, g.nslots, acc, accm, exptab);
+      if (n_hot) feqmod_item_loop<LINEAR, BARYON, REGULATE, OUTFLOW, SPECIES_RENORM, R, PAIR, true>(items + (kTile - n_hot), item_cell + (kTile - n_hot), n_hot, th, renorm, g.nslots, acc, accm, exptab);
+      if (t == 0) blk_items += (unsigned)(n_cold + n_hot);
+      flip ^= 1;
     }
+  }
+  __syncthreads();
+  if (t == 0) {
+    atomicAdd(g.items_done, blk_items); atomicAdd(g.items_done + 4, blk_dropped);
+    if (blk_bound != 0.0) atomicAdd(&g.bsum[(int64_t)blockIdx.x * gridDim.y + (iy * g.Nphi + iphi)], blk_bound);
   }
 
   const int64_t pbase = (int64_t)blockIdx.z * total;
@@ -335,13 +499,44 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
     ctx->set_error("species list holds a baryon number outside -2..2 (the reference's PDG readers produce hadrons and the deuteron only)");
     return IS3D_ERR_INVALID;
   }
+  // thread columns in order of their smallest mT, rapidity rows by expected work (as K1, spectra_df.cu)
+  std::vector<int> class_of_all, rep_all;
+  species_classes(ctx, &class_of_all, &rep_all);
+  auto column_order = [&](const std::vector<int> &sl, int ids_per_group) {
+    const int ngroups = (int)(sl.size() / ids_per_group), NpT = ctx->NpT;
+    std::vector<double> key((size_t)ngroups * NpT);
+    for (int gi = 0; gi < ngroups; gi++) {
+      double m_min = 1e300;
+      for (int k = 0; k < ids_per_group; k++) {
+        const int cls = sl[(size_t)gi * ids_per_group + k];
+        if (cls >= 0) m_min = fmin(m_min, fabs(ctx->h_mass[rep_all[cls]]));
+      }
+      for (int ip = 0; ip < NpT; ip++) key[(size_t)gi * NpT + ip] = sqrt(m_min * m_min + ctx->pT[ip] * ctx->pT[ip]);
+    }
+    std::vector<int> order(key.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    return order;
+  };
+  const std::vector<int> order_single = column_order(slots, kBins), order_pair = column_order(pair_slots, 2 * kBins);
+  std::vector<int> yo(ctx->Ny);
+  {
+    double ymid = 0.0;
+    for (int k = 0; k < ctx->Ny; k++) { yo[k] = k; ymid += ctx->yv[k] / ctx->Ny; }
+    std::stable_sort(yo.begin(), yo.end(), [&](int a, int b) { return fabs(ctx->yv[a] - ymid) < fabs(ctx->yv[b] - ymid); });
+  }
   void *d_slots = nullptr;
   std::vector<int> both(slots);
   both.insert(both.end(), pair_slots.begin(), pair_slots.end());
+  both.insert(both.end(), order_single.begin(), order_single.end());
+  both.insert(both.end(), order_pair.begin(), order_pair.end());
+  both.insert(both.end(), yo.begin(), yo.end());
   IS3D_TRY(ctx->get_scratch("k2_slots", (both.size() + 1) * sizeof(int), &d_slots));
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_slots, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // `both` is pageable host memory
   g.slot_class = (const int *)d_slots;
+  g.col_map = (const int *)d_slots + slots.size() + pair_slots.size();
+  g.y_order = g.col_map + order_single.size() + order_pair.size();
   g.NpT = ctx->NpT; g.ns = sb.nclass; g.nslots = (int)slots.size(); g.ncols = ctx->NpT * (int)(slots.size() / kBins);
   const int64_t per_species = (int64_t)ctx->NpT * ctx->Nphi * ctx->Ny;
   const int64_t total_class = (int64_t)sb.nclass * per_species;
@@ -353,6 +548,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   FeqGrid gp = g;                                                // the pair launch: two class ids / renorm entries per slot
   gp.slot_class = (const int *)d_slots + slots.size();
   gp.nslots = (int)pair_slots.size();
+  gp.col_map = g.col_map + order_single.size();
   gp.ncols = ctx->NpT * (int)(pair_slots.size() / (2 * kBins));
   const int nslices = (g.ncols + kThreads - 1) / kThreads, nslices_pair = (gp.ncols + kThreads - 1) / kThreads;
   const int64_t blocks_per_chunk = (int64_t)(nslices + nslices_pair) * ctx->Ny * ctx->Nphi;
@@ -368,20 +564,55 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   int nchunks; int64_t cpc;
   choose_chunks(ctx, stride, blocks_per_chunk, total_class, kTile, &nchunks, &cpc);
 
-  void *pack = nullptr, *partial = nullptr, *counters = nullptr, *renorm = nullptr, *tile_linear = nullptr;
+  void *pack = nullptr, *partial = nullptr, *counters = nullptr, *renorm = nullptr, *tile_linear = nullptr, *prune = nullptr, *rmax = nullptr;
   const size_t ntile_flags = (size_t)((stride + kTile - 1) / kTile);
   IS3D_TRY(ctx->get_scratch("tile_linear", ntile_flags * sizeof(int), &tile_linear));
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)FP_SIZE * stride * sizeof(double), &pack));
   IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total_class * sizeof(double), &partial));
-  IS3D_TRY(ctx->get_scratch("counters", 16 * sizeof(unsigned long long), &counters));
+  IS3D_TRY(ctx->get_scratch("counters", 32 * sizeof(unsigned long long), &counters));
   if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm", (size_t)stride * all_slots * sizeof(double), &renorm));
+  if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm_max", (size_t)stride * sizeof(double), &rmax));
   double *renorm_pair = species_renorm ? (double *)renorm + (size_t)stride * g.nslots : nullptr;
-  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total_class * sizeof(double), ctx->stream));
-  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  // dropping of negligible items (K1's scheme, spectra_df.cu): row scales | bounds of the dropped terms per block row | bin -> row
+  const int NyNphi = ctx->Ny * ctx->Nphi, nrows = nslices + nslices_pair;
+  const size_t amin_bytes = (size_t)(ctx->Ny + 1) * 8, bsum_bytes = (size_t)nrows * NyNphi * 8;
+  std::vector<int> bin_row((size_t)sb.nclass * ctx->NpT, 0);
+  auto fill_rows = [&](const std::vector<int> &sl, int ids_per_group, const std::vector<int> &order, int row0) {
+    for (size_t c = 0; c < order.size(); c++) {
+      const int grp = order[c] / ctx->NpT, ip = order[c] - grp * ctx->NpT;
+      for (int k = 0; k < ids_per_group; k++) {
+        const int cls = sl[(size_t)grp * ids_per_group + k];
+        if (cls >= 0) bin_row[(size_t)cls * ctx->NpT + ip] = row0 + (int)(c / kThreads);
+      }
+    }
+  };
+  fill_rows(slots, kBins, order_single, 0);
+  fill_rows(pair_slots, 2 * kBins, order_pair, nslices);
+  IS3D_TRY(ctx->get_scratch("k2_prune", amin_bytes + bsum_bytes + bin_row.size() * sizeof(int), &prune));
+  unsigned long long *d_amin = (unsigned long long *)prune;
+  double *d_bsum = (double *)((char *)prune + amin_bytes);
+  int *d_bin_row = (int *)((char *)prune + amin_bytes + bsum_bytes);
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_bin_row, bin_row.data(), bin_row.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // pageable host memory
+  // counters: 0..9 as before; 16 / 17 items marched (single, pair launches), 20 / 21 items dropped, 24 bins failing the bound test
+  g.items_done = (unsigned long long *)counters + 16;
+  gp.items_done = (unsigned long long *)counters + 17;
+  g.amin_bits = gp.amin_bits = d_amin;
+  g.bsum = d_bsum; gp.bsum = d_bsum + (size_t)nslices * NyNphi;
+  g.renorm_max = gp.renorm_max = (const double *)rmax;
 
   cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   float ms_total = 0.f;
-  int64_t launches = 0;
+  int64_t launches = 0, prune_reruns = 0;
+  unsigned long long h_counters[32];
+  // attempt 0 drops items below the margin; if the a-posteriori test fails for any bin, attempt 1 repeats the call without it.
+  // The serial-chain parity mode of df_mode 5 keeps its chain state across calls: no second attempt there, so no margin.
+  const double margin0 = (p.df_mode == 5 && p.famod_chain) ? 0.0 : p.negligible_margin;
+  for (int attempt = 0; attempt < 2; attempt++) {
+  g.margin = gp.margin = attempt == 0 ? margin0 : 0.0;
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * total_class * sizeof(double), ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 32 * sizeof(unsigned long long), ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(d_bsum, 0, bsum_bytes, ctx->stream));
   for (int64_t begin = 0; begin < n; begin += macro) {
     int64_t count = n - begin < macro ? n - begin : macro;
     IS3D_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
@@ -405,6 +636,17 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
         IS3D_CUDA_TRY(ctx, cudaGetLastError());
         launches++;
       }
+      feqmod_renorm_max_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>((double *)renorm, g.nslots, renorm_pair, gp.nslots, count, (double *)rmax);
+      IS3D_CUDA_TRY(ctx, cudaGetLastError());
+      launches++;
+    }
+    if (g.margin > 0.0) {
+      IS3D_CUDA_TRY(ctx, cudaMemsetAsync(d_amin, 0x7f, amin_bytes - 8, ctx->stream));
+      IS3D_CUDA_TRY(ctx, cudaMemsetAsync(d_amin + ctx->Ny, 0, 8, ctx->stream));
+      int64_t ab = (count + 255) / 256, ab_max = 8 * (int64_t)ctx->sm_count;
+      feqmod_amin_kernel<<<(unsigned)(ab < ab_max ? ab : ab_max), 256, amin_bytes, ctx->stream>>>((double *)pack, stride, count, ctx->Ny, ctx->d_y, p.dimension, ctx->Neta, ctx->d_eta, d_amin);
+      IS3D_CUDA_TRY(ctx, cudaGetLastError());
+      launches++;
     }
     IS3D_CUDA_TRY(ctx, cudaMemsetAsync(tile_linear, 0, ntile_flags * sizeof(int), ctx->stream));
     feqmod_tile_flags_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>((double *)pack, stride, count, p.dimension, (int *)tile_linear);
@@ -448,13 +690,19 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
     IS3D_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
     ms_total += ms;
   }
+  PruneCheck chk;                                      // without a margin only the < 1e-295 items are dropped: nothing to test
+  if (g.margin > 0.0) chk.bsum = d_bsum;
+  chk.bin_row = d_bin_row; chk.Ny = ctx->Ny; chk.NyNphi = NyNphi; chk.eps = 1e-13;
+  chk.violations = (unsigned long long *)counters + 24;
   reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((double *)partial, nchunks, total_class, per_species,
-                                                                                sb.class_of, ctx->d_deg, total, out_dev, PruneCheck());
+                                                                                sb.class_of, ctx->d_deg, total, out_dev, chk);
   IS3D_CUDA_TRY(ctx, cudaGetLastError());
   launches++;
-  unsigned long long h_counters[16];
   IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_counters[24] == 0 || h_counters[1] != 0 || !(g.margin > 0.0)) break;
+  prune_reruns++;
+  }
   if (stats) {
     stats->cells_total = n;
     stats->cells_skipped = (int64_t)h_counters[0];
@@ -471,6 +719,10 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
     stats->newton_iterations = (int64_t)h_counters[9];
     stats->kernel_ms = ms_total;
     stats->kernel_launches = launches;
+    stats->pair_evals_executed = 2 * (int64_t)h_counters[17] * kThreads * kBins;
+    stats->evals_executed = (int64_t)h_counters[16] * kThreads * kBins + stats->pair_evals_executed;
+    stats->evals_dropped = ((int64_t)h_counters[20] * kBins + 2 * (int64_t)h_counters[21] * kBins) * kThreads;
+    stats->prune_reruns = prune_reruns;
   }
   if (h_counters[1] != 0) {
     ctx->set_error(std::to_string(h_counters[1]) + " cell(s) outside the df coefficient tables (the reference aborts here)");

@@ -284,13 +284,15 @@ IS3D_HD double feqmod_distribution(const FeqmodItem &it, const FeqmodShared &s, 
 // 7 (exp) + 1 + 3 (rcp) + 2 (+ 1 unfolded) = 21 (22); the first version took 28 (29).
 // Accumulates into acc with the final FMA inside the branch (returning the contribution lets the compiler merge the
 // "+=" of the modified and the linear branch behind their join, which costs a DMUL + DADD instead of one DFMA).
-template <bool BARYON, bool OUTFLOW, bool FOLDED>
+// CLAMP = false: the caller knows E'/T' < kXePairShared for every column of its block (feqmod_item_range)
+template <bool BARYON, bool OUTFLOW, bool FOLDED, bool CLAMP = true>
 IS3D_HD void feqmod_accum_u(double &acc, const FeqmodItem &it, const FeqmodShared &s, double eb, double mT, double mT2, double sign,
                             double renorm_sp, const double *__restrict__ exptab)
 {
   const double e2 = fma(mT2, it.h1, fma(mT, s.ph2, s.ph3));
-  const double e = fast_exp(fast_sqrt(e2), exptab);
-  const double f = fast_rcp(BARYON ? fma(e, eb, sign) : e + sign);
+  int spare;
+  const double e = fast_exp_k<CLAMP>(fast_sqrt(e2), exptab, spare);
+  const double f = fast_rcp(BARYON ? fma(e, eb, sign) : e + sign, spare);
   const double pds = fma(mT, it.c1, s.pd);
   const double sum = FOLDED ? fma(pds, f, acc) : fma(pds * f, renorm_sp, acc);
   acc = (OUTFLOW && pds <= 0.0) ? acc : sum;
@@ -299,18 +301,49 @@ IS3D_HD void feqmod_accum_u(double &acc, const FeqmodItem &it, const FeqmodShare
 // Charge-conjugate pair of classes (baryon class + its antibaryon class: same mass and statistics, b -> -b): E' and its
 // exponential do not depend on b, so both members are evaluated from ONE sqrt + exp (16 shared FP64 instructions + 5-6 per
 // member instead of 21-22 each).  eb / ebm = exp(-+|b| alphaB'), rn / rnm = the members' PTM renormalisations.
-template <bool OUTFLOW, bool FOLDED>
+// CLAMP = false (exponents below kXePairShared): also ONE reciprocal, 1 / q = qm / (q qm), 1 / qm = q / (q qm).
+template <bool OUTFLOW, bool FOLDED, bool CLAMP = true>
 IS3D_HD void feqmod_accum_pair_u(double &acc, double &accm, const FeqmodItem &it, const FeqmodShared &s, double eb, double ebm, double mT,
                                  double mT2, double sign, double rn, double rnm, const double *__restrict__ exptab)
 {
   const double e2 = fma(mT2, it.h1, fma(mT, s.ph2, s.ph3));
-  const double e = fast_exp(fast_sqrt(e2), exptab);
-  const double f = fast_rcp(fma(e, eb, sign)), fm = fast_rcp(fma(e, ebm, sign));
+  int spare;
+  const double e = fast_exp_k<CLAMP>(fast_sqrt(e2), exptab, spare);
+  const double q = fma(e, eb, sign), qm = fma(e, ebm, sign);
+  double f, fm;
+  if (CLAMP) { f = fast_rcp(q, spare); fm = fast_rcp(qm, spare); }
+  else { const double Y = fast_rcp(q * qm, spare); f = Y * qm; fm = Y * q; }
   const double pds = fma(mT, it.c1, s.pd);
   const double sum = FOLDED ? fma(pds, f, acc) : fma(pds * f, rn, acc);
   const double summ = FOLDED ? fma(pds, fm, accm) : fma(pds * fm, rnm, accm);
   acc = (OUTFLOW && pds <= 0.0) ? acc : sum;
   accm = (OUTFLOW && pds <= 0.0) ? accm : summ;
+}
+
+// Range of the exponent x = E'/T' - b alphaB' an item can produce on the columns of a block (mT in [mT_lo, mT_hi], pT <= pT_hi,
+// pT <= mT, mass^2 >= m2_lo).  E'^2/T'^2 = |mT g1 + pT g2|^2 + m^2/T'^2 with |g1|^2 = h1 - 1/T'^2, |g2|^2 = h3 + 1/T'^2
+// (feqmod_make_item), hence  (mT_lo max(|g1| - |g2|, 0))^2 + m2_lo/T'^2  <=  E'^2/T'^2  <=  (mT_hi |g1| + pT_hi |g2|)^2 + mT_hi^2/T'^2.
+struct FeqmodRange { double lo, hi; };
+IS3D_HD FeqmodRange feqmod_item_range(const FeqmodItem &it, double iT2, double mT_lo, double mT_hi, double pT_hi, double m2_lo, double shift)
+{
+  const double g1 = sqrt(fmax(it.h1 - iT2, 0.0)), g2 = sqrt(fmax(it.h3 + iT2, 0.0));
+  const double a = mT_lo * fmax(g1 - g2, 0.0), b = fma(mT_hi, g1, pT_hi * g2);
+  FeqmodRange r;
+  r.lo = sqrt(fma(a, a, m2_lo * iT2)) - shift;
+  r.hi = sqrt(fma(b, b, mT_hi * mT_hi * iT2)) + shift;
+  return r;
+}
+
+// Upper bound of |w p.dsigma renorm / (e^x + sign)| over the columns of a block for an item whose exponent is at least x_lo
+// (the chemical-potential shift already taken off); rn_max = the largest per-class renormalisation of the cell (1 when the
+// cell's renormalisation is folded into c1 / d1).  +inf when it cannot be formed.
+IS3D_HD double feqmod_item_term_bound(const FeqmodItem &it, double x_lo, double mT_hi, double pT_hi, double rn_max,
+                                      const double *__restrict__ exptab)
+{
+  const double E = fast_exp(fmin(x_lo, 680.0), exptab);
+  if (!(E > 4.0)) return as_double(0x7ff0000000000000ll);
+  const double bound = 1.001 * (mT_hi * fabs(it.c1) + pT_hi * fabs(it.d1)) * fabs(rn_max) / (E - 1.0);
+  return bound == bound ? bound : as_double(0x7ff0000000000000ll);
 }
 
 #if defined(__CUDACC__)
