@@ -150,8 +150,8 @@ __global__ void polarization_reduce_kernel(const double *__restrict__ partial, i
 
 }  // namespace
 
-void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
-                   int64_t *cells_per_chunk);
+void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int blocks_per_sm,
+                   int *nchunks, int64_t *cells_per_chunk);
 
 // out_dev: five arrays of Ns NpT Nphi Ny doubles each (St, Sx, Sy, Sn, Snorm), index iy + Ny (iphi + Nphi (ipT + NpT is))
 is3d_status run_polarization(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
@@ -206,7 +206,7 @@ is3d_status run_polarization(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   const int nslices = (g.ncols + kThreads - 1) / kThreads;
   if ((int64_t)ctx->Ny * ctx->Nphi > 65535) { ctx->set_error("Ny*Nphi exceeds 65535"); return IS3D_ERR_INVALID; }
   int nchunks; int64_t cpc;
-  choose_chunks(ctx, n, (int64_t)nslices * ctx->Ny * ctx->Nphi, 5 * total_class, kTile, &nchunks, &cpc);
+  choose_chunks(ctx, n, (int64_t)nslices * ctx->Ny * ctx->Nphi, 5 * total_class, kTile, 2, &nchunks, &cpc);
   void *partial = nullptr;
   IS3D_TRY(ctx->get_scratch("pol_partial", (size_t)nchunks * 5 * total_class * sizeof(double), &partial));
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, (size_t)nchunks * 5 * total_class * sizeof(double), ctx->stream));

@@ -28,11 +28,13 @@ namespace {
 
 // launch shape (tunable at build time for the sweeps recorded in profiles/): threads per block, resident blocks per SM
 // the register allocation is bounded for, species per thread
+// 128 x 3 (12 warps per SM, up to 168 registers) measured 8 % faster than 256 x 2 once negligible items are dropped: narrower blocks
+// agree on more droppable items and the momentum loop keeps its constants in registers (profiles/r02_k1_variants_notes.txt)
 #ifndef IS3D_K1_THREADS
-#define IS3D_K1_THREADS 256
+#define IS3D_K1_THREADS 128
 #endif
 #ifndef IS3D_K1_MINBLOCKS
-#define IS3D_K1_MINBLOCKS 2
+#define IS3D_K1_MINBLOCKS 3
 #endif
 #ifndef IS3D_K1_R
 #define IS3D_K1_R 4
@@ -571,10 +573,10 @@ void pick_chunks(int64_t ncells, int64_t blocks_per_chunk, int64_t resident, int
   *cells_per_chunk = best_cpc;
 }
 
-void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
-                   int64_t *cells_per_chunk)
+void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int blocks_per_sm,
+                   int *nchunks, int64_t *cells_per_chunk)
 {
-  const int64_t resident = IS3D_K1_MINBLOCKS * (int64_t)ctx->sm_count;
+  const int64_t resident = blocks_per_sm * (int64_t)ctx->sm_count;
   int64_t max_by_mem = ((int64_t)1 << 30) / (total * 8);
   if (max_by_mem > 65535) max_by_mem = 65535;
   pick_chunks(ncells, blocks_per_chunk, resident, tile, max_by_mem, nchunks, cells_per_chunk);
@@ -664,7 +666,7 @@ is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
   const int64_t macro = pass_cells(4 << 20);          // cells per pass: bounds the pack scratch to ~1 GB
   const int64_t stride = n < macro ? n : macro;
   int nchunks; int64_t cpc;
-  choose_chunks(ctx, stride, blocks_per_chunk, total_class, kTile, &nchunks, &cpc);
+  choose_chunks(ctx, stride, blocks_per_chunk, total_class, kTile, IS3D_K1_MINBLOCKS, &nchunks, &cpc);
 
   void *pack = nullptr, *partial = nullptr, *counters = nullptr, *prune = nullptr;
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)DP_SIZE * stride * sizeof(double), &pack));

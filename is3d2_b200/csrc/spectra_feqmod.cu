@@ -25,8 +25,8 @@ is3d_status build_bin_arrays(is3d_ctx *ctx, SpeciesBins *out);
 bool build_slot_table(const is3d_ctx *ctx, int R, std::vector<int> *slots);
 bool pair_tables_core(const std::vector<int> &rep, const double *mass, const double *sign, const double *baryon, int R, int R_pair,
                       std::vector<int> *singles, std::vector<int> *pairs);
-void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int *nchunks,
-                   int64_t *cells_per_chunk);
+void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk, int64_t total, int tile, int blocks_per_sm,
+                   int *nchunks, int64_t *cells_per_chunk);
 // df_mode 5 per-cell stage (spectra_famod.cu): fills the same pack layout, counters[8] = reconstruction failures,
 // counters[9] = Newton iterations
 is3d_status famod_setup_pass(is3d_ctx *ctx, int64_t begin, int64_t count, double *pack, int64_t stride, unsigned long long *counters,
@@ -34,8 +34,14 @@ is3d_status famod_setup_pass(is3d_ctx *ctx, int64_t begin, int64_t count, double
 
 namespace {
 
-constexpr int kTile = 256;
-constexpr int kThreads = 256;
+#ifndef IS3D_K2_THREADS
+#define IS3D_K2_THREADS 128
+#endif
+#ifndef IS3D_K2_MINBLOCKS
+#define IS3D_K2_MINBLOCKS 4
+#endif
+constexpr int kThreads = IS3D_K2_THREADS;
+constexpr int kTile = kThreads;
 #ifndef IS3D_K2_R
 #define IS3D_K2_R 4
 #endif
@@ -272,7 +278,7 @@ __device__ __forceinline__ void feqmod_item_loop(const ItemSlot *__restrict__ it
 // Modified-branch items are classified like K1's (spectra_df.cu): negligible for the whole block (dropped, bound summed into
 // g.bsum), cold (no range guard) at the front of the tile, hot at the back.
 template <bool LINEAR, bool BARYON, bool REGULATE, bool OUTFLOW, bool SPECIES_RENORM, int R, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, IS3D_K2_MINBLOCKS)
 feqmod_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, int64_t cells_per_chunk,
                       const double *__restrict__ renorm, const int *__restrict__ tile_linear, FeqGrid g,
                       double *__restrict__ partial, int64_t total)
@@ -562,7 +568,7 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   if (macro < kTile) macro = kTile;
   const int64_t stride = n < macro ? n : macro;
   int nchunks; int64_t cpc;
-  choose_chunks(ctx, stride, blocks_per_chunk, total_class, kTile, &nchunks, &cpc);
+  choose_chunks(ctx, stride, blocks_per_chunk, total_class, kTile, IS3D_K2_MINBLOCKS, &nchunks, &cpc);
 
   void *pack = nullptr, *partial = nullptr, *counters = nullptr, *renorm = nullptr, *tile_linear = nullptr, *prune = nullptr, *rmax = nullptr;
   const size_t ntile_flags = (size_t)((stride + kTile - 1) / kTile);
