@@ -34,16 +34,19 @@ is3d_status famod_setup_pass(is3d_ctx *ctx, int64_t begin, int64_t count, double
 
 namespace {
 
+// 128 threads x 5 blocks per SM with R = 3 classes per thread (<= 102 registers, 20 warps per SM): the modified-distribution loop waits
+// on its table / renormalisation loads, so occupancy pays more than amortising the item loads over a fourth class
+// (profiles/r02_k1_variants_notes.txt)
 #ifndef IS3D_K2_THREADS
 #define IS3D_K2_THREADS 128
 #endif
 #ifndef IS3D_K2_MINBLOCKS
-#define IS3D_K2_MINBLOCKS 4
+#define IS3D_K2_MINBLOCKS 5
 #endif
 constexpr int kThreads = IS3D_K2_THREADS;
 constexpr int kTile = kThreads;
 #ifndef IS3D_K2_R
-#define IS3D_K2_R 4
+#define IS3D_K2_R 3
 #endif
 constexpr int kBins = IS3D_K2_R;     // species classes per thread (R)
 
@@ -576,9 +579,10 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   IS3D_TRY(ctx->get_scratch("cell_pack", (size_t)FP_SIZE * stride * sizeof(double), &pack));
   IS3D_TRY(ctx->get_scratch("partial", (size_t)nchunks * total_class * sizeof(double), &partial));
   IS3D_TRY(ctx->get_scratch("counters", 32 * sizeof(unsigned long long), &counters));
-  if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm", (size_t)stride * all_slots * sizeof(double), &renorm));
+  if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm", ((size_t)stride * all_slots + 2) * sizeof(double), &renorm));
   if (species_renorm) IS3D_TRY(ctx->get_scratch("renorm_max", (size_t)stride * sizeof(double), &rmax));
-  double *renorm_pair = species_renorm ? (double *)renorm + (size_t)stride * g.nslots : nullptr;
+  // the pair table starts on a 16-byte boundary (its rows are read as double2; an odd R makes stride * nslots odd)
+  double *renorm_pair = species_renorm ? (double *)renorm + ((size_t)stride * g.nslots + 1) / 2 * 2 : nullptr;
   // dropping of negligible items (K1's scheme, spectra_df.cu): row scales | bounds of the dropped terms per block row | bin -> row
   const int NyNphi = ctx->Ny * ctx->Nphi, nrows = nslices + nslices_pair;
   const size_t amin_bytes = (size_t)(ctx->Ny + 1) * 8, bsum_bytes = (size_t)nrows * NyNphi * 8;
