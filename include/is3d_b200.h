@@ -94,7 +94,8 @@ typedef struct {
                                     the bins' leading terms.  A speed heuristic, not a precision knob: the library sums a
                                     rigorous bound of everything it dropped and compares it with each finished bin (bound <=
                                     1e-13 |bin|); if any bin fails, the call is repeated without the margin
-                                    (is3d_stats.prune_reruns).  <= 0: off.  Default 80 */
+                                    (is3d_stats.prune_reruns).  <= 0: off.  Default 60: with up to 1e7 dropped
+                                    terms per pass against ONE leading term the bound test still passes with a margin of ~50 */
 } is3d_params;
 
 /* Counters the reference prints (MomentumSpectra.cpp:1039-1040, :1674-1679; ParticleSampler.cpp:1133). */

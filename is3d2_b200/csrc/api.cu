@@ -30,7 +30,7 @@ void is3d_default_params(is3d_params *p)
   p->eta_cut = 7.0; p->eta_bins = 140; p->tau_min = 0.0; p->tau_max = 12.0; p->tau_bins = 120;
   p->r_min = 0.0; p->r_max = 12.0; p->r_bins = 60;
   p->device = 0; p->famod_chain = 0; p->dndx_bug_compat = 0; p->polzn_chunk_compat = 0;
-  p->negligible_margin = 80.0;
+  p->negligible_margin = 60.0;
 }
 
 const char *is3d_last_error(const is3d_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
