@@ -171,6 +171,18 @@ inline int64_t pass_cells(int64_t default_cells)
 
 void species_classes(const is3d_ctx *ctx, std::vector<int> *class_of, std::vector<int> *rep);
 
+// Launch order of the spectra kernels (spectra_df.cu; K1 and K2), host side:
+//   column_order   thread columns (group, pT node) = group * NpT + ip in order of their smallest mT, so that the columns of a
+//                  block span a narrow mT range and agree on which (cell, y) items are negligible.  `slots` lists the class ids
+//                  of the thread groups, ids_per_group each (-1 = padding); rep[class] = a species of the class.
+//   rapidity_order rapidity rows in order of |y - mean y| ascending: the rows that drop the fewest items are launched first
+//   fill_bin_rows  bin_row[class * NpT + ip] = row0 + (position of the bin's column in `order`) / threads_per_block: the block
+//                  row group whose dropped-term bounds belong to that bin (PruneCheck)
+std::vector<int> column_order(const is3d_ctx *ctx, const std::vector<int> &slots, int ids_per_group, const std::vector<int> &rep);
+std::vector<int> rapidity_order(const is3d_ctx *ctx);
+void fill_bin_rows(const is3d_ctx *ctx, const std::vector<int> &slots, int ids_per_group, const std::vector<int> &order, int threads_per_block,
+                   int row0, std::vector<int> *bin_row);
+
 // compute paths (one translation unit each)
 is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);        // df_mode 1,2
 is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats);    // df_mode 3,4 and 5 (PTMA)

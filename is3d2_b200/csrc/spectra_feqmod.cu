@@ -511,29 +511,8 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   // thread columns in order of their smallest mT, rapidity rows by expected work (as K1, spectra_df.cu)
   std::vector<int> class_of_all, rep_all;
   species_classes(ctx, &class_of_all, &rep_all);
-  auto column_order = [&](const std::vector<int> &sl, int ids_per_group) {
-    const int ngroups = (int)(sl.size() / ids_per_group), NpT = ctx->NpT;
-    std::vector<double> key((size_t)ngroups * NpT);
-    for (int gi = 0; gi < ngroups; gi++) {
-      double m_min = 1e300;
-      for (int k = 0; k < ids_per_group; k++) {
-        const int cls = sl[(size_t)gi * ids_per_group + k];
-        if (cls >= 0) m_min = fmin(m_min, fabs(ctx->h_mass[rep_all[cls]]));
-      }
-      for (int ip = 0; ip < NpT; ip++) key[(size_t)gi * NpT + ip] = sqrt(m_min * m_min + ctx->pT[ip] * ctx->pT[ip]);
-    }
-    std::vector<int> order(key.size());
-    for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
-    return order;
-  };
-  const std::vector<int> order_single = column_order(slots, kBins), order_pair = column_order(pair_slots, 2 * kBins);
-  std::vector<int> yo(ctx->Ny);
-  {
-    double ymid = 0.0;
-    for (int k = 0; k < ctx->Ny; k++) { yo[k] = k; ymid += ctx->yv[k] / ctx->Ny; }
-    std::stable_sort(yo.begin(), yo.end(), [&](int a, int b) { return fabs(ctx->yv[a] - ymid) < fabs(ctx->yv[b] - ymid); });
-  }
+  const std::vector<int> order_single = column_order(ctx, slots, kBins, rep_all), order_pair = column_order(ctx, pair_slots, 2 * kBins, rep_all);
+  const std::vector<int> yo = rapidity_order(ctx);
   void *d_slots = nullptr;
   std::vector<int> both(slots);
   both.insert(both.end(), pair_slots.begin(), pair_slots.end());
@@ -587,17 +566,8 @@ is3d_status run_spectra_feqmod(is3d_ctx *ctx, double *out_dev, is3d_stats *stats
   const int NyNphi = ctx->Ny * ctx->Nphi, nrows = nslices + nslices_pair;
   const size_t amin_bytes = (size_t)(ctx->Ny + 1) * 8, bsum_bytes = (size_t)nrows * NyNphi * 8;
   std::vector<int> bin_row((size_t)sb.nclass * ctx->NpT, 0);
-  auto fill_rows = [&](const std::vector<int> &sl, int ids_per_group, const std::vector<int> &order, int row0) {
-    for (size_t c = 0; c < order.size(); c++) {
-      const int grp = order[c] / ctx->NpT, ip = order[c] - grp * ctx->NpT;
-      for (int k = 0; k < ids_per_group; k++) {
-        const int cls = sl[(size_t)grp * ids_per_group + k];
-        if (cls >= 0) bin_row[(size_t)cls * ctx->NpT + ip] = row0 + (int)(c / kThreads);
-      }
-    }
-  };
-  fill_rows(slots, kBins, order_single, 0);
-  fill_rows(pair_slots, 2 * kBins, order_pair, nslices);
+  fill_bin_rows(ctx, slots, kBins, order_single, kThreads, 0, &bin_row);
+  fill_bin_rows(ctx, pair_slots, 2 * kBins, order_pair, kThreads, nslices, &bin_row);
   IS3D_TRY(ctx->get_scratch("k2_prune", amin_bytes + bsum_bytes + bin_row.size() * sizeof(int), &prune));
   unsigned long long *d_amin = (unsigned long long *)prune;
   double *d_bsum = (double *)((char *)prune + amin_bytes);

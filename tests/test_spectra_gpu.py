@@ -84,13 +84,13 @@ def test_launch_realistic_surface_matches_reference(libs, tmp_path, name):
     print(f"{name}: max rel err {worst:.3e}, {st.cells_skipped} of {st.cells_total} cells skipped")
 
 
-def test_negligible_margin_is_checked_a_posteriori(libs, tmp_path, monkeypatch):
-    """is3d_params.negligible_margin (K1): items far above a block row's smallest exponent are dropped before the momentum
-    loop, the bounds of what was dropped are compared with every finished bin, and the call is repeated without the margin
-    when a bin fails.  (a) default margin on the benchmark surface's first cells: fewer evaluations executed, no rerun, same
-    spectra as with the margin off to 1e-13; (b) an absurd margin that drops leading terms: the test fails, the rerun
-    delivers the margin-off result bit for bit."""
-    name = "bench_m2_smash_baryon_2304cells"
+@pytest.mark.parametrize("name", list(cases.BIG_SPECTRA_CASES))
+def test_negligible_margin_is_checked_a_posteriori(libs, tmp_path, monkeypatch, name):
+    """is3d_params.negligible_margin (K1: df_mode 2 case, K2: df_mode 3 case): items far above a block row's smallest exponent
+    are dropped before the momentum loop, the bounds of what was dropped are compared with every finished bin, and the call is
+    repeated without the margin when a bin fails.  (a) default margin on the benchmark surface's first cells: fewer
+    evaluations executed, no rerun, same spectra as with the margin off to 1e-13; (b) an absurd margin that drops leading
+    terms: the test fails, the rerun delivers the margin-off result bit for bit."""
     case = cases.BIG_SPECTRA_CASES[name]
     surf, ref = harness.load_golden(name)
     out = {}
