@@ -107,7 +107,7 @@ struct DndxThread {
 // acc[2 r + 1] = its partner -- the order of the flat slot list)
 template <int N>
 __device__ __forceinline__ void dndx_flush(double (&acc)[N], double factor, double (*red)[kDndxThreads], const DndxGrid &g,
-                                           const DndxCellBins &bins)
+                                           const DndxCellBins &bins, double dropped_bound = 0.0)
 {
   constexpr int R = N;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -125,7 +125,13 @@ __device__ __forceinline__ void dndx_flush(double (&acc)[N], double factor, doub
     for (int i = lane; i < g.NpT; i += 32) v += red[r][gl * g.NpT + i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) dndx_scatter(g, cls, bins, kCooperFryePrefactor * v);
+    if (lane == 0) {
+      // a-posteriori test of the cell's dropped quadrature points: their summed bound (times the summed |pT weights|, without the
+      // Cooper-Frye prefactor, like v) must vanish against the (cell, class) scalar itself; run_dndx repeats the call without the
+      // margin otherwise
+      if (dropped_bound != 0.0 && !(dropped_bound <= 1e-13 * fabs(v) + 1e-280)) atomicAdd(g.prune_counters, 1ull);
+      dndx_scatter(g, cls, bins, kCooperFryePrefactor * v);
+    }
   }
 }
 
@@ -167,6 +173,42 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
   for (int r = 0; r < N; r++) acc[r] = 0.0;
   const DndxTiling tl(g);
   int buf = 0;
+
+  // Dropping of negligible quadrature points (the scheme of the spectra kernels, spectra_df.cu, per CELL): every exponent
+  // x = xE - b alpha_B the block's columns (all pT nodes of its thread groups) can form for a point lies in [mT_lo (aT - max(bT, 0))
+  // - 2|alpha_B|, mT_hi aT + pT_hi max(-bT, 0) + 2|alpha_B|].  A point whose lower bound is >= 680, or exceeds the smallest upper bound
+  // among the cell's points of this tile by more than g.margin, is not marched over; its term bound (df_item_term_bound) is summed
+  // per cell and tested against every (cell, class) scalar in dndx_flush.
+  __shared__ double blk_range[3 * (kDndxThreads / 32)];
+  __shared__ double blk_lohi[4];                         // mT_lo, mT_hi, pT_hi of the block's columns, sum of the pT weights
+  __shared__ unsigned long long cell_xmin[kDndxMaxCells];
+  __shared__ double cell_bound[kDndxMaxCells];
+  __shared__ int cell_cnt[kDndxMaxCells];
+  __shared__ unsigned long long blk_dropped;
+  {
+    const int lane = t & 31, warp = t >> 5;
+    double lo = th.mT[0], hi = th.mT[0], ph = th.pT;
+#pragma unroll
+    for (int r = 1; r < R; r++) { lo = fmin(lo, th.mT[r]); hi = fmax(hi, th.mT[r]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      ph = fmax(ph, __shfl_xor_sync(0xffffffffu, ph, o));
+    }
+    if (lane == 0) { blk_range[3 * warp] = lo; blk_range[3 * warp + 1] = hi; blk_range[3 * warp + 2] = ph; }
+    __syncthreads();
+    if (t == 0) {
+      for (int w = 1; w < kDndxThreads / 32; w++) { lo = fmin(lo, blk_range[3 * w]); hi = fmax(hi, blk_range[3 * w + 1]); ph = fmax(ph, blk_range[3 * w + 2]); }
+      double wsum = 0.0;
+      for (int i = 0; i < g.NpT; i++) wsum += fabs(g.pTw[i]);
+      blk_lohi[0] = lo; blk_lohi[1] = hi; blk_lohi[2] = ph; blk_lohi[3] = wsum;
+      blk_dropped = 0;
+    }
+    __syncthreads();
+  }
+  constexpr unsigned long long kHuge = 0x7f7f7f7f7f7f7f7full;
+
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
   int64_t c1 = c0 + cells_per_block;
   if (c1 > ncells) c1 = ncells;
@@ -174,52 +216,80 @@ dndx_df_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncells, 
     for (int p0 = 0; p0 < tl.npoints; p0 += kDndxTile) {
       const int np_tile = min(kDndxTile, tl.npoints - p0);
       __syncthreads();                                   // previous tile consumed (first pass: exp table loaded)
-      {
-        const int cl = t / np_tile, j = p0 + t - cl * np_tile;
-        const int64_t cell = cell0 + cl;
-        if (cl < tl.cpt && cell < c1) {
-          const bool ok = pack[DP_VALID * stride + cell] != 0.0;
-          if (j == p0) {
-            cell_ok[cl] = ok ? 1 : 0;
-            const int64_t gc = surf_begin + cell;
-            if (ok) cell_bins[cl] = dndx_cell_bins(g, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc]);
-          }
-          if (ok) {
-            auto pk = [&](int k) { return pack[k * stride + cell]; };
-            const DndxPoint pt = dndx_point(g, pk, j);
-            const double d = pt.yval - pt.eta;
-            items[t] = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sinh(d), cosh(d), pt.cphi, pt.sphi, pt.w);
-          }
+      if (t < kDndxMaxCells) { cell_cnt[t] = 0; cell_xmin[t] = kHuge; if (p0 == 0) cell_bound[t] = 0.0; }
+      __syncthreads();
+      const int cl = t / np_tile, j = p0 + t - cl * np_tile;
+      const int64_t cell = cell0 + cl;
+      bool mine = false;
+      double sh = 0.0, ch = 1.0, xe_lo = 0.0, xe_hi = 0.0, cphi = 1.0, sphi = 0.0, w = 1.0;
+      auto pk = [&](int k) { return pack[k * stride + cell]; };
+      if (cl < tl.cpt && cell < c1) {
+        const bool ok = pack[DP_VALID * stride + cell] != 0.0;
+        if (j == p0) {
+          cell_ok[cl] = ok ? 1 : 0;
+          const int64_t gc = surf_begin + cell;
+          if (ok) cell_bins[cl] = dndx_cell_bins(g, surf.col[0][gc], surf.col[1][gc], surf.col[2][gc]);
+        }
+        if (ok) {
+          mine = true;
+          const DndxPoint pt = dndx_point(g, pk, j);
+          const double d = pt.yval - pt.eta;
+          sh = sinh(d); ch = cosh(d); cphi = pt.cphi; sphi = pt.sphi; w = pt.w;
+          // aT, bT exactly as df_make_item_u forms them
+          const double aT = ch * pk(DP_UTT) - sh * pk(DP_TUNT), bT = cphi * pk(DP_UXT) + sphi * pk(DP_UYT);
+          const double shift = BARYON ? kMaxBaryon * fabs(pk(DP_ALPHAB)) : 0.0;
+          const volatile double *range = blk_lohi;
+          xe_lo = range[0] * (aT - fmax(bT, 0.0)) - shift;
+          xe_hi = fma(range[1], aT, range[2] * fmax(-bT, 0.0)) + shift;
+          if (xe_hi > 0.0) atomicMin(&cell_xmin[cl], (unsigned long long)__double_as_longlong(xe_hi));
+        }
+      }
+      __syncthreads();
+      if (mine) {
+        double thr = 680.0;
+        if (g.margin > 0.0) thr = fmin(thr, __longlong_as_double((long long)cell_xmin[cl]) + g.margin);
+        const DfItemU item = df_make_item_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(pk, sh, ch, cphi, sphi, w);
+        if (xe_lo >= thr) {                               // NaN: kept
+          const volatile double *range = blk_lohi;
+          const double shift = BARYON ? kMaxBaryon * fabs(pk(DP_ALPHAB)) : 0.0;
+          atomicAdd(&cell_bound[cl], range[3] * df_item_term_bound<MODE, BARYON, REGULATE>(item, xe_lo + shift, range[1], range[2], exptab));
+        } else {
+          items[cl * np_tile + atomicAdd(&cell_cnt[cl], 1)] = item;
         }
       }
       __syncthreads();
       const bool last_tile = p0 + kDndxTile >= tl.npoints;
-      for (int cl = 0; cl < tl.cpt && cell0 + cl < c1; cl++) {
-        if (!cell_ok[cl]) continue;
+      if (t == 0)
+        for (int c = 0; c < tl.cpt && cell0 + c < c1; c++) if (cell_ok[c]) blk_dropped += (unsigned)(np_tile - cell_cnt[c]);
+      for (int c = 0; c < tl.cpt && cell0 + c < c1; c++) {
+        if (!cell_ok[c]) continue;
         if (th.active) {
+          const int n_kept = cell_cnt[c];
 #pragma unroll 1
-          for (int k = 0; k < np_tile; k++) {
-            const DfItemU &it = items[cl * np_tile + k];
-            const DfSharedU sh = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, tu);
+          for (int k = 0; k < n_kept; k++) {
+            const DfItemU &it = items[c * np_tile + k];
+            const DfSharedU shd = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, tu);
             if (!PAIR) {
 #pragma unroll
-              for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, th.mT[r], th.mT2[r], th.sgn[r], exptab);
+              for (int r = 0; r < R; r++) acc[r] += df_eval_u<MODE, BARYON, REGULATE, OUTFLOW>(it, shd, th.mT[r], th.mT2[r], th.sgn[r], exptab);
             } else {
               const DfSharedU shm = df_share_u<MODE, BARYON, (MODE == 2 && !REGULATE)>(it, tum);
 #pragma unroll
               for (int r = 0; r < R; r++) {           // one x_E and one exponential per pair (spectra_df.cuh)
-                const double xE = df_eval_u_x(it, sh, th.mT[r]);
+                const double xE = df_eval_u_x(it, shd, th.mT[r]);
                 const double e = fast_exp<false>(xE, exptab);
-                acc[2 * r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, sh, th.mT[r], th.mT2[r], th.sgn[r], xE, e);
+                acc[2 * r] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, shd, th.mT[r], th.mT2[r], th.sgn[r], xE, e);
                 acc[2 * r + 1] += df_eval_u_tail<MODE, BARYON, REGULATE, OUTFLOW>(it, shm, th.mT[r], th.mT2[r], th.sgn[r], xE, e);
               }
             }
           }
         }
-        if (last_tile) { dndx_flush<N>(acc, th.wpT, red[buf], g, cell_bins[cl]); buf ^= 1; }
+        if (last_tile) { dndx_flush<N>(acc, th.wpT, red[buf], g, cell_bins[c], cell_bound[c]); buf ^= 1; }
       }
     }
   }
+  __syncthreads();
+  if (t == 0 && blk_dropped) atomicAdd(g.prune_counters + 1, blk_dropped);
 }
 
 union DndxItemSlot {
@@ -481,8 +551,17 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   const int64_t resident = 2LL * ctx->sm_count;      // two 256-thread blocks per SM (launch bounds)
   cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;             // owned by the context: nothing to release on an error path
   float ms_total = 0.f;
-  int64_t launches = 0;
+  int64_t launches = 0, prune_reruns = 0;
   const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0, baryon = p.include_baryon != 0;
+  unsigned long long h_counters[16];
+  // df_mode 1, 2: attempt 0 drops quadrature points below the margin; if the bound test fails for any (cell, class) scalar,
+  // attempt 1 repeats the call without it (counters[4] = failures, [5] = points dropped)
+  for (int attempt = 0; attempt < 2; attempt++) {
+  g.margin = gp.margin = (attempt == 0 && !feqmod) ? p.negligible_margin : 0.0;
+  g.prune_counters = (unsigned long long *)counters + 4;
+  gp.prune_counters = (unsigned long long *)counters + 4;
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(class_hist, 0, class_bins * sizeof(double), ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
   for (int64_t begin = 0; begin < n; begin += macro) {
     int64_t count = n - begin < macro ? n - begin : macro;
     // whole waves of equal blocks (spectra_df.cu pick_chunks); a chunk = whole cells, in multiples of the cells of one tile
@@ -533,6 +612,11 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
     ms_total += ms;
     launches += 2;
   }
+  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
+  IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_counters[4] == 0 || h_counters[1] != 0 || !(g.margin > 0.0)) break;
+  prune_reruns++;
+  }
   // species s = degeneracy_s x its class (SpacetimeDistribution.cpp:408: dN_dy_cell carries the degeneracy)
   const int bins3[3] = {p.tau_bins, p.r_bins, p.phip_bins};
   const double *src3[3] = {g.hist_tau, g.hist_r, g.hist_phi};
@@ -543,8 +627,6 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
     IS3D_CUDA_TRY(ctx, cudaGetLastError());
   }
   launches += 3;
-  unsigned long long h_counters[16];
-  IS3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
   IS3D_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (stats) {
     stats->cells_total = n;
@@ -554,6 +636,9 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
     stats->cells_pl_negative = (int64_t)h_counters[3];
     stats->kernel_ms = ms_total;
     stats->kernel_launches = launches;
+    // quadrature points not marched over x the block's thread slots (kDndxThreads columns x 4 classes per thread in both launches)
+    stats->evals_dropped = (int64_t)h_counters[5] * kDndxThreads * kDndxR;
+    stats->prune_reruns = prune_reruns;
   }
   if (h_counters[1] != 0) {
     ctx->set_error(std::to_string(h_counters[1]) + " cell(s) outside the df coefficient tables (the reference aborts here)");

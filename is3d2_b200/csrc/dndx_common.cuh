@@ -42,6 +42,9 @@ struct DndxGrid {
   int tau_bins, r_bins, phi_bins;
   double *hist_tau, *hist_r, *hist_phi;               // [class][bins]
   const double *exptab;                               // 2^(m/1024), global memory
+  // dropping of negligible quadrature points (df_mode 1, 2; dndx_df_kernel)
+  double margin;                                      // is3d_params.negligible_margin; <= 0: only the x >= 680 points are dropped
+  unsigned long long *prune_counters;                 // [0] += (cell, class) scalars failing the bound test, [1] += points dropped
 };
 
 // histogram bins of a cell (SpacetimeDistribution.cpp:413-440), -1 = outside the histogram; evaluated once per cell
