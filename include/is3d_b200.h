@@ -88,7 +88,7 @@ typedef struct {
   int polzn_chunk_compat;        /* 0 (default) = every cell reads its own thermal vorticity; 1 = the reference's index INSIDE
                                     its 10 000-cell chunk (Polarization.cpp:125-130 use wtx_fo[icell], not [icell_glb]):
                                     identical for surfaces of up to 10 000 cells, unsharded surfaces only */
-  double negligible_margin;      /* continuous spectra, df_mode 1 / 2: (cell, y, phi) items whose every exponent (u.p - b mu_B)/T
+  double negligible_margin;      /* continuous spectra (all df modes) and dN/dX: (cell, y, phi) items whose every exponent (u.p - b mu_B)/T
                                     in a block of momentum columns exceeds the block row's smallest possible exponent by more
                                     than this margin are dropped before the momentum loop -- their terms are below e^-margin of
                                     the bins' leading terms.  A speed heuristic, not a precision knob: the library sums a

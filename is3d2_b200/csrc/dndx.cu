@@ -107,7 +107,7 @@ struct DndxThread {
 // acc[2 r + 1] = its partner -- the order of the flat slot list)
 template <int N>
 __device__ __forceinline__ void dndx_flush(double (&acc)[N], double factor, double (*red)[kDndxThreads], const DndxGrid &g,
-                                           const DndxCellBins &bins, double dropped_bound = 0.0)
+                                           const DndxCellBins &bins, double dropped_bound = 0.0, const double *rn_row = nullptr)
 {
   constexpr int R = N;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -129,7 +129,9 @@ __device__ __forceinline__ void dndx_flush(double (&acc)[N], double factor, doub
       // a-posteriori test of the cell's dropped quadrature points: their summed bound (times the summed |pT weights|, without the
       // Cooper-Frye prefactor, like v) must vanish against the (cell, class) scalar itself; run_dndx repeats the call without the
       // margin otherwise
-      if (dropped_bound != 0.0 && !(dropped_bound <= 1e-13 * fabs(v) + 1e-280)) atomicAdd(g.prune_counters, 1ull);
+      // (rn_row: the PTM renormalisation of this class multiplies every term of the cell, the dropped ones included)
+      const double bound = dropped_bound * (rn_row ? fabs(rn_row[gl * R + r]) : 1.0);
+      if (bound != 0.0 && !(bound <= 1e-13 * fabs(v) + 1e-280)) atomicAdd(g.prune_counters, 1ull);
       dndx_scatter(g, cls, bins, kCooperFryePrefactor * v);
     }
   }
@@ -334,6 +336,42 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
   const DndxTiling tl(g);
   const int nsum = g.gpb * N;
   int buf = 0;
+
+  // dropping of negligible quadrature points as in dndx_df_kernel, for cells whose points all take the modified distribution
+  // (feqmod_item_range / feqmod_item_term_bound, spectra_feqmod.cuh); cells that may hold linear-df items keep every point
+  __shared__ double blk_range[4 * (kDndxThreads / 32)];
+  __shared__ double blk_lohi[5];                         // mT_lo, mT_hi, pT_hi, m2_lo of the block's columns, sum of the pT weights
+  __shared__ unsigned long long cell_xmin[kDndxMaxCells];
+  __shared__ double cell_bound[kDndxMaxCells];
+  __shared__ int cell_cnt[kDndxMaxCells];
+  __shared__ unsigned long long blk_dropped;
+  {
+    const int lane = t & 31, warp = t >> 5;
+    double lo = th.mT[0], hi = th.mT[0], ph = th.pT, m2 = th.mT2[0] - th.pT2;
+#pragma unroll
+    for (int r = 1; r < R; r++) { lo = fmin(lo, th.mT[r]); hi = fmax(hi, th.mT[r]); m2 = fmin(m2, th.mT2[r] - th.pT2); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      ph = fmax(ph, __shfl_xor_sync(0xffffffffu, ph, o));
+      m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if (lane == 0) { blk_range[4 * warp] = lo; blk_range[4 * warp + 1] = hi; blk_range[4 * warp + 2] = ph; blk_range[4 * warp + 3] = m2; }
+    __syncthreads();
+    if (t == 0) {
+      for (int w = 1; w < kDndxThreads / 32; w++) {
+        lo = fmin(lo, blk_range[4 * w]); hi = fmax(hi, blk_range[4 * w + 1]); ph = fmax(ph, blk_range[4 * w + 2]); m2 = fmin(m2, blk_range[4 * w + 3]);
+      }
+      double wsum = 0.0;
+      for (int i = 0; i < g.NpT; i++) wsum += fabs(g.pTw[i]);
+      blk_lohi[0] = lo; blk_lohi[1] = hi; blk_lohi[2] = ph; blk_lohi[3] = fmax(m2 * (1.0 - 1e-12) - 1e-12, 0.0); blk_lohi[4] = wsum;
+      blk_dropped = 0;
+    }
+    __syncthreads();
+  }
+  constexpr unsigned long long kHuge = 0x7f7f7f7f7f7f7f7full;
+
   const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
   int64_t c1 = c0 + cells_per_block;
   if (c1 > ncells) c1 = ncells;
@@ -341,9 +379,15 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
     for (int p0 = 0; p0 < tl.npoints; p0 += kDndxTile) {
       const int np_tile = min(kDndxTile, tl.npoints - p0);
       __syncthreads();                                   // previous tile consumed
+      if (t < kDndxMaxCells) { cell_cnt[t] = 0; cell_xmin[t] = kHuge; if (p0 == 0) cell_bound[t] = 0.0; }
+      __syncthreads();
+      bool mine_mod = false;                             // this thread holds a modified-distribution point of a valid cell
+      double sh_ = 0.0, ch_ = 1.0, x_lo = 0.0;
+      const int cl_ = t / np_tile, j_ = p0 + t - cl_ * np_tile;
+      const int64_t cell_ = cell0 + cl_;
       {
-        const int cl = t / np_tile, j = p0 + t - cl * np_tile;
-        const int64_t cell = cell0 + cl;
+        const int cl = cl_, j = j_;
+        const int64_t cell = cell_;
         if (cl < tl.cpt && cell < c1) {
           const bool ok = pack[DP_VALID * stride + cell] != 0.0;
           auto pk = [&](int k) { return pack[k * stride + cell]; };
@@ -360,9 +404,18 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
             if (g.dimension == 3 && !linear && detA < 0.01 && fabs(pt.yval - pt.eta) < detA) linear = true;
             const double d = linear ? (pt.yval - pt.eta) : (pt.yval - pk(FP_ETA_SCALE) * pt.eta);
             const double sh = sinh(d), ch = cosh(d);
-            if (linear) items[t].lin = feqmod_make_linear_item(pk, sh, ch, pt.cphi, pt.sphi, pt.w, true);
-            else items[t].mod = feqmod_make_item(pk, sh, ch, pt.cphi, pt.sphi, pt.w, true, BARYON, !SPECIES_RENORM);
             item_linear[t] = linear ? 1 : 0;
+            if (linear) {
+              items[t].lin = feqmod_make_linear_item(pk, sh, ch, pt.cphi, pt.sphi, pt.w, true);   // its cell keeps every point in place
+            } else {
+              mine_mod = true; sh_ = sh; ch_ = ch;
+              const FeqmodItem item = feqmod_make_item(pk, sh, ch, pt.cphi, pt.sphi, pt.w, true, BARYON, !SPECIES_RENORM);
+              const volatile double *range = blk_lohi;
+              const FeqmodRange x = feqmod_item_range(item, pk(FP_IT2), range[0], range[1], range[2], range[3],
+                                                      BARYON ? kMaxBaryon * fabs(item.alphaB_mod) : 0.0);
+              x_lo = x.lo;
+              if (x.hi > 0.0) atomicMin(&cell_xmin[cl], (unsigned long long)__double_as_longlong(x.hi));
+            }
           }
         }
         // PTM with bulk: n_linear / n_mod of every (cell, class slot) of this tile, once per cell (first tile of the cell)
@@ -384,7 +437,29 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
         }
       }
       __syncthreads();
+      if (mine_mod) {
+        const int cl = cl_;
+        const int64_t cell = cell_;
+        auto pk = [&](int k) { return pack[k * stride + cell]; };
+        const DndxPoint pt = dndx_point(g, pk, j_);
+        const FeqmodItem item = feqmod_make_item(pk, sh_, ch_, pt.cphi, pt.sphi, pt.w, true, BARYON, !SPECIES_RENORM);
+        if (cell_lin[cl]) {
+          items[t].mod = item;                           // a cell with linear-df points: every point stays in place
+        } else {
+          double thr = 680.0;
+          if (g.margin > 0.0) thr = fmin(thr, __longlong_as_double((long long)cell_xmin[cl]) + g.margin);
+          if (x_lo >= thr) {                             // NaN: kept
+            const volatile double *range = blk_lohi;
+            atomicAdd(&cell_bound[cl], range[4] * feqmod_item_term_bound(item, x_lo, range[1], range[2], 1.0, exptab));
+          } else {
+            items[cl * np_tile + atomicAdd(&cell_cnt[cl], 1)].mod = item;
+          }
+        }
+      }
+      __syncthreads();
       const bool last_tile = p0 + kDndxTile >= tl.npoints;
+      if (t == 0)
+        for (int c = 0; c < tl.cpt && cell0 + c < c1; c++) if (cell_ok[c] && !cell_lin[c]) blk_dropped += (unsigned)(np_tile - cell_cnt[c]);
       for (int cl = 0; cl < tl.cpt && cell0 + cl < c1; cl++) {
         if (!cell_ok[cl]) continue;
         double rn[N];                                    // index = accumulator index (pairs: 2 r = the b > 0 member, 2 r + 1 = its partner)
@@ -407,9 +482,10 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
           }
         };
         if (th.active && !cell_lin[cl]) {
-          // common case, no linear-df item in this cell: lean loop, the R evaluations interleave
+          // common case, no linear-df item in this cell: lean loop over the points that were kept, the R evaluations interleave
+          const int n_kept = cell_cnt[cl];
 #pragma unroll 1
-          for (int k = 0; k < np_tile; k++) modified(items[cl * np_tile + k].mod);
+          for (int k = 0; k < n_kept; k++) modified(items[cl * np_tile + k].mod);
         } else if (th.active) {
 #pragma unroll 1
           for (int k = 0; k < np_tile; k++) {
@@ -438,12 +514,14 @@ dndx_feqmod_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncel
             for (int r = 0; r < N; r++) acc[r] = (rn[r] != 0.0) ? acc[r] : 0.0;
           }
           const double factor = (SPECIES_RENORM || cell_rn[cl] != 0.0) ? th.wpT : 0.0;
-          dndx_flush<N>(acc, factor, red[buf], g, cell_bins[cl]);
+          dndx_flush<N>(acc, factor, red[buf], g, cell_bins[cl], cell_lin[cl] ? 0.0 : cell_bound[cl], SPECIES_RENORM ? class_rn[cl] : nullptr);
           buf ^= 1;
         }
       }
     }
   }
+  __syncthreads();
+  if (t == 0 && blk_dropped) atomicAdd(g.prune_counters + 1, blk_dropped);
 }
 
 __global__ void dndx_expand_kernel(const double *__restrict__ class_hist, const int *__restrict__ class_of, const double *__restrict__ deg,
@@ -554,10 +632,10 @@ is3d_status run_dndx(is3d_ctx *ctx, double *tau_dev, double *r_dev, double *phi_
   int64_t launches = 0, prune_reruns = 0;
   const bool reg = p.regulate_deltaf != 0, outflow = p.outflow != 0, baryon = p.include_baryon != 0;
   unsigned long long h_counters[16];
-  // df_mode 1, 2: attempt 0 drops quadrature points below the margin; if the bound test fails for any (cell, class) scalar,
+  // attempt 0 drops quadrature points below the margin; if the bound test fails for any (cell, class) scalar,
   // attempt 1 repeats the call without it (counters[4] = failures, [5] = points dropped)
   for (int attempt = 0; attempt < 2; attempt++) {
-  g.margin = gp.margin = (attempt == 0 && !feqmod) ? p.negligible_margin : 0.0;
+  g.margin = gp.margin = attempt == 0 ? p.negligible_margin : 0.0;
   g.prune_counters = (unsigned long long *)counters + 4;
   gp.prune_counters = (unsigned long long *)counters + 4;
   IS3D_CUDA_TRY(ctx, cudaMemsetAsync(class_hist, 0, class_bins * sizeof(double), ctx->stream));

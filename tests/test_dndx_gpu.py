@@ -34,6 +34,33 @@ def test_dndx_matches_reference(libs, tmp_path, name):
         harness.assert_hist_close(got[k], ref[k], what=f"{name}/{k}")
 
 
+@pytest.mark.parametrize("name", ["dndx_bench_m2_smash_baryon_512cells", "dndx_s3d_m3"])
+def test_dndx_negligible_margin_is_checked_a_posteriori(libs, tmp_path, monkeypatch, name):
+    """is3d_params.negligible_margin in K4 (df and feqmod kernels): quadrature points far above the cell's smallest exponent are
+    not marched over; their summed bound is tested against every (cell, class) scalar.  Default margin == margin off to 1e-12 per
+    bin (FP64 atomics: no bitwise claim), points are dropped, no rerun; an absurd margin trips the test and the rerun delivers
+    the margin-off histograms."""
+    case = cases.DNDX_CASES.get(name) or cases.BIG_DNDX_CASES[name]
+    surf, ref = harness.load_golden_dndx(name)
+    ns = ref["tau"].shape[0]
+    out = {}
+    for tag, margin in (("off", "0"), ("default", None), ("absurd", "1e-3")):
+        if margin is None:
+            monkeypatch.delenv("IS3D_NEGLIGIBLE_MARGIN", raising=False)
+        else:
+            monkeypatch.setenv("IS3D_NEGLIGIBLE_MARGIN", margin)
+        with harness.open_session(str(tmp_path / tag), case, surf) as h:
+            out[tag] = _device_hists(h, ns, case["params"])
+    (off, st_off), (dflt, st_d), (absurd, st_a) = out["off"], out["default"], out["absurd"]
+    assert st_off.prune_reruns == 0 and st_d.prune_reruns == 0 and st_a.prune_reruns == 1
+    assert st_d.evals_dropped > st_off.evals_dropped
+    for k in ("tau", "r", "phi"):
+        scale = np.abs(off[k]).max()
+        assert np.abs(dflt[k] - off[k]).max() <= 1e-12 * scale
+        assert np.abs(absurd[k] - off[k]).max() <= 1e-12 * scale
+    print(f"{name}: thread-slot evaluations dropped {st_d.evals_dropped:.3g} (margin off {st_off.evals_dropped:.3g})")
+
+
 def test_dndx_host_bug_compat_and_files(libs, tmp_path):
     """Through the host layer (EmissionFunctionArray::calculate_spectra, operation 0): the bug-compatible mode
     reproduces the reference's files; the default writes clean per-species histograms whose total over bins equals

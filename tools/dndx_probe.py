@@ -32,4 +32,5 @@ for rep in range(3):
     dt = time.perf_counter() - t0
     assert rc == 0, h.lib.is3d_last_error(h.ctx)
     evals = float(cells) * ns * npT * nphi * ny
-    print(f"dN/dX df_mode {mode}, {cells} cells, {ns} species: {dt * 1e3:.1f} ms (kernels {st.kernel_ms:.1f} ms) -> {evals / dt:.3e} evals/s")
+    print(f"dN/dX df_mode {mode}, {cells} cells, {ns} species: {dt * 1e3:.1f} ms (kernels {st.kernel_ms:.1f} ms) -> {evals / dt:.3e} evals/s"
+          f" (reruns {st.prune_reruns}, thread-slot evaluations dropped {st.evals_dropped:.3g})")
