@@ -25,6 +25,7 @@ enum DfPackIdx {
   DP_PITT, DP_T2PINN, DP_TPITN, DP_PITX, DP_PITY, DP_TPIXN, DP_TPIYN, DP_PIXX, DP_PIYY, DP_PIXY,
   DP_K0, DP_K1, DP_K2, DP_G0, DP_G1, DP_VT, DP_TVN, DP_VX, DP_VY,
   DP_EBP, DP_EBM,              // exp(-alpha_B), exp(+alpha_B): the chemical-potential factor of the uniform-baryon path
+  DP_EPETA, DP_EMETA,          // exp(+eta), exp(-eta): sinh(y - eta) = (e^y e^-eta - e^-y e^eta) / 2 without a libm call per (cell, y)
   DP_SIZE
 };
 
@@ -85,6 +86,7 @@ IS3D_HD int df_setup_cell(const Cell &c, const DfTables &tb, const DfFlags &fl, 
   pack[DP_UTT] = ut * invT;  pack[DP_TUNT] = tau * un * invT;  pack[DP_UXT] = ux * invT;  pack[DP_UYT] = uy * invT;
   pack[DP_ALPHAB] = alphaB;
   pack[DP_EBP] = exp(-alphaB); pack[DP_EBM] = exp(alphaB);
+  pack[DP_EPETA] = exp(c.eta); pack[DP_EMETA] = exp(-c.eta);
   pack[DP_DAT] = c.dat; pack[DP_DAX] = c.dax; pack[DP_DAY] = c.day; pack[DP_DANT] = c.dan / tau;
   pack[DP_PITT] = sc * pi.tt; pack[DP_T2PINN] = sc * tau2 * pi.nn; pack[DP_TPITN] = sc * tau * pi.tn;
   pack[DP_PITX] = sc * pi.tx; pack[DP_PITY] = sc * pi.ty; pack[DP_TPIXN] = sc * tau * pi.xn; pack[DP_TPIYN] = sc * tau * pi.yn;
