@@ -327,6 +327,15 @@ int         is3d_species_groups(int ns, const double *mass, const double *sign, 
  * is3d_species_groups. */
 int         is3d_species_pairs(int ns, const double *mass, const double *sign, const double *baryon, int slots_per_group,
                                int *single_slots, int single_capacity, int *pair_slots, int pair_capacity, int *n_single, int *n_pair);
+/* Host-only helper: the launch order of the spectra kernels' thread columns (no GPU).  slots[nslots] = the class ids of the thread
+ * groups, ids_per_group each (-1 = padding), as is3d_species_groups / is3d_species_pairs return them; class_mass[nclass].  A column is
+ * (group, pT node) = group * NpT + ip.  order[ngroups * NpT] receives the columns sorted by their smallest transverse mass
+ * sqrt(min mass of the group^2 + pT^2) (stable), so that the threads_per_block columns of a block span a narrow mT range and agree
+ * on which (cell, y) items are negligible (is3d_params.negligible_margin); bin_row[nclass * NpT] the block row
+ * (position in order / threads_per_block) whose dropped-term bounds belong to bin (class, ip), -1 for classes not in slots.
+ * Returns the number of columns, -1 for bad arguments. */
+int         is3d_launch_order(int nslots, const int *slots, int ids_per_group, int nclass, const double *class_mass, int NpT,
+                              const double *pT, int threads_per_block, int *order, int *bin_row);
 /* device -> host copy on the context's stream (e.g. to inspect the list of is3d_sample_device without a CUDA runtime of one's own) */
 is3d_status is3d_copy_from_device(is3d_ctx *ctx, void *host, const void *device, size_t bytes);
 /* the CUDA stream all kernels of this context are launched on (as a void* cudaStream_t) */

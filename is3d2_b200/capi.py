@@ -66,7 +66,7 @@ ABI_SYMBOLS = ["is3d_default_params", "is3d_create", "is3d_destroy", "is3d_last_
                "is3d_set_surface_device", "is3d_spectra_size", "is3d_spectra", "is3d_spectra_device", "is3d_dndx",
                "is3d_dndx_device", "is3d_total_yield", "is3d_cell_yields", "is3d_sample", "is3d_free_particles", "is3d_sample_compact", "is3d_sample_device", "is3d_expand_particles",
                "is3d_sample_histograms", "is3d_set_vorticity", "is3d_polarization", "is3d_measure_fp64_peak", "is3d_probe_math", "is3d_probe_aniso_math",
-               "is3d_species_groups", "is3d_species_pairs", "is3d_stream", "is3d_copy_from_device",
+               "is3d_species_groups", "is3d_species_pairs", "is3d_launch_order", "is3d_stream", "is3d_copy_from_device",
                "is3d_comm_unique_id", "is3d_comm_attach", "is3d_comm_detach", "is3d_comm_size", "is3d_comm_collectives",
                "is3d_comm_last_error", "is3d_group_create", "is3d_group_destroy", "is3d_group_size", "is3d_group_ctx",
                "is3d_group_last_error", "is3d_group_cell_block", "is3d_group_set_surface", "is3d_group_set_vorticity",

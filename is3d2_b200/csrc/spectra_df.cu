@@ -585,22 +585,42 @@ void choose_chunks(const is3d_ctx *ctx, int64_t ncells, int64_t blocks_per_chunk
   pick_chunks(ncells, blocks_per_chunk, resident, tile, max_by_mem, nchunks, cells_per_chunk);
 }
 
-std::vector<int> column_order(const is3d_ctx *ctx, const std::vector<int> &slots, int ids_per_group, const std::vector<int> &rep)
+// ctx-free cores of the launch order (also behind the host-only helper is3d_launch_order)
+std::vector<int> column_order_core(const std::vector<int> &slots, int ids_per_group, const double *class_mass, int NpT, const double *pT)
 {
-  const int ngroups = (int)(slots.size() / ids_per_group), NpT = ctx->NpT;
+  const int ngroups = (int)(slots.size() / ids_per_group);
   std::vector<double> key((size_t)ngroups * NpT);
   for (int gi = 0; gi < ngroups; gi++) {
     double m_min = 1e300;
     for (int k = 0; k < ids_per_group; k++) {
       const int cls = slots[(size_t)gi * ids_per_group + k];
-      if (cls >= 0) m_min = fmin(m_min, fabs(ctx->h_mass[rep[cls]]));
+      if (cls >= 0) m_min = fmin(m_min, fabs(class_mass[cls]));
     }
-    for (int ip = 0; ip < NpT; ip++) key[(size_t)gi * NpT + ip] = sqrt(m_min * m_min + ctx->pT[ip] * ctx->pT[ip]);
+    for (int ip = 0; ip < NpT; ip++) key[(size_t)gi * NpT + ip] = sqrt(m_min * m_min + pT[ip] * pT[ip]);
   }
   std::vector<int> order(key.size());
   for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
   return order;
+}
+
+void fill_bin_rows_core(const std::vector<int> &slots, int ids_per_group, const std::vector<int> &order, int NpT, int threads_per_block,
+                        int row0, std::vector<int> *bin_row)
+{
+  for (size_t c = 0; c < order.size(); c++) {
+    const int grp = order[c] / NpT, ip = order[c] - grp * NpT;
+    for (int k = 0; k < ids_per_group; k++) {
+      const int cls = slots[(size_t)grp * ids_per_group + k];
+      if (cls >= 0) (*bin_row)[(size_t)cls * NpT + ip] = row0 + (int)(c / threads_per_block);
+    }
+  }
+}
+
+std::vector<int> column_order(const is3d_ctx *ctx, const std::vector<int> &slots, int ids_per_group, const std::vector<int> &rep)
+{
+  std::vector<double> class_mass(rep.size());
+  for (size_t c = 0; c < rep.size(); c++) class_mass[c] = ctx->h_mass[rep[c]];
+  return column_order_core(slots, ids_per_group, class_mass.data(), ctx->NpT, ctx->pT.data());
 }
 
 std::vector<int> rapidity_order(const is3d_ctx *ctx)
@@ -615,13 +635,7 @@ std::vector<int> rapidity_order(const is3d_ctx *ctx)
 void fill_bin_rows(const is3d_ctx *ctx, const std::vector<int> &slots, int ids_per_group, const std::vector<int> &order, int threads_per_block,
                    int row0, std::vector<int> *bin_row)
 {
-  for (size_t c = 0; c < order.size(); c++) {
-    const int grp = order[c] / ctx->NpT, ip = order[c] - grp * ctx->NpT;
-    for (int k = 0; k < ids_per_group; k++) {
-      const int cls = slots[(size_t)grp * ids_per_group + k];
-      if (cls >= 0) (*bin_row)[(size_t)cls * ctx->NpT + ip] = row0 + (int)(c / threads_per_block);
-    }
-  }
+  fill_bin_rows_core(slots, ids_per_group, order, ctx->NpT, threads_per_block, row0, bin_row);
 }
 
 is3d_status run_spectra_df(is3d_ctx *ctx, double *out_dev, is3d_stats *stats)
@@ -816,6 +830,21 @@ extern "C" int is3d_species_pairs(int ns, const double *mass, const double *sign
   *n_single = (int)singles.size();
   *n_pair = (int)pairs.size();
   return (int)rep.size();
+}
+
+extern "C" int is3d_launch_order(int nslots, const int *slots, int ids_per_group, int nclass, const double *class_mass, int NpT, const double *pT,
+                                 int threads_per_block, int *order, int *bin_row)
+{
+  if (nslots <= 0 || !slots || ids_per_group <= 0 || nslots % ids_per_group || nclass <= 0 || !class_mass || NpT <= 0 || !pT ||
+      threads_per_block <= 0 || !order || !bin_row) return -1;
+  std::vector<int> sl(slots, slots + nslots);
+  for (int c : sl) if (c >= nclass) return -1;
+  const std::vector<int> ord = is3d::column_order_core(sl, ids_per_group, class_mass, NpT, pT);
+  std::vector<int> rows((size_t)nclass * NpT, -1);
+  is3d::fill_bin_rows_core(sl, ids_per_group, ord, NpT, threads_per_block, 0, &rows);
+  for (size_t k = 0; k < ord.size(); k++) order[k] = ord[k];
+  for (size_t k = 0; k < rows.size(); k++) bin_row[k] = rows[k];
+  return (int)ord.size();
 }
 
 extern "C" int is3d_species_groups(int ns, const double *mass, const double *sign, const double *baryon, int include_baryon,

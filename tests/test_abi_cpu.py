@@ -165,3 +165,52 @@ def test_charge_conjugate_pairs_layout(libs):
                                  np.ascontiguousarray(baryon[keep]).ctypes.data_as(C.c_void_p), R, singles.ctypes.data_as(C.c_void_p), len(singles),
                                  pairs.ctypes.data_as(C.c_void_p), len(pairs), C.byref(n1), C.byref(n2))
     assert nc2 > 0 and n2.value == 0
+
+
+def test_launch_order_sorts_columns_by_transverse_mass(libs):
+    """Host logic behind the dropping of negligible items (is3d_launch_order): the thread columns (group, pT node) are a permutation
+    sorted by sqrt(min mass of the group^2 + pT^2); every block of 128 consecutive columns therefore starts at a transverse mass that
+    is >= the start of the block before it; bin_row maps every (class, pT) bin to the block that holds its column."""
+    import numpy as np
+    lib, _ = libs
+    mass, sign, baryon = _smash_species()
+    ns, R, T = len(mass), 4, 128
+    class_of = np.zeros(ns, dtype=np.int32)
+    slots = np.full(4 * ns, -7, dtype=np.int32)
+    nclass = C.c_int()
+    lib.is3d_species_groups.restype = C.c_int
+    n = lib.is3d_species_groups(ns, mass.ctypes.data_as(C.c_void_p), sign.ctypes.data_as(C.c_void_p), baryon.ctypes.data_as(C.c_void_p),
+                                0, R, class_of.ctypes.data_as(C.c_void_p), slots.ctypes.data_as(C.c_void_p), len(slots), C.byref(nclass))
+    assert n > 0
+    sl = np.ascontiguousarray(slots[:n])
+    nc = nclass.value
+    class_mass = np.zeros(nc)
+    for s_ in range(ns):
+        class_mass[class_of[s_]] = mass[s_]
+    pT = np.loadtxt(os.path.join(REPO, "data", "tables", "momentum", "pT_table.dat"))[:, 0].copy()
+    NpT, ngroups = len(pT), n // R
+    order = np.full(ngroups * NpT, -1, dtype=np.int32)
+    bin_row = np.full(nc * NpT, -5, dtype=np.int32)
+    lib.is3d_launch_order.restype = C.c_int
+    ncol = lib.is3d_launch_order(n, sl.ctypes.data_as(C.c_void_p), R, nc, class_mass.ctypes.data_as(C.c_void_p), NpT,
+                                 pT.ctypes.data_as(C.c_void_p), T, order.ctypes.data_as(C.c_void_p), bin_row.ctypes.data_as(C.c_void_p))
+    assert ncol == ngroups * NpT
+    assert sorted(order) == list(range(ncol))                      # a permutation of the columns
+    grp, ip = order // NpT, order % NpT
+    m_min = np.array([min(class_mass[c] for c in sl[g * R:(g + 1) * R] if c >= 0) for g in range(ngroups)])
+    key = np.sqrt(m_min[grp] ** 2 + pT[ip] ** 2)
+    assert np.all(np.diff(key) >= 0.0)                             # sorted by the column's smallest mT
+    starts = key[::T]
+    assert np.all(np.diff(starts) >= 0.0) and starts[0] == pytest.approx(class_mass.min(), abs=pT.min() + 1e-12)
+    # the widest block spans far less than the whole table: that is what lets a block agree on negligible cells
+    widths = [key[b * T:(b + 1) * T].max() / key[b * T:(b + 1) * T].min() for b in range((ncol + T - 1) // T) if b > 0]
+    assert max(widths) < 1.5
+    # every bin of a class that sits in a slot belongs to the block of its column
+    pos = {int(c): k for k, c in enumerate(order)}
+    for g in range(ngroups):
+        for c in sl[g * R:(g + 1) * R]:
+            if c >= 0:
+                for i in (0, NpT // 2, NpT - 1):
+                    assert bin_row[c * NpT + i] == pos[g * NpT + i] // T
+    assert lib.is3d_launch_order(n + 1, sl.ctypes.data_as(C.c_void_p), R, nc, class_mass.ctypes.data_as(C.c_void_p), NpT,
+                                 pT.ctypes.data_as(C.c_void_p), T, order.ctypes.data_as(C.c_void_p), bin_row.ctypes.data_as(C.c_void_p)) == -1
