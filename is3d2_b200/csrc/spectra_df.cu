@@ -276,7 +276,7 @@ df_spectra_kernel(const double *__restrict__ pack, int64_t stride, int64_t ncell
       // The cell's item for this block's (y, phi), classified by the range of xE over the block's columns:
       //   negligible: every xE >= kXeNegligible -- the Bose/Fermi factor of every evaluation is below 1e-295 (where fast_exp's range
       //               guard saturates and the reference's exp overflows to feq = 0): the item is dropped like a u.dsigma <= 0 cell;
-      //   cold:       every xE < kXeCold: the loop without the range guard;      hot: the rest, the guarded loop.
+      //   cold:       every xE < kXeCold (pair launch: every exponent < kXePairShared): the loop without the range guard;  hot: the rest.
       // Cold items fill the tile from the front, hot items from the back.
       bool cold = false, hot = false, dropped = false;
       double sh = 0.0, ch = 1.0, w = 1.0, dropped_bound = 0.0;
